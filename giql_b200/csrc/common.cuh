@@ -1,0 +1,241 @@
+// common.cuh — context, error plumbing and device helpers shared by every kernel file.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdarg.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <string>
+#include <vector>
+
+#include "../../include/giqlb.h"
+
+#define GIQLB_SM_COUNT_DEFAULT 148
+#define GIQLB_MAX_STRAND_CODES 256
+
+struct giqlb_ctx {
+    int device = 0;
+    int sm_count = GIQLB_SM_COUNT_DEFAULT;
+    cudaStream_t stream = nullptr;
+    bool own_stream = false;
+    char err[512] = {0};
+    // small pinned host + device scratch for scalars returned to the host
+    int64_t* h_scalars = nullptr;   // pinned, 64 slots
+    int64_t* d_scalars = nullptr;   // device, 64 slots
+    int* d_err = nullptr;           // device int[4]: sticky kernel-side error flags ([0] look-back spin limit)
+    giqlb_stats_t stats = {};
+    int32_t launches_this_call = 0;
+};
+
+struct giqlb_dict {
+    std::vector<std::string> names;   // sorted bytewise; code = position
+};
+
+// Genome linearisation.  For chromosome code c with observed canonical coordinate range [lo, hi]:
+//   g(pos) = base[c] + 1 + (pos - lo[c])            (uint32)
+//   base[c+1] = base[c] + (hi - lo) + 3 + pad       (one guard cell either side, `pad` extra)
+// so coordinates of different chromosomes never compare equal or interleave, and a probe coordinate
+// clamped to [lo-1, hi+1] stays inside its own chromosome's cell range.
+struct giqlb_layout {
+    int32_t n_codes = 0;
+    int64_t pad = 0;
+    int64_t* d_lohi = nullptr;   // [2*n_codes]: lo (init INT64_MAX) then hi (init INT64_MIN)
+    uint32_t* d_base = nullptr;  // [n_codes + 1] linear base per code; base[n_codes] = total extent
+    int32_t* d_lo32 = nullptr;   // [n_codes] lo as int32 (valid after finalize; 0 for empty chromosomes)
+    int32_t* d_hi32 = nullptr;   // [n_codes] hi (lo - 1 for empty chromosomes)
+    bool finalized = false;
+    uint64_t total_extent = 0;   // host copy after finalize
+    int key_bits = 32;
+    std::vector<int64_t> h_lo, h_hi;
+    std::vector<uint32_t> h_base;
+};
+
+struct giqlb_index {
+    int64_t n = 0;
+    uint32_t* gs = nullptr;      // linearised start, ascending (within each strand block when grouped)
+    uint32_t* ge = nullptr;      // linearised end of the same row
+    int32_t* rid = nullptr;      // input row id
+    uint8_t* strand = nullptr;   // strand code of the same row (nullptr when table has none)
+    uint32_t* pmax = nullptr;    // lazily built inclusive running max of ge (restarts per strand block)
+    uint32_t* ge_sorted = nullptr;   // lazily built: ge ascending (per strand block) ...
+    int32_t* pos_by_end = nullptr;   // ... and the sorted position (into gs/ge/rid) of each
+    int64_t n_degenerate = 0;    // rows with end <= start (host copy, filled at build)
+    int64_t n_negative = 0;      // rows with end <  start
+    bool tie_by_end = false;     // equal starts are ordered by end
+    bool grouped_by_strand = false;
+    int32_t n_blocks = 1;                                   // strand blocks (1 when not grouped)
+    int64_t block_off[GIQLB_MAX_STRAND_CODES + 1] = {0};    // host: row offsets of each strand-code block
+    int64_t* d_block_off = nullptr;                         // device copy [257]
+    const giqlb_layout* layout = nullptr;
+};
+
+struct giqlb_joinplan {
+    const giqlb_index* L = nullptr;
+    const giqlb_index* R = nullptr;
+    int64_t tiles_a = 0, tiles_b = 0;
+    unsigned long long* tile_off = nullptr;   // [tiles_a + tiles_b + 1] exclusive offsets (device)
+    int64_t total = 0;
+    bool general = false;                     // degenerate-interval path (literal predicate scan)
+};
+
+// ---- host-side helpers ---------------------------------------------------------------------------
+static inline int giqlb_fail(giqlb_ctx* ctx, int code, const char* fmt, ...) __attribute__((format(printf, 3, 4)));
+static inline int giqlb_fail(giqlb_ctx* ctx, int code, const char* fmt, ...) {
+    if (ctx) {
+        va_list ap;
+        va_start(ap, fmt);
+        vsnprintf(ctx->err, sizeof(ctx->err), fmt, ap);
+        va_end(ap);
+    }
+    return code;
+}
+
+#define CUDA_TRY(ctx, expr)                                                                          \
+    do {                                                                                             \
+        cudaError_t _e = (expr);                                                                     \
+        if (_e != cudaSuccess)                                                                       \
+            return giqlb_fail((ctx), _e == cudaErrorMemoryAllocation ? GIQLB_ERR_NOMEM : GIQLB_ERR_CUDA, \
+                              "%s:%d %s -> %s", __FILE__, __LINE__, #expr, cudaGetErrorString(_e));  \
+    } while (0)
+
+#define GIQLB_TRY(expr)              \
+    do {                             \
+        int _s = (expr);             \
+        if (_s != GIQLB_OK) return _s; \
+    } while (0)
+
+#define LAUNCH_CHECK(ctx)                 \
+    do {                                  \
+        (ctx)->launches_this_call++;      \
+        (ctx)->stats.kernels_total++;     \
+        CUDA_TRY((ctx), cudaGetLastError()); \
+    } while (0)
+
+template <typename T>
+static inline int dev_alloc(giqlb_ctx* ctx, T** p, size_t count) {
+    *p = nullptr;
+    size_t bytes = (count ? count : 1) * sizeof(T);
+    bytes = (bytes + 255) & ~(size_t)255;   // keep vector loads of a padded tail in bounds
+    CUDA_TRY(ctx, cudaMallocAsync((void**)p, bytes, ctx->stream));
+    return GIQLB_OK;
+}
+template <typename T>
+static inline void dev_free(giqlb_ctx* ctx, T* p) {
+    if (p) cudaFreeAsync((void*)p, ctx->stream);
+}
+
+static inline int64_t ceil_div(int64_t a, int64_t b) { return (a + b - 1) / b; }
+
+static inline void begin_call(giqlb_ctx* ctx) {
+    ctx->launches_this_call = 0;
+    ctx->err[0] = 0;
+}
+static inline int end_call(giqlb_ctx* ctx, int status = GIQLB_OK) {
+    ctx->stats.kernels_launched = ctx->launches_this_call;
+    return status;
+}
+
+// copies n int64 scalars from device to the pinned host scratch and waits for them
+static inline int fetch_scalars(giqlb_ctx* ctx, const void* d_src, int n_words) {
+    CUDA_TRY(ctx, cudaMemcpyAsync(ctx->h_scalars, d_src, (size_t)n_words * 8, cudaMemcpyDeviceToHost, ctx->stream));
+    CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    return GIQLB_OK;
+}
+
+// ---- device helpers ------------------------------------------------------------------------------
+#ifdef __CUDACC__
+
+#define FULL_MASK 0xffffffffu
+
+__device__ __forceinline__ uint32_t lane_id() { return threadIdx.x & 31; }
+__device__ __forceinline__ uint32_t warp_id() { return threadIdx.x >> 5; }
+
+// first index in [lo, hi) with a[idx] >= x (a ascending)
+template <typename T, typename I>
+__device__ __forceinline__ I lower_bound_dev(const T* __restrict__ a, I lo, I hi, T x) {
+    while (lo < hi) {
+        I mid = lo + ((hi - lo) >> 1);
+        if (a[mid] < x) lo = mid + 1; else hi = mid;
+    }
+    return lo;
+}
+// first index in [lo, hi) with a[idx] > x
+template <typename T, typename I>
+__device__ __forceinline__ I upper_bound_dev(const T* __restrict__ a, I lo, I hi, T x) {
+    while (lo < hi) {
+        I mid = lo + ((hi - lo) >> 1);
+        if (a[mid] <= x) lo = mid + 1; else hi = mid;
+    }
+    return lo;
+}
+
+// streaming (read-once) loads / stores that do not pollute L1
+__device__ __forceinline__ uint32_t ld_stream_u32(const uint32_t* p) {
+    uint32_t v;
+    asm volatile("ld.global.nc.L1::no_allocate.u32 %0, [%1];" : "=r"(v) : "l"(p));
+    return v;
+}
+__device__ __forceinline__ uint4 ld_stream_u32x4(const uint4* p) {
+    uint4 v;
+    asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];"
+                 : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p));
+    return v;
+}
+__device__ __forceinline__ void st_stream_u32(uint32_t* p, uint32_t v) {
+    asm volatile("st.global.L1::no_allocate.u32 [%0], %1;" ::"l"(p), "r"(v));
+}
+__device__ __forceinline__ void st_stream_u32x4(uint4* p, uint4 v) {
+    asm volatile("st.global.L1::no_allocate.v4.u32 [%0], {%1,%2,%3,%4};" ::"l"(p), "r"(v.x), "r"(v.y),
+                 "r"(v.z), "r"(v.w));
+}
+
+template <typename T>
+__device__ __forceinline__ T warp_incl_scan_add(T v) {
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        T o = __shfl_up_sync(FULL_MASK, v, d);
+        if (lane_id() >= (uint32_t)d) v += o;
+    }
+    return v;
+}
+template <typename T>
+__device__ __forceinline__ T warp_reduce_add(T v) {
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) v += __shfl_xor_sync(FULL_MASK, v, d);
+    return v;
+}
+
+// Block-wide exclusive scan of one value per thread.  `scratch` holds >= (blockDim/32 + 1) T's.
+// Returns the exclusive prefix; *total receives the block sum.  Contains two __syncthreads(); callers
+// must __syncthreads() before reusing `scratch`.
+template <typename T>
+__device__ __forceinline__ T block_excl_scan_add(T v, T* scratch, T* total) {
+    T incl = warp_incl_scan_add(v);
+    const uint32_t w = warp_id(), l = lane_id(), nw = (blockDim.x + 31) >> 5;
+    if (l == 31) scratch[w] = incl;
+    __syncthreads();
+    if (w == 0) {
+        T x = l < nw ? scratch[l] : T(0);
+        T xi = warp_incl_scan_add(x);
+        if (l < nw) scratch[l] = xi - x;
+        if (l == nw - 1) scratch[nw] = xi;
+    }
+    __syncthreads();
+    T res = scratch[w] + incl - v;
+    *total = scratch[nw];
+    return res;
+}
+
+#endif  // __CUDACC__
+
+// ---- internal cross-file entry points ---------------------------------------------------------------
+int giqlb_radix_sort_pairs_u32(giqlb_ctx* ctx, uint32_t* keys_a, uint32_t* vals_a, uint32_t* keys_b,
+                               uint32_t* vals_b, int64_t n, int begin_bit, int end_bit, int identity_vals,
+                               int* result_in_b);
+int giqlb_excl_scan_u64(giqlb_ctx* ctx, const unsigned long long* in, unsigned long long* out, int64_t n,
+                        unsigned long long* total_dev);
+int giqlb_incl_scan_max_u32(giqlb_ctx* ctx, const uint32_t* in, uint32_t* out, int64_t n,
+                            const int64_t* d_block_off, int n_blocks);
+int giqlb_index_ensure_pmax(giqlb_ctx* ctx, giqlb_index* ix);
+int giqlb_index_ensure_end_sorted(giqlb_ctx* ctx, giqlb_index* ix);

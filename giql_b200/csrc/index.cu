@@ -1,0 +1,542 @@
+// index.cu — genome layout (linearisation of (chrom code, position) into one uint32 coordinate) and the
+// sorted interval index built with the LSD radix sort.
+//
+// Replaces, for the SQL emitted at src/giql/expanders/intersects_duckdb.py:1283-1299 (reference), the
+// per-chromosome `WHERE chrom = 'c'` re-scans and per-chromosome sorts of DuckDB's IE_JOIN: folding the
+// chromosome into the coordinate makes ONE sort and ONE search space serve all chromosomes, while the
+// guard cells between chromosomes keep `l.chrom = r.chrom` (src/giql/expanders/intersects.py:151) exact.
+// Canonical offsets (src/giql/canonical.py:16-52) are applied here as integers.
+#include "common.cuh"
+#include "scan.cuh"
+
+namespace {
+
+constexpr int LY_THREADS = 256;
+constexpr int LY_SMEM_CODES = 2048;
+
+// per-chromosome min/max of canonical coordinates.  Shared-memory staging with a read-before-atomic
+// test: after the first few rows almost no row improves a bound, so almost no atomics are issued.
+__global__ void __launch_bounds__(LY_THREADS)
+layout_observe_kernel(const int32_t* __restrict__ code, const int32_t* __restrict__ start,
+                      const int32_t* __restrict__ end, int64_t n, int32_t n_codes, int32_t sadj, int32_t eadj,
+                      long long* __restrict__ lohi, int* __restrict__ err) {
+    __shared__ int32_t s_lo[LY_SMEM_CODES];
+    __shared__ int32_t s_hi[LY_SMEM_CODES];
+    const bool use_smem = n_codes <= LY_SMEM_CODES;
+    if (use_smem) {
+        for (int i = threadIdx.x; i < n_codes; i += LY_THREADS) {
+            s_lo[i] = INT32_MAX;
+            s_hi[i] = INT32_MIN;
+        }
+        __syncthreads();
+    }
+    bool bad = false;
+    for (int64_t i = (int64_t)blockIdx.x * LY_THREADS + threadIdx.x; i < n; i += (int64_t)gridDim.x * LY_THREADS) {
+        int32_t c = code[i];
+        long long s = (long long)start[i] + sadj, e = (long long)end[i] + eadj;
+        long long lo = s < e ? s : e, hi = s < e ? e : s;
+        if (c < 0 || c >= n_codes || lo < -(1ll << 30) || hi > (1ll << 31) - 4) {
+            bad = true;
+            continue;
+        }
+        if (use_smem) {
+            if ((int32_t)lo < s_lo[c]) atomicMin(&s_lo[c], (int32_t)lo);
+            if ((int32_t)hi > s_hi[c]) atomicMax(&s_hi[c], (int32_t)hi);
+        } else {
+            if (lo < *(volatile long long*)&lohi[c]) atomicMin(&lohi[c], lo);
+            if (hi > *(volatile long long*)&lohi[n_codes + c]) atomicMax(&lohi[n_codes + c], hi);
+        }
+    }
+    if (bad) err[1] = 1;
+    if (use_smem) {
+        __syncthreads();
+        for (int i = threadIdx.x; i < n_codes; i += LY_THREADS) {
+            if (s_lo[i] != INT32_MAX) atomicMin(&lohi[i], (long long)s_lo[i]);
+            if (s_hi[i] != INT32_MIN) atomicMax(&lohi[n_codes + i], (long long)s_hi[i]);
+        }
+    }
+}
+
+__global__ void layout_init_kernel(long long* lohi, int32_t n_codes) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n_codes) {
+        lohi[i] = INT64_MAX;
+        lohi[n_codes + i] = INT64_MIN;
+    }
+}
+
+// base[] = exclusive scan of per-chromosome cell counts; one CTA, chunked with a carry
+__global__ void __launch_bounds__(1024)
+layout_finalize_kernel(const long long* __restrict__ lohi, int32_t n_codes, long long pad,
+                       uint32_t* __restrict__ base, int32_t* __restrict__ lo32, int32_t* __restrict__ hi32,
+                       unsigned long long* __restrict__ total) {
+    __shared__ unsigned long long scratch[1024 / 32 + 2];
+    unsigned long long carry = 0;
+    for (int b0 = 0; b0 < n_codes; b0 += 1024) {
+        int i = b0 + threadIdx.x;
+        unsigned long long cells = 0;
+        if (i < n_codes) {
+            long long lo = lohi[i], hi = lohi[n_codes + i];
+            if (lo > hi) {   // chromosome never observed
+                lo32[i] = 0;
+                hi32[i] = -1;
+                cells = 0;
+            } else {
+                lo32[i] = (int32_t)lo;
+                hi32[i] = (int32_t)hi;
+                cells = (unsigned long long)(hi - lo) + 3ull + (unsigned long long)pad;
+            }
+        }
+        unsigned long long tot;
+        unsigned long long ex = block_excl_scan_add<unsigned long long>(cells, scratch, &tot);
+        if (i < n_codes) {
+            unsigned long long b = carry + ex;
+            base[i] = b > 0xffffffffull ? 0xffffffffu : (uint32_t)b;
+        }
+        carry += tot;
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) {
+        base[n_codes] = carry > 0xffffffffull ? 0xffffffffu : (uint32_t)carry;
+        *total = carry;
+    }
+}
+
+// linearised start key + linearised end (unsorted), degenerate-row counters
+__global__ void __launch_bounds__(256)
+index_keygen_kernel(const int32_t* __restrict__ code, const int32_t* __restrict__ start,
+                    const int32_t* __restrict__ end, int64_t n, int32_t n_codes, int32_t sadj, int32_t eadj,
+                    const uint32_t* __restrict__ base, const int32_t* __restrict__ lo32,
+                    const int32_t* __restrict__ hi32, uint32_t* __restrict__ gs, uint32_t* __restrict__ ge,
+                    unsigned long long* __restrict__ counters /* [0] end<=start [1] end<start [2] outside layout */) {
+    unsigned int degenerate = 0, negative = 0, outside = 0;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        int32_t c = code[i];
+        long long s = (long long)start[i] + sadj, e = (long long)end[i] + eadj;
+        uint32_t ks = 0xffffffffu, ke = 0xffffffffu;
+        if (c < 0 || c >= n_codes) {
+            outside++;
+        } else {
+            long long lo = __ldg(lo32 + c), hi = __ldg(hi32 + c);
+            if (s < lo || s > hi || e < lo || e > hi) {
+                outside++;
+            } else {
+                uint32_t b = __ldg(base + c) + 1u;
+                ks = b + (uint32_t)(s - lo);
+                ke = b + (uint32_t)(e - lo);
+                degenerate += e <= s;
+                negative += e < s;
+            }
+        }
+        gs[i] = ks;
+        ge[i] = ke;
+    }
+    degenerate = warp_reduce_add(degenerate);
+    negative = warp_reduce_add(negative);
+    outside = warp_reduce_add(outside);
+    if (lane_id() == 0) {
+        if (degenerate) atomicAdd(&counters[0], (unsigned long long)degenerate);
+        if (negative) atomicAdd(&counters[1], (unsigned long long)negative);
+        if (outside) atomicAdd(&counters[2], (unsigned long long)outside);
+    }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256)
+gather_kernel(const T* __restrict__ src, const uint32_t* __restrict__ idx, T* __restrict__ dst, int64_t n) {
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+        dst[i] = src[idx[i]];
+}
+
+__global__ void __launch_bounds__(256)
+strand_histogram_kernel(const uint8_t* __restrict__ strand, int64_t n, unsigned long long* __restrict__ hist) {
+    __shared__ unsigned int sh[256];
+    sh[threadIdx.x] = 0;
+    __syncthreads();
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+        atomicAdd(&sh[strand[i]], 1u);
+    __syncthreads();
+    if (sh[threadIdx.x]) atomicAdd(&hist[threadIdx.x], (unsigned long long)sh[threadIdx.x]);
+}
+
+// stable partition of the sorted rows by strand code: pos = block_off[code] + rank among equal codes.
+// The rank is an exclusive scan of a one-hot per code; with few distinct codes in practice we scan one
+// code at a time (launch count = number of codes present).
+struct InIsCode {
+    const uint8_t* s;
+    uint8_t code;
+    __device__ unsigned long long operator()(int64_t i) const { return s[i] == code ? 1ull : 0ull; }
+};
+struct OutScatterRow {
+    const uint32_t *gs, *ge;
+    const int32_t* rid;
+    const uint8_t* strand;
+    uint32_t *gs_o, *ge_o;
+    int32_t* rid_o;
+    uint8_t* strand_o;
+    int64_t dst0;
+    __device__ void operator()(int64_t i, unsigned long long excl, unsigned long long v) const {
+        if (v) {
+            int64_t d = dst0 + (int64_t)excl;
+            gs_o[d] = gs[i];
+            ge_o[d] = ge[i];
+            rid_o[d] = rid[i];
+            strand_o[d] = strand[i];
+        }
+    }
+};
+
+inline int grid_for(const giqlb_ctx* ctx, int64_t n, int threads, int per_sm) {
+    int64_t want = ceil_div(n, threads);
+    int64_t cap = (int64_t)ctx->sm_count * per_sm;
+    return (int)(want < 1 ? 1 : (want < cap ? want : cap));
+}
+
+}  // namespace
+
+// ---- layout ---------------------------------------------------------------------------------------------
+extern "C" int giqlb_layout_create(giqlb_ctx* ctx, int32_t n_codes, int64_t pad, giqlb_layout** out) {
+    if (!ctx || !out || n_codes < 0 || pad < 0) return giqlb_fail(ctx, GIQLB_ERR_INVALID, "layout_create: bad argument");
+    begin_call(ctx);
+    giqlb_layout* lay = new (std::nothrow) giqlb_layout();
+    if (!lay) return GIQLB_ERR_NOMEM;
+    lay->n_codes = n_codes;
+    lay->pad = pad;
+    int st = dev_alloc(ctx, &lay->d_lohi, (size_t)2 * n_codes);
+    if (st == GIQLB_OK) st = dev_alloc(ctx, &lay->d_base, (size_t)n_codes + 1);
+    if (st == GIQLB_OK) st = dev_alloc(ctx, &lay->d_lo32, (size_t)n_codes);
+    if (st == GIQLB_OK) st = dev_alloc(ctx, &lay->d_hi32, (size_t)n_codes);
+    if (st != GIQLB_OK) {
+        giqlb_layout_free(ctx, lay);
+        return st;
+    }
+    if (n_codes > 0) {
+        layout_init_kernel<<<(n_codes + 255) / 256, 256, 0, ctx->stream>>>((long long*)lay->d_lohi, n_codes);
+        LAUNCH_CHECK(ctx);
+    }
+    *out = lay;
+    return end_call(ctx);
+}
+
+extern "C" int giqlb_layout_observe(giqlb_ctx* ctx, giqlb_layout* lay, const int32_t* code, const int32_t* start,
+                                    const int32_t* end, int64_t n, int32_t start_adj, int32_t end_adj) {
+    if (!ctx || !lay || n < 0 || (n > 0 && (!code || !start || !end))) return giqlb_fail(ctx, GIQLB_ERR_INVALID, "layout_observe: bad argument");
+    if (lay->finalized) return giqlb_fail(ctx, GIQLB_ERR_INVALID, "layout_observe: layout already finalized");
+    begin_call(ctx);
+    if (n > 0) {
+        if (lay->n_codes == 0) return giqlb_fail(ctx, GIQLB_ERR_INVALID, "layout_observe: rows given but the dictionary is empty");
+        layout_observe_kernel<<<grid_for(ctx, n, LY_THREADS * 8, 8), LY_THREADS, 0, ctx->stream>>>(
+            code, start, end, n, lay->n_codes, start_adj, end_adj, (long long*)lay->d_lohi, ctx->d_err);
+        LAUNCH_CHECK(ctx);
+    }
+    return end_call(ctx);
+}
+
+extern "C" int giqlb_layout_finalize(giqlb_ctx* ctx, giqlb_layout* lay) {
+    if (!ctx || !lay) return giqlb_fail(ctx, GIQLB_ERR_INVALID, "layout_finalize: bad argument");
+    if (lay->finalized) return GIQLB_OK;
+    begin_call(ctx);
+    unsigned long long* total = reinterpret_cast<unsigned long long*>(ctx->d_scalars);
+    layout_finalize_kernel<<<1, 1024, 0, ctx->stream>>>((const long long*)lay->d_lohi, lay->n_codes, (long long)lay->pad,
+                                                        lay->d_base, lay->d_lo32, lay->d_hi32, total);
+    LAUNCH_CHECK(ctx);
+    int h_err[4] = {0, 0, 0, 0};
+    CUDA_TRY(ctx, cudaMemcpyAsync(ctx->h_scalars, total, 8, cudaMemcpyDeviceToHost, ctx->stream));
+    lay->h_lo.assign(lay->n_codes, 0);
+    lay->h_hi.assign(lay->n_codes, -1);
+    lay->h_base.assign((size_t)lay->n_codes + 1, 0);
+    std::vector<int32_t> lo32(lay->n_codes), hi32(lay->n_codes);
+    if (lay->n_codes > 0) {
+        CUDA_TRY(ctx, cudaMemcpyAsync(lo32.data(), lay->d_lo32, (size_t)lay->n_codes * 4, cudaMemcpyDeviceToHost, ctx->stream));
+        CUDA_TRY(ctx, cudaMemcpyAsync(hi32.data(), lay->d_hi32, (size_t)lay->n_codes * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    }
+    CUDA_TRY(ctx, cudaMemcpyAsync(lay->h_base.data(), lay->d_base, ((size_t)lay->n_codes + 1) * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    CUDA_TRY(ctx, cudaMemcpyAsync(h_err, ctx->d_err, sizeof(h_err), cudaMemcpyDeviceToHost, ctx->stream));
+    CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    for (int i = 0; i < lay->n_codes; i++) {
+        lay->h_lo[i] = lo32[i];
+        lay->h_hi[i] = hi32[i];
+    }
+    if (h_err[1]) {
+        cudaMemsetAsync(ctx->d_err + 1, 0, sizeof(int), ctx->stream);
+        return giqlb_fail(ctx, GIQLB_ERR_RANGE, "layout: a row has a chromosome code outside the dictionary or a coordinate outside [-2^30, 2^31-4]");
+    }
+    lay->total_extent = (uint64_t)ctx->h_scalars[0];
+    if (lay->total_extent >= 0xffffffffull)
+        return giqlb_fail(ctx, GIQLB_ERR_RANGE, "layout: summed chromosome extent %llu does not fit the 32-bit linear coordinate",
+                          (unsigned long long)lay->total_extent);
+    int bits = 1;
+    while (bits < 32 && (lay->total_extent >> bits) != 0) bits++;
+    lay->key_bits = bits;
+    lay->finalized = true;
+    return end_call(ctx);
+}
+
+extern "C" int giqlb_layout_free(giqlb_ctx* ctx, giqlb_layout* lay) {
+    if (!lay) return GIQLB_OK;
+    if (ctx) {
+        dev_free(ctx, lay->d_lohi);
+        dev_free(ctx, lay->d_base);
+        dev_free(ctx, lay->d_lo32);
+        dev_free(ctx, lay->d_hi32);
+    }
+    delete lay;
+    return GIQLB_OK;
+}
+
+extern "C" int giqlb_layout_info(const giqlb_layout* lay, int32_t* n_codes, uint64_t* total_extent, int32_t* key_bits) {
+    if (!lay || !lay->finalized) return GIQLB_ERR_INVALID;
+    if (n_codes) *n_codes = lay->n_codes;
+    if (total_extent) *total_extent = lay->total_extent;
+    if (key_bits) *key_bits = lay->key_bits;
+    return GIQLB_OK;
+}
+
+extern "C" int giqlb_layout_tables(const giqlb_layout* lay, const uint32_t** base_dev, const int32_t** lo_dev,
+                                   const int32_t** hi_dev) {
+    if (!lay || !lay->finalized) return GIQLB_ERR_INVALID;
+    if (base_dev) *base_dev = lay->d_base;
+    if (lo_dev) *lo_dev = lay->d_lo32;
+    if (hi_dev) *hi_dev = lay->d_hi32;
+    return GIQLB_OK;
+}
+
+// ---- index ----------------------------------------------------------------------------------------------
+extern "C" int giqlb_index_free(giqlb_ctx* ctx, giqlb_index* ix) {
+    if (!ix) return GIQLB_OK;
+    if (ctx) {
+        dev_free(ctx, ix->gs);
+        dev_free(ctx, ix->ge);
+        dev_free(ctx, ix->rid);
+        dev_free(ctx, ix->strand);
+        dev_free(ctx, ix->pmax);
+        dev_free(ctx, ix->ge_sorted);
+        dev_free(ctx, ix->pos_by_end);
+        dev_free(ctx, ix->d_block_off);
+    }
+    delete ix;
+    return GIQLB_OK;
+}
+
+extern "C" int64_t giqlb_index_rows(const giqlb_index* ix) { return ix ? ix->n : -1; }
+
+extern "C" int giqlb_index_columns(const giqlb_index* ix, const uint32_t** gstart, const uint32_t** gend,
+                                   const int32_t** row_id, const uint8_t** strand) {
+    if (!ix) return GIQLB_ERR_INVALID;
+    if (gstart) *gstart = ix->gs;
+    if (gend) *gend = ix->ge;
+    if (row_id) *row_id = ix->rid;
+    if (strand) *strand = ix->strand;
+    return GIQLB_OK;
+}
+
+extern "C" int giqlb_index_info(const giqlb_index* ix, int64_t* n_degenerate, int64_t* n_negative, int32_t* n_blocks,
+                                int64_t* block_off_host /* [257] or NULL */) {
+    if (!ix) return GIQLB_ERR_INVALID;
+    if (n_degenerate) *n_degenerate = ix->n_degenerate;
+    if (n_negative) *n_negative = ix->n_negative;
+    if (n_blocks) *n_blocks = ix->n_blocks;
+    if (block_off_host) memcpy(block_off_host, ix->block_off, sizeof(ix->block_off));
+    return GIQLB_OK;
+}
+
+extern "C" int giqlb_index_build(giqlb_ctx* ctx, const giqlb_layout* lay, const int32_t* code, const int32_t* start,
+                                 const int32_t* end, const uint8_t* strand, int64_t n, int32_t start_adj,
+                                 int32_t end_adj, int flags, giqlb_index** out) {
+    if (!ctx || !lay || !out || n < 0 || (n > 0 && (!code || !start || !end)))
+        return giqlb_fail(ctx, GIQLB_ERR_INVALID, "index_build: bad argument");
+    if (!lay->finalized) return giqlb_fail(ctx, GIQLB_ERR_INVALID, "index_build: layout not finalized");
+    if (n >= (1ll << 30)) return giqlb_fail(ctx, GIQLB_ERR_INVALID, "index_build: n=%lld exceeds 2^30 rows per table", (long long)n);
+    begin_call(ctx);
+    *out = nullptr;
+    giqlb_index* ix = new (std::nothrow) giqlb_index();
+    if (!ix) return GIQLB_ERR_NOMEM;
+    ix->n = n;
+    ix->layout = lay;
+    ix->tie_by_end = (flags & GIQLB_INDEX_TIE_BY_END) != 0;
+    ix->block_off[1] = n;
+    for (int i = 2; i <= GIQLB_MAX_STRAND_CODES; i++) ix->block_off[i] = n;
+
+    uint32_t *ka = nullptr, *kb = nullptr, *va = nullptr, *vb = nullptr, *ge_u = nullptr, *gs_u = nullptr;
+    unsigned long long* counters = reinterpret_cast<unsigned long long*>(ctx->d_scalars + 16);
+    int st = GIQLB_OK;
+#define IB_TRY(expr)                      \
+    do {                                  \
+        st = (expr);                      \
+        if (st != GIQLB_OK) goto fail;    \
+    } while (0)
+#define IB_CUDA(expr)                                                                                   \
+    do {                                                                                                \
+        cudaError_t _e = (expr);                                                                        \
+        if (_e != cudaSuccess) {                                                                        \
+            st = giqlb_fail(ctx, GIQLB_ERR_CUDA, "%s:%d %s -> %s", __FILE__, __LINE__, #expr, cudaGetErrorString(_e)); \
+            goto fail;                                                                                  \
+        }                                                                                               \
+    } while (0)
+
+    IB_TRY(dev_alloc(ctx, &ka, (size_t)n));
+    IB_TRY(dev_alloc(ctx, &kb, (size_t)n));
+    IB_TRY(dev_alloc(ctx, &va, (size_t)n));
+    IB_TRY(dev_alloc(ctx, &vb, (size_t)n));
+    IB_TRY(dev_alloc(ctx, &ge_u, (size_t)n));
+    IB_TRY(dev_alloc(ctx, &ix->ge, (size_t)n));
+    IB_CUDA(cudaMemsetAsync(counters, 0, 3 * 8, ctx->stream));
+    if (n > 0) {
+        int result_in_b = 0;
+        index_keygen_kernel<<<grid_for(ctx, n, 256 * 4, 8), 256, 0, ctx->stream>>>(
+            code, start, end, n, lay->n_codes, start_adj, end_adj, lay->d_base, lay->d_lo32, lay->d_hi32, ka, ge_u, counters);
+        ctx->launches_this_call++;
+        ctx->stats.kernels_total++;
+        IB_CUDA(cudaGetLastError());
+        if (ix->tie_by_end) {
+            // LSD over the compound key (start, end): sort by end first, then stably by start
+            IB_TRY(dev_alloc(ctx, &gs_u, (size_t)n));
+            IB_CUDA(cudaMemcpyAsync(gs_u, ka, (size_t)n * 4, cudaMemcpyDeviceToDevice, ctx->stream));
+            IB_CUDA(cudaMemcpyAsync(ka, ge_u, (size_t)n * 4, cudaMemcpyDeviceToDevice, ctx->stream));
+            IB_TRY(giqlb_radix_sort_pairs_u32(ctx, ka, va, kb, vb, n, 0, lay->key_bits, 1, &result_in_b));
+            uint32_t* rid1 = result_in_b ? vb : va;
+            uint32_t* k2 = result_in_b ? ka : kb;   // the buffer pair NOT holding the result becomes the next input
+            uint32_t* v2 = result_in_b ? va : vb;
+            gather_kernel<uint32_t><<<grid_for(ctx, n, 256 * 4, 8), 256, 0, ctx->stream>>>(gs_u, rid1, k2, n);
+            ctx->launches_this_call++;
+            ctx->stats.kernels_total++;
+            IB_CUDA(cudaGetLastError());
+            IB_CUDA(cudaMemcpyAsync(v2, rid1, (size_t)n * 4, cudaMemcpyDeviceToDevice, ctx->stream));
+            uint32_t* k3 = result_in_b ? kb : ka;
+            uint32_t* v3 = result_in_b ? vb : va;
+            int r2 = 0;
+            IB_TRY(giqlb_radix_sort_pairs_u32(ctx, k2, v2, k3, v3, n, 0, lay->key_bits, 0, &r2));
+            // result is in (k3, v3) when r2 else (k2, v2); normalise so that `result_in_b` describes (kb, vb)
+            uint32_t* rk = r2 ? k3 : k2;
+            result_in_b = (rk == kb) ? 1 : 0;
+        } else {
+            IB_TRY(giqlb_radix_sort_pairs_u32(ctx, ka, va, kb, vb, n, 0, lay->key_bits, 1, &result_in_b));
+        }
+        if (result_in_b) {
+            ix->gs = kb; ix->rid = reinterpret_cast<int32_t*>(vb);
+            kb = nullptr; vb = nullptr;
+        } else {
+            ix->gs = ka; ix->rid = reinterpret_cast<int32_t*>(va);
+            ka = nullptr; va = nullptr;
+        }
+        gather_kernel<uint32_t><<<grid_for(ctx, n, 256 * 4, 8), 256, 0, ctx->stream>>>(
+            ge_u, reinterpret_cast<const uint32_t*>(ix->rid), ix->ge, n);
+        ctx->launches_this_call++;
+        ctx->stats.kernels_total++;
+        IB_CUDA(cudaGetLastError());
+        if (strand) {
+            IB_TRY(dev_alloc(ctx, &ix->strand, (size_t)n));
+            gather_kernel<uint8_t><<<grid_for(ctx, n, 256 * 4, 8), 256, 0, ctx->stream>>>(
+                strand, reinterpret_cast<const uint32_t*>(ix->rid), ix->strand, n);
+            ctx->launches_this_call++;
+            ctx->stats.kernels_total++;
+            IB_CUDA(cudaGetLastError());
+        }
+    } else {
+        ix->gs = ka; ix->rid = reinterpret_cast<int32_t*>(va);
+        ka = nullptr; va = nullptr;
+        if (strand) IB_TRY(dev_alloc(ctx, &ix->strand, 1));
+    }
+    dev_free(ctx, ka); dev_free(ctx, kb); dev_free(ctx, va); dev_free(ctx, vb); dev_free(ctx, ge_u); dev_free(ctx, gs_u);
+    ka = kb = va = vb = ge_u = gs_u = nullptr;
+    st = fetch_scalars(ctx, counters, 3);
+    if (st != GIQLB_OK) goto fail;
+    ix->n_degenerate = ctx->h_scalars[0];
+    ix->n_negative = ctx->h_scalars[1];
+    if (ctx->h_scalars[2] != 0) {
+        st = giqlb_fail(ctx, GIQLB_ERR_RANGE, "index_build: %lld rows lie outside the layout (observe the table before finalize)",
+                        (long long)ctx->h_scalars[2]);
+        goto fail;
+    }
+    ctx->stats.rows_in[0] = n;
+    ctx->stats.rows_in[1] = 0;
+    ctx->stats.rows_out = n;
+    ctx->stats.algorithmic_bytes = 12 * n + 12 * n;
+    *out = ix;
+    return end_call(ctx);
+fail:
+    dev_free(ctx, ka); dev_free(ctx, kb); dev_free(ctx, va); dev_free(ctx, vb); dev_free(ctx, ge_u); dev_free(ctx, gs_u);
+    giqlb_index_free(ctx, ix);
+    return st;
+#undef IB_TRY
+#undef IB_CUDA
+}
+
+// Reorders the index into blocks of equal strand code (ascending code), each block still sorted by start.
+extern "C" int giqlb_index_group_by_strand(giqlb_ctx* ctx, giqlb_index* ix) {
+    using namespace giqlb_scan;
+    if (!ctx || !ix) return giqlb_fail(ctx, GIQLB_ERR_INVALID, "group_by_strand: bad argument");
+    if (!ix->strand) return giqlb_fail(ctx, GIQLB_ERR_INVALID, "group_by_strand: index was built without a strand column");
+    if (ix->grouped_by_strand) return GIQLB_OK;
+    begin_call(ctx);
+    const int64_t n = ix->n;
+    unsigned long long* hist = nullptr;
+    GIQLB_TRY(dev_alloc(ctx, &hist, 256));
+    CUDA_TRY(ctx, cudaMemsetAsync(hist, 0, 256 * 8, ctx->stream));
+    if (n > 0) {
+        strand_histogram_kernel<<<grid_for(ctx, n, 256 * 16, 4), 256, 0, ctx->stream>>>(ix->strand, n, hist);
+        LAUNCH_CHECK(ctx);
+    }
+    std::vector<unsigned long long> h(256);
+    CUDA_TRY(ctx, cudaMemcpyAsync(h.data(), hist, 256 * 8, cudaMemcpyDeviceToHost, ctx->stream));
+    CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    dev_free(ctx, hist);
+    ix->block_off[0] = 0;
+    for (int c = 0; c < 256; c++) ix->block_off[c + 1] = ix->block_off[c] + (int64_t)h[c];
+    ix->n_blocks = 256;
+    if (n > 0) {
+        uint32_t *gs_o = nullptr, *ge_o = nullptr;
+        int32_t* rid_o = nullptr;
+        uint8_t* st_o = nullptr;
+        GIQLB_TRY(dev_alloc(ctx, &gs_o, (size_t)n));
+        GIQLB_TRY(dev_alloc(ctx, &ge_o, (size_t)n));
+        GIQLB_TRY(dev_alloc(ctx, &rid_o, (size_t)n));
+        GIQLB_TRY(dev_alloc(ctx, &st_o, (size_t)n));
+        for (int c = 0; c < 256; c++) {
+            if (!h[c]) continue;
+            GIQLB_TRY((launch_scan<OpAddU64>(ctx, n, InIsCode{ix->strand, (uint8_t)c},
+                                             OutScatterRow{ix->gs, ix->ge, ix->rid, ix->strand, gs_o, ge_o, rid_o, st_o, ix->block_off[c]})));
+        }
+        dev_free(ctx, ix->gs); dev_free(ctx, ix->ge); dev_free(ctx, ix->rid); dev_free(ctx, ix->strand);
+        ix->gs = gs_o; ix->ge = ge_o; ix->rid = rid_o; ix->strand = st_o;
+        // derived arrays are stale now
+        dev_free(ctx, ix->pmax); dev_free(ctx, ix->ge_sorted); dev_free(ctx, ix->pos_by_end);
+        ix->pmax = nullptr; ix->ge_sorted = nullptr; ix->pos_by_end = nullptr;
+    }
+    GIQLB_TRY(dev_alloc(ctx, &ix->d_block_off, (size_t)GIQLB_MAX_STRAND_CODES + 1));
+    CUDA_TRY(ctx, cudaMemcpyAsync(ix->d_block_off, ix->block_off, sizeof(ix->block_off), cudaMemcpyHostToDevice, ctx->stream));
+    CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));   // block_off is pageable host memory inside *ix
+    ix->grouped_by_strand = true;
+    return end_call(ctx);
+}
+
+int giqlb_index_ensure_pmax(giqlb_ctx* ctx, giqlb_index* ix) {
+    if (ix->pmax) return GIQLB_OK;
+    GIQLB_TRY(dev_alloc(ctx, &ix->pmax, (size_t)ix->n));
+    return giqlb_incl_scan_max_u32(ctx, ix->ge, ix->pmax, ix->n, ix->grouped_by_strand ? ix->block_off : nullptr,
+                                   ix->grouped_by_strand ? ix->n_blocks : 1);
+}
+
+// ge ascending with the sorted position of each (pos_by_end).  Within a strand block when grouped.
+int giqlb_index_ensure_end_sorted(giqlb_ctx* ctx, giqlb_index* ix) {
+    if (ix->ge_sorted) return GIQLB_OK;
+    const int64_t n = ix->n;
+    uint32_t *ka = nullptr, *kb = nullptr, *va = nullptr, *vb = nullptr;
+    GIQLB_TRY(dev_alloc(ctx, &ka, (size_t)n));
+    GIQLB_TRY(dev_alloc(ctx, &kb, (size_t)n));
+    GIQLB_TRY(dev_alloc(ctx, &va, (size_t)n));
+    GIQLB_TRY(dev_alloc(ctx, &vb, (size_t)n));
+    if (n > 0) CUDA_TRY(ctx, cudaMemcpyAsync(ka, ix->ge, (size_t)n * 4, cudaMemcpyDeviceToDevice, ctx->stream));
+    const int nb = ix->grouped_by_strand ? ix->n_blocks : 1;
+    // every block is sorted independently; identity payloads are block-relative, so sort whole-array when
+    // ungrouped and fix up per block otherwise
+    if (nb == 1) {
+        int in_b = 0;
+        GIQLB_TRY(giqlb_radix_sort_pairs_u32(ctx, ka, va, kb, vb, n, 0, ix->layout->key_bits, 1, &in_b));
+        if (in_b) { ix->ge_sorted = kb; ix->pos_by_end = (int32_t*)vb; dev_free(ctx, ka); dev_free(ctx, va); }
+        else      { ix->ge_sorted = ka; ix->pos_by_end = (int32_t*)va; dev_free(ctx, kb); dev_free(ctx, vb); }
+        return GIQLB_OK;
+    }
+    dev_free(ctx, ka); dev_free(ctx, kb); dev_free(ctx, va); dev_free(ctx, vb);
+    return giqlb_fail(ctx, GIQLB_ERR_INTERNAL, "end-sorted view of a strand-grouped index is built by nearest.cu");
+}

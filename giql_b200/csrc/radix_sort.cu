@@ -1,0 +1,227 @@
+// radix_sort.cu — device LSD radix sort of uint32 keys with a carried uint32 payload (row ids).
+//
+// Replaces the per-chromosome sorts DuckDB's IE_JOIN performs for the SQL emitted at
+// src/giql/expanders/intersects_duckdb.py:1283-1299 (reference) with ONE sort of the linearised
+// (chrom, start) key.  Design ("onesweep"): one histogram kernel counts every digit of every pass in a
+// single read of the keys; then one kernel per 8-bit digit ranks a 4096-key tile with warp match-any
+// multi-split, obtains its global digit bases through a decoupled look-back over per-tile status words
+// (tiles take tickets from an atomic counter, so a tile only ever waits on tiles already scheduled),
+// stages the tile in shared memory in digit order and writes it out in coalesced runs.
+// HBM traffic: 4 B/key (histogram) + 16 B/key/pass (keys+payload in and out).
+#include "common.cuh"
+
+namespace {
+
+constexpr int RS_THREADS = 256;
+constexpr int RS_WARPS = RS_THREADS / 32;
+constexpr int RS_IPT = 16;
+constexpr int RS_TILE = RS_THREADS * RS_IPT;   // 4096 keys per tile
+constexpr int RS_RADIX = 256;
+constexpr int RS_MAX_PASSES = 4;
+
+constexpr uint32_t ST_FLAG_AGG = 1u << 30;
+constexpr uint32_t ST_FLAG_INCL = 2u << 30;
+constexpr uint32_t ST_VALUE_MASK = (1u << 30) - 1;
+constexpr uint32_t RS_SPIN_LIMIT = 1u << 26;
+
+// ---- histogram of all digits in one read ---------------------------------------------------------
+__global__ void __launch_bounds__(RS_THREADS)
+rs_histogram_kernel(const uint32_t* __restrict__ keys, int64_t n, int begin_bit, int n_passes,
+                    uint32_t* __restrict__ ghist /* [n_passes][256] */) {
+    __shared__ uint32_t sh[RS_MAX_PASSES][RS_RADIX];
+    for (int i = threadIdx.x; i < RS_MAX_PASSES * RS_RADIX; i += RS_THREADS) (&sh[0][0])[i] = 0;
+    __syncthreads();
+    const int64_t n_vec = n >> 2;
+    const uint4* kv = reinterpret_cast<const uint4*>(keys);
+    for (int64_t i = (int64_t)blockIdx.x * RS_THREADS + threadIdx.x; i < n_vec; i += (int64_t)gridDim.x * RS_THREADS) {
+        uint4 k = ld_stream_u32x4(kv + i);
+        uint32_t kk[4] = {k.x, k.y, k.z, k.w};
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+#pragma unroll
+            for (int p = 0; p < RS_MAX_PASSES; p++)
+                if (p < n_passes) atomicAdd(&sh[p][(kk[j] >> (begin_bit + 8 * p)) & 255u], 1u);
+        }
+    }
+    // tail
+    if (blockIdx.x == 0) {
+        for (int64_t i = (n_vec << 2) + threadIdx.x; i < n; i += RS_THREADS) {
+            uint32_t k = keys[i];
+            for (int p = 0; p < n_passes; p++) atomicAdd(&sh[p][(k >> (begin_bit + 8 * p)) & 255u], 1u);
+        }
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < n_passes * RS_RADIX; i += RS_THREADS) {
+        uint32_t c = (&sh[0][0])[i];
+        if (c) atomicAdd(&ghist[i], c);
+    }
+}
+
+// ---- one digit pass ----------------------------------------------------------------------------------
+// IDENTITY_VALS: payload of key i is i itself (first pass; no payload array is read).
+template <bool IDENTITY_VALS>
+__global__ void __launch_bounds__(RS_THREADS)
+rs_onesweep_kernel(const uint32_t* __restrict__ keys_in, const uint32_t* __restrict__ vals_in,
+                   uint32_t* __restrict__ keys_out, uint32_t* __restrict__ vals_out, int64_t n, int shift,
+                   const uint32_t* __restrict__ ghist /* this pass, [256] */,
+                   uint32_t* __restrict__ status /* this pass, [tiles][256] */,
+                   uint32_t* __restrict__ ticket, int* __restrict__ err_flag) {
+    __shared__ uint32_t s_warp_hist[RS_WARPS][RS_RADIX];   // per-warp digit counters -> warp-exclusive offsets
+    __shared__ uint32_t s_keys[RS_TILE];
+    __shared__ uint32_t s_vals[RS_TILE];
+    __shared__ uint32_t s_digit_excl[RS_RADIX];            // tile-local exclusive digit offsets
+    __shared__ int64_t s_global_base[RS_RADIX];            // global position of local sorted slot 0 of each digit
+    __shared__ uint32_t s_scan[RS_WARPS + 2];
+    __shared__ uint32_t s_tile;
+
+    if (threadIdx.x == 0) s_tile = atomicAdd(ticket, 1u);
+    for (int i = threadIdx.x; i < RS_WARPS * RS_RADIX; i += RS_THREADS) (&s_warp_hist[0][0])[i] = 0;
+    __syncthreads();
+    const uint32_t tile = s_tile;
+    const int64_t tile_base = (int64_t)tile * RS_TILE;
+    const int tile_n = (int)min((int64_t)RS_TILE, n - tile_base);
+    const uint32_t w = warp_id(), l = lane_id();
+    const uint32_t lt_mask = (1u << l) - 1u;
+
+    // load: warp w owns keys [w*512, w*512+512) of the tile; item i of lane l is w*512 + i*32 + l
+    uint32_t key[RS_IPT];
+    uint32_t rank[RS_IPT];
+    const int warp_off = w * (32 * RS_IPT);
+#pragma unroll
+    for (int i = 0; i < RS_IPT; i++) {
+        int li = warp_off + i * 32 + l;
+        key[i] = li < tile_n ? ld_stream_u32(keys_in + tile_base + li) : 0xffffffffu;
+    }
+    // rank within the warp, stable in (item, lane) order
+#pragma unroll
+    for (int i = 0; i < RS_IPT; i++) {
+        uint32_t d = (key[i] >> shift) & 255u;
+        uint32_t peers = __match_any_sync(FULL_MASK, d);
+        int leader = __ffs(peers) - 1;
+        uint32_t base = 0;
+        if ((int)l == leader) {
+            base = s_warp_hist[w][d];
+            s_warp_hist[w][d] = base + __popc(peers);
+        }
+        base = __shfl_sync(FULL_MASK, base, leader);
+        rank[i] = base + __popc(peers & lt_mask);
+        __syncwarp();
+    }
+    __syncthreads();
+
+    // thread d: turn per-warp counts into warp-exclusive offsets, get the tile's count of digit d
+    const uint32_t d_own = threadIdx.x;
+    uint32_t count = 0;
+#pragma unroll
+    for (int ww = 0; ww < RS_WARPS; ww++) {
+        uint32_t c = s_warp_hist[ww][d_own];
+        s_warp_hist[ww][d_own] = count;
+        count += c;
+    }
+    if (d_own == 255u) count -= (uint32_t)(RS_TILE - tile_n);   // padding keys are all-ones -> digit 255
+    uint32_t* my_status = status + (size_t)tile * RS_RADIX + d_own;
+    if (tile == 0) {
+        *(volatile uint32_t*)my_status = ST_FLAG_INCL | count;
+    } else {
+        *(volatile uint32_t*)my_status = ST_FLAG_AGG | count;
+    }
+    // tile-local exclusive offsets over digits, and global start of each digit bin
+    uint32_t tot;
+    uint32_t dex = block_excl_scan_add<uint32_t>(count, s_scan, &tot);
+    __syncthreads();
+    uint32_t gtot;
+    uint32_t gstart = block_excl_scan_add<uint32_t>(ghist[d_own], s_scan, &gtot);
+    s_digit_excl[d_own] = dex;
+
+    // decoupled look-back over earlier tiles for digit d_own
+    uint32_t prefix = 0;
+    if (tile > 0) {
+        int64_t t = (int64_t)tile - 1;
+        uint32_t spins = 0;
+        while (true) {
+            uint32_t s = *(volatile uint32_t*)(status + (size_t)t * RS_RADIX + d_own);
+            uint32_t flag = s & ~ST_VALUE_MASK;
+            if (flag == 0) {
+                if (++spins > RS_SPIN_LIMIT) { *err_flag = 1; break; }
+                __nanosleep(20);
+                continue;
+            }
+            prefix += s & ST_VALUE_MASK;
+            if (flag == ST_FLAG_INCL) break;
+            t--;
+        }
+        *(volatile uint32_t*)my_status = ST_FLAG_INCL | (prefix + count);
+    }
+    s_global_base[d_own] = (int64_t)gstart + (int64_t)prefix - (int64_t)dex;
+    __syncthreads();
+
+    // scatter the tile into shared memory in digit order
+#pragma unroll
+    for (int i = 0; i < RS_IPT; i++) {
+        uint32_t d = (key[i] >> shift) & 255u;
+        uint32_t pos = s_digit_excl[d] + s_warp_hist[w][d] + rank[i];
+        int li = warp_off + i * 32 + l;
+        uint32_t v;
+        if (IDENTITY_VALS) v = (uint32_t)(tile_base + li);
+        else v = li < tile_n ? ld_stream_u32(vals_in + tile_base + li) : 0u;
+        s_keys[pos] = key[i];
+        s_vals[pos] = v;
+    }
+    __syncthreads();
+    // write out: consecutive slots of one digit are consecutive in global memory
+    for (int j = threadIdx.x; j < tile_n; j += RS_THREADS) {
+        uint32_t k = s_keys[j];
+        uint32_t d = (k >> shift) & 255u;
+        int64_t out = s_global_base[d] + j;
+        keys_out[out] = k;
+        vals_out[out] = s_vals[j];
+    }
+}
+
+}  // namespace
+
+// Sorts n (key, value) pairs on bits [begin_bit, end_bit).  keys_a/vals_a hold the input; the two buffer
+// pairs ping-pong and *result_in_b says where the output landed.  identity_vals: the payload of key i is
+// i itself (vals_a is scratch and is not read by the first pass).
+int giqlb_radix_sort_pairs_u32(giqlb_ctx* ctx, uint32_t* keys_a, uint32_t* vals_a, uint32_t* keys_b,
+                               uint32_t* vals_b, int64_t n, int begin_bit, int end_bit, int identity_vals,
+                               int* result_in_b) {
+    *result_in_b = 0;
+    if (n >= (int64_t)ST_VALUE_MASK) return giqlb_fail(ctx, GIQLB_ERR_INVALID, "radix sort: n=%lld too large", (long long)n);
+    int n_passes = (end_bit - begin_bit + 7) / 8;
+    if (n_passes < 1) n_passes = 1;   // always run one pass so the payload is materialised
+    if (n_passes > RS_MAX_PASSES) return giqlb_fail(ctx, GIQLB_ERR_INVALID, "radix sort: too many passes");
+    if (n == 0) return GIQLB_OK;
+    const int64_t tiles = ceil_div(n, RS_TILE);
+
+    uint32_t* ghist = nullptr;    // [n_passes][256] | tickets[RS_MAX_PASSES] | status [n_passes][tiles][256]
+    const size_t head_words = (size_t)n_passes * RS_RADIX + RS_MAX_PASSES;
+    const size_t words = head_words + (size_t)n_passes * tiles * RS_RADIX;
+    GIQLB_TRY(dev_alloc(ctx, &ghist, words));
+    CUDA_TRY(ctx, cudaMemsetAsync(ghist, 0, words * sizeof(uint32_t), ctx->stream));
+    uint32_t* tickets = ghist + (size_t)n_passes * RS_RADIX;
+    uint32_t* status = ghist + head_words;
+
+    int64_t hb_want = ceil_div(n, RS_THREADS * 16), hb_cap = (int64_t)ctx->sm_count * 8;
+    int hist_blocks = (int)(hb_want < hb_cap ? hb_want : hb_cap);
+    rs_histogram_kernel<<<hist_blocks, RS_THREADS, 0, ctx->stream>>>(keys_a, n, begin_bit, n_passes, ghist);
+    LAUNCH_CHECK(ctx);
+
+    uint32_t *kin = keys_a, *vin = vals_a, *kout = keys_b, *vout = vals_b;
+    for (int p = 0; p < n_passes; p++) {
+        const int shift = begin_bit + 8 * p;
+        const uint32_t* gh = ghist + (size_t)p * RS_RADIX;
+        uint32_t* st = status + (size_t)p * tiles * RS_RADIX;
+        if (p == 0 && identity_vals)
+            rs_onesweep_kernel<true><<<(unsigned)tiles, RS_THREADS, 0, ctx->stream>>>(kin, vin, kout, vout, n, shift, gh, st, tickets + p, ctx->d_err);
+        else
+            rs_onesweep_kernel<false><<<(unsigned)tiles, RS_THREADS, 0, ctx->stream>>>(kin, vin, kout, vout, n, shift, gh, st, tickets + p, ctx->d_err);
+        LAUNCH_CHECK(ctx);
+        uint32_t* t;
+        t = kin; kin = kout; kout = t;
+        t = vin; vin = vout; vout = t;
+        *result_in_b ^= 1;
+    }
+    dev_free(ctx, ghist);
+    return GIQLB_OK;
+}

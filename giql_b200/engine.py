@@ -1,0 +1,467 @@
+"""Host layer of the B200 engine: ingest (numpy / pandas / Arrow / torch), device-resident tables and one
+method per GIQL operator, each a thin sequence of C-ABI calls into ``libgiqlb200.so``.
+
+PyTorch is used for device memory and stream plumbing only; every data-path kernel lives in
+``giql_b200/csrc``.  There is no CPU fallback: constructing an :class:`Engine` without a CUDA device or
+without the built extension raises.
+
+Operator semantics follow the reference (abdenlab/giql), cited per method.
+"""
+from __future__ import annotations
+
+import ctypes
+from dataclasses import dataclass
+from typing import Any, Optional, Sequence
+
+import numpy as np
+import torch
+
+from . import _cabi
+from ._cabi import EngineError, EngineUnavailable
+from .table import Table, canonical_offsets
+
+_I32_MIN, _I32_MAX = -(2**31), 2**31 - 1
+
+
+def _as_i32(col, what: str) -> np.ndarray:
+    """Host integer column -> contiguous int32, rejecting NULLs and out-of-range values."""
+    if isinstance(col, torch.Tensor):
+        col = col.detach().cpu().numpy()
+    try:
+        import pyarrow as pa
+
+        if isinstance(col, (pa.Array, pa.ChunkedArray)):
+            if col.null_count:
+                raise ValueError(f"{what}: NULL coordinates are not supported (BED never has them)")
+            col = col.to_numpy(zero_copy_only=False) if isinstance(col, pa.Array) else col.combine_chunks().to_numpy(zero_copy_only=False)
+    except ImportError:  # pragma: no cover
+        pass
+    if hasattr(col, "to_numpy") and not isinstance(col, np.ndarray):
+        col = col.to_numpy()
+    a = np.asarray(col)
+    if a.dtype == object:
+        if any(v is None for v in a):
+            raise ValueError(f"{what}: NULL coordinates are not supported (BED never has them)")
+        a = a.astype(np.int64)
+    if a.dtype.kind == "f":
+        if np.isnan(a).any():
+            raise ValueError(f"{what}: NULL coordinates are not supported (BED never has them)")
+        a = a.astype(np.int64)
+    if a.dtype.kind not in "iu":
+        raise ValueError(f"{what}: expected an integer column, got dtype {a.dtype}")
+    if a.dtype != np.int32:
+        if a.size and (int(a.min()) < _I32_MIN or int(a.max()) > _I32_MAX):
+            raise ValueError(f"{what}: coordinate outside the int32 range")
+        a = a.astype(np.int32)
+    return np.ascontiguousarray(a)
+
+
+def _as_utf8(col, what: str):
+    """Host string column -> (offsets int32[n+1], bytes uint8[]) in Arrow utf8 layout."""
+    import pyarrow as pa
+
+    if isinstance(col, pa.ChunkedArray):
+        col = col.combine_chunks()
+    if not isinstance(col, pa.Array):
+        if hasattr(col, "to_numpy") and not isinstance(col, np.ndarray):
+            col = col.to_numpy()
+        if isinstance(col, np.ndarray) and col.dtype.kind in "US":
+            col = col.astype(object) if col.dtype.kind == "U" else np.array([b.decode() for b in col], dtype=object)
+        col = pa.array(list(col) if not isinstance(col, np.ndarray) else col, type=pa.string(), from_pandas=True)
+    if pa.types.is_dictionary(col.type):
+        col = col.dictionary_decode()
+    if pa.types.is_large_string(col.type) or not pa.types.is_string(col.type):
+        col = col.cast(pa.string())
+    if col.null_count:
+        raise ValueError(f"{what}: NULL chromosome names are not supported (BED never has them)")
+    n = len(col)
+    bufs = col.buffers()
+    offsets = np.frombuffer(bufs[1], dtype=np.int32)[col.offset: col.offset + n + 1] if n or bufs[1] is not None else np.zeros(1, np.int32)
+    data = np.frombuffer(bufs[2], dtype=np.uint8) if bufs[2] is not None and bufs[2].size else np.zeros(1, np.uint8)
+    if n == 0:
+        offsets = np.zeros(1, np.int32)
+    return np.ascontiguousarray(offsets), data
+
+
+class Dictionary:
+    """Shared chromosome dictionary: ``names[code]`` sorted bytewise (codes preserve VARCHAR order)."""
+
+    def __init__(self, names: Sequence[str]):
+        self.names = list(names)
+        self._lookup = {n: i for i, n in enumerate(self.names)}
+
+    def __len__(self) -> int:
+        return len(self.names)
+
+    def code(self, name: str) -> int:
+        return self._lookup.get(name, -1)
+
+
+@dataclass
+class PairResult:
+    """Overlapping pairs as row ids into the two input tables (device int32 tensors, order unspecified)."""
+
+    left_rows: torch.Tensor
+    right_rows: torch.Tensor
+
+    def __len__(self) -> int:
+        return int(self.left_rows.numel())
+
+    def sorted_packed(self) -> np.ndarray:
+        """``sort((left << 32) | right)`` on the host — the reference's sorted-multiset normal form
+        (tests/integration/_oracle.py:77-89)."""
+        l = self.left_rows.to(torch.int64)
+        r = self.right_rows.to(torch.int64)
+        return torch.sort((l << 32) | r).values.cpu().numpy()
+
+    def to_host(self):
+        return self.left_rows.cpu().numpy(), self.right_rows.cpu().numpy()
+
+
+class DeviceTable:
+    """Columns of one genomic table resident in HBM."""
+
+    def __init__(self, engine: "Engine", n: int, config: Optional[Table], start: torch.Tensor, end: torch.Tensor,
+                 strand: Optional[torch.Tensor], chrom_offsets: Optional[torch.Tensor], chrom_bytes: Optional[torch.Tensor],
+                 codes: Optional[torch.Tensor] = None, dictionary: Optional[Dictionary] = None):
+        self.engine = engine
+        self.n = n
+        self.config = config
+        self.start, self.end, self.strand = start, end, strand
+        self.chrom_offsets, self.chrom_bytes = chrom_offsets, chrom_bytes
+        self.codes, self.dictionary = codes, dictionary
+
+    def __len__(self) -> int:
+        return self.n
+
+    @property
+    def offsets(self) -> tuple[int, int]:
+        return canonical_offsets(self.config)
+
+    def device_bytes(self) -> int:
+        return sum(t.numel() * t.element_size() for t in (self.start, self.end, self.strand, self.chrom_offsets,
+                                                           self.chrom_bytes, self.codes) if t is not None)
+
+
+def _ptr(t: Optional[torch.Tensor]):
+    return ctypes.c_void_p(t.data_ptr()) if t is not None else None
+
+
+class _Layout:
+    def __init__(self, engine: "Engine", n_codes: int, pad: int = 0):
+        self.e = engine
+        self.h = ctypes.c_void_p()
+        engine._check(engine.lib.giqlb_layout_create(engine.ctx, n_codes, pad, ctypes.byref(self.h)))
+
+    def observe(self, t: DeviceTable, raw: bool = False):
+        sadj, eadj = (0, 0) if raw else t.offsets
+        self.e._check(self.e.lib.giqlb_layout_observe(self.e.ctx, self.h, _ptr(t.codes), _ptr(t.start), _ptr(t.end), t.n, sadj, eadj))
+
+    def finalize(self):
+        self.e._check(self.e.lib.giqlb_layout_finalize(self.e.ctx, self.h))
+
+    def info(self):
+        n, ext, bits = ctypes.c_int32(), ctypes.c_uint64(), ctypes.c_int32()
+        self.e.lib.giqlb_layout_info(self.h, ctypes.byref(n), ctypes.byref(ext), ctypes.byref(bits))
+        return n.value, ext.value, bits.value
+
+    def free(self):
+        if self.h:
+            self.e.lib.giqlb_layout_free(self.e.ctx, self.h)
+            self.h = ctypes.c_void_p()
+
+    def __del__(self):
+        try:
+            self.free()
+        except Exception:
+            pass
+
+
+class _Index:
+    def __init__(self, engine: "Engine", layout: _Layout, t: DeviceTable, raw: bool = False, with_strand: bool = False,
+                 tie_by_end: bool = False):
+        self.e = engine
+        self.layout = layout   # keep the layout alive as long as the index
+        self.h = ctypes.c_void_p()
+        sadj, eadj = (0, 0) if raw else t.offsets
+        strand = t.strand if with_strand else None
+        if with_strand and strand is None:
+            raise ValueError("stranded := true requires a strand column on the table")
+        flags = _cabi.INDEX_TIE_BY_END if tie_by_end else 0
+        engine._check(engine.lib.giqlb_index_build(engine.ctx, layout.h, _ptr(t.codes), _ptr(t.start), _ptr(t.end),
+                                                  _ptr(strand), t.n, sadj, eadj, flags, ctypes.byref(self.h)))
+
+    def info(self):
+        d, ng, nb = ctypes.c_int64(), ctypes.c_int64(), ctypes.c_int32()
+        self.e.lib.giqlb_index_info(self.h, ctypes.byref(d), ctypes.byref(ng), ctypes.byref(nb), None)
+        return d.value, ng.value, nb.value
+
+    def free(self):
+        if self.h:
+            self.e.lib.giqlb_index_free(self.e.ctx, self.h)
+            self.h = ctypes.c_void_p()
+
+    def __del__(self):
+        try:
+            self.free()
+        except Exception:
+            pass
+
+
+class Engine:
+    """One engine per (process, device).  Work is enqueued on the torch stream current at construction."""
+
+    def __init__(self, device: int | str | torch.device | None = None):
+        self.lib = _cabi.load()   # raises EngineUnavailable when the extension is not built
+        if not torch.cuda.is_available():
+            raise EngineUnavailable("giql_b200 needs a CUDA device (sm_100a); there is no CPU fallback")
+        if device is None:
+            device = torch.cuda.current_device()
+        self.device = torch.device("cuda", device) if isinstance(device, int) else torch.device(device)
+        torch.cuda.set_device(self.device)
+        self.stream = torch.cuda.current_stream(self.device)
+        self.ctx = ctypes.c_void_p()
+        st = self.lib.giqlb_create(self.device.index or 0, ctypes.c_void_p(self.stream.cuda_stream), ctypes.byref(self.ctx))
+        if st != _cabi.OK:
+            raise EngineError(st, "giqlb_create failed")
+        self._strand_codes: dict[Any, int] = {"+": 0, "-": 1, ".": 2, "?": 3}
+
+    # ---- plumbing ---------------------------------------------------------------------------------
+    def _check(self, status: int):
+        _cabi.check(self.lib, self.ctx, status)
+
+    def close(self):
+        if getattr(self, "ctx", None):
+            self.lib.giqlb_destroy(self.ctx)
+            self.ctx = ctypes.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def sync(self):
+        self._check(self.lib.giqlb_sync(self.ctx))
+
+    def stats(self) -> dict:
+        s = _cabi.Stats()
+        self._check(self.lib.giqlb_stats(self.ctx, ctypes.byref(s)))
+        return {"rows_in": (s.rows_in[0], s.rows_in[1]), "rows_out": s.rows_out, "algorithmic_bytes": s.algorithmic_bytes,
+                "kernels_launched": s.kernels_launched, "kernels_total": s.kernels_total}
+
+    def kernels_total(self) -> int:
+        return self.stats()["kernels_total"]
+
+    def _dev(self, a: np.ndarray, pinned: bool = False) -> torch.Tensor:
+        t = torch.from_numpy(a)
+        if pinned:
+            t = t.pin_memory()
+        return t.to(self.device, non_blocking=pinned)
+
+    def _empty(self, n: int, dtype) -> torch.Tensor:
+        return torch.empty(max(int(n), 0), dtype=dtype, device=self.device)
+
+    # ---- ingest -----------------------------------------------------------------------------------
+    def strand_codes(self, col) -> np.ndarray:
+        """VARCHAR strand column -> uint8 codes ('+' 0, '-' 1, '.' 2, '?' 3, other literals 4.., NULL 255).
+
+        SQL semantics the codes preserve: ``a.strand = b.strand`` (nearest.py:328-329) is plain equality on
+        non-NULL values, NULL never equals anything; PARTITION BY strand (cluster.py:243-245) groups NULLs.
+        """
+        import pyarrow as pa
+
+        if isinstance(col, pa.ChunkedArray):
+            col = col.combine_chunks()
+        if not isinstance(col, pa.Array):
+            if hasattr(col, "to_numpy") and not isinstance(col, np.ndarray):
+                col = col.to_numpy()
+            col = pa.array(list(col) if not isinstance(col, np.ndarray) else col.astype(object), type=pa.string(), from_pandas=True)
+        if not pa.types.is_dictionary(col.type):
+            col = col.dictionary_encode()
+        values = col.dictionary.to_pylist()
+        lut = np.empty(len(values) + 1, dtype=np.uint8)
+        for i, v in enumerate(values):
+            if v not in self._strand_codes:
+                if len(self._strand_codes) >= 254:
+                    raise ValueError("more than 250 distinct strand literals")
+                self._strand_codes[v] = len(self._strand_codes)
+            lut[i] = self._strand_codes[v]
+        lut[len(values)] = _cabi.STRAND_NULL
+        idx = col.indices.fill_null(len(values)).to_numpy(zero_copy_only=False).astype(np.int64)
+        return lut[idx]
+
+    def table(self, data, config: Table | str | None = None, *, pinned: bool = False) -> DeviceTable:
+        """Upload one table.  ``data``: mapping / pandas DataFrame / pyarrow Table with the columns ``config``
+        names (reference column-mapping contract: src/giql/table.py:16-93; unregistered tables default to
+        chrom/start/end/strand, intersects_duckdb.py:1181-1188)."""
+        if isinstance(config, str):
+            config = Table(config)
+        cfg = config or Table("t")
+        get = (lambda k: data[k]) if not hasattr(data, "column") else (lambda k: data.column(k))
+        names = set(data.keys()) if hasattr(data, "keys") else set(getattr(data, "column_names", []))
+        start = _as_i32(get(cfg.start_col), cfg.start_col)
+        end = _as_i32(get(cfg.end_col), cfg.end_col)
+        if len(start) != len(end):
+            raise ValueError("start and end columns differ in length")
+        offs, byts = _as_utf8(get(cfg.chrom_col), cfg.chrom_col)
+        if len(offs) - 1 != len(start):
+            raise ValueError("chrom column length differs from start/end")
+        strand = None
+        if cfg.strand_col is not None and cfg.strand_col in names:
+            strand = self._dev(self.strand_codes(get(cfg.strand_col)), pinned)
+        return DeviceTable(self, len(start), config, self._dev(start, pinned), self._dev(end, pinned), strand,
+                           self._dev(offs, pinned), self._dev(byts, pinned))
+
+    def table_from_codes(self, codes, start, end, names: Sequence[str] | Dictionary, strand=None,
+                         config: Table | None = None) -> DeviceTable:
+        """Table whose chromosome column is already dictionary-encoded (``names`` sorted bytewise)."""
+        d = names if isinstance(names, Dictionary) else Dictionary(names)
+        if list(d.names) != sorted(d.names, key=lambda s: s.encode()):
+            raise ValueError("dictionary names must be sorted bytewise")
+
+        c = codes.to(self.device, torch.int32).contiguous() if isinstance(codes, torch.Tensor) else self._dev(_as_i32(codes, "codes"))
+        s = start.to(self.device, torch.int32).contiguous() if isinstance(start, torch.Tensor) else self._dev(_as_i32(start, "start"))
+        e = end.to(self.device, torch.int32).contiguous() if isinstance(end, torch.Tensor) else self._dev(_as_i32(end, "end"))
+        st = None
+        if strand is not None:
+            st = strand.to(self.device, torch.uint8).contiguous() if isinstance(strand, torch.Tensor) else self._dev(np.ascontiguousarray(strand, dtype=np.uint8))
+        return DeviceTable(self, int(s.numel()), config, s, e, st, None, None, codes=c, dictionary=d)
+
+    def encode(self, a: DeviceTable, b: Optional[DeviceTable] = None) -> Dictionary:
+        """Dictionary-encode the chromosome column(s) against ONE shared dictionary (giqlb_dict_encode)."""
+        if b is None or b is a:
+            if a.dictionary is not None:
+                return a.dictionary
+        elif a.dictionary is not None and a.dictionary is b.dictionary:
+            return a.dictionary
+        tabs = [a] if (b is None or b is a) else [a, b]
+        for t in tabs:
+            if t.chrom_offsets is None:
+                raise ValueError("tables encoded against different dictionaries cannot be combined; "
+                                 "build them with the same Dictionary or from string columns")
+        ca = self._empty(a.n, torch.int32)
+        cb = self._empty(tabs[-1].n, torch.int32) if len(tabs) == 2 else None
+        h = ctypes.c_void_p()
+        zero = ctypes.c_void_p()
+        t1 = tabs[-1] if len(tabs) == 2 else None
+        self._check(self.lib.giqlb_dict_encode(
+            self.ctx, _ptr(a.chrom_offsets), _ptr(a.chrom_bytes), a.n,
+            _ptr(t1.chrom_offsets) if t1 else zero, _ptr(t1.chrom_bytes) if t1 else zero, t1.n if t1 else 0,
+            _ptr(ca), _ptr(cb) if cb is not None else zero, ctypes.byref(h)))
+        try:
+            names = []
+            for code in range(self.lib.giqlb_dict_size(h)):
+                p, ln = ctypes.c_void_p(), ctypes.c_int32()
+                self.lib.giqlb_dict_get(h, code, ctypes.byref(p), ctypes.byref(ln))
+                names.append(ctypes.string_at(p, ln.value).decode("utf-8", "surrogateescape"))
+        finally:
+            self.lib.giqlb_dict_free(h)
+        d = Dictionary(names)
+        a.codes, a.dictionary = ca, d
+        if t1 is not None:
+            t1.codes, t1.dictionary = cb, d
+        return d
+
+    # ---- INTERSECTS -------------------------------------------------------------------------------
+    def _pair_indexes(self, a: DeviceTable, b: DeviceTable):
+        d = self.encode(a, b)
+        lay = _Layout(self, len(d))
+        lay.observe(a)
+        if b is not a:
+            lay.observe(b)
+        lay.finalize()
+        ia = _Index(self, lay, a)
+        ib = ia if b is a else _Index(self, lay, b)
+        return lay, ia, ib
+
+    def intersects(self, left: DeviceTable, right: DeviceTable) -> PairResult:
+        """Column-to-column INTERSECTS inner join -> (left_row, right_row) pairs.
+
+        reference: src/giql/expanders/intersects.py:149-154 (predicate) evaluated per chromosome by
+        src/giql/expanders/intersects_duckdb.py:1283-1299; bag semantics, unordered.
+        """
+        lay, il, ir = self._pair_indexes(left, right)
+        try:
+            plan, total = ctypes.c_void_p(), ctypes.c_int64()
+            self._check(self.lib.giqlb_intersects_plan(self.ctx, il.h, ir.h, ctypes.byref(plan), ctypes.byref(total)))
+            try:
+                out_l = self._empty(total.value, torch.int32)
+                out_r = self._empty(total.value, torch.int32)
+                self._check(self.lib.giqlb_intersects_emit(self.ctx, plan, _ptr(out_l), _ptr(out_r)))
+            finally:
+                self.lib.giqlb_joinplan_free(self.ctx, plan)
+            return PairResult(out_l, out_r)
+        finally:
+            il.free()
+            ir.free()
+            lay.free()
+
+    def _probe(self, fn, left: DeviceTable, right: DeviceTable, out: torch.Tensor):
+        d = self.encode(left, right)
+        lay = _Layout(self, len(d))
+        lay.observe(right)
+        lay.finalize()
+        ir = _Index(self, lay, right)
+        try:
+            sadj, eadj = left.offsets
+            self._check(fn(self.ctx, lay.h, _ptr(left.codes), _ptr(left.start), _ptr(left.end), left.n, sadj, eadj, ir.h, _ptr(out)))
+        finally:
+            ir.free()
+            lay.free()
+        return out
+
+    def exists(self, left: DeviceTable, right: DeviceTable) -> torch.Tensor:
+        """uint8[n_left]: 1 iff the left row overlaps at least one right row (the EXISTS of
+        intersects_duckdb.py:1254-1282)."""
+        return self._probe(self.lib.giqlb_intersects_exists, left, right, self._empty(left.n, torch.uint8))
+
+    def _select(self, flags: torch.Tensor, want: int) -> torch.Tensor:
+        out = self._empty(flags.numel(), torch.int32)
+        n_out = ctypes.c_int64()
+        self._check(self.lib.giqlb_select_rows(self.ctx, _ptr(flags), flags.numel(), want, _ptr(out), ctypes.byref(n_out)))
+        return out[: n_out.value]
+
+    def semi(self, left: DeviceTable, right: DeviceTable) -> torch.Tensor:
+        """SEMI JOIN: ids of left rows with >= 1 match, one per qualifying ROW, ascending
+        (intersects_duckdb.py:1254-1282, :1259-1262 no dedup)."""
+        return self._select(self.exists(left, right), 1)
+
+    def anti(self, left: DeviceTable, right: DeviceTable) -> torch.Tensor:
+        """ANTI JOIN: ids of left rows with no match; rows on chromosomes absent from ``right`` are kept
+        (partition rule intersects_duckdb.py:1317-1330, tests/test_duckdb_iejoin.py:5873-5919)."""
+        return self._select(self.exists(left, right), 0)
+
+    def count_overlaps(self, left: DeviceTable, right: DeviceTable) -> torch.Tensor:
+        """int64[n_left]: number of right rows overlapping each left row (count_overlaps fast path,
+        intersects_duckdb.py:432-548; the GROUP BY over distinct left keys is a host-side sum of these)."""
+        return self._probe(self.lib.giqlb_intersects_count_rows, left, right, self._empty(left.n, torch.int64))
+
+    # ---- DISTANCE ---------------------------------------------------------------------------------
+    def distance(self, a: DeviceTable, b: DeviceTable, a_rows: Optional[torch.Tensor] = None,
+                 b_rows: Optional[torch.Tensor] = None, stranded: bool = False, signed: bool = False):
+        """DISTANCE(a.interval, b.interval) for paired rows -> (int32 distance, uint8 valid[0 = SQL NULL]).
+
+        ``a_rows`` / ``b_rows`` select the paired rows (e.g. a join result); omitted = row i with row i.
+        reference: src/giql/expanders/_distance.py:67-117.  The stranded CASE is used only when both
+        tables carry a strand column (_distance.py:67).
+        """
+        self.encode(a, b)
+
+        def take(t, rows):
+            return t if rows is None or t is None else t.index_select(0, rows.to(torch.int64))
+
+        cols_a = [take(x, a_rows) for x in (a.codes, a.start, a.end, a.strand)]
+        cols_b = [take(x, b_rows) for x in (b.codes, b.start, b.end, b.strand)]
+        n = int(cols_a[1].numel())
+        if int(cols_b[1].numel()) != n:
+            raise ValueError("paired row selections differ in length")
+        use_strand = bool(stranded) and cols_a[3] is not None and cols_b[3] is not None
+        out = self._empty(n, torch.int32)
+        valid = self._empty(n, torch.uint8)
+        (asj, aej), (bsj, bej) = a.offsets, b.offsets
+        self._check(self.lib.giqlb_distance(
+            self.ctx, _ptr(cols_a[0]), _ptr(cols_a[1]), _ptr(cols_a[2]), _ptr(cols_a[3]) if use_strand else None,
+            _ptr(cols_b[0]), _ptr(cols_b[1]), _ptr(cols_b[2]), _ptr(cols_b[3]) if use_strand else None,
+            n, int(use_strand), int(bool(signed)), asj, aej, bsj, bej, _ptr(out), _ptr(valid)))
+        return out, valid

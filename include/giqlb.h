@@ -1,0 +1,177 @@
+/*
+ * giqlb.h — C ABI of libgiqlb200.so, the B200 (sm_100a) execution engine for GIQL's interval
+ * operators.  This is the drop-in boundary: the Python host layer (giql_b200/) binds exactly these
+ * symbols through ctypes, and a maintainer of the reference would bind the same symbols from an
+ * expander registered with @giql.register(B200Target, <Operator>).
+ *
+ * What each entry point replaces in the reference (abdenlab/giql; paths relative to its root).  The
+ * reference has no FFI of its own — it hands a SQL string to DuckDB — so "replaces" means "computes
+ * what DuckDB computes for the SQL emitted at":
+ *
+ *   giqlb_dict_encode          chrom VARCHAR equality / per-chrom partitioning
+ *                              src/giql/expanders/_per_chrom.py:27,46-74; intersects.py:151
+ *   giqlb_layout_* / giqlb_index_build
+ *                              the per-chromosome sort DuckDB's IE_JOIN performs for
+ *                              src/giql/expanders/intersects_duckdb.py:1283-1299; canonical ±1 offsets of
+ *                              src/giql/canonical.py:16-52 are applied here as integers
+ *   giqlb_intersects_plan/emit/join
+ *                              INNER branch  intersects_duckdb.py:1217-1238,1283-1299,1317-1334
+ *                              (= naive predicate src/giql/expanders/intersects.py:149-154)
+ *   giqlb_intersects_exists    SEMI / ANTI branch intersects_duckdb.py:1254-1282, partition rule :1317-1330
+ *   giqlb_intersects_count_rows  count_overlaps fast path intersects_duckdb.py:432-548, 806-854
+ *   giqlb_distance             src/giql/expanders/_distance.py:22-117 (== distance.py:126-239)
+ *   giqlb_nearest              src/giql/expanders/nearest.py:255-397 (LATERAL form)
+ *   giqlb_cluster              src/giql/expanders/cluster.py:205-310, 430-434
+ *   giqlb_merge                src/giql/expanders/merge.py:183-439
+ *   giqlb_disjoin_*            src/giql/expanders/disjoin.py:102-202
+ *
+ * Conventions
+ *   - Every function returns 0 (GIQLB_OK) or a negative giqlb_status.  giqlb_last_error(ctx) returns a
+ *     library-owned, context-local message.  The library never aborts and never frees caller memory.
+ *   - Pointers are DEVICE pointers owned by the caller (PyTorch tensors) unless the parameter name ends
+ *     in _host.  Work is enqueued on the context's stream; functions that return a host scalar
+ *     synchronise that stream, all others are asynchronous.
+ *   - One giqlb_ctx per (thread, device).  No global state; re-entrant across contexts.
+ *   - Row ids are int32 positions in the caller's input arrays (n < 2^31 per table); pair counts and
+ *     offsets are int64.  Coordinates are int32; canonical 0-based half-open after the *_adj offsets.
+ *   - NULL chrom/start/end are rejected by the host layer before upload (BED never has them).
+ */
+#ifndef GIQLB_H
+#define GIQLB_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define GIQLB_ABI_VERSION 1
+
+typedef enum giqlb_status {
+    GIQLB_OK = 0,
+    GIQLB_ERR_INVALID = -1,     /* bad argument */
+    GIQLB_ERR_CUDA = -2,        /* CUDA runtime error, see giqlb_last_error */
+    GIQLB_ERR_NOMEM = -3,
+    GIQLB_ERR_CAPACITY = -4,    /* caller's output buffer too small; required size returned */
+    GIQLB_ERR_RANGE = -5,       /* coordinates outside the layout / genome extent >= 2^32 */
+    GIQLB_ERR_INTERNAL = -6
+} giqlb_status;
+
+typedef struct giqlb_ctx giqlb_ctx;
+typedef struct giqlb_dict giqlb_dict;       /* shared chromosome dictionary (host strings, sorted bytewise) */
+typedef struct giqlb_layout giqlb_layout;   /* genome linearisation shared by the tables of one query */
+typedef struct giqlb_index giqlb_index;     /* one table sorted by linearised start, with carried row ids */
+typedef struct giqlb_joinplan giqlb_joinplan;
+
+/* strand codes used on the device (host layer maps VARCHAR -> code; SQL NULL never equals anything) */
+#define GIQLB_STRAND_PLUS 0
+#define GIQLB_STRAND_MINUS 1
+#define GIQLB_STRAND_DOT 2       /* '.'  -> stranded distance NULL */
+#define GIQLB_STRAND_QMARK 3     /* '?'  -> stranded distance NULL */
+#define GIQLB_STRAND_OTHER0 4    /* 4..254: other literal values, equality-comparable */
+#define GIQLB_STRAND_NULL 255
+
+/* per-call statistics of the most recent operation on a context */
+typedef struct giqlb_stats_t {
+    int64_t rows_in[2];
+    int64_t rows_out;
+    int64_t algorithmic_bytes;   /* SURVEY.md §8(d) formula for the operation */
+    int32_t kernels_launched;    /* kernels enqueued by the last API call */
+    int32_t reserved;
+    int64_t kernels_total;       /* kernels enqueued since giqlb_create */
+} giqlb_stats_t;
+
+int giqlb_abi_version(void);
+int giqlb_create(int device, void* cuda_stream, giqlb_ctx** out);
+int giqlb_destroy(giqlb_ctx* ctx);
+const char* giqlb_last_error(const giqlb_ctx* ctx);
+int giqlb_sync(giqlb_ctx* ctx);
+int giqlb_stats(const giqlb_ctx* ctx, giqlb_stats_t* out_host);
+
+/* ---- chromosome dictionary --------------------------------------------------------------------
+ * Arrow utf8 layout per table: int32 offsets[n+1], uint8 bytes[].  Builds ONE dictionary over both
+ * tables (n_r may be 0), order-preserving w.r.t. bytewise string order (merge.py:429-437 sorts VARCHAR),
+ * case-sensitive, any byte allowed (tests/test_duckdb_iejoin.py:3780-3810).  Writes int32 codes. */
+int giqlb_dict_encode(giqlb_ctx* ctx,
+                      const int32_t* offs_l, const uint8_t* bytes_l, int64_t n_l,
+                      const int32_t* offs_r, const uint8_t* bytes_r, int64_t n_r,
+                      int32_t* codes_l, int32_t* codes_r, giqlb_dict** out);
+int giqlb_dict_size(const giqlb_dict* d);
+int giqlb_dict_get(const giqlb_dict* d, int32_t code, const char** bytes_host, int32_t* len_host);
+int giqlb_dict_free(giqlb_dict* d);
+
+/* ---- genome layout ----------------------------------------------------------------------------
+ * Linearises (chrom code, position) into one uint32 coordinate: g = base[code] + 1 + (pos - lo[code]),
+ * with one guard cell either side of every chromosome (+ `pad` extra cells between chromosomes).
+ * observe() folds a table's per-chrom extent in (device reduction); finalize() fixes the bases and
+ * synchronises (returns GIQLB_ERR_RANGE when the summed extent does not fit 32 bits).  Every table that
+ * will be INDEXED on the layout must be observed first; tables that only PROBE an index
+ * (giqlb_intersects_exists / _count_rows / giqlb_nearest queries) need not be. */
+int giqlb_layout_create(giqlb_ctx* ctx, int32_t n_codes, int64_t pad, giqlb_layout** out);
+int giqlb_layout_observe(giqlb_ctx* ctx, giqlb_layout* lay, const int32_t* code, const int32_t* start,
+                         const int32_t* end, int64_t n, int32_t start_adj, int32_t end_adj);
+int giqlb_layout_finalize(giqlb_ctx* ctx, giqlb_layout* lay);
+int giqlb_layout_free(giqlb_ctx* ctx, giqlb_layout* lay);
+int giqlb_layout_info(const giqlb_layout* lay, int32_t* n_codes, uint64_t* total_extent, int32_t* key_bits);
+/* device views of base[n_codes+1] (uint32), lo[n_codes], hi[n_codes] (int32; hi < lo for unseen codes) */
+int giqlb_layout_tables(const giqlb_layout* lay, const uint32_t** base_dev, const int32_t** lo_dev,
+                        const int32_t** hi_dev);
+
+/* ---- sorted index -----------------------------------------------------------------------------
+ * LSD radix sort of the linearised start with carried row ids; then gathers the linearised end.
+ * strand may be NULL.  start_adj/end_adj are the canonical.py:16-52 offsets (raw + adj = canonical).
+ * flags: GIQLB_INDEX_TIE_BY_END orders equal starts by end (NEAREST's ORDER BY start, end). */
+#define GIQLB_INDEX_TIE_BY_END 1
+int giqlb_index_build(giqlb_ctx* ctx, const giqlb_layout* lay, const int32_t* code, const int32_t* start,
+                      const int32_t* end, const uint8_t* strand, int64_t n, int32_t start_adj,
+                      int32_t end_adj, int flags, giqlb_index** out);
+int giqlb_index_free(giqlb_ctx* ctx, giqlb_index* ix);
+int64_t giqlb_index_rows(const giqlb_index* ix);
+/* device views of the sorted columns (library-owned, valid until giqlb_index_free) */
+int giqlb_index_columns(const giqlb_index* ix, const uint32_t** gstart, const uint32_t** gend,
+                        const int32_t** row_id, const uint8_t** strand);
+/* rows with end <= start / end < start; strand blocks after giqlb_index_group_by_strand */
+int giqlb_index_info(const giqlb_index* ix, int64_t* n_degenerate, int64_t* n_negative, int32_t* n_blocks,
+                     int64_t* block_off_host /* [257] or NULL */);
+/* reorders the index into blocks of equal strand code, each still sorted by start (CLUSTER/MERGE/NEAREST
+ * with stranded := true) */
+int giqlb_index_group_by_strand(giqlb_ctx* ctx, giqlb_index* ix);
+
+/* ---- INTERSECTS inner join --------------------------------------------------------------------
+ * plan(): count pass; returns the exact number of pairs (host).  emit(): fills out_l/out_r (int32 row
+ * ids, total entries).  join(): plan + emit without a host round trip when capacity suffices; returns
+ * GIQLB_ERR_CAPACITY (and the required total) otherwise.  Pair order is unspecified (multiset).
+ * The indexes are not const: derived arrays (running max of end) are cached on them on demand. */
+int giqlb_intersects_plan(giqlb_ctx* ctx, giqlb_index* L, giqlb_index* R, giqlb_joinplan** out,
+                          int64_t* total_host);
+int giqlb_intersects_emit(giqlb_ctx* ctx, giqlb_joinplan* plan, int32_t* out_l, int32_t* out_r);
+int giqlb_joinplan_free(giqlb_ctx* ctx, giqlb_joinplan* plan);
+int giqlb_intersects_join(giqlb_ctx* ctx, giqlb_index* L, giqlb_index* R, int32_t* out_l, int32_t* out_r,
+                          int64_t capacity, int64_t* total_host);
+
+/* SEMI/ANTI: exists_by_row[i] = 1 iff left input row i has >= 1 match (uint8[n]).  The left table is
+ * probed from its raw columns in input order (no index, no sort).  giqlb_select_rows compacts the row ids
+ * with flag == want (ascending) and returns how many. */
+int giqlb_intersects_exists(giqlb_ctx* ctx, const giqlb_layout* lay, const int32_t* code, const int32_t* start,
+                            const int32_t* end, int64_t n, int32_t start_adj, int32_t end_adj, giqlb_index* R,
+                            uint8_t* exists_by_row);
+int giqlb_select_rows(giqlb_ctx* ctx, const uint8_t* flags, int64_t n, int want, int32_t* out_rows,
+                      int64_t* n_out_host);
+/* count_overlaps: counts_by_row[i] = number of right rows overlapping left input row i (int64[n]) */
+int giqlb_intersects_count_rows(giqlb_ctx* ctx, const giqlb_layout* lay, const int32_t* code, const int32_t* start,
+                                const int32_t* end, int64_t n, int32_t start_adj, int32_t end_adj, giqlb_index* R,
+                                int64_t* counts_by_row);
+
+/* ---- DISTANCE (elementwise over already-paired rows) ------------------------------------------
+ * out[i] = distance, valid[i] = 0 for SQL NULL.  strands may be NULL when !stranded.  *_adj are the
+ * canonical offsets of table a and table b. */
+int giqlb_distance(giqlb_ctx* ctx, const int32_t* a_code, const int32_t* a_start, const int32_t* a_end,
+                   const uint8_t* a_strand, const int32_t* b_code, const int32_t* b_start,
+                   const int32_t* b_end, const uint8_t* b_strand, int64_t n, int stranded, int signed_,
+                   int32_t a_start_adj, int32_t a_end_adj, int32_t b_start_adj, int32_t b_end_adj,
+                   int32_t* out, uint8_t* valid);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GIQLB_H */

@@ -1,0 +1,109 @@
+"""The CPU oracle pinned against the reference's own golden vectors (no GPU).
+
+Sources (all harvested by tests/golden/harvest_reference_vectors.py from /root/reference):
+  * tests/integration/datafusion/test_cross_target_oracle.py — 54 (query, data, expected) triples
+  * tests/test_distance_udf.py — scalar DISTANCE known answers
+  * src/giql/expanders/_distance.py:22-117 executed on SQLite over an input grid
+  * tests/test_duckdb_iejoin.py:107-142 — peaks x genes expected overlaps
+"""
+import json
+
+import numpy as np
+import pytest
+
+from golden_cases import GOLDEN, Unsupported, load_cases, normalise, run_case
+from backends import OracleBackend
+from oracle import giql_oracle as go
+from oracle import sqlite_oracle as so
+
+CASES = load_cases()
+
+
+class _Oracle(OracleBackend):
+    def range_filter(self, t, op, ranges, cfg):
+        from backends import canonicalise
+
+        tc = canonicalise(t, cfg)
+        (c, s, e), = ranges
+        out = []
+        for tc_, ts, te in zip(tc["chrom"], tc["start"], tc["end"]):
+            if op == "contains":      # intersects.py:108-118: start <= lit.start AND end >= lit.end
+                out.append(tc_ == c and ts <= s and te >= e)
+            else:                     # within, intersects.py:119-129
+                out.append(tc_ == c and ts >= s and te <= e)
+        return out
+
+
+@pytest.mark.parametrize("case", CASES, ids=[f"{i}:{c['test']}" for i, c in enumerate(CASES)])
+def test_cross_target_golden(case):
+    if "expected" not in case or isinstance(case["expected"], dict):
+        pytest.skip("reference test has no literal expected rows")
+    rows = run_case(case, _Oracle())
+    assert normalise(rows) == normalise(case["expected"]), case["source"]
+
+
+def test_distance_known_answers():
+    ka = json.loads((GOLDEN / "distance_known_answers.json").read_text())
+    assert len(ka) >= 20
+    for k in ka:
+        a, b = k["a"], k["b"]
+        stranded = k["stranded"] and a["has_strand"] and b["has_strand"]
+        got = go.distance(a["chrom"], a["start"], a["end"], a["strand"], b["chrom"], b["start"], b["end"], b["strand"],
+                          stranded=stranded, signed=k["signed"])
+        assert got == k["expected"], k["source"]
+
+
+def test_distance_matches_reference_case_on_sqlite_grid():
+    grid = json.loads((GOLDEN / "distance_reference_case_grid.json").read_text())
+    rows = grid["rows"]
+    assert len(rows) > 1000
+    for ac, as_, ae, ast, bc, bs, be, bst, stranded, signed, exp in rows:
+        got = go.distance(ac, as_, ae, ast, bc, bs, be, bst, stranded=bool(stranded), signed=bool(signed))
+        assert got == exp, (ac, as_, ae, ast, bc, bs, be, bst, stranded, signed)
+
+
+def test_iejoin_peaks_genes_fixture():
+    g = json.loads((GOLDEN / "iejoin_peaks_genes.json").read_text())
+    def tab(rows):
+        return {"chrom": [r[0] for r in rows], "start": [r[1] for r in rows], "end": [r[2] for r in rows]}
+    P, G = tab(g["peaks"]), tab(g["genes"])
+    pairs = go.join_pairs(P, G)
+    got = sorted((P["chrom"][i], P["start"][i], P["end"][i], G["chrom"][j], G["start"][j], G["end"][j]) for i, j in pairs)
+    assert got == sorted(tuple(r) for r in g["expected_overlaps"])
+
+
+def _random_table(rng, n, chroms=("chr1", "chr2", "chrX"), span=400, max_len=60, zero_width=False, strands=None):
+    start = rng.integers(0, span, size=n)
+    length = rng.integers(0 if zero_width else 1, max_len, size=n)
+    t = {"chrom": [chroms[i] for i in rng.integers(0, len(chroms), size=n)], "start": start.tolist(), "end": (start + length).tolist()}
+    if strands:
+        t["strand"] = [strands[i] for i in rng.integers(0, len(strands), size=n)]
+    return t
+
+
+@pytest.mark.parametrize("seed", range(6))
+def test_oracle_agrees_with_sqlite_and_bruteforce(seed):
+    """Second, independent oracle: the reference's SQL text shapes on stdlib SQLite (not DuckDB)."""
+    rng = np.random.default_rng(seed)
+    L, R = _random_table(rng, 60, zero_width=seed % 2 == 1), _random_table(rng, 50, zero_width=seed % 2 == 1)
+    fast = [tuple(map(int, p)) for p in go.join_pairs(L, R)]
+    assert fast == go.join_pairs_bruteforce(L, R)
+    assert fast == so.intersects_pairs(L, R)
+    assert sorted(go.semi_rows(L, R).tolist()) == so.semi_anti_rows(L, R, anti=False)
+    assert sorted(go.anti_rows(L, R).tolist()) == so.semi_anti_rows(L, R, anti=True)
+
+
+@pytest.mark.parametrize("seed", range(4))
+def test_c_oracle_agrees_with_python_oracle(seed, c_oracle):
+    rng = np.random.default_rng(100 + seed)
+    L, R = _random_table(rng, 300, span=3000), _random_table(rng, 280, span=3000)
+    names = sorted(set(L["chrom"]) | set(R["chrom"]))
+    code = {c: i for i, c in enumerate(names)}
+    lc, rc = [code[c] for c in L["chrom"]], [code[c] for c in R["chrom"]]
+    got = c_oracle.intersects_pairs(lc, L["start"], L["end"], rc, R["start"], R["end"], len(names))
+    exp = go.join_pairs(L, R)
+    assert np.array_equal(got, exp)
+    ex = c_oracle.intersects_exists(lc, L["start"], L["end"], rc, R["start"], R["end"], len(names))
+    assert np.array_equal(np.nonzero(ex)[0], go.semi_rows(L, R))
+    ids = c_oracle.cluster(lc, L["start"], L["end"], len(names), distance=5)
+    assert ids.tolist() == go.cluster(L, distance=5)
