@@ -56,6 +56,8 @@ PROTOTYPES = {
     "giqlb_last_error": (c_char_p, [_P]),
     "giqlb_sync": (c_int, [_P]),
     "giqlb_stats": (c_int, [_P, POINTER(Stats)]),
+    "giqlb_profile_enable": (c_int, [_P, c_int]),
+    "giqlb_profile_read": (c_int, [_P, POINTER(ctypes.c_double), POINTER(c_int64)]),
     "giqlb_dict_encode": (c_int, [_P, _P, _P, c_int64, _P, _P, c_int64, _P, _P, POINTER(_P)]),
     "giqlb_dict_size": (c_int, [_P]),
     "giqlb_dict_get": (c_int, [_P, c_int32, POINTER(_P), POINTER(c_int32)]),
@@ -82,6 +84,9 @@ PROTOTYPES = {
     "giqlb_distance": (c_int, [_P, _P, _P, _P, _P, _P, _P, _P, _P, c_int64, c_int, c_int,
                                c_int32, c_int32, c_int32, c_int32, _P, _P]),
 }
+
+PHASES = ["dict", "layout", "keygen", "sort_hist", "sort_pass", "gather", "scan_max", "join_count", "join_scan",
+          "join_emit", "probe", "select", "distance", "cluster", "merge", "nearest", "other"]
 
 _lib = None
 

@@ -26,6 +26,43 @@ struct giqlb_ctx {
     int* d_err = nullptr;           // device int[4]: sticky kernel-side error flags ([0] look-back spin limit)
     giqlb_stats_t stats = {};
     int32_t launches_this_call = 0;
+    // per-phase CUDA-event profiling (giqlb_profile_*): pairs of events recorded around kernel launches
+    bool prof_enabled = false;
+    struct ProfSpan { int phase; cudaEvent_t start, stop; };
+    std::vector<ProfSpan> prof_spans;
+    std::vector<cudaEvent_t> prof_free_events;
+    double prof_ms[GIQLB_PH_COUNT] = {0};
+    int64_t prof_launches[GIQLB_PH_COUNT] = {0};
+};
+
+// RAII span: records an event pair on the context's stream around the launches made while it is alive.
+struct PhaseSpan {
+    giqlb_ctx* ctx;
+    int phase;
+    cudaEvent_t start = nullptr, stop = nullptr;
+    int launches_before;
+    static cudaEvent_t get_event(giqlb_ctx* c) {
+        if (!c->prof_free_events.empty()) {
+            cudaEvent_t e = c->prof_free_events.back();
+            c->prof_free_events.pop_back();
+            return e;
+        }
+        cudaEvent_t e = nullptr;
+        cudaEventCreate(&e);
+        return e;
+    }
+    PhaseSpan(giqlb_ctx* c, int ph) : ctx(c), phase(ph), launches_before(c->launches_this_call) {
+        if (!c->prof_enabled) return;
+        start = get_event(c);
+        stop = get_event(c);
+        cudaEventRecord(start, c->stream);
+    }
+    ~PhaseSpan() {
+        if (!start) return;
+        cudaEventRecord(stop, ctx->stream);
+        ctx->prof_spans.push_back({phase, start, stop});
+        ctx->prof_launches[phase] += ctx->launches_this_call - launches_before;
+    }
 };
 
 struct giqlb_dict {

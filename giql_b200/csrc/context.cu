@@ -49,6 +49,8 @@ extern "C" int giqlb_destroy(giqlb_ctx* ctx) {
     if (!ctx) return GIQLB_OK;
     cudaSetDevice(ctx->device);
     if (ctx->stream) cudaStreamSynchronize(ctx->stream);
+    for (auto& sp : ctx->prof_spans) { cudaEventDestroy(sp.start); cudaEventDestroy(sp.stop); }
+    for (auto e : ctx->prof_free_events) cudaEventDestroy(e);
     if (ctx->h_scalars) cudaFreeHost(ctx->h_scalars);
     if (ctx->d_scalars) cudaFree(ctx->d_scalars);
     if (ctx->d_err) cudaFree(ctx->d_err);
@@ -71,6 +73,31 @@ extern "C" int giqlb_sync(giqlb_ctx* ctx) {
 extern "C" int giqlb_stats(const giqlb_ctx* ctx, giqlb_stats_t* out_host) {
     if (!ctx || !out_host) return GIQLB_ERR_INVALID;
     *out_host = ctx->stats;
+    return GIQLB_OK;
+}
+
+extern "C" int giqlb_profile_enable(giqlb_ctx* ctx, int on) {
+    if (!ctx) return GIQLB_ERR_INVALID;
+    ctx->prof_enabled = on != 0;
+    return GIQLB_OK;
+}
+
+extern "C" int giqlb_profile_read(giqlb_ctx* ctx, double* ms_host, int64_t* launches_host) {
+    if (!ctx) return GIQLB_ERR_INVALID;
+    CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    for (auto& sp : ctx->prof_spans) {
+        float ms = 0.f;
+        if (cudaEventElapsedTime(&ms, sp.start, sp.stop) == cudaSuccess) ctx->prof_ms[sp.phase] += ms;
+        ctx->prof_free_events.push_back(sp.start);
+        ctx->prof_free_events.push_back(sp.stop);
+    }
+    ctx->prof_spans.clear();
+    for (int i = 0; i < GIQLB_PH_COUNT; i++) {
+        if (ms_host) ms_host[i] += ctx->prof_ms[i];
+        if (launches_host) launches_host[i] += ctx->prof_launches[i];
+        ctx->prof_ms[i] = 0;
+        ctx->prof_launches[i] = 0;
+    }
     return GIQLB_OK;
 }
 
@@ -126,6 +153,7 @@ struct OutCompact {
 // out has n + 1 entries; out[n] (and *total_dev when given) receive the grand total.
 int giqlb_excl_scan_u64(giqlb_ctx* ctx, const unsigned long long* in, unsigned long long* out, int64_t n,
                         unsigned long long* total_dev) {
+    PhaseSpan ps(ctx, GIQLB_PH_JOIN_SCAN);
     excl_scan_u64_kernel<<<1, XS_THREADS, 0, ctx->stream>>>(in, out, n, total_dev);
     LAUNCH_CHECK(ctx);
     return GIQLB_OK;
@@ -135,6 +163,7 @@ int giqlb_excl_scan_u64(giqlb_ctx* ctx, const unsigned long long* in, unsigned l
 int giqlb_incl_scan_max_u32(giqlb_ctx* ctx, const uint32_t* in, uint32_t* out, int64_t n,
                             const int64_t* h_block_off, int n_blocks) {
     using namespace giqlb_scan;
+    PhaseSpan ps(ctx, GIQLB_PH_SCAN_MAX);
     if (!h_block_off || n_blocks <= 1) return launch_scan<OpMaxU32>(ctx, n, InU32{in}, OutInclMax{out});
     for (int b = 0; b < n_blocks; b++) {
         int64_t lo = h_block_off[b], hi = h_block_off[b + 1];
@@ -150,7 +179,10 @@ extern "C" int giqlb_select_rows(giqlb_ctx* ctx, const uint8_t* flags, int64_t n
     begin_call(ctx);
     unsigned long long* total = reinterpret_cast<unsigned long long*>(ctx->d_scalars + 8);
     CUDA_TRY(ctx, cudaMemsetAsync(total, 0, 8, ctx->stream));
-    GIQLB_TRY((launch_scan<OpAddU64>(ctx, n, InFlagEq{flags, want}, OutCompact{out_rows, total, n})));
+    {
+        PhaseSpan ps(ctx, GIQLB_PH_SELECT);
+        GIQLB_TRY((launch_scan<OpAddU64>(ctx, n, InFlagEq{flags, want}, OutCompact{out_rows, total, n})));
+    }
     if (n_out_host) {
         GIQLB_TRY(fetch_scalars(ctx, total, 1));
         *n_out_host = ctx->h_scalars[0];

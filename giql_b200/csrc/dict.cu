@@ -131,6 +131,7 @@ extern "C" int giqlb_dict_encode(giqlb_ctx* ctx, const int32_t* offs_l, const ui
         if (st != GIQLB_OK) break;
         cudaMemsetAsync(slots, 0, (size_t)cap * 8, ctx->stream);
         cudaMemsetAsync(cursor, 0, 3 * 8, ctx->stream);
+        PhaseSpan ps(ctx, GIQLB_PH_DICT);
         dict_insert_kernel<<<grid, 256, 0, ctx->stream>>>(A, B, slots, cap - 1, codes_l, codes_r, n_distinct);
         ctx->launches_this_call++;
         ctx->stats.kernels_total++;
@@ -162,6 +163,7 @@ extern "C" int giqlb_dict_encode(giqlb_ctx* ctx, const int32_t* offs_l, const ui
         if (st == GIQLB_OK && !ent_len) st = dev_alloc(ctx, &ent_len, (size_t)distinct);
         if (st != GIQLB_OK) break;
         cudaMemsetAsync(cursor, 0, 2 * 8, ctx->stream);
+        PhaseSpan ps(ctx, GIQLB_PH_DICT);
         dict_collect_kernel<<<(cap + 255) / 256, 256, 0, ctx->stream>>>(A, B, slots, cap, name_buf, name_cap, cursor, ent_slot,
                                                                         ent_off, ent_len, (uint32_t)distinct);
         ctx->launches_this_call++;
@@ -208,6 +210,7 @@ extern "C" int giqlb_dict_encode(giqlb_ctx* ctx, const int32_t* offs_l, const ui
         st = dev_alloc(ctx, &slot2code, (size_t)cap);
         if (st == GIQLB_OK) {
             cudaMemcpyAsync(slot2code, h_s2c.data(), (size_t)cap * 4, cudaMemcpyHostToDevice, ctx->stream);
+            PhaseSpan ps(ctx, GIQLB_PH_DICT);
             if (n_l > 0) {
                 dict_remap_kernel<<<grid, 256, 0, ctx->stream>>>(codes_l, n_l, slot2code);
                 ctx->launches_this_call++;

@@ -47,6 +47,7 @@ extern "C" int giqlb_distance(giqlb_ctx* ctx, const int32_t* a_code, const int32
     if (n > 0) {
         int64_t blocks = ceil_div(n, 256 * 4);
         int64_t cap = (int64_t)ctx->sm_count * 16;
+        PhaseSpan ps(ctx, GIQLB_PH_DISTANCE);
         distance_kernel<<<(unsigned)(blocks < cap ? blocks : cap), 256, 0, ctx->stream>>>(
             a_code, a_start, a_end, a_strand, b_code, b_start, b_end, b_strand, n, stranded, signed_, a_start_adj, a_end_adj,
             b_start_adj, b_end_adj, out, valid);

@@ -211,6 +211,7 @@ extern "C" int giqlb_layout_create(giqlb_ctx* ctx, int32_t n_codes, int64_t pad,
         return st;
     }
     if (n_codes > 0) {
+        PhaseSpan ps(ctx, GIQLB_PH_LAYOUT);
         layout_init_kernel<<<(n_codes + 255) / 256, 256, 0, ctx->stream>>>((long long*)lay->d_lohi, n_codes);
         LAUNCH_CHECK(ctx);
     }
@@ -225,6 +226,7 @@ extern "C" int giqlb_layout_observe(giqlb_ctx* ctx, giqlb_layout* lay, const int
     begin_call(ctx);
     if (n > 0) {
         if (lay->n_codes == 0) return giqlb_fail(ctx, GIQLB_ERR_INVALID, "layout_observe: rows given but the dictionary is empty");
+        PhaseSpan ps(ctx, GIQLB_PH_LAYOUT);
         layout_observe_kernel<<<grid_for(ctx, n, LY_THREADS * 8, 8), LY_THREADS, 0, ctx->stream>>>(
             code, start, end, n, lay->n_codes, start_adj, end_adj, (long long*)lay->d_lohi, ctx->d_err);
         LAUNCH_CHECK(ctx);
@@ -237,9 +239,12 @@ extern "C" int giqlb_layout_finalize(giqlb_ctx* ctx, giqlb_layout* lay) {
     if (lay->finalized) return GIQLB_OK;
     begin_call(ctx);
     unsigned long long* total = reinterpret_cast<unsigned long long*>(ctx->d_scalars);
-    layout_finalize_kernel<<<1, 1024, 0, ctx->stream>>>((const long long*)lay->d_lohi, lay->n_codes, (long long)lay->pad,
-                                                        lay->d_base, lay->d_lo32, lay->d_hi32, total);
-    LAUNCH_CHECK(ctx);
+    {
+        PhaseSpan ps(ctx, GIQLB_PH_LAYOUT);
+        layout_finalize_kernel<<<1, 1024, 0, ctx->stream>>>((const long long*)lay->d_lohi, lay->n_codes, (long long)lay->pad,
+                                                            lay->d_base, lay->d_lo32, lay->d_hi32, total);
+        LAUNCH_CHECK(ctx);
+    }
     int h_err[4] = {0, 0, 0, 0};
     CUDA_TRY(ctx, cudaMemcpyAsync(ctx->h_scalars, total, 8, cudaMemcpyDeviceToHost, ctx->stream));
     lay->h_lo.assign(lay->n_codes, 0);
@@ -383,10 +388,13 @@ extern "C" int giqlb_index_build(giqlb_ctx* ctx, const giqlb_layout* lay, const 
     IB_CUDA(cudaMemsetAsync(counters, 0, 3 * 8, ctx->stream));
     if (n > 0) {
         int result_in_b = 0;
+        {
+        PhaseSpan ps(ctx, GIQLB_PH_KEYGEN);
         index_keygen_kernel<<<grid_for(ctx, n, 256 * 4, 8), 256, 0, ctx->stream>>>(
             code, start, end, n, lay->n_codes, start_adj, end_adj, lay->d_base, lay->d_lo32, lay->d_hi32, ka, ge_u, counters);
         ctx->launches_this_call++;
         ctx->stats.kernels_total++;
+        }
         IB_CUDA(cudaGetLastError());
         if (ix->tie_by_end) {
             // LSD over the compound key (start, end): sort by end first, then stably by start
@@ -397,6 +405,7 @@ extern "C" int giqlb_index_build(giqlb_ctx* ctx, const giqlb_layout* lay, const 
             uint32_t* rid1 = result_in_b ? vb : va;
             uint32_t* k2 = result_in_b ? ka : kb;   // the buffer pair NOT holding the result becomes the next input
             uint32_t* v2 = result_in_b ? va : vb;
+            PhaseSpan ps(ctx, GIQLB_PH_GATHER);
             gather_kernel<uint32_t><<<grid_for(ctx, n, 256 * 4, 8), 256, 0, ctx->stream>>>(gs_u, rid1, k2, n);
             ctx->launches_this_call++;
             ctx->stats.kernels_total++;
@@ -419,6 +428,7 @@ extern "C" int giqlb_index_build(giqlb_ctx* ctx, const giqlb_layout* lay, const 
             ix->gs = ka; ix->rid = reinterpret_cast<int32_t*>(va);
             ka = nullptr; va = nullptr;
         }
+        PhaseSpan ps_g(ctx, GIQLB_PH_GATHER);
         gather_kernel<uint32_t><<<grid_for(ctx, n, 256 * 4, 8), 256, 0, ctx->stream>>>(
             ge_u, reinterpret_cast<const uint32_t*>(ix->rid), ix->ge, n);
         ctx->launches_this_call++;

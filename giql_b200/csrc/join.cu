@@ -354,11 +354,13 @@ static int plan_enqueue(giqlb_ctx* ctx, giqlb_index* L, giqlb_index* R, giqlb_jo
         if (p->general) {
             st = giqlb_index_ensure_pmax(ctx, R);
             if (st == GIQLB_OK) {
+                PhaseSpan ps(ctx, GIQLB_PH_JOIN_COUNT);
                 join_count_tiles_general_kernel<<<(unsigned)n_tiles, JB, 0, ctx->stream>>>(side_of(L), side_of(R), R->pmax, cnt);
                 ctx->launches_this_call++;
                 ctx->stats.kernels_total++;
             }
         } else {
+            PhaseSpan ps(ctx, GIQLB_PH_JOIN_COUNT);
             join_count_tiles_kernel<<<(unsigned)n_tiles, JB, 0, ctx->stream>>>(side_of(L), side_of(R), p->tiles_a, cnt);
             ctx->launches_this_call++;
             ctx->stats.kernels_total++;
@@ -378,6 +380,7 @@ static int plan_enqueue(giqlb_ctx* ctx, giqlb_index* L, giqlb_index* R, giqlb_jo
 static int emit_enqueue(giqlb_ctx* ctx, giqlb_joinplan* p, int32_t* out_l, int32_t* out_r, int64_t capacity) {
     const int64_t n_tiles = p->tiles_a + p->tiles_b;
     if (n_tiles == 0) return GIQLB_OK;
+    PhaseSpan ps(ctx, GIQLB_PH_JOIN_EMIT);
     if (p->general) {
         join_emit_general_kernel<<<(unsigned)n_tiles, JB, 0, ctx->stream>>>(side_of(p->L), side_of(p->R), p->R->pmax, n_tiles,
                                                                             p->tile_off, out_l, out_r, capacity);
@@ -458,6 +461,7 @@ extern "C" int giqlb_intersects_exists(giqlb_ctx* ctx, const giqlb_layout* lay, 
     if (n > 0) {
         int64_t blocks = ceil_div(n, 256 * 4);
         int64_t cap = (int64_t)ctx->sm_count * 16;
+        PhaseSpan ps(ctx, GIQLB_PH_PROBE);
         probe_exists_kernel<<<(unsigned)(blocks < cap ? blocks : cap), 256, 0, ctx->stream>>>(P, R->gs, R->pmax, R->n, exists_by_row);
         LAUNCH_CHECK(ctx);
     }
@@ -483,6 +487,7 @@ extern "C" int giqlb_intersects_count_rows(giqlb_ctx* ctx, const giqlb_layout* l
     if (n > 0) {
         int64_t blocks = ceil_div(n, 256 * 4);
         int64_t cap = (int64_t)ctx->sm_count * 16;
+        PhaseSpan ps(ctx, GIQLB_PH_PROBE);
         probe_count_kernel<<<(unsigned)(blocks < cap ? blocks : cap), 256, 0, ctx->stream>>>(
             P, R->gs, R->ge, R->pmax, R->ge_sorted, R->n, r_deg, (long long*)counts_by_row);
         LAUNCH_CHECK(ctx);

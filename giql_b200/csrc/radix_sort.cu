@@ -204,11 +204,15 @@ int giqlb_radix_sort_pairs_u32(giqlb_ctx* ctx, uint32_t* keys_a, uint32_t* vals_
 
     int64_t hb_want = ceil_div(n, RS_THREADS * 16), hb_cap = (int64_t)ctx->sm_count * 8;
     int hist_blocks = (int)(hb_want < hb_cap ? hb_want : hb_cap);
-    rs_histogram_kernel<<<hist_blocks, RS_THREADS, 0, ctx->stream>>>(keys_a, n, begin_bit, n_passes, ghist);
-    LAUNCH_CHECK(ctx);
+    {
+        PhaseSpan ps(ctx, GIQLB_PH_SORT_HIST);
+        rs_histogram_kernel<<<hist_blocks, RS_THREADS, 0, ctx->stream>>>(keys_a, n, begin_bit, n_passes, ghist);
+        LAUNCH_CHECK(ctx);
+    }
 
     uint32_t *kin = keys_a, *vin = vals_a, *kout = keys_b, *vout = vals_b;
     for (int p = 0; p < n_passes; p++) {
+        PhaseSpan ps(ctx, GIQLB_PH_SORT_PASS);
         const int shift = begin_bit + 8 * p;
         const uint32_t* gh = ghist + (size_t)p * RS_RADIX;
         uint32_t* st = status + (size_t)p * tiles * RS_RADIX;

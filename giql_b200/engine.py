@@ -250,6 +250,17 @@ class Engine:
         return {"rows_in": (s.rows_in[0], s.rows_in[1]), "rows_out": s.rows_out, "algorithmic_bytes": s.algorithmic_bytes,
                 "kernels_launched": s.kernels_launched, "kernels_total": s.kernels_total}
 
+    def profile(self, on: bool = True):
+        """Record CUDA events around every kernel group (see giqlb_profile_enable)."""
+        self._check(self.lib.giqlb_profile_enable(self.ctx, int(on)))
+
+    def profile_read(self) -> dict:
+        """{phase: (device ms, kernel launches)} accumulated since the previous read; synchronises."""
+        ms = (ctypes.c_double * len(_cabi.PHASES))()
+        ln = (ctypes.c_int64 * len(_cabi.PHASES))()
+        self._check(self.lib.giqlb_profile_read(self.ctx, ms, ln))
+        return {name: (ms[i], ln[i]) for i, name in enumerate(_cabi.PHASES)}
+
     def kernels_total(self) -> int:
         return self.stats()["kernels_total"]
 
@@ -312,6 +323,24 @@ class Engine:
             strand = self._dev(self.strand_codes(get(cfg.strand_col)), pinned)
         return DeviceTable(self, len(start), config, self._dev(start, pinned), self._dev(end, pinned), strand,
                            self._dev(offs, pinned), self._dev(byts, pinned))
+
+    def table_from_buffers(self, chrom_offsets, chrom_bytes, start, end, strand=None,
+                           config: Table | None = None) -> DeviceTable:
+        """Table from columnar HOST buffers already in Arrow layout (utf8 offsets int32[n+1] + bytes, int32
+        start/end, optional uint8 strand codes): numpy arrays or (pinned) torch tensors.  Only copies — no
+        per-row Python work — so it is the ingest path for large inputs."""
+        def dev(x, dt):
+            t = x if isinstance(x, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(x))
+            if t.dtype != dt:
+                raise ValueError(f"expected dtype {dt}, got {t.dtype}")
+            return t.to(self.device, non_blocking=True)
+
+        offs = dev(chrom_offsets, torch.int32)
+        s, e = dev(start, torch.int32), dev(end, torch.int32)
+        if offs.numel() != s.numel() + 1 or e.numel() != s.numel():
+            raise ValueError("column lengths disagree")
+        return DeviceTable(self, int(s.numel()), config, s, e, None if strand is None else dev(strand, torch.uint8),
+                           offs, dev(chrom_bytes, torch.uint8))
 
     def table_from_codes(self, codes, start, end, names: Sequence[str] | Dictionary, strand=None,
                          config: Table | None = None) -> DeviceTable:

@@ -81,12 +81,39 @@ typedef struct giqlb_stats_t {
     int64_t kernels_total;       /* kernels enqueued since giqlb_create */
 } giqlb_stats_t;
 
+/* phases of the per-kernel profile (giqlb_profile_read) */
+enum {
+    GIQLB_PH_DICT = 0,        /* dictionary encoding kernels */
+    GIQLB_PH_LAYOUT = 1,      /* per-chromosome extent reduction + base scan */
+    GIQLB_PH_KEYGEN = 2,      /* linearised key generation */
+    GIQLB_PH_SORT_HIST = 3,   /* radix sort: digit histogram */
+    GIQLB_PH_SORT_PASS = 4,   /* radix sort: one-sweep digit passes */
+    GIQLB_PH_GATHER = 5,      /* gathers of end / strand into sorted order */
+    GIQLB_PH_SCAN_MAX = 6,    /* running max of end */
+    GIQLB_PH_JOIN_COUNT = 7,  /* join count pass */
+    GIQLB_PH_JOIN_SCAN = 8,   /* exclusive scan of tile counts */
+    GIQLB_PH_JOIN_EMIT = 9,   /* join emit pass */
+    GIQLB_PH_PROBE = 10,      /* SEMI/ANTI existence and per-row count probes */
+    GIQLB_PH_SELECT = 11,     /* flag compaction */
+    GIQLB_PH_DISTANCE = 12,
+    GIQLB_PH_CLUSTER = 13,
+    GIQLB_PH_MERGE = 14,
+    GIQLB_PH_NEAREST = 15,
+    GIQLB_PH_OTHER = 16,
+    GIQLB_PH_COUNT = 17
+};
+
 int giqlb_abi_version(void);
 int giqlb_create(int device, void* cuda_stream, giqlb_ctx** out);
 int giqlb_destroy(giqlb_ctx* ctx);
 const char* giqlb_last_error(const giqlb_ctx* ctx);
 int giqlb_sync(giqlb_ctx* ctx);
 int giqlb_stats(const giqlb_ctx* ctx, giqlb_stats_t* out_host);
+/* Per-phase device time.  While enabled, CUDA events are recorded on the context's stream around each
+ * kernel group; read() synchronises, ADDS the elapsed milliseconds and launch counts since the last read
+ * into ms_host[GIQLB_PH_COUNT] / launches_host[GIQLB_PH_COUNT] and clears the internal spans. */
+int giqlb_profile_enable(giqlb_ctx* ctx, int on);
+int giqlb_profile_read(giqlb_ctx* ctx, double* ms_host, int64_t* launches_host);
 
 /* ---- chromosome dictionary --------------------------------------------------------------------
  * Arrow utf8 layout per table: int32 offsets[n+1], uint8 bytes[].  Builds ONE dictionary over both
