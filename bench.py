@@ -1,0 +1,412 @@
+#!/usr/bin/env python
+"""bench.py — the north-star measurement: overlap pairs/sec of the 10M x 10M INTERSECTS inner join.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference] [--rows ROWS]
+
+One *step* is one pass of the hot path over the synthetic hg38-shaped BED tables of BASELINE.json
+configs[1] (`peaks(1e7, 20260103)` x `peaks(1e7, 20260104)`, row order shuffled):
+
+    chromosome dictionary encoding  ->  genome layout  ->  LSD radix-sort index of both tables
+    ->  join count  ->  scan  ->  join emit                      (all kernels of libgiqlb200.so)
+
+`value`  — pairs / device time of the step, inputs (utf8 chrom + int32 start/end) resident in HBM.
+`e2e`    — the same metric through the public host API (`Engine.table_from_buffers` + `Engine.intersects`
+           + pairs copied back) with PINNED HOST buffers: H2D of the inputs and D2H of the pairs are inside
+           the timed region, wall clock bracketed by synchronisation.
+`roofline` — the dominant kernel group of the step, timed live with CUDA events on the engine's stream.
+`cpu_baseline` — the C/OpenMP restatement in oracle/ on the host cores (NOT DuckDB: duckdb and sqlglot
+           are absent from the image), rank 0, N=1 only.
+
+`--impl reference` times that same CPU restatement as the reference arm (oracle port).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import sys
+import threading
+import time
+from pathlib import Path
+
+import numpy as np
+
+ROOT = Path(__file__).resolve().parent
+if str(ROOT) not in sys.path:
+    sys.path.insert(0, str(ROOT))
+
+METRIC = "overlap pairs/sec, 10Mx10M INTERSECTS inner join"
+UNIT = "pairs/s"
+SEED_L, SEED_R = 20260103, 20260104
+ROWS_DEFAULT = 10_000_000
+
+
+def log(*a):
+    print(*a, file=sys.stderr, flush=True)
+
+
+# ---- workload -------------------------------------------------------------------------------------------
+def utf8_columns(codes: np.ndarray, names):
+    """Arrow utf8 layout (int32 offsets[n+1], uint8 bytes) of names[codes]."""
+    import pyarrow as pa
+
+    arr = pa.DictionaryArray.from_arrays(pa.array(codes, type=pa.int32()), pa.array(list(names), type=pa.string())).cast(pa.string())
+    bufs = arr.buffers()
+    offs = np.frombuffer(bufs[1], dtype=np.int32)[: len(codes) + 1].copy()
+    data = np.frombuffer(bufs[2], dtype=np.uint8)[: int(offs[-1])].copy()
+    return offs, data
+
+
+def make_workload(rows: int):
+    from giql_b200 import synth
+
+    t0 = time.time()
+    A, B = synth.peaks(rows, SEED_L), synth.peaks(rows, SEED_R)
+    for T in (A, B):
+        T["offs"], T["bytes"] = utf8_columns(T["code"], T["names"])
+    log(f"[bench] generated 2 x {rows} intervals in {time.time() - t0:.1f}s")
+    return A, B
+
+
+def workload_name(rows):
+    return (f"C2 INTERSECTS inner join {rows}x{rows}, synthetic hg38 BED (24 chroms, log-normal widths median 500bp, "
+            f"80% clustered starts, shuffled rows), seeds {SEED_L}/{SEED_R}")
+
+
+# ---- clocks ------------------------------------------------------------------------------------------------
+class ClockSampler:
+    """Samples SM clock and throttle reasons of one GPU through NVML while the timed region runs."""
+
+    def __init__(self, index: int, period_s: float = 0.002):
+        self.index, self.period = index, period_s
+        self.samples, self.reasons = [], set()
+        self.max_mhz = None
+        self._stop = threading.Event()
+        self._thr = None
+        try:
+            import pynvml
+
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            visible = os.environ.get("CUDA_VISIBLE_DEVICES")
+            phys = index
+            if visible:
+                ids = [v.strip() for v in visible.split(",") if v.strip()]
+                if index < len(ids) and ids[index].isdigit():
+                    phys = int(ids[index])
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(phys)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+        except Exception as exc:  # pragma: no cover
+            log(f"[bench] NVML unavailable ({exc}); clocks not sampled")
+            self.nv = None
+
+    _NAMES = {0x8: "hw_slowdown", 0x40: "hw_thermal_slowdown", 0x20: "sw_thermal_slowdown", 0x4: "sw_power_cap",
+              0x80: "hw_power_brake_slowdown", 0x2: "applications_clocks_setting", 0x100: "display_clock_setting",
+              0x10: "sync_boost"}
+
+    def _run(self):
+        nv = self.nv
+        while not self._stop.is_set():
+            try:
+                self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                r = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h) if hasattr(nv, "nvmlDeviceGetCurrentClocksEventReasons") \
+                    else nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                for bit, name in self._NAMES.items():
+                    if r & bit:
+                        self.reasons.add(name)
+            except Exception:
+                pass
+            time.sleep(self.period)
+
+    def __enter__(self):
+        if self.nv:
+            self._thr = threading.Thread(target=self._run, daemon=True)
+            self._thr.start()
+        return self
+
+    def __exit__(self, *exc):
+        self._stop.set()
+        if self._thr:
+            self._thr.join()
+
+    def summary(self):
+        if not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons), "samples": 0}
+        return {"sm_mhz": float(np.median(self.samples)), "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons),
+                "samples": len(self.samples)}
+
+
+# ---- CPU restatement (cpu_baseline and the reference arm) -------------------------------------------------------
+def cpu_join(A, B, threads: int):
+    """One whole CPU join (bucket + per-chromosome sort + count + scan + emit) of the oracle port."""
+    from oracle import c_oracle
+
+    cap = getattr(cpu_join, "_cap", 0)
+    t0 = time.perf_counter()
+    total, _, _ = c_oracle.intersects_join_timed(A["code"], A["start"], A["end"], B["code"], B["start"], B["end"],
+                                                 len(A["names"]), cap, threads)
+    if total > cap:   # first call sizes the output (untimed), second call is the measured one
+        cpu_join._cap = int(total)
+        t0 = time.perf_counter()
+        total, _, _ = c_oracle.intersects_join_timed(A["code"], A["start"], A["end"], B["code"], B["start"], B["end"],
+                                                     len(A["names"]), int(total), threads)
+    return int(total), time.perf_counter() - t0
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from oracle import c_oracle
+
+    c_oracle.build()
+    threads = c_oracle.default_threads()
+    A, B = make_workload(args.rows)
+    for _ in range(args.warmup):
+        cpu_join(A, B, threads)
+    times, total = [], 0
+    for _ in range(args.steps):
+        total, dt = cpu_join(A, B, threads)
+        times.append(dt)
+    ms = 1e3 * sum(times) / len(times)
+    value = total / (ms / 1e3)
+    sample = f"full workload per step ({args.rows}x{args.rows} rows, {total} pairs)"
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+        "dtype": "int32", "data": "synthetic",
+        "config": {"workload": workload_name(args.rows), "pairs": total,
+                   "note": "reference arm = C/OpenMP restatement of the SQL GIQL emits (oracle/c/giql_oracle.c); "
+                           "duckdb and sqlglot are not installed in this image, so this is NOT DuckDB"},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ---- B200 arm --------------------------------------------------------------------------------------------------
+def algorithmic_bytes(phase: str, n_l: int, n_r: int, pairs: int, sort_passes: int):
+    """Per-phase algorithmic bytes of ONE step."""
+    n = n_l + n_r
+    return {
+        "dict": 8 * n,                       # read the utf8 name (~4.6 B) + offset, write an int32 code: counted as 8 B/row
+        "layout": 12 * n,                    # read code/start/end
+        "keygen": 12 * n + 8 * n,            # read code/start/end, write linear start + linear end
+        "sort_hist": 4 * n,                  # read keys once
+        "sort_pass": 16 * n * sort_passes,   # keys + row ids in and out, per 8-bit digit pass
+        "gather": 12 * n,                    # read row id + gathered end, write end
+        "join_count": 12 * n,
+        "join_scan": 0,
+        "join_emit": 12 * n + 8 * pairs,
+    }.get(phase, 0)
+
+
+def run_b200(args):
+    import torch
+    import torch.distributed as dist
+
+    import giql_b200
+    from giql_b200.engine import DeviceTable
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus:
+        log(f"[bench] WORLD_SIZE={world} but --gpus {args.gpus}; using WORLD_SIZE")
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    eng = giql_b200.Engine(local)
+    peaks = json.loads((ROOT / "MEASURED_PEAKS.json").read_text()) if (ROOT / "MEASURED_PEAKS.json").exists() else {}
+    hbm_peak, peak_src = (peaks["hbm_gbs"], "measured (MEASURED_PEAKS.json)") if "hbm_gbs" in peaks else (6650.0, "fallback (B200_PROFILING.md)")
+
+    A, B = make_workload(args.rows)
+    n_l = n_r = args.rows
+
+    def pinned(a):
+        return torch.from_numpy(a).pin_memory()
+
+    host = {k: {c: pinned(T[c]) for c in ("offs", "bytes", "start", "end")} for k, T in (("l", A), ("r", B))}
+    dev = {k: {c: t.to(eng.device) for c, t in cols.items()} for k, cols in host.items()}
+    torch.cuda.synchronize()
+    h2d_bytes = sum(t.numel() * t.element_size() for cols in host.values() for t in cols.values())
+    flush = torch.empty(512 << 20, dtype=torch.uint8, device=eng.device)   # > 126 MB L2
+
+    if world > 1:
+        from giql_b200 import sharding
+
+        shard = sharding.GenomeRangeShard(eng, rank, world)
+    else:
+        shard = None
+
+    def resident_tables():
+        # fresh DeviceTable objects over the SAME device buffers, so the dictionary is re-encoded each step
+        mk = lambda c: DeviceTable(eng, int(c["start"].numel()), None, c["start"], c["end"], None, c["offs"], c["bytes"])
+        return mk(dev["l"]), mk(dev["r"])
+
+    def step_device():
+        tl, tr = resident_tables()
+        if shard is not None:
+            return shard.intersects(tl, tr)
+        return eng.intersects(tl, tr)
+
+    def step_e2e(out_l_host, out_r_host):
+        tl = eng.table_from_buffers(host["l"]["offs"], host["l"]["bytes"], host["l"]["start"], host["l"]["end"])
+        tr = eng.table_from_buffers(host["r"]["offs"], host["r"]["bytes"], host["r"]["start"], host["r"]["end"])
+        res = shard.intersects(tl, tr) if shard is not None else eng.intersects(tl, tr)
+        n = len(res)
+        out_l_host[:n].copy_(res.left_rows, non_blocking=True)
+        out_r_host[:n].copy_(res.right_rows, non_blocking=True)
+        torch.cuda.synchronize()
+        return n
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- warm-up (also sizes the pinned result buffers) ----
+    pairs_local = 0
+    for _ in range(max(args.warmup, 3)):
+        flush.fill_(1)
+        pairs_local = len(step_device())
+    torch.cuda.synchronize()
+    out_l_host = torch.empty(max(pairs_local, 1), dtype=torch.int32).pin_memory()
+    out_r_host = torch.empty(max(pairs_local, 1), dtype=torch.int32).pin_memory()
+
+    # ---- timed: device-resident steps, one CUDA-event pair per step, L2 flushed between steps ----
+    eng.profile(True)
+    eng.profile_read()
+    k0 = eng.kernels_total()
+    starts = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
+    stops = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
+    barrier()
+    with ClockSampler(local) as clocks:
+        for i in range(args.steps):
+            flush.fill_(i & 0xFF)
+            starts[i].record(eng.stream)
+            res = step_device()
+            stops[i].record(eng.stream)
+            del res
+        torch.cuda.synchronize()
+    barrier()
+    step_ms = [s.elapsed_time(e) for s, e in zip(starts, stops)]
+    launches = eng.kernels_total() - k0
+    prof = eng.profile_read()
+    eng.profile(False)
+    t_dev = torch.tensor([sum(step_ms)], dtype=torch.float64, device=eng.device)
+    pairs_t = torch.tensor([pairs_local], dtype=torch.int64, device=eng.device)
+    if world > 1:
+        dist.all_reduce(t_dev, op=dist.ReduceOp.MAX)
+        dist.all_reduce(pairs_t, op=dist.ReduceOp.SUM)
+    total_ms = float(t_dev.item())
+    pairs = int(pairs_t.item())
+    ms_per_step = total_ms / args.steps
+    value = pairs / (ms_per_step / 1e3)
+
+    # ---- timed: end to end from pinned host buffers through the public API ----
+    for _ in range(2):
+        step_e2e(out_l_host, out_r_host)
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        step_e2e(out_l_host, out_r_host)
+    barrier()
+    e2e_s = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=eng.device)
+    if world > 1:
+        dist.all_reduce(e2e_s, op=dist.ReduceOp.MAX)
+    e2e_ms = 1e3 * float(e2e_s.item()) / args.steps
+    d2h_bytes = 8 * pairs_local
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    # ---- roofline of the dominant kernel group (per-launch, live CUDA events on the engine's stream) ----
+    lay_bits = 32
+    sort_passes = 4
+    phases = {}
+    for name, (ms, n_launch) in prof.items():
+        if n_launch <= 0:
+            continue
+        per_step_ms = ms / args.steps
+        ab = algorithmic_bytes(name, n_l, n_r, pairs_local, sort_passes)
+        phases[name] = {"ms_per_step": round(per_step_ms, 4), "launches_per_step": n_launch / args.steps,
+                        "algorithmic_bytes_per_step": ab,
+                        "gbs": round(ab / (per_step_ms * 1e6), 1) if per_step_ms > 0 else None}
+    dom = max(phases, key=lambda k: phases[k]["ms_per_step"])
+    d = phases[dom]
+    per_launch_ms = d["ms_per_step"] / d["launches_per_step"]
+    per_launch_bytes = d["algorithmic_bytes_per_step"] / d["launches_per_step"]
+    achieved = per_launch_bytes / (per_launch_ms * 1e6)
+    roofline = {"bound": "hbm", "kernel": dom, "achieved": round(achieved, 1), "peak": hbm_peak, "unit": "GB/s",
+                "frac": round(achieved / hbm_peak, 4), "traffic": None, "peak_source": peak_src,
+                "ms_per_launch": round(per_launch_ms, 4), "algorithmic_bytes_per_launch": int(per_launch_bytes)}
+    traffic_file = ROOT / "profiles" / "traffic.json"
+    if traffic_file.exists():
+        try:
+            roofline["traffic"] = json.loads(traffic_file.read_text()).get(dom)
+        except Exception:
+            pass
+    join_ms = sum(phases[p]["ms_per_step"] for p in ("join_count", "join_scan", "join_emit") if p in phases)
+    join_bytes = 12 * (n_l + n_r) + 8 * pairs_local
+    join_roofline = {"ms": round(join_ms, 4), "algorithmic_bytes": join_bytes,
+                     "achieved": round(join_bytes / (join_ms * 1e6), 1) if join_ms else None, "unit": "GB/s",
+                     "frac": round(join_bytes / (join_ms * 1e6) / hbm_peak, 4) if join_ms else None,
+                     "frac_whole_step": round(join_bytes / (ms_per_step * 1e6) / hbm_peak, 4)}
+
+    # ---- CPU baseline beside it (rank 0, N=1 only) ----
+    cpu = None
+    if world == 1 and not args.no_cpu:
+        from oracle import c_oracle
+
+        c_oracle.build()
+        threads = c_oracle.default_threads()
+        cpu_join(A, B, threads)   # sizes the output and warms the page cache
+        total, dt = cpu_join(A, B, threads)
+        assert total == pairs, f"CPU restatement found {total} pairs, GPU {pairs}"
+        cpu = {"value": total / dt, "unit": UNIT, "cores": threads, "kind": "port",
+               "sample": f"full workload, 1 run after 1 warm-up ({dt:.2f}s): C/OpenMP restatement, NOT DuckDB (duckdb/sqlglot absent)"}
+
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+        "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "int32",
+        "data": "synthetic",
+        "config": {"workload": workload_name(args.rows), "pairs": pairs, "rows_left": n_l, "rows_right": n_r,
+                   "sharding": "single GPU" if world == 1 else f"{world} contiguous genome ranges balanced on left interval count; "
+                               "straddling right intervals replicated; owner = rank of the left start",
+                   "l2": "inputs (340 MB) exceed the 126 MB L2 and a 512 MB buffer is rewritten between timed steps",
+                   "step": "dict_encode + layout + radix-sort index x2 + join count/scan/emit"},
+        "e2e": {"value": pairs / (e2e_ms / 1e3), "unit": UNIT, "ms_per_step": e2e_ms, "h2d_bytes_per_step": h2d_bytes,
+                "d2h_bytes_per_step": d2h_bytes},
+        "gpu_launches": int(launches),
+        "roofline": roofline,
+        "join_roofline": join_roofline,
+        "phases": phases,
+        "clocks": clocks.summary(),
+        "cpu_baseline": cpu,
+    }
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--rows", type=int, default=ROWS_DEFAULT, help="rows per table (default: the 10M of BASELINE configs[1])")
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_b200(args)
+
+
+if __name__ == "__main__":
+    main()

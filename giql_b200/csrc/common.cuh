@@ -17,8 +17,7 @@
 struct giqlb_ctx {
     int device = 0;
     int sm_count = GIQLB_SM_COUNT_DEFAULT;
-    cudaStream_t stream = nullptr;
-    bool own_stream = false;
+    cudaStream_t stream = nullptr;   // caller's stream; nullptr = legacy default stream
     char err[512] = {0};
     // small pinned host + device scratch for scalars returned to the host
     int64_t* h_scalars = nullptr;   // pinned, 64 slots

@@ -18,15 +18,9 @@ extern "C" int giqlb_create(int device, void* cuda_stream, giqlb_ctx** out) {
     }
     int sms = 0;
     if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device) == cudaSuccess && sms > 0) ctx->sm_count = sms;
-    if (cuda_stream) {
-        ctx->stream = (cudaStream_t)cuda_stream;
-    } else {
-        if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess) {
-            delete ctx;
-            return GIQLB_ERR_CUDA;
-        }
-        ctx->own_stream = true;
-    }
+    // NULL selects the legacy default stream: the caller's other work on that stream (PyTorch's default
+    // stream has handle 0) stays ordered with ours.  The library never creates a stream of its own.
+    ctx->stream = (cudaStream_t)cuda_stream;
     // keep freed blocks in the stream-ordered pool instead of returning them to the driver each sync
     cudaMemPool_t pool;
     if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) {
@@ -48,13 +42,12 @@ extern "C" int giqlb_create(int device, void* cuda_stream, giqlb_ctx** out) {
 extern "C" int giqlb_destroy(giqlb_ctx* ctx) {
     if (!ctx) return GIQLB_OK;
     cudaSetDevice(ctx->device);
-    if (ctx->stream) cudaStreamSynchronize(ctx->stream);
+    cudaStreamSynchronize(ctx->stream);
     for (auto& sp : ctx->prof_spans) { cudaEventDestroy(sp.start); cudaEventDestroy(sp.stop); }
     for (auto e : ctx->prof_free_events) cudaEventDestroy(e);
     if (ctx->h_scalars) cudaFreeHost(ctx->h_scalars);
     if (ctx->d_scalars) cudaFree(ctx->d_scalars);
     if (ctx->d_err) cudaFree(ctx->d_err);
-    if (ctx->own_stream && ctx->stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
     return GIQLB_OK;
 }

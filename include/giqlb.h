@@ -104,6 +104,8 @@ enum {
 };
 
 int giqlb_abi_version(void);
+/* cuda_stream: the cudaStream_t every call of this context enqueues on; NULL = the legacy default stream
+ * (PyTorch's default stream), so the caller's copies and kernels on that stream stay ordered with ours. */
 int giqlb_create(int device, void* cuda_stream, giqlb_ctx** out);
 int giqlb_destroy(giqlb_ctx* ctx);
 const char* giqlb_last_error(const giqlb_ctx* ctx);
