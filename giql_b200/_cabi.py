@@ -69,6 +69,7 @@ PROTOTYPES = {
     "giqlb_layout_info": (c_int, [_P, POINTER(c_int32), POINTER(c_uint64), POINTER(c_int32)]),
     "giqlb_layout_tables": (c_int, [_P, POINTER(_P), POINTER(_P), POINTER(_P)]),
     "giqlb_index_build": (c_int, [_P, _P, _P, _P, _P, _P, c_int64, c_int32, c_int32, c_int, POINTER(_P)]),
+    "giqlb_index_build_rows": (c_int, [_P, _P, _P, _P, _P, _P, _P, c_int64, c_int32, c_int32, c_int, POINTER(_P)]),
     "giqlb_index_free": (c_int, [_P, _P]),
     "giqlb_index_rows": (c_int64, [_P]),
     "giqlb_index_columns": (c_int, [_P, POINTER(_P), POINTER(_P), POINTER(_P), POINTER(_P)]),
@@ -81,12 +82,21 @@ PROTOTYPES = {
     "giqlb_intersects_exists": (c_int, [_P, _P, _P, _P, _P, c_int64, c_int32, c_int32, _P, _P]),
     "giqlb_select_rows": (c_int, [_P, _P, c_int64, c_int, _P, POINTER(c_int64)]),
     "giqlb_intersects_count_rows": (c_int, [_P, _P, _P, _P, _P, c_int64, c_int32, c_int32, _P, _P]),
+    "giqlb_nearest": (c_int, [_P, _P, _P, _P, _P, _P, c_int64, c_int32, c_int32, _P, c_int, c_int64, c_int, c_int,
+                              _P, _P, _P, _P, c_int64, POINTER(c_int64)]),
+    "giqlb_cluster": (c_int, [_P, _P, c_int64, _P]),
+    "giqlb_merge": (c_int, [_P, _P, c_int64, _P, _P, _P, _P, _P, c_int64, POINTER(c_int64)]),
+    "giqlb_disjoin": (c_int, [_P, _P, _P, _P, _P, c_int64, c_int32, c_int32, _P, c_int, _P, _P, _P, c_int64, POINTER(c_int64)]),
+    "giqlb_shard_cuts": (c_int, [_P, _P, _P, _P, _P, c_int64, c_int32, c_int32, c_int, POINTER(ctypes.c_uint32),
+                                 POINTER(ctypes.c_uint32)]),
+    "giqlb_shard_select": (c_int, [_P, _P, _P, _P, _P, c_int64, c_int32, c_int32, ctypes.c_uint32, ctypes.c_uint32,
+                                   ctypes.c_uint32, _P, POINTER(c_int64)]),
     "giqlb_distance": (c_int, [_P, _P, _P, _P, _P, _P, _P, _P, _P, c_int64, c_int, c_int,
                                c_int32, c_int32, c_int32, c_int32, _P, _P]),
 }
 
 PHASES = ["dict", "layout", "keygen", "sort_hist", "sort_pass", "gather", "scan_max", "join_count", "join_scan",
-          "join_emit", "probe", "select", "distance", "cluster", "merge", "nearest", "other"]
+          "join_emit", "probe", "select", "distance", "cluster", "merge", "nearest", "other", "shard", "disjoin"]
 
 _lib = None
 

@@ -1,0 +1,256 @@
+// cluster.cu — CLUSTER and MERGE as segmented scans over a start-sorted index.
+//
+// Semantics (reference, abdenlab/giql):
+//   CLUSTER  src/giql/expanders/cluster.py:205-310, 430-434.  Per partition (chrom, + strand when
+//            stranded := true, :243-245) ordered by start (:248):
+//              flag_i = 0  iff  MAX(end) over the strictly preceding rows [+ distance] >= start_i   (:254-279)
+//              id_i   = SUM(flag) over the default RANGE frame (:430-434): rows tied on start share the sum
+//                       through their last peer; ids are 1-based and restart per partition.
+//            Raw table coordinates, no canonicalisation (src/giql/expressions.py:223-226).
+//   MERGE    src/giql/expanders/merge.py:183-439: GROUP BY chrom[, strand], id -> MIN(start), MAX(end)
+//            (+ COUNT(*)), default ORDER BY chrom, start (:429-437).
+//
+// Device formulation over the linearised index (index.cu): the running max of end over ALL preceding rows
+// (pmax, restarting per strand block) also serves as the per-chromosome running max, because every end of an
+// earlier chromosome lies at or below the current chromosome's low guard cell: "has a predecessor in my
+// partition" == pmax[i-1] > base[chrom(i)].  One decoupled look-back scan turns the flags into a running
+// cluster count G; ids subtract G at the chromosome's first row; MERGE writes region G[i]-1 directly (the
+// running count IS the output slot, so no compaction pass): the flagged row stores the start, the last row of
+// the run stores the running max end.
+#include "common.cuh"
+#include "scan.cuh"
+
+namespace {
+
+using namespace giqlb_scan;
+
+struct LayoutView {
+    const uint32_t* base;   // [n_codes + 1]
+    const int32_t* lo32;
+    int32_t n_codes;
+};
+
+// chromosome whose cell range holds linear coordinate g: last c with base[c] <= g
+__device__ __forceinline__ int32_t chrom_of(const LayoutView& V, uint32_t g) {
+    int32_t lo = 0, hi = V.n_codes;   // answer in [0, n_codes)
+    while (hi - lo > 1) {
+        int32_t mid = (lo + hi) >> 1;
+        if (__ldg(V.base + mid) <= g) lo = mid; else hi = mid;
+    }
+    return lo;
+}
+
+struct InClusterFlag {
+    const uint32_t* gs;
+    const uint32_t* pmax;
+    LayoutView V;
+    long long d;
+    __device__ unsigned long long operator()(int64_t i) const {
+        if (i == 0) return 1ull;
+        const uint32_t s = gs[i], pm = pmax[i - 1];
+        const uint32_t b = __ldg(V.base + chrom_of(V, s));
+        const bool joins = pm > b && (long long)pm + d >= (long long)s;
+        return joins ? 0ull : 1ull;
+    }
+};
+struct OutRunningCount {
+    uint32_t* G;
+    __device__ void operator()(int64_t i, unsigned long long excl, unsigned long long v) const { G[i] = (uint32_t)(excl + v); }
+};
+
+// off[c] = running cluster count just before chromosome c's first row of this block
+__global__ void cluster_chrom_offsets_kernel(const uint32_t* __restrict__ gs, const uint32_t* __restrict__ G, int64_t n,
+                                             LayoutView V, uint32_t* __restrict__ off) {
+    int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= V.n_codes) return;
+    int64_t first = lower_bound_dev<uint32_t, int64_t>(gs, 0, n, V.base[c]);
+    off[c] = first > 0 ? G[first - 1] : 0u;
+}
+
+// last row of i's peer group (rows tied on start), galloping forward
+__device__ __forceinline__ int64_t last_peer(const uint32_t* __restrict__ gs, int64_t i, int64_t n) {
+    const uint32_t s = gs[i];
+    if (i + 1 >= n || gs[i + 1] != s) return i;
+    int64_t lo = i + 1, step = 1;   // invariant: gs[lo] == s
+    while (lo + step < n && gs[lo + step] == s) {
+        lo += step;
+        step <<= 1;
+    }
+    int64_t hi = lo + step < n ? lo + step : n;   // gs[hi] != s or hi == n
+    return upper_bound_dev<uint32_t, int64_t>(gs, lo, hi, s) - 1;
+}
+
+__global__ void __launch_bounds__(256)
+cluster_ids_kernel(const uint32_t* __restrict__ gs, const int32_t* __restrict__ rid, const uint32_t* __restrict__ G,
+                   const uint32_t* __restrict__ off, int64_t n, LayoutView V, int32_t* __restrict__ out_by_row) {
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t j = last_peer(gs, i, n);
+        const int32_t c = chrom_of(V, gs[i]);
+        out_by_row[rid[i]] = (int32_t)(G[j] - off[c]);
+    }
+}
+
+__global__ void __launch_bounds__(256)
+merge_emit_kernel(const uint32_t* __restrict__ gs, const uint32_t* __restrict__ pmax, const uint32_t* __restrict__ G,
+                  int64_t n, LayoutView V, int64_t out_base, int64_t idx_base, int32_t* __restrict__ out_code,
+                  int32_t* __restrict__ out_start, int32_t* __restrict__ out_end, long long* __restrict__ out_count) {
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        const uint32_t g = G[i];
+        const bool first = i == 0 || G[i - 1] != g;
+        const bool last = i + 1 == n || G[i + 1] != g;
+        if (!first && !last) continue;
+        const int64_t m = out_base + (int64_t)g - 1;
+        const uint32_t s = gs[i];
+        const int32_t c = chrom_of(V, s);
+        const uint32_t b = __ldg(V.base + c) + 1u;
+        const int32_t lo = __ldg(V.lo32 + c);
+        if (first) {
+            out_code[m] = c;
+            out_start[m] = lo + (int32_t)(s - b);
+            if (out_count) atomicAdd((unsigned long long*)&out_count[m], (unsigned long long)(-(long long)(idx_base + i)));
+        }
+        if (last) {
+            out_end[m] = lo + (int32_t)(pmax[i] - b);
+            if (out_count) atomicAdd((unsigned long long*)&out_count[m], (unsigned long long)(idx_base + i + 1));
+        }
+    }
+}
+
+__global__ void fill_u8_kernel(uint8_t* p, uint8_t v, int64_t n) {
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) p[i] = v;
+}
+
+inline int grid_of(const giqlb_ctx* ctx, int64_t n, int per_thread) {
+    int64_t want = ceil_div(n, 256 * per_thread), cap = (int64_t)ctx->sm_count * 8;
+    return (int)(want < 1 ? 1 : (want < cap ? want : cap));
+}
+
+inline LayoutView view_of(const giqlb_layout* lay) { return LayoutView{lay->d_base, lay->d_lo32, lay->n_codes}; }
+
+// flags -> running count G for rows [lo, hi) of the index; returns the block's cluster count in *total_dev
+int running_count(giqlb_ctx* ctx, const giqlb_index* X, int64_t lo, int64_t hi, long long d, uint32_t* G) {
+    return launch_scan<OpAddU64>(ctx, hi - lo, InClusterFlag{X->gs + lo, X->pmax + lo, view_of(X->layout), d},
+                                 OutRunningCount{G + lo});
+}
+
+int check_index(giqlb_ctx* ctx, const giqlb_index* X, const char* who) {
+    if (!X->layout || !X->layout->finalized) return giqlb_fail(ctx, GIQLB_ERR_INVALID, "%s: index has no layout", who);
+    if (X->n_negative > 0)
+        return giqlb_fail(ctx, GIQLB_ERR_INVALID, "%s: %lld rows have end < start; their grouping depends on the engine's tie order "
+                          "in the reference itself and is not supported", who, (long long)X->n_negative);
+    return GIQLB_OK;
+}
+
+}  // namespace
+
+extern "C" int giqlb_cluster(giqlb_ctx* ctx, giqlb_index* X, int64_t distance, int32_t* cluster_id_by_input_row) {
+    if (!ctx || !X || (X->n > 0 && !cluster_id_by_input_row)) return giqlb_fail(ctx, GIQLB_ERR_INVALID, "cluster: bad argument");
+    begin_call(ctx);
+    GIQLB_TRY(check_index(ctx, X, "cluster"));
+    const int64_t n = X->n;
+    if (n == 0) return end_call(ctx);
+    GIQLB_TRY(giqlb_index_ensure_pmax(ctx, X));
+    const long long d = distance > 0 ? (long long)distance : 0;   // cluster.py:266-272: the term is added only when > 0
+    uint32_t *G = nullptr, *off = nullptr;
+    GIQLB_TRY(dev_alloc(ctx, &G, (size_t)n));
+    int st = dev_alloc(ctx, &off, (size_t)X->layout->n_codes);
+    const int nb = X->grouped_by_strand ? X->n_blocks : 1;
+    const LayoutView V = view_of(X->layout);
+    {
+        PhaseSpan ps(ctx, GIQLB_PH_CLUSTER);
+        for (int b = 0; b < nb && st == GIQLB_OK; b++) {
+            const int64_t lo = X->grouped_by_strand ? X->block_off[b] : 0, hi = X->grouped_by_strand ? X->block_off[b + 1] : n;
+            if (hi <= lo) continue;
+            st = running_count(ctx, X, lo, hi, d, G);
+            if (st != GIQLB_OK) break;
+            cluster_chrom_offsets_kernel<<<(V.n_codes + 127) / 128, 128, 0, ctx->stream>>>(X->gs + lo, G + lo, hi - lo, V, off);
+            ctx->launches_this_call++;
+            ctx->stats.kernels_total++;
+            cluster_ids_kernel<<<grid_of(ctx, hi - lo, 4), 256, 0, ctx->stream>>>(X->gs + lo, X->rid + lo, G + lo, off, hi - lo, V,
+                                                                                 cluster_id_by_input_row);
+            ctx->launches_this_call++;
+            ctx->stats.kernels_total++;
+            if (cudaGetLastError() != cudaSuccess) st = giqlb_fail(ctx, GIQLB_ERR_CUDA, "cluster: launch failed");
+        }
+    }
+    dev_free(ctx, G);
+    dev_free(ctx, off);
+    if (st != GIQLB_OK) return st;
+    ctx->stats.rows_in[0] = n;
+    ctx->stats.rows_in[1] = 0;
+    ctx->stats.rows_out = n;
+    ctx->stats.algorithmic_bytes = 12 * n + (X->strand ? n : 0) + 4 * n;
+    return end_call(ctx);
+}
+
+extern "C" int giqlb_merge(giqlb_ctx* ctx, giqlb_index* X, int64_t distance, int32_t* out_code, int32_t* out_start,
+                           int32_t* out_end, uint8_t* out_strand, int64_t* out_count, int64_t capacity, int64_t* n_out_host) {
+    if (!ctx || !X || !n_out_host || capacity < 0 || (capacity > 0 && (!out_code || !out_start || !out_end)))
+        return giqlb_fail(ctx, GIQLB_ERR_INVALID, "merge: bad argument");
+    begin_call(ctx);
+    GIQLB_TRY(check_index(ctx, X, "merge"));
+    *n_out_host = 0;
+    const int64_t n = X->n;
+    if (n == 0) return end_call(ctx);
+    GIQLB_TRY(giqlb_index_ensure_pmax(ctx, X));
+    const long long d = distance > 0 ? (long long)distance : 0;
+    uint32_t* G = nullptr;
+    GIQLB_TRY(dev_alloc(ctx, &G, (size_t)n));
+    const int nb = X->grouped_by_strand ? X->n_blocks : 1;
+    const LayoutView V = view_of(X->layout);
+    int st = GIQLB_OK;
+    // running counts of every strand block, then their totals in one round trip
+    std::vector<int64_t> blk_lo, blk_hi;
+    std::vector<int> blk_code;
+    {
+        PhaseSpan ps(ctx, GIQLB_PH_CLUSTER);
+        for (int b = 0; b < nb && st == GIQLB_OK; b++) {
+            const int64_t lo = X->grouped_by_strand ? X->block_off[b] : 0, hi = X->grouped_by_strand ? X->block_off[b + 1] : n;
+            if (hi <= lo) continue;
+            st = running_count(ctx, X, lo, hi, d, G);
+            blk_lo.push_back(lo);
+            blk_hi.push_back(hi);
+            blk_code.push_back(b);
+        }
+    }
+    std::vector<uint32_t> totals(blk_lo.size(), 0u);
+    for (size_t k = 0; k < blk_lo.size() && st == GIQLB_OK; k++)
+        if (cudaMemcpyAsync(&totals[k], G + blk_hi[k] - 1, 4, cudaMemcpyDeviceToHost, ctx->stream) != cudaSuccess)
+            st = giqlb_fail(ctx, GIQLB_ERR_CUDA, "merge: copy failed");
+    if (st == GIQLB_OK && cudaStreamSynchronize(ctx->stream) != cudaSuccess) st = giqlb_fail(ctx, GIQLB_ERR_CUDA, "merge: sync failed");
+    int64_t total = 0;
+    for (uint32_t t : totals) total += t;
+    *n_out_host = total;
+    if (st == GIQLB_OK && total > capacity) {
+        dev_free(ctx, G);
+        return giqlb_fail(ctx, GIQLB_ERR_CAPACITY, "merge: %lld regions exceed capacity %lld", (long long)total, (long long)capacity);
+    }
+    if (st == GIQLB_OK && total > 0) {
+        PhaseSpan ps(ctx, GIQLB_PH_MERGE);
+        if (out_count) cudaMemsetAsync(out_count, 0, (size_t)total * 8, ctx->stream);
+        int64_t out_base = 0;
+        for (size_t k = 0; k < blk_lo.size(); k++) {
+            const int64_t lo = blk_lo[k], hi = blk_hi[k];
+            merge_emit_kernel<<<grid_of(ctx, hi - lo, 4), 256, 0, ctx->stream>>>(X->gs + lo, X->pmax + lo, G + lo, hi - lo, V, out_base, lo,
+                                                                                out_code, out_start, out_end, (long long*)out_count);
+            ctx->launches_this_call++;
+            ctx->stats.kernels_total++;
+            if (out_strand && totals[k] > 0) {
+                // every row of a strand block carries the block's strand code
+                const uint8_t code = (uint8_t)blk_code[k];
+                fill_u8_kernel<<<grid_of(ctx, totals[k], 4), 256, 0, ctx->stream>>>(out_strand + out_base, code, totals[k]);
+                ctx->launches_this_call++;
+                ctx->stats.kernels_total++;
+            }
+            out_base += totals[k];
+        }
+        if (cudaGetLastError() != cudaSuccess) st = giqlb_fail(ctx, GIQLB_ERR_CUDA, "merge: launch failed");
+    }
+    dev_free(ctx, G);
+    if (st != GIQLB_OK) return st;
+    ctx->stats.rows_in[0] = n;
+    ctx->stats.rows_in[1] = 0;
+    ctx->stats.rows_out = total;
+    ctx->stats.algorithmic_bytes = 12 * n + (X->strand ? n : 0) + 12 * total;
+    return end_call(ctx);
+}

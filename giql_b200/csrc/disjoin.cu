@@ -1,0 +1,203 @@
+// disjoin.cu — DISJOIN(target[, reference]): split every target interval at the reference's breakpoints.
+//
+// Semantics (reference, abdenlab/giql src/giql/expanders/disjoin.py:102-202):
+//   breakpoints = UNION (distinct) of the reference's starts and ends per chromosome            (:149-154)
+//   cuts of a target row = {t.start, t.end} ∪ {bp : t.start < bp < t.end}                         (:159-172)
+//   segments = consecutive cuts (LEAD over the cuts of the target key), kept when seg_end > seg_start (:173-178)
+//   unless the reference is the target itself, a segment is kept only when some reference row covers its
+//   start: r.start <= seg_start AND r.end > seg_start                                              (:184-190)
+//   duplicate target rows share a key and each receives every segment                              (:191-199)
+// Canonical coordinates in, canonical coordinates out (the host layer re-encodes, :139-141).
+//
+// Device formulation: the breakpoints are the sorted, de-duplicated linearised starts and ends of the
+// reference index (one radix sort of 2n keys + a flag scan).  A target row's interior cuts are then the
+// contiguous run bp[lo, hi), lo = upper_bound(bp, t.start), hi = lower_bound(bp, t.end): counting is two
+// binary searches, and the coverage test of a segment start p is one more (rows with r.start <= p exist and
+// their running max end exceeds p).  count -> exclusive scan -> emit, like the join.
+#include "common.cuh"
+#include "scan.cuh"
+
+namespace {
+
+using namespace giqlb_scan;
+
+struct DisjoinView {
+    const uint32_t* bp;
+    int64_t n_bp;
+    const uint32_t* rgs;    // reference index: sorted starts and running max of end (coverage test)
+    const uint32_t* pmax;
+    int64_t n_r;
+    int filter;             // 1: keep only covered segments (reference is not the target itself)
+};
+
+__device__ __forceinline__ bool covered(const DisjoinView& V, uint32_t p) {
+    int64_t u = upper_bound_dev<uint32_t, int64_t>(V.rgs, 0, V.n_r, p);   // rows with r.start <= p
+    return u > 0 && __ldg(V.pmax + u - 1) > p;
+}
+
+// Visits the segments of target row i in order; f(seg_index, start_lin_or_raw...) receives canonical coordinates.
+template <typename F>
+__device__ __forceinline__ unsigned long long for_each_segment(const ProbeCols& T, const DisjoinView& V, int64_t i, F f) {
+    const long long ts = (long long)T.start[i] + T.sadj, te = (long long)T.end[i] + T.eadj;
+    if (ts == te) return 0ull;                       // a single cut: LEAD is NULL, no segment
+    uint32_t gs, ge;
+    const bool on_ref_chrom = V.n_r > 0 && probe_linearise(T, i, gs, ge);
+    unsigned long long n = 0;
+    if (te < ts) {                                   // cuts {end, start}: one segment (end, start), no interior cut
+        if (!V.filter || (on_ref_chrom && covered(V, ge))) {
+            f(n, te, ts);
+            n++;
+        }
+        return n;
+    }
+    if (!on_ref_chrom) {                             // no breakpoint on this chromosome
+        if (!V.filter) {
+            f(n, ts, te);
+            n++;
+        }
+        return n;
+    }
+    const int32_t c = T.code[i];
+    const long long lo_c = __ldg(T.lo32 + c);
+    const uint32_t b1 = __ldg(T.base + c) + 1u;
+    const int64_t lo = upper_bound_dev<uint32_t, int64_t>(V.bp, 0, V.n_bp, gs);   // first bp >  t.start
+    int64_t hi = lower_bound_dev<uint32_t, int64_t>(V.bp, lo, V.n_bp, ge);        // first bp >= t.end
+    if (hi < lo) hi = lo;
+    long long seg_s = ts;
+    uint32_t seg_s_lin = gs;
+    for (int64_t j = lo; j <= hi; j++) {
+        const uint32_t cut_lin = j < hi ? __ldg(V.bp + j) : ge;
+        const long long cut = j < hi ? lo_c + (long long)(cut_lin - b1) : te;
+        if (!V.filter || covered(V, seg_s_lin)) {
+            f(n, seg_s, cut);
+            n++;
+        }
+        seg_s = cut;
+        seg_s_lin = cut_lin;
+    }
+    return n;
+}
+
+struct InSegCount {
+    ProbeCols T;
+    DisjoinView V;
+    __device__ unsigned long long operator()(int64_t i) const {
+        return for_each_segment(T, V, i, [](unsigned long long, long long, long long) {});
+    }
+};
+struct OutOffsets {
+    unsigned long long* off;
+    unsigned long long* total;
+    int64_t n;
+    __device__ void operator()(int64_t i, unsigned long long excl, unsigned long long v) const {
+        off[i] = excl;
+        if (i == n - 1) *total = excl + v;
+    }
+};
+
+__global__ void __launch_bounds__(256)
+disjoin_emit_kernel(ProbeCols T, DisjoinView V, const unsigned long long* __restrict__ off, int32_t* __restrict__ out_row,
+                    int32_t* __restrict__ out_start, int32_t* __restrict__ out_end) {
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < T.n; i += (int64_t)gridDim.x * blockDim.x) {
+        const unsigned long long o = off[i];
+        for_each_segment(T, V, i, [&](unsigned long long k, long long s, long long e) {
+            out_row[o + k] = (int32_t)i;
+            out_start[o + k] = (int32_t)s;
+            out_end[o + k] = (int32_t)e;
+        });
+    }
+}
+
+__global__ void __launch_bounds__(256)
+concat_kernel(const uint32_t* __restrict__ a, const uint32_t* __restrict__ b, int64_t n, uint32_t* __restrict__ out) {
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < 2 * n; i += (int64_t)gridDim.x * blockDim.x)
+        out[i] = i < n ? a[i] : b[i - n];
+}
+
+struct InIsNew {
+    const uint32_t* k;
+    __device__ unsigned long long operator()(int64_t i) const { return (i == 0 || k[i] != k[i - 1]) ? 1ull : 0ull; }
+};
+struct OutUnique {
+    const uint32_t* k;
+    uint32_t* out;
+    unsigned long long* total;
+    int64_t n;
+    __device__ void operator()(int64_t i, unsigned long long excl, unsigned long long v) const {
+        if (v) out[excl] = k[i];
+        if (i == n - 1) *total = excl + v;
+    }
+};
+
+}  // namespace
+
+extern "C" int giqlb_disjoin(giqlb_ctx* ctx, const giqlb_layout* lay, const int32_t* t_code, const int32_t* t_start,
+                             const int32_t* t_end, int64_t n_t, int32_t t_start_adj, int32_t t_end_adj, giqlb_index* REF,
+                             int self_reference, int32_t* out_row, int32_t* out_start, int32_t* out_end, int64_t capacity,
+                             int64_t* n_out_host) {
+    if (!ctx || !REF || !n_out_host || n_t < 0 || capacity < 0) return giqlb_fail(ctx, GIQLB_ERR_INVALID, "disjoin: bad argument");
+    if (REF->layout != lay) return giqlb_fail(ctx, GIQLB_ERR_INVALID, "disjoin: reference index was built on a different layout");
+    if (REF->grouped_by_strand) return giqlb_fail(ctx, GIQLB_ERR_INVALID, "disjoin: strand-grouped index not accepted");
+    begin_call(ctx);
+    *n_out_host = 0;
+    if (n_t == 0) return end_call(ctx);
+    ProbeCols T;
+    GIQLB_TRY(probe_cols(ctx, lay, t_code, t_start, t_end, n_t, t_start_adj, t_end_adj, &T));
+    GIQLB_TRY(giqlb_index_ensure_pmax(ctx, REF));
+    const int64_t nr = REF->n;
+    uint32_t *ka = nullptr, *kb = nullptr, *va = nullptr, *vb = nullptr, *bp = nullptr;
+    unsigned long long* off = nullptr;
+    unsigned long long* total = reinterpret_cast<unsigned long long*>(ctx->d_scalars + 11);
+    int st = GIQLB_OK;
+    int64_t n_bp = 0;
+    PhaseSpan ps(ctx, GIQLB_PH_DISJOIN);
+    if (nr > 0) {
+        st = dev_alloc(ctx, &ka, (size_t)2 * nr);
+        if (st == GIQLB_OK) st = dev_alloc(ctx, &kb, (size_t)2 * nr);
+        if (st == GIQLB_OK) st = dev_alloc(ctx, &va, (size_t)2 * nr);
+        if (st == GIQLB_OK) st = dev_alloc(ctx, &vb, (size_t)2 * nr);
+        if (st == GIQLB_OK) st = dev_alloc(ctx, &bp, (size_t)2 * nr);
+        if (st == GIQLB_OK) {
+            int64_t blocks = ceil_div(2 * nr, 1024), cap = (int64_t)ctx->sm_count * 8;
+            concat_kernel<<<(unsigned)(blocks < cap ? blocks : cap), 256, 0, ctx->stream>>>(REF->gs, REF->ge, nr, ka);
+            ctx->launches_this_call++;
+            ctx->stats.kernels_total++;
+            int in_b = 0;
+            st = giqlb_radix_sort_pairs_u32(ctx, ka, va, kb, vb, 2 * nr, 0, lay->key_bits, 1, &in_b);
+            if (st == GIQLB_OK) {
+                const uint32_t* sorted = in_b ? kb : ka;
+                cudaMemsetAsync(total, 0, 8, ctx->stream);
+                st = launch_scan<OpAddU64>(ctx, 2 * nr, InIsNew{sorted}, OutUnique{sorted, bp, total, 2 * nr});
+            }
+            if (st == GIQLB_OK) st = fetch_scalars(ctx, total, 1);
+            if (st == GIQLB_OK) n_bp = ctx->h_scalars[0];
+        }
+    }
+    DisjoinView V{bp, n_bp, REF->gs, REF->pmax, nr, self_reference ? 0 : 1};
+    if (st == GIQLB_OK) st = dev_alloc(ctx, &off, (size_t)n_t);
+    if (st == GIQLB_OK) {
+        cudaMemsetAsync(total, 0, 8, ctx->stream);
+        st = launch_scan<OpAddU64>(ctx, n_t, InSegCount{T, V}, OutOffsets{off, total, n_t});
+    }
+    if (st == GIQLB_OK) st = fetch_scalars(ctx, total, 1);
+    int64_t n_out = st == GIQLB_OK ? ctx->h_scalars[0] : 0;
+    if (st == GIQLB_OK) {
+        *n_out_host = n_out;
+        if (n_out > capacity) st = giqlb_fail(ctx, GIQLB_ERR_CAPACITY, "disjoin: %lld segments exceed capacity %lld", (long long)n_out, (long long)capacity);
+        else if (n_out > 0 && (!out_row || !out_start || !out_end)) st = giqlb_fail(ctx, GIQLB_ERR_INVALID, "disjoin: null output");
+    }
+    if (st == GIQLB_OK && n_out > 0) {
+        int64_t blocks = ceil_div(n_t, 256), cap = (int64_t)ctx->sm_count * 16;
+        disjoin_emit_kernel<<<(unsigned)(blocks < cap ? blocks : cap), 256, 0, ctx->stream>>>(T, V, off, out_row, out_start, out_end);
+        ctx->launches_this_call++;
+        ctx->stats.kernels_total++;
+        if (cudaGetLastError() != cudaSuccess) st = giqlb_fail(ctx, GIQLB_ERR_CUDA, "disjoin: emit launch failed");
+    }
+    dev_free(ctx, ka); dev_free(ctx, kb); dev_free(ctx, va); dev_free(ctx, vb); dev_free(ctx, bp); dev_free(ctx, off);
+    if (st != GIQLB_OK) return st;
+    ctx->stats.rows_in[0] = n_t;
+    ctx->stats.rows_in[1] = nr;
+    ctx->stats.rows_out = n_out;
+    ctx->stats.algorithmic_bytes = 12 * (n_t + nr) + 12 * n_out;
+    return end_call(ctx);
+}

@@ -105,14 +105,16 @@ layout_finalize_kernel(const long long* __restrict__ lohi, int32_t n_codes, long
 // linearised start key + linearised end (unsorted), degenerate-row counters
 __global__ void __launch_bounds__(256)
 index_keygen_kernel(const int32_t* __restrict__ code, const int32_t* __restrict__ start,
-                    const int32_t* __restrict__ end, int64_t n, int32_t n_codes, int32_t sadj, int32_t eadj,
+                    const int32_t* __restrict__ end, const int32_t* __restrict__ rows /* nullable: row selection */,
+                    int64_t n, int32_t n_codes, int32_t sadj, int32_t eadj,
                     const uint32_t* __restrict__ base, const int32_t* __restrict__ lo32,
                     const int32_t* __restrict__ hi32, uint32_t* __restrict__ gs, uint32_t* __restrict__ ge,
                     unsigned long long* __restrict__ counters /* [0] end<=start [1] end<start [2] outside layout */) {
     unsigned int degenerate = 0, negative = 0, outside = 0;
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
-        int32_t c = code[i];
-        long long s = (long long)start[i] + sadj, e = (long long)end[i] + eadj;
+        const int64_t r = rows ? (int64_t)rows[i] : i;
+        int32_t c = code[r];
+        long long s = (long long)start[r] + sadj, e = (long long)end[r] + eadj;
         uint32_t ks = 0xffffffffu, ke = 0xffffffffu;
         if (c < 0 || c >= n_codes) {
             outside++;
@@ -146,6 +148,12 @@ __global__ void __launch_bounds__(256)
 gather_kernel(const T* __restrict__ src, const uint32_t* __restrict__ idx, T* __restrict__ dst, int64_t n) {
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
         dst[i] = src[idx[i]];
+}
+
+__global__ void __launch_bounds__(256)
+remap_rows_kernel(int32_t* __restrict__ rid, const int32_t* __restrict__ rows, int64_t n) {
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+        rid[i] = rows[rid[i]];
 }
 
 __global__ void __launch_bounds__(256)
@@ -348,6 +356,13 @@ extern "C" int giqlb_index_info(const giqlb_index* ix, int64_t* n_degenerate, in
 extern "C" int giqlb_index_build(giqlb_ctx* ctx, const giqlb_layout* lay, const int32_t* code, const int32_t* start,
                                  const int32_t* end, const uint8_t* strand, int64_t n, int32_t start_adj,
                                  int32_t end_adj, int flags, giqlb_index** out) {
+    return giqlb_index_build_rows(ctx, lay, code, start, end, strand, nullptr, n, start_adj, end_adj, flags, out);
+}
+
+// `rows` (nullable) selects and orders the rows that are indexed; the index then carries rows[i] as row id.
+extern "C" int giqlb_index_build_rows(giqlb_ctx* ctx, const giqlb_layout* lay, const int32_t* code, const int32_t* start,
+                                      const int32_t* end, const uint8_t* strand, const int32_t* rows, int64_t n,
+                                      int32_t start_adj, int32_t end_adj, int flags, giqlb_index** out) {
     if (!ctx || !lay || !out || n < 0 || (n > 0 && (!code || !start || !end)))
         return giqlb_fail(ctx, GIQLB_ERR_INVALID, "index_build: bad argument");
     if (!lay->finalized) return giqlb_fail(ctx, GIQLB_ERR_INVALID, "index_build: layout not finalized");
@@ -391,7 +406,7 @@ extern "C" int giqlb_index_build(giqlb_ctx* ctx, const giqlb_layout* lay, const 
         {
         PhaseSpan ps(ctx, GIQLB_PH_KEYGEN);
         index_keygen_kernel<<<grid_for(ctx, n, 256 * 4, 8), 256, 0, ctx->stream>>>(
-            code, start, end, n, lay->n_codes, start_adj, end_adj, lay->d_base, lay->d_lo32, lay->d_hi32, ka, ge_u, counters);
+            code, start, end, rows, n, lay->n_codes, start_adj, end_adj, lay->d_base, lay->d_lo32, lay->d_hi32, ka, ge_u, counters);
         ctx->launches_this_call++;
         ctx->stats.kernels_total++;
         }
@@ -434,6 +449,12 @@ extern "C" int giqlb_index_build(giqlb_ctx* ctx, const giqlb_layout* lay, const 
         ctx->launches_this_call++;
         ctx->stats.kernels_total++;
         IB_CUDA(cudaGetLastError());
+        if (rows) {   // positions in the selection -> caller's row ids
+            remap_rows_kernel<<<grid_for(ctx, n, 256 * 4, 8), 256, 0, ctx->stream>>>(ix->rid, rows, n);
+            ctx->launches_this_call++;
+            ctx->stats.kernels_total++;
+            IB_CUDA(cudaGetLastError());
+        }
         if (strand) {
             IB_TRY(dev_alloc(ctx, &ix->strand, (size_t)n));
             gather_kernel<uint8_t><<<grid_for(ctx, n, 256 * 4, 8), 256, 0, ctx->stream>>>(
@@ -527,26 +548,37 @@ int giqlb_index_ensure_pmax(giqlb_ctx* ctx, giqlb_index* ix) {
                                    ix->grouped_by_strand ? ix->n_blocks : 1);
 }
 
-// ge ascending with the sorted position of each (pos_by_end).  Within a strand block when grouped.
+// ge ascending with the sorted position of each (pos_by_end), independently inside every strand block;
+// positions are block-relative.  Stable LSD passes keep rows tied on end in index (start) order.
 int giqlb_index_ensure_end_sorted(giqlb_ctx* ctx, giqlb_index* ix) {
     if (ix->ge_sorted) return GIQLB_OK;
     const int64_t n = ix->n;
+    GIQLB_TRY(dev_alloc(ctx, &ix->ge_sorted, (size_t)n));
+    int st = dev_alloc(ctx, &ix->pos_by_end, (size_t)n);
     uint32_t *ka = nullptr, *kb = nullptr, *va = nullptr, *vb = nullptr;
-    GIQLB_TRY(dev_alloc(ctx, &ka, (size_t)n));
-    GIQLB_TRY(dev_alloc(ctx, &kb, (size_t)n));
-    GIQLB_TRY(dev_alloc(ctx, &va, (size_t)n));
-    GIQLB_TRY(dev_alloc(ctx, &vb, (size_t)n));
-    if (n > 0) CUDA_TRY(ctx, cudaMemcpyAsync(ka, ix->ge, (size_t)n * 4, cudaMemcpyDeviceToDevice, ctx->stream));
+    if (st == GIQLB_OK) st = dev_alloc(ctx, &ka, (size_t)n);
+    if (st == GIQLB_OK) st = dev_alloc(ctx, &kb, (size_t)n);
+    if (st == GIQLB_OK) st = dev_alloc(ctx, &va, (size_t)n);
+    if (st == GIQLB_OK) st = dev_alloc(ctx, &vb, (size_t)n);
     const int nb = ix->grouped_by_strand ? ix->n_blocks : 1;
-    // every block is sorted independently; identity payloads are block-relative, so sort whole-array when
-    // ungrouped and fix up per block otherwise
-    if (nb == 1) {
+    for (int b = 0; b < nb && st == GIQLB_OK; b++) {
+        const int64_t lo = ix->grouped_by_strand ? ix->block_off[b] : 0, hi = ix->grouped_by_strand ? ix->block_off[b + 1] : n;
+        if (hi <= lo) continue;
+        const size_t bytes = (size_t)(hi - lo) * 4;
+        if (cudaMemcpyAsync(ka + lo, ix->ge + lo, bytes, cudaMemcpyDeviceToDevice, ctx->stream) != cudaSuccess) {
+            st = giqlb_fail(ctx, GIQLB_ERR_CUDA, "end-sorted view: copy failed");
+            break;
+        }
         int in_b = 0;
-        GIQLB_TRY(giqlb_radix_sort_pairs_u32(ctx, ka, va, kb, vb, n, 0, ix->layout->key_bits, 1, &in_b));
-        if (in_b) { ix->ge_sorted = kb; ix->pos_by_end = (int32_t*)vb; dev_free(ctx, ka); dev_free(ctx, va); }
-        else      { ix->ge_sorted = ka; ix->pos_by_end = (int32_t*)va; dev_free(ctx, kb); dev_free(ctx, vb); }
-        return GIQLB_OK;
+        st = giqlb_radix_sort_pairs_u32(ctx, ka + lo, va + lo, kb + lo, vb + lo, hi - lo, 0, ix->layout->key_bits, 1, &in_b);
+        if (st != GIQLB_OK) break;
+        cudaMemcpyAsync(ix->ge_sorted + lo, (in_b ? kb : ka) + lo, bytes, cudaMemcpyDeviceToDevice, ctx->stream);
+        cudaMemcpyAsync(ix->pos_by_end + lo, (in_b ? vb : va) + lo, bytes, cudaMemcpyDeviceToDevice, ctx->stream);
     }
     dev_free(ctx, ka); dev_free(ctx, kb); dev_free(ctx, va); dev_free(ctx, vb);
-    return giqlb_fail(ctx, GIQLB_ERR_INTERNAL, "end-sorted view of a strand-grouped index is built by nearest.cu");
+    if (st != GIQLB_OK) {
+        dev_free(ctx, ix->ge_sorted); dev_free(ctx, ix->pos_by_end);
+        ix->ge_sorted = nullptr; ix->pos_by_end = nullptr;
+    }
+    return st;
 }

@@ -246,35 +246,6 @@ join_emit_general_kernel(JoinSide L, JoinSide R, const uint32_t* __restrict__ pm
 }
 
 // ---- SEMI / ANTI and per-row counts, probing from the raw (unsorted) left columns --------------------
-struct ProbeCols {
-    const int32_t* code;
-    const int32_t* start;
-    const int32_t* end;
-    int64_t n;
-    int32_t sadj, eadj;
-    int32_t n_codes;
-    const uint32_t* base;
-    const int32_t* lo32;
-    const int32_t* hi32;
-};
-
-// linearise one probe row; coordinates are clamped into the chromosome's guard cells, which preserves
-// every comparison against indexed rows of that chromosome.  Returns false when the chromosome holds no
-// indexed row at all (or the code is outside the dictionary): nothing can match.
-__device__ __forceinline__ bool probe_linearise(const ProbeCols& P, int64_t i, uint32_t& gs, uint32_t& ge) {
-    int32_t c = P.code[i];
-    if (c < 0 || c >= P.n_codes) return false;
-    long long lo = __ldg(P.lo32 + c), hi = __ldg(P.hi32 + c);
-    if (hi < lo) return false;
-    long long s = (long long)P.start[i] + P.sadj, e = (long long)P.end[i] + P.eadj;
-    s = s < lo - 1 ? lo - 1 : (s > hi + 1 ? hi + 1 : s);
-    e = e < lo - 1 ? lo - 1 : (e > hi + 1 ? hi + 1 : e);
-    uint32_t b = __ldg(P.base + c) + 1u;
-    gs = b + (uint32_t)(s - lo);   // lo - 1 maps to the lower guard cell (wraps to b - 1)
-    ge = b + (uint32_t)(e - lo);
-    return true;
-}
-
 __global__ void __launch_bounds__(256)
 probe_exists_kernel(ProbeCols P, const uint32_t* __restrict__ rgs, const uint32_t* __restrict__ pmax, int64_t nr,
                     uint8_t* __restrict__ exists) {
@@ -311,14 +282,6 @@ probe_count_kernel(ProbeCols P, const uint32_t* __restrict__ rgs, const uint32_t
 }
 
 inline JoinSide side_of(const giqlb_index* ix) { return JoinSide{ix->gs, ix->ge, ix->rid, ix->n}; }
-
-inline int probe_cols(giqlb_ctx* ctx, const giqlb_layout* lay, const int32_t* code, const int32_t* start,
-                      const int32_t* end, int64_t n, int32_t sadj, int32_t eadj, ProbeCols* out) {
-    if (!lay || !lay->finalized) return giqlb_fail(ctx, GIQLB_ERR_INVALID, "probe: layout not finalized");
-    if (n < 0 || (n > 0 && (!code || !start || !end))) return giqlb_fail(ctx, GIQLB_ERR_INVALID, "probe: bad column pointers");
-    *out = ProbeCols{code, start, end, n, sadj, eadj, lay->n_codes, lay->d_base, lay->d_lo32, lay->d_hi32};
-    return GIQLB_OK;
-}
 
 }  // namespace
 

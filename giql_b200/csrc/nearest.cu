@@ -1,0 +1,238 @@
+// nearest.cu — NEAREST(target, reference := q.interval, k, max_distance, stranded, signed) as a sorted-neighbour
+// search: three candidate streams per query row, merged in the reference's ORDER BY.
+//
+// Semantics (reference, abdenlab/giql src/giql/expanders/nearest.py:255-397, LATERAL form): for every query row
+//   candidates = target rows with t.chrom = q.chrom [AND q.strand = t.strand when stranded and both tables carry
+//   a strand column, :304-307, :328-329] [AND ABS(distance) <= max_distance, :330-331];
+//   distance   = DISTANCE(q, t) with the same stranded/signed flags (:313-324; _distance.py:67-117);
+//   ORDER BY ABS(distance), t.start, t.end LIMIT k (:391-395).  Fewer than k candidates -> fewer rows; a query
+//   row without candidates produces nothing (CROSS JOIN LATERAL).
+//
+// Device formulation.  The target index is sorted by (start, end) [GIQLB_INDEX_TIE_BY_END], optionally grouped
+// into strand blocks, with two derived arrays: the running max of end (pmax) and the ends in ascending order
+// (ge_sorted / pos_by_end; ties keep start order).  With the CASE of _distance.py every target row falls in
+// exactly one class, each an ordered stream:
+//   overlap     q.start < t.end AND q.end > t.start   |d| = 0      index order = (start, end) order
+//   downstream  q.end <= t.start                       |d| = t.start - q.end + 1, ascending along the index
+//   upstream    otherwise (t.end <= q.start)           |d| = q.start - t.end + 1, ascending walking ge_sorted
+//               backwards; rows tied on end are visited in start order (forward inside the tie group)
+// At equal |d| upstream rows start before downstream rows, so the answer is: the first overlaps, then a 2-way merge
+// of the two streams that prefers upstream on ties.  Query rows are probed from their raw columns; their
+// coordinates are clamped into the chromosome's guard cells for the searches (this preserves every comparison
+// with indexed rows) while distances use the unclamped canonical coordinates.
+#include "common.cuh"
+#include "distance.cuh"
+#include "scan.cuh"
+
+namespace {
+
+struct TargetView {
+    const uint32_t* gs;
+    const uint32_t* ge;
+    const int32_t* rid;
+    const uint8_t* strand;       // nullable
+    const uint32_t* pmax;
+    const uint32_t* ge_sorted;   // per strand block
+    const int32_t* pos_by_end;   // block-relative position of each sorted end
+    const int64_t* block_off;    // device [257]; nullptr when not grouped
+    int64_t n;
+};
+
+struct NearestArgs {
+    int k;
+    long long max_distance;   // < 0: none
+    int stranded;             // both tables carry a strand column and stranded := true
+    int signed_;
+};
+
+__global__ void __launch_bounds__(128)
+nearest_kernel(ProbeCols Q, const uint8_t* __restrict__ q_strand, TargetView T, NearestArgs A,
+               int32_t* __restrict__ tmp_t, int32_t* __restrict__ tmp_d, uint8_t* __restrict__ tmp_v,
+               uint32_t* __restrict__ cnt) {
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < Q.n; i += (int64_t)gridDim.x * blockDim.x) {
+        uint32_t n_out = 0;
+        const int64_t slot0 = i * A.k;
+        uint32_t qs_lin, qe_lin;
+        const uint8_t sq = A.stranded ? q_strand[i] : (uint8_t)GIQLB_STRAND_PLUS;
+        int64_t blo = 0, bhi = T.n;
+        bool any = T.n > 0 && probe_linearise(Q, i, qs_lin, qe_lin);
+        if (any && A.stranded) {
+            if (sq == GIQLB_STRAND_NULL) any = false;   // NULL = anything is never true
+            else {
+                blo = T.block_off[sq];
+                bhi = T.block_off[sq + 1];
+                any = bhi > blo;
+            }
+        }
+        if (any) {
+            const int32_t c = Q.code[i];
+            const uint32_t cb_lo = __ldg(Q.base + c), cb_hi = __ldg(Q.base + c + 1);
+            const long long lo_c = __ldg(Q.lo32 + c);
+            const long long qs = (long long)Q.start[i] + Q.sadj, qe = (long long)Q.end[i] + Q.eadj;
+            const uint32_t* gs = T.gs + blo;
+            const uint32_t* ge = T.ge + blo;
+            const int32_t* rid = T.rid + blo;
+            const int64_t nb = bhi - blo;
+            // canonical coordinate of a linear one on chromosome c
+            auto canon = [&](uint32_t g) { return lo_c + (long long)g - (long long)cb_lo - 1; };
+            const bool null_dist = A.stranded && (sq == GIQLB_STRAND_DOT || sq == GIQLB_STRAND_QMARK);
+            auto emit = [&](int64_t pos) {
+                long long d = 0;
+                bool ok = !null_dist && giqlb_distance_dev(qs, qe, sq, canon(gs[pos]), canon(ge[pos]), sq, A.stranded != 0,
+                                                           A.signed_ != 0, &d);
+                tmp_t[slot0 + n_out] = rid[pos];
+                tmp_d[slot0 + n_out] = ok ? (int32_t)d : 0;
+                tmp_v[slot0 + n_out] = ok ? 1 : 0;
+                n_out++;
+            };
+            const int64_t ub = lower_bound_dev<uint32_t, int64_t>(gs, 0, nb, qe_lin);   // first row with t.start >= q.end
+            if (null_dist) {
+                // every distance is NULL: ORDER BY degenerates to (start, end) over the chromosome's rows of the block,
+                // and ABS(NULL) <= max_distance keeps nothing (nearest.py:330-331)
+                if (A.max_distance < 0) {
+                    int64_t j = upper_bound_dev<uint32_t, int64_t>(gs, 0, nb, cb_lo);
+                    for (; j < nb && n_out < (uint32_t)A.k && gs[j] < cb_hi; j++) emit(j);
+                }
+            } else {
+                // 1. overlaps, in index order
+                const uint32_t* pmax = T.pmax + blo;
+                int64_t j = upper_bound_dev<uint32_t, int64_t>(pmax, 0, ub, qs_lin);   // first row whose running max end > q.start
+                for (; j < ub && n_out < (uint32_t)A.k; j++)
+                    if (ge[j] > qs_lin) emit(j);
+                // 2. merge of the upstream and downstream streams
+                if (n_out < (uint32_t)A.k) {
+                    const uint32_t* ges = T.ge_sorted + blo;
+                    const int32_t* pbe = T.pos_by_end + blo;
+                    int64_t dn = ub;                                                                  // downstream cursor
+                    int64_t up_hi = upper_bound_dev<uint32_t, int64_t>(ges, 0, nb, qs_lin);          // rows with t.end <= q.start: [.., up_hi)
+                    int64_t grp_lo = up_hi, grp_cur = up_hi;                                          // current tie group [grp_cur, up_hi) is empty
+                    const long long maxd = A.max_distance;
+                    while (n_out < (uint32_t)A.k) {
+                        // next upstream candidate: inside the current tie group, else open the next group below
+                        long long m_up = -1, m_dn = -1;
+                        int64_t up_pos = -1;
+                        while (true) {
+                            if (grp_cur < up_hi) {
+                                int64_t p = pbe[grp_cur];
+                                if (gs[p] >= qe_lin) {   // q.end <= t.start: that row is DOWNSTREAM by the CASE order
+                                    grp_cur++;
+                                    continue;
+                                }
+                                up_pos = p;
+                                m_up = qs - canon(ges[grp_cur]) + 1;
+                                break;
+                            }
+                            if (grp_lo <= 0) break;
+                            const uint32_t v = ges[grp_lo - 1];
+                            if (v <= cb_lo) break;   // left the chromosome
+                            up_hi = grp_lo;
+                            grp_lo = lower_bound_dev<uint32_t, int64_t>(ges, 0, up_hi, v);
+                            grp_cur = grp_lo;
+                        }
+                        if (dn < nb && gs[dn] < cb_hi) m_dn = canon(gs[dn]) - qe + 1;
+                        if (maxd >= 0) {
+                            if (m_up > maxd) m_up = -1;
+                            if (m_dn > maxd) m_dn = -1;
+                        }
+                        if (m_up < 0 && m_dn < 0) break;
+                        if (m_up >= 0 && (m_dn < 0 || m_up <= m_dn)) {
+                            emit(up_pos);
+                            grp_cur++;
+                        } else {
+                            emit(dn);
+                            dn++;
+                        }
+                    }
+                }
+            }
+        }
+        cnt[i] = n_out;
+    }
+}
+
+struct InCnt {
+    const uint32_t* cnt;
+    __device__ unsigned long long operator()(int64_t i) const { return cnt[i]; }
+};
+struct OutCompactNearest {
+    const int32_t* tmp_t;
+    const int32_t* tmp_d;
+    const uint8_t* tmp_v;
+    int k;
+    int32_t *out_q, *out_t, *out_d;
+    uint8_t* out_v;
+    unsigned long long* total;
+    int64_t n;
+    __device__ void operator()(int64_t i, unsigned long long excl, unsigned long long v) const {
+        for (unsigned long long j = 0; j < v; j++) {
+            out_q[excl + j] = (int32_t)i;
+            out_t[excl + j] = tmp_t[i * k + j];
+            out_d[excl + j] = tmp_d[i * k + j];
+            out_v[excl + j] = tmp_v[i * k + j];
+        }
+        if (i == n - 1) *total = excl + v;
+    }
+};
+
+}  // namespace
+
+extern "C" int giqlb_nearest(giqlb_ctx* ctx, const giqlb_layout* lay, const int32_t* q_code, const int32_t* q_start,
+                             const int32_t* q_end, const uint8_t* q_strand, int64_t n_q, int32_t q_start_adj, int32_t q_end_adj,
+                             giqlb_index* T, int k, int64_t max_distance, int stranded, int signed_, int32_t* out_q,
+                             int32_t* out_t, int32_t* out_dist, uint8_t* out_valid, int64_t capacity, int64_t* n_out_host) {
+    using namespace giqlb_scan;
+    if (!ctx || !T || !n_out_host || k < 1 || n_q < 0) return giqlb_fail(ctx, GIQLB_ERR_INVALID, "nearest: bad argument");
+    if (T->layout != lay) return giqlb_fail(ctx, GIQLB_ERR_INVALID, "nearest: target index was built on a different layout");
+    if (!T->tie_by_end) return giqlb_fail(ctx, GIQLB_ERR_INVALID, "nearest: target index must be built with GIQLB_INDEX_TIE_BY_END");
+    if (stranded && (!q_strand || !T->strand || !T->grouped_by_strand))
+        return giqlb_fail(ctx, GIQLB_ERR_INVALID, "nearest: stranded needs a query strand column and a strand-grouped target index");
+    if (!stranded && T->grouped_by_strand) return giqlb_fail(ctx, GIQLB_ERR_INVALID, "nearest: unstranded search over a strand-grouped index");
+    if ((double)k * (double)n_q > (double)capacity) {
+        *n_out_host = (int64_t)k * n_q;
+        return giqlb_fail(ctx, GIQLB_ERR_CAPACITY, "nearest: outputs must hold k * n_q = %lld rows", (long long)k * (long long)n_q);
+    }
+    begin_call(ctx);
+    *n_out_host = 0;
+    if (n_q == 0) return end_call(ctx);
+    if (!out_q || !out_t || !out_dist || !out_valid) return giqlb_fail(ctx, GIQLB_ERR_INVALID, "nearest: null output");
+    ProbeCols Q;
+    GIQLB_TRY(probe_cols(ctx, lay, q_code, q_start, q_end, n_q, q_start_adj, q_end_adj, &Q));
+    GIQLB_TRY(giqlb_index_ensure_pmax(ctx, T));
+    GIQLB_TRY(giqlb_index_ensure_end_sorted(ctx, T));
+    int32_t *tmp_t = nullptr, *tmp_d = nullptr;
+    uint8_t* tmp_v = nullptr;
+    uint32_t* cnt = nullptr;
+    unsigned long long* total = reinterpret_cast<unsigned long long*>(ctx->d_scalars + 10);
+    const size_t slots = (size_t)k * (size_t)n_q;
+    int st = dev_alloc(ctx, &tmp_t, slots);
+    if (st == GIQLB_OK) st = dev_alloc(ctx, &tmp_d, slots);
+    if (st == GIQLB_OK) st = dev_alloc(ctx, &tmp_v, slots);
+    if (st == GIQLB_OK) st = dev_alloc(ctx, &cnt, (size_t)n_q);
+    if (st == GIQLB_OK) {
+        PhaseSpan ps(ctx, GIQLB_PH_NEAREST);
+        cudaMemsetAsync(total, 0, 8, ctx->stream);
+        TargetView V{T->gs, T->ge, T->rid, T->strand, T->pmax, T->ge_sorted, T->pos_by_end,
+                     T->grouped_by_strand ? T->d_block_off : nullptr, T->n};
+        NearestArgs A{k, max_distance < 0 ? -1ll : (long long)max_distance, stranded != 0, signed_ != 0};
+        int64_t blocks = ceil_div(n_q, 128), cap = (int64_t)ctx->sm_count * 32;
+        nearest_kernel<<<(unsigned)(blocks < cap ? blocks : cap), 128, 0, ctx->stream>>>(Q, q_strand, V, A, tmp_t, tmp_d, tmp_v, cnt);
+        ctx->launches_this_call++;
+        ctx->stats.kernels_total++;
+        if (cudaGetLastError() != cudaSuccess) st = giqlb_fail(ctx, GIQLB_ERR_CUDA, "nearest: launch failed");
+        if (st == GIQLB_OK)
+            st = launch_scan<OpAddU64>(ctx, n_q, InCnt{cnt},
+                                       OutCompactNearest{tmp_t, tmp_d, tmp_v, k, out_q, out_t, out_dist, out_valid, total, n_q});
+    }
+    if (st == GIQLB_OK) st = fetch_scalars(ctx, total, 1);
+    dev_free(ctx, tmp_t);
+    dev_free(ctx, tmp_d);
+    dev_free(ctx, tmp_v);
+    dev_free(ctx, cnt);
+    if (st != GIQLB_OK) return st;
+    *n_out_host = ctx->h_scalars[0];
+    ctx->stats.rows_in[0] = n_q;
+    ctx->stats.rows_in[1] = T->n;
+    ctx->stats.rows_out = *n_out_host;
+    ctx->stats.algorithmic_bytes = 12 * n_q + 12 * T->n + (stranded ? n_q + T->n : 0) + 12 * *n_out_host;
+    return end_call(ctx);
+}

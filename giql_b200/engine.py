@@ -118,6 +118,65 @@ class PairResult:
         return self.left_rows.cpu().numpy(), self.right_rows.cpu().numpy()
 
 
+@dataclass
+class NearestResult:
+    """(query_row, target_row, distance) rows; ``valid`` is 0 where the distance is SQL NULL."""
+
+    query_rows: torch.Tensor
+    target_rows: torch.Tensor
+    distance: torch.Tensor
+    valid: torch.Tensor
+
+    def __len__(self) -> int:
+        return int(self.query_rows.numel())
+
+    def rows(self):
+        q, t, d, v = (x.cpu().tolist() for x in (self.query_rows, self.target_rows, self.distance, self.valid))
+        return [(qi, ti, di if vi else None) for qi, ti, di, vi in zip(q, t, d, v)]
+
+
+@dataclass
+class DisjoinResult:
+    """(target_row, segment_start, segment_end), canonical 0-based half-open coordinates."""
+
+    target_rows: torch.Tensor
+    start: torch.Tensor
+    end: torch.Tensor
+
+    def __len__(self) -> int:
+        return int(self.target_rows.numel())
+
+    def rows(self):
+        return sorted(zip(self.target_rows.cpu().tolist(), self.start.cpu().tolist(), self.end.cpu().tolist()))
+
+
+@dataclass
+class MergeResult:
+    """Merged regions (device tensors): chromosome code, start, end, optional strand code, COUNT(*)."""
+
+    engine: Any
+    dictionary: "Dictionary"
+    code: torch.Tensor
+    start: torch.Tensor
+    end: torch.Tensor
+    strand: Optional[torch.Tensor]
+    count: torch.Tensor
+
+    def __len__(self) -> int:
+        return int(self.code.numel())
+
+    def rows(self):
+        """Host tuples ``(chrom, [strand,] start, end, count)`` in a canonical sorted order."""
+        names = self.dictionary.names
+        c, s, e, k = (x.cpu().tolist() for x in (self.code, self.start, self.end, self.count))
+        if self.strand is None:
+            rows = [(names[ci], si, ei, ki) for ci, si, ei, ki in zip(c, s, e, k)]
+        else:
+            st = [self.engine.strand_literal(v) for v in self.strand.cpu().tolist()]
+            rows = [(names[ci], ti, si, ei, ki) for ci, ti, si, ei, ki in zip(c, st, s, e, k)]
+        return sorted(rows, key=lambda r: tuple((v is None, v) for v in r))
+
+
 class DeviceTable:
     """Columns of one genomic table resident in HBM."""
 
@@ -179,17 +238,19 @@ class _Layout:
 
 class _Index:
     def __init__(self, engine: "Engine", layout: _Layout, t: DeviceTable, raw: bool = False, with_strand: bool = False,
-                 tie_by_end: bool = False):
+                 tie_by_end: bool = False, rows: Optional[torch.Tensor] = None):
         self.e = engine
         self.layout = layout   # keep the layout alive as long as the index
+        self.rows = rows       # ... and the row selection until the stream has consumed it
         self.h = ctypes.c_void_p()
         sadj, eadj = (0, 0) if raw else t.offsets
         strand = t.strand if with_strand else None
         if with_strand and strand is None:
             raise ValueError("stranded := true requires a strand column on the table")
         flags = _cabi.INDEX_TIE_BY_END if tie_by_end else 0
-        engine._check(engine.lib.giqlb_index_build(engine.ctx, layout.h, _ptr(t.codes), _ptr(t.start), _ptr(t.end),
-                                                  _ptr(strand), t.n, sadj, eadj, flags, ctypes.byref(self.h)))
+        n = t.n if rows is None else int(rows.numel())
+        engine._check(engine.lib.giqlb_index_build_rows(engine.ctx, layout.h, _ptr(t.codes), _ptr(t.start), _ptr(t.end),
+                                                       _ptr(strand), _ptr(rows), n, sadj, eadj, flags, ctypes.byref(self.h)))
 
     def info(self):
         d, ng, nb = ctypes.c_int64(), ctypes.c_int64(), ctypes.c_int32()
@@ -412,19 +473,43 @@ class Engine:
         """
         lay, il, ir = self._pair_indexes(left, right)
         try:
-            plan, total = ctypes.c_void_p(), ctypes.c_int64()
-            self._check(self.lib.giqlb_intersects_plan(self.ctx, il.h, ir.h, ctypes.byref(plan), ctypes.byref(total)))
-            try:
-                out_l = self._empty(total.value, torch.int32)
-                out_r = self._empty(total.value, torch.int32)
-                self._check(self.lib.giqlb_intersects_emit(self.ctx, plan, _ptr(out_l), _ptr(out_r)))
-            finally:
-                self.lib.giqlb_joinplan_free(self.ctx, plan)
-            return PairResult(out_l, out_r)
+            return self._join_indexes(il, ir)
         finally:
             il.free()
             ir.free()
             lay.free()
+
+    def _join_indexes(self, il: _Index, ir: _Index) -> PairResult:
+        """count -> scan -> emit over two indexes built on one layout."""
+        plan, total = ctypes.c_void_p(), ctypes.c_int64()
+        self._check(self.lib.giqlb_intersects_plan(self.ctx, il.h, ir.h, ctypes.byref(plan), ctypes.byref(total)))
+        try:
+            out_l = self._empty(total.value, torch.int32)
+            out_r = self._empty(total.value, torch.int32)
+            self._check(self.lib.giqlb_intersects_emit(self.ctx, plan, _ptr(out_l), _ptr(out_r)))
+        finally:
+            self.lib.giqlb_joinplan_free(self.ctx, plan)
+        return PairResult(out_l, out_r)
+
+    # ---- genome-range sharding (SURVEY.md §8(e); orchestration in giql_b200/sharding.py) -------------
+    def shard_cuts(self, lay: _Layout, left: DeviceTable, world: int) -> tuple[list[int], int]:
+        """Linear-coordinate cuts balancing the LEFT interval count over ``world`` ranges, and the widest
+        left interval (giqlb_shard_cuts).  Deterministic, so every rank computes the same cuts."""
+        cuts = (ctypes.c_uint32 * (world + 1))()
+        mw = ctypes.c_uint32()
+        sadj, eadj = left.offsets
+        self._check(self.lib.giqlb_shard_cuts(self.ctx, lay.h, _ptr(left.codes), _ptr(left.start), _ptr(left.end), left.n,
+                                              sadj, eadj, world, cuts, ctypes.byref(mw)))
+        return list(cuts), int(mw.value)
+
+    def shard_select(self, lay: _Layout, t: DeviceTable, gs_lo: int, gs_hi: int, ge_gt: int) -> torch.Tensor:
+        """Ascending ids of the rows with gs_lo <= linear start < gs_hi and linear end > ge_gt."""
+        rows = self._empty(t.n, torch.int32)
+        n_out = ctypes.c_int64()
+        sadj, eadj = t.offsets
+        self._check(self.lib.giqlb_shard_select(self.ctx, lay.h, _ptr(t.codes), _ptr(t.start), _ptr(t.end), t.n, sadj, eadj,
+                                                gs_lo, gs_hi, ge_gt, _ptr(rows), ctypes.byref(n_out)))
+        return rows[: n_out.value]
 
     def _probe(self, fn, left: DeviceTable, right: DeviceTable, out: torch.Tensor):
         d = self.encode(left, right)
@@ -465,6 +550,130 @@ class Engine:
         """int64[n_left]: number of right rows overlapping each left row (count_overlaps fast path,
         intersects_duckdb.py:432-548; the GROUP BY over distinct left keys is a host-side sum of these)."""
         return self._probe(self.lib.giqlb_intersects_count_rows, left, right, self._empty(left.n, torch.int64))
+
+    # ---- NEAREST -------------------------------------------------------------------------------------
+    def nearest(self, query: DeviceTable, target: DeviceTable, k: int = 1, max_distance: Optional[int] = None,
+                stranded: bool = False, signed: bool = False) -> "NearestResult":
+        """``query CROSS JOIN LATERAL NEAREST(target, reference := query.interval, k, max_distance, stranded, signed)``
+        -> (query_row, target_row, distance) rows, at most k per query row.
+        reference: src/giql/expanders/nearest.py:255-397; parameters :240-252 (k defaults to 1, must be >= 1)."""
+        k = int(k)
+        if k < 1:
+            raise ValueError("k must be a positive integer")
+        if max_distance is not None and int(max_distance) < 0:
+            raise ValueError("max_distance must be non-negative")
+        # the strand filter and the stranded CASE apply only when BOTH tables carry a strand column (nearest.py:304-307)
+        use_strand = bool(stranded) and query.strand is not None and target.strand is not None
+        self.encode(query, target)
+        cap = k * query.n
+        out_q, out_t, out_d = (self._empty(cap, torch.int32) for _ in range(3))
+        out_v = self._empty(cap, torch.uint8)
+        n_out = ctypes.c_int64(0)
+        if query.n and target.n:
+            lay = _Layout(self, len(query.dictionary))
+            lay.observe(target)
+            lay.finalize()
+            ix = _Index(self, lay, target, with_strand=use_strand, tie_by_end=True)
+            try:
+                if use_strand:
+                    self._check(self.lib.giqlb_index_group_by_strand(self.ctx, ix.h))
+                qs, qe = query.offsets
+                self._check(self.lib.giqlb_nearest(
+                    self.ctx, lay.h, _ptr(query.codes), _ptr(query.start), _ptr(query.end),
+                    _ptr(query.strand) if use_strand else None, query.n, qs, qe, ix.h, k,
+                    -1 if max_distance is None else int(max_distance), int(use_strand), int(bool(signed)),
+                    _ptr(out_q), _ptr(out_t), _ptr(out_d), _ptr(out_v), cap, ctypes.byref(n_out)))
+            finally:
+                ix.free()
+                lay.free()
+        m = n_out.value
+        return NearestResult(out_q[:m], out_t[:m], out_d[:m], out_v[:m])
+
+    # ---- CLUSTER / MERGE ---------------------------------------------------------------------------
+    def _self_index(self, t: DeviceTable, stranded: bool, raw: bool, tie_by_end: bool = False):
+        d = self.encode(t)
+        lay = _Layout(self, len(d))
+        lay.observe(t, raw=raw)
+        lay.finalize()
+        ix = _Index(self, lay, t, raw=raw, with_strand=stranded, tie_by_end=tie_by_end)
+        if stranded:
+            self._check(self.lib.giqlb_index_group_by_strand(self.ctx, ix.h))
+        return lay, ix
+
+    def strand_literal(self, code: int):
+        """Inverse of :meth:`strand_codes` for one code (None for SQL NULL)."""
+        if code == _cabi.STRAND_NULL:
+            return None
+        for lit, c in self._strand_codes.items():
+            if c == code:
+                return lit
+        raise KeyError(code)
+
+    def cluster(self, t: DeviceTable, distance: int = 0, stranded: bool = False) -> torch.Tensor:
+        """CLUSTER(interval[, distance][, stranded := true]) -> int32 cluster id per input row (1-based,
+        restarting per chrom[, strand] partition).  reference: src/giql/expanders/cluster.py:205-310, 430-434
+        (raw table coordinates: expressions.py:223-226)."""
+        out = self._empty(t.n, torch.int32)
+        if t.n == 0:
+            return out
+        lay, ix = self._self_index(t, stranded, raw=True)
+        try:
+            self._check(self.lib.giqlb_cluster(self.ctx, ix.h, int(distance or 0), _ptr(out)))
+        finally:
+            ix.free()
+            lay.free()
+        return out
+
+    def merge(self, t: DeviceTable, distance: int = 0, stranded: bool = False) -> "MergeResult":
+        """MERGE(interval[, distance][, stranded := true]) -> merged regions with COUNT(*), ordered by chrom, start
+        (strand block first when stranded).  reference: src/giql/expanders/merge.py:183-439."""
+        d = self.encode(t)
+        n = t.n
+        code, start, end = (self._empty(n, torch.int32) for _ in range(3))
+        strand = self._empty(n, torch.uint8) if stranded else None
+        count = self._empty(n, torch.int64)
+        m = ctypes.c_int64(0)
+        if n:
+            lay, ix = self._self_index(t, stranded, raw=True)
+            try:
+                self._check(self.lib.giqlb_merge(self.ctx, ix.h, int(distance or 0), _ptr(code), _ptr(start), _ptr(end),
+                                                 _ptr(strand), _ptr(count), n, ctypes.byref(m)))
+            finally:
+                ix.free()
+                lay.free()
+        k = m.value
+        return MergeResult(self, d, code[:k], start[:k], end[:k], None if strand is None else strand[:k], count[:k])
+
+    # ---- DISJOIN -------------------------------------------------------------------------------------
+    def disjoin(self, target: DeviceTable, reference: Optional[DeviceTable] = None) -> "DisjoinResult":
+        """DISJOIN(target[, reference]) -> (target_row, segment_start, segment_end) in canonical coordinates.
+        reference: src/giql/expanders/disjoin.py:102-202 (self-reference skips the coverage filter, :184-190)."""
+        ref = target if reference is None else reference
+        self.encode(target, ref)
+        empty = lambda: DisjoinResult(*(self._empty(0, torch.int32) for _ in range(3)))
+        if target.n == 0:
+            return empty()
+        lay = _Layout(self, len(target.dictionary))
+        lay.observe(ref)
+        lay.finalize()
+        ix = _Index(self, lay, ref)
+        try:
+            ts, te = target.offsets
+            args = (self.ctx, lay.h, _ptr(target.codes), _ptr(target.start), _ptr(target.end), target.n, ts, te, ix.h,
+                    int(reference is None))
+            n_out = ctypes.c_int64(0)
+            st = self.lib.giqlb_disjoin(*args, None, None, None, 0, ctypes.byref(n_out))   # sizing call
+            if st not in (_cabi.OK, _cabi.ERR_CAPACITY):
+                self._check(st)
+            m = n_out.value
+            if m == 0:
+                return empty()
+            row, s, e = (self._empty(m, torch.int32) for _ in range(3))
+            self._check(self.lib.giqlb_disjoin(*args, _ptr(row), _ptr(s), _ptr(e), m, ctypes.byref(n_out)))
+            return DisjoinResult(row, s, e)
+        finally:
+            ix.free()
+            lay.free()
 
     # ---- DISTANCE ---------------------------------------------------------------------------------
     def distance(self, a: DeviceTable, b: DeviceTable, a_rows: Optional[torch.Tensor] = None,

@@ -100,7 +100,9 @@ enum {
     GIQLB_PH_MERGE = 14,
     GIQLB_PH_NEAREST = 15,
     GIQLB_PH_OTHER = 16,
-    GIQLB_PH_COUNT = 17
+    GIQLB_PH_SHARD = 17,      /* genome-range partitioning (histogram, cuts, selection) */
+    GIQLB_PH_DISJOIN = 18,
+    GIQLB_PH_COUNT = 19
 };
 
 int giqlb_abi_version(void);
@@ -154,6 +156,11 @@ int giqlb_layout_tables(const giqlb_layout* lay, const uint32_t** base_dev, cons
 int giqlb_index_build(giqlb_ctx* ctx, const giqlb_layout* lay, const int32_t* code, const int32_t* start,
                       const int32_t* end, const uint8_t* strand, int64_t n, int32_t start_adj,
                       int32_t end_adj, int flags, giqlb_index** out);
+/* Same, over a selection: `rows` (device int32[n], nullable) lists the rows of the table that are indexed
+ * (a genome-range shard, giqlb_shard_select); the index carries rows[i] as row id. */
+int giqlb_index_build_rows(giqlb_ctx* ctx, const giqlb_layout* lay, const int32_t* code, const int32_t* start,
+                           const int32_t* end, const uint8_t* strand, const int32_t* rows, int64_t n,
+                           int32_t start_adj, int32_t end_adj, int flags, giqlb_index** out);
 int giqlb_index_free(giqlb_ctx* ctx, giqlb_index* ix);
 int64_t giqlb_index_rows(const giqlb_index* ix);
 /* device views of the sorted columns (library-owned, valid until giqlb_index_free) */
@@ -190,6 +197,60 @@ int giqlb_select_rows(giqlb_ctx* ctx, const uint8_t* flags, int64_t n, int want,
 int giqlb_intersects_count_rows(giqlb_ctx* ctx, const giqlb_layout* lay, const int32_t* code, const int32_t* start,
                                 const int32_t* end, int64_t n, int32_t start_adj, int32_t end_adj, giqlb_index* R,
                                 int64_t* counts_by_row);
+
+/* ---- NEAREST ----------------------------------------------------------------------------------------
+ * For every query row (raw columns, input order; canonical offsets q_*_adj) the k nearest rows of the target
+ * index T by ORDER BY ABS(distance), start, end (nearest.py:391-395), restricted to the query's chromosome,
+ * to its strand when `stranded` (both tables carry a strand column, nearest.py:304-307) and to
+ * ABS(distance) <= max_distance when max_distance >= 0 (nearest.py:330-331).  T must be built with
+ * GIQLB_INDEX_TIE_BY_END on `lay` (only the TARGET table needs to be observed) and, for stranded, grouped by
+ * strand.  Emits up to k rows per query: (query row, target row, distance, valid = 0 for SQL NULL distance);
+ * the outputs must hold k * n_q rows.  Rows tied on (|distance|, start, end) are order-ambiguous in the
+ * reference itself (nearest.py:366-372); here they come in index order (input order among full ties). */
+int giqlb_nearest(giqlb_ctx* ctx, const giqlb_layout* lay, const int32_t* q_code, const int32_t* q_start,
+                  const int32_t* q_end, const uint8_t* q_strand, int64_t n_q, int32_t q_start_adj, int32_t q_end_adj,
+                  giqlb_index* T, int k, int64_t max_distance, int stranded, int signed_, int32_t* out_q,
+                  int32_t* out_t, int32_t* out_dist, uint8_t* out_valid, int64_t capacity, int64_t* n_out_host);
+
+/* ---- CLUSTER / MERGE ------------------------------------------------------------------------------
+ * X: an index built with RAW coordinates (start_adj = end_adj = 0: cluster.py works on the table's own
+ * columns, expressions.py:223-226); for stranded := true build it with a strand column and call
+ * giqlb_index_group_by_strand first.  distance <= 0 means "no bridging" (cluster.py:266-272).
+ * cluster(): 1-based ids restarting per (chrom[, strand]) partition, written at the caller's row ids.
+ * merge():   regions ordered by ([strand block,] chrom, start); returns GIQLB_ERR_CAPACITY and the required
+ *            count in *n_out_host when capacity is too small (capacity = rows always suffices).
+ *            out_strand (nullable) receives the strand code of each region, out_count (nullable) COUNT(*).
+ * Rows with end < start are rejected (their grouping depends on the tie order of the executing engine). */
+int giqlb_cluster(giqlb_ctx* ctx, giqlb_index* X, int64_t distance, int32_t* cluster_id_by_input_row);
+int giqlb_merge(giqlb_ctx* ctx, giqlb_index* X, int64_t distance, int32_t* out_code, int32_t* out_start,
+                int32_t* out_end, uint8_t* out_strand, int64_t* out_count, int64_t capacity, int64_t* n_out_host);
+
+/* ---- DISJOIN ----------------------------------------------------------------------------------------
+ * Splits every target row (raw columns, canonical offsets t_*_adj) at the breakpoints (distinct starts and
+ * ends) of the reference index REF; with self_reference = 0 only segments whose start is covered by a
+ * reference row are kept (disjoin.py:184-190).  Emits (target row, segment start, segment end) in
+ * CANONICAL coordinates, grouped by target row in input order, segments ascending.  `lay` needs only the
+ * reference table observed.  GIQLB_ERR_CAPACITY + required count when the outputs are too small. */
+int giqlb_disjoin(giqlb_ctx* ctx, const giqlb_layout* lay, const int32_t* t_code, const int32_t* t_start,
+                  const int32_t* t_end, int64_t n_t, int32_t t_start_adj, int32_t t_end_adj, giqlb_index* REF,
+                  int self_reference, int32_t* out_row, int32_t* out_start, int32_t* out_end, int64_t capacity,
+                  int64_t* n_out_host);
+
+/* ---- genome-range sharding of a join across GPUs ------------------------------
+ * Every rank holds both tables and the same finalized layout.  shard_cuts(): histogram of the LEFT
+ * table's linearised starts -> cuts_host[world + 1] (cuts[0] = 0, cuts[world] = 2^32 - 1) such that every
+ * range [cuts[g], cuts[g+1]) holds ~n/world left rows; max_width_host = widest left interval (cells).
+ * Deterministic: every rank computes identical cuts without any exchange.
+ * shard_select(): ascending ids of the rows with  gs_lo <= linear start < gs_hi  AND  linear end > ge_gt.
+ *   owner-of-left-start:  left  rows of rank g:  (cuts[g], cuts[g+1], 0)
+ *   replicated straddlers: right rows of rank g:  (0, cuts[g+1] + max_width, cuts[g])
+ * out_rows must hold n entries. */
+int giqlb_shard_cuts(giqlb_ctx* ctx, const giqlb_layout* lay, const int32_t* code, const int32_t* start,
+                     const int32_t* end, int64_t n, int32_t start_adj, int32_t end_adj, int world,
+                     uint32_t* cuts_host, uint32_t* max_width_host);
+int giqlb_shard_select(giqlb_ctx* ctx, const giqlb_layout* lay, const int32_t* code, const int32_t* start,
+                       const int32_t* end, int64_t n, int32_t start_adj, int32_t end_adj, uint32_t gs_lo,
+                       uint32_t gs_hi, uint32_t ge_gt, int32_t* out_rows, int64_t* n_out_host);
 
 /* ---- DISTANCE (elementwise over already-paired rows) ------------------------------------------
  * out[i] = distance, valid[i] = 0 for SQL NULL.  strands may be NULL when !stranded.  *_adj are the

@@ -209,3 +209,159 @@ def test_join_full_size_properties(engine):
     assert torch.equal(packed, mp)
     ex = engine.exists(ta, tb)
     assert torch.equal(ex.bool(), cnt > 0)
+
+
+@pytest.mark.parametrize("world", [2, 8])
+def test_sharded_join_union_equals_single_gpu(world, engine, c_oracle):
+    """§8(e): every rank's genome-range shard joined on ONE GPU in turn; the union must be the exact multiset
+    (owner-of-left-start: nothing twice, nothing lost), left rows partitioned, ranges balanced on left count."""
+    import torch
+
+    from giql_b200 import synth
+    from giql_b200.sharding import EngineOps, shard_ranges
+
+    A, B = synth.peaks(200_000, 31), synth.peaks(150_000, 32)
+    ta = engine.table_from_codes(A["code"], A["start"], A["end"], A["names"])
+    tb = engine.table_from_codes(B["code"], B["start"], B["end"], ta.dictionary)
+    ops = EngineOps(engine)
+    plan = ops.plan(ta, tb, world)
+    cuts = plan["cuts"]
+    assert cuts[0] == 0 and cuts[-1] == 0xFFFFFFFF and all(a <= b for a, b in zip(cuts, cuts[1:]))
+    packed, n_left = [], []
+    for g in range(world):
+        l, r = ops.join_shard(plan, ta, tb, g)
+        packed.append((l.long() << 32) | r.long())
+        n_left.append(int(engine.shard_select(plan["layout"], ta, *shard_ranges(cuts, plan["max_width"], g)[0]).numel()))
+    ops.release(plan)
+    assert sum(n_left) == ta.n
+    assert max(n_left) - min(n_left) < 0.25 * ta.n / world + 70_000 / world   # equal counts up to one 2^16-cell bin
+    got = torch.sort(torch.cat(packed)).values.cpu().numpy()
+    exp = c_oracle.intersects_pairs(A["code"], A["start"], A["end"], B["code"], B["start"], B["end"], len(A["names"]))
+    assert np.array_equal(got, (exp[:, 0] << 32) | exp[:, 1])
+
+
+# ---- CLUSTER / MERGE ---------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("seed,distance,stranded", [(0, 0, False), (1, 0, True), (2, 25, False), (3, 100, True), (4, -1, False)])
+def test_cluster_merge_random_vs_oracle(seed, distance, stranded, engine):
+    rng = np.random.default_rng(200 + seed)
+    T = _rand(rng, 700, span=6000, max_len=40, min_len=0 if seed == 2 else 1, strands=["+", "-", ".", None] if stranded else None)
+    ob, eb = OracleBackend(), EngineBackend(engine)
+    assert eb.cluster(T, distance, stranded) == ob.cluster(T, distance, stranded)
+    assert eb.merge(T, distance, stranded) == ob.merge(T, distance, stranded)
+
+
+def test_cluster_merge_edge_cases(engine):
+    eb, ob = EngineBackend(engine), OracleBackend()
+    # containment (#214): running MAX(end), not the previous row's end (tests/integration/bedtools/test_cluster.py:69-106)
+    T = {"chrom": ["chr1"] * 3, "start": [100, 150, 400], "end": [500, 200, 600]}
+    assert eb.cluster(T) == [1, 1, 1] and eb.merge(T) == [("chr1", 100, 600, 3)]
+    # book-ended joins (>=); a 1-bp gap does not; distance bridges (test_merge.py:168-193)
+    T = {"chrom": ["chr1"] * 4, "start": [100, 200, 301, 500], "end": [200, 300, 350, 600]}
+    assert eb.cluster(T) == [1, 1, 2, 3]
+    assert [r[:3] for r in eb.merge(T, 100)] == [("chr1", 100, 350), ("chr1", 500, 600)]
+    # ids restart per chromosome; equal coordinates on different chromosomes never merge; input order is irrelevant
+    T = {"chrom": ["chr2", "chr1", "chr2", "chr1"], "start": [10, 10, 500, 15], "end": [20, 20, 600, 30]}
+    assert eb.cluster(T) == ob.cluster(T) == [1, 1, 2, 1]
+    assert eb.merge(T) == ob.merge(T)
+    # rows tied on start share an id
+    T = {"chrom": ["chr1"] * 3, "start": [5, 5, 5], "end": [9, 6, 7]}
+    assert eb.cluster(T) == [1, 1, 1]
+
+
+def test_cluster_merge_large_vs_c_oracle(engine, c_oracle):
+    """reads-as-intervals (BASELINE configs[4] shape) at 2M rows against the C restatement"""
+    import torch
+
+    from giql_b200 import synth
+
+    R = synth.reads(2_000_000, 20260109)
+    t = engine.table_from_codes(R["code"], R["start"], R["end"], R["names"])
+    for d in (0, 50):
+        ids = engine.cluster(t, distance=d).cpu().numpy()
+        assert np.array_equal(ids, c_oracle.cluster(R["code"], R["start"], R["end"], len(R["names"]), distance=d))
+        m = engine.merge(t, distance=d)
+        op, os_, oe, oc = c_oracle.merge(R["code"], R["start"], R["end"], len(R["names"]), distance=d)
+        assert len(m) == len(op)
+        assert np.array_equal(m.code.cpu().numpy(), op) and np.array_equal(m.start.cpu().numpy(), os_)
+        assert np.array_equal(m.end.cpu().numpy(), oe) and np.array_equal(m.count.cpu().numpy(), oc)
+        assert int(m.count.sum()) == t.n
+    # idempotence: merging the merged regions changes nothing
+    m = engine.merge(t)
+    t2 = engine.table_from_codes(m.code, m.start, m.end, m.dictionary)
+    m2 = engine.merge(t2)
+    assert torch.equal(m.start, m2.start) and torch.equal(m.end, m2.end) and torch.equal(m.code, m2.code)
+
+
+# ---- NEAREST -----------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("seed,k,maxd,stranded,signed", [
+    (0, 1, None, False, False), (1, 3, None, False, True), (2, 5, 40, False, False), (3, 2, None, True, False),
+    (4, 4, 25, True, True), (5, 1, 0, False, False), (6, 7, None, True, True), (7, 2, None, False, False)])
+def test_nearest_random_vs_oracle(seed, k, maxd, stranded, signed, engine):
+    """ties on (|distance|, start, end) are broken by target row id in both (the reference leaves them open)"""
+    rng = np.random.default_rng(300 + seed)
+    strands = ["+", "-", ".", "?", None] if stranded else None
+    Q = _rand(rng, 150, span=900, max_len=50, min_len=0 if seed == 7 else 1, strands=strands)
+    T = _rand(rng, 170, span=900, max_len=70, min_len=0 if seed == 7 else 1, strands=strands)
+    ob, eb = OracleBackend(), EngineBackend(engine)
+    got = eb.nearest(Q, T, k=k, max_distance=maxd, stranded=stranded, signed=signed)
+    exp = ob.nearest(Q, T, k=k, max_distance=maxd, stranded=stranded, signed=signed)
+    assert sorted(got, key=lambda r: (r[0], r[1])) == sorted(exp, key=lambda r: (r[0], r[1]))
+    # per query the engine emits in the reference's ORDER BY
+    by_q = {}
+    for q, t, d in got:
+        by_q.setdefault(q, []).append((t, d))
+    exp_q = {}
+    for q, t, d in exp:
+        exp_q.setdefault(q, []).append((t, d))
+    assert by_q == exp_q
+
+
+def test_nearest_edge_cases(engine):
+    eb = EngineBackend(engine)
+    Q = {"chrom": ["chr1", "chr2", "chr9"], "start": [1000, 10, 5], "end": [1100, 20, 6]}
+    T = {"chrom": ["chr1", "chr1", "chr1", "chr2"], "start": [50, 280, 1200, 500], "end": [60, 290, 1300, 600]}
+    # fewer than k candidates -> fewer rows; a chromosome without targets vanishes (CROSS JOIN LATERAL)
+    assert eb.nearest(Q, T, k=5) == [(0, 2, 101), (0, 1, 711), (0, 0, 941), (1, 3, 481)]
+    assert eb.nearest(Q, T, k=1, max_distance=100) == []
+    assert eb.nearest(Q, T, k=1, max_distance=101) == [(0, 2, 101)]
+    assert eb.nearest(Q, {"chrom": [], "start": [], "end": []}) == []
+    with pytest.raises(ValueError):
+        engine.nearest(eb._table(Q, None), eb._table(T, None), k=0)
+
+
+def test_nearest_c4_shape_properties(engine):
+    """peaks x gene-like targets, k = 5 stranded: |distance| is non-decreasing per query, every emitted target is
+    on the query's chromosome and strand, DISTANCE() of the pair equals the emitted distance, and k = 1 is the
+    prefix of k = 5."""
+    import torch
+
+    from giql_b200 import synth
+
+    Q, T = synth.peaks(300_000, 41), synth.genes(60_000, 42)
+    tq = engine.table_from_codes(Q["code"], Q["start"], Q["end"], Q["names"], strand=Q["strand_code"])
+    tt = engine.table_from_codes(T["code"], T["start"], T["end"], tq.dictionary, strand=T["strand_code"])
+    r5 = engine.nearest(tq, tt, k=5, stranded=True, signed=True)
+    q, t = r5.query_rows.long(), r5.target_rows.long()
+    assert len(r5) == 5 * tq.n and bool(r5.valid.all())
+    assert bool((tq.codes[q] == tt.codes[t]).all()) and bool((tq.strand[q] == tt.strand[t]).all())
+    d, v = engine.distance(tq, tt, q, t, stranded=True, signed=True)
+    assert torch.equal(d, r5.distance) and bool(v.all())
+    a = r5.distance.abs().view(-1, 5)
+    assert bool((a[:, 1:] >= a[:, :-1]).all()) and bool((r5.query_rows.view(-1, 5) == r5.query_rows.view(-1, 5)[:, :1]).all())
+    r1 = engine.nearest(tq, tt, k=1, stranded=True, signed=True)
+    first = torch.zeros(tq.n, dtype=torch.int64, device=q.device)
+    first[r5.query_rows.view(-1, 5)[:, 0].long()] = r5.target_rows.view(-1, 5)[:, 0].long()
+    got1 = torch.zeros_like(first)
+    got1[r1.query_rows.long()] = r1.target_rows.long()
+    assert torch.equal(first, got1)
+
+
+# ---- DISJOIN -------------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("seed", range(5))
+def test_disjoin_random_vs_oracle(seed, engine):
+    rng = np.random.default_rng(400 + seed)
+    T = _rand(rng, 200, span=700, max_len=90, min_len=0 if seed == 4 else 1)
+    R = _rand(rng, 120, span=700, max_len=60, chroms=("chr1", "chr2", "chr7"))
+    ob, eb = OracleBackend(), EngineBackend(engine)
+    assert eb.disjoin(T) == ob.disjoin(T)
+    assert eb.disjoin(T, R) == ob.disjoin(T, R)
