@@ -31,8 +31,10 @@ rs_histogram_kernel(const uint32_t* __restrict__ keys, int64_t n, int begin_bit,
     __shared__ uint32_t sh[RS_MAX_PASSES][RS_RADIX];
     for (int i = threadIdx.x; i < RS_MAX_PASSES * RS_RADIX; i += RS_THREADS) (&sh[0][0])[i] = 0;
     __syncthreads();
-    const int64_t n_vec = n >> 2;
-    const uint4* kv = reinterpret_cast<const uint4*>(keys);
+    // scalar head up to the first 16-byte boundary (sub-ranges of a larger array need not be aligned), vector body, scalar tail
+    const int64_t head = min(n, (int64_t)((16 - (reinterpret_cast<uintptr_t>(keys) & 15)) & 15) >> 2);
+    const int64_t n_vec = (n - head) >> 2;
+    const uint4* kv = reinterpret_cast<const uint4*>(keys + head);
     for (int64_t i = (int64_t)blockIdx.x * RS_THREADS + threadIdx.x; i < n_vec; i += (int64_t)gridDim.x * RS_THREADS) {
         uint4 k = ld_stream_u32x4(kv + i);
         uint32_t kk[4] = {k.x, k.y, k.z, k.w};
@@ -43,9 +45,10 @@ rs_histogram_kernel(const uint32_t* __restrict__ keys, int64_t n, int begin_bit,
                 if (p < n_passes) atomicAdd(&sh[p][(kk[j] >> (begin_bit + 8 * p)) & 255u], 1u);
         }
     }
-    // tail
-    if (blockIdx.x == 0) {
-        for (int64_t i = (n_vec << 2) + threadIdx.x; i < n; i += RS_THREADS) {
+    if (blockIdx.x == 0) {   // at most 3 head keys and 3 tail keys
+        const int64_t tail0 = head + (n_vec << 2);
+        const int64_t i = threadIdx.x < head ? (int64_t)threadIdx.x : tail0 + ((int64_t)threadIdx.x - head);
+        if (i < n && threadIdx.x < 8) {
             uint32_t k = keys[i];
             for (int p = 0; p < n_passes; p++) atomicAdd(&sh[p][(k >> (begin_bit + 8 * p)) & 255u], 1u);
         }
