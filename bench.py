@@ -372,7 +372,8 @@ def run_b200(args):
 
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
-        "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "int32",
+        "ms_per_step": ms_per_step, "ms_per_step_min_median_max": [round(min(step_ms), 4), round(float(np.median(step_ms)), 4), round(max(step_ms), 4)],
+        "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "int32",
         "data": "synthetic",
         "config": {"workload": workload_name(args.rows), "pairs": pairs, "rows_left": n_l, "rows_right": n_r,
                    "sharding": "single GPU" if world == 1 else f"{world} contiguous genome ranges balanced on left interval count; "

@@ -55,6 +55,7 @@ PROTOTYPES = {
     "giqlb_destroy": (c_int, [_P]),
     "giqlb_last_error": (c_char_p, [_P]),
     "giqlb_sync": (c_int, [_P]),
+    "giqlb_trim": (c_int, [_P]),
     "giqlb_stats": (c_int, [_P, POINTER(Stats)]),
     "giqlb_profile_enable": (c_int, [_P, c_int]),
     "giqlb_profile_read": (c_int, [_P, POINTER(ctypes.c_double), POINTER(c_int64)]),

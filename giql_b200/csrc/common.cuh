@@ -6,7 +6,9 @@
 #include <stdio.h>
 #include <string.h>
 
+#include <map>
 #include <string>
+#include <unordered_map>
 #include <vector>
 
 #include "../../include/giqlb.h"
@@ -25,6 +27,12 @@ struct giqlb_ctx {
     int* d_err = nullptr;           // device int[4]: sticky kernel-side error flags ([0] look-back spin limit)
     giqlb_stats_t stats = {};
     int32_t launches_this_call = 0;
+    // Scratch cache.  Every allocation of a context is used on ITS stream only, so a freed block can be handed
+    // out again immediately (stream order protects it) without a driver call: dev_free parks the block here,
+    // dev_alloc takes the smallest parked block that fits (within 2x) before falling back to cudaMalloc.
+    std::multimap<size_t, void*> cache_free;
+    std::unordered_map<void*, size_t> cache_live;
+    size_t cache_bytes = 0;   // bytes owned (parked + live)
     // per-phase CUDA-event profiling (giqlb_profile_*): pairs of events recorded around kernel launches
     bool prof_enabled = false;
     struct ProfSpan { int phase; cudaEvent_t start, stop; };
@@ -109,8 +117,11 @@ struct giqlb_index {
 struct giqlb_joinplan {
     const giqlb_index* L = nullptr;
     const giqlb_index* R = nullptr;
-    int64_t tiles_a = 0, tiles_b = 0;
-    unsigned long long* tile_off = nullptr;   // [tiles_a + tiles_b + 1] exclusive offsets (device)
+    int64_t n_tiles = 0;
+    int32_t* part = nullptr;                  // [n_tiles + 1] merge-path partition: L rows before each tile (fast path)
+    uint32_t* item_code = nullptr;            // [n_tiles * 1024] run start/class/length of every merged row (fast path)
+    unsigned long long* tile_off = nullptr;   // [n_tiles + 1] exclusive pair offsets (device)
+    unsigned long long* unit_off = nullptr;   // [n_tiles + 1] exclusive emit-work-unit offsets (fast path)
     int64_t total = 0;
     bool general = false;                     // degenerate-interval path (literal predicate scan)
 };
@@ -148,17 +159,48 @@ static inline int giqlb_fail(giqlb_ctx* ctx, int code, const char* fmt, ...) {
         CUDA_TRY((ctx), cudaGetLastError()); \
     } while (0)
 
-template <typename T>
-static inline int dev_alloc(giqlb_ctx* ctx, T** p, size_t count) {
+static inline int dev_alloc_bytes(giqlb_ctx* ctx, void** p, size_t bytes) {
     *p = nullptr;
-    size_t bytes = (count ? count : 1) * sizeof(T);
-    bytes = (bytes + 255) & ~(size_t)255;   // keep vector loads of a padded tail in bounds
-    CUDA_TRY(ctx, cudaMallocAsync((void**)p, bytes, ctx->stream));
+    bytes = ((bytes ? bytes : 1) + 511) & ~(size_t)511;   // keeps vector loads of a padded tail in bounds
+    auto it = ctx->cache_free.lower_bound(bytes);
+    if (it != ctx->cache_free.end() && it->first <= 2 * bytes + 4096) {
+        *p = it->second;
+        ctx->cache_live.emplace(it->second, it->first);
+        ctx->cache_free.erase(it);
+        return GIQLB_OK;
+    }
+    cudaError_t e = cudaMalloc(p, bytes);
+    if (e == cudaErrorMemoryAllocation) {   // give the parked blocks back to the driver and retry once
+        cudaGetLastError();
+        cudaStreamSynchronize(ctx->stream);
+        for (auto& kv : ctx->cache_free) {
+            cudaFree(kv.second);
+            ctx->cache_bytes -= kv.first;
+        }
+        ctx->cache_free.clear();
+        e = cudaMalloc(p, bytes);
+    }
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        *p = nullptr;
+        return giqlb_fail(ctx, e == cudaErrorMemoryAllocation ? GIQLB_ERR_NOMEM : GIQLB_ERR_CUDA, "cudaMalloc(%zu) -> %s", bytes,
+                          cudaGetErrorString(e));
+    }
+    ctx->cache_live.emplace(*p, bytes);
+    ctx->cache_bytes += bytes;
     return GIQLB_OK;
 }
 template <typename T>
+static inline int dev_alloc(giqlb_ctx* ctx, T** p, size_t count) {
+    return dev_alloc_bytes(ctx, reinterpret_cast<void**>(p), count * sizeof(T));
+}
+template <typename T>
 static inline void dev_free(giqlb_ctx* ctx, T* p) {
-    if (p) cudaFreeAsync((void*)p, ctx->stream);
+    if (!p) return;
+    auto it = ctx->cache_live.find((void*)p);
+    if (it == ctx->cache_live.end()) return;   // not ours (or freed twice): never hand it to the driver
+    ctx->cache_free.emplace(it->second, it->first);
+    ctx->cache_live.erase(it);
 }
 
 static inline int64_t ceil_div(int64_t a, int64_t b) { return (a + b - 1) / b; }

@@ -21,12 +21,6 @@ extern "C" int giqlb_create(int device, void* cuda_stream, giqlb_ctx** out) {
     // NULL selects the legacy default stream: the caller's other work on that stream (PyTorch's default
     // stream has handle 0) stays ordered with ours.  The library never creates a stream of its own.
     ctx->stream = (cudaStream_t)cuda_stream;
-    // keep freed blocks in the stream-ordered pool instead of returning them to the driver each sync
-    cudaMemPool_t pool;
-    if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) {
-        uint64_t threshold = UINT64_MAX;
-        cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &threshold);
-    }
     if (cudaMallocHost((void**)&ctx->h_scalars, 64 * sizeof(int64_t)) != cudaSuccess ||
         cudaMalloc((void**)&ctx->d_scalars, 64 * sizeof(int64_t)) != cudaSuccess ||
         cudaMalloc((void**)&ctx->d_err, 4 * sizeof(int)) != cudaSuccess ||
@@ -45,6 +39,8 @@ extern "C" int giqlb_destroy(giqlb_ctx* ctx) {
     cudaStreamSynchronize(ctx->stream);
     for (auto& sp : ctx->prof_spans) { cudaEventDestroy(sp.start); cudaEventDestroy(sp.stop); }
     for (auto e : ctx->prof_free_events) cudaEventDestroy(e);
+    for (auto& kv : ctx->cache_free) cudaFree(kv.second);
+    for (auto& kv : ctx->cache_live) cudaFree(kv.first);   // objects the caller never freed
     if (ctx->h_scalars) cudaFreeHost(ctx->h_scalars);
     if (ctx->d_scalars) cudaFree(ctx->d_scalars);
     if (ctx->d_err) cudaFree(ctx->d_err);
@@ -60,6 +56,17 @@ extern "C" int giqlb_sync(giqlb_ctx* ctx) {
     int h_err[4];
     CUDA_TRY(ctx, cudaMemcpy(h_err, ctx->d_err, sizeof(h_err), cudaMemcpyDeviceToHost));
     if (h_err[0]) return giqlb_fail(ctx, GIQLB_ERR_INTERNAL, "look-back spin limit exceeded (kernel-side)");
+    return GIQLB_OK;
+}
+
+extern "C" int giqlb_trim(giqlb_ctx* ctx) {
+    if (!ctx) return GIQLB_ERR_INVALID;
+    CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    for (auto& kv : ctx->cache_free) {
+        cudaFree(kv.second);
+        ctx->cache_bytes -= kv.first;
+    }
+    ctx->cache_free.clear();
     return GIQLB_OK;
 }
 

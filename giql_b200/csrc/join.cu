@@ -13,12 +13,20 @@
 // overlapping pairs split into two disjoint classes, each a CONTIGUOUS run of a start-sorted array:
 //     class A  (r starts inside l, or at l's start)   l.gs <= r.gs <  l.ge   -> for each l a run of R
 //     class B  (l starts strictly inside r)           r.gs <  l.gs <  r.ge   -> for each r a run of L
-// so counting is two binary searches per row, no candidate is ever filtered out, and emit work is exactly
-// the output size.  Rows are grouped in item tiles of 1024; the count pass stores one total per tile, one
-// CTA scans the totals, and the emit pass cuts the combined (items + outputs) work line into equal chunks
-// (merge-path partitioning at tile granularity): a chunk recomputes the runs of the tiles it touches and
-// writes its slice of the output with a per-slot search in shared memory, so a tile with a huge output is
-// shared by many CTAs and a desert of empty tiles is shared out as well.
+// so counting needs two searches per row, no candidate is ever filtered out, and emit work is exactly the
+// output size.  Both classes are processed by ONE sweep over the merge of the two start arrays ("L before R on
+// ties"): a merge-path partition kernel cuts the merged sequence into tiles of JT rows; a tile holds L[x0, x1)
+// and R[y0, y1), and the merge rank of every row is the START of its run in the other table — inside the
+// tile's own window by construction.  A CTA stages both windows (plus J_EXT rows beyond each, which covers
+// the END of almost every run) in shared memory with coalesced loads, so every input row is read from HBM
+// once per pass and all searches run in shared memory; the rare run that leaves the window continues with a
+// galloping search in global memory.
+//   count pass : per-tile pair count                       (reads gs, ge of both tables)
+//   scan       : one CTA turns tile counts into pair offsets and emit work units; a tile whose output
+//                exceeds J_PART pairs is split into several units, so a skewed tile is shared by many CTAs
+//   emit pass  : persistent CTAs loop over the units, recompute the tile's runs and write their slice; each
+//                thread produces 8 CONSECUTIVE output pairs (one search in the tile's offset table, then a walk),
+//                stored as 16-byte vectors.
 //
 // General path (some row has end <= start): the literal predicate is scanned over the candidates
 //     j in [first j with pmax[j] > l.gs,  lower_bound(R.gs, l.ge))        pmax = running max of R.ge
@@ -28,9 +36,12 @@
 namespace {
 
 constexpr int JB = 256;             // threads per CTA
-constexpr int J_IPT = 4;
-constexpr int JT = JB * J_IPT;      // items per tile
-constexpr int J_CHUNK = 8192;       // work units (items + outputs) per emit chunk
+constexpr int JT = 1024;            // merged rows per tile (fast path) / left rows per tile (general path)
+constexpr int J_IPT = JT / JB;
+constexpr int J_EXT = 512;          // rows staged beyond the tile's own part of each table
+constexpr int JW = JT + J_EXT;      // staged window capacity per table
+constexpr int J_PART = 8192;        // output pairs per emit work unit
+constexpr int J_OPT = 8;            // consecutive outputs per thread in the emit loop
 
 struct JoinSide {
     const uint32_t* gs;
@@ -51,128 +62,304 @@ __device__ __forceinline__ int64_t lb_gallop(const uint32_t* __restrict__ y, int
     return lower_bound_dev<uint32_t, int64_t>(y, lo + 1, hi, x);
 }
 
-// run [lo, hi) of Y matched by item x.  CLASS_B == false: y.gs in [x.gs, x.ge); true: y.gs in (x.gs, x.ge)
-template <bool CLASS_B>
-__device__ __forceinline__ void item_run(uint32_t xgs, uint32_t xge, const uint32_t* __restrict__ ygs, int64_t ny,
-                                         int64_t& lo, int64_t& hi) {
-    lo = CLASS_B ? upper_bound_dev<uint32_t, int64_t>(ygs, 0, ny, xgs) : lower_bound_dev<uint32_t, int64_t>(ygs, 0, ny, xgs);
-    hi = lb_gallop(ygs, lo, ny, xge);
+// shared-memory searches over a[lo, hi)
+__device__ __forceinline__ int s_lower_bound(const uint32_t* a, int lo, int hi, uint32_t x) {
+    while (lo < hi) {
+        int mid = (lo + hi) >> 1;
+        if (a[mid] < x) lo = mid + 1; else hi = mid;
+    }
+    return lo;
+}
+__device__ __forceinline__ int s_upper_bound(const uint32_t* a, int lo, int hi, uint32_t x) {
+    while (lo < hi) {
+        int mid = (lo + hi) >> 1;
+        if (a[mid] <= x) lo = mid + 1; else hi = mid;
+    }
+    return lo;
+}
+// first idx in [lo, hi) with a[idx] >= x, galloping from lo (the run end is usually a few rows away)
+__device__ __forceinline__ int s_gallop(const uint32_t* a, int lo, int hi, uint32_t x) {
+    if (lo >= hi || a[lo] >= x) return lo;
+    int step = 1;                    // invariant: a[lo] < x
+    while (lo + step < hi && a[lo + step] < x) {
+        lo += step;
+        step <<= 1;
+    }
+    int top = lo + step < hi ? lo + step : hi;
+    return s_lower_bound(a, lo + 1, top, x);
 }
 
-// ---- count pass: one total per item tile ---------------------------------------------------------
+// number of entries of a[0, n) that are <= x
+__device__ __forceinline__ int s_upper_bound_u64(const unsigned long long* a, int n, unsigned long long x) {
+    int lo = 0, hi = n;
+    while (lo < hi) {
+        int mid = (lo + hi) >> 1;
+        if (a[mid] <= x) lo = mid + 1; else hi = mid;
+    }
+    return lo;
+}
+
+// ---- merge-path partition: part[t] = number of L rows among the first t*JT rows of the merge -----------
+__global__ void __launch_bounds__(256)
+join_partition_kernel(const uint32_t* __restrict__ lgs, int64_t nl, const uint32_t* __restrict__ rgs, int64_t nr,
+                      int64_t n_tiles, int32_t* __restrict__ part) {
+    const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t > n_tiles) return;
+    int64_t d = t * JT;
+    if (d > nl + nr) d = nl + nr;
+    int64_t lo = d > nr ? d - nr : 0, hi = d < nl ? d : nl;
+    while (lo < hi) {                      // L[mid] precedes R[d-1-mid] in the merge  <=>  more than mid L rows are taken
+        int64_t mid = lo + ((hi - lo) >> 1);
+        if (__ldg(lgs + mid) <= __ldg(rgs + (d - 1 - mid))) lo = mid + 1; else hi = mid;
+    }
+    part[t] = (int32_t)lo;
+}
+
+struct TileGeom {
+    int64_t x0, y0;      // first L / R row of the tile
+    int nl, nr;          // rows of each table in the tile (nl + nr <= JT)
+    int wl, wr;          // staged window lengths (tile part + extension, clipped to the table)
+};
+
+__device__ __forceinline__ TileGeom tile_geom(const int32_t* __restrict__ part, int64_t t, int64_t NL, int64_t NR) {
+    TileGeom g;
+    const int64_t d0 = t * JT, d1 = min((t + 1) * (int64_t)JT, NL + NR);
+    g.x0 = part[t];
+    const int64_t x1 = part[t + 1];
+    g.y0 = d0 - g.x0;
+    const int64_t y1 = d1 - x1;
+    g.nl = (int)(x1 - g.x0);
+    g.nr = (int)(y1 - g.y0);
+    g.wl = (int)min((int64_t)g.nl + J_EXT, NL - g.x0);
+    g.wr = (int)min((int64_t)g.nr + J_EXT, NR - g.y0);
+    return g;
+}
+
+__device__ __forceinline__ void stage_window(uint32_t* dst, const uint32_t* __restrict__ src, int n) {
+    for (int i = threadIdx.x; i < n; i += JB) dst[i] = __ldg(src + i);
+}
+
+// Item code written by the count pass and consumed by the emit pass (one uint32 per merged row):
+//   bits  0..14  run start, as an offset into the other table's window of the tile (0..JT)
+//   bit   15     class: 0 = the item is an L row (run of R rows), 1 = an R row (run of L rows)
+//   bits 16..31  run length, saturated at 0xFFFF (the emit pass then re-derives the exact end)
+constexpr uint32_t J_CLASS_B = 0x8000u;
+constexpr uint32_t J_CNT_SAT = 0xFFFFu;
+
+// ---- count pass -------------------------------------------------------------------------------------------
+// Thread t merges rows [4t, 4t+4) of the tile's merge sequence: one merge-path search for its diagonal, then
+// four merge steps.  The merge position of a row IS the start of its run; the end is a short gallop.
 __global__ void __launch_bounds__(JB)
-join_count_tiles_kernel(JoinSide L, JoinSide R, int64_t tiles_a, unsigned long long* __restrict__ tile_cnt) {
+join_count_tiles_kernel(JoinSide L, JoinSide R, const int32_t* __restrict__ part, uint32_t* __restrict__ item_code,
+                        unsigned long long* __restrict__ tile_cnt) {
+    __shared__ uint32_t s_l[JW];
+    __shared__ uint32_t s_r[JW];
+    __shared__ uint32_t s_lge[JT];
+    __shared__ uint32_t s_rge[JT];
     __shared__ unsigned long long s_red[JB / 32];
-    const int64_t tile = blockIdx.x;
-    const bool class_b = tile >= tiles_a;
-    const JoinSide& X = class_b ? R : L;
-    const JoinSide& Y = class_b ? L : R;
-    const int64_t base = (class_b ? tile - tiles_a : tile) * JT;
+    const TileGeom g = tile_geom(part, blockIdx.x, L.n, R.n);
+    stage_window(s_l, L.gs + g.x0, g.wl);
+    stage_window(s_r, R.gs + g.y0, g.wr);
+    stage_window(s_lge, L.ge + g.x0, g.nl);
+    stage_window(s_rge, R.ge + g.y0, g.nr);
+    __syncthreads();
+    const int n_items = g.nl + g.nr;
+    const int m0 = threadIdx.x * J_IPT;
+    int i = g.nl, j = g.nr;
+    if (m0 < n_items) {   // merge-path diagonal m0: i = L rows among the first m0 merged rows ("L before R on ties")
+        int lo = m0 > g.nr ? m0 - g.nr : 0, hi = m0 < g.nl ? m0 : g.nl;
+        while (lo < hi) {
+            const int mid = (lo + hi) >> 1;
+            if (s_l[mid] <= s_r[m0 - 1 - mid]) lo = mid + 1; else hi = mid;
+        }
+        i = lo;
+        j = m0 - lo;
+    }
+    uint32_t code[J_IPT];
     unsigned long long cnt = 0;
 #pragma unroll
-    for (int j = 0; j < J_IPT; j++) {
-        int64_t i = base + j * JB + threadIdx.x;
-        if (i < X.n) {
-            uint32_t xgs = X.gs[i], xge = X.ge[i];
-            int64_t lo, hi;
-            if (class_b) item_run<true>(xgs, xge, Y.gs, Y.n, lo, hi);
-            else item_run<false>(xgs, xge, Y.gs, Y.n, lo, hi);
-            cnt += (unsigned long long)(hi - lo);
+    for (int k = 0; k < J_IPT; k++) {
+        code[k] = 0;
+        if (m0 + k < n_items) {
+            const bool take_l = j >= g.nr || (i < g.nl && s_l[i] <= s_r[j]);
+            int64_t c;
+            if (take_l) {   // class A: run of R rows [y0 + j, hi)
+                const uint32_t xge = s_lge[i];
+                const int h = s_gallop(s_r, j, g.wr, xge);
+                int64_t hi_g = g.y0 + h;
+                if (h == g.wr && hi_g < R.n) hi_g = lb_gallop(R.gs, hi_g, R.n, xge);
+                c = hi_g - (g.y0 + j);
+                code[k] = (uint32_t)j;
+                i++;
+            } else {        // class B: run of L rows [x0 + i, hi)
+                const uint32_t xge = s_rge[j];
+                const int h = s_gallop(s_l, i, g.wl, xge);
+                int64_t hi_g = g.x0 + h;
+                if (h == g.wl && hi_g < L.n) hi_g = lb_gallop(L.gs, hi_g, L.n, xge);
+                c = hi_g - (g.x0 + i);
+                code[k] = (uint32_t)i | J_CLASS_B;
+                j++;
+            }
+            code[k] |= (uint32_t)(c < (int64_t)J_CNT_SAT ? c : (int64_t)J_CNT_SAT) << 16;
+            cnt += (unsigned long long)c;
         }
     }
+    static_assert(J_IPT == 4, "item codes are stored as one uint4 per thread");
+    reinterpret_cast<uint4*>(item_code + (size_t)blockIdx.x * JT)[threadIdx.x] = make_uint4(code[0], code[1], code[2], code[3]);
     cnt = warp_reduce_add(cnt);
     if (lane_id() == 0) s_red[warp_id()] = cnt;
     __syncthreads();
     if (threadIdx.x == 0) {
         unsigned long long t = 0;
         for (int w = 0; w < JB / 32; w++) t += s_red[w];
-        tile_cnt[tile] = t;
+        tile_cnt[blockIdx.x] = t;
     }
 }
 
-// ---- emit pass -----------------------------------------------------------------------------------
-// work line: tile t occupies [t*JT + off[t], (t+1)*JT + off[t+1]); its first JT units stand for the cost of
-// recomputing the tile, the remaining off[t+1]-off[t] units are its output slots.
+// ---- scan: pair offsets and emit work units of every tile (one CTA) -------------------------------------
+__global__ void __launch_bounds__(1024)
+join_scan_tiles_kernel(const unsigned long long* __restrict__ tile_cnt, int64_t n_tiles, unsigned long long* __restrict__ tile_off,
+                       unsigned long long* __restrict__ unit_off, unsigned long long* __restrict__ totals /* [0] pairs [1] units */) {
+    __shared__ unsigned long long scratch[1024 / 32 + 2];
+    // every thread owns a contiguous chunk: serial sums, ONE block scan per quantity, serial write-back
+    const int64_t per = (n_tiles + 1023) / 1024;
+    const int64_t lo = min((int64_t)threadIdx.x * per, n_tiles), hi = min(lo + per, n_tiles);
+    unsigned long long sp = 0, su = 0;
+    for (int64_t i = lo; i < hi; i++) {
+        const unsigned long long c = tile_cnt[i];
+        sp += c;
+        su += c > J_PART ? (c + J_PART - 1) / J_PART : 1ull;
+    }
+    unsigned long long tot_p, tot_u;
+    unsigned long long ex_p = block_excl_scan_add<unsigned long long>(sp, scratch, &tot_p);
+    __syncthreads();
+    unsigned long long ex_u = block_excl_scan_add<unsigned long long>(su, scratch, &tot_u);
+    for (int64_t i = lo; i < hi; i++) {
+        const unsigned long long c = tile_cnt[i];
+        tile_off[i] = ex_p;
+        unit_off[i] = ex_u;
+        ex_p += c;
+        ex_u += c > J_PART ? (c + J_PART - 1) / J_PART : 1ull;
+    }
+    if (threadIdx.x == 0) {
+        tile_off[n_tiles] = tot_p;
+        unit_off[n_tiles] = tot_u;
+        totals[0] = tot_p;
+        totals[1] = tot_u;
+    }
+}
+
+// ---- emit pass ---------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(JB)
-join_emit_kernel(JoinSide L, JoinSide R, int64_t tiles_a, int64_t n_tiles,
-                 const unsigned long long* __restrict__ tile_off, int32_t* __restrict__ out_l,
-                 int32_t* __restrict__ out_r, int64_t capacity) {
-    __shared__ unsigned long long s_off[JT + 1];
-    __shared__ uint32_t s_lo[JT];
-    __shared__ int32_t s_rid[JT];
+join_emit_kernel(JoinSide L, JoinSide R, const int32_t* __restrict__ part, int64_t n_tiles, const uint32_t* __restrict__ item_code,
+                 const unsigned long long* __restrict__ tile_off, const unsigned long long* __restrict__ unit_off,
+                 int32_t* __restrict__ out_l, int32_t* __restrict__ out_r, int64_t capacity) {
+    __shared__ int32_t s_lrid[JW];
+    __shared__ int32_t s_rrid[JW];
+    __shared__ unsigned long long s_off[JT + 1];   // local exclusive output offsets of the tile's items
+    __shared__ uint32_t s_code[JT];
     __shared__ unsigned long long s_scratch[JB / 32 + 2];
 
     const unsigned long long total = tile_off[n_tiles];
-    if ((long long)total > capacity) return;   // caller's buffer too small: nothing is written
-    const unsigned long long work = (unsigned long long)n_tiles * JT + total;
-    const unsigned long long n_chunks = (work + J_CHUNK - 1) / J_CHUNK;
+    if ((long long)total > capacity) return;       // caller's buffer too small: nothing is written
+    const unsigned long long n_units = unit_off[n_tiles];
+    const bool split = n_units != (unsigned long long)n_tiles;
+    const bool vec_ok = ((reinterpret_cast<uintptr_t>(out_l) | reinterpret_cast<uintptr_t>(out_r)) & 15) == 0;
 
-    for (unsigned long long chunk = blockIdx.x; chunk < n_chunks; chunk += gridDim.x) {
-        const unsigned long long ws = chunk * J_CHUNK;
-        const unsigned long long we = ws + J_CHUNK < work ? ws + J_CHUNK : work;
-        // first tile whose work interval ends after ws
-        int64_t tlo = 0, thi = n_tiles;
-        while (tlo < thi) {
-            int64_t mid = tlo + ((thi - tlo) >> 1);
-            unsigned long long wend = (unsigned long long)(mid + 1) * JT + tile_off[mid + 1];
-            if (wend <= ws) tlo = mid + 1; else thi = mid;
+    for (unsigned long long unit = blockIdx.x; unit < n_units; unit += gridDim.x) {
+        int64_t t = (int64_t)unit;
+        if (split) {   // last tile whose first unit is <= unit
+            int64_t lo = 0, hi = n_tiles;
+            while (hi - lo > 1) {
+                int64_t mid = lo + ((hi - lo) >> 1);
+                if (unit_off[mid] <= unit) lo = mid; else hi = mid;
+            }
+            t = lo;
         }
-        for (int64_t t = tlo; t < n_tiles; t++) {
-            const unsigned long long off_t = tile_off[t], off_t1 = tile_off[t + 1];
-            const unsigned long long w_begin = (unsigned long long)t * JT + off_t;
-            if (w_begin >= we) break;
-            const unsigned long long wo_s = w_begin + JT;                       // first output slot on the work line
-            const unsigned long long wo_e = (unsigned long long)(t + 1) * JT + off_t1;
-            const unsigned long long a_w = wo_s > ws ? wo_s : ws;
-            const unsigned long long b_w = wo_e < we ? wo_e : we;
-            if (a_w >= b_w) continue;
-            const unsigned long long a = a_w - wo_s, b = b_w - wo_s;           // slice of the tile's local outputs
+        const unsigned long long off_t = tile_off[t], cnt_t = tile_off[t + 1] - off_t;
+        if (cnt_t == 0) continue;
+        const unsigned long long a = (unit - unit_off[t]) * (unsigned long long)J_PART;        // this unit's slice of the tile's outputs
+        const unsigned long long b = min(a + (unsigned long long)J_PART, cnt_t);
 
-            const bool class_b = t >= tiles_a;
-            const JoinSide& X = class_b ? R : L;
-            const JoinSide& Y = class_b ? L : R;
-            const int64_t base = (class_b ? t - tiles_a : t) * JT;
-            // recompute the tile's runs and their local exclusive offsets
-            unsigned long long carry = 0;
+        const TileGeom g = tile_geom(part, t, L.n, R.n);
+        for (int i = threadIdx.x; i < g.wl; i += JB) s_lrid[i] = __ldg(L.rid + g.x0 + i);
+        for (int i = threadIdx.x; i < g.wr; i += JB) s_rrid[i] = __ldg(R.rid + g.y0 + i);
+        // the thread's four items: run lengths from the count pass (exact end re-derived when saturated)
+        const uint4 cv = reinterpret_cast<const uint4*>(item_code + (size_t)t * JT)[threadIdx.x];
+        const uint32_t code[J_IPT] = {cv.x, cv.y, cv.z, cv.w};
+        unsigned long long c[J_IPT], sum = 0;
 #pragma unroll
-            for (int j = 0; j < J_IPT; j++) {
-                const int li = j * JB + threadIdx.x;
-                const int64_t i = base + li;
-                int64_t lo = 0, hi = 0;
-                int32_t rid = 0;
-                if (i < X.n) {
-                    uint32_t xgs = X.gs[i], xge = X.ge[i];
-                    if (class_b) item_run<true>(xgs, xge, Y.gs, Y.n, lo, hi);
-                    else item_run<false>(xgs, xge, Y.gs, Y.n, lo, hi);
-                    rid = X.rid[i];
+        for (int k = 0; k < J_IPT; k++) {
+            c[k] = code[k] >> 16;
+            if (c[k] == J_CNT_SAT) {
+                const int m = threadIdx.x * J_IPT + k;
+                const int lo_local = (int)(code[k] & 0x7FFFu);
+                if (code[k] & J_CLASS_B) {
+                    const uint32_t xge = __ldg(R.ge + g.y0 + (m - lo_local));
+                    c[k] = (unsigned long long)(lb_gallop(L.gs, g.x0 + lo_local, L.n, xge) - (g.x0 + lo_local));
+                } else {
+                    const uint32_t xge = __ldg(L.ge + g.x0 + (m - lo_local));
+                    c[k] = (unsigned long long)(lb_gallop(R.gs, g.y0 + lo_local, R.n, xge) - (g.y0 + lo_local));
                 }
-                s_lo[li] = (uint32_t)lo;
-                s_rid[li] = rid;
-                unsigned long long tot;
-                unsigned long long ex = block_excl_scan_add<unsigned long long>((unsigned long long)(hi - lo), s_scratch, &tot);
-                s_off[li] = carry + ex;
-                carry += tot;
-                __syncthreads();
             }
-            if (threadIdx.x == 0) s_off[JT] = carry;
-            __syncthreads();
-            // per-slot search: slot s belongs to the last item whose offset is <= s
-            for (unsigned long long s = a + threadIdx.x; s < b; s += JB) {
-                int lo = 0, hi = JT;
-                while (lo < hi) {
-                    int mid = (lo + hi) >> 1;
-                    if (s_off[mid] <= s) lo = mid + 1; else hi = mid;
-                }
-                const int item = lo - 1;
-                const int64_t ypos = (int64_t)s_lo[item] + (int64_t)(s - s_off[item]);
-                const int32_t xr = s_rid[item];
-                const int32_t yr = Y.rid[ypos];
-                const unsigned long long o = off_t + s;
-                out_l[o] = class_b ? yr : xr;
-                out_r[o] = class_b ? xr : yr;
-            }
-            __syncthreads();   // shared arrays are rewritten by the next tile
+            sum += c[k];
         }
+        unsigned long long tot;
+        unsigned long long ex = block_excl_scan_add<unsigned long long>(sum, s_scratch, &tot);
+#pragma unroll
+        for (int k = 0; k < J_IPT; k++) {
+            s_off[threadIdx.x * J_IPT + k] = ex;
+            s_code[threadIdx.x * J_IPT + k] = code[k];
+            ex += c[k];
+        }
+        if (threadIdx.x == 0) s_off[JT] = tot;
+        __syncthreads();
+
+        // each thread owns J_OPT consecutive GLOBAL output positions, aligned to J_OPT
+        const unsigned long long g_a = off_t + a, g_b = off_t + b;
+        const unsigned long long g_first = g_a & ~(unsigned long long)(J_OPT - 1);
+        for (unsigned long long gp = g_first + (unsigned long long)threadIdx.x * J_OPT; gp < g_b; gp += (unsigned long long)JB * J_OPT) {
+            const unsigned long long p0 = gp > g_a ? gp : g_a, p1 = min(gp + J_OPT, g_b);
+            if (p0 >= p1) continue;
+            int item = s_upper_bound_u64(s_off, JT + 1, p0 - off_t) - 1;    // last item whose offset is <= the first slot
+            int32_t vl[J_OPT], vr[J_OPT];
+#pragma unroll
+            for (int q = 0; q < J_OPT; q++) {
+                const unsigned long long pq = gp + q;
+                vl[q] = 0;
+                vr[q] = 0;
+                if (pq >= p0 && pq < p1) {
+                    const unsigned long long sl = pq - off_t;          // local output slot
+                    while (s_off[item + 1] <= sl) item++;              // skip items with empty runs
+                    const uint32_t cd = s_code[item];
+                    const int lo_local = (int)(cd & 0x7FFFu);
+                    const int64_t w = (int64_t)lo_local + (int64_t)(sl - s_off[item]);   // offset into the other table's window
+                    if (!(cd & J_CLASS_B)) {                           // x is L row (item - lo_local), y an R row
+                        vl[q] = s_lrid[item - lo_local];
+                        vr[q] = w < g.wr ? s_rrid[w] : __ldg(R.rid + g.y0 + w);
+                    } else {                                           // x is R row (item - lo_local), y an L row
+                        vr[q] = s_rrid[item - lo_local];
+                        vl[q] = w < g.wl ? s_lrid[w] : __ldg(L.rid + g.x0 + w);
+                    }
+                }
+            }
+            if (vec_ok && p0 == gp && p1 == gp + J_OPT) {
+                st_stream_u32x4(reinterpret_cast<uint4*>(out_l + gp), make_uint4(vl[0], vl[1], vl[2], vl[3]));
+                st_stream_u32x4(reinterpret_cast<uint4*>(out_l + gp) + 1, make_uint4(vl[4], vl[5], vl[6], vl[7]));
+                st_stream_u32x4(reinterpret_cast<uint4*>(out_r + gp), make_uint4(vr[0], vr[1], vr[2], vr[3]));
+                st_stream_u32x4(reinterpret_cast<uint4*>(out_r + gp) + 1, make_uint4(vr[4], vr[5], vr[6], vr[7]));
+            } else {
+#pragma unroll
+                for (int q = 0; q < J_OPT; q++) {
+                    const unsigned long long pq = gp + q;
+                    if (pq >= p0 && pq < p1) {
+                        out_l[pq] = vl[q];
+                        out_r[pq] = vr[q];
+                    }
+                }
+            }
+        }
+        __syncthreads();   // shared arrays are rewritten by the next unit
     }
 }
 
@@ -288,11 +475,17 @@ inline JoinSide side_of(const giqlb_index* ix) { return JoinSide{ix->gs, ix->ge,
 // ---- C ABI ------------------------------------------------------------------------------------------------
 extern "C" int giqlb_joinplan_free(giqlb_ctx* ctx, giqlb_joinplan* plan) {
     if (!plan) return GIQLB_OK;
-    if (ctx) dev_free(ctx, plan->tile_off);
+    if (ctx) {
+        dev_free(ctx, plan->part);
+        dev_free(ctx, plan->item_code);
+        dev_free(ctx, plan->tile_off);
+        dev_free(ctx, plan->unit_off);
+    }
     delete plan;
     return GIQLB_OK;
 }
 
+// Enqueues partition + count + scan.  The pair total lands in ctx->d_scalars[0].
 static int plan_enqueue(giqlb_ctx* ctx, giqlb_index* L, giqlb_index* R, giqlb_joinplan** out) {
     if (L->layout != R->layout) return giqlb_fail(ctx, GIQLB_ERR_INVALID, "intersects: indexes were built on different layouts");
     if (L->grouped_by_strand || R->grouped_by_strand)
@@ -302,35 +495,42 @@ static int plan_enqueue(giqlb_ctx* ctx, giqlb_index* L, giqlb_index* R, giqlb_jo
     p->L = L;
     p->R = R;
     p->general = (L->n_degenerate + R->n_degenerate) > 0;
-    p->tiles_a = ceil_div(L->n, JT);
-    p->tiles_b = p->general ? 0 : ceil_div(R->n, JT);
-    const int64_t n_tiles = p->tiles_a + p->tiles_b;
+    const bool empty = L->n == 0 || R->n == 0;
+    p->n_tiles = empty ? 0 : (p->general ? ceil_div(L->n, JT) : ceil_div(L->n + R->n, JT));
+    const int64_t n_tiles = p->n_tiles;
     unsigned long long* cnt = nullptr;
+    unsigned long long* totals = reinterpret_cast<unsigned long long*>(ctx->d_scalars);
     int st = dev_alloc(ctx, &cnt, (size_t)n_tiles + 1);
     if (st == GIQLB_OK) st = dev_alloc(ctx, &p->tile_off, (size_t)n_tiles + 1);
-    if (st != GIQLB_OK) {
-        dev_free(ctx, cnt);
-        giqlb_joinplan_free(ctx, p);
-        return st;
-    }
-    if (n_tiles > 0) {
-        if (p->general) {
-            st = giqlb_index_ensure_pmax(ctx, R);
-            if (st == GIQLB_OK) {
-                PhaseSpan ps(ctx, GIQLB_PH_JOIN_COUNT);
-                join_count_tiles_general_kernel<<<(unsigned)n_tiles, JB, 0, ctx->stream>>>(side_of(L), side_of(R), R->pmax, cnt);
-                ctx->launches_this_call++;
-                ctx->stats.kernels_total++;
-            }
-        } else {
+    if (st == GIQLB_OK && !p->general) st = dev_alloc(ctx, &p->unit_off, (size_t)n_tiles + 1);
+    if (st == GIQLB_OK && !p->general) st = dev_alloc(ctx, &p->part, (size_t)n_tiles + 1);
+    if (st == GIQLB_OK && !p->general) st = dev_alloc(ctx, &p->item_code, (size_t)n_tiles * JT);
+    if (st == GIQLB_OK && n_tiles == 0) {
+        if (cudaMemsetAsync(totals, 0, 16, ctx->stream) != cudaSuccess || cudaMemsetAsync(p->tile_off, 0, 8, ctx->stream) != cudaSuccess)
+            st = giqlb_fail(ctx, GIQLB_ERR_CUDA, "intersects: memset failed");
+    } else if (st == GIQLB_OK && p->general) {
+        st = giqlb_index_ensure_pmax(ctx, R);
+        if (st == GIQLB_OK) {
             PhaseSpan ps(ctx, GIQLB_PH_JOIN_COUNT);
-            join_count_tiles_kernel<<<(unsigned)n_tiles, JB, 0, ctx->stream>>>(side_of(L), side_of(R), p->tiles_a, cnt);
+            join_count_tiles_general_kernel<<<(unsigned)n_tiles, JB, 0, ctx->stream>>>(side_of(L), side_of(R), R->pmax, cnt);
             ctx->launches_this_call++;
             ctx->stats.kernels_total++;
         }
-        if (st == GIQLB_OK && cudaGetLastError() != cudaSuccess) st = giqlb_fail(ctx, GIQLB_ERR_CUDA, "intersects: count launch failed");
+        if (st == GIQLB_OK) st = giqlb_excl_scan_u64(ctx, cnt, p->tile_off, n_tiles, totals);
+    } else if (st == GIQLB_OK) {
+        {
+            PhaseSpan ps(ctx, GIQLB_PH_JOIN_COUNT);
+            join_partition_kernel<<<(unsigned)ceil_div(n_tiles + 1, 256), 256, 0, ctx->stream>>>(L->gs, L->n, R->gs, R->n, n_tiles, p->part);
+            join_count_tiles_kernel<<<(unsigned)n_tiles, JB, 0, ctx->stream>>>(side_of(L), side_of(R), p->part, p->item_code, cnt);
+            ctx->launches_this_call += 2;
+            ctx->stats.kernels_total += 2;
+        }
+        PhaseSpan ps(ctx, GIQLB_PH_JOIN_SCAN);
+        join_scan_tiles_kernel<<<1, 1024, 0, ctx->stream>>>(cnt, n_tiles, p->tile_off, p->unit_off, totals);
+        ctx->launches_this_call++;
+        ctx->stats.kernels_total++;
     }
-    if (st == GIQLB_OK) st = giqlb_excl_scan_u64(ctx, cnt, p->tile_off, n_tiles, reinterpret_cast<unsigned long long*>(ctx->d_scalars));
+    if (st == GIQLB_OK && cudaGetLastError() != cudaSuccess) st = giqlb_fail(ctx, GIQLB_ERR_CUDA, "intersects: plan launch failed");
     dev_free(ctx, cnt);
     if (st != GIQLB_OK) {
         giqlb_joinplan_free(ctx, p);
@@ -341,16 +541,17 @@ static int plan_enqueue(giqlb_ctx* ctx, giqlb_index* L, giqlb_index* R, giqlb_jo
 }
 
 static int emit_enqueue(giqlb_ctx* ctx, giqlb_joinplan* p, int32_t* out_l, int32_t* out_r, int64_t capacity) {
-    const int64_t n_tiles = p->tiles_a + p->tiles_b;
+    const int64_t n_tiles = p->n_tiles;
     if (n_tiles == 0) return GIQLB_OK;
     PhaseSpan ps(ctx, GIQLB_PH_JOIN_EMIT);
     if (p->general) {
         join_emit_general_kernel<<<(unsigned)n_tiles, JB, 0, ctx->stream>>>(side_of(p->L), side_of(p->R), p->R->pmax, n_tiles,
                                                                             p->tile_off, out_l, out_r, capacity);
     } else {
-        int grid = ctx->sm_count * 8;
-        join_emit_kernel<<<grid, JB, 0, ctx->stream>>>(side_of(p->L), side_of(p->R), p->tiles_a, n_tiles, p->tile_off, out_l,
-                                                       out_r, capacity);
+        const int64_t cap = (int64_t)ctx->sm_count * 8;
+        const int grid = (int)(n_tiles < cap ? n_tiles : cap);
+        join_emit_kernel<<<grid, JB, 0, ctx->stream>>>(side_of(p->L), side_of(p->R), p->part, n_tiles, p->item_code, p->tile_off, p->unit_off,
+                                                       out_l, out_r, capacity);
     }
     LAUNCH_CHECK(ctx);
     return GIQLB_OK;

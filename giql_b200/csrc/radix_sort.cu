@@ -63,7 +63,7 @@ rs_histogram_kernel(const uint32_t* __restrict__ keys, int64_t n, int begin_bit,
 // ---- one digit pass ----------------------------------------------------------------------------------
 // IDENTITY_VALS: payload of key i is i itself (first pass; no payload array is read).
 template <bool IDENTITY_VALS>
-__global__ void __launch_bounds__(RS_THREADS)
+__global__ void __launch_bounds__(RS_THREADS, 4)
 rs_onesweep_kernel(const uint32_t* __restrict__ keys_in, const uint32_t* __restrict__ vals_in,
                    uint32_t* __restrict__ keys_out, uint32_t* __restrict__ vals_out, int64_t n, int shift,
                    const uint32_t* __restrict__ ghist /* this pass, [256] */,
@@ -73,7 +73,7 @@ rs_onesweep_kernel(const uint32_t* __restrict__ keys_in, const uint32_t* __restr
     __shared__ uint32_t s_keys[RS_TILE];
     __shared__ uint32_t s_vals[RS_TILE];
     __shared__ uint32_t s_digit_excl[RS_RADIX];            // tile-local exclusive digit offsets
-    __shared__ int64_t s_global_base[RS_RADIX];            // global position of local sorted slot 0 of each digit
+    __shared__ int32_t s_global_base[RS_RADIX];            // global position of local sorted slot 0 of each digit (n < 2^30)
     __shared__ uint32_t s_scan[RS_WARPS + 2];
     __shared__ uint32_t s_tile;
 
@@ -95,12 +95,15 @@ rs_onesweep_kernel(const uint32_t* __restrict__ keys_in, const uint32_t* __restr
         int li = warp_off + i * 32 + l;
         key[i] = li < tile_n ? ld_stream_u32(keys_in + tile_base + li) : 0xffffffffu;
     }
-    // rank within the warp, stable in (item, lane) order
+    // rank within the warp, stable in (item, lane) order.  All match instructions are issued first (they are
+    // independent), so only the shared-memory counter update remains on the serial chain.
+#pragma unroll
+    for (int i = 0; i < RS_IPT; i++) rank[i] = __match_any_sync(FULL_MASK, (key[i] >> shift) & 255u);
 #pragma unroll
     for (int i = 0; i < RS_IPT; i++) {
-        uint32_t d = (key[i] >> shift) & 255u;
-        uint32_t peers = __match_any_sync(FULL_MASK, d);
-        int leader = __ffs(peers) - 1;
+        const uint32_t d = (key[i] >> shift) & 255u;
+        const uint32_t peers = rank[i];
+        const int leader = __ffs(peers) - 1;
         uint32_t base = 0;
         if ((int)l == leader) {
             base = s_warp_hist[w][d];
@@ -155,7 +158,7 @@ rs_onesweep_kernel(const uint32_t* __restrict__ keys_in, const uint32_t* __restr
         }
         *(volatile uint32_t*)my_status = ST_FLAG_INCL | (prefix + count);
     }
-    s_global_base[d_own] = (int64_t)gstart + (int64_t)prefix - (int64_t)dex;
+    s_global_base[d_own] = (int32_t)(gstart + prefix - dex);
     __syncthreads();
 
     // scatter the tile into shared memory in digit order
@@ -175,7 +178,7 @@ rs_onesweep_kernel(const uint32_t* __restrict__ keys_in, const uint32_t* __restr
     for (int j = threadIdx.x; j < tile_n; j += RS_THREADS) {
         uint32_t k = s_keys[j];
         uint32_t d = (k >> shift) & 255u;
-        int64_t out = s_global_base[d] + j;
+        const int64_t out = (int64_t)(s_global_base[d] + j);
         keys_out[out] = k;
         vals_out[out] = s_vals[j];
     }

@@ -305,6 +305,10 @@ class Engine:
     def sync(self):
         self._check(self.lib.giqlb_sync(self.ctx))
 
+    def trim(self):
+        """Return the engine's cached scratch memory to the driver (synchronises)."""
+        self._check(self.lib.giqlb_trim(self.ctx))
+
     def stats(self) -> dict:
         s = _cabi.Stats()
         self._check(self.lib.giqlb_stats(self.ctx, ctypes.byref(s)))

@@ -112,6 +112,9 @@ int giqlb_create(int device, void* cuda_stream, giqlb_ctx** out);
 int giqlb_destroy(giqlb_ctx* ctx);
 const char* giqlb_last_error(const giqlb_ctx* ctx);
 int giqlb_sync(giqlb_ctx* ctx);
+/* Scratch and index memory is cached per context (freed blocks are reused without a driver call).
+ * trim() synchronises and returns every parked block to the driver. */
+int giqlb_trim(giqlb_ctx* ctx);
 int giqlb_stats(const giqlb_ctx* ctx, giqlb_stats_t* out_host);
 /* Per-phase device time.  While enabled, CUDA events are recorded on the context's stream around each
  * kernel group; read() synchronises, ADDS the elapsed milliseconds and launch counts since the last read

@@ -365,3 +365,22 @@ def test_disjoin_random_vs_oracle(seed, engine):
     ob, eb = OracleBackend(), EngineBackend(engine)
     assert eb.disjoin(T) == ob.disjoin(T)
     assert eb.disjoin(T, R) == ob.disjoin(T, R)
+
+
+def test_join_heavily_skewed_tiles_are_split(engine, c_oracle):
+    """a few giant intervals overlapping tens of thousands of rows: tiles whose output exceeds one emit work unit
+    are split over many CTAs; runs leave the staged shared-memory window and continue in global memory"""
+    rng = np.random.default_rng(77)
+    n = 60_000
+    rs = np.sort(rng.integers(0, 3_000_000, size=n)).astype(np.int32)
+    R = {"code": np.zeros(n, np.int32), "start": rs, "end": (rs + rng.integers(1, 400, size=n)).astype(np.int32)}
+    ls = rng.integers(0, 3_000_000, size=2000).astype(np.int32)
+    le = ls + rng.integers(1, 300, size=2000).astype(np.int32)
+    ls[:3], le[:3] = [0, 1_000_000, 2_999_000], [3_000_500, 2_000_000, 3_000_400]     # giants
+    L = {"code": np.zeros(2000, np.int32), "start": ls, "end": le.astype(np.int32)}
+    for A, B in ((L, R), (R, L)):
+        ta = engine.table_from_codes(A["code"], A["start"], A["end"], ["chr1"])
+        tb = engine.table_from_codes(B["code"], B["start"], B["end"], ta.dictionary)
+        got = engine.intersects(ta, tb).sorted_packed()
+        exp = c_oracle.intersects_pairs(A["code"], A["start"], A["end"], B["code"], B["start"], B["end"], 1)
+        assert len(got) > 90_000 and np.array_equal(got, (exp[:, 0] << 32) | exp[:, 1])
