@@ -74,7 +74,7 @@ PROTOTYPES = {
     "giqlb_index_free": (c_int, [_P, _P]),
     "giqlb_index_rows": (c_int64, [_P]),
     "giqlb_index_columns": (c_int, [_P, POINTER(_P), POINTER(_P), POINTER(_P), POINTER(_P)]),
-    "giqlb_index_info": (c_int, [_P, POINTER(c_int64), POINTER(c_int64), POINTER(c_int32), POINTER(c_int64)]),
+    "giqlb_index_info": (c_int, [_P, _P, POINTER(c_int64), POINTER(c_int64), POINTER(c_int32), POINTER(c_int64)]),
     "giqlb_index_group_by_strand": (c_int, [_P, _P]),
     "giqlb_intersects_plan": (c_int, [_P, _P, _P, POINTER(_P), POINTER(c_int64)]),
     "giqlb_intersects_emit": (c_int, [_P, _P, _P, _P]),

@@ -133,8 +133,9 @@ int running_count(giqlb_ctx* ctx, const giqlb_index* X, int64_t lo, int64_t hi, 
                                  OutRunningCount{G + lo});
 }
 
-int check_index(giqlb_ctx* ctx, const giqlb_index* X, const char* who) {
+int check_index(giqlb_ctx* ctx, giqlb_index* X, const char* who) {
     if (!X->layout || !X->layout->finalized) return giqlb_fail(ctx, GIQLB_ERR_INVALID, "%s: index has no layout", who);
+    GIQLB_TRY(giqlb_index_resolve(ctx, X, nullptr));
     if (X->n_negative > 0)
         return giqlb_fail(ctx, GIQLB_ERR_INVALID, "%s: %lld rows have end < start; their grouping depends on the engine's tie order "
                           "in the reference itself and is not supported", who, (long long)X->n_negative);

@@ -15,6 +15,7 @@
 
 #define GIQLB_SM_COUNT_DEFAULT 148
 #define GIQLB_MAX_STRAND_CODES 256
+#define GIQLB_STAGE_BYTES (256u * 1024u)
 
 struct giqlb_ctx {
     int device = 0;
@@ -24,6 +25,7 @@ struct giqlb_ctx {
     // small pinned host + device scratch for scalars returned to the host
     int64_t* h_scalars = nullptr;   // pinned, 64 slots
     int64_t* d_scalars = nullptr;   // device, 64 slots
+    void* h_stage = nullptr;        // pinned staging buffer for small host -> device tables (GIQLB_STAGE_BYTES)
     int* d_err = nullptr;           // device int[4]: sticky kernel-side error flags ([0] look-back spin limit)
     giqlb_stats_t stats = {};
     int32_t launches_this_call = 0;
@@ -93,7 +95,18 @@ struct giqlb_layout {
     int key_bits = 32;
     std::vector<int64_t> h_lo, h_hi;
     std::vector<uint32_t> h_base;
+    // tables folded in by observe(): their degenerate-row counts are gathered by the same pass and fetched by
+    // finalize()'s round trip, so an index over an observed table needs no round trip of its own
+    struct Observed {
+        const int32_t* code;
+        int64_t n;
+        int32_t sadj, eadj;
+        int64_t n_degenerate, n_negative;
+    };
+    std::vector<Observed> observed;
+    unsigned long long* d_obs = nullptr;   // [2 * GIQLB_MAX_OBSERVED]: end <= start, end < start per observe() call
 };
+#define GIQLB_MAX_OBSERVED 16
 
 struct giqlb_index {
     int64_t n = 0;
@@ -104,8 +117,10 @@ struct giqlb_index {
     uint32_t* pmax = nullptr;    // lazily built inclusive running max of ge (restarts per strand block)
     uint32_t* ge_sorted = nullptr;   // lazily built: ge ascending (per strand block) ...
     int32_t* pos_by_end = nullptr;   // ... and the sorted position (into gs/ge/rid) of each
-    int64_t n_degenerate = 0;    // rows with end <= start (host copy, filled at build)
+    int64_t n_degenerate = 0;    // rows with end <= start (host copy; valid when `resolved`)
     int64_t n_negative = 0;      // rows with end <  start
+    bool resolved = true;        // false: the counts still sit in d_counters (giqlb_index_resolve fetches them)
+    unsigned long long* d_counters = nullptr;   // [3] end<=start, end<start, rows outside the layout
     bool tie_by_end = false;     // equal starts are ordered by end
     bool grouped_by_strand = false;
     int32_t n_blocks = 1;                                   // strand blocks (1 when not grouped)
@@ -243,6 +258,20 @@ static inline int probe_cols(giqlb_ctx* ctx, const giqlb_layout* lay, const int3
     return GIQLB_OK;
 }
 
+// fetch_scalars + the sticky kernel-side error flags in the same round trip
+static inline int fetch_scalars_checked(giqlb_ctx* ctx, const void* d_src, int n_words) {
+    CUDA_TRY(ctx, cudaMemcpyAsync(ctx->h_scalars, d_src, (size_t)n_words * 8, cudaMemcpyDeviceToHost, ctx->stream));
+    CUDA_TRY(ctx, cudaMemcpyAsync(ctx->h_scalars + 60, ctx->d_err, 4 * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+    CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    const int* e = reinterpret_cast<const int*>(ctx->h_scalars + 60);
+    if (e[0] || e[3]) {
+        cudaMemsetAsync(ctx->d_err, 0, 4 * sizeof(int), ctx->stream);
+        if (e[3]) return giqlb_fail(ctx, GIQLB_ERR_RANGE, "index: rows lie outside the layout (observe the table before finalize)");
+        return giqlb_fail(ctx, GIQLB_ERR_INTERNAL, "look-back spin limit exceeded (kernel-side)");
+    }
+    return GIQLB_OK;
+}
+
 // ---- device helpers ------------------------------------------------------------------------------
 #ifdef __CUDACC__
 
@@ -355,4 +384,5 @@ int giqlb_excl_scan_u64(giqlb_ctx* ctx, const unsigned long long* in, unsigned l
 int giqlb_incl_scan_max_u32(giqlb_ctx* ctx, const uint32_t* in, uint32_t* out, int64_t n,
                             const int64_t* d_block_off, int n_blocks);
 int giqlb_index_ensure_pmax(giqlb_ctx* ctx, giqlb_index* ix);
+int giqlb_index_resolve(giqlb_ctx* ctx, giqlb_index* a, giqlb_index* b);
 int giqlb_index_ensure_end_sorted(giqlb_ctx* ctx, giqlb_index* ix);

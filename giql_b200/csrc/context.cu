@@ -22,6 +22,7 @@ extern "C" int giqlb_create(int device, void* cuda_stream, giqlb_ctx** out) {
     // stream has handle 0) stays ordered with ours.  The library never creates a stream of its own.
     ctx->stream = (cudaStream_t)cuda_stream;
     if (cudaMallocHost((void**)&ctx->h_scalars, 64 * sizeof(int64_t)) != cudaSuccess ||
+        cudaMallocHost(&ctx->h_stage, GIQLB_STAGE_BYTES) != cudaSuccess ||
         cudaMalloc((void**)&ctx->d_scalars, 64 * sizeof(int64_t)) != cudaSuccess ||
         cudaMalloc((void**)&ctx->d_err, 4 * sizeof(int)) != cudaSuccess ||
         cudaMemset(ctx->d_err, 0, 4 * sizeof(int)) != cudaSuccess ||
@@ -42,6 +43,7 @@ extern "C" int giqlb_destroy(giqlb_ctx* ctx) {
     for (auto& kv : ctx->cache_free) cudaFree(kv.second);
     for (auto& kv : ctx->cache_live) cudaFree(kv.first);   // objects the caller never freed
     if (ctx->h_scalars) cudaFreeHost(ctx->h_scalars);
+    if (ctx->h_stage) cudaFreeHost(ctx->h_stage);
     if (ctx->d_scalars) cudaFree(ctx->d_scalars);
     if (ctx->d_err) cudaFree(ctx->d_err);
     delete ctx;
@@ -55,7 +57,11 @@ extern "C" int giqlb_sync(giqlb_ctx* ctx) {
     CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
     int h_err[4];
     CUDA_TRY(ctx, cudaMemcpy(h_err, ctx->d_err, sizeof(h_err), cudaMemcpyDeviceToHost));
-    if (h_err[0]) return giqlb_fail(ctx, GIQLB_ERR_INTERNAL, "look-back spin limit exceeded (kernel-side)");
+    if (h_err[0] || h_err[3]) {
+        cudaMemset(ctx->d_err, 0, sizeof(h_err));
+        if (h_err[3]) return giqlb_fail(ctx, GIQLB_ERR_RANGE, "index: rows lie outside the layout (observe the table before finalize)");
+        return giqlb_fail(ctx, GIQLB_ERR_INTERNAL, "look-back spin limit exceeded (kernel-side)");
+    }
     return GIQLB_OK;
 }
 

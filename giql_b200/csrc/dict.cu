@@ -6,16 +6,28 @@
 // dictionary whose codes preserve bytewise string order (MERGE's default ORDER BY chrom sorts VARCHAR,
 // src/giql/expanders/merge.py:429-437), so every later kernel works on int32 codes.
 //
-// Pass 1: every row probes an open-addressing table whose slots hold (representative row + 1); a row either
-// claims an empty slot with one CAS or compares its bytes with the representative's — exact, no reliance on
-// hash uniqueness.  The row's slot is parked in the output code array.  Pass 2 gathers the distinct names
-// into a small buffer for the host, which sorts them and uploads a slot -> code table.  Pass 3 rewrites the
-// parked slots into codes.  Traffic: offsets + bytes once, 8 B/row of codes.
+// Pass 1 (dict_insert_kernel): a CTA takes 1024 consecutive rows, stages their offsets and their (contiguous)
+// name bytes in shared memory with coalesced loads, and resolves every row to a slot of a global
+// open-addressing table whose slots hold (representative row + 1).  Names of up to 16 bytes — all real
+// chromosome names — are compared as two 64-bit words against a small per-CTA cache of names already
+// resolved, so after the first few rows a lookup touches shared memory only; a cache miss (or a longer
+// name) probes the global table: one CAS claims an empty slot, otherwise the bytes are compared with the
+// representative's — exact, no reliance on hash uniqueness.  The row's slot is parked in the output array.
+// Pass 2 gathers the distinct names into a small buffer; the host sorts them (one round trip for the whole
+// call) and uploads a slot -> code table.  Pass 3 rewrites the parked slots into codes.
+// Traffic: offsets + bytes once, 8 B/row of codes.
 #include <algorithm>
 
 #include "common.cuh"
 
 namespace {
+
+constexpr int DI_THREADS = 256;
+constexpr int DI_ROWS = 1024;          // rows per CTA chunk
+constexpr int DI_BYTES = 16384;        // staged name bytes per chunk (longer chunks read global memory directly)
+constexpr int DI_CACHE = 128;          // per-CTA cache entries
+constexpr int DC_MAX_ENTRIES = 4096;   // distinct names gathered in the first round trip
+constexpr int DC_NAME_CAP = 65536;     // their bytes
 
 struct StrTable {
     const int32_t* offs;
@@ -23,13 +35,28 @@ struct StrTable {
     int64_t n;
 };
 
-__device__ __forceinline__ uint64_t fnv1a(const uint8_t* __restrict__ p, int len) {
+__device__ __forceinline__ uint64_t mix64(uint64_t h) {
+    h ^= h >> 33;
+    h *= 0xff51afd7ed558ccdull;
+    h ^= h >> 33;
+    h *= 0xc4ceb9fe1a85ec53ull;
+    return h ^ (h >> 33);
+}
+// hash of a name: names of <= 16 bytes hash their two zero-padded words, longer names all their bytes
+__device__ __forceinline__ uint64_t hash_short(uint64_t w0, uint64_t w1, int len) { return mix64(w0 ^ mix64(w1 + (uint64_t)len)); }
+__device__ __forceinline__ uint64_t hash_long(const uint8_t* __restrict__ p, int len) {
     uint64_t h = 1469598103934665603ull;
     for (int i = 0; i < len; i++) {
         h ^= p[i];
         h *= 1099511628211ull;
     }
-    return h ^ (h >> 29);
+    return mix64(h);
+}
+__device__ __forceinline__ uint64_t hash_global_name(const uint8_t* __restrict__ p, int len) {
+    if (len > 16) return hash_long(p, len);
+    uint64_t w[2] = {0, 0};
+    for (int i = 0; i < len; i++) w[i >> 3] |= (uint64_t)p[i] << (8 * (i & 7));
+    return hash_short(w[0], w[1], len);
 }
 
 __device__ __forceinline__ bool same_bytes(const uint8_t* __restrict__ a, const uint8_t* __restrict__ b, int len) {
@@ -38,35 +65,118 @@ __device__ __forceinline__ bool same_bytes(const uint8_t* __restrict__ a, const 
     return true;
 }
 
-__global__ void __launch_bounds__(256)
+// Global table: returns the slot of the name (s, len), inserting representative row g when it is new.
+__device__ __forceinline__ uint32_t global_resolve(const StrTable& A, const StrTable& B, unsigned long long* __restrict__ slots,
+                                                   uint32_t cap_mask, const uint8_t* __restrict__ s, int len, uint64_t h, int64_t g,
+                                                   unsigned int* __restrict__ n_distinct) {
+    uint32_t slot = (uint32_t)h & cap_mask;
+    for (uint32_t probes = 0; probes <= cap_mask; probes++) {
+        unsigned long long w = *(volatile unsigned long long*)&slots[slot];
+        if (w == 0) {
+            unsigned long long prev = atomicCAS(&slots[slot], 0ull, (unsigned long long)g + 1ull);
+            if (prev == 0) {
+                atomicAdd(n_distinct, 1u);
+                return slot;
+            }
+            w = prev;
+        }
+        const int64_t rg = (int64_t)w - 1;
+        const StrTable& RT = rg >= A.n ? B : A;
+        const int64_t ri = rg >= A.n ? rg - A.n : rg;
+        const int32_t r0 = RT.offs[ri], rlen = RT.offs[ri + 1] - r0;
+        if (rlen == len && same_bytes(s, RT.bytes + r0, len)) return slot;
+        slot = (slot + 1) & cap_mask;
+    }
+    return cap_mask;   // table full: cannot happen, the host keeps the load factor <= 1/2 and re-runs otherwise
+}
+
+struct CacheEntry {
+    uint64_t w0, w1;
+    int32_t len;
+    uint32_t slot;
+};
+
+__global__ void __launch_bounds__(DI_THREADS)
 dict_insert_kernel(StrTable A, StrTable B, unsigned long long* __restrict__ slots, uint32_t cap_mask,
                    int32_t* __restrict__ slot_a, int32_t* __restrict__ slot_b, unsigned int* __restrict__ n_distinct) {
-    const int64_t n = A.n + B.n;
-    for (int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; g < n; g += (int64_t)gridDim.x * blockDim.x) {
-        const bool in_b = g >= A.n;
+    __shared__ int32_t s_offs[DI_ROWS + 1];
+    __shared__ __align__(16) uint8_t s_bytes[DI_BYTES + 32];
+    __shared__ CacheEntry s_cache[DI_CACHE];
+    __shared__ int s_state[DI_CACHE];   // 0 empty, 1 being written, 2 ready
+
+    for (int i = threadIdx.x; i < DI_CACHE; i += DI_THREADS) s_state[i] = 0;
+    const int64_t chunks_a = (A.n + DI_ROWS - 1) / DI_ROWS, chunks_b = (B.n + DI_ROWS - 1) / DI_ROWS;
+    for (int64_t chunk = blockIdx.x; chunk < chunks_a + chunks_b; chunk += gridDim.x) {
+        const bool in_b = chunk >= chunks_a;
         const StrTable& T = in_b ? B : A;
-        const int64_t i = in_b ? g - A.n : g;
-        const int32_t o0 = T.offs[i], len = T.offs[i + 1] - o0;
-        const uint8_t* s = T.bytes + o0;
-        uint32_t slot = (uint32_t)fnv1a(s, len) & cap_mask;
-        for (uint32_t probes = 0; probes <= cap_mask; probes++) {
-            unsigned long long w = *(volatile unsigned long long*)&slots[slot];
-            if (w == 0) {
-                unsigned long long prev = atomicCAS(&slots[slot], 0ull, (unsigned long long)g + 1ull);
-                if (prev == 0) {
-                    atomicAdd(n_distinct, 1u);
-                    break;
-                }
-                w = prev;
-            }
-            const int64_t rg = (int64_t)w - 1;
-            const StrTable& RT = rg >= A.n ? B : A;
-            const int64_t ri = rg >= A.n ? rg - A.n : rg;
-            const int32_t r0 = RT.offs[ri], rlen = RT.offs[ri + 1] - r0;
-            if (rlen == len && same_bytes(s, RT.bytes + r0, len)) break;
-            slot = (slot + 1) & cap_mask;
+        const int64_t r0 = (in_b ? chunk - chunks_a : chunk) * DI_ROWS;
+        const int rows = (int)min((int64_t)DI_ROWS, T.n - r0);
+        __syncthreads();   // previous chunk's readers are done with s_offs / s_bytes
+        for (int i = threadIdx.x; i <= rows; i += DI_THREADS) s_offs[i] = T.offs[r0 + i];
+        __syncthreads();
+        const int32_t b0 = s_offs[0], b1 = s_offs[rows];
+        const int32_t a0 = b0 & ~15;                       // staged range starts at a 16-byte boundary of the byte buffer
+        const bool staged = (b1 - a0) <= DI_BYTES && (reinterpret_cast<uintptr_t>(T.bytes) & 15) == 0;
+        if (staged) {
+            const uint4* src = reinterpret_cast<const uint4*>(T.bytes + a0);
+            const int n_vec = (b1 - a0 + 15) >> 4;         // the tail vector stays inside the (padded) allocation
+            for (int i = threadIdx.x; i < n_vec; i += DI_THREADS) reinterpret_cast<uint4*>(s_bytes)[i] = ld_stream_u32x4(src + i);
         }
-        (in_b ? slot_b : slot_a)[i] = (int32_t)slot;
+        __syncthreads();
+        for (int k = threadIdx.x; k < rows; k += DI_THREADS) {
+            const int32_t o = s_offs[k], len = s_offs[k + 1] - o;
+            const int64_t g = (in_b ? A.n : 0) + r0 + k;
+            uint32_t slot;
+            if (staged && len <= 16) {
+                // the name as two zero-padded little-endian words, from aligned 32-bit shared loads
+                const int so = o - a0;
+                const uint32_t* wp = reinterpret_cast<const uint32_t*>(s_bytes) + (so >> 2);
+                const int sh = (so & 3) * 8;
+                const uint32_t t0 = wp[0], t1 = wp[1], t2 = wp[2], t3 = wp[3], t4 = wp[4];
+                uint32_t v0 = __funnelshift_r(t0, t1, sh), v1 = __funnelshift_r(t1, t2, sh);
+                uint32_t v2 = __funnelshift_r(t2, t3, sh), v3 = __funnelshift_r(t3, t4, sh);
+                uint64_t w0 = (uint64_t)v0 | ((uint64_t)v1 << 32), w1 = (uint64_t)v2 | ((uint64_t)v3 << 32);
+                if (len < 8) {
+                    w0 &= len ? (~0ull >> (64 - 8 * len)) : 0ull;
+                    w1 = 0;
+                } else if (len < 16) {
+                    w1 &= len > 8 ? (~0ull >> (64 - 8 * (len - 8))) : 0ull;
+                }
+                const uint64_t h = hash_short(w0, w1, len);
+                // per-CTA cache (open addressing; duplicates of one name are harmless)
+                int ci = (int)(h >> 40) & (DI_CACHE - 1);
+                bool hit = false;
+                int free_at = -1;
+                for (int p = 0; p < DI_CACHE; p++) {
+                    const int stt = *(volatile int*)&s_state[ci];
+                    if (stt == 0) {
+                        free_at = ci;
+                        break;
+                    }
+                    if (stt == 2) {
+                        const CacheEntry& e = s_cache[ci];
+                        if (e.len == len && e.w0 == w0 && e.w1 == w1) {
+                            slot = e.slot;
+                            hit = true;
+                            break;
+                        }
+                    }
+                    ci = (ci + 1) & (DI_CACHE - 1);
+                }
+                if (!hit) {
+                    slot = global_resolve(A, B, slots, cap_mask, T.bytes + o, len, h, g, n_distinct);
+                    if (free_at >= 0 && atomicCAS(&s_state[free_at], 0, 1) == 0) {
+                        s_cache[free_at] = CacheEntry{w0, w1, len, slot};
+                        __threadfence_block();
+                        *(volatile int*)&s_state[free_at] = 2;
+                    }
+                }
+            } else {
+                const uint8_t* s = T.bytes + o;
+                slot = global_resolve(A, B, slots, cap_mask, s, len, hash_global_name(s, len), g, n_distinct);
+            }
+            (in_b ? slot_b : slot_a)[r0 + k] = (int32_t)slot;
+        }
     }
 }
 
@@ -74,8 +184,7 @@ dict_insert_kernel(StrTable A, StrTable B, unsigned long long* __restrict__ slot
 __global__ void dict_collect_kernel(StrTable A, StrTable B, const unsigned long long* __restrict__ slots, uint32_t cap,
                                     uint8_t* __restrict__ name_buf, unsigned long long name_cap,
                                     unsigned long long* __restrict__ cursor /* [0] bytes, [1] entries */,
-                                    int32_t* __restrict__ ent_slot, int32_t* __restrict__ ent_off, int32_t* __restrict__ ent_len,
-                                    uint32_t max_entries) {
+                                    int32_t* __restrict__ ent /* [3][max_entries]: slot, offset, length */, uint32_t max_entries) {
     uint32_t slot = blockIdx.x * blockDim.x + threadIdx.x;
     if (slot >= cap) return;
     unsigned long long w = slots[slot];
@@ -87,9 +196,9 @@ __global__ void dict_collect_kernel(StrTable A, StrTable B, const unsigned long 
     unsigned long long off = atomicAdd(&cursor[0], (unsigned long long)len);
     unsigned long long e = atomicAdd(&cursor[1], 1ull);
     if (e < max_entries) {
-        ent_slot[e] = (int32_t)slot;
-        ent_off[e] = (int32_t)off;
-        ent_len[e] = len;
+        ent[e] = (int32_t)slot;
+        ent[max_entries + e] = (int32_t)off;
+        ent[2 * max_entries + e] = len;
     }
     if (off + len <= name_cap)
         for (int i = 0; i < len; i++) name_buf[off + i] = RT.bytes[r0 + i];
@@ -97,8 +206,20 @@ __global__ void dict_collect_kernel(StrTable A, StrTable B, const unsigned long 
 
 __global__ void __launch_bounds__(256)
 dict_remap_kernel(int32_t* __restrict__ codes, int64_t n, const int32_t* __restrict__ slot2code) {
-    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+    const int64_t n_vec = n >> 2;
+    int4* cv = reinterpret_cast<int4*>(codes);
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_vec; i += (int64_t)gridDim.x * blockDim.x) {
+        int4 v = cv[i];
+        v.x = __ldg(slot2code + v.x);
+        v.y = __ldg(slot2code + v.y);
+        v.z = __ldg(slot2code + v.z);
+        v.w = __ldg(slot2code + v.w);
+        cv[i] = v;
+    }
+    if (blockIdx.x == 0 && threadIdx.x < (n & 3)) {
+        const int64_t i = (n_vec << 2) + threadIdx.x;
         codes[i] = __ldg(slot2code + codes[i]);
+    }
 }
 
 }  // namespace
@@ -108,6 +229,8 @@ extern "C" int giqlb_dict_encode(giqlb_ctx* ctx, const int32_t* offs_l, const ui
                                  int32_t* codes_r, giqlb_dict** out) {
     if (!ctx || !out || n_l < 0 || n_r < 0 || (n_l > 0 && (!offs_l || !codes_l)) || (n_r > 0 && (!offs_r || !codes_r)))
         return giqlb_fail(ctx, GIQLB_ERR_INVALID, "dict_encode: bad argument");
+    if (((reinterpret_cast<uintptr_t>(codes_l) | reinterpret_cast<uintptr_t>(codes_r)) & 15) != 0)
+        return giqlb_fail(ctx, GIQLB_ERR_INVALID, "dict_encode: code arrays must be 16-byte aligned");
     begin_call(ctx);
     *out = nullptr;
     giqlb_dict* d = new (std::nothrow) giqlb_dict();
@@ -121,87 +244,94 @@ extern "C" int giqlb_dict_encode(giqlb_ctx* ctx, const int32_t* offs_l, const ui
     unsigned long long* slots = nullptr;
     unsigned long long* cursor = reinterpret_cast<unsigned long long*>(ctx->d_scalars + 24);   // [0] bytes [1] entries [2] distinct
     unsigned int* n_distinct = reinterpret_cast<unsigned int*>(ctx->d_scalars + 26);
+    uint8_t* name_buf = nullptr;
+    int32_t *ent = nullptr, *slot2code = nullptr;
     int st = GIQLB_OK;
     uint32_t cap = 1u << 14;
-    int64_t blocks = ceil_div(n, 256 * 4), cap_blocks = (int64_t)ctx->sm_count * 16;
-    const unsigned grid = (unsigned)(blocks < cap_blocks ? blocks : cap_blocks);
+    size_t max_entries = DC_MAX_ENTRIES, name_cap = DC_NAME_CAP;
+    const int64_t chunks = ceil_div(n_l, DI_ROWS) + ceil_div(n_r, DI_ROWS), cap_blocks = (int64_t)ctx->sm_count * 6;
+    const unsigned grid = (unsigned)(chunks < cap_blocks ? chunks : cap_blocks);
+    std::vector<uint8_t> h_names;
+    std::vector<int32_t> h_ent;
     uint64_t distinct = 0;
-    while (true) {
+    // One round trip in the common case: insert + collect with generous fixed buffers, then ONE synchronisation
+    // fetching the counts, the entry table and the name bytes.  A table that turns out too full, or names that
+    // overflow the buffers, repeat the round with exact sizes.
+    for (int round = 0; round < 4; round++) {
+        dev_free(ctx, slots); dev_free(ctx, name_buf); dev_free(ctx, ent);
+        slots = nullptr; name_buf = nullptr; ent = nullptr;
         st = dev_alloc(ctx, &slots, (size_t)cap);
+        if (st == GIQLB_OK) st = dev_alloc(ctx, &name_buf, name_cap);
+        if (st == GIQLB_OK) st = dev_alloc(ctx, &ent, 3 * max_entries);
         if (st != GIQLB_OK) break;
         cudaMemsetAsync(slots, 0, (size_t)cap * 8, ctx->stream);
         cudaMemsetAsync(cursor, 0, 3 * 8, ctx->stream);
-        PhaseSpan ps(ctx, GIQLB_PH_DICT);
-        dict_insert_kernel<<<grid, 256, 0, ctx->stream>>>(A, B, slots, cap - 1, codes_l, codes_r, n_distinct);
-        ctx->launches_this_call++;
-        ctx->stats.kernels_total++;
-        if (cudaGetLastError() != cudaSuccess) { st = giqlb_fail(ctx, GIQLB_ERR_CUDA, "dict_encode: insert launch failed"); break; }
+        {
+            PhaseSpan ps(ctx, GIQLB_PH_DICT);
+            dict_insert_kernel<<<grid, DI_THREADS, 0, ctx->stream>>>(A, B, slots, cap - 1, codes_l, codes_r, n_distinct);
+            dict_collect_kernel<<<(cap + 255) / 256, 256, 0, ctx->stream>>>(A, B, slots, cap, name_buf, name_cap, cursor, ent,
+                                                                            (uint32_t)max_entries);
+            ctx->launches_this_call += 2;
+            ctx->stats.kernels_total += 2;
+        }
+        if (cudaGetLastError() != cudaSuccess) { st = giqlb_fail(ctx, GIQLB_ERR_CUDA, "dict_encode: launch failed"); break; }
+        h_names.resize(name_cap);
+        h_ent.resize(3 * max_entries);
+        // small tables ride along with the counters (pageable destinations: the copies complete at the sync below)
+        const bool speculative = max_entries * 12 + name_cap <= (size_t)256 * 1024;
+        if (speculative) {
+            cudaMemcpyAsync(h_ent.data(), ent, 3 * max_entries * 4, cudaMemcpyDeviceToHost, ctx->stream);
+            cudaMemcpyAsync(h_names.data(), name_buf, name_cap, cudaMemcpyDeviceToHost, ctx->stream);
+        }
         st = fetch_scalars(ctx, cursor, 3);
         if (st != GIQLB_OK) break;
+        const size_t need_bytes = (size_t)ctx->h_scalars[0];
         distinct = (uint64_t)(ctx->h_scalars[2] & 0xffffffffll);
-        if (distinct * 2 <= cap) break;
-        dev_free(ctx, slots);   // too full for cheap probing: grow and redo
-        slots = nullptr;
-        if (cap >= (1u << 30)) { st = giqlb_fail(ctx, GIQLB_ERR_RANGE, "dict_encode: more than 2^29 distinct chromosome names"); break; }
-        cap <<= 2;
-    }
-    if (st != GIQLB_OK) {
-        dev_free(ctx, slots);
-        delete d;
-        return st;
-    }
-    // gather distinct names; retry once with the exact byte size if the first buffer was too small
-    size_t name_cap = 1 << 16;
-    std::vector<uint8_t> h_names;
-    std::vector<int32_t> h_slot(distinct), h_off(distinct), h_len(distinct);
-    uint8_t* name_buf = nullptr;
-    int32_t *ent_slot = nullptr, *ent_off = nullptr, *ent_len = nullptr, *slot2code = nullptr;
-    for (int attempt = 0; attempt < 2 && st == GIQLB_OK; attempt++) {
-        st = dev_alloc(ctx, &name_buf, name_cap);
-        if (st == GIQLB_OK && !ent_slot) st = dev_alloc(ctx, &ent_slot, (size_t)distinct);
-        if (st == GIQLB_OK && !ent_off) st = dev_alloc(ctx, &ent_off, (size_t)distinct);
-        if (st == GIQLB_OK && !ent_len) st = dev_alloc(ctx, &ent_len, (size_t)distinct);
-        if (st != GIQLB_OK) break;
-        cudaMemsetAsync(cursor, 0, 2 * 8, ctx->stream);
-        PhaseSpan ps(ctx, GIQLB_PH_DICT);
-        dict_collect_kernel<<<(cap + 255) / 256, 256, 0, ctx->stream>>>(A, B, slots, cap, name_buf, name_cap, cursor, ent_slot,
-                                                                        ent_off, ent_len, (uint32_t)distinct);
-        ctx->launches_this_call++;
-        ctx->stats.kernels_total++;
-        if (cudaGetLastError() != cudaSuccess) { st = giqlb_fail(ctx, GIQLB_ERR_CUDA, "dict_encode: collect launch failed"); break; }
-        st = fetch_scalars(ctx, cursor, 2);
-        if (st != GIQLB_OK) break;
-        size_t need = (size_t)ctx->h_scalars[0];
-        if (need <= name_cap) {
-            h_names.resize(need ? need : 1);
-            if (need) cudaMemcpyAsync(h_names.data(), name_buf, need, cudaMemcpyDeviceToHost, ctx->stream);
-            cudaMemcpyAsync(h_slot.data(), ent_slot, distinct * 4, cudaMemcpyDeviceToHost, ctx->stream);
-            cudaMemcpyAsync(h_off.data(), ent_off, distinct * 4, cudaMemcpyDeviceToHost, ctx->stream);
-            cudaMemcpyAsync(h_len.data(), ent_len, distinct * 4, cudaMemcpyDeviceToHost, ctx->stream);
-            if (cudaStreamSynchronize(ctx->stream) != cudaSuccess) st = giqlb_fail(ctx, GIQLB_ERR_CUDA, "dict_encode: name copy failed");
-            dev_free(ctx, name_buf);
-            name_buf = nullptr;
+        bool redo = false;
+        if (distinct * 2 > cap) {   // too full for cheap probing: grow and redo
+            if (cap >= (1u << 30)) { st = giqlb_fail(ctx, GIQLB_ERR_RANGE, "dict_encode: more than 2^29 distinct chromosome names"); break; }
+            while (distinct * 2 > cap && cap < (1u << 30)) cap <<= 2;
+            redo = true;
+        }
+        if (distinct > max_entries || need_bytes > name_cap) {
+            max_entries = std::max<size_t>(max_entries, (size_t)distinct * 2);
+            name_cap = std::max<size_t>(name_cap, need_bytes * 2);
+            redo = true;
+        }
+        if (!redo) {
+            if (!speculative) {
+                cudaMemcpyAsync(h_ent.data(), ent, 3 * max_entries * 4, cudaMemcpyDeviceToHost, ctx->stream);
+                cudaMemcpyAsync(h_names.data(), name_buf, name_cap, cudaMemcpyDeviceToHost, ctx->stream);
+                if (cudaStreamSynchronize(ctx->stream) != cudaSuccess) st = giqlb_fail(ctx, GIQLB_ERR_CUDA, "dict_encode: name copy failed");
+            }
             break;
         }
-        dev_free(ctx, name_buf);
-        name_buf = nullptr;
-        name_cap = need;
-        if (attempt == 1) st = giqlb_fail(ctx, GIQLB_ERR_INTERNAL, "dict_encode: name buffer sizing did not converge");
+        if (round == 3) st = giqlb_fail(ctx, GIQLB_ERR_INTERNAL, "dict_encode: sizing did not converge");
     }
     if (st == GIQLB_OK) {
+        const int32_t *h_slot = h_ent.data(), *h_off = h_ent.data() + max_entries, *h_len = h_ent.data() + 2 * max_entries;
         std::vector<uint32_t> order(distinct);
         for (uint32_t i = 0; i < distinct; i++) order[i] = i;
-        auto name_of = [&](uint32_t e) { return std::string(reinterpret_cast<const char*>(h_names.data()) + h_off[e], (size_t)h_len[e]); };
         std::vector<std::string> names(distinct);
-        for (uint32_t i = 0; i < distinct; i++) names[i] = name_of(i);
-        // bytewise (unsigned char) order == std::string::compare with char_traits<char> only for ASCII; compare as unsigned
+        for (uint32_t i = 0; i < distinct; i++)
+            names[i] = std::string(reinterpret_cast<const char*>(h_names.data()) + h_off[i], (size_t)h_len[i]);
+        // bytewise (unsigned char) order, the order VARCHAR comparison gives for UTF-8
         std::sort(order.begin(), order.end(), [&](uint32_t a, uint32_t b) {
             const std::string &x = names[a], &y = names[b];
             size_t m = x.size() < y.size() ? x.size() : y.size();
             int c = memcmp(x.data(), y.data(), m);
             return c != 0 ? c < 0 : x.size() < y.size();
         });
-        std::vector<int32_t> h_s2c(cap, -1);
+        // slot -> code table through the context's pinned staging buffer: the upload and the remap kernels are
+        // enqueued without waiting (the next use of the staging buffer comes after a synchronisation)
+        int32_t* h_s2c = ctx->h_stage && (size_t)cap * 4 <= GIQLB_STAGE_BYTES ? reinterpret_cast<int32_t*>(ctx->h_stage) : nullptr;
+        std::vector<int32_t> pageable;
+        if (!h_s2c) {
+            pageable.assign(cap, -1);
+            h_s2c = pageable.data();
+        } else {
+            std::fill(h_s2c, h_s2c + cap, -1);
+        }
         d->names.resize(distinct);
         for (uint32_t code = 0; code < distinct; code++) {
             d->names[code] = names[order[code]];
@@ -209,28 +339,27 @@ extern "C" int giqlb_dict_encode(giqlb_ctx* ctx, const int32_t* offs_l, const ui
         }
         st = dev_alloc(ctx, &slot2code, (size_t)cap);
         if (st == GIQLB_OK) {
-            cudaMemcpyAsync(slot2code, h_s2c.data(), (size_t)cap * 4, cudaMemcpyHostToDevice, ctx->stream);
+            cudaMemcpyAsync(slot2code, h_s2c, (size_t)cap * 4, cudaMemcpyHostToDevice, ctx->stream);
             PhaseSpan ps(ctx, GIQLB_PH_DICT);
+            const int64_t rb = ceil_div(n_l > n_r ? n_l : n_r, 256 * 16), rcap = (int64_t)ctx->sm_count * 8;
+            const unsigned rgrid = (unsigned)(rb < 1 ? 1 : (rb < rcap ? rb : rcap));
             if (n_l > 0) {
-                dict_remap_kernel<<<grid, 256, 0, ctx->stream>>>(codes_l, n_l, slot2code);
+                dict_remap_kernel<<<rgrid, 256, 0, ctx->stream>>>(codes_l, n_l, slot2code);
                 ctx->launches_this_call++;
                 ctx->stats.kernels_total++;
             }
             if (n_r > 0) {
-                dict_remap_kernel<<<grid, 256, 0, ctx->stream>>>(codes_r, n_r, slot2code);
+                dict_remap_kernel<<<rgrid, 256, 0, ctx->stream>>>(codes_r, n_r, slot2code);
                 ctx->launches_this_call++;
                 ctx->stats.kernels_total++;
             }
-            // h_s2c is pageable: wait before it goes out of scope
-            if (cudaStreamSynchronize(ctx->stream) != cudaSuccess || cudaGetLastError() != cudaSuccess)
-                st = giqlb_fail(ctx, GIQLB_ERR_CUDA, "dict_encode: remap failed");
+            if (cudaGetLastError() != cudaSuccess) st = giqlb_fail(ctx, GIQLB_ERR_CUDA, "dict_encode: remap failed");
+            if (!pageable.empty() && cudaStreamSynchronize(ctx->stream) != cudaSuccess) st = giqlb_fail(ctx, GIQLB_ERR_CUDA, "dict_encode: remap failed");
         }
     }
     dev_free(ctx, slots);
     dev_free(ctx, name_buf);
-    dev_free(ctx, ent_slot);
-    dev_free(ctx, ent_off);
-    dev_free(ctx, ent_len);
+    dev_free(ctx, ent);
     dev_free(ctx, slot2code);
     if (st != GIQLB_OK) {
         delete d;

@@ -19,7 +19,8 @@ constexpr int LY_SMEM_CODES = 2048;
 __global__ void __launch_bounds__(LY_THREADS)
 layout_observe_kernel(const int32_t* __restrict__ code, const int32_t* __restrict__ start,
                       const int32_t* __restrict__ end, int64_t n, int32_t n_codes, int32_t sadj, int32_t eadj,
-                      long long* __restrict__ lohi, int* __restrict__ err) {
+                      long long* __restrict__ lohi, unsigned long long* __restrict__ obs /* [2] degenerate, negative */,
+                      int* __restrict__ err) {
     __shared__ int32_t s_lo[LY_SMEM_CODES];
     __shared__ int32_t s_hi[LY_SMEM_CODES];
     const bool use_smem = n_codes <= LY_SMEM_CODES;
@@ -31,6 +32,7 @@ layout_observe_kernel(const int32_t* __restrict__ code, const int32_t* __restric
         __syncthreads();
     }
     bool bad = false;
+    unsigned int degenerate = 0, negative = 0;
     for (int64_t i = (int64_t)blockIdx.x * LY_THREADS + threadIdx.x; i < n; i += (int64_t)gridDim.x * LY_THREADS) {
         int32_t c = code[i];
         long long s = (long long)start[i] + sadj, e = (long long)end[i] + eadj;
@@ -39,6 +41,8 @@ layout_observe_kernel(const int32_t* __restrict__ code, const int32_t* __restric
             bad = true;
             continue;
         }
+        degenerate += e <= s;
+        negative += e < s;
         if (use_smem) {
             if ((int32_t)lo < s_lo[c]) atomicMin(&s_lo[c], (int32_t)lo);
             if ((int32_t)hi > s_hi[c]) atomicMax(&s_hi[c], (int32_t)hi);
@@ -48,6 +52,14 @@ layout_observe_kernel(const int32_t* __restrict__ code, const int32_t* __restric
         }
     }
     if (bad) err[1] = 1;
+    if (__any_sync(FULL_MASK, degenerate != 0)) {
+        degenerate = warp_reduce_add(degenerate);
+        negative = warp_reduce_add(negative);
+        if (lane_id() == 0) {
+            atomicAdd(&obs[0], (unsigned long long)degenerate);
+            if (negative) atomicAdd(&obs[1], (unsigned long long)negative);
+        }
+    }
     if (use_smem) {
         __syncthreads();
         for (int i = threadIdx.x; i < n_codes; i += LY_THREADS) {
@@ -109,7 +121,8 @@ index_keygen_kernel(const int32_t* __restrict__ code, const int32_t* __restrict_
                     int64_t n, int32_t n_codes, int32_t sadj, int32_t eadj,
                     const uint32_t* __restrict__ base, const int32_t* __restrict__ lo32,
                     const int32_t* __restrict__ hi32, uint32_t* __restrict__ gs, uint32_t* __restrict__ ge,
-                    unsigned long long* __restrict__ counters /* [0] end<=start [1] end<start [2] outside layout */) {
+                    unsigned long long* __restrict__ counters /* [0] end<=start [1] end<start [2] outside layout */,
+                    int* __restrict__ err) {
     unsigned int degenerate = 0, negative = 0, outside = 0;
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
         const int64_t r = rows ? (int64_t)rows[i] : i;
@@ -139,7 +152,10 @@ index_keygen_kernel(const int32_t* __restrict__ code, const int32_t* __restrict_
     if (lane_id() == 0) {
         if (degenerate) atomicAdd(&counters[0], (unsigned long long)degenerate);
         if (negative) atomicAdd(&counters[1], (unsigned long long)negative);
-        if (outside) atomicAdd(&counters[2], (unsigned long long)outside);
+        if (outside) {
+            atomicAdd(&counters[2], (unsigned long long)outside);
+            err[3] = 1;
+        }
     }
 }
 
@@ -214,6 +230,8 @@ extern "C" int giqlb_layout_create(giqlb_ctx* ctx, int32_t n_codes, int64_t pad,
     if (st == GIQLB_OK) st = dev_alloc(ctx, &lay->d_base, (size_t)n_codes + 1);
     if (st == GIQLB_OK) st = dev_alloc(ctx, &lay->d_lo32, (size_t)n_codes);
     if (st == GIQLB_OK) st = dev_alloc(ctx, &lay->d_hi32, (size_t)n_codes);
+    if (st == GIQLB_OK) st = dev_alloc(ctx, &lay->d_obs, (size_t)2 * GIQLB_MAX_OBSERVED);
+    if (st == GIQLB_OK && cudaMemsetAsync(lay->d_obs, 0, 2 * GIQLB_MAX_OBSERVED * 8, ctx->stream) != cudaSuccess) st = GIQLB_ERR_CUDA;
     if (st != GIQLB_OK) {
         giqlb_layout_free(ctx, lay);
         return st;
@@ -234,10 +252,13 @@ extern "C" int giqlb_layout_observe(giqlb_ctx* ctx, giqlb_layout* lay, const int
     begin_call(ctx);
     if (n > 0) {
         if (lay->n_codes == 0) return giqlb_fail(ctx, GIQLB_ERR_INVALID, "layout_observe: rows given but the dictionary is empty");
+        // the last slot collects every observe() beyond GIQLB_MAX_OBSERVED - 1 (those tables resolve lazily)
+        const size_t slot = lay->observed.size() < GIQLB_MAX_OBSERVED - 1 ? lay->observed.size() : GIQLB_MAX_OBSERVED - 1;
         PhaseSpan ps(ctx, GIQLB_PH_LAYOUT);
         layout_observe_kernel<<<grid_for(ctx, n, LY_THREADS * 8, 8), LY_THREADS, 0, ctx->stream>>>(
-            code, start, end, n, lay->n_codes, start_adj, end_adj, (long long*)lay->d_lohi, ctx->d_err);
+            code, start, end, n, lay->n_codes, start_adj, end_adj, (long long*)lay->d_lohi, lay->d_obs + 2 * slot, ctx->d_err);
         LAUNCH_CHECK(ctx);
+        if (lay->observed.size() < GIQLB_MAX_OBSERVED - 1) lay->observed.push_back({code, n, start_adj, end_adj, -1, -1});
     }
     return end_call(ctx);
 }
@@ -265,7 +286,13 @@ extern "C" int giqlb_layout_finalize(giqlb_ctx* ctx, giqlb_layout* lay) {
     }
     CUDA_TRY(ctx, cudaMemcpyAsync(lay->h_base.data(), lay->d_base, ((size_t)lay->n_codes + 1) * 4, cudaMemcpyDeviceToHost, ctx->stream));
     CUDA_TRY(ctx, cudaMemcpyAsync(h_err, ctx->d_err, sizeof(h_err), cudaMemcpyDeviceToHost, ctx->stream));
+    unsigned long long h_obs[2 * GIQLB_MAX_OBSERVED];
+    CUDA_TRY(ctx, cudaMemcpyAsync(h_obs, lay->d_obs, sizeof(h_obs), cudaMemcpyDeviceToHost, ctx->stream));
     CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    for (size_t k = 0; k < lay->observed.size(); k++) {
+        lay->observed[k].n_degenerate = (int64_t)h_obs[2 * k];
+        lay->observed[k].n_negative = (int64_t)h_obs[2 * k + 1];
+    }
     for (int i = 0; i < lay->n_codes; i++) {
         lay->h_lo[i] = lo32[i];
         lay->h_hi[i] = hi32[i];
@@ -292,6 +319,7 @@ extern "C" int giqlb_layout_free(giqlb_ctx* ctx, giqlb_layout* lay) {
         dev_free(ctx, lay->d_base);
         dev_free(ctx, lay->d_lo32);
         dev_free(ctx, lay->d_hi32);
+        dev_free(ctx, lay->d_obs);
     }
     delete lay;
     return GIQLB_OK;
@@ -326,6 +354,7 @@ extern "C" int giqlb_index_free(giqlb_ctx* ctx, giqlb_index* ix) {
         dev_free(ctx, ix->ge_sorted);
         dev_free(ctx, ix->pos_by_end);
         dev_free(ctx, ix->d_block_off);
+        dev_free(ctx, ix->d_counters);
     }
     delete ix;
     return GIQLB_OK;
@@ -343,9 +372,10 @@ extern "C" int giqlb_index_columns(const giqlb_index* ix, const uint32_t** gstar
     return GIQLB_OK;
 }
 
-extern "C" int giqlb_index_info(const giqlb_index* ix, int64_t* n_degenerate, int64_t* n_negative, int32_t* n_blocks,
+extern "C" int giqlb_index_info(giqlb_ctx* ctx, giqlb_index* ix, int64_t* n_degenerate, int64_t* n_negative, int32_t* n_blocks,
                                 int64_t* block_off_host /* [257] or NULL */) {
-    if (!ix) return GIQLB_ERR_INVALID;
+    if (!ctx || !ix) return GIQLB_ERR_INVALID;
+    GIQLB_TRY(giqlb_index_resolve(ctx, ix, nullptr));
     if (n_degenerate) *n_degenerate = ix->n_degenerate;
     if (n_negative) *n_negative = ix->n_negative;
     if (n_blocks) *n_blocks = ix->n_blocks;
@@ -378,7 +408,7 @@ extern "C" int giqlb_index_build_rows(giqlb_ctx* ctx, const giqlb_layout* lay, c
     for (int i = 2; i <= GIQLB_MAX_STRAND_CODES; i++) ix->block_off[i] = n;
 
     uint32_t *ka = nullptr, *kb = nullptr, *va = nullptr, *vb = nullptr, *ge_u = nullptr, *gs_u = nullptr;
-    unsigned long long* counters = reinterpret_cast<unsigned long long*>(ctx->d_scalars + 16);
+    unsigned long long* counters = nullptr;
     int st = GIQLB_OK;
 #define IB_TRY(expr)                      \
     do {                                  \
@@ -394,6 +424,8 @@ extern "C" int giqlb_index_build_rows(giqlb_ctx* ctx, const giqlb_layout* lay, c
         }                                                                                               \
     } while (0)
 
+    IB_TRY(dev_alloc(ctx, &ix->d_counters, 4));
+    counters = ix->d_counters;
     IB_TRY(dev_alloc(ctx, &ka, (size_t)n));
     IB_TRY(dev_alloc(ctx, &kb, (size_t)n));
     IB_TRY(dev_alloc(ctx, &va, (size_t)n));
@@ -406,7 +438,7 @@ extern "C" int giqlb_index_build_rows(giqlb_ctx* ctx, const giqlb_layout* lay, c
         {
         PhaseSpan ps(ctx, GIQLB_PH_KEYGEN);
         index_keygen_kernel<<<grid_for(ctx, n, 256 * 4, 8), 256, 0, ctx->stream>>>(
-            code, start, end, rows, n, lay->n_codes, start_adj, end_adj, lay->d_base, lay->d_lo32, lay->d_hi32, ka, ge_u, counters);
+            code, start, end, rows, n, lay->n_codes, start_adj, end_adj, lay->d_base, lay->d_lo32, lay->d_hi32, ka, ge_u, counters, ctx->d_err);
         ctx->launches_this_call++;
         ctx->stats.kernels_total++;
         }
@@ -470,14 +502,18 @@ extern "C" int giqlb_index_build_rows(giqlb_ctx* ctx, const giqlb_layout* lay, c
     }
     dev_free(ctx, ka); dev_free(ctx, kb); dev_free(ctx, va); dev_free(ctx, vb); dev_free(ctx, ge_u); dev_free(ctx, gs_u);
     ka = kb = va = vb = ge_u = gs_u = nullptr;
-    st = fetch_scalars(ctx, counters, 3);
-    if (st != GIQLB_OK) goto fail;
-    ix->n_degenerate = ctx->h_scalars[0];
-    ix->n_negative = ctx->h_scalars[1];
-    if (ctx->h_scalars[2] != 0) {
-        st = giqlb_fail(ctx, GIQLB_ERR_RANGE, "index_build: %lld rows lie outside the layout (observe the table before finalize)",
-                        (long long)ctx->h_scalars[2]);
-        goto fail;
+    // degenerate-row counts: known already when the table was observed on this layout with the same offsets
+    // (finalize() fetched them); otherwise they stay on the device until giqlb_index_resolve needs them.
+    // Rows outside the layout raise the sticky flag checked at the next host round trip.
+    ix->resolved = false;
+    for (const auto& o : lay->observed) {
+        if (o.code != code || o.sadj != start_adj || o.eadj != end_adj || o.n_degenerate < 0) continue;
+        if (o.n_degenerate == 0 || (!rows && o.n == n)) {
+            ix->n_degenerate = o.n_degenerate;
+            ix->n_negative = o.n_negative;
+            ix->resolved = true;
+            break;
+        }
     }
     ctx->stats.rows_in[0] = n;
     ctx->stats.rows_in[1] = 0;
@@ -581,4 +617,25 @@ int giqlb_index_ensure_end_sorted(giqlb_ctx* ctx, giqlb_index* ix) {
         ix->ge_sorted = nullptr; ix->pos_by_end = nullptr;
     }
     return st;
+}
+
+// Fetches the degenerate-row counts of up to two indexes in ONE round trip (no-op when already known).
+int giqlb_index_resolve(giqlb_ctx* ctx, giqlb_index* a, giqlb_index* b) {
+    giqlb_index* todo[2] = {a && !a->resolved ? a : nullptr, b && !b->resolved && b != a ? b : nullptr};
+    if (!todo[0] && !todo[1]) return GIQLB_OK;
+    for (int k = 0; k < 2; k++)
+        if (todo[k]) CUDA_TRY(ctx, cudaMemcpyAsync(ctx->h_scalars + 32 + 4 * k, todo[k]->d_counters, 3 * 8, cudaMemcpyDeviceToHost, ctx->stream));
+    CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    for (int k = 0; k < 2; k++) {
+        if (!todo[k]) continue;
+        const int64_t* c = ctx->h_scalars + 32 + 4 * k;
+        todo[k]->n_degenerate = c[0];
+        todo[k]->n_negative = c[1];
+        todo[k]->resolved = true;
+        if (c[2] != 0) {
+            cudaMemsetAsync(ctx->d_err + 3, 0, sizeof(int), ctx->stream);
+            return giqlb_fail(ctx, GIQLB_ERR_RANGE, "index: %lld rows lie outside the layout (observe the table before finalize)", (long long)c[2]);
+        }
+    }
+    return GIQLB_OK;
 }

@@ -490,6 +490,7 @@ static int plan_enqueue(giqlb_ctx* ctx, giqlb_index* L, giqlb_index* R, giqlb_jo
     if (L->layout != R->layout) return giqlb_fail(ctx, GIQLB_ERR_INVALID, "intersects: indexes were built on different layouts");
     if (L->grouped_by_strand || R->grouped_by_strand)
         return giqlb_fail(ctx, GIQLB_ERR_INVALID, "intersects: strand-grouped indexes are not accepted");
+    GIQLB_TRY(giqlb_index_resolve(ctx, L, R));
     giqlb_joinplan* p = new (std::nothrow) giqlb_joinplan();
     if (!p) return GIQLB_ERR_NOMEM;
     p->L = L;
@@ -571,7 +572,7 @@ extern "C" int giqlb_intersects_plan(giqlb_ctx* ctx, giqlb_index* L, giqlb_index
     *out = nullptr;
     giqlb_joinplan* p = nullptr;
     GIQLB_TRY(plan_enqueue(ctx, L, R, &p));
-    int st = fetch_scalars(ctx, ctx->d_scalars, 1);
+    int st = fetch_scalars_checked(ctx, ctx->d_scalars, 1);
     if (st != GIQLB_OK) {
         giqlb_joinplan_free(ctx, p);
         return st;
@@ -601,7 +602,7 @@ extern "C" int giqlb_intersects_join(giqlb_ctx* ctx, giqlb_index* L, giqlb_index
     GIQLB_TRY(plan_enqueue(ctx, L, R, &p));
     // the emit kernel reads the total on the device and writes nothing when it exceeds `capacity`
     int st = capacity > 0 ? emit_enqueue(ctx, p, out_l, out_r, capacity) : GIQLB_OK;
-    if (st == GIQLB_OK) st = fetch_scalars(ctx, ctx->d_scalars, 1);
+    if (st == GIQLB_OK) st = fetch_scalars_checked(ctx, ctx->d_scalars, 1);
     int64_t total = st == GIQLB_OK ? ctx->h_scalars[0] : -1;
     giqlb_joinplan_free(ctx, p);
     if (st != GIQLB_OK) return st;
@@ -646,6 +647,7 @@ extern "C" int giqlb_intersects_count_rows(giqlb_ctx* ctx, const giqlb_layout* l
     ProbeCols P;
     GIQLB_TRY(probe_cols(ctx, lay, code, start, end, n, start_adj, end_adj, &P));
     GIQLB_TRY(giqlb_index_ensure_pmax(ctx, R));
+    GIQLB_TRY(giqlb_index_resolve(ctx, R, nullptr));
     const int r_deg = R->n_degenerate > 0;
     if (!r_deg) GIQLB_TRY(giqlb_index_ensure_end_sorted(ctx, R));
     if (n > 0) {

@@ -14,7 +14,10 @@ namespace {
 
 constexpr int RS_THREADS = 256;
 constexpr int RS_WARPS = RS_THREADS / 32;
-constexpr int RS_IPT = 16;
+#ifndef GIQLB_RS_IPT
+#define GIQLB_RS_IPT 16
+#endif
+constexpr int RS_IPT = GIQLB_RS_IPT;
 constexpr int RS_TILE = RS_THREADS * RS_IPT;   // 4096 keys per tile
 constexpr int RS_RADIX = 256;
 constexpr int RS_MAX_PASSES = 4;
@@ -63,7 +66,7 @@ rs_histogram_kernel(const uint32_t* __restrict__ keys, int64_t n, int begin_bit,
 // ---- one digit pass ----------------------------------------------------------------------------------
 // IDENTITY_VALS: payload of key i is i itself (first pass; no payload array is read).
 template <bool IDENTITY_VALS>
-__global__ void __launch_bounds__(RS_THREADS, 4)
+__global__ void __launch_bounds__(RS_THREADS, RS_IPT >= 16 ? 4 : 6)
 rs_onesweep_kernel(const uint32_t* __restrict__ keys_in, const uint32_t* __restrict__ vals_in,
                    uint32_t* __restrict__ keys_out, uint32_t* __restrict__ vals_out, int64_t n, int shift,
                    const uint32_t* __restrict__ ghist /* this pass, [256] */,

@@ -254,7 +254,7 @@ class _Index:
 
     def info(self):
         d, ng, nb = ctypes.c_int64(), ctypes.c_int64(), ctypes.c_int32()
-        self.e.lib.giqlb_index_info(self.h, ctypes.byref(d), ctypes.byref(ng), ctypes.byref(nb), None)
+        self.e._check(self.e.lib.giqlb_index_info(self.e.ctx, self.h, ctypes.byref(d), ctypes.byref(ng), ctypes.byref(nb), None))
         return d.value, ng.value, nb.value
 
     def free(self):

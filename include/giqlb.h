@@ -151,6 +151,9 @@ int giqlb_layout_info(const giqlb_layout* lay, int32_t* n_codes, uint64_t* total
 int giqlb_layout_tables(const giqlb_layout* lay, const uint32_t** base_dev, const int32_t** lo_dev,
                         const int32_t** hi_dev);
 
+/* index_build is asynchronous.  Rows that lie outside the layout (a table that was not observed) raise a sticky
+ * error reported as GIQLB_ERR_RANGE by the next call that returns a host value (plan/join, index_info, sync).
+ * observe() and index_build() of one table must use the same offsets. */
 /* ---- sorted index -----------------------------------------------------------------------------
  * LSD radix sort of the linearised start with carried row ids; then gathers the linearised end.
  * strand may be NULL.  start_adj/end_adj are the canonical.py:16-52 offsets (raw + adj = canonical).
@@ -170,7 +173,7 @@ int64_t giqlb_index_rows(const giqlb_index* ix);
 int giqlb_index_columns(const giqlb_index* ix, const uint32_t** gstart, const uint32_t** gend,
                         const int32_t** row_id, const uint8_t** strand);
 /* rows with end <= start / end < start; strand blocks after giqlb_index_group_by_strand */
-int giqlb_index_info(const giqlb_index* ix, int64_t* n_degenerate, int64_t* n_negative, int32_t* n_blocks,
+int giqlb_index_info(giqlb_ctx* ctx, giqlb_index* ix, int64_t* n_degenerate, int64_t* n_negative, int32_t* n_blocks,
                      int64_t* block_off_host /* [257] or NULL */);
 /* reorders the index into blocks of equal strand code, each still sorted by start (CLUSTER/MERGE/NEAREST
  * with stranded := true) */

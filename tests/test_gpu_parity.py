@@ -384,3 +384,25 @@ def test_join_heavily_skewed_tiles_are_split(engine, c_oracle):
         got = engine.intersects(ta, tb).sorted_packed()
         exp = c_oracle.intersects_pairs(A["code"], A["start"], A["end"], B["code"], B["start"], B["end"], 1)
         assert len(got) > 90_000 and np.array_equal(got, (exp[:, 0] << 32) | exp[:, 1])
+
+
+# ---- chromosome dictionary ---------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("n_names,max_len", [(1, 5), (24, 5), (300, 16), (3000, 40), (20000, 24)])
+def test_dict_encode_matches_host_sort(n_names, max_len, engine):
+    """device dictionary: codes decode to the original strings, names are sorted bytewise (VARCHAR order), any byte
+    is allowed (quotes, empty string, names longer than the 16-byte fast path, more names than one round trip)"""
+    rng = np.random.default_rng(n_names)
+    alphabet = list("abcXYZ019_'\"-. é")
+    names = {""} if n_names > 1 else set()
+    while len(names) < n_names:
+        names.add("".join(rng.choice(alphabet, size=rng.integers(1, max_len + 1))))
+    names = sorted(names)
+    rows_a = [names[i] for i in rng.integers(0, len(names), size=7000)]
+    rows_b = [names[i] for i in rng.integers(0, len(names), size=5000)] + names     # every name appears
+    ta = engine.table({"chrom": rows_a, "start": np.zeros(len(rows_a), np.int32), "end": np.ones(len(rows_a), np.int32)})
+    tb = engine.table({"chrom": rows_b, "start": np.zeros(len(rows_b), np.int32), "end": np.ones(len(rows_b), np.int32)})
+    d = engine.encode(ta, tb)
+    assert d.names == sorted(names, key=lambda s: s.encode())
+    dn = np.array(d.names, dtype=object)
+    assert list(dn[ta.codes.cpu().numpy()]) == rows_a and list(dn[tb.codes.cpu().numpy()]) == rows_b
+    assert ta.dictionary is tb.dictionary
