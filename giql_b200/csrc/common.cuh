@@ -176,7 +176,7 @@ static inline int giqlb_fail(giqlb_ctx* ctx, int code, const char* fmt, ...) {
 
 static inline int dev_alloc_bytes(giqlb_ctx* ctx, void** p, size_t bytes) {
     *p = nullptr;
-    bytes = ((bytes ? bytes : 1) + 511) & ~(size_t)511;   // keeps vector loads of a padded tail in bounds
+    bytes = (bytes + 64 + 511) & ~(size_t)511;   // >= 64 bytes of slack: vector loads / 16-byte bulk copies of a tail stay in bounds
     auto it = ctx->cache_free.lower_bound(bytes);
     if (it != ctx->cache_free.end() && it->first <= 2 * bytes + 4096) {
         *p = it->second;

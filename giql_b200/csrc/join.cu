@@ -31,6 +31,8 @@
 // General path (some row has end <= start): the literal predicate is scanned over the candidates
 //     j in [first j with pmax[j] > l.gs,  lower_bound(R.gs, l.ge))        pmax = running max of R.ge
 // which is exact for any rows, at the cost of visiting non-matching candidates.
+#include <cuda/ptx>
+
 #include "common.cuh"
 
 namespace {
@@ -363,6 +365,281 @@ join_emit_kernel(JoinSide L, JoinSide R, const int32_t* __restrict__ part, int64
     }
 }
 
+// ---- single-pass join (giqlb_intersects_join): count, offset and emit of a tile in ONE kernel ------------------
+// When the caller brings an output buffer, the count and emit passes collapse: a CTA stages its tile with bulk
+// (TMA) copies, computes the runs, publishes the tile's pair count and obtains its output offset through a
+// decoupled look-back over per-tile status words (tiles take tickets, so a tile only waits on tiles already
+// scheduled), then emits straight from shared memory.  Every input row is read once, no item codes travel
+// through HBM, and the capacity check is per tile (a tile that would overrun the buffer writes nothing; the
+// grand total tells the host how much room a retry needs).  Tiles whose output exceeds J_BIG pairs only
+// publish their offset and are emitted afterwards by a second kernel that shares each of them among many CTAs.
+constexpr int J_BIG = 32768;
+constexpr unsigned long long JF_FLAG_AGG = 1ull << 62;
+constexpr unsigned long long JF_FLAG_INCL = 2ull << 62;
+constexpr unsigned long long JF_VALUE_MASK = (1ull << 62) - 1;
+constexpr uint32_t JF_SPIN_LIMIT = 1u << 26;
+
+struct __align__(16) TileSmem {
+    uint32_t gs[2][JW + 8];                  // staged start windows: [0] L, [1] R (16-byte aligned source => up to 3 lead-in rows)
+    uint32_t ge[2][JT + 8];                  // ends of the tile's own rows
+    int32_t rid[2][JW + 8];                  // row ids of the windows
+    unsigned long long off[JT + 1];          // local exclusive output offsets of the tile's items (merge order)
+    uint32_t code[JT];                       // run start | class of every item
+    unsigned long long scratch[JB / 32 + 2];
+    unsigned long long tile_off;
+    unsigned long long bar[2];               // mbarriers: [0] starts + ends, [1] row ids
+    uint32_t tile;
+};
+
+__device__ __forceinline__ void bar_wait(unsigned long long* bar, uint32_t parity) {
+    while (!cuda::ptx::mbarrier_try_wait_parity(reinterpret_cast<uint64_t*>(bar), parity)) {
+    }
+}
+
+// Issues the bulk copy of elements [first, first + count) of a 4-byte array into dst; the source is rounded down
+// to a 16-byte boundary (the library pads its arrays), so dst[(first & 3) + i] = src[first + i].
+__device__ __forceinline__ uint32_t window_bytes(int64_t first, int count) {
+    return (uint32_t)((((int)(first & 3) + count + 3) >> 2) << 4);
+}
+__device__ __forceinline__ void window_copy(void* dst, const void* src_base, int64_t first, int count, unsigned long long* bar) {
+    if (count <= 0) return;
+    const char* src = reinterpret_cast<const char*>(src_base) + ((first & ~(int64_t)3) << 2);
+    cuda::ptx::cp_async_bulk(cuda::ptx::space_cluster, cuda::ptx::space_global, dst, src, window_bytes(first, count),
+                             reinterpret_cast<uint64_t*>(bar));
+}
+
+// Thread 0 arms both barriers and issues the six window copies of tile g.
+__device__ __forceinline__ void tile_stage(TileSmem& sm, const TileGeom& g, const JoinSide& L, const JoinSide& R) {
+    uint32_t b0 = 0, b1 = 0;
+    if (g.wl > 0) b0 += window_bytes(g.x0, g.wl), b1 += window_bytes(g.x0, g.wl);
+    if (g.wr > 0) b0 += window_bytes(g.y0, g.wr), b1 += window_bytes(g.y0, g.wr);
+    if (g.nl > 0) b0 += window_bytes(g.x0, g.nl);
+    if (g.nr > 0) b0 += window_bytes(g.y0, g.nr);
+    cuda::ptx::mbarrier_arrive_expect_tx(cuda::ptx::sem_release, cuda::ptx::scope_cta, cuda::ptx::space_shared,
+                                         reinterpret_cast<uint64_t*>(&sm.bar[0]), b0);
+    window_copy(sm.gs[0], L.gs, g.x0, g.wl, &sm.bar[0]);
+    window_copy(sm.gs[1], R.gs, g.y0, g.wr, &sm.bar[0]);
+    window_copy(sm.ge[0], L.ge, g.x0, g.nl, &sm.bar[0]);
+    window_copy(sm.ge[1], R.ge, g.y0, g.nr, &sm.bar[0]);
+    cuda::ptx::mbarrier_arrive_expect_tx(cuda::ptx::sem_release, cuda::ptx::scope_cta, cuda::ptx::space_shared,
+                                         reinterpret_cast<uint64_t*>(&sm.bar[1]), b1);
+    window_copy(sm.rid[0], L.rid, g.x0, g.wl, &sm.bar[1]);
+    window_copy(sm.rid[1], R.rid, g.y0, g.wr, &sm.bar[1]);
+}
+
+// The thread's J_IPT consecutive rows of the tile's merge sequence: run start/class codes and exact run lengths.
+// Branch-free in the class: the row's own table and the other table are selected by index.
+__device__ __forceinline__ void tile_runs(const TileSmem& sm, const TileGeom& g, const JoinSide& L, const JoinSide& R,
+                                          uint32_t (&code)[J_IPT], uint32_t (&cnt)[J_IPT]) {
+    const uint32_t* gsl = sm.gs[0] + (g.x0 & 3);
+    const uint32_t* gsr = sm.gs[1] + (g.y0 & 3);
+    const uint32_t* gel = sm.ge[0] + (g.x0 & 3);
+    const uint32_t* ger = sm.ge[1] + (g.y0 & 3);
+    const int n_items = g.nl + g.nr;
+    const int m0 = threadIdx.x * J_IPT;
+    int i = g.nl, j = g.nr;
+    if (m0 < n_items) {   // merge-path diagonal m0: i = L rows among the first m0 merged rows ("L before R on ties")
+        int lo = m0 > g.nr ? m0 - g.nr : 0, hi = m0 < g.nl ? m0 : g.nl;
+        while (lo < hi) {
+            const int mid = (lo + hi) >> 1;
+            if (gsl[mid] <= gsr[m0 - 1 - mid]) lo = mid + 1; else hi = mid;
+        }
+        i = lo;
+        j = m0 - lo;
+    }
+#pragma unroll
+    for (int k = 0; k < J_IPT; k++) {
+        code[k] = 0;
+        cnt[k] = 0;
+        if (m0 + k < n_items) {
+            const bool take_l = j >= g.nr || (i < g.nl && gsl[i] <= gsr[j]);
+            const uint32_t xge = take_l ? gel[i] : ger[j];   // the row's own end
+            const uint32_t* ys = take_l ? gsr : gsl;         // the other table's window
+            const int start = take_l ? j : i, wy = take_l ? g.wr : g.wl;
+            int h = start;                                   // run end: a few rows away on average -> linear probe, then binary
+            while (h < wy && h < start + 8 && ys[h] < xge) h++;
+            if (h == start + 8 && h < wy && ys[h] < xge) h = s_lower_bound(ys, h + 1, wy, xge);
+            int64_t c = h - start;
+            if (h == wy) {                                   // the run may continue beyond the staged window
+                const uint32_t* yg = take_l ? R.gs : L.gs;
+                const int64_t yn = take_l ? R.n : L.n, ybase = take_l ? g.y0 : g.x0;
+                if (ybase + wy < yn) c = lb_gallop(yg, ybase + wy, yn, xge) - (ybase + start);
+            }
+            code[k] = (uint32_t)start | (take_l ? 0u : J_CLASS_B);
+            cnt[k] = (uint32_t)c;
+            i += take_l ? 1 : 0;
+            j += take_l ? 0 : 1;
+        }
+    }
+}
+
+// Block scan of the run lengths into sm.off / sm.code; returns the tile's pair count (same value in every thread).
+__device__ __forceinline__ unsigned long long tile_offsets(TileSmem& sm, const uint32_t (&code)[J_IPT], const uint32_t (&cnt)[J_IPT]) {
+    unsigned long long sum = 0;
+#pragma unroll
+    for (int k = 0; k < J_IPT; k++) sum += cnt[k];
+    unsigned long long tot;
+    unsigned long long ex = block_excl_scan_add<unsigned long long>(sum, sm.scratch, &tot);
+#pragma unroll
+    for (int k = 0; k < J_IPT; k++) {
+        sm.off[threadIdx.x * J_IPT + k] = ex;
+        sm.code[threadIdx.x * J_IPT + k] = code[k];
+        ex += cnt[k];
+    }
+    if (threadIdx.x == 0) sm.off[JT] = tot;
+    return tot;
+}
+
+// Emits the tile's local output slots [a, b) at global positions off_t + slot; every thread writes J_OPT consecutive
+// pairs aligned to J_OPT (16-byte vector stores).
+__device__ __forceinline__ void tile_emit(const TileSmem& sm, const TileGeom& g, const JoinSide& L, const JoinSide& R,
+                                          unsigned long long off_t, unsigned long long a, unsigned long long b,
+                                          int32_t* __restrict__ out_l, int32_t* __restrict__ out_r, bool vec_ok) {
+    const int32_t* lrid = sm.rid[0] + (g.x0 & 3);
+    const int32_t* rrid = sm.rid[1] + (g.y0 & 3);
+    const unsigned long long g_a = off_t + a, g_b = off_t + b;
+    const unsigned long long g_first = g_a & ~(unsigned long long)(J_OPT - 1);
+    for (unsigned long long gp = g_first + (unsigned long long)threadIdx.x * J_OPT; gp < g_b; gp += (unsigned long long)JB * J_OPT) {
+        const unsigned long long p0 = gp > g_a ? gp : g_a, p1 = min(gp + J_OPT, g_b);
+        if (p0 >= p1) continue;
+        int item = s_upper_bound_u64(sm.off, JT + 1, p0 - off_t) - 1;    // last item whose offset is <= the first slot
+        int32_t vl[J_OPT], vr[J_OPT];
+#pragma unroll
+        for (int q = 0; q < J_OPT; q++) {
+            const unsigned long long pq = gp + q;
+            vl[q] = 0;
+            vr[q] = 0;
+            if (pq >= p0 && pq < p1) {
+                const unsigned long long sl = pq - off_t;
+                while (sm.off[item + 1] <= sl) item++;              // skip items with empty runs
+                const uint32_t cd = sm.code[item];
+                const int start = (int)(cd & 0x7FFFu);
+                const int64_t w = (int64_t)start + (int64_t)(sl - sm.off[item]);   // offset into the other table's window
+                if (!(cd & J_CLASS_B)) {                            // item is L row (item - start); its run lies in R
+                    vl[q] = lrid[item - start];
+                    vr[q] = w < g.wr ? rrid[w] : __ldg(R.rid + g.y0 + w);
+                } else {                                            // item is R row (item - start); its run lies in L
+                    vr[q] = rrid[item - start];
+                    vl[q] = w < g.wl ? lrid[w] : __ldg(L.rid + g.x0 + w);
+                }
+            }
+        }
+        if (vec_ok && p0 == gp && p1 == gp + J_OPT) {
+            st_stream_u32x4(reinterpret_cast<uint4*>(out_l + gp), make_uint4(vl[0], vl[1], vl[2], vl[3]));
+            st_stream_u32x4(reinterpret_cast<uint4*>(out_l + gp) + 1, make_uint4(vl[4], vl[5], vl[6], vl[7]));
+            st_stream_u32x4(reinterpret_cast<uint4*>(out_r + gp), make_uint4(vr[0], vr[1], vr[2], vr[3]));
+            st_stream_u32x4(reinterpret_cast<uint4*>(out_r + gp) + 1, make_uint4(vr[4], vr[5], vr[6], vr[7]));
+        } else {
+#pragma unroll
+            for (int q = 0; q < J_OPT; q++) {
+                const unsigned long long pq = gp + q;
+                if (pq >= p0 && pq < p1) {
+                    out_l[pq] = vl[q];
+                    out_r[pq] = vr[q];
+                }
+            }
+        }
+    }
+}
+
+__global__ void __launch_bounds__(JB)
+join_fused_kernel(JoinSide L, JoinSide R, const int32_t* __restrict__ part, int64_t n_tiles,
+                  unsigned long long* __restrict__ status, uint32_t* __restrict__ ticket, int32_t* __restrict__ out_l,
+                  int32_t* __restrict__ out_r, int64_t capacity, unsigned long long* __restrict__ totals /* [0] pairs */,
+                  uint32_t* __restrict__ big_count, uint32_t* __restrict__ big_tile, unsigned long long* __restrict__ big_off,
+                  int* __restrict__ err_flag) {
+    __shared__ TileSmem sm;
+    if (threadIdx.x == 0) {
+        sm.tile = atomicAdd(ticket, 1u);
+        cuda::ptx::mbarrier_init(reinterpret_cast<uint64_t*>(&sm.bar[0]), 1);
+        cuda::ptx::mbarrier_init(reinterpret_cast<uint64_t*>(&sm.bar[1]), 1);
+        cuda::ptx::fence_mbarrier_init(cuda::ptx::sem_release, cuda::ptx::scope_cluster);
+    }
+    __syncthreads();
+    const int64_t t = sm.tile;
+    const TileGeom g = tile_geom(part, t, L.n, R.n);
+    if (threadIdx.x == 0) tile_stage(sm, g, L, R);
+    bar_wait(&sm.bar[0], 0);
+    uint32_t code[J_IPT], cnt[J_IPT];
+    tile_runs(sm, g, L, R, code, cnt);
+    const unsigned long long tot = tile_offsets(sm, code, cnt);
+    if (threadIdx.x == 0) {
+        // publish the tile's count, then sum the counts of the tiles before it (decoupled look-back)
+        volatile unsigned long long* st = status;
+        unsigned long long prefix = 0;
+        if (t == 0) {
+            st[0] = JF_FLAG_INCL | tot;
+        } else {
+            st[t] = JF_FLAG_AGG | tot;
+            int64_t k = t - 1;
+            uint32_t spins = 0;
+            while (true) {
+                const unsigned long long s = st[k];
+                const unsigned long long flag = s & ~JF_VALUE_MASK;
+                if (flag == 0) {
+                    if (++spins > JF_SPIN_LIMIT) { *err_flag = 1; break; }
+                    __nanosleep(20);
+                    continue;
+                }
+                prefix += s & JF_VALUE_MASK;
+                if (flag == JF_FLAG_INCL) break;
+                k--;
+            }
+            st[t] = JF_FLAG_INCL | (prefix + tot);
+        }
+        sm.tile_off = prefix;
+        if (t == n_tiles - 1) totals[0] = prefix + tot;
+        if (tot > (unsigned long long)J_BIG) {   // shared among many CTAs by join_emit_big_kernel
+            const uint32_t slot = atomicAdd(big_count, 1u);
+            big_tile[slot] = (uint32_t)t;
+            big_off[slot] = prefix;
+        }
+    }
+    __syncthreads();   // sm.off / sm.code / sm.tile_off are visible
+    const unsigned long long off_t = sm.tile_off;
+    if (tot == 0 || tot > (unsigned long long)J_BIG || off_t + tot > (unsigned long long)capacity) return;
+    bar_wait(&sm.bar[1], 0);
+    const bool vec_ok = ((reinterpret_cast<uintptr_t>(out_l) | reinterpret_cast<uintptr_t>(out_r)) & 15) == 0;
+    tile_emit(sm, g, L, R, off_t, 0, tot, out_l, out_r, vec_ok);
+}
+
+// Tiles with more than J_BIG pairs: every CTA recomputes the tile and emits its share of J_PART-pair slices.
+__global__ void __launch_bounds__(JB)
+join_emit_big_kernel(JoinSide L, JoinSide R, const int32_t* __restrict__ part, const uint32_t* __restrict__ big_count,
+                     const uint32_t* __restrict__ big_tile, const unsigned long long* __restrict__ big_off,
+                     int32_t* __restrict__ out_l, int32_t* __restrict__ out_r, int64_t capacity) {
+    __shared__ TileSmem sm;
+    const uint32_t n_big = *big_count;
+    if (n_big == 0) return;
+    if (threadIdx.x == 0) {
+        cuda::ptx::mbarrier_init(reinterpret_cast<uint64_t*>(&sm.bar[0]), 1);
+        cuda::ptx::mbarrier_init(reinterpret_cast<uint64_t*>(&sm.bar[1]), 1);
+        cuda::ptx::fence_mbarrier_init(cuda::ptx::sem_release, cuda::ptx::scope_cluster);
+    }
+    __syncthreads();
+    const bool vec_ok = ((reinterpret_cast<uintptr_t>(out_l) | reinterpret_cast<uintptr_t>(out_r)) & 15) == 0;
+    uint32_t parity = 0;
+    for (uint32_t bi = 0; bi < n_big; bi++) {
+        const int64_t t = big_tile[bi];
+        const unsigned long long off_t = big_off[bi];
+        const TileGeom g = tile_geom(part, t, L.n, R.n);
+        if (threadIdx.x == 0) tile_stage(sm, g, L, R);
+        bar_wait(&sm.bar[0], parity);
+        uint32_t code[J_IPT], cnt[J_IPT];
+        tile_runs(sm, g, L, R, code, cnt);
+        const unsigned long long tot = tile_offsets(sm, code, cnt);
+        __syncthreads();
+        bar_wait(&sm.bar[1], parity);
+        parity ^= 1;
+        if (off_t + tot <= (unsigned long long)capacity) {
+            const unsigned long long n_parts = (tot + J_PART - 1) / J_PART;
+            for (unsigned long long p = blockIdx.x; p < n_parts; p += gridDim.x)
+                tile_emit(sm, g, L, R, off_t, p * J_PART, min((p + 1) * (unsigned long long)J_PART, tot), out_l, out_r, vec_ok);
+        }
+        __syncthreads();   // everyone is done with the staged tile before the next one overwrites it
+    }
+}
+
 // ---- general path (degenerate rows present) --------------------------------------------------------
 __device__ __forceinline__ void general_candidates(uint32_t lgs, uint32_t lge, const uint32_t* __restrict__ rgs,
                                                    const uint32_t* __restrict__ pmax, int64_t nr, int64_t& lo, int64_t& hi) {
@@ -598,13 +875,57 @@ extern "C" int giqlb_intersects_join(giqlb_ctx* ctx, giqlb_index* L, giqlb_index
     if (!ctx || !L || !R || capacity < 0 || (capacity > 0 && (!out_l || !out_r)))
         return giqlb_fail(ctx, GIQLB_ERR_INVALID, "intersects_join: bad argument");
     begin_call(ctx);
-    giqlb_joinplan* p = nullptr;
-    GIQLB_TRY(plan_enqueue(ctx, L, R, &p));
-    // the emit kernel reads the total on the device and writes nothing when it exceeds `capacity`
-    int st = capacity > 0 ? emit_enqueue(ctx, p, out_l, out_r, capacity) : GIQLB_OK;
-    if (st == GIQLB_OK) st = fetch_scalars_checked(ctx, ctx->d_scalars, 1);
-    int64_t total = st == GIQLB_OK ? ctx->h_scalars[0] : -1;
-    giqlb_joinplan_free(ctx, p);
+    if (L->layout != R->layout) return giqlb_fail(ctx, GIQLB_ERR_INVALID, "intersects: indexes were built on different layouts");
+    if (L->grouped_by_strand || R->grouped_by_strand)
+        return giqlb_fail(ctx, GIQLB_ERR_INVALID, "intersects: strand-grouped indexes are not accepted");
+    GIQLB_TRY(giqlb_index_resolve(ctx, L, R));
+    int64_t total = 0;
+    int st = GIQLB_OK;
+    if (L->n_degenerate + R->n_degenerate > 0 || L->n == 0 || R->n == 0) {
+        // degenerate rows: two-pass general path (the emit kernel writes nothing when the total exceeds `capacity`)
+        giqlb_joinplan* p = nullptr;
+        GIQLB_TRY(plan_enqueue(ctx, L, R, &p));
+        st = capacity > 0 ? emit_enqueue(ctx, p, out_l, out_r, capacity) : GIQLB_OK;
+        if (st == GIQLB_OK) st = fetch_scalars_checked(ctx, ctx->d_scalars, 1);
+        total = st == GIQLB_OK ? ctx->h_scalars[0] : -1;
+        giqlb_joinplan_free(ctx, p);
+    } else {
+        const int64_t n_tiles = ceil_div(L->n + R->n, JT);
+        int32_t* part = nullptr;
+        unsigned long long* status = nullptr;   // [n_tiles] look-back words | [n_tiles] big offsets | ticket, big count | [n_tiles] big tiles
+        unsigned long long* totals = reinterpret_cast<unsigned long long*>(ctx->d_scalars);
+        st = dev_alloc(ctx, &part, (size_t)n_tiles + 1);
+        if (st == GIQLB_OK) st = dev_alloc(ctx, &status, (size_t)3 * n_tiles + 2);
+        if (st == GIQLB_OK) {
+            unsigned long long* big_off = status + n_tiles;
+            uint32_t* ticket = reinterpret_cast<uint32_t*>(status + 2 * n_tiles);
+            uint32_t* big_count = ticket + 1;
+            uint32_t* big_tile = reinterpret_cast<uint32_t*>(status + 2 * n_tiles + 1);
+            cudaMemsetAsync(status, 0, ((size_t)n_tiles) * 8, ctx->stream);
+            cudaMemsetAsync(ticket, 0, 8, ctx->stream);
+            cudaMemsetAsync(totals, 0, 8, ctx->stream);
+            {
+                PhaseSpan ps(ctx, GIQLB_PH_JOIN_COUNT);
+                join_partition_kernel<<<(unsigned)ceil_div(n_tiles + 1, 256), 256, 0, ctx->stream>>>(L->gs, L->n, R->gs, R->n, n_tiles, part);
+                ctx->launches_this_call++;
+                ctx->stats.kernels_total++;
+            }
+            {
+                PhaseSpan ps(ctx, GIQLB_PH_JOIN_EMIT);
+                join_fused_kernel<<<(unsigned)n_tiles, JB, 0, ctx->stream>>>(side_of(L), side_of(R), part, n_tiles, status, ticket, out_l, out_r,
+                                                                             capacity, totals, big_count, big_tile, big_off, ctx->d_err);
+                join_emit_big_kernel<<<ctx->sm_count * 2, JB, 0, ctx->stream>>>(side_of(L), side_of(R), part, big_count, big_tile, big_off,
+                                                                                out_l, out_r, capacity);
+                ctx->launches_this_call += 2;
+                ctx->stats.kernels_total += 2;
+            }
+            if (cudaGetLastError() != cudaSuccess) st = giqlb_fail(ctx, GIQLB_ERR_CUDA, "intersects_join: launch failed");
+        }
+        if (st == GIQLB_OK) st = fetch_scalars_checked(ctx, totals, 1);
+        total = st == GIQLB_OK ? ctx->h_scalars[0] : -1;
+        dev_free(ctx, part);
+        dev_free(ctx, status);
+    }
     if (st != GIQLB_OK) return st;
     if (total_host) *total_host = total;
     join_stats(ctx, L, R, total);

@@ -286,6 +286,7 @@ class Engine:
         if st != _cabi.OK:
             raise EngineError(st, "giqlb_create failed")
         self._strand_codes: dict[Any, int] = {"+": 0, "-": 1, ".": 2, "?": 3}
+        self._pair_capacity = 0   # running estimate of the pair-buffer size for the single-pass join
 
     # ---- plumbing ---------------------------------------------------------------------------------
     def _check(self, status: int):
@@ -469,31 +470,55 @@ class Engine:
         ib = ia if b is a else _Index(self, lay, b)
         return lay, ia, ib
 
-    def intersects(self, left: DeviceTable, right: DeviceTable) -> PairResult:
+    def intersects(self, left: DeviceTable, right: DeviceTable, mode: str = "auto") -> PairResult:
         """Column-to-column INTERSECTS inner join -> (left_row, right_row) pairs.
 
         reference: src/giql/expanders/intersects.py:149-154 (predicate) evaluated per chromosome by
-        src/giql/expanders/intersects_duckdb.py:1283-1299; bag semantics, unordered.
+        src/giql/expanders/intersects_duckdb.py:1283-1299; bag semantics, unordered.  ``mode``: see
+        :meth:`_join_indexes`.
         """
         lay, il, ir = self._pair_indexes(left, right)
         try:
-            return self._join_indexes(il, ir)
+            return self._join_indexes(il, ir, mode)
         finally:
             il.free()
             ir.free()
             lay.free()
 
-    def _join_indexes(self, il: _Index, ir: _Index) -> PairResult:
-        """count -> scan -> emit over two indexes built on one layout."""
-        plan, total = ctypes.c_void_p(), ctypes.c_int64()
-        self._check(self.lib.giqlb_intersects_plan(self.ctx, il.h, ir.h, ctypes.byref(plan), ctypes.byref(total)))
-        try:
-            out_l = self._empty(total.value, torch.int32)
-            out_r = self._empty(total.value, torch.int32)
-            self._check(self.lib.giqlb_intersects_emit(self.ctx, plan, _ptr(out_l), _ptr(out_r)))
-        finally:
-            self.lib.giqlb_joinplan_free(self.ctx, plan)
-        return PairResult(out_l, out_r)
+    def _join_indexes(self, il: _Index, ir: _Index, mode: str = "auto") -> PairResult:
+        """INTERSECTS over two indexes built on one layout.
+
+        ``two_pass``: giqlb_intersects_plan (count + scan, exact size) then giqlb_intersects_emit.
+        ``single_pass``: giqlb_intersects_join into a buffer sized from the engine's running capacity estimate — one
+        fused kernel counts, offsets and emits; when the estimate is too small the library reports the exact size
+        and the join is repeated once into an exact buffer.  ``auto`` = two_pass until an estimate exists.
+        """
+        if mode not in ("auto", "two_pass", "single_pass"):
+            raise ValueError(f"unknown join mode {mode!r}")
+        if mode == "two_pass" or (mode == "auto" and self._pair_capacity == 0):
+            plan, total = ctypes.c_void_p(), ctypes.c_int64()
+            self._check(self.lib.giqlb_intersects_plan(self.ctx, il.h, ir.h, ctypes.byref(plan), ctypes.byref(total)))
+            try:
+                out_l = self._empty(total.value, torch.int32)
+                out_r = self._empty(total.value, torch.int32)
+                self._check(self.lib.giqlb_intersects_emit(self.ctx, plan, _ptr(out_l), _ptr(out_r)))
+            finally:
+                self.lib.giqlb_joinplan_free(self.ctx, plan)
+            self._pair_capacity = max(self._pair_capacity, int(total.value * 1.25) + 1024)
+            return PairResult(out_l, out_r)
+        cap = max(self._pair_capacity, 1024)
+        total = ctypes.c_int64()
+        for _ in range(2):
+            out_l = self._empty(cap, torch.int32)
+            out_r = self._empty(cap, torch.int32)
+            st = self.lib.giqlb_intersects_join(self.ctx, il.h, ir.h, _ptr(out_l), _ptr(out_r), cap, ctypes.byref(total))
+            if st == _cabi.OK:
+                return PairResult(out_l[: total.value], out_r[: total.value])
+            if st != _cabi.ERR_CAPACITY:
+                self._check(st)
+            cap = total.value                      # exact size reported by the library
+            self._pair_capacity = int(cap * 1.25) + 1024
+        raise EngineError(_cabi.ERR_INTERNAL, "intersects_join: capacity retry did not converge")
 
     # ---- genome-range sharding (SURVEY.md §8(e); orchestration in giql_b200/sharding.py) -------------
     def shard_cuts(self, lay: _Layout, left: DeviceTable, world: int) -> tuple[list[int], int]:

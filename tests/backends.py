@@ -70,8 +70,9 @@ class EngineBackend:
 
     name = "b200"
 
-    def __init__(self, engine):
+    def __init__(self, engine, join_mode="auto"):
         self.e = engine
+        self.join_mode = join_mode
 
     def _table(self, T, cfg):
         cfg = cfg or Table("t")
@@ -81,7 +82,7 @@ class EngineBackend:
         return self.e.table(data, cfg)
 
     def pairs(self, L, R, lcfg=None, rcfg=None):
-        res = self.e.intersects(self._table(L, lcfg), self._table(R, rcfg))
+        res = self.e.intersects(self._table(L, lcfg), self._table(R, rcfg), mode=self.join_mode)
         l, r = res.to_host()
         return sorted(zip(l.tolist(), r.tolist()))
 

@@ -406,3 +406,37 @@ def test_dict_encode_matches_host_sort(n_names, max_len, engine):
     dn = np.array(d.names, dtype=object)
     assert list(dn[ta.codes.cpu().numpy()]) == rows_a and list(dn[tb.codes.cpu().numpy()]) == rows_b
     assert ta.dictionary is tb.dictionary
+
+
+# ---- both join paths explicitly --------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("mode", ["two_pass", "single_pass"])
+def test_join_modes_vs_oracle(mode, engine, c_oracle):
+    """two_pass = plan (count + scan) then emit; single_pass = the fused count/offset/emit kernel, including the
+    capacity-overflow retry (the estimate is reset so the first attempt is too small) and tiles delegated to the
+    big-tile kernel."""
+    from giql_b200 import synth
+
+    rng = np.random.default_rng(5)
+    ob = OracleBackend()
+    for seed in range(3):
+        L, R = _rand(rng, 900 + 300 * seed, span=5000), _rand(rng, 700 + 200 * seed, span=5000)
+        assert EngineBackend(engine, mode).pairs(L, R) == ob.pairs(L, R)
+    L, R = _rand(rng, 300, min_len=0, max_len=6, span=150), _rand(rng, 300, min_len=0, max_len=6, span=150)   # degenerate rows
+    assert EngineBackend(engine, mode).pairs(L, R) == ob.pairs(L, R)
+    A, B = synth.peaks(300_000, 51), synth.genes(80_000, 52)      # long gene-like intervals: runs leave the staged window
+    ta = engine.table_from_codes(A["code"], A["start"], A["end"], A["names"])
+    tb = engine.table_from_codes(B["code"], B["start"], B["end"], ta.dictionary)
+    exp = c_oracle.intersects_pairs(A["code"], A["start"], A["end"], B["code"], B["start"], B["end"], len(A["names"]))
+    exp = (exp[:, 0] << 32) | exp[:, 1]
+    engine._pair_capacity = 1                                         # force the overflow + retry path
+    assert np.array_equal(engine.intersects(ta, tb, mode=mode).sorted_packed(), exp)
+    assert np.array_equal(engine.intersects(tb, ta, mode=mode).sorted_packed(), np.sort(((exp & 0xFFFFFFFF) << 32) | (exp >> 32)))
+    # a giant interval: one tile with far more than J_BIG pairs
+    n = 120_000
+    rs = np.sort(rng.integers(0, 5_000_000, size=n)).astype(np.int32)
+    T = {"code": np.zeros(n, np.int32), "start": rs, "end": (rs + 50).astype(np.int32)}
+    G = {"code": np.zeros(2, np.int32), "start": np.array([0, 10], np.int32), "end": np.array([5_000_100, 2_500_000], np.int32)}
+    tg = engine.table_from_codes(G["code"], G["start"], G["end"], ["chr1"])
+    tt = engine.table_from_codes(T["code"], T["start"], T["end"], tg.dictionary)
+    exp = c_oracle.intersects_pairs(G["code"], G["start"], G["end"], T["code"], T["start"], T["end"], 1)
+    assert np.array_equal(engine.intersects(tg, tt, mode=mode).sorted_packed(), (exp[:, 0] << 32) | exp[:, 1])
