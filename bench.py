@@ -293,6 +293,7 @@ def run_b200(args):
     barrier()
     step_ms = [s.elapsed_time(e) for s, e in zip(starts, stops)]
     launches = eng.kernels_total() - k0
+    big_tiles = eng.stats().get("big_tiles")
     prof = eng.profile_read()
     eng.profile(False)
     t_dev = torch.tensor([sum(step_ms)], dtype=torch.float64, device=eng.device)
@@ -375,7 +376,7 @@ def run_b200(args):
         "ms_per_step": ms_per_step, "ms_per_step_min_median_max": [round(min(step_ms), 4), round(float(np.median(step_ms)), 4), round(max(step_ms), 4)],
         "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "int32",
         "data": "synthetic",
-        "config": {"workload": workload_name(args.rows), "pairs": pairs, "rows_left": n_l, "rows_right": n_r,
+        "config": {"workload": workload_name(args.rows), "pairs": pairs, "rows_left": n_l, "rows_right": n_r, "join_tiles_delegated_to_big_kernel": big_tiles,
                    "sharding": "single GPU" if world == 1 else f"{world} contiguous genome ranges balanced on left interval count; "
                                "straddling right intervals replicated; owner = rank of the left start",
                    "l2": "inputs (340 MB) exceed the 126 MB L2 and a 512 MB buffer is rewritten between timed steps",

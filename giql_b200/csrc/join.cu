@@ -373,22 +373,33 @@ join_emit_kernel(JoinSide L, JoinSide R, const int32_t* __restrict__ part, int64
 // through HBM, and the capacity check is per tile (a tile that would overrun the buffer writes nothing; the
 // grand total tells the host how much room a retry needs).  Tiles whose output exceeds J_BIG pairs only
 // publish their offset and are emitted afterwards by a second kernel that shares each of them among many CTAs.
-constexpr int J_BIG = 32768;
+constexpr int J_BIG = 8192;           // tiles with more pairs are shared among CTAs by join_emit_big_kernel
 constexpr unsigned long long JF_FLAG_AGG = 1ull << 62;
 constexpr unsigned long long JF_FLAG_INCL = 2ull << 62;
 constexpr unsigned long long JF_VALUE_MASK = (1ull << 62) - 1;
 constexpr uint32_t JF_SPIN_LIMIT = 1u << 26;
 
+constexpr int J_STAGE = ((2 * (JW + 8) + 2 * (JT + 8)) / 2) & ~3;   // output pairs staged per window (aliases gs + ge)
+
 struct __align__(16) TileSmem {
     uint32_t gs[2][JW + 8];                  // staged start windows: [0] L, [1] R (16-byte aligned source => up to 3 lead-in rows)
-    uint32_t ge[2][JT + 8];                  // ends of the tile's own rows
+    uint32_t ge[2][JT + 8];                  // ends of the tile's own rows.  gs + ge are dead once the runs are known: the
+                                             // fused kernel reuses them as the output staging window (stage_l / stage_r)
     int32_t rid[2][JW + 8];                  // row ids of the windows
-    unsigned long long off[JT + 1];          // local exclusive output offsets of the tile's items (merge order)
-    uint32_t code[JT];                       // run start | class of every item
     unsigned long long scratch[JB / 32 + 2];
     unsigned long long tile_off;
     unsigned long long bar[2];               // mbarriers: [0] starts + ends, [1] row ids
     uint32_t tile;
+};
+
+struct TileSlots {                           // fused kernel (tiles of <= J_BIG pairs): slot -> item lookup
+    uint16_t off[JT + 2];                    // local exclusive output offsets of the tile's items (merge order), then the total
+    uint16_t code[JT];                       // run start | class of every item
+    uint16_t first_item[J_BIG / J_OPT + 2];  // item that owns the first slot of every J_OPT-slot chunk
+};
+struct TileOffsets {                         // big-tile kernel: per-item offsets for the slot -> item search
+    unsigned long long off[JT + 1];          // local exclusive output offsets of the tile's items (merge order)
+    uint32_t code[JT];                       // run start | class of every item
 };
 
 __device__ __forceinline__ void bar_wait(unsigned long long* bar, uint32_t parity) {
@@ -456,9 +467,15 @@ __device__ __forceinline__ void tile_runs(const TileSmem& sm, const TileGeom& g,
             const uint32_t xge = take_l ? gel[i] : ger[j];   // the row's own end
             const uint32_t* ys = take_l ? gsr : gsl;         // the other table's window
             const int start = take_l ? j : i, wy = take_l ? g.wr : g.wl;
-            int h = start;                                   // run end: a few rows away on average -> linear probe, then binary
-            while (h < wy && h < start + 8 && ys[h] < xge) h++;
-            if (h == start + 8 && h < wy && ys[h] < xge) h = s_lower_bound(ys, h + 1, wy, xge);
+            // run end = first row of the other window whose start is >= the row's end.  Almost every run is a few rows
+            // long: a fixed-trip (divergence-free) binary lifting over the next 32 rows, then the rare long run.
+            int h = start;
+            const int lim = min(start + 32, wy);
+#pragma unroll
+            for (int step = 16; step > 0; step >>= 1)
+                if (h + step <= lim && ys[h + step - 1] < xge) h += step;
+            if (h < lim && ys[h] < xge) h++;
+            if (h == lim && lim < wy && ys[h] < xge) h = s_lower_bound(ys, h + 1, wy, xge);
             int64_t c = h - start;
             if (h == wy) {                                   // the run may continue beyond the staged window
                 const uint32_t* yg = take_l ? R.gs : L.gs;
@@ -474,7 +491,7 @@ __device__ __forceinline__ void tile_runs(const TileSmem& sm, const TileGeom& g,
 }
 
 // Block scan of the run lengths into sm.off / sm.code; returns the tile's pair count (same value in every thread).
-__device__ __forceinline__ unsigned long long tile_offsets(TileSmem& sm, const uint32_t (&code)[J_IPT], const uint32_t (&cnt)[J_IPT]) {
+__device__ __forceinline__ unsigned long long tile_offsets(TileSmem& sm, TileOffsets& so, const uint32_t (&code)[J_IPT], const uint32_t (&cnt)[J_IPT]) {
     unsigned long long sum = 0;
 #pragma unroll
     for (int k = 0; k < J_IPT; k++) sum += cnt[k];
@@ -482,17 +499,17 @@ __device__ __forceinline__ unsigned long long tile_offsets(TileSmem& sm, const u
     unsigned long long ex = block_excl_scan_add<unsigned long long>(sum, sm.scratch, &tot);
 #pragma unroll
     for (int k = 0; k < J_IPT; k++) {
-        sm.off[threadIdx.x * J_IPT + k] = ex;
-        sm.code[threadIdx.x * J_IPT + k] = code[k];
+        so.off[threadIdx.x * J_IPT + k] = ex;
+        so.code[threadIdx.x * J_IPT + k] = code[k];
         ex += cnt[k];
     }
-    if (threadIdx.x == 0) sm.off[JT] = tot;
+    if (threadIdx.x == 0) so.off[JT] = tot;
     return tot;
 }
 
 // Emits the tile's local output slots [a, b) at global positions off_t + slot; every thread writes J_OPT consecutive
 // pairs aligned to J_OPT (16-byte vector stores).
-__device__ __forceinline__ void tile_emit(const TileSmem& sm, const TileGeom& g, const JoinSide& L, const JoinSide& R,
+__device__ __forceinline__ void tile_emit(const TileSmem& sm, const TileOffsets& so, const TileGeom& g, const JoinSide& L, const JoinSide& R,
                                           unsigned long long off_t, unsigned long long a, unsigned long long b,
                                           int32_t* __restrict__ out_l, int32_t* __restrict__ out_r, bool vec_ok) {
     const int32_t* lrid = sm.rid[0] + (g.x0 & 3);
@@ -502,7 +519,7 @@ __device__ __forceinline__ void tile_emit(const TileSmem& sm, const TileGeom& g,
     for (unsigned long long gp = g_first + (unsigned long long)threadIdx.x * J_OPT; gp < g_b; gp += (unsigned long long)JB * J_OPT) {
         const unsigned long long p0 = gp > g_a ? gp : g_a, p1 = min(gp + J_OPT, g_b);
         if (p0 >= p1) continue;
-        int item = s_upper_bound_u64(sm.off, JT + 1, p0 - off_t) - 1;    // last item whose offset is <= the first slot
+        int item = s_upper_bound_u64(so.off, JT + 1, p0 - off_t) - 1;    // last item whose offset is <= the first slot
         int32_t vl[J_OPT], vr[J_OPT];
 #pragma unroll
         for (int q = 0; q < J_OPT; q++) {
@@ -511,10 +528,10 @@ __device__ __forceinline__ void tile_emit(const TileSmem& sm, const TileGeom& g,
             vr[q] = 0;
             if (pq >= p0 && pq < p1) {
                 const unsigned long long sl = pq - off_t;
-                while (sm.off[item + 1] <= sl) item++;              // skip items with empty runs
-                const uint32_t cd = sm.code[item];
+                while (so.off[item + 1] <= sl) item++;              // skip items with empty runs
+                const uint32_t cd = so.code[item];
                 const int start = (int)(cd & 0x7FFFu);
-                const int64_t w = (int64_t)start + (int64_t)(sl - sm.off[item]);   // offset into the other table's window
+                const int64_t w = (int64_t)start + (int64_t)(sl - so.off[item]);   // offset into the other table's window
                 if (!(cd & J_CLASS_B)) {                            // item is L row (item - start); its run lies in R
                     vl[q] = lrid[item - start];
                     vr[q] = w < g.wr ? rrid[w] : __ldg(R.rid + g.y0 + w);
@@ -542,13 +559,96 @@ __device__ __forceinline__ void tile_emit(const TileSmem& sm, const TileGeom& g,
     }
 }
 
+// One row id of the "other" table's window (shared memory, or global memory beyond the staged extension)
+__device__ __forceinline__ int32_t other_rid(const int32_t* win, int w_len, const int32_t* __restrict__ glob, int64_t base, int idx) {
+    return idx < w_len ? win[idx] : __ldg(glob + base + idx);
+}
+
+// Item table of the tile: offsets, codes, and for every chunk of J_OPT output slots the item owning its first slot
+// (written by that item itself, so the expansion below needs no search).
+__device__ __forceinline__ void tile_slot_table(TileSlots& ts, const uint32_t (&code)[J_IPT], const uint32_t (&cnt)[J_IPT], uint32_t ex,
+                                                uint32_t tot) {
+    uint32_t o = ex;
+#pragma unroll
+    for (int k = 0; k < J_IPT; k++) {
+        const int item = threadIdx.x * J_IPT + k;
+        ts.off[item] = (uint16_t)o;
+        ts.code[item] = (uint16_t)code[k];
+        for (uint32_t q = (o + J_OPT - 1) / J_OPT; q * J_OPT < o + cnt[k]; q++) ts.first_item[q] = (uint16_t)item;
+        o += cnt[k];
+    }
+    if (threadIdx.x == JB - 1) {
+        ts.off[JT] = (uint16_t)tot;       // tot <= J_BIG < 2^16
+        ts.off[JT + 1] = 0xFFFFu;         // sentinel: the walk below never leaves the table
+    }
+}
+
+// Expands output slots [w0, w0 + n) of the tile into the staging window: a thread owns J_OPT consecutive slots.
+__device__ __forceinline__ void tile_expand(TileSmem& sm, const TileSlots& ts, const TileGeom& g, const JoinSide& L, const JoinSide& R,
+                                            uint32_t w0, uint32_t n) {
+    int32_t* stage_l = reinterpret_cast<int32_t*>(&sm.gs[0][0]);
+    int32_t* stage_r = stage_l + J_STAGE;
+    const int32_t* lrid = sm.rid[0] + (g.x0 & 3);
+    const int32_t* rrid = sm.rid[1] + (g.y0 & 3);
+    for (uint32_t s0 = w0 + threadIdx.x * J_OPT; s0 < w0 + n; s0 += JB * J_OPT) {
+        int item = ts.first_item[s0 / J_OPT];
+#pragma unroll
+        for (int q = 0; q < J_OPT; q++) {
+            const uint32_t sl = s0 + q;
+            if (sl < w0 + n) {
+                while (ts.off[item + 1] <= sl) item++;              // skip finished and empty items
+                const uint32_t cd = ts.code[item];
+                const int start = (int)(cd & 0x7FFFu);
+                const int w = start + (int)(sl - ts.off[item]);     // offset into the other table's window
+                const int own = item - start;
+                int32_t vl, vr;
+                if (!(cd & J_CLASS_B)) {                            // item is an L row; its run lies in R
+                    vl = lrid[own];
+                    vr = w < g.wr ? rrid[w] : __ldg(R.rid + g.y0 + w);
+                } else {                                            // item is an R row; its run lies in L
+                    vr = rrid[own];
+                    vl = w < g.wl ? lrid[w] : __ldg(L.rid + g.x0 + w);
+                }
+                stage_l[sl - w0] = vl;
+                stage_r[sl - w0] = vr;
+            }
+        }
+    }
+}
+
+// staging window -> global memory, 16-byte vector stores on 16-byte aligned global positions
+__device__ __forceinline__ void tile_flush(const TileSmem& sm, unsigned long long g_w0, uint32_t n, int32_t* __restrict__ out_l,
+                                           int32_t* __restrict__ out_r, bool vec_ok) {
+    const int32_t* stage_l = reinterpret_cast<const int32_t*>(&sm.gs[0][0]);
+    const int32_t* stage_r = stage_l + J_STAGE;
+    const unsigned long long g_w1 = g_w0 + n;
+    const unsigned long long first = g_w0 & ~3ull;
+    for (unsigned long long gp = first + (unsigned long long)threadIdx.x * 4; gp < g_w1; gp += (unsigned long long)JB * 4) {
+        if (vec_ok && gp >= g_w0 && gp + 4 <= g_w1) {
+            const uint32_t sidx = (uint32_t)(gp - g_w0);
+            st_stream_u32x4(reinterpret_cast<uint4*>(out_l + gp), make_uint4(stage_l[sidx], stage_l[sidx + 1], stage_l[sidx + 2], stage_l[sidx + 3]));
+            st_stream_u32x4(reinterpret_cast<uint4*>(out_r + gp), make_uint4(stage_r[sidx], stage_r[sidx + 1], stage_r[sidx + 2], stage_r[sidx + 3]));
+        } else {
+#pragma unroll
+            for (int q = 0; q < 4; q++) {
+                const unsigned long long pq = gp + q;
+                if (pq >= g_w0 && pq < g_w1) {
+                    out_l[pq] = stage_l[pq - g_w0];
+                    out_r[pq] = stage_r[pq - g_w0];
+                }
+            }
+        }
+    }
+}
+
 __global__ void __launch_bounds__(JB)
 join_fused_kernel(JoinSide L, JoinSide R, const int32_t* __restrict__ part, int64_t n_tiles,
                   unsigned long long* __restrict__ status, uint32_t* __restrict__ ticket, int32_t* __restrict__ out_l,
                   int32_t* __restrict__ out_r, int64_t capacity, unsigned long long* __restrict__ totals /* [0] pairs */,
                   uint32_t* __restrict__ big_count, uint32_t* __restrict__ big_tile, unsigned long long* __restrict__ big_off,
-                  int* __restrict__ err_flag) {
+                  unsigned long long* __restrict__ big_cnt, int* __restrict__ err_flag) {
     __shared__ TileSmem sm;
+    __shared__ TileSlots ts;
     if (threadIdx.x == 0) {
         sm.tile = atomicAdd(ticket, 1u);
         cuda::ptx::mbarrier_init(reinterpret_cast<uint64_t*>(&sm.bar[0]), 1);
@@ -562,9 +662,14 @@ join_fused_kernel(JoinSide L, JoinSide R, const int32_t* __restrict__ part, int6
     bar_wait(&sm.bar[0], 0);
     uint32_t code[J_IPT], cnt[J_IPT];
     tile_runs(sm, g, L, R, code, cnt);
-    const unsigned long long tot = tile_offsets(sm, code, cnt);
-    if (threadIdx.x == 0) {
-        // publish the tile's count, then sum the counts of the tiles before it (decoupled look-back)
+    unsigned long long sum = 0;
+#pragma unroll
+    for (int k = 0; k < J_IPT; k++) sum += cnt[k];
+    unsigned long long tot;
+    const unsigned long long ex64 = block_excl_scan_add<unsigned long long>(sum, sm.scratch, &tot);   // two barriers: gs / ge are dead now
+    if (threadIdx.x == JB - 1) {
+        // The last thread publishes the tile's count and sums the counts of the tiles before it (decoupled look-back)
+        // while the other warps already expand the tile into shared memory.
         volatile unsigned long long* st = status;
         unsigned long long prefix = 0;
         if (t == 0) {
@@ -593,22 +698,36 @@ join_fused_kernel(JoinSide L, JoinSide R, const int32_t* __restrict__ part, int6
             const uint32_t slot = atomicAdd(big_count, 1u);
             big_tile[slot] = (uint32_t)t;
             big_off[slot] = prefix;
+            big_cnt[slot] = tot;
         }
     }
-    __syncthreads();   // sm.off / sm.code / sm.tile_off are visible
-    const unsigned long long off_t = sm.tile_off;
-    if (tot == 0 || tot > (unsigned long long)J_BIG || off_t + tot > (unsigned long long)capacity) return;
-    bar_wait(&sm.bar[1], 0);
+    bar_wait(&sm.bar[1], 0);   // also before leaving: a CTA must not exit with bulk copies into its shared memory in flight
+    if (tot == 0 || tot > (unsigned long long)J_BIG) return;
     const bool vec_ok = ((reinterpret_cast<uintptr_t>(out_l) | reinterpret_cast<uintptr_t>(out_r)) & 15) == 0;
-    tile_emit(sm, g, L, R, off_t, 0, tot, out_l, out_r, vec_ok);
+    const uint32_t tot32 = (uint32_t)tot;
+    tile_slot_table(ts, code, cnt, (uint32_t)ex64, tot32);
+    __syncthreads();                           // item table complete
+    static_assert(J_STAGE % J_OPT == 0, "windows start on chunk boundaries");
+    for (uint32_t w0 = 0; w0 < tot32; w0 += J_STAGE) {
+        const uint32_t n = min((uint32_t)J_STAGE, tot32 - w0);
+        tile_expand(sm, ts, g, L, R, w0, n);
+        __syncthreads();                       // staging window complete (and, first time round, sm.tile_off published)
+        const unsigned long long off_t = sm.tile_off;
+        if (off_t + tot > (unsigned long long)capacity) return;   // the caller's buffer is too small: write nothing
+        tile_flush(sm, off_t + w0, n, out_l, out_r, vec_ok);
+        if (w0 + J_STAGE < tot32) __syncthreads();   // the next window overwrites the staging area
+    }
 }
 
-// Tiles with more than J_BIG pairs: every CTA recomputes the tile and emits its share of J_PART-pair slices.
+// Tiles with more than J_BIG pairs.  Their output is cut into J_PART-pair units that are dealt round-robin to the
+// CTAs; a CTA recomputes only the tiles it owns a unit of.
 __global__ void __launch_bounds__(JB)
 join_emit_big_kernel(JoinSide L, JoinSide R, const int32_t* __restrict__ part, const uint32_t* __restrict__ big_count,
                      const uint32_t* __restrict__ big_tile, const unsigned long long* __restrict__ big_off,
-                     int32_t* __restrict__ out_l, int32_t* __restrict__ out_r, int64_t capacity) {
+                     const unsigned long long* __restrict__ big_cnt, int32_t* __restrict__ out_l, int32_t* __restrict__ out_r,
+                     int64_t capacity) {
     __shared__ TileSmem sm;
+    __shared__ TileOffsets so;
     const uint32_t n_big = *big_count;
     if (n_big == 0) return;
     if (threadIdx.x == 0) {
@@ -619,24 +738,30 @@ join_emit_big_kernel(JoinSide L, JoinSide R, const int32_t* __restrict__ part, c
     __syncthreads();
     const bool vec_ok = ((reinterpret_cast<uintptr_t>(out_l) | reinterpret_cast<uintptr_t>(out_r)) & 15) == 0;
     uint32_t parity = 0;
+    unsigned long long unit_base = 0;
     for (uint32_t bi = 0; bi < n_big; bi++) {
-        const int64_t t = big_tile[bi];
+        const unsigned long long tot = big_cnt[bi], n_parts = (tot + J_PART - 1) / J_PART;
+        // my first unit at or after unit_base
+        const unsigned long long first = unit_base + ((unsigned long long)blockIdx.x + gridDim.x - unit_base % gridDim.x) % gridDim.x;
         const unsigned long long off_t = big_off[bi];
-        const TileGeom g = tile_geom(part, t, L.n, R.n);
-        if (threadIdx.x == 0) tile_stage(sm, g, L, R);
-        bar_wait(&sm.bar[0], parity);
-        uint32_t code[J_IPT], cnt[J_IPT];
-        tile_runs(sm, g, L, R, code, cnt);
-        const unsigned long long tot = tile_offsets(sm, code, cnt);
-        __syncthreads();
-        bar_wait(&sm.bar[1], parity);
-        parity ^= 1;
-        if (off_t + tot <= (unsigned long long)capacity) {
-            const unsigned long long n_parts = (tot + J_PART - 1) / J_PART;
-            for (unsigned long long p = blockIdx.x; p < n_parts; p += gridDim.x)
-                tile_emit(sm, g, L, R, off_t, p * J_PART, min((p + 1) * (unsigned long long)J_PART, tot), out_l, out_r, vec_ok);
+        if (first < unit_base + n_parts && off_t + tot <= (unsigned long long)capacity) {
+            const int64_t t = big_tile[bi];
+            const TileGeom g = tile_geom(part, t, L.n, R.n);
+            if (threadIdx.x == 0) tile_stage(sm, g, L, R);
+            bar_wait(&sm.bar[0], parity);
+            uint32_t code[J_IPT], cnt[J_IPT];
+            tile_runs(sm, g, L, R, code, cnt);
+            tile_offsets(sm, so, code, cnt);
+            __syncthreads();
+            bar_wait(&sm.bar[1], parity);
+            parity ^= 1;
+            for (unsigned long long u = first; u < unit_base + n_parts; u += gridDim.x) {
+                const unsigned long long p = u - unit_base;
+                tile_emit(sm, so, g, L, R, off_t, p * J_PART, min((p + 1) * (unsigned long long)J_PART, tot), out_l, out_r, vec_ok);
+            }
+            __syncthreads();   // everyone is done with the staged tile before the next one overwrites it
         }
-        __syncthreads();   // everyone is done with the staged tile before the next one overwrites it
+        unit_base += n_parts;
     }
 }
 
@@ -895,12 +1020,13 @@ extern "C" int giqlb_intersects_join(giqlb_ctx* ctx, giqlb_index* L, giqlb_index
         unsigned long long* status = nullptr;   // [n_tiles] look-back words | [n_tiles] big offsets | ticket, big count | [n_tiles] big tiles
         unsigned long long* totals = reinterpret_cast<unsigned long long*>(ctx->d_scalars);
         st = dev_alloc(ctx, &part, (size_t)n_tiles + 1);
-        if (st == GIQLB_OK) st = dev_alloc(ctx, &status, (size_t)3 * n_tiles + 2);
+        if (st == GIQLB_OK) st = dev_alloc(ctx, &status, (size_t)4 * n_tiles + 2);
         if (st == GIQLB_OK) {
             unsigned long long* big_off = status + n_tiles;
-            uint32_t* ticket = reinterpret_cast<uint32_t*>(status + 2 * n_tiles);
+            unsigned long long* big_cnt = status + 2 * n_tiles;
+            uint32_t* ticket = reinterpret_cast<uint32_t*>(status + 3 * n_tiles);
             uint32_t* big_count = ticket + 1;
-            uint32_t* big_tile = reinterpret_cast<uint32_t*>(status + 2 * n_tiles + 1);
+            uint32_t* big_tile = reinterpret_cast<uint32_t*>(status + 3 * n_tiles + 1);
             cudaMemsetAsync(status, 0, ((size_t)n_tiles) * 8, ctx->stream);
             cudaMemsetAsync(ticket, 0, 8, ctx->stream);
             cudaMemsetAsync(totals, 0, 8, ctx->stream);
@@ -913,9 +1039,10 @@ extern "C" int giqlb_intersects_join(giqlb_ctx* ctx, giqlb_index* L, giqlb_index
             {
                 PhaseSpan ps(ctx, GIQLB_PH_JOIN_EMIT);
                 join_fused_kernel<<<(unsigned)n_tiles, JB, 0, ctx->stream>>>(side_of(L), side_of(R), part, n_tiles, status, ticket, out_l, out_r,
-                                                                             capacity, totals, big_count, big_tile, big_off, ctx->d_err);
+                                                                             capacity, totals, big_count, big_tile, big_off, big_cnt, ctx->d_err);
                 join_emit_big_kernel<<<ctx->sm_count * 2, JB, 0, ctx->stream>>>(side_of(L), side_of(R), part, big_count, big_tile, big_off,
-                                                                                out_l, out_r, capacity);
+                                                                                big_cnt, out_l, out_r, capacity);
+                cudaMemcpyAsync(ctx->h_scalars + 8, big_count, 4, cudaMemcpyDeviceToHost, ctx->stream);
                 ctx->launches_this_call += 2;
                 ctx->stats.kernels_total += 2;
             }
@@ -923,6 +1050,7 @@ extern "C" int giqlb_intersects_join(giqlb_ctx* ctx, giqlb_index* L, giqlb_index
         }
         if (st == GIQLB_OK) st = fetch_scalars_checked(ctx, totals, 1);
         total = st == GIQLB_OK ? ctx->h_scalars[0] : -1;
+        ctx->stats.reserved = (int32_t)(ctx->h_scalars[8] & 0xffffffff);   // tiles delegated to the big-tile kernel
         dev_free(ctx, part);
         dev_free(ctx, status);
     }

@@ -314,7 +314,7 @@ class Engine:
         s = _cabi.Stats()
         self._check(self.lib.giqlb_stats(self.ctx, ctypes.byref(s)))
         return {"rows_in": (s.rows_in[0], s.rows_in[1]), "rows_out": s.rows_out, "algorithmic_bytes": s.algorithmic_bytes,
-                "kernels_launched": s.kernels_launched, "kernels_total": s.kernels_total}
+                "kernels_launched": s.kernels_launched, "kernels_total": s.kernels_total, "big_tiles": s.reserved}
 
     def profile(self, on: bool = True):
         """Record CUDA events around every kernel group (see giqlb_profile_enable)."""
