@@ -18,6 +18,9 @@ constexpr int RS_WARPS = RS_THREADS / 32;
 #define GIQLB_RS_IPT 16
 #endif
 constexpr int RS_IPT = GIQLB_RS_IPT;
+#ifndef GIQLB_RS_USE_MATCH
+#define GIQLB_RS_USE_MATCH 0
+#endif
 constexpr int RS_TILE = RS_THREADS * RS_IPT;   // 4096 keys per tile
 constexpr int RS_RADIX = 256;
 constexpr int RS_MAX_PASSES = 4;
@@ -101,7 +104,23 @@ rs_onesweep_kernel(const uint32_t* __restrict__ keys_in, const uint32_t* __restr
     // rank within the warp, stable in (item, lane) order.  All match instructions are issued first (they are
     // independent), so only the shared-memory counter update remains on the serial chain.
 #pragma unroll
-    for (int i = 0; i < RS_IPT; i++) rank[i] = __match_any_sync(FULL_MASK, (key[i] >> shift) & 255u);
+    for (int i = 0; i < RS_IPT; i++) {
+#if GIQLB_RS_USE_MATCH
+        rank[i] = __match_any_sync(FULL_MASK, (key[i] >> shift) & 255u);
+#else
+        // lanes holding the same digit, from eight ballots: the hardware MATCH instruction has a long latency and
+        // a low issue rate, the votes pipeline freely
+        const uint32_t d = key[i] >> shift;
+        uint32_t peers = FULL_MASK;
+#pragma unroll
+        for (int b = 0; b < 8; b++) {
+            const bool bit = (d >> b) & 1u;
+            const uint32_t m = __ballot_sync(FULL_MASK, bit);
+            peers &= bit ? m : ~m;
+        }
+        rank[i] = peers;
+#endif
+    }
 #pragma unroll
     for (int i = 0; i < RS_IPT; i++) {
         const uint32_t d = (key[i] >> shift) & 255u;
