@@ -46,6 +46,13 @@ class Stats(ctypes.Structure):
     ]
 
 
+class TableDesc(ctypes.Structure):
+    _fields_ = [
+        ("chrom_offsets", c_void_p), ("chrom_bytes", c_void_p), ("codes", c_void_p), ("codes_valid", c_int32),
+        ("start", c_void_p), ("end", c_void_p), ("n", c_int64), ("start_adj", c_int32), ("end_adj", c_int32),
+    ]
+
+
 # name -> (restype, argtypes).  Every symbol declared in include/giqlb.h appears here; the CPU test-suite
 # checks the two lists against each other and against the built library.
 _P = c_void_p
@@ -80,6 +87,8 @@ PROTOTYPES = {
     "giqlb_intersects_emit": (c_int, [_P, _P, _P, _P]),
     "giqlb_joinplan_free": (c_int, [_P, _P]),
     "giqlb_intersects_join": (c_int, [_P, _P, _P, _P, _P, c_int64, POINTER(c_int64)]),
+    "giqlb_intersects_tables": (c_int, [_P, POINTER(TableDesc), POINTER(TableDesc), c_int32, _P, _P, c_int64, POINTER(c_int64),
+                                        POINTER(_P)]),
     "giqlb_intersects_exists": (c_int, [_P, _P, _P, _P, _P, c_int64, c_int32, c_int32, _P, _P]),
     "giqlb_select_rows": (c_int, [_P, _P, c_int64, c_int, _P, POINTER(c_int64)]),
     "giqlb_intersects_count_rows": (c_int, [_P, _P, _P, _P, _P, c_int64, c_int32, c_int32, _P, _P]),

@@ -11,6 +11,9 @@
 
 namespace {
 
+#ifndef GIQLB_KEYGEN_HIST
+#define GIQLB_KEYGEN_HIST 0
+#endif
 constexpr int LY_THREADS = 256;
 constexpr int LY_SMEM_CODES = 2048;
 
@@ -33,13 +36,12 @@ layout_observe_kernel(const int32_t* __restrict__ code, const int32_t* __restric
     }
     bool bad = false;
     unsigned int degenerate = 0, negative = 0;
-    for (int64_t i = (int64_t)blockIdx.x * LY_THREADS + threadIdx.x; i < n; i += (int64_t)gridDim.x * LY_THREADS) {
-        int32_t c = code[i];
-        long long s = (long long)start[i] + sadj, e = (long long)end[i] + eadj;
+    auto fold = [&](int32_t c, int32_t s0, int32_t e0) {
+        long long s = (long long)s0 + sadj, e = (long long)e0 + eadj;
         long long lo = s < e ? s : e, hi = s < e ? e : s;
         if (c < 0 || c >= n_codes || lo < -(1ll << 30) || hi > (1ll << 31) - 4) {
             bad = true;
-            continue;
+            return;
         }
         degenerate += e <= s;
         negative += e < s;
@@ -50,7 +52,21 @@ layout_observe_kernel(const int32_t* __restrict__ code, const int32_t* __restric
             if (lo < *(volatile long long*)&lohi[c]) atomicMin(&lohi[c], lo);
             if (hi > *(volatile long long*)&lohi[n_codes + c]) atomicMax(&lohi[n_codes + c], hi);
         }
+    };
+    // 16-byte vector loads when the three columns are aligned (they are when they come from one allocation each)
+    const bool vec = ((reinterpret_cast<uintptr_t>(code) | reinterpret_cast<uintptr_t>(start) | reinterpret_cast<uintptr_t>(end)) & 15) == 0;
+    const int64_t n_vec = vec ? n >> 2 : 0;
+    for (int64_t i = (int64_t)blockIdx.x * LY_THREADS + threadIdx.x; i < n_vec; i += (int64_t)gridDim.x * LY_THREADS) {
+        const int4 c = __ldg(reinterpret_cast<const int4*>(code) + i);
+        const int4 s = __ldg(reinterpret_cast<const int4*>(start) + i);
+        const int4 e = __ldg(reinterpret_cast<const int4*>(end) + i);
+        fold(c.x, s.x, e.x);
+        fold(c.y, s.y, e.y);
+        fold(c.z, s.z, e.z);
+        fold(c.w, s.w, e.w);
     }
+    for (int64_t i = (n_vec << 2) + (int64_t)blockIdx.x * LY_THREADS + threadIdx.x; i < n; i += (int64_t)gridDim.x * LY_THREADS)
+        fold(code[i], start[i], end[i]);
     if (bad) err[1] = 1;
     if (__any_sync(FULL_MASK, degenerate != 0)) {
         degenerate = warp_reduce_add(degenerate);
@@ -122,7 +138,13 @@ index_keygen_kernel(const int32_t* __restrict__ code, const int32_t* __restrict_
                     const uint32_t* __restrict__ base, const int32_t* __restrict__ lo32,
                     const int32_t* __restrict__ hi32, uint32_t* __restrict__ gs, uint32_t* __restrict__ ge,
                     unsigned long long* __restrict__ counters /* [0] end<=start [1] end<start [2] outside layout */,
+                    uint32_t* __restrict__ ghist /* nullable: [4][256] digit counts of the start keys, for the sort */,
                     int* __restrict__ err) {
+    __shared__ uint32_t s_hist[4][256];
+    if (ghist) {
+        for (int i = threadIdx.x; i < 4 * 256; i += blockDim.x) (&s_hist[0][0])[i] = 0;
+        __syncthreads();
+    }
     unsigned int degenerate = 0, negative = 0, outside = 0;
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
         const int64_t r = rows ? (int64_t)rows[i] : i;
@@ -145,6 +167,19 @@ index_keygen_kernel(const int32_t* __restrict__ code, const int32_t* __restrict_
         }
         gs[i] = ks;
         ge[i] = ke;
+        if (ghist) {
+            atomicAdd(&s_hist[0][ks & 255u], 1u);
+            atomicAdd(&s_hist[1][(ks >> 8) & 255u], 1u);
+            atomicAdd(&s_hist[2][(ks >> 16) & 255u], 1u);
+            atomicAdd(&s_hist[3][ks >> 24], 1u);
+        }
+    }
+    if (ghist) {
+        __syncthreads();
+        for (int i = threadIdx.x; i < 4 * 256; i += blockDim.x) {
+            const uint32_t c = (&s_hist[0][0])[i];
+            if (c) atomicAdd(&ghist[i], c);
+        }
     }
     degenerate = warp_reduce_add(degenerate);
     negative = warp_reduce_add(negative);
@@ -409,6 +444,7 @@ extern "C" int giqlb_index_build_rows(giqlb_ctx* ctx, const giqlb_layout* lay, c
 
     uint32_t *ka = nullptr, *kb = nullptr, *va = nullptr, *vb = nullptr, *ge_u = nullptr, *gs_u = nullptr;
     unsigned long long* counters = nullptr;
+    uint32_t* key_hist = nullptr;
     int st = GIQLB_OK;
 #define IB_TRY(expr)                      \
     do {                                  \
@@ -424,21 +460,23 @@ extern "C" int giqlb_index_build_rows(giqlb_ctx* ctx, const giqlb_layout* lay, c
         }                                                                                               \
     } while (0)
 
-    IB_TRY(dev_alloc(ctx, &ix->d_counters, 4));
+    IB_TRY(dev_alloc(ctx, &ix->d_counters, 4 + 512));   // [0..3] counters, then uint32 [4][256] digit counts of the start keys
     counters = ix->d_counters;
+    // (measured: counting the digits inside keygen costs more than the separate histogram pass saves; kept switchable)
+    key_hist = GIQLB_KEYGEN_HIST && !ix->tie_by_end ? reinterpret_cast<uint32_t*>(ix->d_counters + 4) : nullptr;
     IB_TRY(dev_alloc(ctx, &ka, (size_t)n));
     IB_TRY(dev_alloc(ctx, &kb, (size_t)n));
     IB_TRY(dev_alloc(ctx, &va, (size_t)n));
     IB_TRY(dev_alloc(ctx, &vb, (size_t)n));
     IB_TRY(dev_alloc(ctx, &ge_u, (size_t)n));
     IB_TRY(dev_alloc(ctx, &ix->ge, (size_t)n));
-    IB_CUDA(cudaMemsetAsync(counters, 0, 3 * 8, ctx->stream));
+    IB_CUDA(cudaMemsetAsync(counters, 0, (4 + 512) * 8, ctx->stream));
     if (n > 0) {
         int result_in_b = 0;
         {
         PhaseSpan ps(ctx, GIQLB_PH_KEYGEN);
         index_keygen_kernel<<<grid_for(ctx, n, 256 * 4, 8), 256, 0, ctx->stream>>>(
-            code, start, end, rows, n, lay->n_codes, start_adj, end_adj, lay->d_base, lay->d_lo32, lay->d_hi32, ka, ge_u, counters, ctx->d_err);
+            code, start, end, rows, n, lay->n_codes, start_adj, end_adj, lay->d_base, lay->d_lo32, lay->d_hi32, ka, ge_u, counters, key_hist, ctx->d_err);
         ctx->launches_this_call++;
         ctx->stats.kernels_total++;
         }
@@ -466,7 +504,7 @@ extern "C" int giqlb_index_build_rows(giqlb_ctx* ctx, const giqlb_layout* lay, c
             uint32_t* rk = r2 ? k3 : k2;
             result_in_b = (rk == kb) ? 1 : 0;
         } else {
-            IB_TRY(giqlb_radix_sort_pairs_u32(ctx, ka, va, kb, vb, n, 0, lay->key_bits, 1, &result_in_b));
+            IB_TRY(giqlb_radix_sort_pairs_u32(ctx, ka, va, kb, vb, n, 0, lay->key_bits, 1, &result_in_b, key_hist));
         }
         if (result_in_b) {
             ix->gs = kb; ix->rid = reinterpret_cast<int32_t*>(vb);

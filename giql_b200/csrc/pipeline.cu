@@ -1,0 +1,47 @@
+// pipeline.cu — the whole INTERSECTS hot path behind ONE C call.
+//
+// giqlb_intersects_tables() runs, for two tables given as raw columns, exactly the sequence the host layer would
+// issue call by call — dictionary encode (unless the caller passes codes), genome layout, sorted index of both
+// tables, single-pass join — so a host written in any language pays one FFI crossing and the GPU never idles
+// waiting for an interpreter between the three host round trips the path needs (dictionary names, layout
+// extent, pair total).  Replaces, in one call, what DuckDB does for the statement emitted at
+// src/giql/expanders/intersects_duckdb.py:1283-1334 (reference).
+#include "common.cuh"
+
+extern "C" int giqlb_intersects_tables(giqlb_ctx* ctx, giqlb_table_t* L, giqlb_table_t* R, int32_t n_codes, int32_t* out_l,
+                                       int32_t* out_r, int64_t capacity, int64_t* total_host, giqlb_dict** dict_out) {
+    if (!ctx || !L || !R || !total_host) return giqlb_fail(ctx, GIQLB_ERR_INVALID, "intersects_tables: bad argument");
+    if (dict_out) *dict_out = nullptr;
+    giqlb_dict* dict = nullptr;
+    giqlb_layout* lay = nullptr;
+    giqlb_index *il = nullptr, *ir = nullptr;
+    int st = GIQLB_OK;
+    const bool same = L == R;
+    if (!L->codes_valid || !R->codes_valid) {
+        if (L->codes_valid != R->codes_valid) return giqlb_fail(ctx, GIQLB_ERR_INVALID, "intersects_tables: encode both tables or neither");
+        st = giqlb_dict_encode(ctx, L->chrom_offsets, L->chrom_bytes, L->n, same ? nullptr : R->chrom_offsets,
+                               same ? nullptr : R->chrom_bytes, same ? 0 : R->n, L->codes, same ? nullptr : R->codes, &dict);
+        if (st != GIQLB_OK) return st;
+        n_codes = giqlb_dict_size(dict);
+        L->codes_valid = R->codes_valid = 1;
+    }
+    const int32_t launches0 = 0;
+    (void)launches0;
+    if (st == GIQLB_OK) st = giqlb_layout_create(ctx, n_codes, 0, &lay);
+    if (st == GIQLB_OK) st = giqlb_layout_observe(ctx, lay, L->codes, L->start, L->end, L->n, L->start_adj, L->end_adj);
+    if (st == GIQLB_OK && !same) st = giqlb_layout_observe(ctx, lay, R->codes, R->start, R->end, R->n, R->start_adj, R->end_adj);
+    if (st == GIQLB_OK) st = giqlb_layout_finalize(ctx, lay);
+    if (st == GIQLB_OK) st = giqlb_index_build(ctx, lay, L->codes, L->start, L->end, nullptr, L->n, L->start_adj, L->end_adj, 0, &il);
+    if (st == GIQLB_OK && !same) st = giqlb_index_build(ctx, lay, R->codes, R->start, R->end, nullptr, R->n, R->start_adj, R->end_adj, 0, &ir);
+    if (st == GIQLB_OK) st = giqlb_intersects_join(ctx, il, same ? il : ir, out_l, out_r, capacity, total_host);
+    // keep the failing call's message across the clean-up calls
+    char msg[sizeof(ctx->err)];
+    memcpy(msg, ctx->err, sizeof(msg));
+    giqlb_index_free(ctx, il);
+    if (!same) giqlb_index_free(ctx, ir);
+    giqlb_layout_free(ctx, lay);
+    if (dict_out) *dict_out = dict;
+    else giqlb_dict_free(dict);
+    if (st != GIQLB_OK) memcpy(ctx->err, msg, sizeof(msg));
+    return st;
+}

@@ -213,7 +213,7 @@ rs_onesweep_kernel(const uint32_t* __restrict__ keys_in, const uint32_t* __restr
 // i itself (vals_a is scratch and is not read by the first pass).
 int giqlb_radix_sort_pairs_u32(giqlb_ctx* ctx, uint32_t* keys_a, uint32_t* vals_a, uint32_t* keys_b,
                                uint32_t* vals_b, int64_t n, int begin_bit, int end_bit, int identity_vals,
-                               int* result_in_b) {
+                               int* result_in_b, const uint32_t* hist_dev) {
     *result_in_b = 0;
     if (n >= (int64_t)ST_VALUE_MASK) return giqlb_fail(ctx, GIQLB_ERR_INVALID, "radix sort: n=%lld too large", (long long)n);
     int n_passes = (end_bit - begin_bit + 7) / 8;
@@ -230,17 +230,20 @@ int giqlb_radix_sort_pairs_u32(giqlb_ctx* ctx, uint32_t* keys_a, uint32_t* vals_
     uint32_t* tickets = ghist + (size_t)n_passes * RS_RADIX;
     uint32_t* status = ghist + head_words;
 
-    int64_t hb_want = ceil_div(n, RS_THREADS * 16), hb_cap = (int64_t)ctx->sm_count * 8;
-    int hist_blocks = (int)(hb_want < hb_cap ? hb_want : hb_cap);
-    {
+    if (hist_dev && begin_bit == 0) {
+        // the producer of the keys already counted every digit (index_keygen_kernel): [4][256] for bits 0..31
+        CUDA_TRY(ctx, cudaMemcpyAsync(ghist, hist_dev, (size_t)n_passes * RS_RADIX * sizeof(uint32_t), cudaMemcpyDeviceToDevice, ctx->stream));
+    } else {
+        int64_t hb_want = ceil_div(n, RS_THREADS * 16), hb_cap = (int64_t)ctx->sm_count * 8;
+        int hist_blocks = (int)(hb_want < hb_cap ? hb_want : hb_cap);
         PhaseSpan ps(ctx, GIQLB_PH_SORT_HIST);
         rs_histogram_kernel<<<hist_blocks, RS_THREADS, 0, ctx->stream>>>(keys_a, n, begin_bit, n_passes, ghist);
         LAUNCH_CHECK(ctx);
     }
 
     uint32_t *kin = keys_a, *vin = vals_a, *kout = keys_b, *vout = vals_b;
+    PhaseSpan ps_passes(ctx, GIQLB_PH_SORT_PASS);
     for (int p = 0; p < n_passes; p++) {
-        PhaseSpan ps(ctx, GIQLB_PH_SORT_PASS);
         const int shift = begin_bit + 8 * p;
         const uint32_t* gh = ghist + (size_t)p * RS_RADIX;
         uint32_t* st = status + (size_t)p * tiles * RS_RADIX;

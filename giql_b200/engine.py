@@ -444,15 +444,7 @@ class Engine:
             self.ctx, _ptr(a.chrom_offsets), _ptr(a.chrom_bytes), a.n,
             _ptr(t1.chrom_offsets) if t1 else zero, _ptr(t1.chrom_bytes) if t1 else zero, t1.n if t1 else 0,
             _ptr(ca), _ptr(cb) if cb is not None else zero, ctypes.byref(h)))
-        try:
-            names = []
-            for code in range(self.lib.giqlb_dict_size(h)):
-                p, ln = ctypes.c_void_p(), ctypes.c_int32()
-                self.lib.giqlb_dict_get(h, code, ctypes.byref(p), ctypes.byref(ln))
-                names.append(ctypes.string_at(p, ln.value).decode("utf-8", "surrogateescape"))
-        finally:
-            self.lib.giqlb_dict_free(h)
-        d = Dictionary(names)
+        d = self._take_dictionary(h)
         a.codes, a.dictionary = ca, d
         if t1 is not None:
             t1.codes, t1.dictionary = cb, d
@@ -477,6 +469,10 @@ class Engine:
         src/giql/expanders/intersects_duckdb.py:1283-1299; bag semantics, unordered.  ``mode``: see
         :meth:`_join_indexes`.
         """
+        if mode != "two_pass" and self._pair_capacity > 0:
+            res = self._intersects_one_call(left, right)
+            if res is not None:
+                return res
         lay, il, ir = self._pair_indexes(left, right)
         try:
             return self._join_indexes(il, ir, mode)
@@ -484,6 +480,60 @@ class Engine:
             il.free()
             ir.free()
             lay.free()
+
+    def _table_desc(self, t: DeviceTable) -> "_cabi.TableDesc":
+        sadj, eadj = t.offsets
+        if t.codes is None:
+            t.codes = self._empty(t.n, torch.int32)
+            valid = 0
+        else:
+            valid = 1 if t.dictionary is not None else 0
+        d = _cabi.TableDesc()
+        d.chrom_offsets = t.chrom_offsets.data_ptr() if t.chrom_offsets is not None else None
+        d.chrom_bytes = t.chrom_bytes.data_ptr() if t.chrom_bytes is not None else None
+        d.codes, d.codes_valid = t.codes.data_ptr(), valid
+        d.start, d.end, d.n, d.start_adj, d.end_adj = t.start.data_ptr(), t.end.data_ptr(), t.n, sadj, eadj
+        return d
+
+    def _intersects_one_call(self, left: DeviceTable, right: DeviceTable) -> Optional[PairResult]:
+        """The whole path through giqlb_intersects_tables (one FFI crossing).  Returns None when the tables cannot take
+        it (one encoded, one not; encoded against different dictionaries) and the step-by-step path must run."""
+        enc_l, enc_r = left.dictionary is not None, right.dictionary is not None
+        if enc_l != enc_r or (enc_l and left.dictionary is not right.dictionary):
+            return None
+        if not enc_l and (left.chrom_offsets is None or right.chrom_offsets is None):
+            return None
+        dl = self._table_desc(left)
+        dr = dl if right is left else self._table_desc(right)
+        n_codes = len(left.dictionary) if enc_l else 0
+        cap = max(self._pair_capacity, 1024)
+        total, dict_h = ctypes.c_int64(), ctypes.c_void_p()
+        for _ in range(2):
+            out_l, out_r = self._empty(cap, torch.int32), self._empty(cap, torch.int32)
+            st = self.lib.giqlb_intersects_tables(self.ctx, ctypes.byref(dl), ctypes.byref(dr), n_codes, _ptr(out_l), _ptr(out_r), cap,
+                                                  ctypes.byref(total), ctypes.byref(dict_h))
+            if dict_h.value:
+                d = self._take_dictionary(dict_h)
+                left.dictionary = right.dictionary = d
+                n_codes, enc_l = len(d), True
+            if st == _cabi.OK:
+                return PairResult(out_l[: total.value], out_r[: total.value])
+            if st != _cabi.ERR_CAPACITY:
+                self._check(st)
+            cap = total.value
+            self._pair_capacity = int(cap * 1.25) + 1024
+        raise EngineError(_cabi.ERR_INTERNAL, "intersects_tables: capacity retry did not converge")
+
+    def _take_dictionary(self, h: ctypes.c_void_p) -> Dictionary:
+        try:
+            names = []
+            for code in range(self.lib.giqlb_dict_size(h)):
+                p, ln = ctypes.c_void_p(), ctypes.c_int32()
+                self.lib.giqlb_dict_get(h, code, ctypes.byref(p), ctypes.byref(ln))
+                names.append(ctypes.string_at(p, ln.value).decode("utf-8", "surrogateescape"))
+        finally:
+            self.lib.giqlb_dict_free(h)
+        return Dictionary(names)
 
     def _join_indexes(self, il: _Index, ir: _Index, mode: str = "auto") -> PairResult:
         """INTERSECTS over two indexes built on one layout.

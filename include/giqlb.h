@@ -191,6 +191,23 @@ int giqlb_joinplan_free(giqlb_ctx* ctx, giqlb_joinplan* plan);
 int giqlb_intersects_join(giqlb_ctx* ctx, giqlb_index* L, giqlb_index* R, int32_t* out_l, int32_t* out_r,
                           int64_t capacity, int64_t* total_host);
 
+/* The whole path in one call: dictionary encode (skipped when both tables arrive with codes_valid = 1 and a shared
+ * dictionary of n_codes names), layout, index of both tables, single-pass join into out_l/out_r.  Returns
+ * GIQLB_ERR_CAPACITY and the exact total when `capacity` is too small.  On success with encoding done here,
+ * *dict_out (nullable) receives the dictionary (caller frees) and L->codes / R->codes hold the codes. */
+typedef struct giqlb_table_t {
+    const int32_t* chrom_offsets;   /* Arrow utf8 offsets[n + 1] (device); unused when codes_valid */
+    const uint8_t* chrom_bytes;
+    int32_t* codes;                 /* int32[n] (device): written by the encode, or supplied with codes_valid = 1 */
+    int32_t codes_valid;
+    const int32_t* start;
+    const int32_t* end;
+    int64_t n;
+    int32_t start_adj, end_adj;     /* canonical.py:16-52 offsets */
+} giqlb_table_t;
+int giqlb_intersects_tables(giqlb_ctx* ctx, giqlb_table_t* L, giqlb_table_t* R, int32_t n_codes, int32_t* out_l,
+                            int32_t* out_r, int64_t capacity, int64_t* total_host, giqlb_dict** dict_out);
+
 /* SEMI/ANTI: exists_by_row[i] = 1 iff left input row i has >= 1 match (uint8[n]).  The left table is
  * probed from its raw columns in input order (no index, no sort).  giqlb_select_rows compacts the row ids
  * with flag == want (ascending) and returns how many. */
