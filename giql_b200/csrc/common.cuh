@@ -383,6 +383,16 @@ int giqlb_excl_scan_u64(giqlb_ctx* ctx, const unsigned long long* in, unsigned l
                         unsigned long long* total_dev);
 int giqlb_incl_scan_max_u32(giqlb_ctx* ctx, const uint32_t* in, uint32_t* out, int64_t n,
                             const int64_t* d_block_off, int n_blocks);
+// keys produced by a fused select + keygen pass (shard.cu), handed to the index builder
+struct giqlb_prekeyed {
+    uint32_t* gs = nullptr;               // [n] linear starts of the selected rows (unsorted)
+    uint32_t* ge = nullptr;               // [n] their linear ends
+    int32_t* rows = nullptr;              // [n] their row ids
+    unsigned long long* counters = nullptr;   // [4 + 512] as giqlb_index::d_counters
+};
+int giqlb_index_build_impl(giqlb_ctx* ctx, const giqlb_layout* lay, const int32_t* code, const int32_t* start,
+                           const int32_t* end, const uint8_t* strand, const int32_t* rows, int64_t n, int32_t start_adj,
+                           int32_t end_adj, int flags, giqlb_prekeyed* pre, giqlb_index** out);
 int giqlb_index_ensure_pmax(giqlb_ctx* ctx, giqlb_index* ix);
 int giqlb_index_resolve(giqlb_ctx* ctx, giqlb_index* a, giqlb_index* b);
 int giqlb_index_ensure_end_sorted(giqlb_ctx* ctx, giqlb_index* ix);

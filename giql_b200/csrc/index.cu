@@ -421,13 +421,21 @@ extern "C" int giqlb_index_info(giqlb_ctx* ctx, giqlb_index* ix, int64_t* n_dege
 extern "C" int giqlb_index_build(giqlb_ctx* ctx, const giqlb_layout* lay, const int32_t* code, const int32_t* start,
                                  const int32_t* end, const uint8_t* strand, int64_t n, int32_t start_adj,
                                  int32_t end_adj, int flags, giqlb_index** out) {
-    return giqlb_index_build_rows(ctx, lay, code, start, end, strand, nullptr, n, start_adj, end_adj, flags, out);
+    return giqlb_index_build_impl(ctx, lay, code, start, end, strand, nullptr, n, start_adj, end_adj, flags, nullptr, out);
 }
 
 // `rows` (nullable) selects and orders the rows that are indexed; the index then carries rows[i] as row id.
 extern "C" int giqlb_index_build_rows(giqlb_ctx* ctx, const giqlb_layout* lay, const int32_t* code, const int32_t* start,
                                       const int32_t* end, const uint8_t* strand, const int32_t* rows, int64_t n,
                                       int32_t start_adj, int32_t end_adj, int flags, giqlb_index** out) {
+    return giqlb_index_build_impl(ctx, lay, code, start, end, strand, rows, n, start_adj, end_adj, flags, nullptr, out);
+}
+
+// `pre` (nullable): the keys were already generated by a fused select + keygen pass (shard.cu); the builder takes
+// ownership of its buffers.
+int giqlb_index_build_impl(giqlb_ctx* ctx, const giqlb_layout* lay, const int32_t* code, const int32_t* start,
+                           const int32_t* end, const uint8_t* strand, const int32_t* rows, int64_t n, int32_t start_adj,
+                           int32_t end_adj, int flags, giqlb_prekeyed* pre, giqlb_index** out) {
     if (!ctx || !lay || !out || n < 0 || (n > 0 && (!code || !start || !end)))
         return giqlb_fail(ctx, GIQLB_ERR_INVALID, "index_build: bad argument");
     if (!lay->finalized) return giqlb_fail(ctx, GIQLB_ERR_INVALID, "index_build: layout not finalized");
@@ -443,6 +451,7 @@ extern "C" int giqlb_index_build_rows(giqlb_ctx* ctx, const giqlb_layout* lay, c
     for (int i = 2; i <= GIQLB_MAX_STRAND_CODES; i++) ix->block_off[i] = n;
 
     uint32_t *ka = nullptr, *kb = nullptr, *va = nullptr, *vb = nullptr, *ge_u = nullptr, *gs_u = nullptr;
+    int32_t* pre_rows = nullptr;   // selection buffer handed over by a fused select + keygen pass
     unsigned long long* counters = nullptr;
     uint32_t* key_hist = nullptr;
     int st = GIQLB_OK;
@@ -460,20 +469,26 @@ extern "C" int giqlb_index_build_rows(giqlb_ctx* ctx, const giqlb_layout* lay, c
         }                                                                                               \
     } while (0)
 
-    IB_TRY(dev_alloc(ctx, &ix->d_counters, 4 + 512));   // [0..3] counters, then uint32 [4][256] digit counts of the start keys
+    if (pre) {
+        ka = pre->gs; ge_u = pre->ge; rows = pre->rows; ix->d_counters = pre->counters;
+        pre_rows = pre->rows;
+        pre->gs = pre->ge = nullptr; pre->rows = nullptr; pre->counters = nullptr;
+    } else {
+        IB_TRY(dev_alloc(ctx, &ix->d_counters, 4 + 512));   // [0..3] counters, then uint32 [4][256] digit counts of the start keys
+        IB_TRY(dev_alloc(ctx, &ka, (size_t)n));
+        IB_TRY(dev_alloc(ctx, &ge_u, (size_t)n));
+    }
     counters = ix->d_counters;
     // (measured: counting the digits inside keygen costs more than the separate histogram pass saves; kept switchable)
-    key_hist = GIQLB_KEYGEN_HIST && !ix->tie_by_end ? reinterpret_cast<uint32_t*>(ix->d_counters + 4) : nullptr;
-    IB_TRY(dev_alloc(ctx, &ka, (size_t)n));
+    key_hist = GIQLB_KEYGEN_HIST && !ix->tie_by_end && !pre ? reinterpret_cast<uint32_t*>(ix->d_counters + 4) : nullptr;
     IB_TRY(dev_alloc(ctx, &kb, (size_t)n));
     IB_TRY(dev_alloc(ctx, &va, (size_t)n));
     IB_TRY(dev_alloc(ctx, &vb, (size_t)n));
-    IB_TRY(dev_alloc(ctx, &ge_u, (size_t)n));
     IB_TRY(dev_alloc(ctx, &ix->ge, (size_t)n));
-    IB_CUDA(cudaMemsetAsync(counters, 0, (4 + 512) * 8, ctx->stream));
+    if (!pre) IB_CUDA(cudaMemsetAsync(counters, 0, (4 + 512) * 8, ctx->stream));
     if (n > 0) {
         int result_in_b = 0;
-        {
+        if (!pre) {
         PhaseSpan ps(ctx, GIQLB_PH_KEYGEN);
         index_keygen_kernel<<<grid_for(ctx, n, 256 * 4, 8), 256, 0, ctx->stream>>>(
             code, start, end, rows, n, lay->n_codes, start_adj, end_adj, lay->d_base, lay->d_lo32, lay->d_hi32, ka, ge_u, counters, key_hist, ctx->d_err);
@@ -539,7 +554,9 @@ extern "C" int giqlb_index_build_rows(giqlb_ctx* ctx, const giqlb_layout* lay, c
         if (strand) IB_TRY(dev_alloc(ctx, &ix->strand, 1));
     }
     dev_free(ctx, ka); dev_free(ctx, kb); dev_free(ctx, va); dev_free(ctx, vb); dev_free(ctx, ge_u); dev_free(ctx, gs_u);
+    dev_free(ctx, pre_rows);
     ka = kb = va = vb = ge_u = gs_u = nullptr;
+    pre_rows = nullptr;
     // degenerate-row counts: known already when the table was observed on this layout with the same offsets
     // (finalize() fetched them); otherwise they stay on the device until giqlb_index_resolve needs them.
     // Rows outside the layout raise the sticky flag checked at the next host round trip.
@@ -561,6 +578,7 @@ extern "C" int giqlb_index_build_rows(giqlb_ctx* ctx, const giqlb_layout* lay, c
     return end_call(ctx);
 fail:
     dev_free(ctx, ka); dev_free(ctx, kb); dev_free(ctx, va); dev_free(ctx, vb); dev_free(ctx, ge_u); dev_free(ctx, gs_u);
+    dev_free(ctx, pre_rows);
     giqlb_index_free(ctx, ix);
     return st;
 #undef IB_TRY

@@ -50,50 +50,147 @@ shard_hist_kernel(ProbeCols P, uint32_t* __restrict__ hist, uint32_t* __restrict
     if (bad) err[2] = 1;
 }
 
-// one CTA: walks the bins with a running count and records, for g = 1..world-1, the first bin boundary at
-// which at least ceil(g*n/world) left rows lie below.
+// one CTA: every thread owns a contiguous chunk of bins (serial sums, ONE block scan) and records, for
+// g = 1..world-1, the first bin boundary at which at least ceil(g*n/world) left rows lie below.
 __global__ void __launch_bounds__(1024)
 shard_cuts_kernel(const uint32_t* __restrict__ hist, int64_t n_bins, int64_t n, int world,
                   unsigned long long* __restrict__ cuts /* [world + 1] */) {
     __shared__ unsigned long long scratch[1024 / 32 + 2];
-    unsigned long long carry = 0;
-    for (int64_t b0 = 0; b0 < n_bins; b0 += 1024) {
-        int64_t b = b0 + threadIdx.x;
-        unsigned long long v = b < n_bins ? hist[b] : 0ull, tot;
-        unsigned long long excl = carry + block_excl_scan_add<unsigned long long>(v, scratch, &tot);
-        unsigned long long incl = excl + v;
+    const int64_t per = (n_bins + 1023) / 1024;
+    const int64_t lo = min((int64_t)threadIdx.x * per, n_bins), hi = min(lo + per, n_bins);
+    unsigned long long sum = 0;
+    for (int64_t b = lo; b < hi; b++) sum += hist[b];
+    unsigned long long tot;
+    unsigned long long excl = block_excl_scan_add<unsigned long long>(sum, scratch, &tot);
+    for (int64_t b = lo; b < hi; b++) {
+        const unsigned long long v = hist[b];
         if (v) {
+            const unsigned long long incl = excl + v;
             // targets g with excl < ceil(g*n/world) <= incl
             long long g_lo = (long long)((excl * (unsigned long long)world) / (unsigned long long)n);   // floor
             for (long long g = g_lo > 1 ? g_lo : 1; g < world; g++) {
-                unsigned long long target = ((unsigned long long)g * (unsigned long long)n + world - 1) / world;
+                const unsigned long long target = ((unsigned long long)g * (unsigned long long)n + world - 1) / world;
                 if (target > incl) break;
                 if (target > excl) cuts[g] = (unsigned long long)(b + 1) << SH_BIN_SHIFT;
             }
+            excl = incl;
         }
-        carry += tot;
-        __syncthreads();
     }
 }
 
-struct InShardPred {
-    ProbeCols P;
-    uint32_t gs_lo, gs_hi, ge_gt;
-    __device__ unsigned long long operator()(int64_t i) const {
-        uint32_t gs, ge;
-        if (!row_linearise(P, i, gs, ge)) return 0ull;
-        return (gs >= gs_lo && gs < gs_hi && ge > ge_gt) ? 1ull : 0ull;
+// Selection without a scan: a CTA takes 1024 rows, scans its predicate counts in shared memory and claims its
+// slice of the output with ONE atomic; ids are ascending inside a slice, slices land in arbitrary order (the
+// selection is sorted by the index build anyway).
+__global__ void __launch_bounds__(SH_THREADS)
+shard_select_kernel(ProbeCols P, uint32_t gs_lo, uint32_t gs_hi, uint32_t ge_gt, int32_t* __restrict__ out_rows,
+                    unsigned long long* __restrict__ total) {
+    __shared__ unsigned int scratch[SH_THREADS / 32 + 2];
+    __shared__ unsigned long long s_base;
+    for (int64_t base = (int64_t)blockIdx.x * (SH_THREADS * 4); base < P.n; base += (int64_t)gridDim.x * (SH_THREADS * 4)) {
+        // thread t owns rows base + 4t .. base + 4t + 3 (ascending within the slice)
+        bool keep[4];
+        unsigned int cnt = 0;
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+            const int64_t i = base + (int64_t)threadIdx.x * 4 + k;
+            uint32_t gs, ge;
+            keep[k] = i < P.n && row_linearise(P, i, gs, ge) && gs >= gs_lo && gs < gs_hi && ge > ge_gt;
+            cnt += keep[k];
+        }
+        unsigned int tot;
+        unsigned int ex = block_excl_scan_add<unsigned int>(cnt, scratch, &tot);
+        if (threadIdx.x == 0 && tot) s_base = atomicAdd(total, (unsigned long long)tot);
+        __syncthreads();
+        if (tot) {
+            unsigned long long o = s_base + ex;
+#pragma unroll
+            for (int k = 0; k < 4; k++)
+                if (keep[k]) out_rows[o++] = (int32_t)(base + (int64_t)threadIdx.x * 4 + k);
+        }
+        __syncthreads();   // scratch / s_base are reused by the next slice
     }
-};
-struct OutShardRows {
-    int32_t* rows;
-    unsigned long long* total;
-    int64_t n;
-    __device__ void operator()(int64_t i, unsigned long long excl, unsigned long long v) const {
-        if (v) rows[excl] = (int32_t)i;
-        if (i == n - 1) *total = excl + v;
+}
+
+// Device-side finish of the cuts (what giqlb_shard_cuts does on the host): u32 cuts[world + 1] with cuts[0] = 0,
+// cuts[world] = 2^32 - 1, unset cuts inherit the next boundary, monotone; cuts32[world + 1] = widest left interval.
+__global__ void shard_cuts_finish_kernel(const unsigned long long* __restrict__ cuts64, const uint32_t* __restrict__ max_width, int world,
+                                         uint32_t* __restrict__ cuts32) {
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    cuts32[0] = 0u;
+    cuts32[world] = 0xffffffffu;
+    for (int g = world - 1; g >= 1; g--) {
+        unsigned long long c = cuts64[g];
+        if (c == 0 || c > 0xffffffffull) c = cuts32[g + 1];
+        cuts32[g] = (uint32_t)c;
     }
-};
+    for (int g = 1; g < world; g++)
+        if (cuts32[g] < cuts32[g - 1]) cuts32[g] = cuts32[g - 1];
+    cuts32[world + 1] = *max_width;
+}
+
+// Fused selection + key generation for one rank: reads the table once, keeps the rows of the rank's genome range
+// (side 0: owner-of-left-start; side 1: right rows that can overlap the range) and writes their linear keys and row
+// ids compacted (CTA-aggregated: one atomic per 1024 rows).  The range comes from DEVICE memory, so the host never
+// waits for the cuts.
+__global__ void __launch_bounds__(SH_THREADS)
+shard_select_keygen_kernel(ProbeCols P, const uint32_t* __restrict__ cuts32, int world, int rank, int side,
+                           uint32_t* __restrict__ out_gs, uint32_t* __restrict__ out_ge, int32_t* __restrict__ out_rows,
+                           unsigned long long* __restrict__ counters /* [0] end<=start [1] end<start [2] outside [3] selected */,
+                           int* __restrict__ err) {
+    __shared__ unsigned int scratch[SH_THREADS / 32 + 2];
+    __shared__ unsigned long long s_base;
+    const uint32_t lo = cuts32[rank], hi = cuts32[rank + 1], maxw = cuts32[world + 1];
+    const uint32_t gs_lo = side == 0 ? lo : 0u;
+    const uint32_t gs_hi = side == 0 ? hi : (hi > 0xffffffffu - maxw ? 0xffffffffu : hi + maxw);
+    const uint32_t ge_gt = side == 0 ? 0u : lo;
+    unsigned int degenerate = 0, negative = 0, outside = 0;
+    for (int64_t base = (int64_t)blockIdx.x * (SH_THREADS * 4); base < P.n; base += (int64_t)gridDim.x * (SH_THREADS * 4)) {
+        bool keep[4];
+        uint32_t gs[4], ge[4];
+        unsigned int cnt = 0;
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+            const int64_t i = base + (int64_t)threadIdx.x * 4 + k;
+            keep[k] = false;
+            if (i < P.n) {
+                if (!row_linearise(P, i, gs[k], ge[k])) outside++;
+                else keep[k] = gs[k] >= gs_lo && gs[k] < gs_hi && ge[k] > ge_gt;
+            }
+            if (keep[k]) {
+                degenerate += ge[k] <= gs[k];
+                negative += ge[k] < gs[k];
+            }
+            cnt += keep[k];
+        }
+        unsigned int tot;
+        unsigned int ex = block_excl_scan_add<unsigned int>(cnt, scratch, &tot);
+        if (threadIdx.x == 0 && tot) s_base = atomicAdd(&counters[3], (unsigned long long)tot);
+        __syncthreads();
+        if (tot) {
+            unsigned long long o = s_base + ex;
+#pragma unroll
+            for (int k = 0; k < 4; k++)
+                if (keep[k]) {
+                    out_gs[o] = gs[k];
+                    out_ge[o] = ge[k];
+                    out_rows[o] = (int32_t)(base + (int64_t)threadIdx.x * 4 + k);
+                    o++;
+                }
+        }
+        __syncthreads();
+    }
+    degenerate = warp_reduce_add(degenerate);
+    negative = warp_reduce_add(negative);
+    outside = warp_reduce_add(outside);
+    if (lane_id() == 0) {
+        if (degenerate) atomicAdd(&counters[0], (unsigned long long)degenerate);
+        if (negative) atomicAdd(&counters[1], (unsigned long long)negative);
+        if (outside) {
+            atomicAdd(&counters[2], (unsigned long long)outside);
+            err[3] = 1;
+        }
+    }
+}
 
 }  // namespace
 
@@ -160,16 +257,17 @@ extern "C" int giqlb_shard_cuts(giqlb_ctx* ctx, const giqlb_layout* lay, const i
 extern "C" int giqlb_shard_select(giqlb_ctx* ctx, const giqlb_layout* lay, const int32_t* code, const int32_t* start,
                                   const int32_t* end, int64_t n, int32_t start_adj, int32_t end_adj, uint32_t gs_lo,
                                   uint32_t gs_hi, uint32_t ge_gt, int32_t* out_rows, int64_t* n_out_host) {
-    using namespace giqlb_scan;
     if (!ctx || !n_out_host || (n > 0 && !out_rows)) return giqlb_fail(ctx, GIQLB_ERR_INVALID, "shard_select: bad argument");
     begin_call(ctx);
     ProbeCols P;
     GIQLB_TRY(probe_cols(ctx, lay, code, start, end, n, start_adj, end_adj, &P));
     unsigned long long* total = reinterpret_cast<unsigned long long*>(ctx->d_scalars + 9);
     CUDA_TRY(ctx, cudaMemsetAsync(total, 0, 8, ctx->stream));
-    {
+    if (n > 0) {
         PhaseSpan ps(ctx, GIQLB_PH_SHARD);
-        GIQLB_TRY((launch_scan<OpAddU64>(ctx, n, InShardPred{P, gs_lo, gs_hi, ge_gt}, OutShardRows{out_rows, total, n})));
+        int64_t blocks = ceil_div(n, SH_THREADS * 4), cap = (int64_t)ctx->sm_count * 8;
+        shard_select_kernel<<<(unsigned)(blocks < cap ? blocks : cap), SH_THREADS, 0, ctx->stream>>>(P, gs_lo, gs_hi, ge_gt, out_rows, total);
+        LAUNCH_CHECK(ctx);
     }
     GIQLB_TRY(fetch_scalars(ctx, total, 1));
     *n_out_host = ctx->h_scalars[0];
@@ -178,4 +276,112 @@ extern "C" int giqlb_shard_select(giqlb_ctx* ctx, const giqlb_layout* lay, const
     ctx->stats.rows_out = *n_out_host;
     ctx->stats.algorithmic_bytes = 12 * n + 4 * *n_out_host;
     return end_call(ctx);
+}
+
+// ---- the rank-local hot path in one call --------------------------------------------------------------------------
+// dictionary encode -> layout -> cuts (stay on the device) -> fused select + keygen of both tables -> ONE round trip
+// for the two selection sizes -> sort / index of the selections -> single-pass join.  Host round trips: dictionary
+// names, layout extent, selection sizes, pair total.
+extern "C" int giqlb_intersects_tables_sharded(giqlb_ctx* ctx, giqlb_table_t* L, giqlb_table_t* R, int32_t n_codes, int world,
+                                               int rank, int32_t* out_l, int32_t* out_r, int64_t capacity, int64_t* total_host,
+                                               giqlb_dict** dict_out) {
+    if (!ctx || !L || !R || !total_host || world < 1 || rank < 0 || rank >= world || L == R)
+        return giqlb_fail(ctx, GIQLB_ERR_INVALID, "intersects_tables_sharded: bad argument");
+    if (dict_out) *dict_out = nullptr;
+    giqlb_dict* dict = nullptr;
+    giqlb_layout* lay = nullptr;
+    giqlb_index *il = nullptr, *ir = nullptr;
+    giqlb_prekeyed pre[2];
+    uint32_t *hist = nullptr, *cuts32 = nullptr;
+    unsigned long long* cuts64 = nullptr;
+    int st = GIQLB_OK;
+    if (!L->codes_valid || !R->codes_valid) {
+        if (L->codes_valid != R->codes_valid) return giqlb_fail(ctx, GIQLB_ERR_INVALID, "intersects_tables_sharded: encode both tables or neither");
+        st = giqlb_dict_encode(ctx, L->chrom_offsets, L->chrom_bytes, L->n, R->chrom_offsets, R->chrom_bytes, R->n, L->codes, R->codes, &dict);
+        if (st != GIQLB_OK) return st;
+        n_codes = giqlb_dict_size(dict);
+        L->codes_valid = R->codes_valid = 1;
+    }
+    if (st == GIQLB_OK) st = giqlb_layout_create(ctx, n_codes, 0, &lay);
+    if (st == GIQLB_OK) st = giqlb_layout_observe(ctx, lay, L->codes, L->start, L->end, L->n, L->start_adj, L->end_adj);
+    if (st == GIQLB_OK) st = giqlb_layout_observe(ctx, lay, R->codes, R->start, R->end, R->n, R->start_adj, R->end_adj);
+    if (st == GIQLB_OK) st = giqlb_layout_finalize(ctx, lay);
+    giqlb_table_t* T[2] = {L, R};
+    int64_t n_sel[2] = {0, 0};
+    if (st == GIQLB_OK) {
+        begin_call(ctx);
+        ProbeCols P[2];
+        for (int k = 0; k < 2 && st == GIQLB_OK; k++)
+            st = probe_cols(ctx, lay, T[k]->codes, T[k]->start, T[k]->end, T[k]->n, T[k]->start_adj, T[k]->end_adj, &P[k]);
+        const int64_t n_bins = (int64_t)(lay->total_extent >> SH_BIN_SHIFT) + 1;
+        if (st == GIQLB_OK) st = dev_alloc(ctx, &hist, (size_t)n_bins + 1);
+        if (st == GIQLB_OK) st = dev_alloc(ctx, &cuts64, (size_t)world + 1);
+        if (st == GIQLB_OK) st = dev_alloc(ctx, &cuts32, (size_t)world + 2);
+        for (int k = 0; k < 2 && st == GIQLB_OK; k++) {
+            const size_t cap = (size_t)(T[k]->n > 0 ? T[k]->n : 1);
+            st = dev_alloc(ctx, &pre[k].gs, cap);
+            if (st == GIQLB_OK) st = dev_alloc(ctx, &pre[k].ge, cap);
+            if (st == GIQLB_OK) st = dev_alloc(ctx, &pre[k].rows, cap);
+            if (st == GIQLB_OK) st = dev_alloc(ctx, &pre[k].counters, 4 + 512);
+            if (st == GIQLB_OK && cudaMemsetAsync(pre[k].counters, 0, (4 + 512) * 8, ctx->stream) != cudaSuccess) st = GIQLB_ERR_CUDA;
+        }
+        if (st == GIQLB_OK) {
+            cudaMemsetAsync(hist, 0, ((size_t)n_bins + 1) * 4, ctx->stream);
+            cudaMemsetAsync(cuts64, 0, ((size_t)world + 1) * 8, ctx->stream);
+            PhaseSpan ps(ctx, GIQLB_PH_SHARD);
+            const int64_t cap = (int64_t)ctx->sm_count * 8;
+            if (L->n > 0) {
+                int64_t blocks = ceil_div(L->n, SH_THREADS * 8);
+                shard_hist_kernel<<<(unsigned)(blocks < cap ? blocks : cap), SH_THREADS, 0, ctx->stream>>>(P[0], hist, hist + n_bins, ctx->d_err);
+                shard_cuts_kernel<<<1, 1024, 0, ctx->stream>>>(hist, n_bins, L->n, world, cuts64);
+                ctx->launches_this_call += 2;
+                ctx->stats.kernels_total += 2;
+            }
+            shard_cuts_finish_kernel<<<1, 32, 0, ctx->stream>>>(cuts64, hist + n_bins, world, cuts32);
+            ctx->launches_this_call++;
+            ctx->stats.kernels_total++;
+            for (int k = 0; k < 2; k++) {
+                if (T[k]->n == 0) continue;
+                int64_t blocks = ceil_div(T[k]->n, SH_THREADS * 4);
+                shard_select_keygen_kernel<<<(unsigned)(blocks < cap ? blocks : cap), SH_THREADS, 0, ctx->stream>>>(
+                    P[k], cuts32, world, rank, k, pre[k].gs, pre[k].ge, pre[k].rows, pre[k].counters, ctx->d_err);
+                ctx->launches_this_call++;
+                ctx->stats.kernels_total++;
+            }
+            if (cudaGetLastError() != cudaSuccess) st = giqlb_fail(ctx, GIQLB_ERR_CUDA, "intersects_tables_sharded: launch failed");
+        }
+        // ONE round trip: both selection sizes (and the sticky error flags)
+        if (st == GIQLB_OK) {
+            cudaMemcpyAsync(ctx->h_scalars + 40, pre[0].counters, 4 * 8, cudaMemcpyDeviceToHost, ctx->stream);
+            cudaMemcpyAsync(ctx->h_scalars + 44, pre[1].counters, 4 * 8, cudaMemcpyDeviceToHost, ctx->stream);
+            st = fetch_scalars_checked(ctx, ctx->d_scalars, 1);
+            n_sel[0] = ctx->h_scalars[43];
+            n_sel[1] = ctx->h_scalars[47];
+        }
+    }
+    for (int k = 0; k < 2 && st == GIQLB_OK; k++) {
+        giqlb_index** dst = k == 0 ? &il : &ir;
+        const int64_t deg = ctx->h_scalars[40 + 4 * k], neg = ctx->h_scalars[41 + 4 * k];
+        st = giqlb_index_build_impl(ctx, lay, T[k]->codes, T[k]->start, T[k]->end, nullptr, pre[k].rows, n_sel[k], T[k]->start_adj,
+                                    T[k]->end_adj, 0, &pre[k], dst);
+        if (st == GIQLB_OK) {   // the counters came back with the selection sizes
+            (*dst)->n_degenerate = deg;
+            (*dst)->n_negative = neg;
+            (*dst)->resolved = true;
+        }
+    }
+    if (st == GIQLB_OK) st = giqlb_intersects_join(ctx, il, ir, out_l, out_r, capacity, total_host);
+    char msg[sizeof(ctx->err)];
+    memcpy(msg, ctx->err, sizeof(msg));
+    for (int k = 0; k < 2; k++) {
+        dev_free(ctx, pre[k].gs); dev_free(ctx, pre[k].ge); dev_free(ctx, pre[k].rows); dev_free(ctx, pre[k].counters);
+    }
+    dev_free(ctx, hist); dev_free(ctx, cuts64); dev_free(ctx, cuts32);
+    giqlb_index_free(ctx, il);
+    giqlb_index_free(ctx, ir);
+    giqlb_layout_free(ctx, lay);
+    if (dict_out) *dict_out = dict;
+    else giqlb_dict_free(dict);
+    if (st != GIQLB_OK) memcpy(ctx->err, msg, sizeof(msg));
+    return st;
 }

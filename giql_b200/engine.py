@@ -524,6 +524,32 @@ class Engine:
             self._pair_capacity = int(cap * 1.25) + 1024
         raise EngineError(_cabi.ERR_INTERNAL, "intersects_tables: capacity retry did not converge")
 
+    def intersects_shard(self, left: DeviceTable, right: DeviceTable, world: int, rank: int) -> PairResult:
+        """Rank ``rank``'s share of the join under genome-range sharding, through giqlb_intersects_tables_sharded (one FFI
+        crossing: encode, layout, device-side cuts, fused select + keygen, index, single-pass join)."""
+        enc_l, enc_r = left.dictionary is not None, right.dictionary is not None
+        if enc_l != enc_r or (enc_l and left.dictionary is not right.dictionary) or right is left:
+            raise ValueError("sharded join needs two distinct tables, both un-encoded or encoded against one dictionary")
+        dl, dr = self._table_desc(left), self._table_desc(right)
+        n_codes = len(left.dictionary) if enc_l else 0
+        cap = max(self._pair_capacity, 1024)
+        total, dict_h = ctypes.c_int64(), ctypes.c_void_p()
+        for _ in range(2):
+            out_l, out_r = self._empty(cap, torch.int32), self._empty(cap, torch.int32)
+            st = self.lib.giqlb_intersects_tables_sharded(self.ctx, ctypes.byref(dl), ctypes.byref(dr), n_codes, world, rank,
+                                                          _ptr(out_l), _ptr(out_r), cap, ctypes.byref(total), ctypes.byref(dict_h))
+            if dict_h.value:
+                d = self._take_dictionary(dict_h)
+                left.dictionary = right.dictionary = d
+                n_codes = len(d)
+            if st == _cabi.OK:
+                return PairResult(out_l[: total.value], out_r[: total.value])
+            if st != _cabi.ERR_CAPACITY:
+                self._check(st)
+            cap = total.value
+            self._pair_capacity = int(cap * 1.25) + 1024
+        raise EngineError(_cabi.ERR_INTERNAL, "intersects_tables_sharded: capacity retry did not converge")
+
     def _take_dictionary(self, h: ctypes.c_void_p) -> Dictionary:
         try:
             names = []

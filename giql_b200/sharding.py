@@ -18,7 +18,6 @@ The class is written against a small *ops* interface so the orchestration can be
 """
 from __future__ import annotations
 
-from dataclasses import dataclass
 from typing import Optional
 
 import torch
@@ -27,14 +26,24 @@ import torch.distributed as dist
 UINT32_MAX = 0xFFFFFFFF
 
 
-@dataclass
 class ShardedPairs:
-    """This rank's pairs plus where they sit in the global result."""
+    """This rank's pairs plus where they sit in the global result.
 
-    left_rows: torch.Tensor
-    right_rows: torch.Tensor
-    counts: list[int]          # pairs per rank (all-gathered)
-    rank: int
+    ``counts`` (pairs per rank) comes from an all-gather that is ISSUED when the join finishes and awaited only when
+    the counts are first read: the rank's own data path never depends on it.
+    """
+
+    def __init__(self, left_rows: torch.Tensor, right_rows: torch.Tensor, counts, rank: int):
+        self.left_rows, self.right_rows, self.rank = left_rows, right_rows, rank
+        self._counts = counts          # list[int], or a pending (work handle, gathered tensor)
+
+    @property
+    def counts(self) -> list[int]:
+        if not isinstance(self._counts, list):
+            work, gathered = self._counts
+            work.wait()
+            self._counts = [int(x) for x in gathered.cpu().tolist()]
+        return self._counts
 
     def __len__(self) -> int:
         return int(self.left_rows.numel())
@@ -65,7 +74,24 @@ def shard_ranges(cuts: list[int], max_width: int, g: int) -> tuple[tuple[int, in
 
 
 class EngineOps:
-    """ops interface over giql_b200.Engine (hand-written CUDA; no CPU fallback)."""
+    """ops interface over giql_b200.Engine (hand-written CUDA; no CPU fallback): the rank-local path in ONE library call
+    (giqlb_intersects_tables_sharded) — the cuts never leave the device."""
+
+    def __init__(self, engine):
+        self.e = engine
+        self.device = engine.device
+
+    def plan(self, left, right, world):
+        return {"world": world}
+
+    def join_shard(self, plan, left, right, g):
+        res = self.e.intersects_shard(left, right, plan["world"], g)
+        return res.left_rows, res.right_rows
+
+
+class EngineOpsStepwise:
+    """The same through the individual C-ABI calls (cuts fetched to the host, explicit selections): the reference
+    sequence the one-call path is tested against."""
 
     def __init__(self, engine):
         self.e = engine
@@ -115,16 +141,16 @@ class GenomeRangeShard:
         finally:
             if hasattr(self.ops, "release"):
                 self.ops.release(plan)
-        counts = self.all_gather_counts(int(out_l.numel()))
-        return ShardedPairs(out_l, out_r, counts, self.rank)
+        return ShardedPairs(out_l, out_r, self.all_gather_counts(int(out_l.numel())), self.rank)
 
-    def all_gather_counts(self, local: int) -> list[int]:
+    def all_gather_counts(self, local: int):
+        """Starts the all-gather of the per-rank pair counts (one int64 each); see ShardedPairs.counts."""
         if self.world == 1 or not dist.is_initialized():
             return [local]
         mine = torch.tensor([local], dtype=torch.int64, device=self.ops.device)
         allc = torch.empty(self.world, dtype=torch.int64, device=self.ops.device)
-        dist.all_gather_into_tensor(allc, mine, group=self.group)
-        return [int(x) for x in allc.cpu().tolist()]
+        work = dist.all_gather_into_tensor(allc, mine, group=self.group, async_op=True)
+        return (work, allc)
 
     def gather_pairs(self, res: ShardedPairs) -> tuple[torch.Tensor, torch.Tensor]:
         """Final pair gather: every rank receives all pairs, rank-major (rank g's slice starts at offsets[g])."""

@@ -208,6 +208,13 @@ typedef struct giqlb_table_t {
 int giqlb_intersects_tables(giqlb_ctx* ctx, giqlb_table_t* L, giqlb_table_t* R, int32_t n_codes, int32_t* out_l,
                             int32_t* out_r, int64_t capacity, int64_t* total_host, giqlb_dict** dict_out);
 
+/* The same for rank `rank` of `world` genome-range shards: both tables are given in full; the cuts
+ * are derived on the device from the left table, the rank's rows are selected and keyed in one pass per table, and
+ * only the rank's pairs are produced (row ids refer to the full tables).  The caller all-gathers the totals. */
+int giqlb_intersects_tables_sharded(giqlb_ctx* ctx, giqlb_table_t* L, giqlb_table_t* R, int32_t n_codes, int world, int rank,
+                                    int32_t* out_l, int32_t* out_r, int64_t capacity, int64_t* total_host,
+                                    giqlb_dict** dict_out);
+
 /* SEMI/ANTI: exists_by_row[i] = 1 iff left input row i has >= 1 match (uint8[n]).  The left table is
  * probed from its raw columns in input order (no index, no sort).  giqlb_select_rows compacts the row ids
  * with flag == want (ascending) and returns how many. */
@@ -264,7 +271,8 @@ int giqlb_disjoin(giqlb_ctx* ctx, const giqlb_layout* lay, const int32_t* t_code
  * table's linearised starts -> cuts_host[world + 1] (cuts[0] = 0, cuts[world] = 2^32 - 1) such that every
  * range [cuts[g], cuts[g+1]) holds ~n/world left rows; max_width_host = widest left interval (cells).
  * Deterministic: every rank computes identical cuts without any exchange.
- * shard_select(): ascending ids of the rows with  gs_lo <= linear start < gs_hi  AND  linear end > ge_gt.
+ * shard_select(): ids of the rows with  gs_lo <= linear start < gs_hi  AND  linear end > ge_gt, in unspecified order
+ *   (slices of ascending ids; the index build sorts the selection anyway).
  *   owner-of-left-start:  left  rows of rank g:  (cuts[g], cuts[g+1], 0)
  *   replicated straddlers: right rows of rank g:  (0, cuts[g+1] + max_width, cuts[g])
  * out_rows must hold n entries. */

@@ -218,12 +218,23 @@ def test_sharded_join_union_equals_single_gpu(world, engine, c_oracle):
     import torch
 
     from giql_b200 import synth
-    from giql_b200.sharding import EngineOps, shard_ranges
+    from giql_b200.sharding import EngineOps, EngineOpsStepwise, shard_ranges
 
     A, B = synth.peaks(200_000, 31), synth.peaks(150_000, 32)
     ta = engine.table_from_codes(A["code"], A["start"], A["end"], A["names"])
     tb = engine.table_from_codes(B["code"], B["start"], B["end"], ta.dictionary)
-    ops = EngineOps(engine)
+    exp = c_oracle.intersects_pairs(A["code"], A["start"], A["end"], B["code"], B["start"], B["end"], len(A["names"]))
+    exp = (exp[:, 0] << 32) | exp[:, 1]
+    # the one-call rank-local path (device-side cuts, fused select + keygen), from string chromosomes
+    S, T = synth.with_strings(A), synth.with_strings(B)
+    sa = engine.table({"chrom": S["chrom"], "start": S["start"], "end": S["end"]})
+    sb = engine.table({"chrom": T["chrom"], "start": T["start"], "end": T["end"]})
+    one = EngineOps(engine)
+    parts = [one.join_shard(one.plan(sa, sb, world), sa, sb, g) for g in range(world)]
+    got = torch.sort(torch.cat([(l.long() << 32) | r.long() for l, r in parts])).values.cpu().numpy()
+    assert np.array_equal(got, exp)
+    assert max(len(l) for l, _ in parts) < 2.5 * len(exp) / world + 1000
+    ops = EngineOpsStepwise(engine)
     plan = ops.plan(ta, tb, world)
     cuts = plan["cuts"]
     assert cuts[0] == 0 and cuts[-1] == 0xFFFFFFFF and all(a <= b for a, b in zip(cuts, cuts[1:]))
@@ -236,8 +247,7 @@ def test_sharded_join_union_equals_single_gpu(world, engine, c_oracle):
     assert sum(n_left) == ta.n
     assert max(n_left) - min(n_left) < 0.25 * ta.n / world + 70_000 / world   # equal counts up to one 2^16-cell bin
     got = torch.sort(torch.cat(packed)).values.cpu().numpy()
-    exp = c_oracle.intersects_pairs(A["code"], A["start"], A["end"], B["code"], B["start"], B["end"], len(A["names"]))
-    assert np.array_equal(got, (exp[:, 0] << 32) | exp[:, 1])
+    assert np.array_equal(got, exp)
 
 
 # ---- CLUSTER / MERGE ---------------------------------------------------------------------------------------------
