@@ -23,6 +23,7 @@ _STATUS_NAMES = {
 
 STRAND_PLUS, STRAND_MINUS, STRAND_DOT, STRAND_QMARK, STRAND_OTHER0, STRAND_NULL = 0, 1, 2, 3, 4, 255
 INDEX_TIE_BY_END = 1
+OP_CONTAINS, OP_WITHIN = 1, 2
 
 
 class EngineUnavailable(RuntimeError):
@@ -91,6 +92,7 @@ PROTOTYPES = {
                                         POINTER(_P)]),
     "giqlb_intersects_tables_sharded": (c_int, [_P, POINTER(TableDesc), POINTER(TableDesc), c_int32, c_int, c_int, _P, _P, c_int64,
                                                 POINTER(c_int64), POINTER(_P)]),
+    "giqlb_spatial_join": (c_int, [_P, _P, _P, c_int, _P, _P, c_int64, POINTER(c_int64)]),
     "giqlb_intersects_exists": (c_int, [_P, _P, _P, _P, _P, c_int64, c_int32, c_int32, _P, _P]),
     "giqlb_select_rows": (c_int, [_P, _P, c_int64, c_int, _P, POINTER(c_int64)]),
     "giqlb_intersects_count_rows": (c_int, [_P, _P, _P, _P, _P, c_int64, c_int32, c_int32, _P, _P]),

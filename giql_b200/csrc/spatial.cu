@@ -1,0 +1,154 @@
+// spatial.cu — column-to-column CONTAINS and WITHIN joins.
+//
+// Semantics (reference, abdenlab/giql src/giql/expanders/intersects.py:155-166):
+//   CONTAINS   l.chrom = r.chrom AND l.start <= r.start AND l.end >= r.end
+//   WITHIN     l.chrom = r.chrom AND l.start >= r.start AND l.end <= r.end        ( = CONTAINS with the roles swapped )
+// The reference has no IEJoin override for these (they always run the naive plan).  Here: for every container row x
+// the candidates are the rows of the other table whose start lies in [x.start, x.end] — one contiguous run of the
+// start-sorted index — filtered by end <= x.end; count -> exclusive scan -> emit, one thread per container row.
+#include "common.cuh"
+
+namespace {
+
+constexpr int SPB = 256;
+constexpr int SP_IPT = 4;
+constexpr int SPT = SPB * SP_IPT;
+
+struct Side {
+    const uint32_t* gs;
+    const uint32_t* ge;
+    const int32_t* rid;
+    int64_t n;
+};
+
+// candidate run of container x in Y: rows with x.gs <= y.gs <= x.ge.  With negative-width rows in Y (end < start) a
+// contained row may start beyond x.ge, so the run extends to the end of the chromosome's cell range.
+__device__ __forceinline__ void candidates(uint32_t xgs, uint32_t xge, const Side& Y, const uint32_t* __restrict__ base, int32_t n_codes,
+                                           int y_has_negative, int64_t& lo, int64_t& hi) {
+    lo = lower_bound_dev<uint32_t, int64_t>(Y.gs, 0, Y.n, xgs);
+    uint32_t top = xge;
+    if (y_has_negative) {   // last cell of x's chromosome: first base above xgs, minus one
+        int32_t a = 0, b = n_codes;
+        while (b - a > 1) {
+            int32_t mid = (a + b) >> 1;
+            if (__ldg(base + mid) <= xgs) a = mid; else b = mid;
+        }
+        top = __ldg(base + a + 1) - 1u;
+    }
+    hi = upper_bound_dev<uint32_t, int64_t>(Y.gs, lo, Y.n, top);
+}
+
+__global__ void __launch_bounds__(SPB)
+contains_count_kernel(Side X, Side Y, const uint32_t* __restrict__ base, int32_t n_codes, int y_has_negative,
+                      unsigned long long* __restrict__ tile_cnt) {
+    __shared__ unsigned long long s_red[SPB / 32];
+    unsigned long long cnt = 0;
+    const int64_t t0 = (int64_t)blockIdx.x * SPT;
+#pragma unroll 1
+    for (int j = 0; j < SP_IPT; j++) {
+        const int64_t i = t0 + j * SPB + threadIdx.x;
+        if (i < X.n) {
+            const uint32_t xgs = X.gs[i], xge = X.ge[i];
+            int64_t lo, hi;
+            candidates(xgs, xge, Y, base, n_codes, y_has_negative, lo, hi);
+            for (int64_t k = lo; k < hi; k++) cnt += __ldg(Y.ge + k) <= xge;
+        }
+    }
+    cnt = warp_reduce_add(cnt);
+    if (lane_id() == 0) s_red[warp_id()] = cnt;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        unsigned long long t = 0;
+        for (int w = 0; w < SPB / 32; w++) t += s_red[w];
+        tile_cnt[blockIdx.x] = t;
+    }
+}
+
+__global__ void __launch_bounds__(SPB)
+contains_emit_kernel(Side X, Side Y, const uint32_t* __restrict__ base, int32_t n_codes, int y_has_negative,
+                     const unsigned long long* __restrict__ tile_off, int32_t* __restrict__ out_x, int32_t* __restrict__ out_y) {
+    __shared__ unsigned long long s_scratch[SPB / 32 + 2];
+    const int64_t t0 = (int64_t)blockIdx.x * SPT;
+    unsigned long long carry = tile_off[blockIdx.x];
+#pragma unroll 1
+    for (int j = 0; j < SP_IPT; j++) {
+        const int64_t i = t0 + j * SPB + threadIdx.x;
+        unsigned long long cnt = 0;
+        int64_t lo = 0, hi = 0;
+        uint32_t xge = 0;
+        if (i < X.n) {
+            xge = X.ge[i];
+            candidates(X.gs[i], xge, Y, base, n_codes, y_has_negative, lo, hi);
+            for (int64_t k = lo; k < hi; k++) cnt += __ldg(Y.ge + k) <= xge;
+        }
+        unsigned long long tot;
+        unsigned long long o = carry + block_excl_scan_add<unsigned long long>(cnt, s_scratch, &tot);
+        carry += tot;
+        if (cnt) {
+            const int32_t xr = X.rid[i];
+            for (int64_t k = lo; k < hi; k++)
+                if (__ldg(Y.ge + k) <= xge) {
+                    out_x[o] = xr;
+                    out_y[o] = Y.rid[k];
+                    o++;
+                }
+        }
+        __syncthreads();
+    }
+}
+
+}  // namespace
+
+extern "C" int giqlb_spatial_join(giqlb_ctx* ctx, giqlb_index* L, giqlb_index* R, int op, int32_t* out_l, int32_t* out_r,
+                                  int64_t capacity, int64_t* total_host) {
+    if (!ctx || !L || !R || !total_host || capacity < 0 || (op != GIQLB_OP_CONTAINS && op != GIQLB_OP_WITHIN))
+        return giqlb_fail(ctx, GIQLB_ERR_INVALID, "spatial_join: bad argument");
+    if (L->layout != R->layout) return giqlb_fail(ctx, GIQLB_ERR_INVALID, "spatial_join: indexes were built on different layouts");
+    if (L->grouped_by_strand || R->grouped_by_strand) return giqlb_fail(ctx, GIQLB_ERR_INVALID, "spatial_join: strand-grouped indexes are not accepted");
+    begin_call(ctx);
+    GIQLB_TRY(giqlb_index_resolve(ctx, L, R));
+    *total_host = 0;
+    // WITHIN(l, r) == CONTAINS(r, l): X is always the container
+    giqlb_index* Xi = op == GIQLB_OP_CONTAINS ? L : R;
+    giqlb_index* Yi = op == GIQLB_OP_CONTAINS ? R : L;
+    int32_t* out_x = op == GIQLB_OP_CONTAINS ? out_l : out_r;
+    int32_t* out_y = op == GIQLB_OP_CONTAINS ? out_r : out_l;
+    if (Xi->n == 0 || Yi->n == 0) return end_call(ctx);
+    const Side X{Xi->gs, Xi->ge, Xi->rid, Xi->n}, Y{Yi->gs, Yi->ge, Yi->rid, Yi->n};
+    const int64_t n_tiles = ceil_div(X.n, SPT);
+    unsigned long long *cnt = nullptr, *off = nullptr;
+    unsigned long long* total = reinterpret_cast<unsigned long long*>(ctx->d_scalars);
+    int st = dev_alloc(ctx, &cnt, (size_t)n_tiles + 1);
+    if (st == GIQLB_OK) st = dev_alloc(ctx, &off, (size_t)n_tiles + 1);
+    const giqlb_layout* lay = L->layout;
+    const int y_neg = Yi->n_negative > 0;
+    if (st == GIQLB_OK) {
+        PhaseSpan ps(ctx, GIQLB_PH_JOIN_COUNT);
+        contains_count_kernel<<<(unsigned)n_tiles, SPB, 0, ctx->stream>>>(X, Y, lay->d_base, lay->n_codes, y_neg, cnt);
+        ctx->launches_this_call++;
+        ctx->stats.kernels_total++;
+    }
+    if (st == GIQLB_OK) st = giqlb_excl_scan_u64(ctx, cnt, off, n_tiles, total);
+    if (st == GIQLB_OK) st = fetch_scalars_checked(ctx, total, 1);
+    const int64_t n_out = st == GIQLB_OK ? ctx->h_scalars[0] : 0;
+    if (st == GIQLB_OK) {
+        *total_host = n_out;
+        if (n_out > capacity) st = giqlb_fail(ctx, GIQLB_ERR_CAPACITY, "spatial_join: %lld pairs exceed capacity %lld", (long long)n_out, (long long)capacity);
+        else if (n_out > 0 && (!out_l || !out_r)) st = giqlb_fail(ctx, GIQLB_ERR_INVALID, "spatial_join: null output");
+    }
+    if (st == GIQLB_OK && n_out > 0) {
+        PhaseSpan ps(ctx, GIQLB_PH_JOIN_EMIT);
+        contains_emit_kernel<<<(unsigned)n_tiles, SPB, 0, ctx->stream>>>(X, Y, lay->d_base, lay->n_codes, y_neg, off, out_x, out_y);
+        ctx->launches_this_call++;
+        ctx->stats.kernels_total++;
+        if (cudaGetLastError() != cudaSuccess) st = giqlb_fail(ctx, GIQLB_ERR_CUDA, "spatial_join: launch failed");
+    }
+    dev_free(ctx, cnt);
+    dev_free(ctx, off);
+    if (st != GIQLB_OK) return st;
+    ctx->stats.rows_in[0] = L->n;
+    ctx->stats.rows_in[1] = R->n;
+    ctx->stats.rows_out = n_out;
+    ctx->stats.algorithmic_bytes = 12 * (L->n + R->n) + 8 * n_out;
+    return end_call(ctx);
+}

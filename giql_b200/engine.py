@@ -616,6 +616,32 @@ class Engine:
                                                 gs_lo, gs_hi, ge_gt, _ptr(rows), ctypes.byref(n_out)))
         return rows[: n_out.value]
 
+    def _spatial(self, left: DeviceTable, right: DeviceTable, op: int) -> PairResult:
+        lay, il, ir = self._pair_indexes(left, right)
+        try:
+            total = ctypes.c_int64()
+            st = self.lib.giqlb_spatial_join(self.ctx, il.h, ir.h, op, None, None, 0, ctypes.byref(total))   # sizing call
+            if st not in (_cabi.OK, _cabi.ERR_CAPACITY):
+                self._check(st)
+            out_l, out_r = self._empty(total.value, torch.int32), self._empty(total.value, torch.int32)
+            if total.value:
+                self._check(self.lib.giqlb_spatial_join(self.ctx, il.h, ir.h, op, _ptr(out_l), _ptr(out_r), total.value, ctypes.byref(total)))
+            return PairResult(out_l, out_r)
+        finally:
+            il.free()
+            ir.free()
+            lay.free()
+
+    def contains(self, left: DeviceTable, right: DeviceTable) -> PairResult:
+        """``left.interval CONTAINS right.interval`` join: l.start <= r.start AND l.end >= r.end on one chromosome
+        (reference: src/giql/expanders/intersects.py:155-160)."""
+        return self._spatial(left, right, _cabi.OP_CONTAINS)
+
+    def within(self, left: DeviceTable, right: DeviceTable) -> PairResult:
+        """``left.interval WITHIN right.interval`` join: l.start >= r.start AND l.end <= r.end
+        (reference: src/giql/expanders/intersects.py:161-166)."""
+        return self._spatial(left, right, _cabi.OP_WITHIN)
+
     def _probe(self, fn, left: DeviceTable, right: DeviceTable, out: torch.Tensor):
         d = self.encode(left, right)
         lay = _Layout(self, len(d))

@@ -215,6 +215,14 @@ int giqlb_intersects_tables_sharded(giqlb_ctx* ctx, giqlb_table_t* L, giqlb_tabl
                                     int32_t* out_l, int32_t* out_r, int64_t capacity, int64_t* total_host,
                                     giqlb_dict** dict_out);
 
+/* ---- CONTAINS / WITHIN column-to-column joins (intersects.py:155-166) -----------------------------
+ * op GIQLB_OP_CONTAINS: l.start <= r.start AND l.end >= r.end;  GIQLB_OP_WITHIN: the mirror.  Same chromosome, bag
+ * semantics, pair order unspecified.  GIQLB_ERR_CAPACITY + the exact total when the outputs are too small. */
+#define GIQLB_OP_CONTAINS 1
+#define GIQLB_OP_WITHIN 2
+int giqlb_spatial_join(giqlb_ctx* ctx, giqlb_index* L, giqlb_index* R, int op, int32_t* out_l, int32_t* out_r,
+                       int64_t capacity, int64_t* total_host);
+
 /* SEMI/ANTI: exists_by_row[i] = 1 iff left input row i has >= 1 match (uint8[n]).  The left table is
  * probed from its raw columns in input order (no index, no sort).  giqlb_select_rows compacts the row ids
  * with flag == want (ascending) and returns how many. */

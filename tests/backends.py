@@ -31,6 +31,10 @@ class OracleBackend:
         p = self.go.join_pairs(canonicalise(L, lcfg), canonicalise(R, rcfg))
         return sorted((int(a), int(b)) for a, b in p)
 
+    def spatial_pairs(self, L, R, op, lcfg=None, rcfg=None):
+        p = self.go.join_pairs(canonicalise(L, lcfg), canonicalise(R, rcfg), op)
+        return sorted((int(a), int(b)) for a, b in p)
+
     def exists(self, L, R, lcfg=None, rcfg=None):
         n = len(L["start"])
         cnt = self.go.count_per_left(canonicalise(L, lcfg), canonicalise(R, rcfg)) if n else np.zeros(0, np.int64)
@@ -85,6 +89,17 @@ class EngineBackend:
         res = self.e.intersects(self._table(L, lcfg), self._table(R, rcfg), mode=self.join_mode)
         l, r = res.to_host()
         return sorted(zip(l.tolist(), r.tolist()))
+
+    def spatial_pairs(self, L, R, op, lcfg=None, rcfg=None):
+        res = (self.e.contains if op == "contains" else self.e.within)(self._table(L, lcfg), self._table(R, rcfg))
+        l, r = res.to_host()
+        return sorted(zip(l.tolist(), r.tolist()))
+
+    def range_filter(self, t, op, ranges, cfg):
+        """literal-range CONTAINS / WITHIN filter = the column join against the one-row table of the literal"""
+        lit = {"chrom": [r[0] for r in ranges], "start": [r[1] for r in ranges], "end": [r[2] for r in ranges]}
+        hit = {i for i, _ in self.spatial_pairs(t, lit, op, cfg, None)}
+        return [i in hit for i in range(len(t["start"]))]
 
     def exists(self, L, R, lcfg=None, rcfg=None):
         return [bool(x) for x in self.e.exists(self._table(L, lcfg), self._table(R, rcfg)).cpu().tolist()]

@@ -450,3 +450,20 @@ def test_join_modes_vs_oracle(mode, engine, c_oracle):
     tt = engine.table_from_codes(T["code"], T["start"], T["end"], tg.dictionary)
     exp = c_oracle.intersects_pairs(G["code"], G["start"], G["end"], T["code"], T["start"], T["end"], 1)
     assert np.array_equal(engine.intersects(tg, tt, mode=mode).sorted_packed(), (exp[:, 0] << 32) | exp[:, 1])
+
+
+# ---- CONTAINS / WITHIN joins (intersects.py:155-166) ----------------------------------------------------------------------
+@pytest.mark.parametrize("seed", range(4))
+def test_contains_within_joins_vs_oracle(seed, engine):
+    rng = np.random.default_rng(500 + seed)
+    L = _rand(rng, 400, span=800, max_len=120, min_len=0 if seed == 3 else 1)
+    R = _rand(rng, 500, span=800, max_len=40, min_len=0 if seed == 3 else 1)
+    ob, eb = OracleBackend(), EngineBackend(engine)
+    for op in ("contains", "within"):
+        assert eb.spatial_pairs(L, R, op) == ob.spatial_pairs(L, R, op)
+        assert eb.spatial_pairs(R, L, op) == ob.spatial_pairs(R, L, op)
+    # identical intervals contain each other; touching ones do not
+    X = {"chrom": ["chr1", "chr1", "chr2"], "start": [10, 10, 10], "end": [20, 20, 20]}
+    Y = {"chrom": ["chr1", "chr1"], "start": [10, 20], "end": [20, 30]}
+    assert eb.spatial_pairs(X, Y, "contains") == [(0, 0), (1, 0)] == eb.spatial_pairs(X, Y, "within")
+    assert eb.spatial_pairs(X, {"chrom": [], "start": [], "end": []}, "contains") == []
