@@ -101,6 +101,9 @@ PROTOTYPES = {
     "giqlb_cluster": (c_int, [_P, _P, c_int64, _P]),
     "giqlb_merge": (c_int, [_P, _P, c_int64, _P, _P, _P, _P, _P, c_int64, POINTER(c_int64)]),
     "giqlb_disjoin": (c_int, [_P, _P, _P, _P, _P, c_int64, c_int32, c_int32, _P, c_int, _P, _P, _P, c_int64, POINTER(c_int64)]),
+    "giqlb_shard_max_end": (c_int, [_P, _P, POINTER(ctypes.c_uint32)]),
+    "giqlb_cluster_shard": (c_int, [_P, _P, c_int64, ctypes.c_uint32, POINTER(ctypes.c_uint32), _P, POINTER(ctypes.c_uint32)]),
+    "giqlb_merge_shard": (c_int, [_P, _P, c_int64, ctypes.c_uint32, _P, _P, _P, _P, c_int64, POINTER(c_int64), POINTER(c_int64)]),
     "giqlb_shard_cuts": (c_int, [_P, _P, _P, _P, _P, c_int64, c_int32, c_int32, c_int, POINTER(ctypes.c_uint32),
                                  POINTER(ctypes.c_uint32)]),
     "giqlb_shard_select": (c_int, [_P, _P, _P, _P, _P, c_int64, c_int32, c_int32, ctypes.c_uint32, ctypes.c_uint32,

@@ -45,9 +45,11 @@ struct InClusterFlag {
     const uint32_t* pmax;
     LayoutView V;
     long long d;
+    uint32_t carry;   // running max of end over the rows of EARLIER genome-range shards (0: none)
     __device__ unsigned long long operator()(int64_t i) const {
-        if (i == 0) return 1ull;
-        const uint32_t s = gs[i], pm = pmax[i - 1];
+        const uint32_t s = gs[i];
+        uint32_t pm = carry;
+        if (i > 0) pm = max(pm, pmax[i - 1]);
         const uint32_t b = __ldg(V.base + chrom_of(V, s));
         const bool joins = pm > b && (long long)pm + d >= (long long)s;
         return joins ? 0ull : 1ull;
@@ -96,6 +98,7 @@ merge_emit_kernel(const uint32_t* __restrict__ gs, const uint32_t* __restrict__ 
                   int32_t* __restrict__ out_start, int32_t* __restrict__ out_end, long long* __restrict__ out_count) {
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
         const uint32_t g = G[i];
+        if (g == 0) continue;   // head fragment of a shard: continues a region owned by an earlier shard
         const bool first = i == 0 || G[i - 1] != g;
         const bool last = i + 1 == n || G[i + 1] != g;
         if (!first && !last) continue;
@@ -116,6 +119,47 @@ merge_emit_kernel(const uint32_t* __restrict__ gs, const uint32_t* __restrict__ 
     }
 }
 
+// per-chromosome number of clusters STARTING in this shard: running count at the chromosome's last row minus the
+// count before its first row
+__global__ void cluster_chrom_counts_kernel(const uint32_t* __restrict__ gs, const uint32_t* __restrict__ G, int64_t n, LayoutView V,
+                                            uint32_t* __restrict__ counts) {
+    int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= V.n_codes) return;
+    const int64_t first = lower_bound_dev<uint32_t, int64_t>(gs, 0, n, V.base[c]);
+    const int64_t last = lower_bound_dev<uint32_t, int64_t>(gs, 0, n, V.base[c + 1]);
+    counts[c] = last > first ? G[last - 1] - (first > 0 ? G[first - 1] : 0u) : 0u;
+}
+
+__global__ void cluster_ids_offset_kernel(const uint32_t* __restrict__ gs, const int32_t* __restrict__ rid, const uint32_t* __restrict__ G,
+                                          const uint32_t* __restrict__ off, const uint32_t* __restrict__ id_offset, int64_t n, LayoutView V,
+                                          int32_t* __restrict__ out_by_row) {
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t j = last_peer(gs, i, n);
+        const int32_t c = chrom_of(V, gs[i]);
+        out_by_row[rid[i]] = (int32_t)(G[j] - off[c] + id_offset[c]);
+    }
+}
+
+// head fragment of a shard: rows before the first cluster start.  out[0] = number of head rows, out[1] = chromosome code,
+// out[2] = canonical max end of the head rows
+__global__ void merge_head_kernel(const uint32_t* __restrict__ gs, const uint32_t* __restrict__ pmax, const uint32_t* __restrict__ G, int64_t n,
+                                  LayoutView V, long long* __restrict__ out) {
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    int64_t lo = 0, hi = n;   // first row with G >= 1 (G is non-decreasing)
+    while (lo < hi) {
+        int64_t mid = lo + ((hi - lo) >> 1);
+        if (G[mid] < 1u) lo = mid + 1; else hi = mid;
+    }
+    out[0] = lo;
+    out[1] = -1;
+    out[2] = 0;
+    if (lo > 0) {
+        const int32_t c = chrom_of(V, gs[0]);
+        out[1] = c;
+        out[2] = (long long)__ldg(V.lo32 + c) + (long long)(pmax[lo - 1] - (__ldg(V.base + c) + 1u));
+    }
+}
+
 __global__ void fill_u8_kernel(uint8_t* p, uint8_t v, int64_t n) {
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) p[i] = v;
 }
@@ -128,8 +172,8 @@ inline int grid_of(const giqlb_ctx* ctx, int64_t n, int per_thread) {
 inline LayoutView view_of(const giqlb_layout* lay) { return LayoutView{lay->d_base, lay->d_lo32, lay->n_codes}; }
 
 // flags -> running count G for rows [lo, hi) of the index; returns the block's cluster count in *total_dev
-int running_count(giqlb_ctx* ctx, const giqlb_index* X, int64_t lo, int64_t hi, long long d, uint32_t* G) {
-    return launch_scan<OpAddU64>(ctx, hi - lo, InClusterFlag{X->gs + lo, X->pmax + lo, view_of(X->layout), d},
+int running_count(giqlb_ctx* ctx, const giqlb_index* X, int64_t lo, int64_t hi, long long d, uint32_t* G, uint32_t carry = 0) {
+    return launch_scan<OpAddU64>(ctx, hi - lo, InClusterFlag{X->gs + lo, X->pmax + lo, view_of(X->layout), d, carry},
                                  OutRunningCount{G + lo});
 }
 
@@ -254,4 +298,121 @@ extern "C" int giqlb_merge(giqlb_ctx* ctx, giqlb_index* X, int64_t distance, int
     ctx->stats.rows_out = total;
     ctx->stats.algorithmic_bytes = 12 * n + (X->strand ? n : 0) + 12 * total;
     return end_call(ctx);
+}
+
+// ---- genome-range shards of CLUSTER / MERGE -------------------------------------------------------
+// A shard owns the rows whose START lies in its genome range.  What it needs from the shards before it is one
+// number — the running max of end over all earlier rows (`carry`, a linear coordinate; the guard cells make it
+// chromosome-safe) — and, for cluster ids, how many clusters earlier shards started on each chromosome.
+static int shard_index_ok(giqlb_ctx* ctx, giqlb_index* X, const char* who) {
+    GIQLB_TRY(check_index(ctx, X, who));
+    if (X->grouped_by_strand) return giqlb_fail(ctx, GIQLB_ERR_INVALID, "%s: strand-grouped indexes are not sharded", who);
+    return GIQLB_OK;
+}
+
+extern "C" int giqlb_shard_max_end(giqlb_ctx* ctx, giqlb_index* X, uint32_t* max_end_host) {
+    if (!ctx || !X || !max_end_host) return giqlb_fail(ctx, GIQLB_ERR_INVALID, "shard_max_end: bad argument");
+    begin_call(ctx);
+    *max_end_host = 0;
+    if (X->n == 0) return end_call(ctx);
+    GIQLB_TRY(giqlb_index_ensure_pmax(ctx, X));
+    GIQLB_TRY(fetch_scalars(ctx, X->pmax + X->n - 1, 1) == GIQLB_OK ? GIQLB_OK : GIQLB_ERR_CUDA);
+    *max_end_host = (uint32_t)(ctx->h_scalars[0] & 0xffffffffll);
+    return end_call(ctx);
+}
+
+extern "C" int giqlb_cluster_shard(giqlb_ctx* ctx, giqlb_index* X, int64_t distance, uint32_t carry, const uint32_t* id_offset_by_code_host,
+                                   int32_t* cluster_id_by_input_row, uint32_t* counts_by_code_host) {
+    if (!ctx || !X) return giqlb_fail(ctx, GIQLB_ERR_INVALID, "cluster_shard: bad argument");
+    begin_call(ctx);
+    GIQLB_TRY(shard_index_ok(ctx, X, "cluster_shard"));
+    const int32_t nc = X->layout->n_codes;
+    if (counts_by_code_host) memset(counts_by_code_host, 0, (size_t)nc * 4);
+    const int64_t n = X->n;
+    if (n == 0) return end_call(ctx);
+    GIQLB_TRY(giqlb_index_ensure_pmax(ctx, X));
+    const long long d = distance > 0 ? (long long)distance : 0;
+    const LayoutView V = view_of(X->layout);
+    uint32_t *G = nullptr, *off = nullptr, *aux = nullptr;
+    int st = dev_alloc(ctx, &G, (size_t)n);
+    if (st == GIQLB_OK) st = dev_alloc(ctx, &off, (size_t)nc);
+    if (st == GIQLB_OK) st = dev_alloc(ctx, &aux, (size_t)nc);
+    if (st == GIQLB_OK) {
+        PhaseSpan ps(ctx, GIQLB_PH_CLUSTER);
+        st = running_count(ctx, X, 0, n, d, G, carry);
+        if (st == GIQLB_OK && counts_by_code_host) {
+            cluster_chrom_counts_kernel<<<(nc + 127) / 128, 128, 0, ctx->stream>>>(X->gs, G, n, V, aux);
+            ctx->launches_this_call++;
+            ctx->stats.kernels_total++;
+            if (cudaMemcpyAsync(counts_by_code_host, aux, (size_t)nc * 4, cudaMemcpyDeviceToHost, ctx->stream) != cudaSuccess ||
+                cudaStreamSynchronize(ctx->stream) != cudaSuccess)
+                st = giqlb_fail(ctx, GIQLB_ERR_CUDA, "cluster_shard: count copy failed");
+        }
+        if (st == GIQLB_OK && cluster_id_by_input_row) {
+            if (!id_offset_by_code_host) st = giqlb_fail(ctx, GIQLB_ERR_INVALID, "cluster_shard: ids need the per-chromosome offsets");
+            if (st == GIQLB_OK && cudaMemcpyAsync(aux, id_offset_by_code_host, (size_t)nc * 4, cudaMemcpyHostToDevice, ctx->stream) != cudaSuccess)
+                st = giqlb_fail(ctx, GIQLB_ERR_CUDA, "cluster_shard: offset copy failed");
+            if (st == GIQLB_OK) {
+                cluster_chrom_offsets_kernel<<<(nc + 127) / 128, 128, 0, ctx->stream>>>(X->gs, G, n, V, off);
+                cluster_ids_offset_kernel<<<grid_of(ctx, n, 4), 256, 0, ctx->stream>>>(X->gs, X->rid, G, off, aux, n, V, cluster_id_by_input_row);
+                ctx->launches_this_call += 2;
+                ctx->stats.kernels_total += 2;
+                // id_offset_by_code_host is pageable caller memory: wait before returning
+                if (cudaStreamSynchronize(ctx->stream) != cudaSuccess || cudaGetLastError() != cudaSuccess)
+                    st = giqlb_fail(ctx, GIQLB_ERR_CUDA, "cluster_shard: launch failed");
+            }
+        }
+    }
+    dev_free(ctx, G);
+    dev_free(ctx, off);
+    dev_free(ctx, aux);
+    return st == GIQLB_OK ? end_call(ctx) : st;
+}
+
+extern "C" int giqlb_merge_shard(giqlb_ctx* ctx, giqlb_index* X, int64_t distance, uint32_t carry, int32_t* out_code, int32_t* out_start,
+                                 int32_t* out_end, int64_t* out_count, int64_t capacity, int64_t* n_out_host, int64_t* head_host) {
+    if (!ctx || !X || !n_out_host || !head_host || capacity < 0) return giqlb_fail(ctx, GIQLB_ERR_INVALID, "merge_shard: bad argument");
+    begin_call(ctx);
+    GIQLB_TRY(shard_index_ok(ctx, X, "merge_shard"));
+    *n_out_host = 0;
+    head_host[0] = 0; head_host[1] = -1; head_host[2] = 0;
+    const int64_t n = X->n;
+    if (n == 0) return end_call(ctx);
+    GIQLB_TRY(giqlb_index_ensure_pmax(ctx, X));
+    const long long d = distance > 0 ? (long long)distance : 0;
+    const LayoutView V = view_of(X->layout);
+    uint32_t* G = nullptr;
+    long long* head = reinterpret_cast<long long*>(ctx->d_scalars + 12);   // [3] head rows, code, end; then [15] region count
+    int st = dev_alloc(ctx, &G, (size_t)n);
+    if (st == GIQLB_OK) {
+        PhaseSpan ps(ctx, GIQLB_PH_CLUSTER);
+        st = running_count(ctx, X, 0, n, d, G, carry);
+        if (st == GIQLB_OK) {
+            merge_head_kernel<<<1, 32, 0, ctx->stream>>>(X->gs, X->pmax, G, n, V, head);
+            ctx->launches_this_call++;
+            ctx->stats.kernels_total++;
+            cudaMemcpyAsync(ctx->h_scalars + 4, G + n - 1, 4, cudaMemcpyDeviceToHost, ctx->stream);
+            st = fetch_scalars(ctx, head, 3);
+        }
+    }
+    int64_t total = 0;
+    if (st == GIQLB_OK) {
+        head_host[0] = ctx->h_scalars[0];   // rows of the head fragment
+        head_host[1] = ctx->h_scalars[1];   // its chromosome code (-1: no head)
+        head_host[2] = ctx->h_scalars[2];   // its max end, table coordinates
+        total = (int64_t)(ctx->h_scalars[4] & 0xffffffffll);
+        *n_out_host = total;
+        if (total > capacity) st = giqlb_fail(ctx, GIQLB_ERR_CAPACITY, "merge_shard: %lld regions exceed capacity %lld", (long long)total, (long long)capacity);
+        else if (total > 0 && (!out_code || !out_start || !out_end)) st = giqlb_fail(ctx, GIQLB_ERR_INVALID, "merge_shard: null output");
+    }
+    if (st == GIQLB_OK && total > 0) {
+        PhaseSpan ps(ctx, GIQLB_PH_MERGE);
+        if (out_count) cudaMemsetAsync(out_count, 0, (size_t)total * 8, ctx->stream);
+        merge_emit_kernel<<<grid_of(ctx, n, 4), 256, 0, ctx->stream>>>(X->gs, X->pmax, G, n, V, 0, 0, out_code, out_start, out_end, (long long*)out_count);
+        ctx->launches_this_call++;
+        ctx->stats.kernels_total++;
+        if (cudaGetLastError() != cudaSuccess) st = giqlb_fail(ctx, GIQLB_ERR_CUDA, "merge_shard: launch failed");
+    }
+    dev_free(ctx, G);
+    return st == GIQLB_OK ? end_call(ctx) : st;
 }

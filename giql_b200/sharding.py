@@ -166,3 +166,160 @@ class GenomeRangeShard:
         ls = [everything[g, 0, : res.counts[g]] for g in range(self.world)]
         rs = [everything[g, 1, : res.counts[g]] for g in range(self.world)]
         return torch.cat(ls), torch.cat(rs)
+
+
+# ---- CLUSTER / MERGE over genome-range shards ------------------------------------------------------
+# A shard owns the rows whose START lies in its range.  Two tiny exchanges stitch the shards together:
+#   * the running max of end over each shard (one number per rank): the carry of rank g is the max over ranks < g;
+#   * CLUSTER: the number of clusters each shard starts per chromosome -> id offsets;
+#     MERGE:   each shard's head fragment (rows continuing a region of an earlier shard) -> folded into the last
+#              region of the nearest earlier shard that starts one.
+# ops interface (EngineOps below; a numpy stand-in in the CPU tests):
+#   ops.cm_plan(table, world) -> plan;  ops.cm_max_end(plan, g) -> int
+#   ops.cm_cluster_counts(plan, g, distance, carry) -> list[int] (per chromosome code)
+#   ops.cm_cluster_ids(plan, g, distance, carry, offsets) -> int32 tensor [n rows of the table], 0 outside the shard
+#   ops.cm_merge(plan, g, distance, carry) -> (regions: dict of equally long tensors code/start/end/count,
+#                                              head: (rows, code, end))
+
+def carry_before(max_ends: list[int], g: int) -> int:
+    """Running max of end over the shards before g (0 when there is none)."""
+    return max(max_ends[:g], default=0)
+
+
+def id_offsets(counts_per_rank: list[list[int]], g: int) -> list[int]:
+    """Clusters started by the shards before g, per chromosome code."""
+    n_codes = len(counts_per_rank[0]) if counts_per_rank else 0
+    return [sum(counts_per_rank[h][c] for h in range(g)) for c in range(n_codes)]
+
+
+def stitch_heads(infos: list[tuple[int, int, int, int]]) -> list[tuple[int, Optional[int]]]:
+    """infos[g] = (regions started by shard g, head rows, head chromosome code, head max end).  Returns, per shard,
+    (extra rows, extra max end or None) to fold into the shard's LAST region: the head fragments of the later shards
+    that continue it (a head continues the last region of the nearest earlier shard that starts one)."""
+    out: list[list] = [[0, None] for _ in infos]
+    for g, (_, head_rows, _, head_end) in enumerate(infos):
+        if head_rows <= 0:
+            continue
+        h = g - 1
+        while h >= 0 and infos[h][0] == 0:
+            h -= 1
+        if h < 0:
+            raise ValueError(f"shard {g} continues a region but no earlier shard starts one")
+        out[h][0] += head_rows
+        out[h][1] = head_end if out[h][1] is None else max(out[h][1], head_end)
+    return [(a, b) for a, b in out]
+
+
+def _all_gather_ints(vec: list[int], world: int, device, group=None) -> list[list[int]]:
+    if world == 1 or not dist.is_initialized():
+        return [list(vec)]
+    mine = torch.tensor(vec, dtype=torch.int64, device=device)
+    allv = torch.empty(world * len(vec), dtype=torch.int64, device=device)
+    dist.all_gather_into_tensor(allv, mine, group=group)
+    flat = allv.cpu().tolist()
+    return [flat[r * len(vec):(r + 1) * len(vec)] for r in range(world)]
+
+
+def sharded_cluster(ops, rank: int, world: int, table, distance: int = 0, group=None) -> torch.Tensor:
+    """Global CLUSTER ids of this rank's rows (0 for rows owned by other ranks)."""
+    plan = ops.cm_plan(table, world)
+    try:
+        max_ends = [v[0] for v in _all_gather_ints([ops.cm_max_end(plan, rank)], world, ops.device, group)]
+        carry = carry_before(max_ends, rank)
+        counts = _all_gather_ints(ops.cm_cluster_counts(plan, rank, distance, carry), world, ops.device, group)
+        return ops.cm_cluster_ids(plan, rank, distance, carry, id_offsets(counts, rank))
+    finally:
+        if hasattr(ops, "cm_release"):
+            ops.cm_release(plan)
+
+
+def sharded_merge(ops, rank: int, world: int, table, distance: int = 0, group=None) -> dict:
+    """The merged regions that START in this rank's genome range, with the rows of later shards that continue the
+    last one folded in.  Returns a dict of equally long tensors: code, start, end, count."""
+    plan = ops.cm_plan(table, world)
+    try:
+        max_ends = [v[0] for v in _all_gather_ints([ops.cm_max_end(plan, rank)], world, ops.device, group)]
+        carry = carry_before(max_ends, rank)
+        regions, head = ops.cm_merge(plan, rank, distance, carry)
+        n_regions = int(regions["start"].numel())
+        infos = [tuple(v) for v in _all_gather_ints([n_regions, head[0], head[1], head[2]], world, ops.device, group)]
+        extra_rows, extra_end = stitch_heads(infos)[rank]
+        if extra_rows:
+            regions["count"][-1] += extra_rows
+            regions["end"][-1] = max(int(regions["end"][-1]), int(extra_end))
+        return regions
+    finally:
+        if hasattr(ops, "cm_release"):
+            ops.cm_release(plan)
+
+
+def _engine_cm_plan(self, table, world):
+    from .engine import _Layout
+
+    d = self.e.encode(table)
+    lay = _Layout(self.e, len(d))
+    lay.observe(table, raw=True)
+    lay.finalize()
+    cuts = (ctypes.c_uint32 * (world + 1))()
+    mw = ctypes.c_uint32()
+    self.e._check(self.e.lib.giqlb_shard_cuts(self.e.ctx, lay.h, table.codes.data_ptr(), table.start.data_ptr(), table.end.data_ptr(),
+                                              table.n, 0, 0, world, cuts, ctypes.byref(mw)))
+    return {"layout": lay, "cuts": list(cuts), "table": table, "index": {}, "n_codes": len(d)}
+
+
+def _engine_cm_index(self, plan, g):
+    from .engine import _Index
+
+    if g not in plan["index"]:
+        t, lay = plan["table"], plan["layout"]
+        rows = self.e._empty(t.n, torch.int32)
+        n_out = ctypes.c_int64()
+        self.e._check(self.e.lib.giqlb_shard_select(self.e.ctx, lay.h, t.codes.data_ptr(), t.start.data_ptr(), t.end.data_ptr(), t.n, 0, 0,
+                                                    plan["cuts"][g], plan["cuts"][g + 1], 0, rows.data_ptr(), ctypes.byref(n_out)))
+        plan["index"][g] = _Index(self.e, lay, t, raw=True, rows=rows[: n_out.value])
+    return plan["index"][g]
+
+
+def _engine_cm_max_end(self, plan, g):
+    v = ctypes.c_uint32()
+    self.e._check(self.e.lib.giqlb_shard_max_end(self.e.ctx, _engine_cm_index(self, plan, g).h, ctypes.byref(v)))
+    return int(v.value)
+
+
+def _engine_cm_cluster_counts(self, plan, g, distance, carry):
+    counts = (ctypes.c_uint32 * max(plan["n_codes"], 1))()
+    self.e._check(self.e.lib.giqlb_cluster_shard(self.e.ctx, _engine_cm_index(self, plan, g).h, int(distance or 0), carry, None, None, counts))
+    return list(counts)[: plan["n_codes"]]
+
+
+def _engine_cm_cluster_ids(self, plan, g, distance, carry, offsets):
+    ids = torch.zeros(plan["table"].n, dtype=torch.int32, device=self.e.device)
+    off = (ctypes.c_uint32 * max(plan["n_codes"], 1))(*offsets)
+    self.e._check(self.e.lib.giqlb_cluster_shard(self.e.ctx, _engine_cm_index(self, plan, g).h, int(distance or 0), carry, off,
+                                                 ids.data_ptr(), None))
+    return ids
+
+
+def _engine_cm_merge(self, plan, g, distance, carry):
+    ix = _engine_cm_index(self, plan, g)
+    n = int(self.e.lib.giqlb_index_rows(ix.h))
+    code, start, end = (self.e._empty(n, torch.int32) for _ in range(3))
+    count = self.e._empty(n, torch.int64)
+    m, head = ctypes.c_int64(), (ctypes.c_int64 * 3)()
+    self.e._check(self.e.lib.giqlb_merge_shard(self.e.ctx, ix.h, int(distance or 0), carry, code.data_ptr(), start.data_ptr(), end.data_ptr(),
+                                               count.data_ptr(), n, ctypes.byref(m), head))
+    k = m.value
+    return {"code": code[:k], "start": start[:k], "end": end[:k], "count": count[:k]}, (int(head[0]), int(head[1]), int(head[2]))
+
+
+def _engine_cm_release(self, plan):
+    for ix in plan["index"].values():
+        ix.free()
+    plan["layout"].free()
+
+
+import ctypes  # noqa: E402  (only the Engine-backed ops need it)
+
+for _cls in (EngineOps, EngineOpsStepwise):
+    _cls.cm_plan, _cls.cm_max_end, _cls.cm_cluster_counts = _engine_cm_plan, _engine_cm_max_end, _engine_cm_cluster_counts
+    _cls.cm_cluster_ids, _cls.cm_merge, _cls.cm_release = _engine_cm_cluster_ids, _engine_cm_merge, _engine_cm_release

@@ -274,6 +274,22 @@ int giqlb_disjoin(giqlb_ctx* ctx, const giqlb_layout* lay, const int32_t* t_code
                   int self_reference, int32_t* out_row, int32_t* out_start, int32_t* out_end, int64_t capacity,
                   int64_t* n_out_host);
 
+/* Genome-range shards of CLUSTER / MERGE.  X indexes the rows whose start lies in the shard's range
+ * (giqlb_shard_select + giqlb_index_build_rows, raw coordinates, unstranded).  `carry` = max over the EARLIER shards
+ * of giqlb_shard_max_end() (0 for the first shard): the running max of end of everything before this shard.
+ *   cluster_shard(): counts_by_code_host (nullable, [n_codes]) <- clusters this shard STARTS per chromosome; with
+ *     id_offset_by_code_host ([n_codes]: clusters started by earlier shards per chromosome) it writes the global
+ *     1-based ids of the shard's rows into cluster_id_by_input_row (rows of other shards are not touched).
+ *   merge_shard(): the regions that START in this shard (their end / count may still grow by the head fragments of
+ *     later shards) and, in head_host[3], the shard's head fragment — rows that continue a region of an earlier
+ *     shard: {row count, chromosome code or -1, max end in table coordinates}.  The host stitches heads onto the
+ *     last region of the nearest earlier shard that starts one (giql_b200/sharding.py). */
+int giqlb_shard_max_end(giqlb_ctx* ctx, giqlb_index* X, uint32_t* max_end_host);
+int giqlb_cluster_shard(giqlb_ctx* ctx, giqlb_index* X, int64_t distance, uint32_t carry, const uint32_t* id_offset_by_code_host,
+                        int32_t* cluster_id_by_input_row, uint32_t* counts_by_code_host);
+int giqlb_merge_shard(giqlb_ctx* ctx, giqlb_index* X, int64_t distance, uint32_t carry, int32_t* out_code, int32_t* out_start,
+                      int32_t* out_end, int64_t* out_count, int64_t capacity, int64_t* n_out_host, int64_t* head_host);
+
 /* ---- genome-range sharding of a join across GPUs ------------------------------
  * Every rank holds both tables and the same finalized layout.  shard_cuts(): histogram of the LEFT
  * table's linearised starts -> cuts_host[world + 1] (cuts[0] = 0, cuts[world] = 2^32 - 1) such that every

@@ -467,3 +467,36 @@ def test_contains_within_joins_vs_oracle(seed, engine):
     Y = {"chrom": ["chr1", "chr1"], "start": [10, 20], "end": [20, 30]}
     assert eb.spatial_pairs(X, Y, "contains") == [(0, 0), (1, 0)] == eb.spatial_pairs(X, Y, "within")
     assert eb.spatial_pairs(X, {"chrom": [], "start": [], "end": []}, "contains") == []
+
+
+# ---- CLUSTER / MERGE over genome-range shards (§8(e)): every rank on ONE GPU in turn, exchanges emulated --------------------
+@pytest.mark.parametrize("world,distance", [(2, 0), (5, 0), (8, 40)])
+def test_sharded_cluster_merge_equal_single_gpu(world, distance, engine, c_oracle):
+    import torch
+
+    from giql_b200 import synth
+    from giql_b200.sharding import EngineOps, carry_before, id_offsets, stitch_heads
+
+    R = synth.reads(400_000, 61)
+    t = engine.table_from_codes(R["code"], R["start"], R["end"], R["names"])
+    ops = EngineOps(engine)
+    plan = ops.cm_plan(t, world)
+    max_ends = [ops.cm_max_end(plan, g) for g in range(world)]                                   # all-gather 1
+    carries = [carry_before(max_ends, g) for g in range(world)]
+    counts = [ops.cm_cluster_counts(plan, g, distance, carries[g]) for g in range(world)]         # all-gather 2
+    ids = sum(ops.cm_cluster_ids(plan, g, distance, carries[g], id_offsets(counts, g)) for g in range(world))
+    exp_ids = c_oracle.cluster(R["code"], R["start"], R["end"], len(R["names"]), distance=distance)
+    assert np.array_equal(ids.cpu().numpy(), exp_ids)
+    parts = [ops.cm_merge(plan, g, distance, carries[g]) for g in range(world)]
+    infos = [(int(reg["start"].numel()), *head) for reg, head in parts]                          # all-gather 3
+    extra = stitch_heads(infos)
+    rows = []
+    for g, (reg, _) in enumerate(parts):
+        if extra[g][0]:
+            reg["count"][-1] += extra[g][0]
+            reg["end"][-1] = max(int(reg["end"][-1]), extra[g][1])
+        rows += list(zip(reg["code"].tolist(), reg["start"].tolist(), reg["end"].tolist(), reg["count"].tolist()))
+    ops.cm_release(plan)
+    op, os_, oe, oc = c_oracle.merge(R["code"], R["start"], R["end"], len(R["names"]), distance=distance)
+    assert sorted(rows) == sorted(zip(op.tolist(), os_.tolist(), oe.tolist(), oc.tolist()))
+    assert sum(r[3] for r in rows) == t.n

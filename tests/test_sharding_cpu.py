@@ -95,3 +95,109 @@ def test_shard_ranges_cover_the_genome_once():
 def test_sharded_pairs_offsets():
     r = ShardedPairs(torch.zeros(3, dtype=torch.int32), torch.zeros(3, dtype=torch.int32), [5, 3, 0, 7], 1)
     assert r.offsets == [0, 5, 8, 8] and r.global_total == 15 and r.global_offset == 5
+
+
+# ---- CLUSTER / MERGE shards over gloo with a numpy stand-in ------------------------------------------------------------------
+class NumpyClusterOps:
+    """cm_* ops of giql_b200.sharding over numpy (TEST stand-in): linear coordinate = (code << 32) + position."""
+
+    device = torch.device("cpu")
+
+    def cm_plan(self, T, world):
+        ks = (T["code"].astype(np.int64) << 32) + T["start"]
+        order = np.argsort(ks, kind="stable")
+        n = len(ks)
+        cuts = [0] + [int(ks[order][min(-(-g * n // world), n - 1)]) for g in range(1, world)] + [1 << 62]
+        return {"T": T, "ks": ks, "order": order, "cuts": cuts, "n_codes": int(T["code"].max()) + 1}
+
+    def _rows(self, plan, g):
+        o = plan["order"]
+        k = plan["ks"][o]
+        return o[(k >= plan["cuts"][g]) & (k < plan["cuts"][g + 1])]
+
+    def cm_max_end(self, plan, g):
+        r = self._rows(plan, g)
+        T = plan["T"]
+        return int(((T["code"][r].astype(np.int64) << 32) + T["end"][r]).max()) if len(r) else 0
+
+    def _flags(self, plan, g, distance, carry):
+        T, r = plan["T"], self._rows(plan, g)
+        d = max(int(distance), 0)
+        run, flags = carry, []
+        for i in r:
+            c, s, e = int(T["code"][i]), int(T["start"][i]), int(T["end"][i])
+            prev_in_chrom = (run >> 32) == c and run > 0
+            flags.append(0 if prev_in_chrom and (run & 0xFFFFFFFF) + d >= s else 1)
+            run = max(run, (c << 32) + e)
+        return r, np.array(flags, dtype=np.int64)
+
+    def cm_cluster_counts(self, plan, g, distance, carry):
+        r, f = self._flags(plan, g, distance, carry)
+        return np.bincount(plan["T"]["code"][r], weights=f, minlength=plan["n_codes"]).astype(np.int64).tolist()
+
+    def cm_cluster_ids(self, plan, g, distance, carry, offsets):
+        r, f = self._flags(plan, g, distance, carry)
+        ids = torch.zeros(len(plan["T"]["start"]), dtype=torch.int32)
+        run = dict(enumerate(offsets))
+        for i, fl in zip(r, f):
+            c = int(plan["T"]["code"][i])
+            run[c] += int(fl)
+            ids[int(i)] = run[c]
+        return ids
+
+    def cm_merge(self, plan, g, distance, carry):
+        T = plan["T"]
+        r, f = self._flags(plan, g, distance, carry)
+        regs, head = [], [0, -1, 0]
+        for i, fl in zip(r, f):
+            c, s, e = int(T["code"][i]), int(T["start"][i]), int(T["end"][i])
+            if fl:
+                regs.append([c, s, e, 1])
+            elif regs:
+                regs[-1][2] = max(regs[-1][2], e)
+                regs[-1][3] += 1
+            else:
+                head = [head[0] + 1, c, max(head[2], e)]
+        cols = list(zip(*regs)) if regs else [(), (), (), ()]
+        return ({"code": torch.tensor(cols[0], dtype=torch.int32), "start": torch.tensor(cols[1], dtype=torch.int32),
+                 "end": torch.tensor(cols[2], dtype=torch.int32), "count": torch.tensor(cols[3], dtype=torch.int64)}, tuple(head))
+
+
+def _cm_worker(rank, world, port, out):
+    from giql_b200.sharding import sharded_cluster, sharded_merge
+
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        T = synth.reads(6000, 9)
+        ops = NumpyClusterOps()
+        ids = sharded_cluster(ops, rank, world, T, distance=30)
+        reg = sharded_merge(ops, rank, world, T, distance=30)
+        out[rank] = {"ids": ids.numpy(), "regions": [tuple(int(v) for v in r) for r in zip(reg["code"], reg["start"], reg["end"], reg["count"])]}
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world", [2, 3])
+def test_sharded_cluster_merge_over_gloo(world):
+    from oracle import c_oracle
+
+    c_oracle.build()
+    out = mp.Manager().dict()
+    mp.spawn(_cm_worker, args=(world, _free_port(), out), nprocs=world, join=True)
+    T = synth.reads(6000, 9)
+    ids = sum(out[r]["ids"] for r in range(world))
+    assert np.array_equal(ids, c_oracle.cluster(T["code"], T["start"], T["end"], 24, distance=30))
+    op, os_, oe, oc = c_oracle.merge(T["code"], T["start"], T["end"], 24, distance=30)
+    got = sorted(r for k in range(world) for r in out[k]["regions"])
+    assert got == sorted(zip(op.tolist(), os_.tolist(), oe.tolist(), oc.tolist()))
+
+
+def test_stitch_and_offsets_helpers():
+    from giql_b200.sharding import carry_before, id_offsets, stitch_heads
+
+    assert stitch_heads([(3, 0, -1, 0), (0, 5, 1, 900), (2, 4, 1, 950), (1, 0, -1, 0)]) == [(9, 950), (0, None), (0, None), (0, None)]
+    assert id_offsets([[1, 2], [0, 3], [4, 0]], 2) == [1, 5] and id_offsets([[1, 2]], 0) == [0, 0]
+    assert carry_before([5, 9, 2], 0) == 0 and carry_before([5, 9, 2], 2) == 9
+    with pytest.raises(ValueError):
+        stitch_heads([(0, 2, 0, 10)])
