@@ -43,7 +43,9 @@ __device__ __forceinline__ uint64_t mix64(uint64_t h) {
     return h ^ (h >> 33);
 }
 // hash of a name: names of <= 16 bytes hash their two zero-padded words, longer names all their bytes
-__device__ __forceinline__ uint64_t hash_short(uint64_t w0, uint64_t w1, int len) { return mix64(w0 ^ mix64(w1 + (uint64_t)len)); }
+__device__ __forceinline__ uint64_t hash_short(uint64_t w0, uint64_t w1, int len) {
+    return (w0 ^ (w1 * 0x9E3779B97F4A7C15ull) ^ (uint64_t)len) * 0xff51afd7ed558ccdull;   // high bits are the well-mixed ones
+}
 __device__ __forceinline__ uint64_t hash_long(const uint8_t* __restrict__ p, int len) {
     uint64_t h = 1469598103934665603ull;
     for (int i = 0; i < len; i++) {
@@ -69,7 +71,7 @@ __device__ __forceinline__ bool same_bytes(const uint8_t* __restrict__ a, const 
 __device__ __forceinline__ uint32_t global_resolve(const StrTable& A, const StrTable& B, unsigned long long* __restrict__ slots,
                                                    uint32_t cap_mask, const uint8_t* __restrict__ s, int len, uint64_t h, int64_t g,
                                                    unsigned int* __restrict__ n_distinct) {
-    uint32_t slot = (uint32_t)h & cap_mask;
+    uint32_t slot = (uint32_t)(h >> 24) & cap_mask;
     for (uint32_t probes = 0; probes <= cap_mask; probes++) {
         unsigned long long w = *(volatile unsigned long long*)&slots[slot];
         if (w == 0) {
@@ -90,21 +92,19 @@ __device__ __forceinline__ uint32_t global_resolve(const StrTable& A, const StrT
     return cap_mask;   // table full: cannot happen, the host keeps the load factor <= 1/2 and re-runs otherwise
 }
 
-struct CacheEntry {
-    uint64_t w0, w1;
-    int32_t len;
-    uint32_t slot;
-};
+constexpr uint32_t DI_EMPTY = 0xFFFFFFFFu, DI_PENDING = 0xFFFFFFFEu;
 
 __global__ void __launch_bounds__(DI_THREADS)
 dict_insert_kernel(StrTable A, StrTable B, unsigned long long* __restrict__ slots, uint32_t cap_mask,
                    int32_t* __restrict__ slot_a, int32_t* __restrict__ slot_b, unsigned int* __restrict__ n_distinct) {
-    __shared__ int32_t s_offs[DI_ROWS + 1];
+    __shared__ __align__(16) int32_t s_offs[DI_ROWS + 4];
     __shared__ __align__(16) uint8_t s_bytes[DI_BYTES + 32];
-    __shared__ CacheEntry s_cache[DI_CACHE];
-    __shared__ int s_state[DI_CACHE];   // 0 empty, 1 being written, 2 ready
+    // per-CTA cache of resolved names (open addressing): key words, length, global slot (DI_EMPTY / DI_PENDING / slot)
+    __shared__ unsigned long long s_k0[DI_CACHE], s_k1[DI_CACHE];
+    __shared__ uint32_t s_slot[DI_CACHE];
+    __shared__ uint8_t s_len[DI_CACHE];
 
-    for (int i = threadIdx.x; i < DI_CACHE; i += DI_THREADS) s_state[i] = 0;
+    for (int i = threadIdx.x; i < DI_CACHE; i += DI_THREADS) s_slot[i] = DI_EMPTY;
     const int64_t chunks_a = (A.n + DI_ROWS - 1) / DI_ROWS, chunks_b = (B.n + DI_ROWS - 1) / DI_ROWS;
     for (int64_t chunk = blockIdx.x; chunk < chunks_a + chunks_b; chunk += gridDim.x) {
         const bool in_b = chunk >= chunks_a;
@@ -112,7 +112,12 @@ dict_insert_kernel(StrTable A, StrTable B, unsigned long long* __restrict__ slot
         const int64_t r0 = (in_b ? chunk - chunks_a : chunk) * DI_ROWS;
         const int rows = (int)min((int64_t)DI_ROWS, T.n - r0);
         __syncthreads();   // previous chunk's readers are done with s_offs / s_bytes
-        for (int i = threadIdx.x; i <= rows; i += DI_THREADS) s_offs[i] = T.offs[r0 + i];
+        if (rows == DI_ROWS && (reinterpret_cast<uintptr_t>(T.offs) & 15) == 0) {   // r0 is a multiple of 1024: aligned 16-byte loads
+            reinterpret_cast<int4*>(s_offs)[threadIdx.x] = __ldg(reinterpret_cast<const int4*>(T.offs + r0) + threadIdx.x);
+            if (threadIdx.x == 0) s_offs[DI_ROWS] = T.offs[r0 + DI_ROWS];
+        } else {
+            for (int i = threadIdx.x; i <= rows; i += DI_THREADS) s_offs[i] = T.offs[r0 + i];
+        }
         __syncthreads();
         const int32_t b0 = s_offs[0], b1 = s_offs[rows];
         const int32_t a0 = b0 & ~15;                       // staged range starts at a 16-byte boundary of the byte buffer
@@ -123,59 +128,55 @@ dict_insert_kernel(StrTable A, StrTable B, unsigned long long* __restrict__ slot
             for (int i = threadIdx.x; i < n_vec; i += DI_THREADS) reinterpret_cast<uint4*>(s_bytes)[i] = ld_stream_u32x4(src + i);
         }
         __syncthreads();
+        int32_t* out = (in_b ? slot_b : slot_a) + r0;
         for (int k = threadIdx.x; k < rows; k += DI_THREADS) {
             const int32_t o = s_offs[k], len = s_offs[k + 1] - o;
             const int64_t g = (in_b ? A.n : 0) + r0 + k;
-            uint32_t slot;
+            uint32_t slot = DI_EMPTY;
             if (staged && len <= 16) {
                 // the name as two zero-padded little-endian words, from aligned 32-bit shared loads
                 const int so = o - a0;
                 const uint32_t* wp = reinterpret_cast<const uint32_t*>(s_bytes) + (so >> 2);
                 const int sh = (so & 3) * 8;
-                const uint32_t t0 = wp[0], t1 = wp[1], t2 = wp[2], t3 = wp[3], t4 = wp[4];
-                uint32_t v0 = __funnelshift_r(t0, t1, sh), v1 = __funnelshift_r(t1, t2, sh);
-                uint32_t v2 = __funnelshift_r(t2, t3, sh), v3 = __funnelshift_r(t3, t4, sh);
-                uint64_t w0 = (uint64_t)v0 | ((uint64_t)v1 << 32), w1 = (uint64_t)v2 | ((uint64_t)v3 << 32);
-                if (len < 8) {
-                    w0 &= len ? (~0ull >> (64 - 8 * len)) : 0ull;
-                    w1 = 0;
-                } else if (len < 16) {
-                    w1 &= len > 8 ? (~0ull >> (64 - 8 * (len - 8))) : 0ull;
+                const uint32_t t0 = wp[0], t1 = wp[1], t2 = wp[2];
+                uint64_t w0 = (uint64_t)__funnelshift_r(t0, t1, sh) | ((uint64_t)__funnelshift_r(t1, t2, sh) << 32), w1 = 0;
+                if (len > 8) {
+                    const uint32_t t3 = wp[3], t4 = wp[4];
+                    w1 = (uint64_t)__funnelshift_r(t2, t3, sh) | ((uint64_t)__funnelshift_r(t3, t4, sh) << 32);
+                    if (len < 16) w1 &= ~0ull >> (64 - 8 * (len - 8));
+                } else {
+                    w0 &= len == 8 ? ~0ull : ((1ull << (8 * len)) - 1ull);
                 }
                 const uint64_t h = hash_short(w0, w1, len);
-                // per-CTA cache (open addressing; duplicates of one name are harmless)
-                int ci = (int)(h >> 40) & (DI_CACHE - 1);
-                bool hit = false;
+                int ci = (int)(h >> 57);                   // DI_CACHE == 128
                 int free_at = -1;
                 for (int p = 0; p < DI_CACHE; p++) {
-                    const int stt = *(volatile int*)&s_state[ci];
-                    if (stt == 0) {
+                    const uint32_t v = *(volatile uint32_t*)&s_slot[ci];
+                    if (v == DI_EMPTY) {
                         free_at = ci;
                         break;
                     }
-                    if (stt == 2) {
-                        const CacheEntry& e = s_cache[ci];
-                        if (e.len == len && e.w0 == w0 && e.w1 == w1) {
-                            slot = e.slot;
-                            hit = true;
-                            break;
-                        }
+                    if (v != DI_PENDING && s_k0[ci] == w0 && s_len[ci] == len && s_k1[ci] == w1) {
+                        slot = v;
+                        break;
                     }
                     ci = (ci + 1) & (DI_CACHE - 1);
                 }
-                if (!hit) {
+                if (slot == DI_EMPTY) {
                     slot = global_resolve(A, B, slots, cap_mask, T.bytes + o, len, h, g, n_distinct);
-                    if (free_at >= 0 && atomicCAS(&s_state[free_at], 0, 1) == 0) {
-                        s_cache[free_at] = CacheEntry{w0, w1, len, slot};
+                    if (free_at >= 0 && atomicCAS(&s_slot[free_at], DI_EMPTY, DI_PENDING) == DI_EMPTY) {
+                        s_k0[free_at] = w0;
+                        s_k1[free_at] = w1;
+                        s_len[free_at] = (uint8_t)len;
                         __threadfence_block();
-                        *(volatile int*)&s_state[free_at] = 2;
+                        *(volatile uint32_t*)&s_slot[free_at] = slot;
                     }
                 }
             } else {
-                const uint8_t* s = T.bytes + o;
-                slot = global_resolve(A, B, slots, cap_mask, s, len, hash_global_name(s, len), g, n_distinct);
+                const uint8_t* sp = T.bytes + o;
+                slot = global_resolve(A, B, slots, cap_mask, sp, len, hash_global_name(sp, len), g, n_distinct);
             }
-            (in_b ? slot_b : slot_a)[r0 + k] = (int32_t)slot;
+            out[k] = (int32_t)slot;
         }
     }
 }

@@ -131,6 +131,7 @@ layout_finalize_kernel(const long long* __restrict__ lohi, int32_t n_codes, long
 }
 
 // linearised start key + linearised end (unsorted), degenerate-row counters
+template <bool HIST>
 __global__ void __launch_bounds__(256)
 index_keygen_kernel(const int32_t* __restrict__ code, const int32_t* __restrict__ start,
                     const int32_t* __restrict__ end, const int32_t* __restrict__ rows /* nullable: row selection */,
@@ -140,8 +141,8 @@ index_keygen_kernel(const int32_t* __restrict__ code, const int32_t* __restrict_
                     unsigned long long* __restrict__ counters /* [0] end<=start [1] end<start [2] outside layout */,
                     uint32_t* __restrict__ ghist /* nullable: [4][256] digit counts of the start keys, for the sort */,
                     int* __restrict__ err) {
-    __shared__ uint32_t s_hist[4][256];
-    if (ghist) {
+    __shared__ uint32_t s_hist[HIST ? 4 : 1][256];
+    if (HIST) {
         for (int i = threadIdx.x; i < 4 * 256; i += blockDim.x) (&s_hist[0][0])[i] = 0;
         __syncthreads();
     }
@@ -167,14 +168,14 @@ index_keygen_kernel(const int32_t* __restrict__ code, const int32_t* __restrict_
         }
         gs[i] = ks;
         ge[i] = ke;
-        if (ghist) {
+        if (HIST) {
             atomicAdd(&s_hist[0][ks & 255u], 1u);
-            atomicAdd(&s_hist[1][(ks >> 8) & 255u], 1u);
-            atomicAdd(&s_hist[2][(ks >> 16) & 255u], 1u);
-            atomicAdd(&s_hist[3][ks >> 24], 1u);
+            atomicAdd(&s_hist[HIST ? 1 : 0][(ks >> 8) & 255u], 1u);
+            atomicAdd(&s_hist[HIST ? 2 : 0][(ks >> 16) & 255u], 1u);
+            atomicAdd(&s_hist[HIST ? 3 : 0][ks >> 24], 1u);
         }
     }
-    if (ghist) {
+    if (HIST) {
         __syncthreads();
         for (int i = threadIdx.x; i < 4 * 256; i += blockDim.x) {
             const uint32_t c = (&s_hist[0][0])[i];
@@ -490,8 +491,12 @@ int giqlb_index_build_impl(giqlb_ctx* ctx, const giqlb_layout* lay, const int32_
         int result_in_b = 0;
         if (!pre) {
         PhaseSpan ps(ctx, GIQLB_PH_KEYGEN);
-        index_keygen_kernel<<<grid_for(ctx, n, 256 * 4, 8), 256, 0, ctx->stream>>>(
-            code, start, end, rows, n, lay->n_codes, start_adj, end_adj, lay->d_base, lay->d_lo32, lay->d_hi32, ka, ge_u, counters, key_hist, ctx->d_err);
+        if (key_hist)
+            index_keygen_kernel<true><<<grid_for(ctx, n, 256 * 4, 8), 256, 0, ctx->stream>>>(
+                code, start, end, rows, n, lay->n_codes, start_adj, end_adj, lay->d_base, lay->d_lo32, lay->d_hi32, ka, ge_u, counters, key_hist, ctx->d_err);
+        else
+            index_keygen_kernel<false><<<grid_for(ctx, n, 256 * 4, 8), 256, 0, ctx->stream>>>(
+                code, start, end, rows, n, lay->n_codes, start_adj, end_adj, lay->d_base, lay->d_lo32, lay->d_hi32, ka, ge_u, counters, nullptr, ctx->d_err);
         ctx->launches_this_call++;
         ctx->stats.kernels_total++;
         }

@@ -392,10 +392,11 @@ struct __align__(16) TileSmem {
     uint32_t tile;
 };
 
-struct TileSlots {                           // fused kernel (tiles of <= J_BIG pairs): slot -> item lookup
-    uint16_t off[JT + 2];                    // local exclusive output offsets of the tile's items (merge order), then the total
-    uint16_t code[JT];                       // run start | class of every item
-    uint16_t first_item[J_BIG / J_OPT + 2];  // item that owns the first slot of every J_OPT-slot chunk
+struct TileSlots {                           // fused kernel (tiles of <= J_BIG pairs): slot -> item lookup over the NON-EMPTY items
+    uint16_t off[JT + 2];                    // local exclusive output offsets of the non-empty items (merge order), then the total
+    uint16_t code[JT];                       // run start | class
+    uint16_t own[JT];                        // the item's index in its own table's window
+    uint16_t first_item[J_BIG / J_OPT + 2];  // non-empty item that owns the first slot of every J_OPT-slot chunk
 };
 struct TileOffsets {                         // big-tile kernel: per-item offsets for the slot -> item search
     unsigned long long off[JT + 1];          // local exclusive output offsets of the tile's items (merge order)
@@ -403,7 +404,8 @@ struct TileOffsets {                         // big-tile kernel: per-item offset
 };
 
 __device__ __forceinline__ void bar_wait(unsigned long long* bar, uint32_t parity) {
-    while (!cuda::ptx::mbarrier_try_wait_parity(reinterpret_cast<uint64_t*>(bar), parity)) {
+    // the hint lets the hardware park the warp instead of spinning on the barrier while the bulk copies land
+    while (!cuda::ptx::mbarrier_try_wait_parity(reinterpret_cast<uint64_t*>(bar), parity, 2000u)) {
     }
 }
 
@@ -441,7 +443,7 @@ __device__ __forceinline__ void tile_stage(TileSmem& sm, const TileGeom& g, cons
 // The thread's J_IPT consecutive rows of the tile's merge sequence: run start/class codes and exact run lengths.
 // Branch-free in the class: the row's own table and the other table are selected by index.
 __device__ __forceinline__ void tile_runs(const TileSmem& sm, const TileGeom& g, const JoinSide& L, const JoinSide& R,
-                                          uint32_t (&code)[J_IPT], uint32_t (&cnt)[J_IPT]) {
+                                          uint32_t (&code)[J_IPT], uint32_t (&cnt)[J_IPT], bool* leaves_window = nullptr) {
     const uint32_t* gsl = sm.gs[0] + (g.x0 & 3);
     const uint32_t* gsr = sm.gs[1] + (g.y0 & 3);
     const uint32_t* gel = sm.ge[0] + (g.x0 & 3);
@@ -480,7 +482,10 @@ __device__ __forceinline__ void tile_runs(const TileSmem& sm, const TileGeom& g,
             if (h == wy) {                                   // the run may continue beyond the staged window
                 const uint32_t* yg = take_l ? R.gs : L.gs;
                 const int64_t yn = take_l ? R.n : L.n, ybase = take_l ? g.y0 : g.x0;
-                if (ybase + wy < yn) c = lb_gallop(yg, ybase + wy, yn, xge) - (ybase + start);
+                if (ybase + wy < yn) {
+                    c = lb_gallop(yg, ybase + wy, yn, xge) - (ybase + start);
+                    if (leaves_window && c > wy - start) *leaves_window = true;
+                }
             }
             code[k] = (uint32_t)start | (take_l ? 0u : J_CLASS_B);
             cnt[k] = (uint32_t)c;
@@ -564,26 +569,32 @@ __device__ __forceinline__ int32_t other_rid(const int32_t* win, int w_len, cons
     return idx < w_len ? win[idx] : __ldg(glob + base + idx);
 }
 
-// Item table of the tile: offsets, codes, and for every chunk of J_OPT output slots the item owning its first slot
-// (written by that item itself, so the expansion below needs no search).
+// Item table of the tile over its NON-EMPTY items (compacted with the item count that rides in the high bits of the
+// block scan): offsets, codes, own indexes, and for every chunk of J_OPT output slots the entry owning its first slot
+// (written by that item itself, so the expansion below needs no search and its walk never meets an empty item).
 __device__ __forceinline__ void tile_slot_table(TileSlots& ts, const uint32_t (&code)[J_IPT], const uint32_t (&cnt)[J_IPT], uint32_t ex,
-                                                uint32_t tot) {
-    uint32_t o = ex;
+                                                uint32_t ex_items, uint32_t tot, uint32_t tot_items) {
+    uint32_t o = ex, ci = ex_items;
 #pragma unroll
     for (int k = 0; k < J_IPT; k++) {
+        if (cnt[k] == 0) continue;
         const int item = threadIdx.x * J_IPT + k;
-        ts.off[item] = (uint16_t)o;
-        ts.code[item] = (uint16_t)code[k];
-        for (uint32_t q = (o + J_OPT - 1) / J_OPT; q * J_OPT < o + cnt[k]; q++) ts.first_item[q] = (uint16_t)item;
+        ts.off[ci] = (uint16_t)o;
+        ts.code[ci] = (uint16_t)code[k];
+        ts.own[ci] = (uint16_t)(item - (int)(code[k] & 0x7FFFu));
+        for (uint32_t q = (o + J_OPT - 1) / J_OPT; q * J_OPT < o + cnt[k]; q++) ts.first_item[q] = (uint16_t)ci;
         o += cnt[k];
+        ci++;
     }
     if (threadIdx.x == JB - 1) {
-        ts.off[JT] = (uint16_t)tot;       // tot <= J_BIG < 2^16
-        ts.off[JT + 1] = 0xFFFFu;         // sentinel: the walk below never leaves the table
+        ts.off[tot_items] = (uint16_t)tot;       // tot <= J_BIG < 2^16
+        ts.off[tot_items + 1] = 0xFFFFu;         // sentinel: the walk below never leaves the table
     }
 }
 
 // Expands output slots [w0, w0 + n) of the tile into the staging window: a thread owns J_OPT consecutive slots.
+// CHECKED = some run of the tile leaves the staged row-id windows (rare): those slots read global memory.
+template <bool CHECKED>
 __device__ __forceinline__ void tile_expand(TileSmem& sm, const TileSlots& ts, const TileGeom& g, const JoinSide& L, const JoinSide& R,
                                             uint32_t w0, uint32_t n) {
     int32_t* stage_l = reinterpret_cast<int32_t*>(&sm.gs[0][0]);
@@ -591,23 +602,26 @@ __device__ __forceinline__ void tile_expand(TileSmem& sm, const TileSlots& ts, c
     const int32_t* lrid = sm.rid[0] + (g.x0 & 3);
     const int32_t* rrid = sm.rid[1] + (g.y0 & 3);
     for (uint32_t s0 = w0 + threadIdx.x * J_OPT; s0 < w0 + n; s0 += JB * J_OPT) {
-        int item = ts.first_item[s0 / J_OPT];
+        uint32_t ci = ts.first_item[s0 / J_OPT];
+        uint32_t next = ts.off[ci + 1];
 #pragma unroll
         for (int q = 0; q < J_OPT; q++) {
             const uint32_t sl = s0 + q;
             if (sl < w0 + n) {
-                while (ts.off[item + 1] <= sl) item++;              // skip finished and empty items
-                const uint32_t cd = ts.code[item];
-                const int start = (int)(cd & 0x7FFFu);
-                const int w = start + (int)(sl - ts.off[item]);     // offset into the other table's window
-                const int own = item - start;
+                if (sl >= next) {                                   // exactly one step: entries are non-empty
+                    ci++;
+                    next = ts.off[ci + 1];
+                }
+                const uint32_t cd = ts.code[ci];
+                const int w = (int)(cd & 0x7FFFu) + (int)(sl - ts.off[ci]);   // offset into the other table's window
+                const int own = ts.own[ci];
                 int32_t vl, vr;
                 if (!(cd & J_CLASS_B)) {                            // item is an L row; its run lies in R
                     vl = lrid[own];
-                    vr = w < g.wr ? rrid[w] : __ldg(R.rid + g.y0 + w);
+                    vr = (!CHECKED || w < g.wr) ? rrid[w] : __ldg(R.rid + g.y0 + w);
                 } else {                                            // item is an R row; its run lies in L
                     vr = rrid[own];
-                    vl = w < g.wl ? lrid[w] : __ldg(L.rid + g.x0 + w);
+                    vl = (!CHECKED || w < g.wl) ? lrid[w] : __ldg(L.rid + g.x0 + w);
                 }
                 stage_l[sl - w0] = vl;
                 stage_r[sl - w0] = vr;
@@ -661,12 +675,16 @@ join_fused_kernel(JoinSide L, JoinSide R, const int32_t* __restrict__ part, int6
     if (threadIdx.x == 0) tile_stage(sm, g, L, R);
     bar_wait(&sm.bar[0], 0);
     uint32_t code[J_IPT], cnt[J_IPT];
-    tile_runs(sm, g, L, R, code, cnt);
+    bool leaves = false;
+    tile_runs(sm, g, L, R, code, cnt, &leaves);
+    // one block scan carries both the pair count (low 40 bits: < 1024 * 2^30) and the non-empty item count (high bits)
     unsigned long long sum = 0;
 #pragma unroll
-    for (int k = 0; k < J_IPT; k++) sum += cnt[k];
-    unsigned long long tot;
-    const unsigned long long ex64 = block_excl_scan_add<unsigned long long>(sum, sm.scratch, &tot);   // two barriers: gs / ge are dead now
+    for (int k = 0; k < J_IPT; k++) sum += (unsigned long long)cnt[k] + (cnt[k] ? (1ull << 40) : 0ull);
+    unsigned long long tot_packed;
+    const unsigned long long ex_packed = block_excl_scan_add<unsigned long long>(sum, sm.scratch, &tot_packed);   // two barriers: gs / ge are dead now
+    const unsigned long long tot = tot_packed & ((1ull << 40) - 1), ex64 = ex_packed & ((1ull << 40) - 1);
+    const uint32_t tot_items = (uint32_t)(tot_packed >> 40), ex_items = (uint32_t)(ex_packed >> 40);
     if (threadIdx.x == JB - 1) {
         // The last thread publishes the tile's count and sums the counts of the tiles before it (decoupled look-back)
         // while the other warps already expand the tile into shared memory.
@@ -705,12 +723,13 @@ join_fused_kernel(JoinSide L, JoinSide R, const int32_t* __restrict__ part, int6
     if (tot == 0 || tot > (unsigned long long)J_BIG) return;
     const bool vec_ok = ((reinterpret_cast<uintptr_t>(out_l) | reinterpret_cast<uintptr_t>(out_r)) & 15) == 0;
     const uint32_t tot32 = (uint32_t)tot;
-    tile_slot_table(ts, code, cnt, (uint32_t)ex64, tot32);
-    __syncthreads();                           // item table complete
+    tile_slot_table(ts, code, cnt, (uint32_t)ex64, ex_items, tot32, tot_items);
+    const bool checked = __syncthreads_or(leaves);   // item table complete; does any run leave the staged windows?
     static_assert(J_STAGE % J_OPT == 0, "windows start on chunk boundaries");
     for (uint32_t w0 = 0; w0 < tot32; w0 += J_STAGE) {
         const uint32_t n = min((uint32_t)J_STAGE, tot32 - w0);
-        tile_expand(sm, ts, g, L, R, w0, n);
+        if (checked) tile_expand<true>(sm, ts, g, L, R, w0, n);
+        else tile_expand<false>(sm, ts, g, L, R, w0, n);
         __syncthreads();                       // staging window complete (and, first time round, sm.tile_off published)
         const unsigned long long off_t = sm.tile_off;
         if (off_t + tot > (unsigned long long)capacity) return;   // the caller's buffer is too small: write nothing

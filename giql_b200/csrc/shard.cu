@@ -3,7 +3,7 @@
 // The pair predicate never crosses chromosomes (abdenlab/giql src/giql/expanders/intersects.py:151) and the
 // DuckDB plan already evaluates it per chromosome (src/giql/expanders/intersects_duckdb.py:1283-1299), so the
 // join shards by contiguous ranges of the linearised genome.  Every rank holds both tables; it
-//   1. histograms the LEFT table's linearised starts in 2^16-cell bins and cuts the genome into `world`
+//   1. histograms the LEFT table's linearised starts in 2^19-cell bins and cuts the genome into `world`
 //      ranges holding equal numbers of left rows (giqlb_shard_cuts — identical on every rank, no exchange),
 //   2. selects the left rows whose START lies in its range — each left row has exactly one owner, so no
 //      pair is ever produced twice — and the right rows that can overlap that range; right rows straddling
@@ -15,7 +15,8 @@
 
 namespace {
 
-constexpr int SH_BIN_SHIFT = 16;
+constexpr int SH_BIN_SHIFT = 19;            // 2^19-cell bins: at most 8192 of them, a shared-memory histogram per CTA
+constexpr int SH_MAX_BINS = 8192;
 constexpr int SH_THREADS = 256;
 
 // exact linearisation of a row of an OBSERVED table (no clamping); false when the row lies outside the layout
@@ -33,6 +34,9 @@ __device__ __forceinline__ bool row_linearise(const ProbeCols& P, int64_t i, uin
 
 __global__ void __launch_bounds__(SH_THREADS)
 shard_hist_kernel(ProbeCols P, uint32_t* __restrict__ hist, uint32_t* __restrict__ max_width, int* __restrict__ err) {
+    __shared__ uint32_t s_hist[SH_MAX_BINS];
+    for (int i = threadIdx.x; i < SH_MAX_BINS; i += SH_THREADS) s_hist[i] = 0;
+    __syncthreads();
     uint32_t mw = 0;
     bool bad = false;
     for (int64_t i = (int64_t)blockIdx.x * SH_THREADS + threadIdx.x; i < P.n; i += (int64_t)gridDim.x * SH_THREADS) {
@@ -41,13 +45,16 @@ shard_hist_kernel(ProbeCols P, uint32_t* __restrict__ hist, uint32_t* __restrict
             bad = true;
             continue;
         }
-        atomicAdd(&hist[gs >> SH_BIN_SHIFT], 1u);
+        atomicAdd(&s_hist[gs >> SH_BIN_SHIFT], 1u);
         if (ge > gs && ge - gs > mw) mw = ge - gs;
     }
 #pragma unroll
     for (int d = 16; d > 0; d >>= 1) mw = max(mw, __shfl_xor_sync(FULL_MASK, mw, d));
     if (lane_id() == 0 && mw) atomicMax(max_width, mw);
     if (bad) err[2] = 1;
+    __syncthreads();
+    for (int i = threadIdx.x; i < SH_MAX_BINS; i += SH_THREADS)
+        if (s_hist[i]) atomicAdd(&hist[i], s_hist[i]);
 }
 
 // one CTA: every thread owns a contiguous chunk of bins (serial sums, ONE block scan) and records, for
@@ -217,7 +224,7 @@ extern "C" int giqlb_shard_cuts(giqlb_ctx* ctx, const giqlb_layout* lay, const i
     cudaMemsetAsync(cuts, 0, ((size_t)world + 1) * 8, ctx->stream);
     if (n > 0) {
         PhaseSpan ps(ctx, GIQLB_PH_SHARD);
-        int64_t blocks = ceil_div(n, SH_THREADS * 8), cap = (int64_t)ctx->sm_count * 8;
+        int64_t blocks = ceil_div(n, SH_THREADS * 8), cap = (int64_t)ctx->sm_count * 2;
         shard_hist_kernel<<<(unsigned)(blocks < cap ? blocks : cap), SH_THREADS, 0, ctx->stream>>>(P, hist, hist + n_bins, ctx->d_err);
         ctx->launches_this_call++;
         ctx->stats.kernels_total++;
@@ -331,8 +338,8 @@ extern "C" int giqlb_intersects_tables_sharded(giqlb_ctx* ctx, giqlb_table_t* L,
             PhaseSpan ps(ctx, GIQLB_PH_SHARD);
             const int64_t cap = (int64_t)ctx->sm_count * 8;
             if (L->n > 0) {
-                int64_t blocks = ceil_div(L->n, SH_THREADS * 8);
-                shard_hist_kernel<<<(unsigned)(blocks < cap ? blocks : cap), SH_THREADS, 0, ctx->stream>>>(P[0], hist, hist + n_bins, ctx->d_err);
+                int64_t blocks = ceil_div(L->n, SH_THREADS * 8), hcap = (int64_t)ctx->sm_count * 2;
+                shard_hist_kernel<<<(unsigned)(blocks < hcap ? blocks : hcap), SH_THREADS, 0, ctx->stream>>>(P[0], hist, hist + n_bins, ctx->d_err);
                 shard_cuts_kernel<<<1, 1024, 0, ctx->stream>>>(hist, n_bins, L->n, world, cuts64);
                 ctx->launches_this_call += 2;
                 ctx->stats.kernels_total += 2;

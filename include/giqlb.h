@@ -292,7 +292,7 @@ int giqlb_merge_shard(giqlb_ctx* ctx, giqlb_index* X, int64_t distance, uint32_t
 
 /* ---- genome-range sharding of a join across GPUs ------------------------------
  * Every rank holds both tables and the same finalized layout.  shard_cuts(): histogram of the LEFT
- * table's linearised starts -> cuts_host[world + 1] (cuts[0] = 0, cuts[world] = 2^32 - 1) such that every
+ * table's linearised starts (2^19-cell bins) -> cuts_host[world + 1] (cuts[0] = 0, cuts[world] = 2^32 - 1) such that every
  * range [cuts[g], cuts[g+1]) holds ~n/world left rows; max_width_host = widest left interval (cells).
  * Deterministic: every rank computes identical cuts without any exchange.
  * shard_select(): ids of the rows with  gs_lo <= linear start < gs_hi  AND  linear end > ge_gt, in unspecified order
