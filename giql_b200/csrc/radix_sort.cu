@@ -161,6 +161,22 @@ rs_onesweep_kernel(const uint32_t* __restrict__ keys_in, const uint32_t* __restr
     uint32_t gstart = block_excl_scan_add<uint32_t>(ghist[d_own], s_scan, &gtot);
     s_digit_excl[d_own] = dex;
 
+    __syncthreads();   // s_digit_excl and the warp-exclusive offsets are complete
+
+    // scatter the tile into shared memory in digit order FIRST: it needs only tile-local offsets, and it gives the
+    // preceding tiles time to publish their counts before this tile looks back
+#pragma unroll
+    for (int i = 0; i < RS_IPT; i++) {
+        uint32_t d = (key[i] >> shift) & 255u;
+        uint32_t pos = s_digit_excl[d] + s_warp_hist[w][d] + rank[i];
+        int li = warp_off + i * 32 + l;
+        uint32_t v;
+        if (IDENTITY_VALS) v = (uint32_t)(tile_base + li);
+        else v = li < tile_n ? ld_stream_u32(vals_in + tile_base + li) : 0u;
+        s_keys[pos] = key[i];
+        s_vals[pos] = v;
+    }
+
     // decoupled look-back over earlier tiles for digit d_own
     uint32_t prefix = 0;
     if (tile > 0) {
@@ -181,20 +197,6 @@ rs_onesweep_kernel(const uint32_t* __restrict__ keys_in, const uint32_t* __restr
         *(volatile uint32_t*)my_status = ST_FLAG_INCL | (prefix + count);
     }
     s_global_base[d_own] = (int32_t)(gstart + prefix - dex);
-    __syncthreads();
-
-    // scatter the tile into shared memory in digit order
-#pragma unroll
-    for (int i = 0; i < RS_IPT; i++) {
-        uint32_t d = (key[i] >> shift) & 255u;
-        uint32_t pos = s_digit_excl[d] + s_warp_hist[w][d] + rank[i];
-        int li = warp_off + i * 32 + l;
-        uint32_t v;
-        if (IDENTITY_VALS) v = (uint32_t)(tile_base + li);
-        else v = li < tile_n ? ld_stream_u32(vals_in + tile_base + li) : 0u;
-        s_keys[pos] = key[i];
-        s_vals[pos] = v;
-    }
     __syncthreads();
     // write out: consecutive slots of one digit are consecutive in global memory
     for (int j = threadIdx.x; j < tile_n; j += RS_THREADS) {
