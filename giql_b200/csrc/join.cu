@@ -596,12 +596,12 @@ __device__ __forceinline__ void tile_slot_table(TileSlots& ts, const uint32_t (&
 // CHECKED = some run of the tile leaves the staged row-id windows (rare): those slots read global memory.
 template <bool CHECKED>
 __device__ __forceinline__ void tile_expand(TileSmem& sm, const TileSlots& ts, const TileGeom& g, const JoinSide& L, const JoinSide& R,
-                                            uint32_t w0, uint32_t n) {
+                                            uint32_t w0, uint32_t n, uint32_t n_threads) {
     int32_t* stage_l = reinterpret_cast<int32_t*>(&sm.gs[0][0]);
     int32_t* stage_r = stage_l + J_STAGE;
     const int32_t* lrid = sm.rid[0] + (g.x0 & 3);
     const int32_t* rrid = sm.rid[1] + (g.y0 & 3);
-    for (uint32_t s0 = w0 + threadIdx.x * J_OPT; s0 < w0 + n; s0 += JB * J_OPT) {
+    for (uint32_t s0 = w0 + threadIdx.x * J_OPT; s0 < w0 + n; s0 += n_threads * J_OPT) {
         uint32_t ci = ts.first_item[s0 / J_OPT];
         uint32_t next = ts.off[ci + 1];
 #pragma unroll
@@ -672,8 +672,11 @@ join_fused_kernel(JoinSide L, JoinSide R, const int32_t* __restrict__ part, int6
     __syncthreads();
     const int64_t t = sm.tile;
     const TileGeom g = tile_geom(part, t, L.n, R.n);
-    if (threadIdx.x == 0) tile_stage(sm, g, L, R);
-    bar_wait(&sm.bar[0], 0);
+    if (threadIdx.x == 0) {
+        tile_stage(sm, g, L, R);
+        bar_wait(&sm.bar[0], 0);               // one thread polls the barrier; the others sleep at the hardware barrier below
+    }
+    __syncthreads();
     uint32_t code[J_IPT], cnt[J_IPT];
     bool leaves = false;
     tile_runs(sm, g, L, R, code, cnt, &leaves);
@@ -685,56 +688,75 @@ join_fused_kernel(JoinSide L, JoinSide R, const int32_t* __restrict__ part, int6
     const unsigned long long ex_packed = block_excl_scan_add<unsigned long long>(sum, sm.scratch, &tot_packed);   // two barriers: gs / ge are dead now
     const unsigned long long tot = tot_packed & ((1ull << 40) - 1), ex64 = ex_packed & ((1ull << 40) - 1);
     const uint32_t tot_items = (uint32_t)(tot_packed >> 40), ex_items = (uint32_t)(ex_packed >> 40);
+    const bool big = tot > (unsigned long long)J_BIG;
+    volatile unsigned long long* st = status;
     if (threadIdx.x == JB - 1) {
-        // The last thread publishes the tile's count and sums the counts of the tiles before it (decoupled look-back)
-        // while the other warps already expand the tile into shared memory.
-        volatile unsigned long long* st = status;
-        unsigned long long prefix = 0;
-        if (t == 0) {
-            st[0] = JF_FLAG_INCL | tot;
-        } else {
-            st[t] = JF_FLAG_AGG | tot;
-            int64_t k = t - 1;
-            uint32_t spins = 0;
-            while (true) {
-                const unsigned long long s = st[k];
-                const unsigned long long flag = s & ~JF_VALUE_MASK;
-                if (flag == 0) {
-                    if (++spins > JF_SPIN_LIMIT) { *err_flag = 1; break; }
-                    __nanosleep(20);
-                    continue;
-                }
-                prefix += s & JF_VALUE_MASK;
-                if (flag == JF_FLAG_INCL) break;
-                k--;
-            }
-            st[t] = JF_FLAG_INCL | (prefix + tot);
-        }
-        sm.tile_off = prefix;
-        if (t == n_tiles - 1) totals[0] = prefix + tot;
-        if (tot > (unsigned long long)J_BIG) {   // shared among many CTAs by join_emit_big_kernel
-            const uint32_t slot = atomicAdd(big_count, 1u);
-            big_tile[slot] = (uint32_t)t;
-            big_off[slot] = prefix;
-            big_cnt[slot] = tot;
-        }
+        st[t] = (t == 0 ? JF_FLAG_INCL : JF_FLAG_AGG) | tot;   // publish the tile's count as early as possible
+        bar_wait(&sm.bar[1], 0);               // row ids have landed (also: never exit with bulk copies in flight)
     }
-    bar_wait(&sm.bar[1], 0);   // also before leaving: a CTA must not exit with bulk copies into its shared memory in flight
-    if (tot == 0 || tot > (unsigned long long)J_BIG) return;
-    const bool vec_ok = ((reinterpret_cast<uintptr_t>(out_l) | reinterpret_cast<uintptr_t>(out_r)) & 15) == 0;
     const uint32_t tot32 = (uint32_t)tot;
-    tile_slot_table(ts, code, cnt, (uint32_t)ex64, ex_items, tot32, tot_items);
-    const bool checked = __syncthreads_or(leaves);   // item table complete; does any run leave the staged windows?
+    if (!big && tot32) tile_slot_table(ts, code, cnt, (uint32_t)ex64, ex_items, tot32, tot_items);
+    const bool checked = __syncthreads_or(leaves);   // item table complete, row ids visible; does any run leave the staged windows?
+    const bool vec_ok = ((reinterpret_cast<uintptr_t>(out_l) | reinterpret_cast<uintptr_t>(out_r)) & 15) == 0;
+    constexpr uint32_t N_EXPAND = JB - 32;     // warps 0..6 expand the tile while the last warp looks back
     static_assert(J_STAGE % J_OPT == 0, "windows start on chunk boundaries");
+    if (threadIdx.x >= N_EXPAND) {
+        // The last warp sums the counts of the tiles before this one (decoupled look-back, 32 predecessors per step)
+        // while the other warps expand the tile.
+        const int lane = (int)lane_id();
+        unsigned long long prefix = 0;
+        int64_t base = t - 1;
+        bool done = t == 0;
+        uint32_t spins = 0;
+        while (!done) {
+            const int64_t k = base - lane;
+            unsigned long long sv = 2ull << 62;                      // before tile 0: an inclusive zero (= JF_FLAG_INCL)
+            if (k >= 0) sv = st[k];
+            while (__any_sync(FULL_MASK, (sv & ~JF_VALUE_MASK) == 0)) {   // a predecessor in the window has not published yet
+                if ((sv & ~JF_VALUE_MASK) == 0) {
+                    __nanosleep(20);
+                    sv = st[k];
+                }
+                if (++spins > JF_SPIN_LIMIT) {
+                    *err_flag = 1;
+                    sv |= JF_FLAG_INCL;
+                }
+            }
+            const uint32_t incl = __ballot_sync(FULL_MASK, (sv & ~JF_VALUE_MASK) == JF_FLAG_INCL);
+            const int first_incl = incl ? __ffs(incl) - 1 : 32;
+            prefix += warp_reduce_add<unsigned long long>(lane <= first_incl ? (sv & JF_VALUE_MASK) : 0ull);
+            if (incl) done = true;
+            else base -= 32;
+        }
+        if (lane == 31) {
+            if (t > 0) st[t] = JF_FLAG_INCL | (prefix + tot);
+            sm.tile_off = prefix;
+            if (t == n_tiles - 1) totals[0] = prefix + tot;
+            if (big) {   // shared among many CTAs by join_emit_big_kernel
+                const uint32_t slot = atomicAdd(big_count, 1u);
+                big_tile[slot] = (uint32_t)t;
+                big_off[slot] = prefix;
+                big_cnt[slot] = tot;
+            }
+        }
+    } else if (!big && tot32) {
+        const uint32_t n = min((uint32_t)J_STAGE, tot32);
+        if (checked) tile_expand<true>(sm, ts, g, L, R, 0, n, N_EXPAND);
+        else tile_expand<false>(sm, ts, g, L, R, 0, n, N_EXPAND);
+    }
+    __syncthreads();                           // first staging window complete, sm.tile_off published
+    if (big || tot32 == 0) return;
+    const unsigned long long off_t = sm.tile_off;
+    if (off_t + tot > (unsigned long long)capacity) return;   // the caller's buffer is too small: write nothing
     for (uint32_t w0 = 0; w0 < tot32; w0 += J_STAGE) {
         const uint32_t n = min((uint32_t)J_STAGE, tot32 - w0);
-        if (checked) tile_expand<true>(sm, ts, g, L, R, w0, n);
-        else tile_expand<false>(sm, ts, g, L, R, w0, n);
-        __syncthreads();                       // staging window complete (and, first time round, sm.tile_off published)
-        const unsigned long long off_t = sm.tile_off;
-        if (off_t + tot > (unsigned long long)capacity) return;   // the caller's buffer is too small: write nothing
+        if (w0) {                              // further windows (rare): everyone expands
+            __syncthreads();                   // the previous window has been flushed
+            if (checked) tile_expand<true>(sm, ts, g, L, R, w0, n, JB);
+            else tile_expand<false>(sm, ts, g, L, R, w0, n, JB);
+            __syncthreads();
+        }
         tile_flush(sm, off_t + w0, n, out_l, out_r, vec_ok);
-        if (w0 + J_STAGE < tot32) __syncthreads();   // the next window overwrites the staging area
     }
 }
 
