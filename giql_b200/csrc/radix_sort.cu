@@ -177,22 +177,33 @@ rs_onesweep_kernel(const uint32_t* __restrict__ keys_in, const uint32_t* __restr
         s_vals[pos] = v;
     }
 
-    // decoupled look-back over earlier tiles for digit d_own
+    // decoupled look-back over earlier tiles for digit d_own; four predecessors are fetched per step so that the
+    // chain of dependent L2 round trips is four times shorter
     uint32_t prefix = 0;
     if (tile > 0) {
         int64_t t = (int64_t)tile - 1;
         uint32_t spins = 0;
-        while (true) {
-            uint32_t s = *(volatile uint32_t*)(status + (size_t)t * RS_RADIX + d_own);
-            uint32_t flag = s & ~ST_VALUE_MASK;
-            if (flag == 0) {
+        bool done = false;
+        while (!done) {
+            uint32_t sv[4];
+#pragma unroll
+            for (int j = 0; j < 4; j++)
+                sv[j] = t - j >= 0 ? *(volatile uint32_t*)(status + (size_t)(t - j) * RS_RADIX + d_own) : (2u << 30);   // = ST_FLAG_INCL | 0
+            int used = 0;
+#pragma unroll
+            for (int j = 0; j < 4; j++) {
+                if (done || used != j) continue;
+                const uint32_t flag = sv[j] & ~ST_VALUE_MASK;
+                if (flag == 0) continue;              // not published yet: retry from this tile
+                prefix += sv[j] & ST_VALUE_MASK;
+                used = j + 1;
+                if (flag == ST_FLAG_INCL) done = true;
+            }
+            t -= used;
+            if (!done && used < 4) {
                 if (++spins > RS_SPIN_LIMIT) { *err_flag = 1; break; }
                 __nanosleep(20);
-                continue;
             }
-            prefix += s & ST_VALUE_MASK;
-            if (flag == ST_FLAG_INCL) break;
-            t--;
         }
         *(volatile uint32_t*)my_status = ST_FLAG_INCL | (prefix + count);
     }

@@ -69,41 +69,53 @@ scan_lookback_kernel(int64_t n, In in, Out out, unsigned long long* __restrict__
     if (l == 0) warp_excl = Op::identity();
     if (l == 31) s_warp[w] = incl;
     __syncthreads();
-    if (tid == 0) {
-        // serial scan over the 8 warp totals, then publish the tile aggregate and look back
-        T acc = Op::identity();
-        for (int ww = 0; ww < SC_THREADS / 32; ww++) {
-            T t = s_warp[ww];
-            s_warp[ww] = acc;
-            acc = Op::combine(acc, t);
-        }
+    if (w == 0) {
+        // lane 0: serial scan over the 8 warp totals, publish the tile aggregate.  Then the whole warp looks back,
+        // 32 predecessor tiles per step (lane j reads tile - 1 - j), combining in tile order.
         volatile unsigned long long* st = status;
-        T prefix = Op::identity();
-        if (tile == 0) {
-            st[0] = SC_FLAG_INCL | (unsigned long long)acc;
-        } else {
-            st[tile] = SC_FLAG_AGG | (unsigned long long)acc;
-            int64_t t = (int64_t)tile - 1;
-            uint32_t spins = 0;
-            // accumulate right-to-left: prefix = combine(status[t], prefix)
-            bool first = true;
-            while (true) {
-                unsigned long long s = st[t];
-                unsigned long long flag = s & ~SC_VALUE_MASK;
-                if (flag == 0) {
-                    if (++spins > SC_SPIN_LIMIT) { *err_flag = 1; break; }
-                    __nanosleep(20);
-                    continue;
-                }
-                T val = (T)(s & SC_VALUE_MASK);
-                prefix = first ? val : Op::combine(val, prefix);
-                first = false;
-                if (flag == SC_FLAG_INCL) break;
-                t--;
+        T acc = Op::identity();
+        if (l == 0) {
+            for (int ww = 0; ww < SC_THREADS / 32; ww++) {
+                T t = s_warp[ww];
+                s_warp[ww] = acc;
+                acc = Op::combine(acc, t);
             }
-            st[tile] = SC_FLAG_INCL | (unsigned long long)Op::combine(prefix, acc);
+            st[tile] = (tile == 0 ? SC_FLAG_INCL : SC_FLAG_AGG) | (unsigned long long)acc;
         }
-        s_prefix = prefix;
+        T prefix = Op::identity();
+        if (tile > 0) {
+            int64_t base = (int64_t)tile - 1;
+            uint32_t spins = 0;
+            bool done = false;
+            while (!done) {
+                const int64_t k = base - (int64_t)l;
+                unsigned long long sv = SC_FLAG_INCL | (unsigned long long)Op::identity();   // before tile 0
+                if (k >= 0) sv = st[k];
+                while (__any_sync(FULL_MASK, (sv & ~SC_VALUE_MASK) == 0)) {
+                    if ((sv & ~SC_VALUE_MASK) == 0) {
+                        __nanosleep(20);
+                        sv = st[k];
+                    }
+                    if (++spins > SC_SPIN_LIMIT) {
+                        *err_flag = 1;
+                        sv |= SC_FLAG_INCL;
+                    }
+                }
+                const uint32_t incl = __ballot_sync(FULL_MASK, (sv & ~SC_VALUE_MASK) == SC_FLAG_INCL);
+                const int first_incl = incl ? __ffs(incl) - 1 : 32;
+                T v = (int)l <= first_incl ? (T)(sv & SC_VALUE_MASK) : Op::identity();
+#pragma unroll
+                for (int d = 1; d < 32; d <<= 1) {   // lane j ends with combine(tile-1-31 .. tile-1-j): earlier tiles on the left
+                    T o = __shfl_down_sync(FULL_MASK, v, d);
+                    if (l + d < 32) v = Op::combine(o, v);
+                }
+                prefix = Op::combine(__shfl_sync(FULL_MASK, v, 0), prefix);
+                done = incl != 0;
+                base -= 32;
+            }
+            if (l == 0) st[tile] = SC_FLAG_INCL | (unsigned long long)Op::combine(prefix, acc);
+        }
+        if (l == 0) s_prefix = prefix;
     }
     __syncthreads();
     T excl = Op::combine(Op::combine(s_prefix, s_warp[w]), warp_excl);
