@@ -378,7 +378,8 @@ __device__ __forceinline__ T block_excl_scan_add(T v, T* scratch, T* total) {
 // ---- internal cross-file entry points ---------------------------------------------------------------
 int giqlb_radix_sort_pairs_u32(giqlb_ctx* ctx, uint32_t* keys_a, uint32_t* vals_a, uint32_t* keys_b,
                                uint32_t* vals_b, int64_t n, int begin_bit, int end_bit, int identity_vals,
-                               int* result_in_b, const uint32_t* hist_dev = nullptr);
+                               int* result_in_b, const uint32_t* hist_dev = nullptr, const uint32_t* gather_src = nullptr,
+                               uint32_t* gather_dst = nullptr);
 int giqlb_excl_scan_u64(giqlb_ctx* ctx, const unsigned long long* in, unsigned long long* out, int64_t n,
                         unsigned long long* total_dev);
 int giqlb_incl_scan_max_u32(giqlb_ctx* ctx, const uint32_t* in, uint32_t* out, int64_t n,

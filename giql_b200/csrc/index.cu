@@ -11,6 +11,9 @@
 
 namespace {
 
+#ifndef GIQLB_SORT_GATHERS_END
+#define GIQLB_SORT_GATHERS_END 0
+#endif
 #ifndef GIQLB_KEYGEN_HIST
 #define GIQLB_KEYGEN_HIST 0
 #endif
@@ -453,6 +456,7 @@ int giqlb_index_build_impl(giqlb_ctx* ctx, const giqlb_layout* lay, const int32_
 
     uint32_t *ka = nullptr, *kb = nullptr, *va = nullptr, *vb = nullptr, *ge_u = nullptr, *gs_u = nullptr;
     int32_t* pre_rows = nullptr;   // selection buffer handed over by a fused select + keygen pass
+    bool ge_gathered = false;      // the last sort pass already wrote ix->ge
     unsigned long long* counters = nullptr;
     uint32_t* key_hist = nullptr;
     int st = GIQLB_OK;
@@ -524,7 +528,11 @@ int giqlb_index_build_impl(giqlb_ctx* ctx, const giqlb_layout* lay, const int32_
             uint32_t* rk = r2 ? k3 : k2;
             result_in_b = (rk == kb) ? 1 : 0;
         } else {
-            IB_TRY(giqlb_radix_sort_pairs_u32(ctx, ka, va, kb, vb, n, 0, lay->key_bits, 1, &result_in_b, key_hist));
+            // (measured: letting the last pass gather the linear ends costs 34 us/pass and saves a 28 us gather kernel,
+            //  so the fused variant stays off)
+            IB_TRY(giqlb_radix_sort_pairs_u32(ctx, ka, va, kb, vb, n, 0, lay->key_bits, 1, &result_in_b, key_hist,
+                                              GIQLB_SORT_GATHERS_END ? ge_u : nullptr, GIQLB_SORT_GATHERS_END ? ix->ge : nullptr));
+            ge_gathered = GIQLB_SORT_GATHERS_END != 0;
         }
         if (result_in_b) {
             ix->gs = kb; ix->rid = reinterpret_cast<int32_t*>(vb);
@@ -534,11 +542,13 @@ int giqlb_index_build_impl(giqlb_ctx* ctx, const giqlb_layout* lay, const int32_
             ka = nullptr; va = nullptr;
         }
         PhaseSpan ps_g(ctx, GIQLB_PH_GATHER);
-        gather_kernel<uint32_t><<<grid_for(ctx, n, 256 * 4, 8), 256, 0, ctx->stream>>>(
-            ge_u, reinterpret_cast<const uint32_t*>(ix->rid), ix->ge, n);
-        ctx->launches_this_call++;
-        ctx->stats.kernels_total++;
-        IB_CUDA(cudaGetLastError());
+        if (!ge_gathered) {
+            gather_kernel<uint32_t><<<grid_for(ctx, n, 256 * 4, 8), 256, 0, ctx->stream>>>(
+                ge_u, reinterpret_cast<const uint32_t*>(ix->rid), ix->ge, n);
+            ctx->launches_this_call++;
+            ctx->stats.kernels_total++;
+            IB_CUDA(cudaGetLastError());
+        }
         if (rows) {   // positions in the selection -> caller's row ids
             remap_rows_kernel<<<grid_for(ctx, n, 256 * 4, 8), 256, 0, ctx->stream>>>(ix->rid, rows, n);
             ctx->launches_this_call++;

@@ -68,10 +68,13 @@ rs_histogram_kernel(const uint32_t* __restrict__ keys, int64_t n, int begin_bit,
 
 // ---- one digit pass ----------------------------------------------------------------------------------
 // IDENTITY_VALS: payload of key i is i itself (first pass; no payload array is read).
-template <bool IDENTITY_VALS>
+// GATHER: the last pass of an index build also fetches gather_src[payload] (the row's linear end) into
+// gather_dst at the row's sorted position, which saves the separate gather pass.
+template <bool IDENTITY_VALS, bool GATHER>
 __global__ void __launch_bounds__(RS_THREADS, RS_IPT >= 16 ? 4 : 6)
 rs_onesweep_kernel(const uint32_t* __restrict__ keys_in, const uint32_t* __restrict__ vals_in,
                    uint32_t* __restrict__ keys_out, uint32_t* __restrict__ vals_out, int64_t n, int shift,
+                   const uint32_t* __restrict__ gather_src, uint32_t* __restrict__ gather_dst,
                    const uint32_t* __restrict__ ghist /* this pass, [256] */,
                    uint32_t* __restrict__ status /* this pass, [tiles][256] */,
                    uint32_t* __restrict__ ticket, int* __restrict__ err_flag) {
@@ -214,8 +217,10 @@ rs_onesweep_kernel(const uint32_t* __restrict__ keys_in, const uint32_t* __restr
         uint32_t k = s_keys[j];
         uint32_t d = (k >> shift) & 255u;
         const int64_t out = (int64_t)(s_global_base[d] + j);
+        const uint32_t v = s_vals[j];
         keys_out[out] = k;
-        vals_out[out] = s_vals[j];
+        vals_out[out] = v;
+        if (GATHER) gather_dst[out] = __ldg(gather_src + v);
     }
 }
 
@@ -226,7 +231,7 @@ rs_onesweep_kernel(const uint32_t* __restrict__ keys_in, const uint32_t* __restr
 // i itself (vals_a is scratch and is not read by the first pass).
 int giqlb_radix_sort_pairs_u32(giqlb_ctx* ctx, uint32_t* keys_a, uint32_t* vals_a, uint32_t* keys_b,
                                uint32_t* vals_b, int64_t n, int begin_bit, int end_bit, int identity_vals,
-                               int* result_in_b, const uint32_t* hist_dev) {
+                               int* result_in_b, const uint32_t* hist_dev, const uint32_t* gather_src, uint32_t* gather_dst) {
     *result_in_b = 0;
     if (n >= (int64_t)ST_VALUE_MASK) return giqlb_fail(ctx, GIQLB_ERR_INVALID, "radix sort: n=%lld too large", (long long)n);
     int n_passes = (end_bit - begin_bit + 7) / 8;
@@ -260,10 +265,16 @@ int giqlb_radix_sort_pairs_u32(giqlb_ctx* ctx, uint32_t* keys_a, uint32_t* vals_
         const int shift = begin_bit + 8 * p;
         const uint32_t* gh = ghist + (size_t)p * RS_RADIX;
         uint32_t* st = status + (size_t)p * tiles * RS_RADIX;
-        if (p == 0 && identity_vals)
-            rs_onesweep_kernel<true><<<(unsigned)tiles, RS_THREADS, 0, ctx->stream>>>(kin, vin, kout, vout, n, shift, gh, st, tickets + p, ctx->d_err);
-        else
-            rs_onesweep_kernel<false><<<(unsigned)tiles, RS_THREADS, 0, ctx->stream>>>(kin, vin, kout, vout, n, shift, gh, st, tickets + p, ctx->d_err);
+        const bool gather = gather_src && gather_dst && p == n_passes - 1;
+#define RS_LAUNCH(IDV, GTH)                                                                                                        \
+    rs_onesweep_kernel<IDV, GTH><<<(unsigned)tiles, RS_THREADS, 0, ctx->stream>>>(kin, vin, kout, vout, n, shift, gather_src, gather_dst, \
+                                                                                  gh, st, tickets + p, ctx->d_err)
+        if (p == 0 && identity_vals) {
+            if (gather) RS_LAUNCH(true, true); else RS_LAUNCH(true, false);
+        } else {
+            if (gather) RS_LAUNCH(false, true); else RS_LAUNCH(false, false);
+        }
+#undef RS_LAUNCH
         LAUNCH_CHECK(ctx);
         uint32_t* t;
         t = kin; kin = kout; kout = t;
