@@ -21,12 +21,16 @@
 // the END of almost every run) in shared memory with coalesced loads, so every input row is read from HBM
 // once per pass and all searches run in shared memory; the rare run that leaves the window continues with a
 // galloping search in global memory.
-//   count pass : per-tile pair count                       (reads gs, ge of both tables)
-//   scan       : one CTA turns tile counts into pair offsets and emit work units; a tile whose output
-//                exceeds J_PART pairs is split into several units, so a skewed tile is shared by many CTAs
-//   emit pass  : persistent CTAs loop over the units, recompute the tile's runs and write their slice; each
-//                thread produces 8 CONSECUTIVE output pairs (one search in the tile's offset table, then a walk),
-//                stored as 16-byte vectors.
+// Two entry points share that tile machinery:
+//   giqlb_intersects_plan + _emit (exact-size, two passes)
+//     count pass : every thread merges 4 rows of the tile; writes one item code (run start, class, length) per
+//                  row and the tile's pair count
+//     scan       : one CTA turns tile counts into pair offsets and emit work units; a tile whose output exceeds
+//                  J_PART pairs is split into several units, so a skewed tile is shared by many CTAs
+//     emit pass  : persistent CTAs loop over the units, scan the item codes and write their slice; each thread
+//                  produces 8 CONSECUTIVE output pairs, stored as 16-byte vectors
+//   giqlb_intersects_join (caller brings the buffer; ONE pass — see "single-pass join" below): count, look-back
+//     offset and emit of a tile inside one kernel, TMA bulk staging, no item codes through HBM.
 //
 // General path (some row has end <= start): the literal predicate is scanned over the candidates
 //     j in [first j with pmax[j] > l.gs,  lower_bound(R.gs, l.ge))        pmax = running max of R.ge
@@ -37,8 +41,11 @@
 
 namespace {
 
-constexpr int JB = 256;             // threads per CTA
-constexpr int JT = 1024;            // merged rows per tile (fast path) / left rows per tile (general path)
+#ifndef GIQLB_JOIN_THREADS
+#define GIQLB_JOIN_THREADS 256
+#endif
+constexpr int JB = GIQLB_JOIN_THREADS;   // threads per CTA
+constexpr int JT = JB * 4;               // merged rows per tile (fast path) / left rows per tile (general path)
 constexpr int J_IPT = JT / JB;
 constexpr int J_EXT = 512;          // rows staged beyond the tile's own part of each table
 constexpr int JW = JT + J_EXT;      // staged window capacity per table
@@ -69,13 +76,6 @@ __device__ __forceinline__ int s_lower_bound(const uint32_t* a, int lo, int hi, 
     while (lo < hi) {
         int mid = (lo + hi) >> 1;
         if (a[mid] < x) lo = mid + 1; else hi = mid;
-    }
-    return lo;
-}
-__device__ __forceinline__ int s_upper_bound(const uint32_t* a, int lo, int hi, uint32_t x) {
-    while (lo < hi) {
-        int mid = (lo + hi) >> 1;
-        if (a[mid] <= x) lo = mid + 1; else hi = mid;
     }
     return lo;
 }
@@ -373,7 +373,7 @@ join_emit_kernel(JoinSide L, JoinSide R, const int32_t* __restrict__ part, int64
 // through HBM, and the capacity check is per tile (a tile that would overrun the buffer writes nothing; the
 // grand total tells the host how much room a retry needs).  Tiles whose output exceeds J_BIG pairs only
 // publish their offset and are emitted afterwards by a second kernel that shares each of them among many CTAs.
-constexpr int J_BIG = 8192;           // tiles with more pairs are shared among CTAs by join_emit_big_kernel
+constexpr int J_BIG = 8 * JT;          // tiles with more pairs are shared among CTAs by join_emit_big_kernel
 constexpr unsigned long long JF_FLAG_AGG = 1ull << 62;
 constexpr unsigned long long JF_FLAG_INCL = 2ull << 62;
 constexpr unsigned long long JF_VALUE_MASK = (1ull << 62) - 1;
@@ -564,11 +564,6 @@ __device__ __forceinline__ void tile_emit(const TileSmem& sm, const TileOffsets&
     }
 }
 
-// One row id of the "other" table's window (shared memory, or global memory beyond the staged extension)
-__device__ __forceinline__ int32_t other_rid(const int32_t* win, int w_len, const int32_t* __restrict__ glob, int64_t base, int idx) {
-    return idx < w_len ? win[idx] : __ldg(glob + base + idx);
-}
-
 // Item table of the tile over its NON-EMPTY items (compacted with the item count that rides in the high bits of the
 // block scan): offsets, codes, own indexes, and for every chunk of J_OPT output slots the entry owning its first slot
 // (written by that item itself, so the expansion below needs no search and its walk never meets an empty item).
@@ -661,8 +656,9 @@ join_fused_kernel(JoinSide L, JoinSide R, const int32_t* __restrict__ part, int6
                   int32_t* __restrict__ out_r, int64_t capacity, unsigned long long* __restrict__ totals /* [0] pairs */,
                   uint32_t* __restrict__ big_count, uint32_t* __restrict__ big_tile, unsigned long long* __restrict__ big_off,
                   unsigned long long* __restrict__ big_cnt, int* __restrict__ err_flag) {
-    __shared__ TileSmem sm;
-    __shared__ TileSlots ts;
+    extern __shared__ __align__(16) unsigned char dyn_smem[];   // > 48 KB with 512-thread tiles: dynamic, opted in by the host
+    TileSmem& sm = *reinterpret_cast<TileSmem*>(dyn_smem);
+    TileSlots& ts = *reinterpret_cast<TileSlots*>(dyn_smem + sizeof(TileSmem));
     if (threadIdx.x == 0) {
         sm.tile = atomicAdd(ticket, 1u);
         cuda::ptx::mbarrier_init(reinterpret_cast<uint64_t*>(&sm.bar[0]), 1);
@@ -767,8 +763,9 @@ join_emit_big_kernel(JoinSide L, JoinSide R, const int32_t* __restrict__ part, c
                      const uint32_t* __restrict__ big_tile, const unsigned long long* __restrict__ big_off,
                      const unsigned long long* __restrict__ big_cnt, int32_t* __restrict__ out_l, int32_t* __restrict__ out_r,
                      int64_t capacity) {
-    __shared__ TileSmem sm;
-    __shared__ TileOffsets so;
+    extern __shared__ __align__(16) unsigned char dyn_smem[];
+    TileSmem& sm = *reinterpret_cast<TileSmem*>(dyn_smem);
+    TileOffsets& so = *reinterpret_cast<TileOffsets*>(dyn_smem + sizeof(TileSmem));
     const uint32_t n_big = *big_count;
     if (n_big == 0) return;
     if (threadIdx.x == 0) {
@@ -1078,10 +1075,16 @@ extern "C" int giqlb_intersects_join(giqlb_ctx* ctx, giqlb_index* L, giqlb_index
                 ctx->stats.kernels_total++;
             }
             {
+                static bool smem_opted_in = false;   // per process: the kernels' dynamic shared memory limit
+                if (!smem_opted_in) {
+                    cudaFuncSetAttribute(join_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(TileSmem) + sizeof(TileSlots)));
+                    cudaFuncSetAttribute(join_emit_big_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(TileSmem) + sizeof(TileOffsets)));
+                    smem_opted_in = true;
+                }
                 PhaseSpan ps(ctx, GIQLB_PH_JOIN_EMIT);
-                join_fused_kernel<<<(unsigned)n_tiles, JB, 0, ctx->stream>>>(side_of(L), side_of(R), part, n_tiles, status, ticket, out_l, out_r,
+                join_fused_kernel<<<(unsigned)n_tiles, JB, sizeof(TileSmem) + sizeof(TileSlots), ctx->stream>>>(side_of(L), side_of(R), part, n_tiles, status, ticket, out_l, out_r,
                                                                              capacity, totals, big_count, big_tile, big_off, big_cnt, ctx->d_err);
-                join_emit_big_kernel<<<ctx->sm_count * 2, JB, 0, ctx->stream>>>(side_of(L), side_of(R), part, big_count, big_tile, big_off,
+                join_emit_big_kernel<<<ctx->sm_count * 2, JB, sizeof(TileSmem) + sizeof(TileOffsets), ctx->stream>>>(side_of(L), side_of(R), part, big_count, big_tile, big_off,
                                                                                 big_cnt, out_l, out_r, capacity);
                 cudaMemcpyAsync(ctx->h_scalars + 8, big_count, 4, cudaMemcpyDeviceToHost, ctx->stream);
                 ctx->launches_this_call += 2;
