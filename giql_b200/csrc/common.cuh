@@ -264,8 +264,10 @@ static inline int fetch_scalars_checked(giqlb_ctx* ctx, const void* d_src, int n
     CUDA_TRY(ctx, cudaMemcpyAsync(ctx->h_scalars + 60, ctx->d_err, 4 * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
     CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
     const int* e = reinterpret_cast<const int*>(ctx->h_scalars + 60);
-    if (e[0] || e[3]) {
+    if (e[0] || e[1] || e[3]) {
         cudaMemsetAsync(ctx->d_err, 0, 4 * sizeof(int), ctx->stream);
+        if (e[1] == 2) return giqlb_fail(ctx, GIQLB_ERR_RANGE, "layout: the summed chromosome extent does not fit the 32-bit linear coordinate");
+        if (e[1]) return giqlb_fail(ctx, GIQLB_ERR_RANGE, "layout: a row has a chromosome code outside the dictionary or a coordinate outside [-2^30, 2^31-4]");
         if (e[3]) return giqlb_fail(ctx, GIQLB_ERR_RANGE, "index: rows lie outside the layout (observe the table before finalize)");
         return giqlb_fail(ctx, GIQLB_ERR_INTERNAL, "look-back spin limit exceeded (kernel-side)");
     }
@@ -394,6 +396,9 @@ struct giqlb_prekeyed {
 int giqlb_index_build_impl(giqlb_ctx* ctx, const giqlb_layout* lay, const int32_t* code, const int32_t* start,
                            const int32_t* end, const uint8_t* strand, const int32_t* rows, int64_t n, int32_t start_adj,
                            int32_t end_adj, int flags, giqlb_prekeyed* pre, giqlb_index** out);
+int giqlb_layout_finalize_async(giqlb_ctx* ctx, giqlb_layout* lay);
+int giqlb_intersects_join_impl(giqlb_ctx* ctx, giqlb_index* L, giqlb_index* R, int32_t* out_l, int32_t* out_r, int64_t capacity,
+                               int64_t* total_host, bool speculative);
 int giqlb_index_ensure_pmax(giqlb_ctx* ctx, giqlb_index* ix);
 int giqlb_index_resolve(giqlb_ctx* ctx, giqlb_index* a, giqlb_index* b);
 int giqlb_index_ensure_end_sorted(giqlb_ctx* ctx, giqlb_index* ix);

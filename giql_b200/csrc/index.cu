@@ -100,7 +100,7 @@ __global__ void layout_init_kernel(long long* lohi, int32_t n_codes) {
 __global__ void __launch_bounds__(1024)
 layout_finalize_kernel(const long long* __restrict__ lohi, int32_t n_codes, long long pad,
                        uint32_t* __restrict__ base, int32_t* __restrict__ lo32, int32_t* __restrict__ hi32,
-                       unsigned long long* __restrict__ total) {
+                       unsigned long long* __restrict__ total, int* __restrict__ err) {
     __shared__ unsigned long long scratch[1024 / 32 + 2];
     unsigned long long carry = 0;
     for (int b0 = 0; b0 < n_codes; b0 += 1024) {
@@ -130,6 +130,7 @@ layout_finalize_kernel(const long long* __restrict__ lohi, int32_t n_codes, long
     if (threadIdx.x == 0) {
         base[n_codes] = carry > 0xffffffffull ? 0xffffffffu : (uint32_t)carry;
         *total = carry;
+        if (carry >= 0xffffffffull) err[1] = 2;   // the summed extent does not fit the 32-bit linear coordinate
     }
 }
 
@@ -302,6 +303,26 @@ extern "C" int giqlb_layout_observe(giqlb_ctx* ctx, giqlb_layout* lay, const int
     return end_call(ctx);
 }
 
+// finalize without a host round trip: the bases are computed on the device; the host assumes the widest key
+// (32 bits) and an overflowing extent or a bad row raises the sticky error flag that the next checked fetch reports.
+// The observed tables' degenerate-row counts stay on the device (indexes resolve them lazily).
+int giqlb_layout_finalize_async(giqlb_ctx* ctx, giqlb_layout* lay) {
+    if (!ctx || !lay) return giqlb_fail(ctx, GIQLB_ERR_INVALID, "layout_finalize: bad argument");
+    if (lay->finalized) return GIQLB_OK;
+    begin_call(ctx);
+    {
+        PhaseSpan ps(ctx, GIQLB_PH_LAYOUT);
+        layout_finalize_kernel<<<1, 1024, 0, ctx->stream>>>((const long long*)lay->d_lohi, lay->n_codes, (long long)lay->pad, lay->d_base,
+                                                            lay->d_lo32, lay->d_hi32, reinterpret_cast<unsigned long long*>(ctx->d_scalars + 2),
+                                                            ctx->d_err);
+        LAUNCH_CHECK(ctx);
+    }
+    lay->total_extent = 0xfffffffeull;   // upper bound
+    lay->key_bits = 32;
+    lay->finalized = true;
+    return end_call(ctx);
+}
+
 extern "C" int giqlb_layout_finalize(giqlb_ctx* ctx, giqlb_layout* lay) {
     if (!ctx || !lay) return giqlb_fail(ctx, GIQLB_ERR_INVALID, "layout_finalize: bad argument");
     if (lay->finalized) return GIQLB_OK;
@@ -310,7 +331,7 @@ extern "C" int giqlb_layout_finalize(giqlb_ctx* ctx, giqlb_layout* lay) {
     {
         PhaseSpan ps(ctx, GIQLB_PH_LAYOUT);
         layout_finalize_kernel<<<1, 1024, 0, ctx->stream>>>((const long long*)lay->d_lohi, lay->n_codes, (long long)lay->pad,
-                                                            lay->d_base, lay->d_lo32, lay->d_hi32, total);
+                                                            lay->d_base, lay->d_lo32, lay->d_hi32, total, ctx->d_err);
         LAUNCH_CHECK(ctx);
     }
     int h_err[4] = {0, 0, 0, 0};

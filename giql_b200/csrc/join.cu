@@ -1035,16 +1035,26 @@ extern "C" int giqlb_intersects_emit(giqlb_ctx* ctx, giqlb_joinplan* plan, int32
 
 extern "C" int giqlb_intersects_join(giqlb_ctx* ctx, giqlb_index* L, giqlb_index* R, int32_t* out_l, int32_t* out_r,
                                      int64_t capacity, int64_t* total_host) {
+    return giqlb_intersects_join_impl(ctx, L, R, out_l, out_r, capacity, total_host, false);
+}
+
+// speculative: when the degenerate-row counts of the indexes are still on the device, do not fetch them first —
+// run the fused (proper-interval) path, bring the counts back with the pair total, and fall back to the general
+// path only if a degenerate row turns up (the fused kernels are memory-safe on any input; their result is discarded).
+int giqlb_intersects_join_impl(giqlb_ctx* ctx, giqlb_index* L, giqlb_index* R, int32_t* out_l, int32_t* out_r, int64_t capacity,
+                               int64_t* total_host, bool speculative) {
     if (!ctx || !L || !R || capacity < 0 || (capacity > 0 && (!out_l || !out_r)))
         return giqlb_fail(ctx, GIQLB_ERR_INVALID, "intersects_join: bad argument");
     begin_call(ctx);
     if (L->layout != R->layout) return giqlb_fail(ctx, GIQLB_ERR_INVALID, "intersects: indexes were built on different layouts");
     if (L->grouped_by_strand || R->grouped_by_strand)
         return giqlb_fail(ctx, GIQLB_ERR_INVALID, "intersects: strand-grouped indexes are not accepted");
-    GIQLB_TRY(giqlb_index_resolve(ctx, L, R));
+    const bool empty = L->n == 0 || R->n == 0;
+    const bool speculate = speculative && !empty && (!L->resolved || !R->resolved);
+    if (!speculate) GIQLB_TRY(giqlb_index_resolve(ctx, L, R));
     int64_t total = 0;
     int st = GIQLB_OK;
-    if (L->n_degenerate + R->n_degenerate > 0 || L->n == 0 || R->n == 0) {
+    if (!speculate && (empty || L->n_degenerate + R->n_degenerate > 0)) {
         // degenerate rows: two-pass general path (the emit kernel writes nothing when the total exceeds `capacity`)
         giqlb_joinplan* p = nullptr;
         GIQLB_TRY(plan_enqueue(ctx, L, R, &p));
@@ -1092,8 +1102,24 @@ extern "C" int giqlb_intersects_join(giqlb_ctx* ctx, giqlb_index* L, giqlb_index
             }
             if (cudaGetLastError() != cudaSuccess) st = giqlb_fail(ctx, GIQLB_ERR_CUDA, "intersects_join: launch failed");
         }
+        giqlb_index* pending[2] = {!L->resolved ? L : nullptr, !R->resolved && R != L ? R : nullptr};
+        for (int k = 0; k < 2 && st == GIQLB_OK; k++)   // the degenerate-row counts ride along with the pair total
+            if (pending[k]) cudaMemcpyAsync(ctx->h_scalars + 32 + 4 * k, pending[k]->d_counters, 3 * 8, cudaMemcpyDeviceToHost, ctx->stream);
         if (st == GIQLB_OK) st = fetch_scalars_checked(ctx, totals, 1);
         total = st == GIQLB_OK ? ctx->h_scalars[0] : -1;
+        bool degenerate = false;
+        for (int k = 0; k < 2 && st == GIQLB_OK; k++) {
+            if (!pending[k]) continue;
+            pending[k]->n_degenerate = ctx->h_scalars[32 + 4 * k];
+            pending[k]->n_negative = ctx->h_scalars[33 + 4 * k];
+            pending[k]->resolved = true;
+            degenerate = degenerate || pending[k]->n_degenerate > 0;
+        }
+        if (st == GIQLB_OK && degenerate) {   // speculation failed: redo through the general path
+            dev_free(ctx, part);
+            dev_free(ctx, status);
+            return giqlb_intersects_join_impl(ctx, L, R, out_l, out_r, capacity, total_host, false);
+        }
         ctx->stats.reserved = (int32_t)(ctx->h_scalars[8] & 0xffffffff);   // tiles delegated to the big-tile kernel
         dev_free(ctx, part);
         dev_free(ctx, status);

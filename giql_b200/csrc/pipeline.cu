@@ -30,10 +30,10 @@ extern "C" int giqlb_intersects_tables(giqlb_ctx* ctx, giqlb_table_t* L, giqlb_t
     if (st == GIQLB_OK) st = giqlb_layout_create(ctx, n_codes, 0, &lay);
     if (st == GIQLB_OK) st = giqlb_layout_observe(ctx, lay, L->codes, L->start, L->end, L->n, L->start_adj, L->end_adj);
     if (st == GIQLB_OK && !same) st = giqlb_layout_observe(ctx, lay, R->codes, R->start, R->end, R->n, R->start_adj, R->end_adj);
-    if (st == GIQLB_OK) st = giqlb_layout_finalize(ctx, lay);
+    if (st == GIQLB_OK) st = giqlb_layout_finalize_async(ctx, lay);   // no round trip: errors surface with the pair total
     if (st == GIQLB_OK) st = giqlb_index_build(ctx, lay, L->codes, L->start, L->end, nullptr, L->n, L->start_adj, L->end_adj, 0, &il);
     if (st == GIQLB_OK && !same) st = giqlb_index_build(ctx, lay, R->codes, R->start, R->end, nullptr, R->n, R->start_adj, R->end_adj, 0, &ir);
-    if (st == GIQLB_OK) st = giqlb_intersects_join(ctx, il, same ? il : ir, out_l, out_r, capacity, total_host);
+    if (st == GIQLB_OK) st = giqlb_intersects_join_impl(ctx, il, same ? il : ir, out_l, out_r, capacity, total_host, true);
     // keep the failing call's message across the clean-up calls
     char msg[sizeof(ctx->err)];
     memcpy(msg, ctx->err, sizeof(msg));
