@@ -396,6 +396,11 @@ struct giqlb_prekeyed {
 int giqlb_index_build_impl(giqlb_ctx* ctx, const giqlb_layout* lay, const int32_t* code, const int32_t* start,
                            const int32_t* end, const uint8_t* strand, const int32_t* rows, int64_t n, int32_t start_adj,
                            int32_t end_adj, int flags, giqlb_prekeyed* pre, giqlb_index** out);
+struct giqlb_dict_pending;
+#define GIQLB_ASYNC_DICT_MAX_CODES 1024   // upper bound of the code space while the dictionary is still on the device
+int giqlb_dict_encode_async(giqlb_ctx* ctx, const int32_t* offs_l, const uint8_t* bytes_l, int64_t n_l, const int32_t* offs_r,
+                            const uint8_t* bytes_r, int64_t n_r, int32_t* codes_l, int32_t* codes_r, giqlb_dict_pending** out);
+int giqlb_dict_finish(giqlb_ctx* ctx, giqlb_dict_pending* p, giqlb_dict** dict_out, int* fallback);
 int giqlb_layout_finalize_async(giqlb_ctx* ctx, giqlb_layout* lay);
 int giqlb_intersects_join_impl(giqlb_ctx* ctx, giqlb_index* L, giqlb_index* R, int32_t* out_l, int32_t* out_r, int64_t capacity,
                                int64_t* total_host, bool speculative);

@@ -206,7 +206,8 @@ __global__ void dict_collect_kernel(StrTable A, StrTable B, const unsigned long 
 }
 
 __global__ void __launch_bounds__(256)
-dict_remap_kernel(int32_t* __restrict__ codes, int64_t n, const int32_t* __restrict__ slot2code) {
+dict_remap_kernel(int32_t* __restrict__ codes, int64_t n, const int32_t* __restrict__ slot2code, const int* __restrict__ ok_flag) {
+    if (ok_flag && !*ok_flag) return;   // the device-side ranking declined: the host path will redo the encode
     const int64_t n_vec = n >> 2;
     int4* cv = reinterpret_cast<int4*>(codes);
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_vec; i += (int64_t)gridDim.x * blockDim.x) {
@@ -223,7 +224,142 @@ dict_remap_kernel(int32_t* __restrict__ codes, int64_t n, const int32_t* __restr
     }
 }
 
+// Orders the gathered names bytewise ON THE DEVICE (at most DR_MAX of them): entry e's code is the number of names
+// that compare below it.  Declines (ok = 0) when there are more names, or the first-round buffers overflowed, or the
+// table is too full — the host path then redoes the encode.
+constexpr int DR_MAX = 1024;
+
+__device__ __forceinline__ bool name_less(const uint8_t* __restrict__ a, int la, const uint8_t* __restrict__ b, int lb) {
+    const int m = la < lb ? la : lb;
+    for (int i = 0; i < m; i++)
+        if (a[i] != b[i]) return a[i] < b[i];
+    return la < lb;
+}
+
+__global__ void __launch_bounds__(DR_MAX)
+dict_rank_kernel(const unsigned long long* __restrict__ cursor /* [0] bytes [1] entries [2] distinct */, const uint8_t* __restrict__ name_buf,
+                 uint32_t name_cap, const int32_t* __restrict__ ent, uint32_t max_entries, uint32_t cap, int32_t* __restrict__ slot2code,
+                 int32_t* __restrict__ ent_rank, int* __restrict__ ok_flag) {
+    const unsigned long long n = cursor[1], bytes = cursor[0], distinct = cursor[2] & 0xffffffffull;
+    const bool ok = n <= (unsigned long long)DR_MAX && n <= max_entries && bytes <= name_cap && distinct * 2 <= cap && n == distinct;
+    if (threadIdx.x == 0) *ok_flag = ok ? 1 : 0;
+    if (!ok || threadIdx.x >= n) return;
+    const int e = threadIdx.x;
+    const uint8_t* me = name_buf + ent[max_entries + e];
+    const int len = ent[2 * max_entries + e];
+    int rank = 0;
+    for (int f = 0; f < (int)n; f++)
+        if (f != e && name_less(name_buf + ent[max_entries + f], ent[2 * max_entries + f], me, len)) rank++;
+    slot2code[ent[e]] = rank;
+    ent_rank[e] = rank;
+}
+
 }  // namespace
+
+// ---- asynchronous encode: no host round trip ---------------------------------------------------------------------------
+// Enqueues insert, collect, device-side ranking and remap, plus the copies that bring the names back; the caller
+// synchronises later (with whatever it waits for anyway) and then calls giqlb_dict_finish.
+struct giqlb_dict_pending {
+    unsigned long long* slots = nullptr;
+    uint8_t* name_buf = nullptr;
+    int32_t *ent = nullptr, *slot2code = nullptr, *ent_rank = nullptr;
+    int* ok_flag = nullptr;
+    uint32_t cap = 0, max_entries = 0, name_cap = 0;
+};
+
+int giqlb_dict_encode_async(giqlb_ctx* ctx, const int32_t* offs_l, const uint8_t* bytes_l, int64_t n_l, const int32_t* offs_r,
+                            const uint8_t* bytes_r, int64_t n_r, int32_t* codes_l, int32_t* codes_r, giqlb_dict_pending** out) {
+    *out = nullptr;
+    if (n_l + n_r == 0 || !ctx->h_stage) return GIQLB_ERR_INVALID;   // caller uses the synchronous path
+    if (((reinterpret_cast<uintptr_t>(codes_l) | reinterpret_cast<uintptr_t>(codes_r)) & 15) != 0) return GIQLB_ERR_INVALID;
+    begin_call(ctx);
+    giqlb_dict_pending* p = new (std::nothrow) giqlb_dict_pending();
+    if (!p) return GIQLB_ERR_NOMEM;
+    p->cap = 1u << 14;
+    p->max_entries = DR_MAX;
+    p->name_cap = 32768;
+    StrTable A{offs_l, bytes_l, n_l}, B{offs_r, bytes_r, n_r};
+    unsigned long long* cursor = reinterpret_cast<unsigned long long*>(ctx->d_scalars + 24);
+    unsigned int* n_distinct = reinterpret_cast<unsigned int*>(ctx->d_scalars + 26);
+    int st = dev_alloc(ctx, &p->slots, (size_t)p->cap);
+    if (st == GIQLB_OK) st = dev_alloc(ctx, &p->name_buf, p->name_cap);
+    if (st == GIQLB_OK) st = dev_alloc(ctx, &p->ent, 3 * (size_t)p->max_entries);
+    if (st == GIQLB_OK) st = dev_alloc(ctx, &p->slot2code, (size_t)p->cap);
+    if (st == GIQLB_OK) st = dev_alloc(ctx, &p->ent_rank, (size_t)p->max_entries);
+    if (st == GIQLB_OK) st = dev_alloc(ctx, &p->ok_flag, 4);
+    if (st != GIQLB_OK) {
+        giqlb_dict_finish(ctx, p, nullptr, nullptr);
+        return st;
+    }
+    cudaMemsetAsync(p->slots, 0, (size_t)p->cap * 8, ctx->stream);
+    cudaMemsetAsync(p->slot2code, 0xFF, (size_t)p->cap * 4, ctx->stream);
+    cudaMemsetAsync(cursor, 0, 3 * 8, ctx->stream);
+    const int64_t chunks = ceil_div(n_l, DI_ROWS) + ceil_div(n_r, DI_ROWS), cap_blocks = (int64_t)ctx->sm_count * 6;
+    const unsigned grid = (unsigned)(chunks < cap_blocks ? chunks : cap_blocks);
+    {
+        PhaseSpan ps(ctx, GIQLB_PH_DICT);
+        dict_insert_kernel<<<grid, DI_THREADS, 0, ctx->stream>>>(A, B, p->slots, p->cap - 1, codes_l, codes_r, n_distinct);
+        dict_collect_kernel<<<(p->cap + 255) / 256, 256, 0, ctx->stream>>>(A, B, p->slots, p->cap, p->name_buf, p->name_cap, cursor, p->ent,
+                                                                           p->max_entries);
+        dict_rank_kernel<<<1, DR_MAX, 0, ctx->stream>>>(cursor, p->name_buf, p->name_cap, p->ent, p->max_entries, p->cap, p->slot2code,
+                                                        p->ent_rank, p->ok_flag);
+        const int64_t rb = ceil_div(n_l > n_r ? n_l : n_r, 256 * 16), rcap = (int64_t)ctx->sm_count * 8;
+        const unsigned rgrid = (unsigned)(rb < 1 ? 1 : (rb < rcap ? rb : rcap));
+        if (n_l > 0) dict_remap_kernel<<<rgrid, 256, 0, ctx->stream>>>(codes_l, n_l, p->slot2code, p->ok_flag);
+        if (n_r > 0) dict_remap_kernel<<<rgrid, 256, 0, ctx->stream>>>(codes_r, n_r, p->slot2code, p->ok_flag);
+        ctx->launches_this_call += 3 + (n_l > 0) + (n_r > 0);
+        ctx->stats.kernels_total += 3 + (n_l > 0) + (n_r > 0);
+    }
+    // names, entries, ranks and the verdict land in the context's PINNED staging buffer whenever the caller next waits
+    unsigned char* h = reinterpret_cast<unsigned char*>(ctx->h_stage);
+    cudaMemcpyAsync(h, cursor, 24, cudaMemcpyDeviceToHost, ctx->stream);
+    cudaMemcpyAsync(h + 32, p->ok_flag, 4, cudaMemcpyDeviceToHost, ctx->stream);
+    cudaMemcpyAsync(h + 64, p->ent, 3 * (size_t)p->max_entries * 4, cudaMemcpyDeviceToHost, ctx->stream);
+    cudaMemcpyAsync(h + 64 + 12 * (size_t)p->max_entries, p->ent_rank, (size_t)p->max_entries * 4, cudaMemcpyDeviceToHost, ctx->stream);
+    cudaMemcpyAsync(h + 64 + 16 * (size_t)p->max_entries, p->name_buf, p->name_cap, cudaMemcpyDeviceToHost, ctx->stream);
+    if (cudaGetLastError() != cudaSuccess) {
+        giqlb_dict_finish(ctx, p, nullptr, nullptr);
+        return giqlb_fail(ctx, GIQLB_ERR_CUDA, "dict_encode_async: launch failed");
+    }
+    static_assert(64 + 16 * DR_MAX + 32768 <= GIQLB_STAGE_BYTES, "staging buffer too small");
+    ctx->stats.rows_in[0] = n_l;
+    ctx->stats.rows_in[1] = n_r;
+    ctx->stats.rows_out = n_l + n_r;
+    ctx->stats.algorithmic_bytes = 8 * (n_l + n_r);
+    *out = p;
+    return end_call(ctx);
+}
+
+// After the stream has been synchronised: builds the dictionary from the staged names (or reports that the device
+// declined: *fallback = 1, *dict_out = nullptr) and releases the scratch.  dict_out == nullptr just releases.
+int giqlb_dict_finish(giqlb_ctx* ctx, giqlb_dict_pending* p, giqlb_dict** dict_out, int* fallback) {
+    if (!p) return GIQLB_OK;
+    int st = GIQLB_OK;
+    if (dict_out) {
+        *dict_out = nullptr;
+        const unsigned char* h = reinterpret_cast<const unsigned char*>(ctx->h_stage);
+        const unsigned long long n = reinterpret_cast<const unsigned long long*>(h)[1];
+        const int ok = *reinterpret_cast<const int*>(h + 32);
+        if (fallback) *fallback = ok ? 0 : 1;
+        if (ok) {
+            const int32_t* ent = reinterpret_cast<const int32_t*>(h + 64);
+            const int32_t* rank = reinterpret_cast<const int32_t*>(h + 64 + 12 * (size_t)p->max_entries);
+            const char* names = reinterpret_cast<const char*>(h + 64 + 16 * (size_t)p->max_entries);
+            giqlb_dict* d = new (std::nothrow) giqlb_dict();
+            if (!d) st = GIQLB_ERR_NOMEM;
+            else {
+                d->names.resize((size_t)n);
+                for (unsigned long long e = 0; e < n; e++)
+                    d->names[(size_t)rank[e]] = std::string(names + ent[p->max_entries + e], (size_t)ent[2 * p->max_entries + e]);
+                *dict_out = d;
+            }
+        }
+    }
+    dev_free(ctx, p->slots); dev_free(ctx, p->name_buf); dev_free(ctx, p->ent); dev_free(ctx, p->slot2code);
+    dev_free(ctx, p->ent_rank); dev_free(ctx, p->ok_flag);
+    delete p;
+    return st;
+}
 
 extern "C" int giqlb_dict_encode(giqlb_ctx* ctx, const int32_t* offs_l, const uint8_t* bytes_l, int64_t n_l,
                                  const int32_t* offs_r, const uint8_t* bytes_r, int64_t n_r, int32_t* codes_l,
@@ -345,12 +481,12 @@ extern "C" int giqlb_dict_encode(giqlb_ctx* ctx, const int32_t* offs_l, const ui
             const int64_t rb = ceil_div(n_l > n_r ? n_l : n_r, 256 * 16), rcap = (int64_t)ctx->sm_count * 8;
             const unsigned rgrid = (unsigned)(rb < 1 ? 1 : (rb < rcap ? rb : rcap));
             if (n_l > 0) {
-                dict_remap_kernel<<<rgrid, 256, 0, ctx->stream>>>(codes_l, n_l, slot2code);
+                dict_remap_kernel<<<rgrid, 256, 0, ctx->stream>>>(codes_l, n_l, slot2code, nullptr);
                 ctx->launches_this_call++;
                 ctx->stats.kernels_total++;
             }
             if (n_r > 0) {
-                dict_remap_kernel<<<rgrid, 256, 0, ctx->stream>>>(codes_r, n_r, slot2code);
+                dict_remap_kernel<<<rgrid, 256, 0, ctx->stream>>>(codes_r, n_r, slot2code, nullptr);
                 ctx->launches_this_call++;
                 ctx->stats.kernels_total++;
             }

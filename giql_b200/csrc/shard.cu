@@ -312,7 +312,7 @@ extern "C" int giqlb_intersects_tables_sharded(giqlb_ctx* ctx, giqlb_table_t* L,
     if (st == GIQLB_OK) st = giqlb_layout_create(ctx, n_codes, 0, &lay);
     if (st == GIQLB_OK) st = giqlb_layout_observe(ctx, lay, L->codes, L->start, L->end, L->n, L->start_adj, L->end_adj);
     if (st == GIQLB_OK) st = giqlb_layout_observe(ctx, lay, R->codes, R->start, R->end, R->n, R->start_adj, R->end_adj);
-    if (st == GIQLB_OK) st = giqlb_layout_finalize(ctx, lay);
+    if (st == GIQLB_OK) st = giqlb_layout_finalize_async(ctx, lay);   // errors surface with the selection sizes
     giqlb_table_t* T[2] = {L, R};
     int64_t n_sel[2] = {0, 0};
     if (st == GIQLB_OK) {

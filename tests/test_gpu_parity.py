@@ -500,3 +500,26 @@ def test_sharded_cluster_merge_equal_single_gpu(world, distance, engine, c_oracl
     op, os_, oe, oc = c_oracle.merge(R["code"], R["start"], R["end"], len(R["names"]), distance=distance)
     assert sorted(rows) == sorted(zip(op.tolist(), os_.tolist(), oe.tolist(), oc.tolist()))
     assert sum(r[3] for r in rows) == t.n
+
+
+def test_one_call_pipeline_dictionary_paths(engine):
+    """giqlb_intersects_tables orders the dictionary on the device when it has at most 1024 names and falls back to the
+    host-ordered encode beyond that; both must give the oracle's pairs and a bytewise-sorted dictionary."""
+    rng = np.random.default_rng(91)
+    ob = OracleBackend()
+    engine._pair_capacity = max(engine._pair_capacity, 4096)          # take the one-call path
+    for n_names in (40, 1024, 1500):
+        names = [f"ctg{i:05d}_{'x' * (i % 19)}" for i in range(n_names)]
+        mk = lambda n: {"chrom": [names[i] for i in rng.integers(0, n_names, size=n)], "start": rng.integers(0, 300, size=n).tolist()}
+        L, R = mk(3000), mk(2500)
+        for T in (L, R):
+            T["end"] = [s + int(w) for s, w in zip(T["start"], rng.integers(1, 40, size=len(T["start"])))]
+        tl = engine.table({"chrom": L["chrom"], "start": L["start"], "end": L["end"]})
+        tr = engine.table({"chrom": R["chrom"], "start": R["start"], "end": R["end"]})
+        res = engine.intersects(tl, tr)
+        l, r = res.to_host()
+        assert sorted(zip(l.tolist(), r.tolist())) == ob.pairs(L, R)
+        present = sorted(set(L["chrom"]) | set(R["chrom"]), key=lambda s: s.encode())
+        assert tl.dictionary is tr.dictionary and tl.dictionary.names == present
+        dn = np.array(tl.dictionary.names, dtype=object)
+        assert list(dn[tl.codes.cpu().numpy()]) == L["chrom"]
