@@ -289,25 +289,27 @@ extern "C" int giqlb_shard_select(giqlb_ctx* ctx, const giqlb_layout* lay, const
 // dictionary encode -> layout -> cuts (stay on the device) -> fused select + keygen of both tables -> ONE round trip
 // for the two selection sizes -> sort / index of the selections -> single-pass join.  Host round trips: dictionary
 // names, layout extent, selection sizes, pair total.
-extern "C" int giqlb_intersects_tables_sharded(giqlb_ctx* ctx, giqlb_table_t* L, giqlb_table_t* R, int32_t n_codes, int world,
-                                               int rank, int32_t* out_l, int32_t* out_r, int64_t capacity, int64_t* total_host,
-                                               giqlb_dict** dict_out) {
-    if (!ctx || !L || !R || !total_host || world < 1 || rank < 0 || rank >= world || L == R)
-        return giqlb_fail(ctx, GIQLB_ERR_INVALID, "intersects_tables_sharded: bad argument");
-    if (dict_out) *dict_out = nullptr;
+static int sharded_impl(giqlb_ctx* ctx, giqlb_table_t* L, giqlb_table_t* R, int32_t n_codes, int world, int rank, int32_t* out_l,
+                        int32_t* out_r, int64_t capacity, int64_t* total_host, giqlb_dict** dict_out, bool async_dict) {
     giqlb_dict* dict = nullptr;
+    giqlb_dict_pending* pend = nullptr;
     giqlb_layout* lay = nullptr;
     giqlb_index *il = nullptr, *ir = nullptr;
     giqlb_prekeyed pre[2];
     uint32_t *hist = nullptr, *cuts32 = nullptr;
     unsigned long long* cuts64 = nullptr;
     int st = GIQLB_OK;
-    if (!L->codes_valid || !R->codes_valid) {
-        if (L->codes_valid != R->codes_valid) return giqlb_fail(ctx, GIQLB_ERR_INVALID, "intersects_tables_sharded: encode both tables or neither");
-        st = giqlb_dict_encode(ctx, L->chrom_offsets, L->chrom_bytes, L->n, R->chrom_offsets, R->chrom_bytes, R->n, L->codes, R->codes, &dict);
-        if (st != GIQLB_OK) return st;
-        n_codes = giqlb_dict_size(dict);
-        L->codes_valid = R->codes_valid = 1;
+    const bool encode = !L->codes_valid;
+    if (encode) {
+        if (async_dict && giqlb_dict_encode_async(ctx, L->chrom_offsets, L->chrom_bytes, L->n, R->chrom_offsets, R->chrom_bytes, R->n,
+                                                  L->codes, R->codes, &pend) == GIQLB_OK) {
+            n_codes = GIQLB_ASYNC_DICT_MAX_CODES;   // upper bound until the names come back with the selection sizes
+        } else {
+            pend = nullptr;
+            st = giqlb_dict_encode(ctx, L->chrom_offsets, L->chrom_bytes, L->n, R->chrom_offsets, R->chrom_bytes, R->n, L->codes, R->codes, &dict);
+            if (st != GIQLB_OK) return st;
+            n_codes = giqlb_dict_size(dict);
+        }
     }
     if (st == GIQLB_OK) st = giqlb_layout_create(ctx, n_codes, 0, &lay);
     if (st == GIQLB_OK) st = giqlb_layout_observe(ctx, lay, L->codes, L->start, L->end, L->n, L->start_adj, L->end_adj);
@@ -366,6 +368,22 @@ extern "C" int giqlb_intersects_tables_sharded(giqlb_ctx* ctx, giqlb_table_t* L,
             n_sel[1] = ctx->h_scalars[47];
         }
     }
+    if (pend) {   // the round trip above also landed the names (or the device's refusal to order them)
+        int fallback = 0;
+        if (st != GIQLB_OK) cudaStreamSynchronize(ctx->stream);
+        const int st2 = giqlb_dict_finish(ctx, pend, &dict, &fallback);
+        pend = nullptr;
+        if (fallback) {   // codes were never written: redo everything with the host-ordered dictionary
+            for (int k = 0; k < 2; k++) {
+                dev_free(ctx, pre[k].gs); dev_free(ctx, pre[k].ge); dev_free(ctx, pre[k].rows); dev_free(ctx, pre[k].counters);
+            }
+            dev_free(ctx, hist); dev_free(ctx, cuts64); dev_free(ctx, cuts32);
+            giqlb_layout_free(ctx, lay);
+            cudaMemsetAsync(ctx->d_err, 0, 4 * sizeof(int), ctx->stream);
+            return sharded_impl(ctx, L, R, n_codes, world, rank, out_l, out_r, capacity, total_host, dict_out, false);
+        }
+        if (st == GIQLB_OK) st = st2;
+    }
     for (int k = 0; k < 2 && st == GIQLB_OK; k++) {
         giqlb_index** dst = k == 0 ? &il : &ir;
         const int64_t deg = ctx->h_scalars[40 + 4 * k], neg = ctx->h_scalars[41 + 4 * k];
@@ -387,8 +405,19 @@ extern "C" int giqlb_intersects_tables_sharded(giqlb_ctx* ctx, giqlb_table_t* L,
     giqlb_index_free(ctx, il);
     giqlb_index_free(ctx, ir);
     giqlb_layout_free(ctx, lay);
+    if (encode && dict && (st == GIQLB_OK || st == GIQLB_ERR_CAPACITY)) L->codes_valid = R->codes_valid = 1;
     if (dict_out) *dict_out = dict;
     else giqlb_dict_free(dict);
     if (st != GIQLB_OK) memcpy(ctx->err, msg, sizeof(msg));
     return st;
+}
+
+extern "C" int giqlb_intersects_tables_sharded(giqlb_ctx* ctx, giqlb_table_t* L, giqlb_table_t* R, int32_t n_codes, int world,
+                                               int rank, int32_t* out_l, int32_t* out_r, int64_t capacity, int64_t* total_host,
+                                               giqlb_dict** dict_out) {
+    if (!ctx || !L || !R || !total_host || world < 1 || rank < 0 || rank >= world || L == R)
+        return giqlb_fail(ctx, GIQLB_ERR_INVALID, "intersects_tables_sharded: bad argument");
+    if (dict_out) *dict_out = nullptr;
+    if (L->codes_valid != R->codes_valid) return giqlb_fail(ctx, GIQLB_ERR_INVALID, "intersects_tables_sharded: encode both tables or neither");
+    return sharded_impl(ctx, L, R, n_codes, world, rank, out_l, out_r, capacity, total_host, dict_out, true);
 }
