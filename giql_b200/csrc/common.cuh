@@ -104,7 +104,8 @@ struct giqlb_layout {
         int64_t n_degenerate, n_negative;
     };
     std::vector<Observed> observed;
-    unsigned long long* d_obs = nullptr;   // [2 * GIQLB_MAX_OBSERVED]: end <= start, end < start per observe() call
+    unsigned long long* d_obs = nullptr;   // [2 * GIQLB_MAX_OBSERVED]: end <= start, end < start per observe() call;
+                                           // then [GIQLB_MAX_OBSERVED]: widest interval of each observed table
 };
 #define GIQLB_MAX_OBSERVED 16
 

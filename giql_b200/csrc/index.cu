@@ -26,7 +26,7 @@ __global__ void __launch_bounds__(LY_THREADS)
 layout_observe_kernel(const int32_t* __restrict__ code, const int32_t* __restrict__ start,
                       const int32_t* __restrict__ end, int64_t n, int32_t n_codes, int32_t sadj, int32_t eadj,
                       long long* __restrict__ lohi, unsigned long long* __restrict__ obs /* [2] degenerate, negative */,
-                      int* __restrict__ err) {
+                      unsigned long long* __restrict__ max_width /* widest interval of the table (cells) */, int* __restrict__ err) {
     __shared__ int32_t s_lo[LY_SMEM_CODES];
     __shared__ int32_t s_hi[LY_SMEM_CODES];
     const bool use_smem = n_codes <= LY_SMEM_CODES;
@@ -39,8 +39,10 @@ layout_observe_kernel(const int32_t* __restrict__ code, const int32_t* __restric
     }
     bool bad = false;
     unsigned int degenerate = 0, negative = 0;
+    long long widest = 0;
     auto fold = [&](int32_t c, int32_t s0, int32_t e0) {
         long long s = (long long)s0 + sadj, e = (long long)e0 + eadj;
+        if (e - s > widest) widest = e - s;
         long long lo = s < e ? s : e, hi = s < e ? e : s;
         if (c < 0 || c >= n_codes || lo < -(1ll << 30) || hi > (1ll << 31) - 4) {
             bad = true;
@@ -71,6 +73,10 @@ layout_observe_kernel(const int32_t* __restrict__ code, const int32_t* __restric
     for (int64_t i = (n_vec << 2) + (int64_t)blockIdx.x * LY_THREADS + threadIdx.x; i < n; i += (int64_t)gridDim.x * LY_THREADS)
         fold(code[i], start[i], end[i]);
     if (bad) err[1] = 1;
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) widest = max(widest, __shfl_xor_sync(FULL_MASK, widest, d));
+    if (lane_id() == 0 && widest > 0 && (unsigned long long)widest > *(volatile unsigned long long*)max_width)
+        atomicMax(max_width, (unsigned long long)widest);
     if (__any_sync(FULL_MASK, degenerate != 0)) {
         degenerate = warp_reduce_add(degenerate);
         negative = warp_reduce_add(negative);
@@ -270,8 +276,8 @@ extern "C" int giqlb_layout_create(giqlb_ctx* ctx, int32_t n_codes, int64_t pad,
     if (st == GIQLB_OK) st = dev_alloc(ctx, &lay->d_base, (size_t)n_codes + 1);
     if (st == GIQLB_OK) st = dev_alloc(ctx, &lay->d_lo32, (size_t)n_codes);
     if (st == GIQLB_OK) st = dev_alloc(ctx, &lay->d_hi32, (size_t)n_codes);
-    if (st == GIQLB_OK) st = dev_alloc(ctx, &lay->d_obs, (size_t)2 * GIQLB_MAX_OBSERVED);
-    if (st == GIQLB_OK && cudaMemsetAsync(lay->d_obs, 0, 2 * GIQLB_MAX_OBSERVED * 8, ctx->stream) != cudaSuccess) st = GIQLB_ERR_CUDA;
+    if (st == GIQLB_OK) st = dev_alloc(ctx, &lay->d_obs, (size_t)3 * GIQLB_MAX_OBSERVED);
+    if (st == GIQLB_OK && cudaMemsetAsync(lay->d_obs, 0, 3 * GIQLB_MAX_OBSERVED * 8, ctx->stream) != cudaSuccess) st = GIQLB_ERR_CUDA;
     if (st != GIQLB_OK) {
         giqlb_layout_free(ctx, lay);
         return st;
@@ -296,7 +302,7 @@ extern "C" int giqlb_layout_observe(giqlb_ctx* ctx, giqlb_layout* lay, const int
         const size_t slot = lay->observed.size() < GIQLB_MAX_OBSERVED - 1 ? lay->observed.size() : GIQLB_MAX_OBSERVED - 1;
         PhaseSpan ps(ctx, GIQLB_PH_LAYOUT);
         layout_observe_kernel<<<grid_for(ctx, n, LY_THREADS * 8, 8), LY_THREADS, 0, ctx->stream>>>(
-            code, start, end, n, lay->n_codes, start_adj, end_adj, (long long*)lay->d_lohi, lay->d_obs + 2 * slot, ctx->d_err);
+            code, start, end, n, lay->n_codes, start_adj, end_adj, (long long*)lay->d_lohi, lay->d_obs + 2 * slot, lay->d_obs + 2 * GIQLB_MAX_OBSERVED + slot, ctx->d_err);
         LAUNCH_CHECK(ctx);
         if (lay->observed.size() < GIQLB_MAX_OBSERVED - 1) lay->observed.push_back({code, n, start_adj, end_adj, -1, -1});
     }

@@ -32,14 +32,29 @@ __device__ __forceinline__ bool row_linearise(const ProbeCols& P, int64_t i, uin
     return true;
 }
 
+// `stride` > 1 histograms every stride-th row only (a deterministic sample: every rank takes the same rows); the
+// widest interval then comes from the layout's observe pass instead of this kernel.
+// the same from values already in registers
+__device__ __forceinline__ bool vals_linearise(const ProbeCols& P, int32_t c, int32_t s0, int32_t e0, uint32_t& gs, uint32_t& ge) {
+    if (c < 0 || c >= P.n_codes) return false;
+    long long lo = __ldg(P.lo32 + c), hi = __ldg(P.hi32 + c);
+    long long s = (long long)s0 + P.sadj, e = (long long)e0 + P.eadj;
+    if (s < lo || s > hi || e < lo || e > hi) return false;
+    uint32_t b = __ldg(P.base + c) + 1u;
+    gs = b + (uint32_t)(s - lo);
+    ge = b + (uint32_t)(e - lo);
+    return true;
+}
+
 __global__ void __launch_bounds__(SH_THREADS)
-shard_hist_kernel(ProbeCols P, uint32_t* __restrict__ hist, uint32_t* __restrict__ max_width, int* __restrict__ err) {
+shard_hist_kernel(ProbeCols P, int64_t stride, uint32_t* __restrict__ hist, uint32_t* __restrict__ max_width, int* __restrict__ err) {
     __shared__ uint32_t s_hist[SH_MAX_BINS];
     for (int i = threadIdx.x; i < SH_MAX_BINS; i += SH_THREADS) s_hist[i] = 0;
     __syncthreads();
     uint32_t mw = 0;
     bool bad = false;
-    for (int64_t i = (int64_t)blockIdx.x * SH_THREADS + threadIdx.x; i < P.n; i += (int64_t)gridDim.x * SH_THREADS) {
+    for (int64_t k = (int64_t)blockIdx.x * SH_THREADS + threadIdx.x; k * stride < P.n; k += (int64_t)gridDim.x * SH_THREADS) {
+        const int64_t i = k * stride;
         uint32_t gs, ge;
         if (!row_linearise(P, i, gs, ge)) {
             bad = true;
@@ -120,7 +135,8 @@ shard_select_kernel(ProbeCols P, uint32_t gs_lo, uint32_t gs_hi, uint32_t ge_gt,
 
 // Device-side finish of the cuts (what giqlb_shard_cuts does on the host): u32 cuts[world + 1] with cuts[0] = 0,
 // cuts[world] = 2^32 - 1, unset cuts inherit the next boundary, monotone; cuts32[world + 1] = widest left interval.
-__global__ void shard_cuts_finish_kernel(const unsigned long long* __restrict__ cuts64, const uint32_t* __restrict__ max_width, int world,
+__global__ void shard_cuts_finish_kernel(const unsigned long long* __restrict__ cuts64, const uint32_t* __restrict__ max_width,
+                                         const unsigned long long* __restrict__ observed_width /* nullable: from layout observe */, int world,
                                          uint32_t* __restrict__ cuts32) {
     if (threadIdx.x != 0 || blockIdx.x != 0) return;
     cuts32[0] = 0u;
@@ -132,7 +148,8 @@ __global__ void shard_cuts_finish_kernel(const unsigned long long* __restrict__ 
     }
     for (int g = 1; g < world; g++)
         if (cuts32[g] < cuts32[g - 1]) cuts32[g] = cuts32[g - 1];
-    cuts32[world + 1] = *max_width;
+    unsigned long long w = observed_width ? *observed_width : (unsigned long long)*max_width;
+    cuts32[world + 1] = w > 0xffffffffull ? 0xffffffffu : (uint32_t)w;
 }
 
 // Fused selection + key generation for one rank: reads the table once, keeps the rows of the rank's genome range
@@ -151,16 +168,34 @@ shard_select_keygen_kernel(ProbeCols P, const uint32_t* __restrict__ cuts32, int
     const uint32_t gs_hi = side == 0 ? hi : (hi > 0xffffffffu - maxw ? 0xffffffffu : hi + maxw);
     const uint32_t ge_gt = side == 0 ? 0u : lo;
     unsigned int degenerate = 0, negative = 0, outside = 0;
+    const bool vec = ((reinterpret_cast<uintptr_t>(P.code) | reinterpret_cast<uintptr_t>(P.start) | reinterpret_cast<uintptr_t>(P.end)) & 15) == 0;
     for (int64_t base = (int64_t)blockIdx.x * (SH_THREADS * 4); base < P.n; base += (int64_t)gridDim.x * (SH_THREADS * 4)) {
         bool keep[4];
         uint32_t gs[4], ge[4];
         unsigned int cnt = 0;
+        const int64_t i0 = base + (int64_t)threadIdx.x * 4;
+        int32_t c4[4], s4[4], e4[4];
+        if (vec && i0 + 3 < P.n) {   // one 16-byte load per column
+            const int4 c = __ldg(reinterpret_cast<const int4*>(P.code + i0));
+            const int4 s = __ldg(reinterpret_cast<const int4*>(P.start + i0));
+            const int4 e = __ldg(reinterpret_cast<const int4*>(P.end + i0));
+            c4[0] = c.x; c4[1] = c.y; c4[2] = c.z; c4[3] = c.w;
+            s4[0] = s.x; s4[1] = s.y; s4[2] = s.z; s4[3] = s.w;
+            e4[0] = e.x; e4[1] = e.y; e4[2] = e.z; e4[3] = e.w;
+        } else {
+#pragma unroll
+            for (int k = 0; k < 4; k++) {
+                const bool in = i0 + k < P.n;
+                c4[k] = in ? P.code[i0 + k] : -1;
+                s4[k] = in ? P.start[i0 + k] : 0;
+                e4[k] = in ? P.end[i0 + k] : 0;
+            }
+        }
 #pragma unroll
         for (int k = 0; k < 4; k++) {
-            const int64_t i = base + (int64_t)threadIdx.x * 4 + k;
             keep[k] = false;
-            if (i < P.n) {
-                if (!row_linearise(P, i, gs[k], ge[k])) outside++;
+            if (i0 + k < P.n) {
+                if (!vals_linearise(P, c4[k], s4[k], e4[k], gs[k], ge[k])) outside++;
                 else keep[k] = gs[k] >= gs_lo && gs[k] < gs_hi && ge[k] > ge_gt;
             }
             if (keep[k]) {
@@ -225,7 +260,7 @@ extern "C" int giqlb_shard_cuts(giqlb_ctx* ctx, const giqlb_layout* lay, const i
     if (n > 0) {
         PhaseSpan ps(ctx, GIQLB_PH_SHARD);
         int64_t blocks = ceil_div(n, SH_THREADS * 8), cap = (int64_t)ctx->sm_count * 2;
-        shard_hist_kernel<<<(unsigned)(blocks < cap ? blocks : cap), SH_THREADS, 0, ctx->stream>>>(P, hist, hist + n_bins, ctx->d_err);
+        shard_hist_kernel<<<(unsigned)(blocks < cap ? blocks : cap), SH_THREADS, 0, ctx->stream>>>(P, 1, hist, hist + n_bins, ctx->d_err);
         ctx->launches_this_call++;
         ctx->stats.kernels_total++;
         shard_cuts_kernel<<<1, 1024, 0, ctx->stream>>>(hist, n_bins, n, world, cuts);
@@ -340,13 +375,17 @@ static int sharded_impl(giqlb_ctx* ctx, giqlb_table_t* L, giqlb_table_t* R, int3
             PhaseSpan ps(ctx, GIQLB_PH_SHARD);
             const int64_t cap = (int64_t)ctx->sm_count * 8;
             if (L->n > 0) {
-                int64_t blocks = ceil_div(L->n, SH_THREADS * 8), hcap = (int64_t)ctx->sm_count * 2;
-                shard_hist_kernel<<<(unsigned)(blocks < hcap ? blocks : hcap), SH_THREADS, 0, ctx->stream>>>(P[0], hist, hist + n_bins, ctx->d_err);
-                shard_cuts_kernel<<<1, 1024, 0, ctx->stream>>>(hist, n_bins, L->n, world, cuts64);
+                // a 1-in-16 sample of the left rows places the cuts (balance error ~ 1/sqrt(n/16) of a shard); the widest
+                // left interval, needed for the right-side replication bound, comes from the observe pass (slot 0 = L)
+                const int64_t stride = L->n >= (1 << 20) ? 16 : 1, n_samp = ceil_div(L->n, stride);
+                int64_t blocks = ceil_div(n_samp, SH_THREADS * 8), hcap = (int64_t)ctx->sm_count * 2;
+                shard_hist_kernel<<<(unsigned)(blocks < 1 ? 1 : (blocks < hcap ? blocks : hcap)), SH_THREADS, 0, ctx->stream>>>(
+                    P[0], stride, hist, hist + n_bins, ctx->d_err);
+                shard_cuts_kernel<<<1, 1024, 0, ctx->stream>>>(hist, n_bins, n_samp, world, cuts64);
                 ctx->launches_this_call += 2;
                 ctx->stats.kernels_total += 2;
             }
-            shard_cuts_finish_kernel<<<1, 32, 0, ctx->stream>>>(cuts64, hist + n_bins, world, cuts32);
+            shard_cuts_finish_kernel<<<1, 32, 0, ctx->stream>>>(cuts64, hist + n_bins, lay->d_obs + 2 * GIQLB_MAX_OBSERVED, world, cuts32);
             ctx->launches_this_call++;
             ctx->stats.kernels_total++;
             for (int k = 0; k < 2; k++) {
