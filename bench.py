@@ -230,7 +230,7 @@ def run_b200(args):
     host = {k: {c: pinned(T[c]) for c in ("offs", "bytes", "start", "end")} for k, T in (("l", A), ("r", B))}
     dev = {k: {c: t.to(eng.device) for c, t in cols.items()} for k, cols in host.items()}
     torch.cuda.synchronize()
-    h2d_bytes = sum(t.numel() * t.element_size() for cols in host.values() for t in cols.values())
+    h2d_bytes = sum(t.numel() * t.element_size() for cols in host.values() for t in cols.values()) // max(world, 1)
     flush = torch.empty(512 << 20, dtype=torch.uint8, device=eng.device)   # > 126 MB L2
 
     if world > 1:
@@ -252,8 +252,13 @@ def run_b200(args):
         return eng.intersects(tl, tr, mode=args.join_mode)
 
     def step_e2e(out_l_host, out_r_host):
-        tl = eng.table_from_buffers(host["l"]["offs"], host["l"]["bytes"], host["l"]["start"], host["l"]["end"])
-        tr = eng.table_from_buffers(host["r"]["offs"], host["r"]["bytes"], host["r"]["start"], host["r"]["end"])
+        if shard is not None:
+            # every rank uploads 1/N of the rows over its own PCIe link; NCCL all-gathers the blocks over NVLink
+            tl = sharding.upload_replicated(eng, host["l"], rank, world)
+            tr = sharding.upload_replicated(eng, host["r"], rank, world)
+        else:
+            tl = eng.table_from_buffers(host["l"]["offs"], host["l"]["bytes"], host["l"]["start"], host["l"]["end"])
+            tr = eng.table_from_buffers(host["r"]["offs"], host["r"]["bytes"], host["r"]["start"], host["r"]["end"])
         res = shard.intersects(tl, tr) if shard is not None else eng.intersects(tl, tr, mode=args.join_mode)
         n = len(res)
         out_l_host[:n].copy_(res.left_rows, non_blocking=True)
@@ -392,7 +397,9 @@ def run_b200(args):
                            "with count+scan+emit; timed calls run the fused single-pass count/offset/emit kernel into a buffer of 1.25x "
                            "the previous total, overflow checked on the device)"},
         "e2e": {"value": pairs / (e2e_ms / 1e3), "unit": UNIT, "ms_per_step": e2e_ms, "h2d_bytes_per_step": h2d_bytes,
-                "d2h_bytes_per_step": d2h_bytes},
+                "d2h_bytes_per_step": d2h_bytes,
+                "note": "per-rank bytes" + ("" if world == 1 else "; each rank uploads 1/N of the rows, NCCL all-gathers the blocks over NVLink; "
+                                            "each rank reads back its own pairs")},
         "gpu_launches": int(launches),
         "roofline": roofline,
         "join_roofline": join_roofline,

@@ -323,3 +323,48 @@ import ctypes  # noqa: E402  (only the Engine-backed ops need it)
 for _cls in (EngineOps, EngineOpsStepwise):
     _cls.cm_plan, _cls.cm_max_end, _cls.cm_cluster_counts = _engine_cm_plan, _engine_cm_max_end, _engine_cm_cluster_counts
     _cls.cm_cluster_ids, _cls.cm_merge, _cls.cm_release = _engine_cm_cluster_ids, _engine_cm_merge, _engine_cm_release
+
+
+# ---- multi-GPU ingest: every rank uploads 1/world of the rows over its own PCIe link, NVLink replicates ----------------
+def upload_replicated(engine, host_cols: dict, rank: int, world: int, group=None):
+    """Host columns of ONE table (pinned tensors ``offs`` int32[n+1], ``bytes`` uint8[], ``start``/``end`` int32[n], the
+    same on every rank) -> a DeviceTable holding the FULL table on every rank.
+
+    With ``world`` > 1 a rank copies only its block of rows host->device and the blocks are all-gathered over
+    NVLink (NCCL), so the PCIe traffic per GPU is 1/world of the table instead of all of it.  The join itself still
+    needs the whole table on every rank (replicated-input sharding).
+    """
+    offs, byts, start, end = host_cols["offs"], host_cols["bytes"], host_cols["start"], host_cols["end"]
+    n = int(start.numel())
+    if world == 1 or not dist.is_initialized():
+        return engine.table_from_buffers(offs, byts, start, end)
+    dev = engine.device
+    per = -(-n // world)                                  # rows per rank (the last block may be short)
+    lo, hi = min(rank * per, n), min((rank + 1) * per, n)
+
+    def gather_rows(col: torch.Tensor, width: int = per) -> torch.Tensor:
+        mine = torch.zeros(width, dtype=col.dtype, device=dev)
+        mine[: hi - lo].copy_(col[lo:hi], non_blocking=True)
+        out = torch.empty(world * width, dtype=col.dtype, device=dev)
+        dist.all_gather_into_tensor(out, mine, group=group)
+        return out[:n]
+
+    d_start, d_end = gather_rows(start), gather_rows(end)
+    # offsets are absolute positions into the byte buffer: blocks of offs[0:n] concatenate back to the original array
+    d_offs = torch.empty(n + 1, dtype=torch.int32, device=dev)
+    d_offs[:n] = gather_rows(offs[:n])
+    d_offs[n:].copy_(offs[n:], non_blocking=True)
+    # byte blocks differ in length: pad to the longest (every rank knows all block bounds from the host offsets)
+    bounds = [int(offs[min(r * per, n)]) for r in range(world + 1)]
+    bounds[world] = int(offs[n])
+    width = max(bounds[r + 1] - bounds[r] for r in range(world))
+    mine = torch.zeros(max(width, 1), dtype=torch.uint8, device=dev)
+    mine[: bounds[rank + 1] - bounds[rank]].copy_(byts[bounds[rank]: bounds[rank + 1]], non_blocking=True)
+    allb = torch.empty(world * max(width, 1), dtype=torch.uint8, device=dev)
+    dist.all_gather_into_tensor(allb, mine, group=group)
+    d_bytes = torch.cat([allb[r * max(width, 1): r * max(width, 1) + bounds[r + 1] - bounds[r]] for r in range(world)])
+    if d_bytes.numel() == 0:
+        d_bytes = torch.zeros(1, dtype=torch.uint8, device=dev)
+    from .engine import DeviceTable
+
+    return DeviceTable(engine, n, None, d_start, d_end, None, d_offs, d_bytes)

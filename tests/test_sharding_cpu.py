@@ -201,3 +201,36 @@ def test_stitch_and_offsets_helpers():
     assert carry_before([5, 9, 2], 0) == 0 and carry_before([5, 9, 2], 2) == 9
     with pytest.raises(ValueError):
         stitch_heads([(0, 2, 0, 10)])
+
+
+# ---- multi-GPU ingest (1/N upload + all-gather) over gloo ---------------------------------------------------------------------
+class _CpuEngine:
+    device = torch.device("cpu")
+
+
+def _ingest_worker(rank, world, port, out):
+    from giql_b200.sharding import upload_replicated
+
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        names = np.array(["chr1", "chr10", "chrX_random_contig", "", "c"], dtype=object)
+        rng = np.random.default_rng(3)
+        codes = rng.integers(0, len(names), size=1003)
+        lens = np.array([len(names[c].encode()) for c in codes])
+        offs = np.concatenate([[0], np.cumsum(lens)]).astype(np.int32)
+        byts = np.frombuffer("".join(names[c] for c in codes).encode(), dtype=np.uint8).copy()
+        cols = {"offs": torch.from_numpy(offs), "bytes": torch.from_numpy(byts),
+                "start": torch.arange(1003, dtype=torch.int32), "end": torch.arange(1003, dtype=torch.int32) + 7}
+        t = upload_replicated(_CpuEngine(), cols, rank, world)
+        out[rank] = all(torch.equal(a, b) for a, b in ((t.chrom_offsets, cols["offs"]), (t.chrom_bytes, cols["bytes"]),
+                                                         (t.start, cols["start"]), (t.end, cols["end"]))) and t.n == 1003
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world", [2, 3])
+def test_upload_replicated_over_gloo(world):
+    out = mp.Manager().dict()
+    mp.spawn(_ingest_worker, args=(world, _free_port(), out), nprocs=world, join=True)
+    assert all(out[r] for r in range(world))
