@@ -186,19 +186,20 @@ def run_reference(args):
 
 
 # ---- B200 arm --------------------------------------------------------------------------------------------------
-def algorithmic_bytes(phase: str, n_l: int, n_r: int, pairs: int, sort_passes: int):
-    """Per-phase algorithmic bytes of ONE step."""
-    n = n_l + n_r
+def algorithmic_bytes(phase: str, n_full: int, n_local: int, pairs: int, sort_passes: int):
+    """Per-phase algorithmic bytes of ONE step on ONE rank.  n_full = rows of both tables (phases that
+    read the whole replicated input), n_local = rows this rank indexes and joins (= n_full on one GPU)."""
     return {
-        "dict": 8 * n,                       # read the utf8 name (~4.6 B) + offset, write an int32 code: counted as 8 B/row
-        "layout": 12 * n,                    # read code/start/end
-        "keygen": 12 * n + 8 * n,            # read code/start/end, write linear start + linear end
-        "sort_hist": 4 * n,                  # read keys once
-        "sort_pass": 16 * n * sort_passes,   # keys + row ids in and out, per 8-bit digit pass
-        "gather": 12 * n,                    # read row id + gathered end, write end
-        "join_count": 12 * n,
+        "dict": 8 * n_full,                        # read the utf8 name (~4.6 B) + offset, write an int32 code: counted as 8 B/row
+        "layout": 12 * n_full,                     # read code/start/end
+        "shard": 12 * n_full + 12 * n_local,       # sampled histogram + fused select/keygen: read the columns, write keys + row ids
+        "keygen": 12 * n_local + 8 * n_local,      # read code/start/end, write linear start + linear end
+        "sort_hist": 4 * n_local,                  # read keys once
+        "sort_pass": 16 * n_local * sort_passes,   # keys + row ids in and out, per 8-bit digit pass
+        "gather": 12 * n_local,                    # read row id + gathered end, write end
+        "join_count": 8 * n_local,                 # merge-path partition (or the count pass of the two-pass API)
         "join_scan": 0,
-        "join_emit": 12 * n + 8 * pairs,
+        "join_emit": 12 * n_local + 8 * pairs,
     }.get(phase, 0)
 
 
@@ -344,7 +345,7 @@ def run_b200(args):
         if n_launch <= 0:
             continue
         per_step_ms = ms / args.steps
-        ab = algorithmic_bytes(name, n_l, n_r, pairs_local, sort_passes)
+        ab = algorithmic_bytes(name, n_l + n_r, (n_l + n_r) // world, pairs_local, sort_passes)
         phases[name] = {"ms_per_step": round(per_step_ms, 4), "launches_per_step": n_launch / args.steps,
                         "algorithmic_bytes_per_step": ab,
                         "gbs": round(ab / (per_step_ms * 1e6), 1) if per_step_ms > 0 else None}
@@ -363,7 +364,7 @@ def run_b200(args):
         except Exception:
             pass
     join_ms = sum(phases[p]["ms_per_step"] for p in ("join_count", "join_scan", "join_emit") if p in phases)
-    join_bytes = 12 * (n_l + n_r) + 8 * pairs_local
+    join_bytes = 12 * ((n_l + n_r) // world) + 8 * pairs_local
     join_roofline = {"ms": round(join_ms, 4), "algorithmic_bytes": join_bytes,
                      "achieved": round(join_bytes / (join_ms * 1e6), 1) if join_ms else None, "unit": "GB/s",
                      "frac": round(join_bytes / (join_ms * 1e6) / hbm_peak, 4) if join_ms else None,
