@@ -18,6 +18,9 @@ constexpr int RS_WARPS = RS_THREADS / 32;
 #define GIQLB_RS_IPT 16
 #endif
 constexpr int RS_IPT = GIQLB_RS_IPT;
+#ifndef GIQLB_RS_CTAS_PER_SM
+#define GIQLB_RS_CTAS_PER_SM 4   // measured: 5 (48 registers, small spills) is slower
+#endif
 #ifndef GIQLB_RS_USE_MATCH
 #define GIQLB_RS_USE_MATCH 0
 #endif
@@ -71,7 +74,7 @@ rs_histogram_kernel(const uint32_t* __restrict__ keys, int64_t n, int begin_bit,
 // GATHER: the last pass of an index build also fetches gather_src[payload] (the row's linear end) into
 // gather_dst at the row's sorted position, which saves the separate gather pass.
 template <bool IDENTITY_VALS, bool GATHER>
-__global__ void __launch_bounds__(RS_THREADS, RS_IPT >= 16 ? 4 : 6)
+__global__ void __launch_bounds__(RS_THREADS, RS_IPT >= 16 ? GIQLB_RS_CTAS_PER_SM : 6)
 rs_onesweep_kernel(const uint32_t* __restrict__ keys_in, const uint32_t* __restrict__ vals_in,
                    uint32_t* __restrict__ keys_out, uint32_t* __restrict__ vals_out, int64_t n, int shift,
                    const uint32_t* __restrict__ gather_src, uint32_t* __restrict__ gather_dst,
