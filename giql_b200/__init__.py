@@ -5,10 +5,11 @@ The data path is hand-written sm_100a CUDA behind the C ABI in ``include/giqlb.h
 operator surface (abdenlab/giql).  There is no CPU fallback.
 """
 from ._cabi import EngineError, EngineUnavailable
+from .ranges import parse_range
 from .table import Table, Tables, canonical_offsets
 
 __all__ = ["Engine", "DeviceTable", "Dictionary", "PairResult", "Table", "Tables", "canonical_offsets",
-           "EngineError", "EngineUnavailable"]
+           "EngineError", "EngineUnavailable", "Session", "UnsupportedQuery", "parse_range"]
 
 
 def __getattr__(name):
@@ -17,4 +18,8 @@ def __getattr__(name):
         from . import engine
 
         return getattr(engine, name)
+    if name in ("Session", "UnsupportedQuery", "EngineBackend"):
+        from . import frontend
+
+        return getattr(frontend, name)
     raise AttributeError(name)

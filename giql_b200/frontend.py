@@ -1,0 +1,857 @@
+"""A minimal GIQL front-end for the B200 engine: query string in, rows out, without sqlglot.
+
+The reference's parser/AST (``giql.dialect``, ``giql.expressions``) is reused as-is whenever ``giql`` is importable
+(INTEGRATION.md shows the ``@giql.register(B200Target, ...)`` binding).  This module is the fallback SURVEY.md §8(f)-1
+asks for: a small recursive-descent parser for the operator surface users actually write and a
+binder that maps every recognised shape onto ONE engine operator call, evaluating projections, DISTINCT, ORDER BY and
+LIMIT on the host.  Anything else raises :class:`UnsupportedQuery` — the analogue of the reference's expanders
+declining a shape to the generic SQL path (``src/giql/expanders/intersects_duckdb.py:618-804``).
+
+Recognised shapes (GIQL semantics cited per branch in :class:`Session`):
+
+* ``FROM a [x] [INNER|LEFT|SEMI|ANTI] JOIN b [y] ON x.interval INTERSECTS|CONTAINS|WITHIN y.interval`` and the comma form
+  ``FROM a x, b y WHERE x.interval INTERSECTS y.interval``
+* ``FROM t WHERE interval INTERSECTS|CONTAINS|WITHIN 'chr1:100-200'`` and ``... INTERSECTS ANY|ALL(...)``
+* ``FROM a x CROSS JOIN LATERAL NEAREST(b, reference := x.interval[, k, max_distance, stranded, signed]) [y]`` (repeatable)
+* ``FROM a x JOIN b y ON x.chrom = y.chrom WHERE DISTANCE(x.interval, y.interval[, ...]) < n``
+* ``SELECT ..., CLUSTER(interval[, d][, stranded := true]) AS c FROM t``; ``SELECT MERGE(interval[, d][, stranded := true])[, COUNT(*)] FROM t``
+* ``FROM DISJOIN(t[, ref])``;  ``WITH name AS (SELECT * FROM t) ...``;  a derived table ``FROM (<query>) alias``
+* projections ``*``, ``x.*``, ``[x.]col [AS name]``, ``DISTANCE(x.interval, y.interval[, ...]) [AS name]``; ``DISTINCT``;
+  ``ORDER BY col [DESC]``; ``LIMIT n``
+
+A *backend* supplies the operators on plain dict tables (``{"chrom": [...], "start": [...], "end": [...], ...}``):
+:class:`EngineBackend` is the product (CUDA through the C ABI); the test-suite plugs its CPU oracle in the same seat.
+"""
+from __future__ import annotations
+
+import re
+from typing import Any, Optional
+
+import numpy as np
+import torch
+
+from .ranges import parse_range
+from .table import Table, canonical_offsets
+
+
+class UnsupportedQuery(ValueError):
+    """The query shape is outside the built-in front-end; run it through giql.transpile + a SQL engine."""
+
+
+# ---- backend over the engine -----------------------------------------------------------------------------------------
+class EngineBackend:
+    """Operator calls on dict tables -> giql_b200.Engine -> ctypes -> libgiqlb200.so -> sm_100a kernels.
+
+    Two flavours per operator: the list-returning one (``pairs``, ``exists`` ...) is the small-case interface the parity
+    tests share with the CPU oracle; the ``*_arrays`` one returns numpy arrays without per-row Python work and is what
+    :class:`Session` uses.  Uploaded tables are cached on the dict they came from, so a registered relation is sent to
+    the device once, not once per statement."""
+
+    name = "b200"
+
+    def __init__(self, engine, join_mode: str = "auto"):
+        self.e = engine
+        self.join_mode = join_mode
+
+    def _table(self, T, cfg):
+        cfg = cfg or Table("t")
+        cache = T.setdefault("__device__", {}) if isinstance(T, dict) else {}
+        key = (id(self.e), cfg.chrom_col, cfg.start_col, cfg.end_col, cfg.strand_col, cfg.coordinate_system, cfg.interval_type)
+        if key not in cache:
+            data = {cfg.chrom_col: T["chrom"], cfg.start_col: T["start"], cfg.end_col: T["end"]}
+            if "strand" in T and cfg.strand_col:
+                data[cfg.strand_col] = T["strand"]
+            cache[key] = self.e.table(data, cfg)
+        return cache[key]
+
+    # -- array flavour (numpy in, numpy out)
+    def pair_arrays(self, L, R, op="intersects", lcfg=None, rcfg=None):
+        l, r = self._table(L, lcfg), self._table(R, rcfg)
+        res = self.e.intersects(l, r, mode=self.join_mode) if op == "intersects" else (self.e.contains if op == "contains" else self.e.within)(l, r)
+        return res.to_host()
+
+    def exists_array(self, L, R, lcfg=None, rcfg=None):
+        return self.e.exists(self._table(L, lcfg), self._table(R, rcfg)).cpu().numpy().astype(bool)
+
+    def counts_array(self, L, R, lcfg=None, rcfg=None):
+        return self.e.count_overlaps(self._table(L, lcfg), self._table(R, rcfg)).cpu().numpy()
+
+    def distance_arrays(self, A, B, a_rows, b_rows, acfg=None, bcfg=None, stranded=False, signed=False):
+        """(distance int64, valid bool) for the paired rows ``A[a_rows[i]]``, ``B[b_rows[i]]``"""
+        dev = self.e.device
+        ia, ib = (torch.from_numpy(np.ascontiguousarray(x, dtype=np.int64)).to(dev) for x in (a_rows, b_rows))
+        d, v = self.e.distance(self._table(A, acfg), self._table(B, bcfg), ia, ib, stranded=stranded, signed=signed)
+        return d.cpu().numpy().astype(np.int64), v.cpu().numpy().astype(bool)
+
+    def nearest_arrays(self, Q, T, qcfg=None, tcfg=None, k=1, max_distance=None, stranded=False, signed=False):
+        res = self.e.nearest(self._table(Q, qcfg), self._table(T, tcfg), k=k, max_distance=max_distance, stranded=stranded, signed=signed)
+        return tuple(x.cpu().numpy() for x in (res.query_rows, res.target_rows, res.distance, res.valid))
+
+    def cluster_array(self, T, distance=0, stranded=False):
+        return self.e.cluster(self._table(T, None), distance=distance, stranded=stranded).cpu().numpy()
+
+    # -- list flavour (shared with the oracle backend of the test-suite)
+    def pairs(self, L, R, lcfg=None, rcfg=None):
+        l, r = self.pair_arrays(L, R, "intersects", lcfg, rcfg)
+        return sorted(zip(l.tolist(), r.tolist()))
+
+    def spatial_pairs(self, L, R, op, lcfg=None, rcfg=None):
+        l, r = self.pair_arrays(L, R, op, lcfg, rcfg)
+        return sorted(zip(l.tolist(), r.tolist()))
+
+    def exists(self, L, R, lcfg=None, rcfg=None):
+        return self.exists_array(L, R, lcfg, rcfg).tolist()
+
+    def counts(self, L, R, lcfg=None, rcfg=None):
+        return self.counts_array(L, R, lcfg, rcfg).tolist()
+
+    def distance(self, A, B, acfg=None, bcfg=None, stranded=False, signed=False):
+        d, v = self.e.distance(self._table(A, acfg), self._table(B, bcfg), stranded=stranded, signed=signed)
+        return [int(x) if ok else None for x, ok in zip(d.cpu().tolist(), v.cpu().tolist())]
+
+    def nearest(self, Q, T, qcfg=None, tcfg=None, k=1, max_distance=None, stranded=False, signed=False):
+        res = self.e.nearest(self._table(Q, qcfg), self._table(T, tcfg), k=k, max_distance=max_distance,
+                             stranded=stranded, signed=signed)
+        return res.rows()
+
+    def cluster(self, T, distance=0, stranded=False):
+        return self.cluster_array(T, distance, stranded).tolist()
+
+    def merge(self, T, distance=0, stranded=False):
+        return self.e.merge(self._table(T, None), distance=distance, stranded=stranded).rows()
+
+    def disjoin(self, T, REF=None, tcfg=None, rcfg=None):
+        res = self.e.disjoin(self._table(T, tcfg), None if REF is None else self._table(REF, rcfg))
+        return res.rows()
+
+
+# ---- tokenizer / parser -------------------------------------------------------------------------------------------------
+_TOKEN = re.compile(r"""\s*(?:(?P<str>'(?:[^']|'')*')|(?P<qid>"[^"]*")|(?P<num>-?\d+)|(?P<op>:=|=>|<=|>=|<>|!=|[(),.*=<>;])|(?P<id>[A-Za-z_][A-Za-z_0-9]*))""")
+_KEYWORDS = {"SELECT", "DISTINCT", "FROM", "WHERE", "JOIN", "INNER", "LEFT", "SEMI", "ANTI", "CROSS", "LATERAL", "ON", "AS", "AND",
+             "ORDER", "BY", "LIMIT", "DESC", "ASC", "WITH", "INTERSECTS", "CONTAINS", "WITHIN", "ANY", "ALL", "SOME", "IS", "NULL", "NOT",
+             "OUTER", "GROUP"}
+
+
+def _tokenize(text: str):
+    out, pos = [], 0
+    text = text.strip().rstrip(";")
+    while pos < len(text):
+        m = _TOKEN.match(text, pos)
+        if not m or m.end() == pos:
+            raise UnsupportedQuery(f"cannot tokenize near {text[pos:pos + 20]!r}")
+        pos = m.end()
+        if m.group("str") is not None:
+            out.append(("str", m.group("str")[1:-1].replace("''", "'")))
+        elif m.group("qid") is not None:
+            out.append(("id", m.group("qid")[1:-1]))
+        elif m.group("num") is not None:
+            out.append(("num", int(m.group("num"))))
+        elif m.group("op") is not None:
+            out.append(("op", m.group("op")))
+        else:
+            word = m.group("id")
+            out.append(("kw", word.upper()) if word.upper() in _KEYWORDS else ("id", word))
+    return out
+
+
+class _Parser:
+    def __init__(self, tokens):
+        self.t, self.i = tokens, 0
+
+    def peek(self, k=0):
+        return self.t[self.i + k] if self.i + k < len(self.t) else ("eof", None)
+
+    def at(self, kind, val=None, k=0):
+        tk = self.peek(k)
+        return tk[0] == kind and (val is None or tk[1] == val)
+
+    def take(self, kind=None, val=None):
+        tk = self.peek()
+        if (kind and tk[0] != kind) or (val is not None and tk[1] != val):
+            raise UnsupportedQuery(f"expected {val or kind}, found {tk[1]!r}")
+        self.i += 1
+        return tk[1]
+
+    def accept(self, kind, val=None):
+        if self.at(kind, val):
+            self.i += 1
+            return True
+        return False
+
+    # query := [WITH name AS (query) {, ...}] select
+    def query(self):
+        ctes = {}
+        if self.accept("kw", "WITH"):
+            while True:
+                name = self.take("id")
+                self.take("kw", "AS")
+                self.take("op", "(")
+                ctes[name] = self.query()
+                self.take("op", ")")
+                if not self.accept("op", ","):
+                    break
+        q = self.select()
+        q["ctes"] = ctes
+        return q
+
+    def select(self):
+        self.take("kw", "SELECT")
+        q: dict[str, Any] = {"distinct": self.accept("kw", "DISTINCT"), "proj": [], "joins": [], "where": [], "order": [], "limit": None}
+        while True:
+            q["proj"].append(self.projection())
+            if not self.accept("op", ","):
+                break
+        self.take("kw", "FROM")
+        q["source"] = self.source()
+        while True:
+            if self.accept("op", ","):
+                q["joins"].append({"kind": "comma", "source": self.source()})
+            elif self.at("kw", "CROSS"):
+                self.take("kw", "CROSS"); self.take("kw", "JOIN"); self.take("kw", "LATERAL")
+                q["joins"].append({"kind": "nearest", **self.nearest_call()})
+            elif self.at("kw", "JOIN") or self.at("kw", "INNER") or self.at("kw", "LEFT") or self.at("kw", "SEMI") or self.at("kw", "ANTI"):
+                kind = "inner"
+                if not self.at("kw", "JOIN"):
+                    kind = self.take("kw").lower()
+                    self.accept("kw", "OUTER")
+                self.take("kw", "JOIN")
+                src = self.source()
+                self.take("kw", "ON")
+                q["joins"].append({"kind": kind, "source": src, "on": self.condition()})
+            else:
+                break
+        if self.accept("kw", "WHERE"):
+            while True:
+                q["where"].append(self.condition())
+                if not self.accept("kw", "AND"):
+                    break
+        if self.at("kw", "GROUP"):
+            raise UnsupportedQuery("GROUP BY is finished by the SQL engine, not by the built-in front-end")
+        if self.accept("kw", "ORDER"):
+            self.take("kw", "BY")
+            while True:
+                col = self.column_ref()
+                desc = self.accept("kw", "DESC")
+                if not desc:
+                    self.accept("kw", "ASC")
+                q["order"].append((col, desc))
+                if not self.accept("op", ","):
+                    break
+        if self.accept("kw", "LIMIT"):
+            q["limit"] = self.take("num")
+        return q
+
+    def source(self):
+        if self.accept("op", "("):
+            sub = self.query()
+            self.take("op", ")")
+            self.accept("kw", "AS")
+            return {"kind": "subquery", "query": sub, "alias": self.take("id")}
+        name = self.take("id")
+        if name.upper() == "DISJOIN" and self.at("op", "("):
+            self.take("op", "(")
+            target = self.take("id")
+            ref = self.take("id") if self.accept("op", ",") else None
+            self.take("op", ")")
+            return {"kind": "disjoin", "table": target, "reference": ref, "alias": self.alias() or target}
+        return {"kind": "table", "table": name, "alias": self.alias() or name}
+
+    def alias(self):
+        if self.accept("kw", "AS"):
+            return self.take("id")
+        if self.at("id"):
+            return self.take("id")
+        return None
+
+    def named_args(self):
+        """`name := value` / `name => value` pairs up to the closing parenthesis (src/giql/expressions.py:184-194)."""
+        args = {}
+        while self.accept("op", ","):
+            if self.at("id") and (self.at("op", ":=", 1) or self.at("op", "=>", 1)):
+                key = self.take("id").lower()
+                self.take("op")
+                args[key] = self.scalar()
+            else:
+                args.setdefault("_positional", []).append(self.scalar())
+        return args
+
+    def scalar(self):
+        if self.at("num"):
+            return self.take("num")
+        if self.at("str"):
+            return self.take("str")
+        if self.at("id") and self.at("op", ".", 1):
+            return ("col",) + self.column_ref()
+        word = self.take("id")
+        if word.lower() in ("true", "false"):
+            return word.lower() == "true"
+        return ("col", None, word)
+
+    def nearest_call(self):
+        if self.take("id").upper() != "NEAREST":
+            raise UnsupportedQuery("only NEAREST(...) may follow CROSS JOIN LATERAL")
+        self.take("op", "(")
+        target = self.take("id")
+        args = self.named_args()
+        self.take("op", ")")
+        ref = args.get("reference")
+        if not (isinstance(ref, tuple) and ref[0] == "col" and ref[2] == "interval"):
+            raise UnsupportedQuery("NEAREST needs reference := <alias>.interval")
+        alias = self.alias()
+        return {"target": target, "ref_alias": ref[1], "alias": alias, "k": int(args.get("k", 1)), "max_distance": args.get("max_distance"),
+                "stranded": bool(args.get("stranded", False)), "signed": bool(args.get("signed", False))}
+
+    def column_ref(self):
+        a = self.take("id")
+        if self.accept("op", "."):
+            if self.accept("op", "*"):
+                return (a, "*")
+            return (a, self.take("id"))
+        return (None, a)
+
+    def distance_call(self):
+        self.take("op", "(")
+        a = self.column_ref()
+        self.take("op", ",")
+        b = self.column_ref()
+        args = self.named_args()
+        self.take("op", ")")
+        if a[1] != "interval" or b[1] != "interval":
+            raise UnsupportedQuery("DISTANCE takes two <alias>.interval operands")
+        return {"a": a[0], "b": b[0], "stranded": bool(args.get("stranded", False)), "signed": bool(args.get("signed", False))}
+
+    def projection(self):
+        if self.accept("op", "*"):
+            return {"kind": "star", "alias": None}
+        if self.at("id") and self.at("op", "(", 1):
+            fn = self.take("id").upper()
+            if fn == "DISTANCE":
+                item = {"kind": "distance", **self.distance_call()}
+            elif fn in ("CLUSTER", "MERGE"):
+                self.take("op", "(")
+                col = self.column_ref()
+                if col[1] != "interval":
+                    raise UnsupportedQuery(f"{fn} takes the genomic column")
+                args = self.named_args()
+                self.take("op", ")")
+                pos = args.get("_positional", [])
+                item = {"kind": fn.lower(), "distance": int(pos[0]) if pos else int(args.get("distance", 0) or 0),
+                        "stranded": bool(args.get("stranded", False))}
+            elif fn == "COUNT":
+                self.take("op", "(")
+                self.take("op", "*")
+                self.take("op", ")")
+                item = {"kind": "count_star"}
+            else:
+                raise UnsupportedQuery(f"function {fn} is not handled by the built-in front-end")
+        else:
+            ref = self.column_ref()
+            item = {"kind": "star", "alias": ref[0]} if ref[1] == "*" else {"kind": "col", "alias": ref[0], "col": ref[1]}
+        if self.accept("kw", "AS"):
+            item["name"] = self.take("id")
+        return item
+
+    def condition(self):
+        if self.at("id") and self.peek()[1].upper() == "DISTANCE" and self.at("op", "(", 1):
+            self.take("id")
+            d = self.distance_call()
+            op = self.take("op")
+            return {"kind": "distance_cmp", **d, "op": op, "value": self.take("num")}
+        left = self.column_ref()
+        if self.accept("kw", "IS"):
+            neg = self.accept("kw", "NOT")
+            self.take("kw", "NULL")
+            return {"kind": "is_null", "col": left, "negated": neg}
+        if self.at("kw", "INTERSECTS") or self.at("kw", "CONTAINS") or self.at("kw", "WITHIN"):
+            op = self.take("kw").lower()
+            if left[1] != "interval":
+                raise UnsupportedQuery("spatial predicates take the genomic column")
+            if self.at("str"):
+                return {"kind": "literal", "op": op, "alias": left[0], "quant": None, "ranges": [self.take("str")]}
+            if self.at("kw", "ANY") or self.at("kw", "ALL") or self.at("kw", "SOME"):
+                quant = self.take("kw")
+                self.take("op", "(")
+                ranges = [self.take("str")]
+                while self.accept("op", ","):
+                    ranges.append(self.take("str"))
+                self.take("op", ")")
+                return {"kind": "literal", "op": op, "alias": left[0], "quant": "ALL" if quant == "ALL" else "ANY", "ranges": ranges}
+            right = self.column_ref()
+            if right[1] != "interval":
+                raise UnsupportedQuery("spatial predicates compare two genomic columns or a column and a literal range")
+            return {"kind": "spatial", "op": op, "left": left[0], "right": right[0]}
+        op = self.take("op")
+        right = self.column_ref()
+        return {"kind": "compare", "op": op, "left": left, "right": right}
+
+
+def parse(query: str) -> dict:
+    p = _Parser(_tokenize(query))
+    q = p.query()
+    if not p.at("eof"):
+        raise UnsupportedQuery(f"unexpected {p.peek()[1]!r}")
+    return q
+
+
+# ---- binder / evaluator ---------------------------------------------------------------------------------------------------
+def _column(values) -> np.ndarray:
+    """host column: int64 / float / bool arrays stay typed, anything holding strings or NULLs becomes an object array"""
+    if isinstance(values, np.ndarray) and values.dtype != object and values.dtype.kind not in "US":
+        return values
+    if hasattr(values, "to_numpy") and not isinstance(values, np.ndarray):
+        values = values.to_numpy()
+    seq = values.tolist() if isinstance(values, np.ndarray) else list(values)
+    if seq and all(isinstance(v, (int, np.integer)) and not isinstance(v, bool) for v in seq):
+        return np.asarray(seq, dtype=np.int64)
+    out = np.empty(len(seq), dtype=object)
+    out[:] = seq
+    return out
+
+
+class Result:
+    """Columnar result: ``columns`` (names, duplicates allowed as in SQL) and ``arrays``; ``rows`` = list of tuples."""
+
+    def __init__(self, columns: list[str], arrays: list[np.ndarray]):
+        self.columns, self.arrays = columns, arrays
+
+    @property
+    def rows(self) -> list[tuple]:
+        if not self.arrays:
+            return []
+        return list(zip(*(a.tolist() for a in self.arrays)))
+
+    def take(self, sel) -> "Result":
+        return Result(self.columns, [a[sel] for a in self.arrays])
+
+    def to_pydict(self) -> dict:
+        return {c: a.tolist() for c, a in zip(self.columns, self.arrays)}
+
+    def __iter__(self):
+        return iter(self.rows)
+
+    def __len__(self):
+        return len(self.arrays[0]) if self.arrays else 0
+
+
+class _Rel:
+    """A host relation: ordered column names + equally long numpy columns, and the Table config it came from."""
+
+    def __init__(self, cols: list[str], data: dict, config: Optional[Table] = None):
+        self.cols, self.data, self.config = cols, data, config
+        self._genomic = None
+
+    def __len__(self):
+        return len(self.data[self.cols[0]]) if self.cols else 0
+
+    def genomic(self) -> dict:
+        """the dict-table view the backends take (cached: the engine backend parks its device copy on it)"""
+        if self._genomic is None:
+            c = self.config or Table("t")
+            for col in (c.chrom_col, c.start_col, c.end_col):
+                if col not in self.data:
+                    raise ValueError(f"genomic column {col!r} is missing")
+            g = {"chrom": self.data[c.chrom_col], "start": self.data[c.start_col], "end": self.data[c.end_col]}
+            if c.strand_col and c.strand_col in self.data:
+                g["strand"] = self.data[c.strand_col]
+            self._genomic = g
+        return self._genomic
+
+
+class _Frame:
+    """Joined rows in columnar form: per alias an int64 row-index array into its relation (-1 = the NULL row of an
+    outer join) plus computed columns (NEAREST's distance, DISJOIN's segment)."""
+
+    def __init__(self):
+        self.order: list[str] = []
+        self.rels: dict[str, _Rel] = {}
+        self.idx: dict[str, np.ndarray] = {}
+        self.extra: dict[str, dict[str, np.ndarray]] = {}
+
+    def add(self, alias, rel, idx, extra=None):
+        if alias in self.rels:
+            raise UnsupportedQuery(f"alias {alias!r} is used twice")
+        self.order.append(alias)
+        self.rels[alias], self.idx[alias], self.extra[alias] = rel, idx, dict(extra or {})
+
+    def __len__(self):
+        return len(self.idx[self.order[0]])
+
+    def take(self, sel):
+        for a in self.order:
+            self.idx[a] = self.idx[a][sel]
+            self.extra[a] = {c: v[sel] for c, v in self.extra[a].items()}
+
+    def schema(self, alias) -> list[str]:
+        return list(self.rels[alias].cols) + list(self.extra[alias])
+
+    def resolve(self, alias, col) -> str:
+        for a in ([alias] if alias else self.order):
+            if a not in self.rels:
+                raise ValueError(f"unknown alias {a!r}")
+            if col in self.extra[a] or col in self.rels[a].data:
+                return a
+        raise ValueError(f"unknown column {col!r}")
+
+    def column(self, alias, col) -> np.ndarray:
+        if col in self.extra[alias]:
+            return self.extra[alias][col]
+        src, ix = self.rels[alias].data[col], self.idx[alias]
+        if len(ix) and ix.min() < 0:
+            out = np.empty(len(ix), dtype=object)
+            ok = ix >= 0
+            out[ok] = src[ix[ok]].tolist()
+            out[~ok] = None
+            return out
+        return src[ix]
+
+    def genomic(self, alias) -> dict:
+        g = self.rels[alias].genomic()
+        return {k: v[self.idx[alias]] for k, v in g.items() if not k.startswith("__")}
+
+
+def _expand(frame_rows: np.ndarray, l: np.ndarray, r: np.ndarray, keep_unmatched: bool):
+    """Join the frame (its per-row id ``frame_rows`` into the left relation) with the pair list (l, r): returns
+    (frame row to repeat, matched right row or -1 for the NULL row of a LEFT join)."""
+    l, r = np.asarray(l, dtype=np.int64), np.asarray(r, dtype=np.int64)
+    order = np.lexsort((r, l))
+    l, r = l[order], r[order]
+    lo, hi = np.searchsorted(l, frame_rows, "left"), np.searchsorted(l, frame_rows, "right")
+    cnt = hi - lo
+    out = np.maximum(cnt, 1) if keep_unmatched else cnt
+    rep = np.repeat(np.arange(len(frame_rows)), out)
+    within = np.arange(len(rep)) - np.repeat(np.cumsum(out) - out, out)
+    pos = np.repeat(lo, out) + within
+    matched = np.repeat(cnt, out) > 0
+    right = np.where(matched, r[np.minimum(pos, max(len(r) - 1, 0))] if len(r) else -1, -1)
+    return rep, right
+
+
+def _pairs(be, L, R, op, lcfg, rcfg):
+    if hasattr(be, "pair_arrays"):
+        return be.pair_arrays(L, R, op, lcfg, rcfg)
+    p = be.pairs(L, R, lcfg, rcfg) if op == "intersects" else be.spatial_pairs(L, R, op, lcfg, rcfg)
+    a = np.asarray(p, dtype=np.int64).reshape(-1, 2)
+    return a[:, 0], a[:, 1]
+
+
+def _exists(be, L, R, lcfg, rcfg):
+    return be.exists_array(L, R, lcfg, rcfg) if hasattr(be, "exists_array") else np.asarray(be.exists(L, R, lcfg, rcfg), dtype=bool)
+
+
+def _counts(be, L, R, lcfg, rcfg):
+    return be.counts_array(L, R, lcfg, rcfg) if hasattr(be, "counts_array") else np.asarray(be.counts(L, R, lcfg, rcfg), dtype=np.int64)
+
+
+def _distance(be, a: _Rel, b: _Rel, ia, ib, stranded, signed):
+    """object column of distances (None = SQL NULL) for the paired rows"""
+    if not len(ia):
+        return np.empty(0, dtype=object)
+    if hasattr(be, "distance_arrays"):
+        d, v = be.distance_arrays(a.genomic(), b.genomic(), ia, ib, a.config, b.config, stranded=stranded, signed=signed)
+        if v.all():
+            return d
+        out = np.empty(len(d), dtype=object)
+        out[:] = d.tolist()
+        out[~v] = None
+        return out
+    ga, gb = a.genomic(), b.genomic()
+    pa = {c: x[ia].tolist() for c, x in ga.items() if not c.startswith("__")}
+    pb = {c: x[ib].tolist() for c, x in gb.items() if not c.startswith("__")}
+    return _column(be.distance(pa, pb, a.config, b.config, stranded=stranded, signed=signed))
+
+
+def _nearest(be, Q: _Rel, T: _Rel, j):
+    kw = dict(k=j["k"], max_distance=j["max_distance"], stranded=j["stranded"], signed=j["signed"])
+    if hasattr(be, "nearest_arrays"):
+        q, t, d, v = be.nearest_arrays(Q.genomic(), T.genomic(), Q.config, T.config, **kw)
+        dist = d.astype(np.int64)
+        if not v.all():
+            dist = _column([x if ok else None for x, ok in zip(d.tolist(), v.tolist())])
+        return q.astype(np.int64), t.astype(np.int64), dist
+    res = be.nearest(Q.genomic(), T.genomic(), Q.config, T.config, **kw)
+    return (np.asarray([x[0] for x in res], dtype=np.int64), np.asarray([x[1] for x in res], dtype=np.int64), _column([x[2] for x in res]))
+
+
+_CMP = {"<": np.less, "<=": np.less_equal, ">": np.greater, ">=": np.greater_equal, "=": np.equal}
+
+
+class Session:
+    """Registered tables + ``execute(giql_query)``.  ``backend`` defaults to the CUDA engine on device 0."""
+
+    def __init__(self, backend=None):
+        self._backend = backend
+        self.tables: dict[str, _Rel] = {}
+
+    @property
+    def backend(self):
+        if self._backend is None:
+            from .engine import Engine
+
+            self._backend = EngineBackend(Engine(0))
+        return self._backend
+
+    def register(self, name: str, data, table: Optional[Table] = None, columns: Optional[list[str]] = None):
+        """``data``: mapping column -> sequence / numpy array (a pandas DataFrame or pyarrow Table works too).
+        ``table``: the reference's column-mapping contract (src/giql/table.py:16-93); defaults to chrom/start/end/strand."""
+        if hasattr(data, "to_pydict"):
+            data = data.to_pydict()
+        elif hasattr(data, "to_dict") and not isinstance(data, dict):
+            data = data.to_dict(orient="list")
+        cols = columns or list(data.keys())
+        rel = _Rel(cols, {c: _column(data[c]) for c in cols}, table)
+        if len({len(v) for v in rel.data.values()}) > 1:
+            raise ValueError("columns differ in length")
+        self.tables[name] = rel
+
+    def execute(self, query: str) -> Result:
+        return self._run(parse(query))
+
+    # -- sources
+    @staticmethod
+    def _derived(res: Result) -> _Rel:
+        if len(set(res.columns)) != len(res.columns):
+            raise UnsupportedQuery("a derived table with duplicate column names is ambiguous")
+        return _Rel(list(res.columns), dict(zip(res.columns, res.arrays)))
+
+    def _relation(self, q, src) -> _Rel:
+        if src["kind"] == "subquery":
+            return self._derived(self._run(src["query"]))
+        name = src["table"]
+        if name in q["ctes"]:
+            return self._derived(self._run(q["ctes"][name]))
+        if name not in self.tables:
+            raise ValueError(f"unknown table {name!r}")
+        return self.tables[name]
+
+    def _run(self, q) -> Result:
+        be = self.backend
+        src = q["source"]
+        f = _Frame()
+        if src["kind"] == "disjoin":
+            # DISJOIN(t[, ref])   (src/giql/expanders/disjoin.py:102-202; output in the target's encoding, :139-141)
+            t = self._relation(q, {"kind": "table", "table": src["table"]})
+            ref = self._relation(q, {"kind": "table", "table": src["reference"]}) if src["reference"] else None
+            sadj, eadj = canonical_offsets(t.config)
+            segs = []
+            if len(t) and (ref is None or len(ref)):
+                segs = be.disjoin(t.genomic(), None if ref is None else ref.genomic(), t.config, None if ref is None else ref.config)
+            rows = np.asarray([s[0] for s in segs], dtype=np.int64)
+            f.add(src["alias"], t, rows, {
+                "disjoin_chrom": t.genomic()["chrom"][rows],
+                "disjoin_start": np.asarray([s[1] - sadj for s in segs], dtype=np.int64),
+                "disjoin_end": np.asarray([s[2] - eadj for s in segs], dtype=np.int64)})
+        else:
+            base = self._relation(q, src)
+            f.add(src["alias"], base, np.arange(len(base), dtype=np.int64))
+        where = list(q["where"])
+        for j in q["joins"]:
+            if j["kind"] == "nearest":
+                self._join_nearest(q, f, j)
+                continue
+            right = self._relation(q, j["source"])
+            ra, la = j["source"]["alias"], f.order[0]
+            left = f.rels[la]
+            on, kind = j.get("on"), j["kind"]
+            if kind == "comma":
+                sp = [w for w in where if w["kind"] == "spatial" and {w["left"], w["right"]} == {la, ra}]
+                if len(sp) != 1:
+                    raise UnsupportedQuery("a comma join needs exactly one spatial predicate between the two tables")
+                on, kind = sp[0], "inner"
+                where.remove(on)
+            if on["kind"] == "compare":
+                # chromosome equi-join feeding DISTANCE (docs/dialect/distance-operators.rst:130-155): quadratic by nature
+                chrom = (left.config or Table("t")).chrom_col
+                if not (on["op"] == "=" and kind == "inner" and on["left"][1] == chrom and on["right"][1] == (right.config or Table("t")).chrom_col
+                        and {on["left"][0], on["right"][0]} == {la, ra}):
+                    raise UnsupportedQuery("only `a.chrom = b.chrom` equi-joins are handled")
+                lc, rc = f.genomic(la)["chrom"], right.genomic()["chrom"]
+                names, codes = np.unique(np.concatenate([lc.astype(str), rc.astype(str)]), return_inverse=True)
+                cl, cr = codes[: len(lc)], codes[len(lc):]
+                by = np.argsort(cr, kind="stable")
+                lo, hi = np.searchsorted(cr[by], cl, "left"), np.searchsorted(cr[by], cl, "right")
+                cnt = hi - lo
+                rep = np.repeat(np.arange(len(lc)), cnt)
+                pos = np.repeat(lo, cnt) + np.arange(len(rep)) - np.repeat(np.cumsum(cnt) - cnt, cnt)
+                f.take(rep)
+                f.add(ra, right, by[pos].astype(np.int64))
+                continue
+            if on["kind"] != "spatial" or {on["left"], on["right"]} != {la, ra}:
+                raise UnsupportedQuery("JOIN ... ON needs `<left>.interval <op> <right>.interval`")
+            op = on["op"]
+            if on["left"] == ra and op != "intersects":                 # `b.interval CONTAINS a.interval` == a WITHIN b
+                op = "within" if op == "contains" else "contains"
+            nonempty = len(left) and len(right)
+            if kind in ("semi", "anti"):
+                # src/giql/expanders/intersects_duckdb.py:1254-1282: one row per qualifying LEFT row; ANTI keeps left-only chroms
+                if op != "intersects":
+                    raise UnsupportedQuery("SEMI / ANTI joins are bound for INTERSECTS only")
+                flags = _exists(be, left.genomic(), right.genomic(), left.config, right.config) if nonempty else np.zeros(len(left), bool)
+                f.take(flags[f.idx[la]] == (kind == "semi"))
+                continue
+            # src/giql/expanders/intersects.py:149-154 (INTERSECTS), :155-166 (CONTAINS / WITHIN)
+            l, r = _pairs(be, left.genomic(), right.genomic(), op, left.config, right.config) if nonempty else (np.zeros(0, np.int64),) * 2
+            rep, rrow = _expand(f.idx[la], l, r, keep_unmatched=(kind == "left"))
+            f.take(rep)
+            f.add(ra, right, rrow)
+        for w in where:
+            self._filter(f, w)
+        return self._finish(q, f)
+
+    def _join_nearest(self, q, f: _Frame, j):
+        """src/giql/expanders/nearest.py:336-397 — one engine call per NEAREST, joined back on the query row"""
+        tgt = self._relation(q, {"kind": "table", "table": j["target"]})
+        qa = j["ref_alias"] or f.order[0]
+        if qa not in f.rels or f.extra[qa]:
+            raise UnsupportedQuery(f"NEAREST reference alias {qa!r} is not a base table of this query")
+        Q = f.rels[qa]
+        if len(Q) and len(tgt):
+            qi, ti, dist = _nearest(self.backend, Q, tgt, j)
+        else:
+            qi, ti, dist = np.zeros(0, np.int64), np.zeros(0, np.int64), np.zeros(0, np.int64)
+        order = np.argsort(qi, kind="stable")                              # keep the engine's per-query rank order
+        qi, ti, dist = qi[order], ti[order], dist[order]
+        lo, hi = np.searchsorted(qi, f.idx[qa], "left"), np.searchsorted(qi, f.idx[qa], "right")
+        cnt = hi - lo
+        rep = np.repeat(np.arange(len(f)), cnt)
+        pos = np.repeat(lo, cnt) + np.arange(len(rep)) - np.repeat(np.cumsum(cnt) - cnt, cnt)
+        f.take(rep)
+        f.add(j["alias"] or f"__nearest{len(f.order)}", tgt, ti[pos], {"distance": dist[pos]})
+
+    def _filter(self, f: _Frame, w):
+        be = self.backend
+        if w["kind"] == "literal":
+            # src/giql/expanders/intersects.py:85-133 (literal range), :243-270 (ANY / ALL)
+            alias = w["alias"] or f.order[0]
+            if alias not in f.rels:
+                raise ValueError(f"unknown alias {alias!r}")
+            rel = f.rels[alias]
+            ranges = [parse_range(r) for r in w["ranges"]]
+            lit = {"chrom": _column([r[0] for r in ranges]), "start": _column([r[1] for r in ranges]), "end": _column([r[2] for r in ranges])}
+            if not len(rel):
+                keep = np.zeros(0, bool)
+            elif w["op"] == "intersects":
+                if w["quant"] == "ALL":
+                    keep = _counts(be, rel.genomic(), lit, rel.config, None) == len(ranges)
+                else:
+                    keep = _exists(be, rel.genomic(), lit, rel.config, None)
+            else:
+                if len(ranges) != 1:
+                    raise UnsupportedQuery("CONTAINS / WITHIN take one literal range")
+                # the column join against the one-row table of the literal (intersects.py:155-166 on a literal operand)
+                hit, _ = _pairs(be, rel.genomic(), lit, w["op"], rel.config, None)
+                keep = np.zeros(len(rel), bool)
+                keep[np.asarray(hit, dtype=np.int64)] = True
+            ix = f.idx[alias]
+            f.take((ix >= 0) & keep[np.maximum(ix, 0)] if len(keep) else np.zeros(len(ix), bool))
+        elif w["kind"] == "distance_cmp":
+            for a in (w["a"], w["b"]):
+                if a not in f.rels:
+                    raise ValueError(f"unknown alias {a!r}")
+            d = _distance(be, f.rels[w["a"]], f.rels[w["b"]], f.idx[w["a"]], f.idx[w["b"]], w["stranded"], w["signed"])
+            if w["op"] not in _CMP:
+                raise UnsupportedQuery(f"DISTANCE comparison {w['op']}")
+            if d.dtype == object:
+                ok = np.array([x is not None for x in d], dtype=bool)
+                keep = np.zeros(len(d), bool)
+                keep[ok] = _CMP[w["op"]](d[ok].astype(np.int64), w["value"])
+            else:
+                keep = _CMP[w["op"]](d, w["value"])
+            f.take(keep)
+        elif w["kind"] == "is_null":
+            alias = f.resolve(*w["col"])
+            col = f.column(alias, w["col"][1])
+            null = np.array([x is None for x in col], dtype=bool) if col.dtype == object else np.zeros(len(col), bool)
+            f.take(null != w["negated"])
+        elif w["kind"] == "spatial":
+            raise UnsupportedQuery("a residual spatial predicate between already joined tables is not handled")
+        else:
+            raise UnsupportedQuery("general WHERE comparisons are finished by the SQL engine")
+
+    def _finish(self, q, f: _Frame) -> Result:
+        """projection (incl. CLUSTER / MERGE / DISTANCE), DISTINCT, ORDER BY, LIMIT"""
+        be = self.backend
+        proj = q["proj"]
+        kinds = {p["kind"] for p in proj}
+        if kinds & {"merge", "cluster"} and len(f.order) != 1:
+            raise UnsupportedQuery("CLUSTER / MERGE are bound over a single FROM source")
+        if "merge" in kinds:
+            # src/giql/expanders/merge.py:183-439: (chrom[, strand], start, end[, COUNT(*)]), default ORDER BY chrom, start
+            m = next(p for p in proj if p["kind"] == "merge")
+            if any(p["kind"] not in ("merge", "count_star") for p in proj) or q["distinct"]:
+                raise UnsupportedQuery("MERGE is bound for `SELECT MERGE(interval...)[, COUNT(*)] FROM t`")
+            g = f.genomic(f.order[0])
+            if m["stranded"] and "strand" not in g:
+                raise ValueError("MERGE(stranded := true) needs a strand column")
+            rows = be.merge(g, m["distance"], m["stranded"]) if len(f) else []
+            width = 4 if m["stranded"] else 3
+            out = [tuple(r[:width]) + ((r[-1],) if "count_star" in kinds else ()) for r in rows]
+            out.sort(key=lambda r: (r[0], r[width - 2]))
+            cols = ["chrom"] + (["strand"] if m["stranded"] else []) + ["start", "end"] + (["count"] if "count_star" in kinds else [])
+            return self._order_limit(q, Result(cols, [_column([r[i] for r in out]) for i in range(len(cols))]))
+        if "count_star" in kinds:
+            raise UnsupportedQuery("COUNT(*) outside MERGE is finished by the SQL engine")
+        cols: list[str] = []
+        arrays: list[np.ndarray] = []
+        for p in proj:
+            if p["kind"] == "star":
+                for a in ([p["alias"]] if p["alias"] else f.order):
+                    if a not in f.rels:
+                        raise ValueError(f"unknown alias {a!r}")
+                    for c in f.schema(a):
+                        cols.append(c)
+                        arrays.append(f.column(a, c))
+            elif p["kind"] == "col":
+                a = f.resolve(p["alias"], p["col"])
+                cols.append(p.get("name", p["col"]))
+                arrays.append(f.column(a, p["col"]))
+            elif p["kind"] == "cluster":
+                # src/giql/expanders/cluster.py:205-310, 430-434 over the rows the FROM clause produced
+                g = f.genomic(f.order[0])
+                if p["stranded"] and "strand" not in g:
+                    raise ValueError("CLUSTER(stranded := true) needs a strand column")
+                if not p["stranded"]:
+                    g.pop("strand", None)
+                if not len(f):
+                    ids = np.zeros(0, np.int64)
+                elif hasattr(be, "cluster_array"):
+                    ids = be.cluster_array(g, p["distance"], p["stranded"]).astype(np.int64)
+                else:
+                    ids = np.asarray(be.cluster({k: v.tolist() for k, v in g.items()}, p["distance"], p["stranded"]), dtype=np.int64)
+                cols.append(p.get("name", "cluster"))
+                arrays.append(ids)
+            elif p["kind"] == "distance":
+                # src/giql/expanders/_distance.py:67-117 over the joined pairs
+                for a in (p["a"], p["b"]):
+                    if a not in f.rels:
+                        raise ValueError(f"unknown alias {a!r}")
+                ia, ib = f.idx[p["a"]], f.idx[p["b"]]
+                if len(ia) and (ia.min() < 0 or ib.min() < 0):
+                    raise UnsupportedQuery("DISTANCE over the NULL side of an outer join")
+                cols.append(p.get("name", "distance"))
+                arrays.append(_distance(be, f.rels[p["a"]], f.rels[p["b"]], ia, ib, p["stranded"], p["signed"]))
+            else:
+                raise UnsupportedQuery(f"projection {p['kind']}")
+        res = Result(cols, arrays)
+        if q["distinct"]:
+            first: dict[tuple, int] = {}
+            for i, r in enumerate(res.rows):
+                first.setdefault(r, i)
+            res = res.take(np.fromiter(first.values(), dtype=np.int64, count=len(first)))
+        return self._order_limit(q, res)
+
+    @staticmethod
+    def _order_limit(q, res: Result) -> Result:
+        for (_alias, col), desc in reversed(q["order"]):
+            if col not in res.columns:
+                raise ValueError(f"ORDER BY column {col!r} is not in the select list")
+            key = res.arrays[res.columns.index(col)]
+            if key.dtype == object:                                         # NULLs last, as DuckDB orders by default
+                vals = key.tolist()
+                some = sorted((i for i in range(len(vals)) if vals[i] is not None), key=lambda i: vals[i], reverse=desc)
+                perm = np.asarray(some + [i for i in range(len(vals)) if vals[i] is None], dtype=np.int64)
+            else:
+                perm = np.argsort(-key if desc else key, kind="stable")
+            res = res.take(perm)
+        if q["limit"] is not None:
+            res = res.take(slice(0, q["limit"]))
+        return res

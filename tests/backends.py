@@ -69,59 +69,4 @@ class OracleBackend:
         return self.go.disjoin(canonicalise(T, tcfg), None if REF is None else canonicalise(REF, rcfg))
 
 
-class EngineBackend:
-    """The product path: giql_b200.Engine -> ctypes -> libgiqlb200.so -> sm_100a kernels."""
-
-    name = "b200"
-
-    def __init__(self, engine, join_mode="auto"):
-        self.e = engine
-        self.join_mode = join_mode
-
-    def _table(self, T, cfg):
-        cfg = cfg or Table("t")
-        data = {cfg.chrom_col: T["chrom"], cfg.start_col: T["start"], cfg.end_col: T["end"]}
-        if "strand" in T and cfg.strand_col:
-            data[cfg.strand_col] = T["strand"]
-        return self.e.table(data, cfg)
-
-    def pairs(self, L, R, lcfg=None, rcfg=None):
-        res = self.e.intersects(self._table(L, lcfg), self._table(R, rcfg), mode=self.join_mode)
-        l, r = res.to_host()
-        return sorted(zip(l.tolist(), r.tolist()))
-
-    def spatial_pairs(self, L, R, op, lcfg=None, rcfg=None):
-        res = (self.e.contains if op == "contains" else self.e.within)(self._table(L, lcfg), self._table(R, rcfg))
-        l, r = res.to_host()
-        return sorted(zip(l.tolist(), r.tolist()))
-
-    def range_filter(self, t, op, ranges, cfg):
-        """literal-range CONTAINS / WITHIN filter = the column join against the one-row table of the literal"""
-        lit = {"chrom": [r[0] for r in ranges], "start": [r[1] for r in ranges], "end": [r[2] for r in ranges]}
-        hit = {i for i, _ in self.spatial_pairs(t, lit, op, cfg, None)}
-        return [i in hit for i in range(len(t["start"]))]
-
-    def exists(self, L, R, lcfg=None, rcfg=None):
-        return [bool(x) for x in self.e.exists(self._table(L, lcfg), self._table(R, rcfg)).cpu().tolist()]
-
-    def counts(self, L, R, lcfg=None, rcfg=None):
-        return [int(x) for x in self.e.count_overlaps(self._table(L, lcfg), self._table(R, rcfg)).cpu().tolist()]
-
-    def distance(self, A, B, acfg=None, bcfg=None, stranded=False, signed=False):
-        d, v = self.e.distance(self._table(A, acfg), self._table(B, bcfg), stranded=stranded, signed=signed)
-        return [int(x) if ok else None for x, ok in zip(d.cpu().tolist(), v.cpu().tolist())]
-
-    def nearest(self, Q, T, qcfg=None, tcfg=None, k=1, max_distance=None, stranded=False, signed=False):
-        res = self.e.nearest(self._table(Q, qcfg), self._table(T, tcfg), k=k, max_distance=max_distance,
-                             stranded=stranded, signed=signed)
-        return res.rows()
-
-    def cluster(self, T, distance=0, stranded=False):
-        return [int(x) for x in self.e.cluster(self._table(T, None), distance=distance, stranded=stranded).cpu().tolist()]
-
-    def merge(self, T, distance=0, stranded=False):
-        return self.e.merge(self._table(T, None), distance=distance, stranded=stranded).rows()
-
-    def disjoin(self, T, REF=None, tcfg=None, rcfg=None):
-        res = self.e.disjoin(self._table(T, tcfg), None if REF is None else self._table(REF, rcfg))
-        return res.rows()
+from giql_b200.frontend import EngineBackend  # noqa: E402,F401  (the product backend lives in the package)

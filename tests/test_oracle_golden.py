@@ -19,26 +19,11 @@ from oracle import sqlite_oracle as so
 CASES = load_cases()
 
 
-class _Oracle(OracleBackend):
-    def range_filter(self, t, op, ranges, cfg):
-        from backends import canonicalise
-
-        tc = canonicalise(t, cfg)
-        (c, s, e), = ranges
-        out = []
-        for tc_, ts, te in zip(tc["chrom"], tc["start"], tc["end"]):
-            if op == "contains":      # intersects.py:108-118: start <= lit.start AND end >= lit.end
-                out.append(tc_ == c and ts <= s and te >= e)
-            else:                     # within, intersects.py:119-129
-                out.append(tc_ == c and ts >= s and te <= e)
-        return out
-
-
 @pytest.mark.parametrize("case", CASES, ids=[f"{i}:{c['test']}" for i, c in enumerate(CASES)])
 def test_cross_target_golden(case):
     if "expected" not in case or isinstance(case["expected"], dict):
         pytest.skip("reference test has no literal expected rows")
-    rows = run_case(case, _Oracle())
+    rows = run_case(case, OracleBackend())
     assert normalise(rows) == normalise(case["expected"]), case["source"]
 
 
