@@ -319,6 +319,7 @@ def run_b200(args):
     value = pairs / (ms_per_step / 1e3)
 
     # ---- timed: end to end from pinned host buffers through the public API ----
+    # (1) one synchronous call per step: upload, join, download, synchronize (the latency of a single request)
     for _ in range(2):
         step_e2e(out_l_host, out_r_host)
     barrier()
@@ -326,6 +327,23 @@ def run_b200(args):
     for _ in range(args.steps):
         step_e2e(out_l_host, out_r_host)
     barrier()
+    e2e_sync_ms = 1e3 * (time.perf_counter() - t0) / args.steps
+    # (2) the same K steps through Engine.intersects_batches: every step still uploads its inputs and downloads its
+    # pairs, but step i+1's upload and step i's download overlap the compute (PCIe is full duplex).  Single GPU only;
+    # the sharded path keeps the synchronous schedule.
+    e2e_mode = "synchronous call per step"
+    if shard is None and not args.no_pipeline:
+        batch = (host["l"], host["r"])
+        for n_b, _, _ in eng.intersects_batches(iter([batch] * 3), mode=args.join_mode):
+            assert n_b == pairs_local
+        barrier()
+        t0 = time.perf_counter()
+        seen = 0
+        for n_b, _, _ in eng.intersects_batches(iter([batch] * args.steps), mode=args.join_mode):
+            seen += n_b
+        barrier()
+        assert seen == pairs_local * args.steps
+        e2e_mode = "pipelined over steps, depth 2 (upload of step i+1 and download of step i overlap compute; Engine.intersects_batches)"
     e2e_s = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=eng.device)
     if world > 1:
         dist.all_reduce(e2e_s, op=dist.ReduceOp.MAX)
@@ -397,7 +415,8 @@ def run_b200(args):
                    "step": "dict_encode + layout + radix-sort index x2 + join (" + args.join_mode + ": the warm-up call sizes the pair buffer "
                            "with count+scan+emit; timed calls run the fused single-pass count/offset/emit kernel into a buffer of 1.25x "
                            "the previous total, overflow checked on the device)"},
-        "e2e": {"value": pairs / (e2e_ms / 1e3), "unit": UNIT, "ms_per_step": e2e_ms, "h2d_bytes_per_step": h2d_bytes,
+        "e2e": {"value": pairs / (e2e_ms / 1e3), "unit": UNIT, "ms_per_step": e2e_ms, "ms_per_step_synchronous": e2e_sync_ms, "schedule": e2e_mode,
+                "h2d_bytes_per_step": h2d_bytes,
                 "d2h_bytes_per_step": d2h_bytes,
                 "note": "per-rank bytes" + ("" if world == 1 else "; each rank uploads 1/N of the rows, NCCL all-gathers the blocks over NVLink; "
                                             "each rank reads back its own pairs")},
@@ -421,6 +440,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--rows", type=int, default=ROWS_DEFAULT, help="rows per table (default: the 10M of BASELINE configs[1])")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--no-pipeline", action="store_true", help="e2e: one synchronous call per step instead of Engine.intersects_batches")
     ap.add_argument("--join-mode", default="auto", choices=["auto", "two_pass", "single_pass"],
                     help="auto: count+scan+emit on the first call, then the fused single-pass join into a buffer sized from the "
                          "engine's running estimate (overflow is detected on the device and retried exactly)")

@@ -481,6 +481,78 @@ class Engine:
             ir.free()
             lay.free()
 
+    def intersects_batches(self, batches, mode: str = "auto", depth: int = 2):
+        """INTERSECTS joins over a stream of HOST batches with the PCIe transfers of neighbouring batches overlapped.
+
+        ``batches`` yields ``(left, right)``; each side is a mapping with the pinned host buffers ``table_from_buffers``
+        takes (``offs``, ``bytes``, ``start``, ``end``[, ``strand``]).  Yields ``(n_pairs, left_rows, right_rows)`` per
+        batch, in order: pinned host int32 tensors from a ring of ``depth`` result buffers (a result stays valid until
+        ``depth - 1`` further results have been taken).  Per batch the work is the same as ``table_from_buffers`` x2 + ``intersects`` + the
+        copy of the pairs to the host; what changes is the schedule: batch i+1 is uploaded on its own stream while batch
+        i is computed, and batch i's pairs travel back on a third stream while batch i+1 runs — PCIe is full duplex, so
+        the step time drops from upload + compute + download to about max(upload, compute + download).
+        """
+        if depth < 2:
+            raise ValueError("depth must be >= 2")
+        main = self.stream
+        s_in, s_out = torch.cuda.Stream(self.device), torch.cuda.Stream(self.device)
+
+        def upload(batch):
+            with torch.cuda.stream(s_in):
+                tabs = []
+                for side in batch:
+                    tabs.append(self.table_from_buffers(side["offs"], side["bytes"], side["start"], side["end"], side.get("strand")))
+                ev = torch.cuda.Event()
+                ev.record(s_in)
+            return tabs[0], tabs[1], ev
+
+        ring = self.__dict__.setdefault("_result_ring", [])          # pinned (left_rows, right_rows) result buffers, kept across calls
+        ring.extend([None] * (depth - len(ring)))
+        # (slot, n, done event, tensors kept alive) not yet yielded.  Inputs live in s_in's allocator pool and pairs in the
+        # engine stream's; holding them until the download event has completed makes their reuse safe without
+        # record_stream (whose deferred frees made the caching allocator fall back to cudaMalloc / cudaFree every batch).
+        inflight = []
+        it = iter(batches)
+        try:
+            nxt = upload(next(it))
+        except StopIteration:
+            return
+        i = 0
+        while nxt is not None:
+            tl, tr, ev = nxt
+            try:
+                nxt = upload(next(it))                               # batch i+1 starts travelling before batch i is computed
+            except StopIteration:
+                nxt = None
+            main.wait_event(ev)
+            res = self.intersects(tl, tr, mode=mode)
+            n = len(res)
+            done_c = torch.cuda.Event()
+            done_c.record(main)
+            slot = i % depth
+            if len(inflight) >= depth - 1:
+                s0, n0, e0, keep = inflight.pop(0)                   # hand the oldest result out before a slot is reused
+                e0.synchronize()
+                del keep
+                yield n0, ring[s0][0][:n0], ring[s0][1][:n0]
+            if ring[slot] is None or ring[slot][0].numel() < n:
+                cap = max(int(n * 1.25), 1024)
+                ring[slot] = (torch.empty(cap, dtype=torch.int32, pin_memory=True), torch.empty(cap, dtype=torch.int32, pin_memory=True))
+            s_out.wait_event(done_c)
+            with torch.cuda.stream(s_out):
+                ring[slot][0][:n].copy_(res.left_rows[:n], non_blocking=True)
+                ring[slot][1][:n].copy_(res.right_rows[:n], non_blocking=True)
+                done = torch.cuda.Event()
+                done.record(s_out)
+            inflight.append((slot, n, done, (tl, tr, res)))
+            del tl, tr, res
+            i += 1
+        while inflight:
+            s0, n0, e0, keep = inflight.pop(0)
+            e0.synchronize()
+            del keep
+            yield n0, ring[s0][0][:n0], ring[s0][1][:n0]
+
     def _table_desc(self, t: DeviceTable) -> "_cabi.TableDesc":
         sadj, eadj = t.offsets
         if t.codes is None:

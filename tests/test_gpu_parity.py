@@ -523,3 +523,34 @@ def test_one_call_pipeline_dictionary_paths(engine):
         assert tl.dictionary is tr.dictionary and tl.dictionary.names == present
         dn = np.array(tl.dictionary.names, dtype=object)
         assert list(dn[tl.codes.cpu().numpy()]) == L["chrom"]
+
+
+def test_pipelined_host_batches_equal_synchronous_joins(engine):
+    """Engine.intersects_batches (upload / compute / download of neighbouring batches overlapped on three streams)
+    returns, batch by batch, exactly the pairs of the synchronous table_from_buffers + intersects path"""
+    import torch
+    from giql_b200 import synth
+    from giql_b200.engine import _as_utf8
+
+    def host_side(T):
+        S = synth.with_strings(T)
+        offs, byts = _as_utf8(S["chrom"], "chrom")
+        pin = lambda a, dt: torch.from_numpy(np.ascontiguousarray(a, dtype=dt)).pin_memory()
+        return {"offs": pin(offs, np.int32), "bytes": pin(byts, np.uint8), "start": pin(T["start"], np.int32), "end": pin(T["end"], np.int32)}
+
+    sizes = [(30_000, 20_000), (5_000, 60_000), (1, 1), (80_000, 80_000), (20_000, 100)]
+    batches = [(host_side(synth.peaks(a, 100 + i)), host_side(synth.genes(b, 200 + i))) for i, (a, b) in enumerate(sizes)]
+    want = []
+    for l, r in batches:
+        tl = engine.table_from_buffers(l["offs"], l["bytes"], l["start"], l["end"])
+        tr = engine.table_from_buffers(r["offs"], r["bytes"], r["start"], r["end"])
+        want.append(engine.intersects(tl, tr).sorted_packed())
+    for depth in (2, 3):
+        got = []
+        for n, lr, rr in engine.intersects_batches(iter(batches), depth=depth):
+            assert lr.numel() == n == rr.numel()
+            got.append(np.sort((lr.numpy().astype(np.int64) << 32) | rr.numpy().astype(np.int64)))   # copied out before the slot is reused
+        assert len(got) == len(want)
+        for g, w in zip(got, want):
+            assert np.array_equal(g, w)
+    assert list(engine.intersects_batches(iter([]))) == []
