@@ -117,6 +117,14 @@ class PairResult:
     def to_host(self):
         return self.left_rows.cpu().numpy(), self.right_rows.cpu().numpy()
 
+    def to_arrow(self, left_name: str = "l", right_name: str = "r"):
+        """pyarrow Table of the row-id pairs — the relation a SQL engine joins back on ``rowid`` to finish arbitrary
+        projections / GROUP BY / ORDER BY (the `__giql_p0` / `__giql_p1` columns of intersects_duckdb.py:1339-1345)."""
+        import pyarrow as pa
+
+        l, r = self.to_host()
+        return pa.table({left_name: pa.array(l, type=pa.int32()), right_name: pa.array(r, type=pa.int32())})
+
 
 @dataclass
 class NearestResult:
@@ -703,6 +711,56 @@ class Engine:
             il.free()
             ir.free()
             lay.free()
+
+    _CMP_OPS = {"=": 0, "==": 0, "!=": 1, "<>": 1, "<": 2, "<=": 3, ">": 4, ">=": 5}
+    _CMP_DTYPES = {torch.uint8: 1, torch.int32: 2, torch.int64: 3, torch.float32: 4, torch.float64: 5}
+
+    def filter_pairs(self, pairs: PairResult, left_col, right_col, op: str, *, left_valid=None, right_valid=None,
+                     strand: bool = False) -> PairResult:
+        """Residual predicate over join pairs: keeps ``left_col[l] <op> right_col[r]`` (both non-NULL), order preserved.
+
+        The extra ON-conjunct of intersects_duckdb.py:1239-1243 (``AND a.score > b.score``).  Columns: device or host
+        arrays of one common dtype (uint8 / int32 / int64 / float32 / float64), indexed by table row; ``*_valid``:
+        optional 0/1 masks for NULLs; ``strand=True`` treats uint8 columns as strand codes (255 = NULL)."""
+        if op not in self._CMP_OPS:
+            raise ValueError(f"unknown comparison {op!r}")
+
+        def dev(x, dt=None):
+            if x is None:
+                return None
+            t = x if isinstance(x, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(x))
+            if dt is not None:
+                t = t.to(dt)
+            return t.to(self.device).contiguous()
+
+        lc, rc = dev(left_col), dev(right_col)
+        if lc.dtype != rc.dtype:
+            common = torch.promote_types(lc.dtype, rc.dtype)
+            lc, rc = lc.to(common), rc.to(common)
+        if lc.dtype in (torch.int8, torch.int16, torch.bool):
+            lc, rc = lc.to(torch.int32), rc.to(torch.int32)
+        if lc.dtype not in self._CMP_DTYPES:
+            raise ValueError(f"unsupported column dtype {lc.dtype}")
+        dtype = 0 if strand else self._CMP_DTYPES[lc.dtype]
+        if strand and lc.dtype != torch.uint8:
+            raise ValueError("strand columns must be uint8 codes")
+        lv, rv = dev(left_valid, torch.uint8), dev(right_valid, torch.uint8)
+        n = len(pairs)
+        out_l, out_r = self._empty(n, torch.int32), self._empty(n, torch.int32)
+        kept = ctypes.c_int64()
+        self._check(self.lib.giqlb_pairs_filter(self.ctx, _ptr(pairs.left_rows), _ptr(pairs.right_rows), n, _ptr(lc), _ptr(rc), dtype,
+                                                None if lv is None else _ptr(lv), None if rv is None else _ptr(rv), self._CMP_OPS[op],
+                                                _ptr(out_l), _ptr(out_r), ctypes.byref(kept)))
+        return PairResult(out_l[: kept.value], out_r[: kept.value])
+
+    def intersects_stranded(self, left: DeviceTable, right: DeviceTable, same: bool = True, mode: str = "auto") -> PairResult:
+        """INTERSECTS join restricted to pairs on the same (``a.strand = b.strand``, bedtools -s) or on opposite
+        (``a.strand != b.strand``, bedtools -S) strands — docs/recipes/bedtools-migration.rst:271-307.  SQL semantics:
+        plain (in)equality of the strand literals, NULL strands never qualify."""
+        if left.strand is None or right.strand is None:
+            raise ValueError("both tables need a strand column")
+        pairs = self.intersects(left, right, mode=mode)
+        return self.filter_pairs(pairs, left.strand, right.strand, "=" if same else "!=", strand=True)
 
     def contains(self, left: DeviceTable, right: DeviceTable) -> PairResult:
         """``left.interval CONTAINS right.interval`` join: l.start <= r.start AND l.end >= r.end on one chromosome

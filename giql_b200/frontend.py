@@ -65,9 +65,13 @@ class EngineBackend:
         return cache[key]
 
     # -- array flavour (numpy in, numpy out)
-    def pair_arrays(self, L, R, op="intersects", lcfg=None, rcfg=None):
+    def pair_arrays(self, L, R, op="intersects", lcfg=None, rcfg=None, residuals=()):
+        """``residuals``: extra ON-conjuncts as dicts ``{l, r, op[, lvalid, rvalid]}`` of per-row host columns, applied
+        on the device (giqlb_pairs_filter) before the pairs travel back."""
         l, r = self._table(L, lcfg), self._table(R, rcfg)
         res = self.e.intersects(l, r, mode=self.join_mode) if op == "intersects" else (self.e.contains if op == "contains" else self.e.within)(l, r)
+        for x in residuals:
+            res = self.e.filter_pairs(res, x["l"], x["r"], x["op"], left_valid=x.get("lvalid"), right_valid=x.get("rvalid"))
         return res.to_host()
 
     def exists_array(self, L, R, lcfg=None, rcfg=None):
@@ -217,7 +221,10 @@ class _Parser:
                 self.take("kw", "JOIN")
                 src = self.source()
                 self.take("kw", "ON")
-                q["joins"].append({"kind": kind, "source": src, "on": self.condition()})
+                on = [self.condition()]
+                while self.accept("kw", "AND"):
+                    on.append(self.condition())
+                q["joins"].append({"kind": kind, "source": src, "on": on})
             else:
                 break
         if self.accept("kw", "WHERE"):
@@ -381,6 +388,8 @@ class _Parser:
                 raise UnsupportedQuery("spatial predicates compare two genomic columns or a column and a literal range")
             return {"kind": "spatial", "op": op, "left": left[0], "right": right[0]}
         op = self.take("op")
+        if self.at("num") or self.at("str"):
+            return {"kind": "compare_literal", "op": op, "col": left, "value": self.take()}
         right = self.column_ref()
         return {"kind": "compare", "op": op, "left": left, "right": right}
 
@@ -394,6 +403,9 @@ def parse(query: str) -> dict:
 
 
 # ---- binder / evaluator ---------------------------------------------------------------------------------------------------
+_CMP = {"<": np.less, "<=": np.less_equal, ">": np.greater, ">=": np.greater_equal, "=": np.equal, "!=": np.not_equal}
+
+
 def _column(values) -> np.ndarray:
     """host column: int64 / float / bool arrays stay typed, anything holding strings or NULLs becomes an object array"""
     if isinstance(values, np.ndarray) and values.dtype != object and values.dtype.kind not in "US":
@@ -526,12 +538,53 @@ def _expand(frame_rows: np.ndarray, l: np.ndarray, r: np.ndarray, keep_unmatched
     return rep, right
 
 
-def _pairs(be, L, R, op, lcfg, rcfg):
+def _pairs(be, L, R, op, lcfg, rcfg, residuals=()):
     if hasattr(be, "pair_arrays"):
-        return be.pair_arrays(L, R, op, lcfg, rcfg)
+        return be.pair_arrays(L, R, op, lcfg, rcfg, residuals) if residuals else be.pair_arrays(L, R, op, lcfg, rcfg)
     p = be.pairs(L, R, lcfg, rcfg) if op == "intersects" else be.spatial_pairs(L, R, op, lcfg, rcfg)
     a = np.asarray(p, dtype=np.int64).reshape(-1, 2)
-    return a[:, 0], a[:, 1]
+    l, r = a[:, 0], a[:, 1]
+    for x in residuals:                                                  # a backend without a device filter: same rule on the host
+        keep = _CMP[x["op"]](x["l"][l], x["r"][r])
+        if x.get("lvalid") is not None:
+            keep &= x["lvalid"][l].astype(bool)
+        if x.get("rvalid") is not None:
+            keep &= x["rvalid"][r].astype(bool)
+        l, r = l[keep], r[keep]
+    return l, r
+
+
+def _residual(left: _Rel, right: _Rel, la, ra, cond) -> dict:
+    """One `a.col <op> b.col` ON-conjunct as comparable per-row columns: numbers as they are, anything else as the rank
+    of its value in the sorted union of both sides (equality and order preserved); NULLs through validity masks."""
+    (a1, c1), (a2, c2), op = cond["left"], cond["right"], cond["op"]
+    op = {"<>": "!=", "==": "="}.get(op, op)
+    if op not in _CMP:
+        raise UnsupportedQuery(f"comparison {op}")
+    if {a1, a2} != {la, ra}:
+        raise UnsupportedQuery("a residual join predicate must compare one column of each side")
+    if a1 == ra:                                                         # written `b.col <op> a.col`: mirror it
+        (a1, c1), (a2, c2) = (a2, c2), (a1, c1)
+        op = {"<": ">", "<=": ">=", ">": "<", ">=": "<="}.get(op, op)
+    for rel, c in ((left, c1), (right, c2)):
+        if c not in rel.data:
+            raise ValueError(f"unknown column {c!r}")
+    lc, rc = left.data[c1], right.data[c2]
+    out = {"op": op}
+    if lc.dtype != object and rc.dtype != object:
+        out["l"], out["r"] = lc, rc
+        return out
+    lv = np.array([v is not None for v in lc], dtype=bool) if lc.dtype == object else np.ones(len(lc), bool)
+    rv = np.array([v is not None for v in rc], dtype=bool) if rc.dtype == object else np.ones(len(rc), bool)
+    values = sorted(set(lc[lv].tolist()) | set(rc[rv].tolist()))         # mixed incomparable types raise, as SQL would
+    rank = {v: i for i, v in enumerate(values)}
+    out["l"] = np.fromiter((rank[v] if ok else 0 for v, ok in zip(lc.tolist(), lv)), dtype=np.int32, count=len(lc))
+    out["r"] = np.fromiter((rank[v] if ok else 0 for v, ok in zip(rc.tolist(), rv)), dtype=np.int32, count=len(rc))
+    if not lv.all():
+        out["lvalid"] = lv.astype(np.uint8)
+    if not rv.all():
+        out["rvalid"] = rv.astype(np.uint8)
+    return out
 
 
 def _exists(be, L, R, lcfg, rcfg):
@@ -570,9 +623,6 @@ def _nearest(be, Q: _Rel, T: _Rel, j):
         return q.astype(np.int64), t.astype(np.int64), dist
     res = be.nearest(Q.genomic(), T.genomic(), Q.config, T.config, **kw)
     return (np.asarray([x[0] for x in res], dtype=np.int64), np.asarray([x[1] for x in res], dtype=np.int64), _column([x[2] for x in res]))
-
-
-_CMP = {"<": np.less, "<=": np.less_equal, ">": np.greater, ">=": np.greater_equal, "=": np.equal}
 
 
 class Session:
@@ -651,19 +701,24 @@ class Session:
             right = self._relation(q, j["source"])
             ra, la = j["source"]["alias"], f.order[0]
             left = f.rels[la]
-            on, kind = j.get("on"), j["kind"]
+            conds, kind = list(j.get("on") or []), j["kind"]
             if kind == "comma":
-                sp = [w for w in where if w["kind"] == "spatial" and {w["left"], w["right"]} == {la, ra}]
-                if len(sp) != 1:
-                    raise UnsupportedQuery("a comma join needs exactly one spatial predicate between the two tables")
-                on, kind = sp[0], "inner"
-                where.remove(on)
-            if on["kind"] == "compare":
+                # `FROM a, b WHERE a.interval INTERSECTS b.interval [AND a.x = b.x]`: the WHERE conjuncts over both tables are the ON
+                between = lambda w: (w["kind"] == "spatial" and {w["left"], w["right"]} == {la, ra}) or \
+                    (w["kind"] == "compare" and {w["left"][0], w["right"][0]} == {la, ra})
+                conds, kind = [w for w in where if between(w)], "inner"
+                where = [w for w in where if not between(w)]
+            spatial = [c for c in conds if c["kind"] == "spatial"]
+            compares = [c for c in conds if c["kind"] == "compare"]
+            if len(spatial) + len(compares) != len(conds) or len(spatial) > 1:
+                raise UnsupportedQuery("JOIN ... ON takes one spatial predicate and column comparisons between the two tables")
+            if not spatial:
                 # chromosome equi-join feeding DISTANCE (docs/dialect/distance-operators.rst:130-155): quadratic by nature
+                on = compares[0] if len(compares) == 1 else None
                 chrom = (left.config or Table("t")).chrom_col
-                if not (on["op"] == "=" and kind == "inner" and on["left"][1] == chrom and on["right"][1] == (right.config or Table("t")).chrom_col
+                if not (on and on["op"] == "=" and kind == "inner" and on["left"][1] == chrom and on["right"][1] == (right.config or Table("t")).chrom_col
                         and {on["left"][0], on["right"][0]} == {la, ra}):
-                    raise UnsupportedQuery("only `a.chrom = b.chrom` equi-joins are handled")
+                    raise UnsupportedQuery("without a spatial predicate only the `a.chrom = b.chrom` equi-join is handled")
                 lc, rc = f.genomic(la)["chrom"], right.genomic()["chrom"]
                 names, codes = np.unique(np.concatenate([lc.astype(str), rc.astype(str)]), return_inverse=True)
                 cl, cr = codes[: len(lc)], codes[len(lc):]
@@ -675,13 +730,15 @@ class Session:
                 f.take(rep)
                 f.add(ra, right, by[pos].astype(np.int64))
                 continue
-            if on["kind"] != "spatial" or {on["left"], on["right"]} != {la, ra}:
+            on = spatial[0]
+            if {on["left"], on["right"]} != {la, ra}:
                 raise UnsupportedQuery("JOIN ... ON needs `<left>.interval <op> <right>.interval`")
+            residuals = [_residual(left, right, la, ra, c) for c in compares]      # intersects_duckdb.py:1239-1243
             op = on["op"]
             if on["left"] == ra and op != "intersects":                 # `b.interval CONTAINS a.interval` == a WITHIN b
                 op = "within" if op == "contains" else "contains"
             nonempty = len(left) and len(right)
-            if kind in ("semi", "anti"):
+            if kind in ("semi", "anti") and not residuals:
                 # src/giql/expanders/intersects_duckdb.py:1254-1282: one row per qualifying LEFT row; ANTI keeps left-only chroms
                 if op != "intersects":
                     raise UnsupportedQuery("SEMI / ANTI joins are bound for INTERSECTS only")
@@ -689,7 +746,12 @@ class Session:
                 f.take(flags[f.idx[la]] == (kind == "semi"))
                 continue
             # src/giql/expanders/intersects.py:149-154 (INTERSECTS), :155-166 (CONTAINS / WITHIN)
-            l, r = _pairs(be, left.genomic(), right.genomic(), op, left.config, right.config) if nonempty else (np.zeros(0, np.int64),) * 2
+            l, r = _pairs(be, left.genomic(), right.genomic(), op, left.config, right.config, residuals) if nonempty else (np.zeros(0, np.int64),) * 2
+            if kind in ("semi", "anti"):                                 # [NOT] EXISTS over the residual-filtered pairs
+                flags = np.zeros(len(left), bool)
+                flags[np.asarray(l, dtype=np.int64)] = True
+                f.take(flags[f.idx[la]] == (kind == "semi"))
+                continue
             rep, rrow = _expand(f.idx[la], l, r, keep_unmatched=(kind == "left"))
             f.take(rep)
             f.add(ra, right, rrow)
@@ -762,10 +824,23 @@ class Session:
             col = f.column(alias, w["col"][1])
             null = np.array([x is None for x in col], dtype=bool) if col.dtype == object else np.zeros(len(col), bool)
             f.take(null != w["negated"])
-        elif w["kind"] == "spatial":
-            raise UnsupportedQuery("a residual spatial predicate between already joined tables is not handled")
+        elif w["kind"] in ("compare", "compare_literal"):
+            # a plain column comparison over the joined rows, SQL three-valued: NULL operands drop the row
+            op = {"<>": "!=", "==": "="}.get(w["op"], w["op"])
+            if op not in _CMP:
+                raise UnsupportedQuery(f"comparison {op}")
+            lc = w["left"] if w["kind"] == "compare" else w["col"]
+            a = f.column(f.resolve(*lc), lc[1])
+            b = f.column(f.resolve(*w["right"]), w["right"][1]) if w["kind"] == "compare" else np.full(len(a), w["value"], dtype=object if isinstance(w["value"], str) else np.int64)
+            if a.dtype == object or b.dtype == object:
+                fn = {"<": lambda x, y: x < y, "<=": lambda x, y: x <= y, ">": lambda x, y: x > y, ">=": lambda x, y: x >= y,
+                      "=": lambda x, y: x == y, "!=": lambda x, y: x != y}[op]
+                keep = np.fromiter((x is not None and y is not None and fn(x, y) for x, y in zip(a.tolist(), b.tolist())), dtype=bool, count=len(a))
+            else:
+                keep = _CMP[op](a, b)
+            f.take(keep)
         else:
-            raise UnsupportedQuery("general WHERE comparisons are finished by the SQL engine")
+            raise UnsupportedQuery("a residual spatial predicate between already joined tables is not handled")
 
     def _finish(self, q, f: _Frame) -> Result:
         """projection (incl. CLUSTER / MERGE / DISTANCE), DISTINCT, ORDER BY, LIMIT"""

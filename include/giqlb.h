@@ -223,6 +223,29 @@ int giqlb_intersects_tables_sharded(giqlb_ctx* ctx, giqlb_table_t* L, giqlb_tabl
 int giqlb_spatial_join(giqlb_ctx* ctx, giqlb_index* L, giqlb_index* R, int op, int32_t* out_l, int32_t* out_r,
                        int64_t capacity, int64_t* total_host);
 
+/* ---- residual predicates over join pairs (intersects_duckdb.py:1239-1243; bedtools -s / -S as
+ * `AND a.strand = b.strand` / `AND a.strand != b.strand`, docs/recipes/bedtools-migration.rst:271-307) ------------
+ * Keeps pair i iff  left_col[left_rows[i]] <op> right_col[right_rows[i]]  with both operands non-NULL; survivors keep
+ * their order.  dtype names the element type of both columns; GIQLB_T_STRAND is uint8 strand codes where
+ * GIQLB_STRAND_NULL is SQL NULL.  left_valid / right_valid: optional uint8[n_rows] masks (1 = value present) or NULL.
+ * Floating point follows DuckDB's total order (NaN = NaN, NaN > every number).  Outputs must not alias the inputs
+ * and hold up to n_pairs entries; *n_out_host receives the number kept (one host round trip). */
+#define GIQLB_T_STRAND 0
+#define GIQLB_T_U8 1
+#define GIQLB_T_I32 2
+#define GIQLB_T_I64 3
+#define GIQLB_T_F32 4
+#define GIQLB_T_F64 5
+#define GIQLB_CMP_EQ 0
+#define GIQLB_CMP_NE 1
+#define GIQLB_CMP_LT 2
+#define GIQLB_CMP_LE 3
+#define GIQLB_CMP_GT 4
+#define GIQLB_CMP_GE 5
+int giqlb_pairs_filter(giqlb_ctx* ctx, const int32_t* left_rows, const int32_t* right_rows, int64_t n_pairs,
+                       const void* left_col, const void* right_col, int dtype, const uint8_t* left_valid,
+                       const uint8_t* right_valid, int op, int32_t* out_left, int32_t* out_right, int64_t* n_out_host);
+
 /* SEMI/ANTI: exists_by_row[i] = 1 iff left input row i has >= 1 match (uint8[n]).  The left table is
  * probed from its raw columns in input order (no index, no sort).  giqlb_select_rows compacts the row ids
  * with flag == want (ascending) and returns how many. */

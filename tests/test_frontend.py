@@ -63,6 +63,15 @@ STATEMENTS = [
     "WITH hot AS (SELECT a.chrom, a.start, a.\"end\", a.name FROM peaks a SEMI JOIN genes b ON a.interval INTERSECTS b.interval) "
     "SELECT MERGE(interval) FROM hot",
     "SELECT name, start FROM peaks WHERE interval INTERSECTS 'chr1:0-100000' ORDER BY start DESC LIMIT 5",
+    # residual ON-conjuncts (intersects_duckdb.py:1239-1243); same / opposite strand = bedtools -s / -S
+    "SELECT a.name, b.name FROM peaks a JOIN genes b ON a.interval INTERSECTS b.interval AND a.strand = b.strand",
+    "SELECT a.name, b.name FROM peaks a JOIN genes b ON a.interval INTERSECTS b.interval AND a.strand != b.strand",
+    "SELECT a.name, b.name FROM peaks a, genes b WHERE a.interval INTERSECTS b.interval AND b.start < a.start",
+    "SELECT a.name FROM peaks a SEMI JOIN genes b ON a.interval INTERSECTS b.interval AND a.strand = b.strand",
+    "SELECT a.name FROM peaks a ANTI JOIN genes b ON a.interval INTERSECTS b.interval AND a.strand = b.strand",
+    "SELECT a.name, b.name FROM peaks a LEFT JOIN genes b ON a.interval INTERSECTS b.interval AND a.strand = b.strand WHERE a.start >= 1000",
+    "SELECT a.name, b.name FROM peaks a JOIN genes b ON a.interval INTERSECTS b.interval WHERE a.strand = '+' AND b.start > a.start",
+    "SELECT a.name, b.name FROM peaks a JOIN genes b ON a.interval WITHIN b.interval AND a.name <> b.name AND a.\"end\" <= b.\"end\"",
 ]
 
 
@@ -87,7 +96,7 @@ def test_parse_shapes():
 
 @pytest.mark.parametrize("q", [
     "SELECT a.name, COUNT(*) FROM peaks a JOIN genes b ON a.interval INTERSECTS b.interval GROUP BY a.name",
-    "SELECT name FROM peaks WHERE start > 100",
+    "SELECT name FROM peaks WHERE start + 1 > 100",
     "SELECT upper(name) FROM peaks",
     "SELECT a.name FROM peaks a JOIN genes b ON a.name = b.name",
     "SELECT a.name FROM peaks a SEMI JOIN genes b ON a.interval CONTAINS b.interval",
@@ -165,6 +174,33 @@ def test_literal_and_merge_shapes_against_brute_force():
     top = s.execute(STATEMENTS[28]).rows
     chr1 = sorted(((P["name"][i], P["start"][i]) for i in range(90) if P["chrom"][i] == "chr1"), key=lambda r: -r[1])
     assert [r[1] for r in top] == [r[1] for r in chr1[:5]]
+
+
+def test_residual_join_predicates_against_brute_force():
+    s = sessions(OracleBackend())
+    P, G = s.tables["peaks"].data, s.tables["genes"].data
+    ov = [(i, j) for i in range(90) for j in range(60) if overlap(P, i, G, j)]
+    names = lambda pairs: sorted((P["name"][i], G["name"][j]) for i, j in pairs)
+    assert sorted(s.execute(STATEMENTS[29]).rows) == names((i, j) for i, j in ov if P["strand"][i] == G["strand"][j])
+    assert sorted(s.execute(STATEMENTS[30]).rows) == names((i, j) for i, j in ov if P["strand"][i] != G["strand"][j])
+    assert sorted(s.execute(STATEMENTS[31]).rows) == names((i, j) for i, j in ov if G["start"][j] < P["start"][i])
+    same = {i for i, j in ov if P["strand"][i] == G["strand"][j]}
+    assert sorted(r[0] for r in s.execute(STATEMENTS[32]).rows) == sorted(P["name"][i] for i in same)
+    assert sorted(r[0] for r in s.execute(STATEMENTS[33]).rows) == sorted(P["name"][i] for i in range(90) if i not in same)
+    left = s.execute(STATEMENTS[34]).rows
+    big = [i for i in range(90) if P["start"][i] >= 1000]
+    want = names((i, j) for i, j in ov if i in big and P["strand"][i] == G["strand"][j]) + [(P["name"][i], None) for i in big if i not in same]
+    assert sorted(left, key=lambda r: (r[0], r[1] or "")) == sorted(want, key=lambda r: (r[0], r[1] or ""))
+    assert sorted(s.execute(STATEMENTS[35]).rows) == names((i, j) for i, j in ov if P["strand"][i] == "+" and G["start"][j] > P["start"][i])
+    # NULL strands never satisfy = or != (SQL three-valued logic)
+    t = make(21, 40)
+    t["strand"] = [None if i % 5 == 0 else v for i, v in enumerate(t["strand"])]
+    s.register("nulls", t)
+    got = s.execute("SELECT a.name, b.name FROM nulls a JOIN genes b ON a.interval INTERSECTS b.interval AND a.strand != b.strand").rows
+    N = s.tables["nulls"].data
+    want = sorted((N["name"][i], G["name"][j]) for i in range(40) for j in range(60)
+                  if overlap(N, i, G, j) and N["strand"][i] is not None and N["strand"][i] != G["strand"][j])
+    assert sorted(got) == want
 
 
 @pytest.mark.gpu

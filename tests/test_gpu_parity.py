@@ -554,3 +554,53 @@ def test_pipelined_host_batches_equal_synchronous_joins(engine):
         for g, w in zip(got, want):
             assert np.array_equal(g, w)
     assert list(engine.intersects_batches(iter([]))) == []
+
+
+@pytest.mark.parametrize("dtype", ["uint8", "int32", "int64", "float32", "float64"])
+def test_pairs_filter_vs_numpy(dtype, engine):
+    """giqlb_pairs_filter: every comparison, NULL masks, NaN total order (DuckDB: NaN = NaN, NaN > numbers), order kept"""
+    import torch
+    from giql_b200.engine import PairResult
+
+    rng = np.random.default_rng(7)
+    nl, nr, n = 5000, 3000, 300_000
+    if dtype.startswith("float"):
+        lc, rc = rng.integers(0, 50, nl).astype(dtype), rng.integers(0, 50, nr).astype(dtype)
+        lc[::17] = np.nan
+        rc[::13] = np.nan
+    else:
+        lc, rc = rng.integers(0, 50, nl).astype(dtype), rng.integers(0, 50, nr).astype(dtype)
+    lv, rv = (rng.random(nl) > 0.1).astype(np.uint8), (rng.random(nr) > 0.1).astype(np.uint8)
+    l, r = rng.integers(0, nl, n).astype(np.int32), rng.integers(0, nr, n).astype(np.int32)
+    pairs = PairResult(torch.from_numpy(l).to(engine.device), torch.from_numpy(r).to(engine.device))
+
+    def order(a, b):      # -1 / 0 / 1 under the total order
+        na, nb = np.isnan(a) if a.dtype.kind == "f" else np.zeros(len(a), bool), np.isnan(b) if b.dtype.kind == "f" else np.zeros(len(b), bool)
+        c = np.where(a < b, -1, np.where(a > b, 1, 0))
+        return np.where(na & nb, 0, np.where(na, 1, np.where(nb, -1, c)))
+
+    c = order(lc[l], rc[r])
+    rule = {"=": c == 0, "!=": c != 0, "<": c < 0, "<=": c <= 0, ">": c > 0, ">=": c >= 0}
+    for op, keep in rule.items():
+        for masks in (False, True):
+            k = keep & (lv[l] & rv[r]).astype(bool) if masks else keep
+            got = engine.filter_pairs(pairs, lc, rc, op, left_valid=lv if masks else None, right_valid=rv if masks else None)
+            gl, gr = got.to_host()
+            assert np.array_equal(gl, l[k]) and np.array_equal(gr, r[k]), (dtype, op, masks)
+    empty = engine.filter_pairs(PairResult(pairs.left_rows[:0], pairs.right_rows[:0]), lc, rc, "=")
+    assert len(empty) == 0
+
+
+def test_stranded_joins_vs_oracle(engine):
+    """same-strand / opposite-strand INTERSECTS joins (bedtools -s / -S); NULL strands never qualify"""
+    ob = OracleBackend()
+    rng = np.random.default_rng(5)
+    L, R = _rand(rng, 4000, span=20_000, strands=["+", "-", "."]), _rand(rng, 3000, span=20_000, strands=["+", "-", ".", None])
+    tl, tr = engine.table(L), engine.table(R)
+    ov = ob.pairs(L, R)
+    for same in (True, False):
+        want = sorted((i, j) for i, j in ov if R["strand"][j] is not None and (L["strand"][i] == R["strand"][j]) == same)
+        gl, gr = engine.intersects_stranded(tl, tr, same=same).to_host()
+        assert sorted(zip(gl.tolist(), gr.tolist())) == want
+    tab = engine.intersects(tl, tr).to_arrow()
+    assert tab.num_rows == len(ov) and tab.column_names == ["l", "r"]
