@@ -93,6 +93,8 @@ PROTOTYPES = {
     "giqlb_intersects_tables_sharded": (c_int, [_P, POINTER(TableDesc), POINTER(TableDesc), c_int32, c_int, c_int, _P, _P, c_int64,
                                                 POINTER(c_int64), POINTER(_P)]),
     "giqlb_spatial_join": (c_int, [_P, _P, _P, c_int, _P, _P, c_int64, POINTER(c_int64)]),
+    "giqlb_bed_count": (c_int, [_P, _P, c_int64, POINTER(c_int64)]),
+    "giqlb_bed_parse": (c_int, [_P, _P, c_int64, c_int64, c_int, _P, _P, c_int64, _P, _P, _P, _P, c_int64, _P, _P, POINTER(c_int64), POINTER(c_int64)]),
     "giqlb_pairs_filter": (c_int, [_P, _P, _P, c_int64, _P, _P, c_int, _P, _P, c_int, _P, _P, POINTER(c_int64)]),
     "giqlb_intersects_exists": (c_int, [_P, _P, _P, _P, _P, c_int64, c_int32, c_int32, _P, _P]),
     "giqlb_select_rows": (c_int, [_P, _P, c_int64, c_int, _P, POINTER(c_int64)]),

@@ -10,6 +10,7 @@ Operator semantics follow the reference (abdenlab/giql), cited per method.
 from __future__ import annotations
 
 import ctypes
+import os
 from dataclasses import dataclass
 from typing import Any, Optional, Sequence
 
@@ -397,6 +398,78 @@ class Engine:
             strand = self._dev(self.strand_codes(get(cfg.strand_col)), pinned)
         return DeviceTable(self, len(start), config, self._dev(start, pinned), self._dev(end, pinned), strand,
                            self._dev(offs, pinned), self._dev(byts, pinned))
+
+    # ---- BED text ingest ----------------------------------------------------------------------------------
+    @staticmethod
+    def _bed_data_start(head: bytes) -> int:
+        """byte offset of the first data line: leading `#`, `track` and `browser` lines are header (UCSC BED format)"""
+        at = 0
+        while at < len(head):
+            nl = head.find(b"\n", at)
+            line = head[at: nl if nl >= 0 else len(head)]
+            if line.startswith((b"#", b"track", b"browser")) or not line.strip():
+                if nl < 0:
+                    return len(head)
+                at = nl + 1
+                continue
+            break
+        return at
+
+    def read_bed(self, source, fields: Optional[int] = None, config: Table | str | None = None) -> DeviceTable:
+        """BED text -> DeviceTable, parsed on the device (giqlb_bed_count / giqlb_bed_parse).
+
+        ``source``: a path, ``bytes`` or a uint8 numpy array with the file's content (< 2 GiB; TAB-separated, lines
+        ending in \\n or \\r\\n; leading ``#`` / ``track`` / ``browser`` lines are skipped).  ``fields``: 3..6 columns to
+        read (default: as many of the first six as the first data line has).  The table carries chrom / start / end and,
+        from BED6, strand; ``.bed_name`` = (utf8 offsets, bytes) and ``.bed_score`` (int32) hold the other columns on
+        the device.  BED is 0-based half-open, which is also the default ``Table`` encoding."""
+        if isinstance(source, (str, os.PathLike)):
+            raw = np.fromfile(source, dtype=np.uint8)
+        elif isinstance(source, (bytes, bytearray, memoryview)):
+            raw = np.frombuffer(source, dtype=np.uint8)
+        else:
+            raw = np.ascontiguousarray(source, dtype=np.uint8)
+        skip = self._bed_data_start(raw[: 1 << 16].tobytes())
+        if skip == min(len(raw), 1 << 16) and len(raw) > (1 << 16):
+            raise ValueError("read_bed: more than 64 KiB of header lines")
+        raw = raw[skip:]
+        if isinstance(config, str):
+            config = Table(config)
+        if fields is None:
+            first = raw[: 4096].tobytes().split(b"\n", 1)[0]
+            fields = max(3, min(6, first.count(b"\t") + 1))
+        if not 3 <= fields <= 6:
+            raise ValueError("fields must be 3..6")
+        if len(raw) and not (raw.flags.writeable and raw.flags.c_contiguous):
+            raw = raw.copy()                                             # torch wants a writable, contiguous source
+        text = torch.from_numpy(raw).to(self.device) if len(raw) else self._empty(0, torch.uint8)
+        n_lines = ctypes.c_int64()
+        self._check(self.lib.giqlb_bed_count(self.ctx, _ptr(text), text.numel(), ctypes.byref(n_lines)))
+        n = n_lines.value
+        start, end, offs = self._empty(n, torch.int32), self._empty(n, torch.int32), self._empty(n + 1, torch.int32)
+        name_offs = self._empty(n + 1, torch.int32) if fields >= 4 else None
+        score = self._empty(n, torch.int32) if fields >= 5 else None
+        strand = self._empty(n, torch.uint8) if fields >= 6 else None
+        if n == 0:
+            offs.zero_()
+            t = DeviceTable(self, 0, config, start, end, strand, offs, self._empty(1, torch.uint8))
+            t.bed_name, t.bed_score = None, score
+            return t
+        chrom_cap, name_cap = 8 * n, 16 * n if fields >= 4 else 0
+        ct, nt = ctypes.c_int64(), ctypes.c_int64()
+        for _ in range(2):
+            cbytes = self._empty(chrom_cap + 16, torch.uint8)           # + 16: the dictionary kernels read whole 16-byte vectors
+            nbytes = self._empty(name_cap + 16, torch.uint8) if fields >= 4 else None
+            st = self.lib.giqlb_bed_parse(self.ctx, _ptr(text), text.numel(), n, fields, _ptr(offs), _ptr(cbytes), chrom_cap, _ptr(start), _ptr(end),
+                                          _ptr(name_offs), _ptr(nbytes), name_cap, _ptr(score), _ptr(strand), ctypes.byref(ct), ctypes.byref(nt))
+            if st != _cabi.ERR_CAPACITY:
+                break
+            chrom_cap, name_cap = ct.value, nt.value
+        self._check(st)
+        t = DeviceTable(self, n, config, start, end, strand, offs, cbytes[: max(ct.value, 1) + 16])
+        t.bed_name = (name_offs, nbytes[: max(nt.value, 1)]) if fields >= 4 else None
+        t.bed_score = score
+        return t
 
     def table_from_buffers(self, chrom_offsets, chrom_bytes, start, end, strand=None,
                            config: Table | None = None) -> DeviceTable:

@@ -653,6 +653,31 @@ class Session:
             raise ValueError("columns differ in length")
         self.tables[name] = rel
 
+    def register_bed(self, name: str, source, fields: Optional[int] = None):
+        """Register a BED file (path or bytes), parsed on the device (``Engine.read_bed``); columns are named chrom, start,
+        end, name, score, strand as far as the file has them."""
+        be = self.backend
+        if not isinstance(be, EngineBackend):
+            raise UnsupportedQuery("register_bed needs the CUDA engine backend")
+        t = be.e.read_bed(source, fields)
+        import pyarrow as pa
+
+        def strings(offs, byts):
+            o, b = offs.cpu().numpy(), byts.cpu().numpy()
+            return pa.StringArray.from_buffers(len(o) - 1, pa.py_buffer(o), pa.py_buffer(b)).to_numpy(zero_copy_only=False)
+
+        data = {"chrom": strings(t.chrom_offsets, t.chrom_bytes), "start": t.start.cpu().numpy().astype(np.int64), "end": t.end.cpu().numpy().astype(np.int64)}
+        if t.bed_name is not None:
+            data["name"] = strings(*t.bed_name)
+        if t.bed_score is not None:
+            data["score"] = t.bed_score.cpu().numpy().astype(np.int64)
+        if t.strand is not None:
+            data["strand"] = np.array([be.e.strand_literal(c) for c in range(3)], dtype=object)[t.strand.cpu().numpy()]
+        self.register(name, data)
+        cfg = Table("t")
+        key = (id(be.e), cfg.chrom_col, cfg.start_col, cfg.end_col, cfg.strand_col, cfg.coordinate_system, cfg.interval_type)
+        self.tables[name].genomic().setdefault("__device__", {})[key] = t      # the parsed columns are already on the device
+
     def execute(self, query: str) -> Result:
         return self._run(parse(query))
 

@@ -223,6 +223,20 @@ int giqlb_intersects_tables_sharded(giqlb_ctx* ctx, giqlb_table_t* L, giqlb_tabl
 int giqlb_spatial_join(giqlb_ctx* ctx, giqlb_index* L, giqlb_index* R, int op, int32_t* out_l, int32_t* out_r,
                        int64_t capacity, int64_t* total_host);
 
+/* ---- BED text ingest (the reference's users load BED with DuckDB's read_csv) -----------------------
+ * text: the file's bytes on the device (16-byte aligned, < 2 GiB, header lines already stripped), lines ending in \n or
+ * \r\n, TAB-separated fields.  giqlb_bed_count returns the number of lines (a final unterminated line counts).
+ * giqlb_bed_parse fills, for n_fields in 3..6: chromosome names in Arrow utf8 layout (chrom_offsets int32[n_lines + 1],
+ * chrom_bytes), start / end (int32), and when requested (non-NULL, n_fields large enough) the name column (utf8),
+ * score (int32; '.' reads as 0) and strand codes (GIQLB strand coding: '+' 0, '-' 1, '.' 2).  The byte totals are
+ * returned either way; GIQLB_ERR_CAPACITY when a byte buffer is too small (call again with the totals);
+ * GIQLB_ERR_INVALID naming the first blank or malformed line. */
+int giqlb_bed_count(giqlb_ctx* ctx, const uint8_t* text, int64_t n_bytes, int64_t* n_lines_host);
+int giqlb_bed_parse(giqlb_ctx* ctx, const uint8_t* text, int64_t n_bytes, int64_t n_lines, int n_fields,
+                    int32_t* chrom_offsets, uint8_t* chrom_bytes, int64_t chrom_capacity, int32_t* start, int32_t* end,
+                    int32_t* name_offsets, uint8_t* name_bytes, int64_t name_capacity, int32_t* score, uint8_t* strand,
+                    int64_t* chrom_total_host, int64_t* name_total_host);
+
 /* ---- residual predicates over join pairs (intersects_duckdb.py:1239-1243; bedtools -s / -S as
  * `AND a.strand = b.strand` / `AND a.strand != b.strand`, docs/recipes/bedtools-migration.rst:271-307) ------------
  * Keeps pair i iff  left_col[left_rows[i]] <op> right_col[right_rows[i]]  with both operands non-NULL; survivors keep

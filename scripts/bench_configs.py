@@ -23,7 +23,7 @@ from giql_b200 import synth
 
 ap = argparse.ArgumentParser()
 ap.add_argument("--scale", type=float, default=1.0)
-ap.add_argument("--only", default="c1,c3,c4,c5")
+ap.add_argument("--only", default="c1,c3,c4,c5,bed,strand")
 ap.add_argument("--reps", type=int, default=5)
 args = ap.parse_args()
 only = set(args.only.split(","))
@@ -108,3 +108,47 @@ if "c5" in only:
     ms, m = timed(lambda: eng.merge(t), reps=3)
     emit("C5 MERGE 200M", n, ms, 12 * n + 12 * len(m), regions=len(m))
     assert int(m.count.sum()) == n
+
+if "bed" in only:
+    import io
+    import pyarrow as pa
+    import pyarrow.csv as pc
+
+    n = int(10_000_000 * args.scale)
+    T = synth.with_strings(synth.peaks(n, 20260103))
+    tab = pa.table({"chrom": pa.array(T["chrom"], type=pa.string()), "start": T["start"], "end": T["end"],
+                    "name": pa.array(np.char.add("p", np.arange(n).astype(str))), "score": np.zeros(n, np.int32), "strand": pa.array(T["strand"], type=pa.string())})
+    sink = io.BytesIO()
+    pc.write_csv(tab, sink, pc.WriteOptions(include_header=False, delimiter="\t", quoting_style="none"))
+    raw = np.frombuffer(sink.getvalue(), dtype=np.uint8).copy()
+    text = torch.from_numpy(raw).to(eng.device)
+    import ctypes
+    from giql_b200.engine import _ptr
+
+    def parse_resident():
+        nl = ctypes.c_int64()
+        eng._check(eng.lib.giqlb_bed_count(eng.ctx, _ptr(text), text.numel(), ctypes.byref(nl)))
+        m = nl.value
+        cols = [eng._empty(m + 1, torch.int32), eng._empty(8 * m + 16, torch.uint8), eng._empty(m, torch.int32), eng._empty(m, torch.int32),
+                eng._empty(m + 1, torch.int32), eng._empty(16 * m + 16, torch.uint8), eng._empty(m, torch.int32), eng._empty(m, torch.uint8)]
+        a, b = ctypes.c_int64(), ctypes.c_int64()
+        eng._check(eng.lib.giqlb_bed_parse(eng.ctx, _ptr(text), text.numel(), m, 6, _ptr(cols[0]), _ptr(cols[1]), 8 * m, _ptr(cols[2]), _ptr(cols[3]),
+                                           _ptr(cols[4]), _ptr(cols[5]), 16 * m, _ptr(cols[6]), _ptr(cols[7]), ctypes.byref(a), ctypes.byref(b)))
+        return m, a.value, b.value
+
+    ms, (m, cb, nb) = timed(parse_resident)
+    assert m == n
+    emit("BED6 text parse, 10M lines resident in HBM", n, ms, 3 * len(raw) + 21 * n + cb + nb, text_bytes=len(raw), text_gbs=round(len(raw) / (ms * 1e6), 1))
+    t0 = time.perf_counter()
+    t = eng.read_bed(raw)
+    torch.cuda.synchronize()
+    emit("BED6 read_bed from host bytes (pageable H2D + parse)", n, (time.perf_counter() - t0) * 1e3, 3 * len(raw) + 21 * n + cb + nb, text_bytes=len(raw))
+
+if "strand" in only:
+    nq = int(10_000_000 * args.scale)
+    A, B = synth.peaks(nq, 20260103), synth.peaks(nq, 20260104)
+    ta = table(A, strand=True)
+    tb = table(B, strand=True, dictionary=ta.dictionary)
+    ms, res = timed(lambda: eng.intersects(ta, tb))
+    ms2, kept = timed(lambda: eng.filter_pairs(res, ta.strand, tb.strand, "=", strand=True))
+    emit("same-strand residual over the C2 pairs (giqlb_pairs_filter)", len(res), ms2, 10 * len(res) + 8 * len(kept), kept=len(kept), join_ms=round(ms, 3))

@@ -220,3 +220,19 @@ def test_every_statement_matches_oracle_on_gpu(engine):
             assert normalise(a.rows) == normalise(b.rows), q
         else:
             assert normalise(a.rows) == normalise(b.rows), q
+
+
+@pytest.mark.gpu
+def test_register_bed_runs_queries_from_text(engine):
+    from giql_b200.frontend import EngineBackend
+
+    P, G = make(11, 90), make(12, 60)
+    bed = lambda T: "".join(f"{c}\t{s}\t{e}\t{n}\t0\t{st}\n" for c, s, e, n, st in zip(T["chrom"], T["start"], T["end"], T["name"], T["strand"])).encode()
+    dev, ref = Session(EngineBackend(engine)), sessions(OracleBackend())
+    dev.register_bed("peaks", b"track name=peaks\n" + bed(P))
+    dev.register_bed("genes", bed(G))
+    for q in (STATEMENTS[0], STATEMENTS[9], STATEMENTS[15], STATEMENTS[29]):
+        assert sorted(dev.execute(q).rows) == sorted(ref.execute(q).rows), q
+    got = dev.execute("SELECT a.name, a.score, b.strand FROM peaks a JOIN genes b ON a.interval WITHIN b.interval")
+    want = ref.execute("SELECT a.name, b.strand FROM peaks a JOIN genes b ON a.interval WITHIN b.interval")
+    assert sorted((r[0], 0, r[1]) for r in want.rows) == sorted(got.rows)

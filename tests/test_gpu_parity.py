@@ -604,3 +604,79 @@ def test_stranded_joins_vs_oracle(engine):
         assert sorted(zip(gl.tolist(), gr.tolist())) == want
     tab = engine.intersects(tl, tr).to_arrow()
     assert tab.num_rows == len(ov) and tab.column_names == ["l", "r"]
+
+
+def _bed_text(rng, n, fields, crlf=False, long_names=False, trailing_newline=True, header=True):
+    chroms = ["chr1", "chr2", "chr10", "chrX", "chrUn_KI270742v1", "scaffold_000123456789_random_alt"] if long_names else ["chr1", "chr2", "chr10", "chrX"]
+    rows, lines = [], []
+    for i in range(n):
+        c = chroms[int(rng.integers(0, len(chroms)))]
+        s = int(rng.integers(0, 2_000_000_000)) if i % 7 else 0
+        e = s + int(rng.integers(1, 5000))
+        name = ("peak_%d" % i) * (6 if long_names and i % 5 == 0 else 1) if i % 11 else ""
+        score = int(rng.integers(0, 1001))
+        strand = "+-."[int(rng.integers(0, 3))]
+        rec = [c, str(s), str(e), name, "." if i % 13 == 0 else str(score), strand][:fields]
+        rows.append((c, s, e, name, 0 if i % 13 == 0 else score, strand))
+        lines.append("\t".join(rec))
+    eol = "\r\n" if crlf else "\n"
+    text = eol.join(lines) + (eol if trailing_newline and lines else "")
+    if header:
+        text = "track name=test description=\"x\"\n# a comment\nbrowser position chr1:1-100\n" + text
+    return text.encode(), rows
+
+
+def _utf8_list(offs, byts):
+    o, b = offs.cpu().numpy(), byts.cpu().numpy().tobytes()
+    return [b[o[i]: o[i + 1]].decode() for i in range(len(o) - 1)]
+
+
+@pytest.mark.parametrize("fields,crlf,long_names,trailing", [(3, False, False, True), (4, True, False, True), (5, False, True, False),
+                                                              (6, False, False, True), (6, True, True, False)])
+def test_bed_parse_vs_python(fields, crlf, long_names, trailing, engine, tmp_path):
+    """device BED parser (giqlb_bed_count / giqlb_bed_parse) against a Python split of the same text"""
+    rng = np.random.default_rng(fields * 10 + crlf)
+    text, rows = _bed_text(rng, 20_011, fields, crlf, long_names, trailing)
+    path = tmp_path / "t.bed"
+    path.write_bytes(text)
+    for source in (path, text):
+        t = engine.read_bed(source)
+        assert t.n == len(rows)
+        assert _utf8_list(t.chrom_offsets, t.chrom_bytes[: int(t.chrom_offsets[-1])]) == [r[0] for r in rows]
+        assert t.start.cpu().tolist() == [r[1] for r in rows] and t.end.cpu().tolist() == [r[2] for r in rows]
+        if fields >= 4:
+            assert _utf8_list(*t.bed_name) == [r[3] for r in rows]
+        if fields >= 5:
+            assert t.bed_score.cpu().tolist() == [r[4] for r in rows]
+        if fields >= 6:
+            assert [engine.strand_literal(c) for c in t.strand.cpu().tolist()] == [r[5] for r in rows]
+    assert engine.read_bed(text, fields=3).strand is None
+
+
+def test_bed_parse_edge_cases_and_errors(engine):
+    from giql_b200 import EngineError
+
+    assert engine.read_bed(b"").n == 0 and engine.read_bed(b"# only a header\ntrack x\n").n == 0
+    one = engine.read_bed(b"chr1\t5\t9")                       # no trailing newline, minimal line
+    assert (one.n, one.start.item(), one.end.item()) == (1, 5, 9)
+    neg = engine.read_bed(b"chrM\t-3\t+7\tn\t.\t-\n")
+    assert (neg.start.item(), neg.end.item(), neg.bed_score.item(), engine.strand_literal(neg.strand.item())) == (-3, 7, 0, "-")
+    for bad, line in ((b"chr1\t1\t2\nchr1\t3\n", 2), (b"chr1\t1\t2\n\nchr1\t3\t4\n", 2), (b"chr1\tx\t2\n", 1), (b"chr1\t1\t99999999999\n", 1),
+                      (b"chr1\t1\t2\tn\t5\t*\n", 1), (b"chr1\t1\t2\tn\t0.5\t+\n", 1), (b"chr1 1 2\n", 1)):
+        with pytest.raises(EngineError, match=f"line {line} is blank or malformed"):
+            engine.read_bed(bad)
+
+
+def test_join_from_bed_equals_join_from_columns(engine, tmp_path):
+    from giql_b200 import synth
+
+    A, B = synth.with_strings(synth.peaks(30_000, 31)), synth.with_strings(synth.genes(8_000, 32))
+
+    def bed(T):
+        return "".join(f"{c}\t{s}\t{e}\tr{i}\t0\t{st}\n" for i, (c, s, e, st) in enumerate(zip(T["chrom"], T["start"], T["end"], T["strand"]))).encode()
+
+    ta, tb = engine.read_bed(bed(A)), engine.read_bed(bed(B))
+    ca = engine.table({"chrom": A["chrom"], "start": A["start"], "end": A["end"], "strand": A["strand"]})
+    cb = engine.table({"chrom": B["chrom"], "start": B["start"], "end": B["end"], "strand": B["strand"]})
+    assert np.array_equal(engine.intersects(ta, tb).sorted_packed(), engine.intersects(ca, cb).sorted_packed())
+    assert np.array_equal(engine.intersects_stranded(ta, tb).sorted_packed(), engine.intersects_stranded(ca, cb).sorted_packed())
