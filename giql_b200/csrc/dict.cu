@@ -93,93 +93,194 @@ __device__ __forceinline__ uint32_t global_resolve(const StrTable& A, const StrT
 }
 
 constexpr uint32_t DI_EMPTY = 0xFFFFFFFFu, DI_PENDING = 0xFFFFFFFEu;
+constexpr uint32_t DI_SLOT_BITS = 27, DI_SLOT_MASK = (1u << DI_SLOT_BITS) - 1u;   // cache word = slot | len << 27 (len <= 16)
+
+// Per-CTA cache of resolved names (open addressing over DI_CACHE entries): key words + one packed word.
+struct DictCache {
+    unsigned long long k0[DI_CACHE], k1[DI_CACHE];
+    uint32_t meta[DI_CACHE];   // DI_EMPTY / DI_PENDING / (global slot | len << 27)
+};
+
+// Resolves the name (w0, w1, len <= 16; zero padded) of global row g to its slot of the global table, through the cache.
+__device__ __forceinline__ uint32_t cached_resolve(DictCache& c, const StrTable& A, const StrTable& B, unsigned long long* __restrict__ slots,
+                                                   uint32_t cap_mask, const uint8_t* __restrict__ name, uint64_t w0, uint64_t w1, int len,
+                                                   int64_t g, unsigned int* __restrict__ n_distinct) {
+    // 32-bit mix for the cache index (the 64-bit hash is only needed on a miss)
+    const uint32_t lo = (uint32_t)w0, hi = (uint32_t)(w0 >> 32);
+    uint32_t h = (lo ^ (hi * 0x9E3779B1u) ^ ((uint32_t)w1 * 0x85EBCA6Bu) ^ (uint32_t)(w1 >> 32) ^ (uint32_t)len) * 0xC2B2AE35u;
+    int ci = (int)(h >> 25);                               // DI_CACHE == 128
+    const uint32_t want_len = (uint32_t)len << DI_SLOT_BITS;
+    int free_at = -1;
+#pragma unroll 1
+    for (int p = 0; p < DI_CACHE; p++) {
+        const uint32_t v = *(volatile uint32_t*)&c.meta[ci];
+        const unsigned long long k = c.k0[ci];             // issued together with the meta load
+        if (v == DI_EMPTY) {
+            free_at = ci;
+            break;
+        }
+        if (v == DI_PENDING) break;                        // another thread is filling this entry (almost surely with this very name):
+                                                           // resolve globally and do NOT insert, or the cache fills up with duplicates
+        if ((v & ~DI_SLOT_MASK) == want_len && k == w0 && (len <= 8 || c.k1[ci] == w1)) return v & DI_SLOT_MASK;   // PENDING never matches: its top bits are all ones
+        ci = (ci + 1) & (DI_CACHE - 1);
+    }
+    const uint32_t slot = global_resolve(A, B, slots, cap_mask, name, len, hash_short(w0, w1, len), g, n_distinct);
+    if (free_at >= 0 && slot <= DI_SLOT_MASK && atomicCAS(&c.meta[free_at], DI_EMPTY, DI_PENDING) == DI_EMPTY) {
+        c.k0[free_at] = w0;
+        c.k1[free_at] = w1;
+        __threadfence_block();
+        *(volatile uint32_t*)&c.meta[free_at] = slot | want_len;
+    }
+    return slot;
+}
+
+// name of <= 16 bytes at byte offset so of the staged buffer, as two zero-padded little-endian words
+__device__ __forceinline__ void staged_name(const uint8_t* s_bytes, int so, int len, uint64_t& w0, uint64_t& w1) {
+    const uint32_t* wp = reinterpret_cast<const uint32_t*>(s_bytes) + (so >> 2);
+    const int sh = (so & 3) * 8;
+    const uint32_t t0 = wp[0], t1 = wp[1], t2 = wp[2];
+    w0 = (uint64_t)__funnelshift_r(t0, t1, sh) | ((uint64_t)__funnelshift_r(t1, t2, sh) << 32);
+    w1 = 0;
+    if (len > 8) {
+        const uint32_t t3 = wp[3], t4 = wp[4];
+        w1 = (uint64_t)__funnelshift_r(t2, t3, sh) | ((uint64_t)__funnelshift_r(t3, t4, sh) << 32);
+        if (len < 16) w1 &= ~0ull >> (128 - 8 * len);
+    } else {
+        w0 = len ? w0 & (~0ull >> (64 - 8 * len)) : 0ull;
+    }
+}
+
+__device__ __forceinline__ void cp_async_16(void* smem, const void* gmem) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(smem)), "l"(gmem) : "memory");
+}
+__device__ __forceinline__ void cp_async_4(void* smem, const void* gmem) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"((uint32_t)__cvta_generic_to_shared(smem)), "l"(gmem) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+// One 1024-row chunk of table A or B, and what is needed to stage it before its offsets are in shared memory:
+// the byte range comes from two scalar loads of the offsets column.
+struct DictChunk {
+    bool valid, in_b, async;       // async: full chunk, aligned columns, bytes fit -> staged with cp.async one iteration ahead
+    int rows;
+    int64_t r0;
+    int32_t b0, b1;
+};
+
+__device__ __forceinline__ DictChunk dict_chunk(const StrTable& A, const StrTable& B, int chunk, int chunks_a, int total) {
+    DictChunk c;
+    c.valid = chunk < total;
+    c.in_b = chunk >= chunks_a;
+    c.r0 = 0; c.rows = 0; c.b0 = c.b1 = 0; c.async = false;
+    if (!c.valid) return c;
+    const StrTable& T = c.in_b ? B : A;
+    c.r0 = (int64_t)(c.in_b ? chunk - chunks_a : chunk) * DI_ROWS;
+    c.rows = (int)min((int64_t)DI_ROWS, T.n - c.r0);
+    c.b0 = __ldg(T.offs + c.r0);
+    c.b1 = __ldg(T.offs + c.r0 + c.rows);
+    c.async = c.rows == DI_ROWS && ((reinterpret_cast<uintptr_t>(T.offs) | reinterpret_cast<uintptr_t>(T.bytes)) & 15) == 0 &&
+              c.b1 - (c.b0 & ~15) <= DI_BYTES;
+    return c;
+}
+
+struct DictStage {
+    __align__(16) int32_t offs[DI_ROWS + 4];
+    __align__(16) uint8_t bytes[DI_BYTES + 32];
+};
+
+__device__ __forceinline__ void dict_stage_async(const StrTable& A, const StrTable& B, const DictChunk& c, DictStage& st) {
+    if (!c.valid || !c.async) return;
+    const StrTable& T = c.in_b ? B : A;
+    cp_async_16(reinterpret_cast<int4*>(st.offs) + threadIdx.x, reinterpret_cast<const int4*>(T.offs + c.r0) + threadIdx.x);
+    if (threadIdx.x == 0) cp_async_4(&st.offs[DI_ROWS], T.offs + c.r0 + DI_ROWS);
+    const int32_t a0 = c.b0 & ~15;
+    const uint4* src = reinterpret_cast<const uint4*>(T.bytes + a0);
+    const int n_vec = (c.b1 - a0 + 15) >> 4;               // the tail vector stays inside the (padded) allocation
+    for (int i = threadIdx.x; i < n_vec; i += DI_THREADS) cp_async_16(reinterpret_cast<uint4*>(st.bytes) + i, src + i);
+}
 
 __global__ void __launch_bounds__(DI_THREADS)
 dict_insert_kernel(StrTable A, StrTable B, unsigned long long* __restrict__ slots, uint32_t cap_mask,
                    int32_t* __restrict__ slot_a, int32_t* __restrict__ slot_b, unsigned int* __restrict__ n_distinct) {
-    __shared__ __align__(16) int32_t s_offs[DI_ROWS + 4];
-    __shared__ __align__(16) uint8_t s_bytes[DI_BYTES + 32];
-    // per-CTA cache of resolved names (open addressing): key words, length, global slot (DI_EMPTY / DI_PENDING / slot)
-    __shared__ unsigned long long s_k0[DI_CACHE], s_k1[DI_CACHE];
-    __shared__ uint32_t s_slot[DI_CACHE];
-    __shared__ uint8_t s_len[DI_CACHE];
+    extern __shared__ __align__(16) uint8_t s_dyn[];
+    DictStage* stage = reinterpret_cast<DictStage*>(s_dyn);                 // two stages: one being read, one in flight
+    DictCache& cache = *reinterpret_cast<DictCache*>(s_dyn + 2 * sizeof(DictStage));
 
-    for (int i = threadIdx.x; i < DI_CACHE; i += DI_THREADS) s_slot[i] = DI_EMPTY;
-    const int64_t chunks_a = (A.n + DI_ROWS - 1) / DI_ROWS, chunks_b = (B.n + DI_ROWS - 1) / DI_ROWS;
-    for (int64_t chunk = blockIdx.x; chunk < chunks_a + chunks_b; chunk += gridDim.x) {
-        const bool in_b = chunk >= chunks_a;
-        const StrTable& T = in_b ? B : A;
-        const int64_t r0 = (in_b ? chunk - chunks_a : chunk) * DI_ROWS;
-        const int rows = (int)min((int64_t)DI_ROWS, T.n - r0);
-        __syncthreads();   // previous chunk's readers are done with s_offs / s_bytes
-        if (rows == DI_ROWS && (reinterpret_cast<uintptr_t>(T.offs) & 15) == 0) {   // r0 is a multiple of 1024: aligned 16-byte loads
-            reinterpret_cast<int4*>(s_offs)[threadIdx.x] = __ldg(reinterpret_cast<const int4*>(T.offs + r0) + threadIdx.x);
-            if (threadIdx.x == 0) s_offs[DI_ROWS] = T.offs[r0 + DI_ROWS];
-        } else {
-            for (int i = threadIdx.x; i <= rows; i += DI_THREADS) s_offs[i] = T.offs[r0 + i];
-        }
-        __syncthreads();
-        const int32_t b0 = s_offs[0], b1 = s_offs[rows];
-        const int32_t a0 = b0 & ~15;                       // staged range starts at a 16-byte boundary of the byte buffer
-        const bool staged = (b1 - a0) <= DI_BYTES && (reinterpret_cast<uintptr_t>(T.bytes) & 15) == 0;
-        if (staged) {
-            const uint4* src = reinterpret_cast<const uint4*>(T.bytes + a0);
-            const int n_vec = (b1 - a0 + 15) >> 4;         // the tail vector stays inside the (padded) allocation
-            for (int i = threadIdx.x; i < n_vec; i += DI_THREADS) reinterpret_cast<uint4*>(s_bytes)[i] = ld_stream_u32x4(src + i);
-        }
-        __syncthreads();
-        int32_t* out = (in_b ? slot_b : slot_a) + r0;
-        for (int k = threadIdx.x; k < rows; k += DI_THREADS) {
-            const int32_t o = s_offs[k], len = s_offs[k + 1] - o;
-            const int64_t g = (in_b ? A.n : 0) + r0 + k;
-            uint32_t slot = DI_EMPTY;
-            if (staged && len <= 16) {
-                // the name as two zero-padded little-endian words, from aligned 32-bit shared loads
-                const int so = o - a0;
-                const uint32_t* wp = reinterpret_cast<const uint32_t*>(s_bytes) + (so >> 2);
-                const int sh = (so & 3) * 8;
-                const uint32_t t0 = wp[0], t1 = wp[1], t2 = wp[2];
-                uint64_t w0 = (uint64_t)__funnelshift_r(t0, t1, sh) | ((uint64_t)__funnelshift_r(t1, t2, sh) << 32), w1 = 0;
-                if (len > 8) {
-                    const uint32_t t3 = wp[3], t4 = wp[4];
-                    w1 = (uint64_t)__funnelshift_r(t2, t3, sh) | ((uint64_t)__funnelshift_r(t3, t4, sh) << 32);
-                    if (len < 16) w1 &= ~0ull >> (64 - 8 * (len - 8));
-                } else {
-                    w0 &= len == 8 ? ~0ull : ((1ull << (8 * len)) - 1ull);
-                }
-                const uint64_t h = hash_short(w0, w1, len);
-                int ci = (int)(h >> 57);                   // DI_CACHE == 128
-                int free_at = -1;
-                for (int p = 0; p < DI_CACHE; p++) {
-                    const uint32_t v = *(volatile uint32_t*)&s_slot[ci];
-                    if (v == DI_EMPTY) {
-                        free_at = ci;
-                        break;
-                    }
-                    if (v != DI_PENDING && s_k0[ci] == w0 && s_len[ci] == len && s_k1[ci] == w1) {
-                        slot = v;
-                        break;
-                    }
-                    ci = (ci + 1) & (DI_CACHE - 1);
-                }
-                if (slot == DI_EMPTY) {
-                    slot = global_resolve(A, B, slots, cap_mask, T.bytes + o, len, h, g, n_distinct);
-                    if (free_at >= 0 && atomicCAS(&s_slot[free_at], DI_EMPTY, DI_PENDING) == DI_EMPTY) {
-                        s_k0[free_at] = w0;
-                        s_k1[free_at] = w1;
-                        s_len[free_at] = (uint8_t)len;
-                        __threadfence_block();
-                        *(volatile uint32_t*)&s_slot[free_at] = slot;
-                    }
-                }
-            } else {
-                const uint8_t* sp = T.bytes + o;
-                slot = global_resolve(A, B, slots, cap_mask, sp, len, hash_global_name(sp, len), g, n_distinct);
+    for (int i = threadIdx.x; i < DI_CACHE; i += DI_THREADS) cache.meta[i] = DI_EMPTY;
+    const int chunks_a = (int)((A.n + DI_ROWS - 1) / DI_ROWS), chunks_b = (int)((B.n + DI_ROWS - 1) / DI_ROWS);
+    const int total = chunks_a + chunks_b, stride = gridDim.x;
+    int chunk = blockIdx.x;
+    DictChunk cur = dict_chunk(A, B, chunk, chunks_a, total);
+    dict_stage_async(A, B, cur, stage[0]);
+    cp_async_commit();
+    DictChunk nxt = dict_chunk(A, B, chunk + stride, chunks_a, total);
+    for (int it = 0; cur.valid; it++, chunk += stride) {
+        DictStage& st = stage[it & 1];
+        dict_stage_async(A, B, nxt, stage[(it & 1) ^ 1]);       // that stage was released by the barrier ending the previous iteration
+        cp_async_commit();
+        const DictChunk after = dict_chunk(A, B, chunk + 2 * stride, chunks_a, total);   // its two scalar loads overlap this chunk's work
+        cp_async_wait<1>();                                      // everything but the group just committed has landed
+        const StrTable& T = cur.in_b ? B : A;
+        const int rows = cur.rows;
+        const int64_t r0 = cur.r0, g0 = (cur.in_b ? A.n : 0) + r0;
+        const int32_t a0 = cur.b0 & ~15;
+        bool staged = cur.async;
+        if (!cur.async) {                                        // tail chunk / unaligned columns / long names: staged synchronously
+            for (int i = threadIdx.x; i <= rows; i += DI_THREADS) st.offs[i] = T.offs[r0 + i];
+            staged = (cur.b1 - a0) <= DI_BYTES && (reinterpret_cast<uintptr_t>(T.bytes) & 15) == 0;
+            if (staged) {
+                const uint4* src = reinterpret_cast<const uint4*>(T.bytes + a0);
+                const int n_vec = (cur.b1 - a0 + 15) >> 4;
+                for (int i = threadIdx.x; i < n_vec; i += DI_THREADS) reinterpret_cast<uint4*>(st.bytes)[i] = ld_stream_u32x4(src + i);
             }
-            out[k] = (int32_t)slot;
         }
+        __syncthreads();
+        int32_t* out = (cur.in_b ? slot_b : slot_a) + r0;
+        if (cur.async && (reinterpret_cast<uintptr_t>(out) & 15) == 0) {
+            // the common case: a thread owns four consecutive rows — one 16-byte load of their offsets, one 16-byte store
+            // of their slots
+            const int k = threadIdx.x * 4;
+            const int4 o4 = reinterpret_cast<const int4*>(st.offs)[threadIdx.x];
+            const int32_t o[5] = {o4.x, o4.y, o4.z, o4.w, st.offs[k + 4]};
+            int32_t res[4];
+#pragma unroll
+            for (int q = 0; q < 4; q++) {
+                const int len = o[q + 1] - o[q];
+                if (len <= 16) {
+                    uint64_t w0, w1;
+                    staged_name(st.bytes, o[q] - a0, len, w0, w1);
+                    res[q] = (int32_t)cached_resolve(cache, A, B, slots, cap_mask, T.bytes + o[q], w0, w1, len, g0 + k + q, n_distinct);
+                } else {
+                    const uint8_t* sp = T.bytes + o[q];
+                    res[q] = (int32_t)global_resolve(A, B, slots, cap_mask, sp, len, hash_global_name(sp, len), g0 + k + q, n_distinct);
+                }
+            }
+            reinterpret_cast<int4*>(out)[threadIdx.x] = make_int4(res[0], res[1], res[2], res[3]);
+        } else {
+            for (int k = threadIdx.x; k < rows; k += DI_THREADS) {
+                const int32_t o = st.offs[k], len = st.offs[k + 1] - o;
+                uint32_t slot;
+                if (staged && len <= 16) {
+                    uint64_t w0, w1;
+                    staged_name(st.bytes, o - a0, len, w0, w1);
+                    slot = cached_resolve(cache, A, B, slots, cap_mask, T.bytes + o, w0, w1, len, g0 + k, n_distinct);
+                } else {
+                    const uint8_t* sp = T.bytes + o;
+                    slot = global_resolve(A, B, slots, cap_mask, sp, len, hash_global_name(sp, len), g0 + k, n_distinct);
+                }
+                out[k] = (int32_t)slot;
+            }
+        }
+        __syncthreads();   // this stage may be refilled from the next iteration on
+        cur = nxt;
+        nxt = after;
     }
+    cp_async_wait<0>();
 }
+
+constexpr size_t DI_SMEM = 2 * sizeof(DictStage) + sizeof(DictCache);
 
 // one thread per slot: copy the representative's bytes into the name buffer
 __global__ void dict_collect_kernel(StrTable A, StrTable B, const unsigned long long* __restrict__ slots, uint32_t cap,
@@ -294,11 +395,11 @@ int giqlb_dict_encode_async(giqlb_ctx* ctx, const int32_t* offs_l, const uint8_t
     cudaMemsetAsync(p->slots, 0, (size_t)p->cap * 8, ctx->stream);
     cudaMemsetAsync(p->slot2code, 0xFF, (size_t)p->cap * 4, ctx->stream);
     cudaMemsetAsync(cursor, 0, 3 * 8, ctx->stream);
-    const int64_t chunks = ceil_div(n_l, DI_ROWS) + ceil_div(n_r, DI_ROWS), cap_blocks = (int64_t)ctx->sm_count * 6;
+    const int64_t chunks = ceil_div(n_l, DI_ROWS) + ceil_div(n_r, DI_ROWS), cap_blocks = (int64_t)ctx->sm_count * 5;   // 5 CTAs of 43.6 KB shared memory are resident per SM
     const unsigned grid = (unsigned)(chunks < cap_blocks ? chunks : cap_blocks);
     {
         PhaseSpan ps(ctx, GIQLB_PH_DICT);
-        dict_insert_kernel<<<grid, DI_THREADS, 0, ctx->stream>>>(A, B, p->slots, p->cap - 1, codes_l, codes_r, n_distinct);
+        dict_insert_kernel<<<grid, DI_THREADS, DI_SMEM, ctx->stream>>>(A, B, p->slots, p->cap - 1, codes_l, codes_r, n_distinct);
         dict_collect_kernel<<<(p->cap + 255) / 256, 256, 0, ctx->stream>>>(A, B, p->slots, p->cap, p->name_buf, p->name_cap, cursor, p->ent,
                                                                            p->max_entries);
         dict_rank_kernel<<<1, DR_MAX, 0, ctx->stream>>>(cursor, p->name_buf, p->name_cap, p->ent, p->max_entries, p->cap, p->slot2code,
@@ -386,7 +487,7 @@ extern "C" int giqlb_dict_encode(giqlb_ctx* ctx, const int32_t* offs_l, const ui
     int st = GIQLB_OK;
     uint32_t cap = 1u << 14;
     size_t max_entries = DC_MAX_ENTRIES, name_cap = DC_NAME_CAP;
-    const int64_t chunks = ceil_div(n_l, DI_ROWS) + ceil_div(n_r, DI_ROWS), cap_blocks = (int64_t)ctx->sm_count * 6;
+    const int64_t chunks = ceil_div(n_l, DI_ROWS) + ceil_div(n_r, DI_ROWS), cap_blocks = (int64_t)ctx->sm_count * 5;   // 5 CTAs of 43.6 KB shared memory are resident per SM
     const unsigned grid = (unsigned)(chunks < cap_blocks ? chunks : cap_blocks);
     std::vector<uint8_t> h_names;
     std::vector<int32_t> h_ent;
@@ -405,7 +506,7 @@ extern "C" int giqlb_dict_encode(giqlb_ctx* ctx, const int32_t* offs_l, const ui
         cudaMemsetAsync(cursor, 0, 3 * 8, ctx->stream);
         {
             PhaseSpan ps(ctx, GIQLB_PH_DICT);
-            dict_insert_kernel<<<grid, DI_THREADS, 0, ctx->stream>>>(A, B, slots, cap - 1, codes_l, codes_r, n_distinct);
+            dict_insert_kernel<<<grid, DI_THREADS, DI_SMEM, ctx->stream>>>(A, B, slots, cap - 1, codes_l, codes_r, n_distinct);
             dict_collect_kernel<<<(cap + 255) / 256, 256, 0, ctx->stream>>>(A, B, slots, cap, name_buf, name_cap, cursor, ent,
                                                                             (uint32_t)max_entries);
             ctx->launches_this_call += 2;

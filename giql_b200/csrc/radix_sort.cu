@@ -120,9 +120,16 @@ rs_onesweep_kernel(const uint32_t* __restrict__ keys_in, const uint32_t* __restr
         uint32_t peers = FULL_MASK;
 #pragma unroll
         for (int b = 0; b < 8; b++) {
-            const bool bit = (d >> b) & 1u;
-            const uint32_t m = __ballot_sync(FULL_MASK, bit);
-            peers &= bit ? m : ~m;
+            // four instructions per bit (LOP3 -> predicate, VOTE, SEL, LOP3); written in PTX because the compiler
+            // otherwise canonicalises the bit test into shift + and + compare (six per bit)
+            uint32_t m, own;
+            asm("{\n\t.reg .pred p;\n\t.reg .b32 t;\n\t"
+                "and.b32 t, %2, %3;\n\t"
+                "setp.ne.u32 p, t, 0;\n\t"
+                "vote.sync.ballot.b32 %0, p, 0xffffffff;\n\t"
+                "selp.b32 %1, 0xffffffff, 0, p;\n\t}"
+                : "=r"(m), "=r"(own) : "r"(d), "r"(1u << b));
+            peers &= ~(m ^ own);
         }
         rank[i] = peers;
 #endif
@@ -159,6 +166,11 @@ rs_onesweep_kernel(const uint32_t* __restrict__ keys_in, const uint32_t* __restr
     } else {
         *(volatile uint32_t*)my_status = ST_FLAG_AGG | count;
     }
+    // first look-back step issued now: its L2 round trip overlaps the two block scans and the shared-memory scatter
+    uint32_t pre[4];
+#pragma unroll
+    for (int j = 0; j < 4; j++)
+        pre[j] = (int64_t)tile - 1 - j >= 0 ? *(volatile uint32_t*)(status + (size_t)(tile - 1 - j) * RS_RADIX + d_own) : (2u << 30);
     // tile-local exclusive offsets over digits, and global start of each digit bin
     uint32_t tot;
     uint32_t dex = block_excl_scan_add<uint32_t>(count, s_scan, &tot);
@@ -189,12 +201,13 @@ rs_onesweep_kernel(const uint32_t* __restrict__ keys_in, const uint32_t* __restr
     if (tile > 0) {
         int64_t t = (int64_t)tile - 1;
         uint32_t spins = 0;
-        bool done = false;
+        bool done = false, first = true;
         while (!done) {
             uint32_t sv[4];
 #pragma unroll
             for (int j = 0; j < 4; j++)
-                sv[j] = t - j >= 0 ? *(volatile uint32_t*)(status + (size_t)(t - j) * RS_RADIX + d_own) : (2u << 30);   // = ST_FLAG_INCL | 0
+                sv[j] = first ? pre[j] : (t - j >= 0 ? *(volatile uint32_t*)(status + (size_t)(t - j) * RS_RADIX + d_own) : (2u << 30));   // = ST_FLAG_INCL | 0
+            first = false;
             int used = 0;
 #pragma unroll
             for (int j = 0; j < 4; j++) {
