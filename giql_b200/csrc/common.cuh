@@ -399,8 +399,14 @@ int giqlb_index_build_impl(giqlb_ctx* ctx, const giqlb_layout* lay, const int32_
                            int32_t end_adj, int flags, giqlb_prekeyed* pre, giqlb_index** out);
 struct giqlb_dict_pending;
 #define GIQLB_ASYNC_DICT_MAX_CODES 1024   // upper bound of the code space while the dictionary is still on the device
+// defer_remap: leave the parked table slots in codes_l / codes_r; the caller translates them with
+// giqlb_layout_observe_remap (tables given in slot2code / ok_flag of giqlb_dict_pending_tables)
 int giqlb_dict_encode_async(giqlb_ctx* ctx, const int32_t* offs_l, const uint8_t* bytes_l, int64_t n_l, const int32_t* offs_r,
-                            const uint8_t* bytes_r, int64_t n_r, int32_t* codes_l, int32_t* codes_r, giqlb_dict_pending** out);
+                            const uint8_t* bytes_r, int64_t n_r, int32_t* codes_l, int32_t* codes_r, giqlb_dict_pending** out,
+                            bool defer_remap = false);
+void giqlb_dict_pending_tables(const giqlb_dict_pending* p, const int32_t** slot2code, const int** ok_flag);
+int giqlb_layout_observe_remap(giqlb_ctx* ctx, giqlb_layout* lay, int32_t* code, const int32_t* start, const int32_t* end, int64_t n,
+                               int32_t start_adj, int32_t end_adj, const int32_t* slot2code, const int* ok_flag);
 int giqlb_dict_finish(giqlb_ctx* ctx, giqlb_dict_pending* p, giqlb_dict** dict_out, int* fallback);
 int giqlb_layout_finalize_async(giqlb_ctx* ctx, giqlb_layout* lay);
 int giqlb_intersects_join_impl(giqlb_ctx* ctx, giqlb_index* L, giqlb_index* R, int32_t* out_l, int32_t* out_r, int64_t capacity,

@@ -369,7 +369,8 @@ struct giqlb_dict_pending {
 };
 
 int giqlb_dict_encode_async(giqlb_ctx* ctx, const int32_t* offs_l, const uint8_t* bytes_l, int64_t n_l, const int32_t* offs_r,
-                            const uint8_t* bytes_r, int64_t n_r, int32_t* codes_l, int32_t* codes_r, giqlb_dict_pending** out) {
+                            const uint8_t* bytes_r, int64_t n_r, int32_t* codes_l, int32_t* codes_r, giqlb_dict_pending** out,
+                            bool defer_remap) {
     *out = nullptr;
     if (n_l + n_r == 0 || !ctx->h_stage) return GIQLB_ERR_INVALID;   // caller uses the synchronous path
     if (((reinterpret_cast<uintptr_t>(codes_l) | reinterpret_cast<uintptr_t>(codes_r)) & 15) != 0) return GIQLB_ERR_INVALID;
@@ -406,10 +407,11 @@ int giqlb_dict_encode_async(giqlb_ctx* ctx, const int32_t* offs_l, const uint8_t
                                                         p->ent_rank, p->ok_flag);
         const int64_t rb = ceil_div(n_l > n_r ? n_l : n_r, 256 * 16), rcap = (int64_t)ctx->sm_count * 8;
         const unsigned rgrid = (unsigned)(rb < 1 ? 1 : (rb < rcap ? rb : rcap));
-        if (n_l > 0) dict_remap_kernel<<<rgrid, 256, 0, ctx->stream>>>(codes_l, n_l, p->slot2code, p->ok_flag);
-        if (n_r > 0) dict_remap_kernel<<<rgrid, 256, 0, ctx->stream>>>(codes_r, n_r, p->slot2code, p->ok_flag);
-        ctx->launches_this_call += 3 + (n_l > 0) + (n_r > 0);
-        ctx->stats.kernels_total += 3 + (n_l > 0) + (n_r > 0);
+        const int remaps = defer_remap ? 0 : (n_l > 0) + (n_r > 0);
+        if (!defer_remap && n_l > 0) dict_remap_kernel<<<rgrid, 256, 0, ctx->stream>>>(codes_l, n_l, p->slot2code, p->ok_flag);
+        if (!defer_remap && n_r > 0) dict_remap_kernel<<<rgrid, 256, 0, ctx->stream>>>(codes_r, n_r, p->slot2code, p->ok_flag);
+        ctx->launches_this_call += 3 + remaps;
+        ctx->stats.kernels_total += 3 + remaps;
     }
     // names, entries, ranks and the verdict land in the context's PINNED staging buffer whenever the caller next waits
     unsigned char* h = reinterpret_cast<unsigned char*>(ctx->h_stage);
@@ -433,6 +435,11 @@ int giqlb_dict_encode_async(giqlb_ctx* ctx, const int32_t* offs_l, const uint8_t
 
 // After the stream has been synchronised: builds the dictionary from the staged names (or reports that the device
 // declined: *fallback = 1, *dict_out = nullptr) and releases the scratch.  dict_out == nullptr just releases.
+void giqlb_dict_pending_tables(const giqlb_dict_pending* p, const int32_t** slot2code, const int** ok_flag) {
+    *slot2code = p->slot2code;
+    *ok_flag = p->ok_flag;
+}
+
 int giqlb_dict_finish(giqlb_ctx* ctx, giqlb_dict_pending* p, giqlb_dict** dict_out, int* fallback) {
     if (!p) return GIQLB_OK;
     int st = GIQLB_OK;

@@ -22,11 +22,17 @@ constexpr int LY_SMEM_CODES = 2048;
 
 // per-chromosome min/max of canonical coordinates.  Shared-memory staging with a read-before-atomic
 // test: after the first few rows almost no row improves a bound, so almost no atomics are issued.
+// REMAP: the code column still holds the dictionary encoder's parked table slots; they are translated through
+// slot2code here and written back, which saves the separate remap pass over the column (the kernel does nothing
+// when the device-side ranking declined — the caller then redoes the encode on the host-ordered path).
+template <bool REMAP>
 __global__ void __launch_bounds__(LY_THREADS)
-layout_observe_kernel(const int32_t* __restrict__ code, const int32_t* __restrict__ start,
+layout_observe_kernel(int32_t* code, const int32_t* __restrict__ start,
                       const int32_t* __restrict__ end, int64_t n, int32_t n_codes, int32_t sadj, int32_t eadj,
                       long long* __restrict__ lohi, unsigned long long* __restrict__ obs /* [2] degenerate, negative */,
-                      unsigned long long* __restrict__ max_width /* widest interval of the table (cells) */, int* __restrict__ err) {
+                      unsigned long long* __restrict__ max_width /* widest interval of the table (cells) */, int* __restrict__ err,
+                      const int32_t* __restrict__ slot2code, const int* __restrict__ ok_flag) {
+    if (REMAP && !*ok_flag) return;
     __shared__ int32_t s_lo[LY_SMEM_CODES];
     __shared__ int32_t s_hi[LY_SMEM_CODES];
     const bool use_smem = n_codes <= LY_SMEM_CODES;
@@ -62,7 +68,11 @@ layout_observe_kernel(const int32_t* __restrict__ code, const int32_t* __restric
     const bool vec = ((reinterpret_cast<uintptr_t>(code) | reinterpret_cast<uintptr_t>(start) | reinterpret_cast<uintptr_t>(end)) & 15) == 0;
     const int64_t n_vec = vec ? n >> 2 : 0;
     for (int64_t i = (int64_t)blockIdx.x * LY_THREADS + threadIdx.x; i < n_vec; i += (int64_t)gridDim.x * LY_THREADS) {
-        const int4 c = __ldg(reinterpret_cast<const int4*>(code) + i);
+        int4 c = reinterpret_cast<const int4*>(code)[i];
+        if (REMAP) {
+            c = make_int4(__ldg(slot2code + c.x), __ldg(slot2code + c.y), __ldg(slot2code + c.z), __ldg(slot2code + c.w));
+            reinterpret_cast<int4*>(code)[i] = c;
+        }
         const int4 s = __ldg(reinterpret_cast<const int4*>(start) + i);
         const int4 e = __ldg(reinterpret_cast<const int4*>(end) + i);
         fold(c.x, s.x, e.x);
@@ -70,8 +80,11 @@ layout_observe_kernel(const int32_t* __restrict__ code, const int32_t* __restric
         fold(c.z, s.z, e.z);
         fold(c.w, s.w, e.w);
     }
-    for (int64_t i = (n_vec << 2) + (int64_t)blockIdx.x * LY_THREADS + threadIdx.x; i < n; i += (int64_t)gridDim.x * LY_THREADS)
-        fold(code[i], start[i], end[i]);
+    for (int64_t i = (n_vec << 2) + (int64_t)blockIdx.x * LY_THREADS + threadIdx.x; i < n; i += (int64_t)gridDim.x * LY_THREADS) {
+        int32_t c = code[i];
+        if (REMAP) code[i] = c = __ldg(slot2code + c);
+        fold(c, start[i], end[i]);
+    }
     if (bad) err[1] = 1;
 #pragma unroll
     for (int d = 16; d > 0; d >>= 1) widest = max(widest, __shfl_xor_sync(FULL_MASK, widest, d));
@@ -293,6 +306,12 @@ extern "C" int giqlb_layout_create(giqlb_ctx* ctx, int32_t n_codes, int64_t pad,
 
 extern "C" int giqlb_layout_observe(giqlb_ctx* ctx, giqlb_layout* lay, const int32_t* code, const int32_t* start,
                                     const int32_t* end, int64_t n, int32_t start_adj, int32_t end_adj) {
+    return giqlb_layout_observe_remap(ctx, lay, const_cast<int32_t*>(code), start, end, n, start_adj, end_adj, nullptr, nullptr);
+}
+
+// observe() that first translates the parked dictionary slots of `code` into codes, in place (slot2code == nullptr: plain observe)
+int giqlb_layout_observe_remap(giqlb_ctx* ctx, giqlb_layout* lay, int32_t* code, const int32_t* start, const int32_t* end, int64_t n,
+                               int32_t start_adj, int32_t end_adj, const int32_t* slot2code, const int* ok_flag) {
     if (!ctx || !lay || n < 0 || (n > 0 && (!code || !start || !end))) return giqlb_fail(ctx, GIQLB_ERR_INVALID, "layout_observe: bad argument");
     if (lay->finalized) return giqlb_fail(ctx, GIQLB_ERR_INVALID, "layout_observe: layout already finalized");
     begin_call(ctx);
@@ -301,8 +320,14 @@ extern "C" int giqlb_layout_observe(giqlb_ctx* ctx, giqlb_layout* lay, const int
         // the last slot collects every observe() beyond GIQLB_MAX_OBSERVED - 1 (those tables resolve lazily)
         const size_t slot = lay->observed.size() < GIQLB_MAX_OBSERVED - 1 ? lay->observed.size() : GIQLB_MAX_OBSERVED - 1;
         PhaseSpan ps(ctx, GIQLB_PH_LAYOUT);
-        layout_observe_kernel<<<grid_for(ctx, n, LY_THREADS * 8, 8), LY_THREADS, 0, ctx->stream>>>(
-            code, start, end, n, lay->n_codes, start_adj, end_adj, (long long*)lay->d_lohi, lay->d_obs + 2 * slot, lay->d_obs + 2 * GIQLB_MAX_OBSERVED + slot, ctx->d_err);
+        if (slot2code)
+            layout_observe_kernel<true><<<grid_for(ctx, n, LY_THREADS * 8, 8), LY_THREADS, 0, ctx->stream>>>(
+                code, start, end, n, lay->n_codes, start_adj, end_adj, (long long*)lay->d_lohi, lay->d_obs + 2 * slot,
+                lay->d_obs + 2 * GIQLB_MAX_OBSERVED + slot, ctx->d_err, slot2code, ok_flag);
+        else
+            layout_observe_kernel<false><<<grid_for(ctx, n, LY_THREADS * 8, 8), LY_THREADS, 0, ctx->stream>>>(
+                code, start, end, n, lay->n_codes, start_adj, end_adj, (long long*)lay->d_lohi, lay->d_obs + 2 * slot,
+                lay->d_obs + 2 * GIQLB_MAX_OBSERVED + slot, ctx->d_err, nullptr, nullptr);
         LAUNCH_CHECK(ctx);
         if (lay->observed.size() < GIQLB_MAX_OBSERVED - 1) lay->observed.push_back({code, n, start_adj, end_adj, -1, -1});
     }

@@ -460,37 +460,59 @@ __device__ __forceinline__ void tile_runs(const TileSmem& sm, const TileGeom& g,
         i = lo;
         j = m0 - lo;
     }
+    // Three passes over the thread's rows so that the J_IPT run searches — chains of dependent shared-memory loads —
+    // are independent straight-line code the scheduler can interleave; the rare long-run paths come last.
+    bool is_l[J_IPT];
+    int start[J_IPT], h[J_IPT], lim[J_IPT];
+    uint32_t xge[J_IPT];
+#pragma unroll
+    for (int k = 0; k < J_IPT; k++) {
+        const bool live = m0 + k < n_items;
+        const bool take_l = live && (j >= g.nr || (i < g.nl && gsl[i] <= gsr[j]));
+        is_l[k] = take_l;
+        xge[k] = !live ? 0u : (take_l ? gel[i] : ger[j]);     // the row's own end (0: no row of the other table starts below it)
+        start[k] = take_l ? j : i;
+        lim[k] = !live ? start[k] : min(start[k] + 32, take_l ? g.wr : g.wl);
+        h[k] = start[k];
+        i += (live && take_l) ? 1 : 0;
+        j += (live && !take_l) ? 1 : 0;
+    }
+    // run end = first row of the other window whose start is >= the row's end.  Almost every run is a few rows long:
+    // a fixed-trip (divergence-free) binary lifting over the next 32 rows
+#pragma unroll
+    for (int step = 16; step > 0; step >>= 1) {
+#pragma unroll
+        for (int k = 0; k < J_IPT; k++) {
+            const uint32_t* ys = is_l[k] ? gsr : gsl;         // the other table's window
+            if (h[k] + step <= lim[k] && ys[h[k] + step - 1] < xge[k]) h[k] += step;
+        }
+    }
+#pragma unroll
+    for (int k = 0; k < J_IPT; k++) {
+        const uint32_t* ys = is_l[k] ? gsr : gsl;
+        if (h[k] < lim[k] && ys[h[k]] < xge[k]) h[k]++;
+    }
 #pragma unroll
     for (int k = 0; k < J_IPT; k++) {
         code[k] = 0;
         cnt[k] = 0;
         if (m0 + k < n_items) {
-            const bool take_l = j >= g.nr || (i < g.nl && gsl[i] <= gsr[j]);
-            const uint32_t xge = take_l ? gel[i] : ger[j];   // the row's own end
-            const uint32_t* ys = take_l ? gsr : gsl;         // the other table's window
-            const int start = take_l ? j : i, wy = take_l ? g.wr : g.wl;
-            // run end = first row of the other window whose start is >= the row's end.  Almost every run is a few rows
-            // long: a fixed-trip (divergence-free) binary lifting over the next 32 rows, then the rare long run.
-            int h = start;
-            const int lim = min(start + 32, wy);
-#pragma unroll
-            for (int step = 16; step > 0; step >>= 1)
-                if (h + step <= lim && ys[h + step - 1] < xge) h += step;
-            if (h < lim && ys[h] < xge) h++;
-            if (h == lim && lim < wy && ys[h] < xge) h = s_lower_bound(ys, h + 1, wy, xge);
-            int64_t c = h - start;
-            if (h == wy) {                                   // the run may continue beyond the staged window
+            const bool take_l = is_l[k];
+            const uint32_t* ys = take_l ? gsr : gsl;
+            const int wy = take_l ? g.wr : g.wl;
+            int hh = h[k];
+            if (hh == lim[k] && lim[k] < wy && ys[hh] < xge[k]) hh = s_lower_bound(ys, hh + 1, wy, xge[k]);   // the rare long run
+            int64_t c = hh - start[k];
+            if (hh == wy) {                                  // the run may continue beyond the staged window
                 const uint32_t* yg = take_l ? R.gs : L.gs;
                 const int64_t yn = take_l ? R.n : L.n, ybase = take_l ? g.y0 : g.x0;
                 if (ybase + wy < yn) {
-                    c = lb_gallop(yg, ybase + wy, yn, xge) - (ybase + start);
-                    if (leaves_window && c > wy - start) *leaves_window = true;
+                    c = lb_gallop(yg, ybase + wy, yn, xge[k]) - (ybase + start[k]);
+                    if (leaves_window && c > wy - start[k]) *leaves_window = true;
                 }
             }
-            code[k] = (uint32_t)start | (take_l ? 0u : J_CLASS_B);
+            code[k] = (uint32_t)start[k] | (take_l ? 0u : J_CLASS_B);
             cnt[k] = (uint32_t)c;
-            i += take_l ? 1 : 0;
-            j += take_l ? 0 : 1;
         }
     }
 }

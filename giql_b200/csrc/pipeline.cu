@@ -15,6 +15,8 @@ static int tables_impl(giqlb_ctx* ctx, giqlb_table_t* L, giqlb_table_t* R, int32
                        int64_t capacity, int64_t* total_host, giqlb_dict** dict_out, bool async_dict) {
     giqlb_dict* dict = nullptr;
     giqlb_dict_pending* pend = nullptr;
+    const int32_t* slot2code = nullptr;
+    const int* ok_flag = nullptr;
     giqlb_layout* lay = nullptr;
     giqlb_index *il = nullptr, *ir = nullptr;
     int st = GIQLB_OK;
@@ -25,8 +27,9 @@ static int tables_impl(giqlb_ctx* ctx, giqlb_table_t* L, giqlb_table_t* R, int32
         const uint8_t* rb = same ? nullptr : R->chrom_bytes;
         const int64_t rn = same ? 0 : R->n;
         int32_t* rc = same ? nullptr : R->codes;
-        if (async_dict && giqlb_dict_encode_async(ctx, L->chrom_offsets, L->chrom_bytes, L->n, ro, rb, rn, L->codes, rc, &pend) == GIQLB_OK) {
+        if (async_dict && giqlb_dict_encode_async(ctx, L->chrom_offsets, L->chrom_bytes, L->n, ro, rb, rn, L->codes, rc, &pend, true) == GIQLB_OK) {
             n_codes = GIQLB_ASYNC_DICT_MAX_CODES;   // upper bound: the real size is known when the names come back
+            giqlb_dict_pending_tables(pend, &slot2code, &ok_flag);   // the slot -> code translation rides in the observe pass
         } else {
             pend = nullptr;
             st = giqlb_dict_encode(ctx, L->chrom_offsets, L->chrom_bytes, L->n, ro, rb, rn, L->codes, rc, &dict);
@@ -35,8 +38,8 @@ static int tables_impl(giqlb_ctx* ctx, giqlb_table_t* L, giqlb_table_t* R, int32
         }
     }
     if (st == GIQLB_OK) st = giqlb_layout_create(ctx, n_codes, 0, &lay);
-    if (st == GIQLB_OK) st = giqlb_layout_observe(ctx, lay, L->codes, L->start, L->end, L->n, L->start_adj, L->end_adj);
-    if (st == GIQLB_OK && !same) st = giqlb_layout_observe(ctx, lay, R->codes, R->start, R->end, R->n, R->start_adj, R->end_adj);
+    if (st == GIQLB_OK) st = giqlb_layout_observe_remap(ctx, lay, L->codes, L->start, L->end, L->n, L->start_adj, L->end_adj, slot2code, ok_flag);
+    if (st == GIQLB_OK && !same) st = giqlb_layout_observe_remap(ctx, lay, R->codes, R->start, R->end, R->n, R->start_adj, R->end_adj, slot2code, ok_flag);
     if (st == GIQLB_OK) st = giqlb_layout_finalize_async(ctx, lay);   // no round trip: errors surface with the pair total
     if (st == GIQLB_OK) st = giqlb_index_build(ctx, lay, L->codes, L->start, L->end, nullptr, L->n, L->start_adj, L->end_adj, 0, &il);
     if (st == GIQLB_OK && !same) st = giqlb_index_build(ctx, lay, R->codes, R->start, R->end, nullptr, R->n, R->start_adj, R->end_adj, 0, &ir);
