@@ -27,6 +27,7 @@ constexpr int RS_IPT = GIQLB_RS_IPT;
 constexpr int RS_TILE = RS_THREADS * RS_IPT;   // 4096 keys per tile
 constexpr int RS_RADIX = 256;
 constexpr int RS_MAX_PASSES = 4;
+constexpr int RS_HIST_COPIES = 1;   // 4 lane-private copies measured no faster: ATOMS issue rate, not bank conflicts, bounds the kernel
 
 constexpr uint32_t ST_FLAG_AGG = 1u << 30;
 constexpr uint32_t ST_FLAG_INCL = 2u << 30;
@@ -37,8 +38,11 @@ constexpr uint32_t RS_SPIN_LIMIT = 1u << 26;
 __global__ void __launch_bounds__(RS_THREADS)
 rs_histogram_kernel(const uint32_t* __restrict__ keys, int64_t n, int begin_bit, int n_passes,
                     uint32_t* __restrict__ ghist /* [n_passes][256] */) {
-    __shared__ uint32_t sh[RS_MAX_PASSES][RS_RADIX];
-    for (int i = threadIdx.x; i < RS_MAX_PASSES * RS_RADIX; i += RS_THREADS) (&sh[0][0])[i] = 0;
+    // RS_HIST_COPIES private copies, chosen by lane: the shared-memory atomics are the bottleneck of this kernel and
+    // lanes of one warp that hit the same bin serialise (the high digits of genome coordinates are far from uniform)
+    __shared__ uint32_t sh_all[RS_HIST_COPIES][RS_MAX_PASSES][RS_RADIX];
+    for (int i = threadIdx.x; i < RS_HIST_COPIES * RS_MAX_PASSES * RS_RADIX; i += RS_THREADS) (&sh_all[0][0][0])[i] = 0;
+    uint32_t (*sh)[RS_RADIX] = sh_all[threadIdx.x & (RS_HIST_COPIES - 1)];
     __syncthreads();
     // scalar head up to the first 16-byte boundary (sub-ranges of a larger array need not be aligned), vector body, scalar tail
     const int64_t head = min(n, (int64_t)((16 - (reinterpret_cast<uintptr_t>(keys) & 15)) & 15) >> 2);
@@ -64,7 +68,9 @@ rs_histogram_kernel(const uint32_t* __restrict__ keys, int64_t n, int begin_bit,
     }
     __syncthreads();
     for (int i = threadIdx.x; i < n_passes * RS_RADIX; i += RS_THREADS) {
-        uint32_t c = (&sh[0][0])[i];
+        uint32_t c = 0;
+#pragma unroll
+        for (int q = 0; q < RS_HIST_COPIES; q++) c += (&sh_all[q][0][0])[i];
         if (c) atomicAdd(&ghist[i], c);
     }
 }
