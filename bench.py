@@ -445,10 +445,17 @@ def main():
                     help="auto: count+scan+emit on the first call, then the fused single-pass join into a buffer sized from the "
                          "engine's running estimate (overflow is detected on the device and retried exactly)")
     args = ap.parse_args()
+    # stdout carries exactly ONE JSON line: libraries that write to file descriptor 1 (NCCL prints its version banner
+    # there) are pointed at stderr for the duration of the run, and the line goes to the saved descriptor
+    sys.stdout.flush()
+    saved = os.dup(1)
+    os.dup2(2, 1)
+    sys.stdout = os.fdopen(saved, "w")
     if args.impl == "reference":
         run_reference(args)
     else:
         run_b200(args)
+    sys.stdout.flush()
 
 
 if __name__ == "__main__":

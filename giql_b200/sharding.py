@@ -339,32 +339,27 @@ def upload_replicated(engine, host_cols: dict, rank: int, world: int, group=None
     if world == 1 or not dist.is_initialized():
         return engine.table_from_buffers(offs, byts, start, end)
     dev = engine.device
-    per = -(-n // world)                                  # rows per rank (the last block may be short)
-    lo, hi = min(rank * per, n), min((rank + 1) * per, n)
 
-    def gather_rows(col: torch.Tensor, width: int = per) -> torch.Tensor:
-        mine = torch.zeros(width, dtype=col.dtype, device=dev)
+    def gather_flat(col: torch.Tensor, extra: int = 0) -> torch.Tensor:
+        """all-gather of equal blocks of a flat host column straight into its final device array (the last block is
+        padded, `extra` spare elements follow): no staging copy, no concatenation"""
+        m = int(col.numel())
+        per = max(-(-m // world), 1)
+        lo, hi = min(rank * per, m), min((rank + 1) * per, m)
+        out = torch.empty(world * per + extra, dtype=col.dtype, device=dev)
+        mine = out[rank * per: (rank + 1) * per]          # NCCL all-gather in place: a rank's block already sits in its slot
         mine[: hi - lo].copy_(col[lo:hi], non_blocking=True)
-        out = torch.empty(world * width, dtype=col.dtype, device=dev)
-        dist.all_gather_into_tensor(out, mine, group=group)
-        return out[:n]
+        dist.all_gather_into_tensor(out[: world * per], mine, group=group)
+        return out
 
-    d_start, d_end = gather_rows(start), gather_rows(end)
-    # offsets are absolute positions into the byte buffer: blocks of offs[0:n] concatenate back to the original array
-    d_offs = torch.empty(n + 1, dtype=torch.int32, device=dev)
-    d_offs[:n] = gather_rows(offs[:n])
-    d_offs[n:].copy_(offs[n:], non_blocking=True)
-    # byte blocks differ in length: pad to the longest (every rank knows all block bounds from the host offsets)
-    bounds = [int(offs[min(r * per, n)]) for r in range(world + 1)]
-    bounds[world] = int(offs[n])
-    width = max(bounds[r + 1] - bounds[r] for r in range(world))
-    mine = torch.zeros(max(width, 1), dtype=torch.uint8, device=dev)
-    mine[: bounds[rank + 1] - bounds[rank]].copy_(byts[bounds[rank]: bounds[rank + 1]], non_blocking=True)
-    allb = torch.empty(world * max(width, 1), dtype=torch.uint8, device=dev)
-    dist.all_gather_into_tensor(allb, mine, group=group)
-    d_bytes = torch.cat([allb[r * max(width, 1): r * max(width, 1) + bounds[r + 1] - bounds[r]] for r in range(world)])
-    if d_bytes.numel() == 0:
-        d_bytes = torch.zeros(1, dtype=torch.uint8, device=dev)
+    d_start, d_end = gather_flat(start)[:n], gather_flat(end)[:n]
+    # offsets are absolute positions into the byte buffer, and the byte buffer is just a flat array: both are cut into
+    # equal blocks regardless of row boundaries
+    d_offs = gather_flat(offs[:n], extra=1)
+    d_offs[n: n + 1].copy_(offs[n:], non_blocking=True)
+    d_offs = d_offs[: n + 1]
+    n_bytes = int(byts.numel())
+    d_bytes = gather_flat(byts, extra=16)[: max(n_bytes, 1) + 16] if n_bytes else torch.zeros(17, dtype=torch.uint8, device=dev)
     from .engine import DeviceTable
 
-    return DeviceTable(engine, n, None, d_start, d_end, None, d_offs, d_bytes)
+    return DeviceTable(engine, n, None, d_start, d_end, None, d_offs, d_bytes[: max(n_bytes, 1)] if n_bytes else d_bytes[:1])
