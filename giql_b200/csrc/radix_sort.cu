@@ -18,6 +18,12 @@ constexpr int RS_WARPS = RS_THREADS / 32;
 #define GIQLB_RS_IPT 16
 #endif
 constexpr int RS_IPT = GIQLB_RS_IPT;
+#ifndef GIQLB_RS_LOOKBACK
+#define GIQLB_RS_LOOKBACK 4      // predecessor tiles fetched per look-back step
+#endif
+#ifndef GIQLB_RS_BACKOFF_NS
+#define GIQLB_RS_BACKOFF_NS 20   // pause between polls of a predecessor tile that has not published yet
+#endif
 #ifndef GIQLB_RS_CTAS_PER_SM
 #define GIQLB_RS_CTAS_PER_SM 4   // measured: 5 (48 registers, small spills) is slower
 #endif
@@ -173,9 +179,9 @@ rs_onesweep_kernel(const uint32_t* __restrict__ keys_in, const uint32_t* __restr
         *(volatile uint32_t*)my_status = ST_FLAG_AGG | count;
     }
     // first look-back step issued now: its L2 round trip overlaps the two block scans and the shared-memory scatter
-    uint32_t pre[4];
+    uint32_t pre[GIQLB_RS_LOOKBACK];
 #pragma unroll
-    for (int j = 0; j < 4; j++)
+    for (int j = 0; j < GIQLB_RS_LOOKBACK; j++)
         pre[j] = (int64_t)tile - 1 - j >= 0 ? *(volatile uint32_t*)(status + (size_t)(tile - 1 - j) * RS_RADIX + d_own) : (2u << 30);
     // tile-local exclusive offsets over digits, and global start of each digit bin
     uint32_t tot;
@@ -209,14 +215,14 @@ rs_onesweep_kernel(const uint32_t* __restrict__ keys_in, const uint32_t* __restr
         uint32_t spins = 0;
         bool done = false, first = true;
         while (!done) {
-            uint32_t sv[4];
+            uint32_t sv[GIQLB_RS_LOOKBACK];
 #pragma unroll
-            for (int j = 0; j < 4; j++)
+            for (int j = 0; j < GIQLB_RS_LOOKBACK; j++)
                 sv[j] = first ? pre[j] : (t - j >= 0 ? *(volatile uint32_t*)(status + (size_t)(t - j) * RS_RADIX + d_own) : (2u << 30));   // = ST_FLAG_INCL | 0
             first = false;
             int used = 0;
 #pragma unroll
-            for (int j = 0; j < 4; j++) {
+            for (int j = 0; j < GIQLB_RS_LOOKBACK; j++) {
                 if (done || used != j) continue;
                 const uint32_t flag = sv[j] & ~ST_VALUE_MASK;
                 if (flag == 0) continue;              // not published yet: retry from this tile
@@ -225,9 +231,9 @@ rs_onesweep_kernel(const uint32_t* __restrict__ keys_in, const uint32_t* __restr
                 if (flag == ST_FLAG_INCL) done = true;
             }
             t -= used;
-            if (!done && used < 4) {
+            if (!done && used < GIQLB_RS_LOOKBACK) {
                 if (++spins > RS_SPIN_LIMIT) { *err_flag = 1; break; }
-                __nanosleep(20);
+                __nanosleep(GIQLB_RS_BACKOFF_NS);
             }
         }
         *(volatile uint32_t*)my_status = ST_FLAG_INCL | (prefix + count);
