@@ -85,8 +85,10 @@ rs_histogram_kernel(const uint32_t* __restrict__ keys, int64_t n, int begin_bit,
 // IDENTITY_VALS: payload of key i is i itself (first pass; no payload array is read).
 // GATHER: the last pass of an index build also fetches gather_src[payload] (the row's linear end) into
 // gather_dst at the row's sorted position, which saves the separate gather pass.
-template <bool IDENTITY_VALS, bool GATHER>
-__global__ void __launch_bounds__(RS_THREADS, RS_IPT >= 16 ? GIQLB_RS_CTAS_PER_SM : 6)
+// IPT keys per thread: 16 (4096-key tiles) for large inputs; 8 (2048-key tiles) when the input has fewer tiles than the
+// GPU has resident CTA slots, where the pass time is one tile's lifetime and shorter tiles finish sooner.
+template <bool IDENTITY_VALS, bool GATHER, int IPT>
+__global__ void __launch_bounds__(RS_THREADS, IPT >= 16 ? GIQLB_RS_CTAS_PER_SM : 6)
 rs_onesweep_kernel(const uint32_t* __restrict__ keys_in, const uint32_t* __restrict__ vals_in,
                    uint32_t* __restrict__ keys_out, uint32_t* __restrict__ vals_out, int64_t n, int shift,
                    const uint32_t* __restrict__ gather_src, uint32_t* __restrict__ gather_dst,
@@ -94,8 +96,8 @@ rs_onesweep_kernel(const uint32_t* __restrict__ keys_in, const uint32_t* __restr
                    uint32_t* __restrict__ status /* this pass, [tiles][256] */,
                    uint32_t* __restrict__ ticket, int* __restrict__ err_flag) {
     __shared__ uint32_t s_warp_hist[RS_WARPS][RS_RADIX];   // per-warp digit counters -> warp-exclusive offsets
-    __shared__ uint32_t s_keys[RS_TILE];
-    __shared__ uint32_t s_vals[RS_TILE];
+    __shared__ uint32_t s_keys[(RS_THREADS * IPT)];
+    __shared__ uint32_t s_vals[(RS_THREADS * IPT)];
     __shared__ uint32_t s_digit_excl[RS_RADIX];            // tile-local exclusive digit offsets
     __shared__ int32_t s_global_base[RS_RADIX];            // global position of local sorted slot 0 of each digit (n < 2^30)
     __shared__ uint32_t s_scan[RS_WARPS + 2];
@@ -105,24 +107,24 @@ rs_onesweep_kernel(const uint32_t* __restrict__ keys_in, const uint32_t* __restr
     for (int i = threadIdx.x; i < RS_WARPS * RS_RADIX; i += RS_THREADS) (&s_warp_hist[0][0])[i] = 0;
     __syncthreads();
     const uint32_t tile = s_tile;
-    const int64_t tile_base = (int64_t)tile * RS_TILE;
-    const int tile_n = (int)min((int64_t)RS_TILE, n - tile_base);
+    const int64_t tile_base = (int64_t)tile * (RS_THREADS * IPT);
+    const int tile_n = (int)min((int64_t)(RS_THREADS * IPT), n - tile_base);
     const uint32_t w = warp_id(), l = lane_id();
     const uint32_t lt_mask = (1u << l) - 1u;
 
     // load: warp w owns keys [w*512, w*512+512) of the tile; item i of lane l is w*512 + i*32 + l
-    uint32_t key[RS_IPT];
-    uint32_t rank[RS_IPT];
-    const int warp_off = w * (32 * RS_IPT);
+    uint32_t key[IPT];
+    uint32_t rank[IPT];
+    const int warp_off = w * (32 * IPT);
 #pragma unroll
-    for (int i = 0; i < RS_IPT; i++) {
+    for (int i = 0; i < IPT; i++) {
         int li = warp_off + i * 32 + l;
         key[i] = li < tile_n ? ld_stream_u32(keys_in + tile_base + li) : 0xffffffffu;
     }
     // rank within the warp, stable in (item, lane) order.  All match instructions are issued first (they are
     // independent), so only the shared-memory counter update remains on the serial chain.
 #pragma unroll
-    for (int i = 0; i < RS_IPT; i++) {
+    for (int i = 0; i < IPT; i++) {
 #if GIQLB_RS_USE_MATCH
         rank[i] = __match_any_sync(FULL_MASK, (key[i] >> shift) & 255u);
 #else
@@ -147,7 +149,7 @@ rs_onesweep_kernel(const uint32_t* __restrict__ keys_in, const uint32_t* __restr
 #endif
     }
 #pragma unroll
-    for (int i = 0; i < RS_IPT; i++) {
+    for (int i = 0; i < IPT; i++) {
         const uint32_t d = (key[i] >> shift) & 255u;
         const uint32_t peers = rank[i];
         const int leader = __ffs(peers) - 1;
@@ -171,7 +173,7 @@ rs_onesweep_kernel(const uint32_t* __restrict__ keys_in, const uint32_t* __restr
         s_warp_hist[ww][d_own] = count;
         count += c;
     }
-    if (d_own == 255u) count -= (uint32_t)(RS_TILE - tile_n);   // padding keys are all-ones -> digit 255
+    if (d_own == 255u) count -= (uint32_t)((RS_THREADS * IPT) - tile_n);   // padding keys are all-ones -> digit 255
     uint32_t* my_status = status + (size_t)tile * RS_RADIX + d_own;
     if (tile == 0) {
         *(volatile uint32_t*)my_status = ST_FLAG_INCL | count;
@@ -196,7 +198,7 @@ rs_onesweep_kernel(const uint32_t* __restrict__ keys_in, const uint32_t* __restr
     // scatter the tile into shared memory in digit order FIRST: it needs only tile-local offsets, and it gives the
     // preceding tiles time to publish their counts before this tile looks back
 #pragma unroll
-    for (int i = 0; i < RS_IPT; i++) {
+    for (int i = 0; i < IPT; i++) {
         uint32_t d = (key[i] >> shift) & 255u;
         uint32_t pos = s_digit_excl[d] + s_warp_hist[w][d] + rank[i];
         int li = warp_off + i * 32 + l;
@@ -266,7 +268,9 @@ int giqlb_radix_sort_pairs_u32(giqlb_ctx* ctx, uint32_t* keys_a, uint32_t* vals_
     if (n_passes < 1) n_passes = 1;   // always run one pass so the payload is materialised
     if (n_passes > RS_MAX_PASSES) return giqlb_fail(ctx, GIQLB_ERR_INVALID, "radix sort: too many passes");
     if (n == 0) return GIQLB_OK;
-    const int64_t tiles = ceil_div(n, RS_TILE);
+    // fewer 4096-key tiles than resident CTA slots (4 per SM): halve the tile
+    const bool small = ceil_div(n, RS_TILE) < (int64_t)ctx->sm_count * GIQLB_RS_CTAS_PER_SM;
+    const int64_t tiles = ceil_div(n, small ? RS_TILE / 2 : RS_TILE);
 
     uint32_t* ghist = nullptr;    // [n_passes][256] | tickets[RS_MAX_PASSES] | status [n_passes][tiles][256]
     const size_t head_words = (size_t)n_passes * RS_RADIX + RS_MAX_PASSES;
@@ -294,9 +298,15 @@ int giqlb_radix_sort_pairs_u32(giqlb_ctx* ctx, uint32_t* keys_a, uint32_t* vals_
         const uint32_t* gh = ghist + (size_t)p * RS_RADIX;
         uint32_t* st = status + (size_t)p * tiles * RS_RADIX;
         const bool gather = gather_src && gather_dst && p == n_passes - 1;
-#define RS_LAUNCH(IDV, GTH)                                                                                                        \
-    rs_onesweep_kernel<IDV, GTH><<<(unsigned)tiles, RS_THREADS, 0, ctx->stream>>>(kin, vin, kout, vout, n, shift, gather_src, gather_dst, \
-                                                                                  gh, st, tickets + p, ctx->d_err)
+#define RS_LAUNCH(IDV, GTH)                                                                                                                     \
+    do {                                                                                                                                        \
+        if (small)                                                                                                                              \
+            rs_onesweep_kernel<IDV, GTH, RS_IPT / 2><<<(unsigned)tiles, RS_THREADS, 0, ctx->stream>>>(kin, vin, kout, vout, n, shift, gather_src,  \
+                                                                                                      gather_dst, gh, st, tickets + p, ctx->d_err); \
+        else                                                                                                                                    \
+            rs_onesweep_kernel<IDV, GTH, RS_IPT><<<(unsigned)tiles, RS_THREADS, 0, ctx->stream>>>(kin, vin, kout, vout, n, shift, gather_src,      \
+                                                                                                  gather_dst, gh, st, tickets + p, ctx->d_err);    \
+    } while (0)
         if (p == 0 && identity_vals) {
             if (gather) RS_LAUNCH(true, true); else RS_LAUNCH(true, false);
         } else {

@@ -328,6 +328,8 @@ static int sharded_impl(giqlb_ctx* ctx, giqlb_table_t* L, giqlb_table_t* R, int3
                         int32_t* out_r, int64_t capacity, int64_t* total_host, giqlb_dict** dict_out, bool async_dict) {
     giqlb_dict* dict = nullptr;
     giqlb_dict_pending* pend = nullptr;
+    const int32_t* slot2code = nullptr;
+    const int* ok_flag = nullptr;
     giqlb_layout* lay = nullptr;
     giqlb_index *il = nullptr, *ir = nullptr;
     giqlb_prekeyed pre[2];
@@ -337,8 +339,9 @@ static int sharded_impl(giqlb_ctx* ctx, giqlb_table_t* L, giqlb_table_t* R, int3
     const bool encode = !L->codes_valid;
     if (encode) {
         if (async_dict && giqlb_dict_encode_async(ctx, L->chrom_offsets, L->chrom_bytes, L->n, R->chrom_offsets, R->chrom_bytes, R->n,
-                                                  L->codes, R->codes, &pend) == GIQLB_OK) {
+                                                  L->codes, R->codes, &pend, true) == GIQLB_OK) {
             n_codes = GIQLB_ASYNC_DICT_MAX_CODES;   // upper bound until the names come back with the selection sizes
+            giqlb_dict_pending_tables(pend, &slot2code, &ok_flag);   // the slot -> code translation rides in the observe pass
         } else {
             pend = nullptr;
             st = giqlb_dict_encode(ctx, L->chrom_offsets, L->chrom_bytes, L->n, R->chrom_offsets, R->chrom_bytes, R->n, L->codes, R->codes, &dict);
@@ -347,8 +350,8 @@ static int sharded_impl(giqlb_ctx* ctx, giqlb_table_t* L, giqlb_table_t* R, int3
         }
     }
     if (st == GIQLB_OK) st = giqlb_layout_create(ctx, n_codes, 0, &lay);
-    if (st == GIQLB_OK) st = giqlb_layout_observe(ctx, lay, L->codes, L->start, L->end, L->n, L->start_adj, L->end_adj);
-    if (st == GIQLB_OK) st = giqlb_layout_observe(ctx, lay, R->codes, R->start, R->end, R->n, R->start_adj, R->end_adj);
+    if (st == GIQLB_OK) st = giqlb_layout_observe_remap(ctx, lay, L->codes, L->start, L->end, L->n, L->start_adj, L->end_adj, slot2code, ok_flag);
+    if (st == GIQLB_OK) st = giqlb_layout_observe_remap(ctx, lay, R->codes, R->start, R->end, R->n, R->start_adj, R->end_adj, slot2code, ok_flag);
     if (st == GIQLB_OK) st = giqlb_layout_finalize_async(ctx, lay);   // errors surface with the selection sizes
     giqlb_table_t* T[2] = {L, R};
     int64_t n_sel[2] = {0, 0};
