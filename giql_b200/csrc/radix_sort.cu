@@ -268,8 +268,9 @@ int giqlb_radix_sort_pairs_u32(giqlb_ctx* ctx, uint32_t* keys_a, uint32_t* vals_
     if (n_passes < 1) n_passes = 1;   // always run one pass so the payload is materialised
     if (n_passes > RS_MAX_PASSES) return giqlb_fail(ctx, GIQLB_ERR_INVALID, "radix sort: too many passes");
     if (n == 0) return GIQLB_OK;
-    // fewer 4096-key tiles than resident CTA slots (4 per SM): halve the tile
-    const bool small = ceil_div(n, RS_TILE) < (int64_t)ctx->sm_count * GIQLB_RS_CTAS_PER_SM;
+    // fewer 4096-key tiles than SMs: halve the tile (measured: 8 passes over 250 k keys 101 -> 89 us; at 1.25 M keys, i.e.
+    // between one tile per SM and one per resident CTA slot, the halved tiles are SLOWER — 20.6 vs 18.7 us per pass)
+    const bool small = ceil_div(n, RS_TILE) < (int64_t)ctx->sm_count;
     const int64_t tiles = ceil_div(n, small ? RS_TILE / 2 : RS_TILE);
 
     uint32_t* ghist = nullptr;    // [n_passes][256] | tickets[RS_MAX_PASSES] | status [n_passes][tiles][256]
