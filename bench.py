@@ -216,6 +216,9 @@ def run_b200(args):
     if world != args.gpus:
         log(f"[bench] WORLD_SIZE={world} but --gpus {args.gpus}; using WORLD_SIZE")
     torch.cuda.set_device(local)
+    # host buffers NUMA-local to this rank's GPU (first touch); the CPU baseline leg gets the full core set back
+    prev_aff, new_aff = giql_b200.bind_host_to_gpu(local) if not args.no_bind else (os.sched_getaffinity(0), None)
+    log(f"[bench] rank {rank}: cpu affinity {'unchanged (' + str(len(prev_aff)) + ' cores)' if new_aff is None else str(len(prev_aff)) + ' -> ' + str(len(new_aff)) + ' GPU-local cores'}")
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     eng = giql_b200.Engine(local)
@@ -334,7 +337,7 @@ def run_b200(args):
     e2e_mode = "synchronous call per step"
     if shard is None and not args.no_pipeline:
         batch = (host["l"], host["r"])
-        for n_b, _, _ in eng.intersects_batches(iter([batch] * 3), mode=args.join_mode):
+        for n_b, _, _ in eng.intersects_batches(iter([batch] * max(3, min(args.steps, 10))), mode=args.join_mode):   # untimed warm-up
             assert n_b == pairs_local
         barrier()
         t0 = time.perf_counter()
@@ -390,6 +393,7 @@ def run_b200(args):
 
     # ---- CPU baseline beside it (rank 0, N=1 only) ----
     cpu = None
+    os.sched_setaffinity(0, prev_aff)
     if world == 1 and not args.no_cpu:
         from oracle import c_oracle
 
@@ -440,6 +444,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--rows", type=int, default=ROWS_DEFAULT, help="rows per table (default: the 10M of BASELINE configs[1])")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--no-bind", action="store_true", help="do not pin the process to the GPU-local CPU cores")
     ap.add_argument("--no-pipeline", action="store_true", help="e2e: one synchronous call per step instead of Engine.intersects_batches")
     ap.add_argument("--join-mode", default="auto", choices=["auto", "two_pass", "single_pass"],
                     help="auto: count+scan+emit on the first call, then the fused single-pass join into a buffer sized from the "

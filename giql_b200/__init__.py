@@ -9,12 +9,12 @@ from .ranges import parse_range
 from .table import Table, Tables, canonical_offsets
 
 __all__ = ["Engine", "DeviceTable", "Dictionary", "PairResult", "Table", "Tables", "canonical_offsets",
-           "EngineError", "EngineUnavailable", "Session", "UnsupportedQuery", "parse_range"]
+           "EngineError", "EngineUnavailable", "bind_host_to_gpu", "Session", "UnsupportedQuery", "parse_range"]
 
 
 def __getattr__(name):
     # torch is imported lazily so that `import giql_b200` (Table, canonical_offsets) stays light
-    if name in ("Engine", "DeviceTable", "Dictionary", "PairResult"):
+    if name in ("Engine", "DeviceTable", "Dictionary", "PairResult", "bind_host_to_gpu"):
         from . import engine
 
         return getattr(engine, name)

@@ -211,6 +211,28 @@ class DeviceTable:
                                                            self.chrom_bytes, self.codes) if t is not None)
 
 
+def bind_host_to_gpu(index: int = 0):
+    """Pin the calling process to the CPU cores NVML reports as local to GPU ``index`` (same NUMA node / PCIe root), so
+    that the pinned host buffers it allocates afterwards are first-touched on that node and host<->device copies do not
+    cross the socket interconnect.  Returns ``(previous affinity, new affinity)``; a no-op (previous, None) when NVML is
+    unavailable or the local cores are outside the cores the process may use (containers)."""
+    prev = os.sched_getaffinity(0)
+    try:
+        import pynvml
+
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(index)
+        n_cpu = os.cpu_count() or 1
+        words = pynvml.nvmlDeviceGetCpuAffinity(h, (n_cpu + 63) // 64)
+        local = {i for i in range(n_cpu) if (int(words[i // 64]) >> (i % 64)) & 1} & prev
+        if not local or local == prev:
+            return prev, None
+        os.sched_setaffinity(0, local)
+        return prev, local
+    except Exception:                                               # noqa: BLE001 — affinity is an optimisation only
+        return prev, None
+
+
 def _ptr(t: Optional[torch.Tensor]):
     return ctypes.c_void_p(t.data_ptr()) if t is not None else None
 
