@@ -331,22 +331,25 @@ def run_b200(args):
         step_e2e(out_l_host, out_r_host)
     barrier()
     e2e_sync_ms = 1e3 * (time.perf_counter() - t0) / args.steps
-    # (2) the same K steps through Engine.intersects_batches: every step still uploads its inputs and downloads its
-    # pairs, but step i+1's upload and step i's download overlap the compute (PCIe is full duplex).  Single GPU only;
-    # the sharded path keeps the synchronous schedule.
+    # (2) the same K steps through Engine.intersects_batches (GenomeRangeShard.intersects_batches when sharded): every
+    # step still uploads its inputs and downloads its pairs, but step i+1's upload and step i's download overlap the
+    # compute (PCIe is full duplex).
     e2e_mode = "synchronous call per step"
-    if shard is None and not args.no_pipeline:
+    if not args.no_pipeline:
         batch = (host["l"], host["r"])
-        for n_b, _, _ in eng.intersects_batches(iter([batch] * max(3, min(args.steps, 10))), mode=args.join_mode):   # untimed warm-up
+        run = (lambda k: eng.intersects_batches(iter([batch] * k), mode=args.join_mode)) if shard is None else \
+              (lambda k: shard.intersects_batches(iter([batch] * k)))
+        for n_b, _, _ in run(max(3, min(args.steps, 10))):          # untimed warm-up
             assert n_b == pairs_local
         barrier()
         t0 = time.perf_counter()
         seen = 0
-        for n_b, _, _ in eng.intersects_batches(iter([batch] * args.steps), mode=args.join_mode):
+        for n_b, _, _ in run(args.steps):
             seen += n_b
         barrier()
         assert seen == pairs_local * args.steps
-        e2e_mode = "pipelined over steps, depth 2 (upload of step i+1 and download of step i overlap compute; Engine.intersects_batches)"
+        e2e_mode = "pipelined over steps, depth 2 (upload of step i+1 and download of step i overlap compute; " + \
+                   ("Engine.intersects_batches)" if shard is None else "GenomeRangeShard.intersects_batches: 1/N upload per rank + NCCL all-gather)")
     e2e_s = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=eng.device)
     if world > 1:
         dist.all_reduce(e2e_s, op=dist.ReduceOp.MAX)

@@ -143,6 +143,69 @@ class GenomeRangeShard:
                 self.ops.release(plan)
         return ShardedPairs(out_l, out_r, self.all_gather_counts(int(out_l.numel())), self.rank)
 
+    def intersects_batches(self, batches, depth: int = 2):
+        """The sharded counterpart of ``Engine.intersects_batches``: a stream of HOST batches ``(left, right)`` (pinned
+        column dicts, the same on every rank), each uploaded 1/world per rank + all-gathered (``upload_replicated``),
+        joined on this rank's genome range, and this rank's pairs copied back — with batch i+1's upload and batch i's
+        download overlapping the compute on their own streams.  Yields ``(n_local_pairs, left_rows, right_rows)``
+        (pinned host tensors from a ring of ``depth`` buffers).  Every rank must consume the same batches in the same
+        order (the uploads are collectives)."""
+        eng = self.ops.e
+        main = eng.stream
+        s_in, s_out = torch.cuda.Stream(eng.device), torch.cuda.Stream(eng.device)
+
+        def upload(batch):
+            with torch.cuda.stream(s_in):
+                tl = upload_replicated(eng, batch[0], self.rank, self.world, self.group)
+                tr = upload_replicated(eng, batch[1], self.rank, self.world, self.group)
+                ev = torch.cuda.Event()
+                ev.record(s_in)
+            return tl, tr, ev
+
+        ring = self.__dict__.setdefault("_result_ring", [])
+        ring.extend([None] * (depth - len(ring)))
+        inflight = []                                                # (slot, n, done event, tensors kept alive)
+        it = iter(batches)
+        try:
+            nxt = upload(next(it))
+        except StopIteration:
+            return
+        i = 0
+        while nxt is not None:
+            tl, tr, ev = nxt
+            try:
+                nxt = upload(next(it))
+            except StopIteration:
+                nxt = None
+            main.wait_event(ev)
+            res = self.intersects(tl, tr)
+            n = len(res)
+            done_c = torch.cuda.Event()
+            done_c.record(main)
+            slot = i % depth
+            if len(inflight) >= depth - 1:
+                s0, n0, e0, keep = inflight.pop(0)
+                e0.synchronize()
+                del keep
+                yield n0, ring[s0][0][:n0], ring[s0][1][:n0]
+            if ring[slot] is None or ring[slot][0].numel() < n:
+                cap = max(int(n * 1.25), 1024)
+                ring[slot] = (torch.empty(cap, dtype=torch.int32, pin_memory=True), torch.empty(cap, dtype=torch.int32, pin_memory=True))
+            s_out.wait_event(done_c)
+            with torch.cuda.stream(s_out):
+                ring[slot][0][:n].copy_(res.left_rows[:n], non_blocking=True)
+                ring[slot][1][:n].copy_(res.right_rows[:n], non_blocking=True)
+                done = torch.cuda.Event()
+                done.record(s_out)
+            inflight.append((slot, n, done, (tl, tr, res)))
+            del tl, tr, res
+            i += 1
+        while inflight:
+            s0, n0, e0, keep = inflight.pop(0)
+            e0.synchronize()
+            del keep
+            yield n0, ring[s0][0][:n0], ring[s0][1][:n0]
+
     def all_gather_counts(self, local: int):
         """Starts the all-gather of the per-rank pair counts (one int64 each); see ShardedPairs.counts."""
         if self.world == 1 or not dist.is_initialized():
