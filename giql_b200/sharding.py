@@ -153,11 +153,17 @@ class GenomeRangeShard:
         eng = self.ops.e
         main = eng.stream
         s_in, s_out = torch.cuda.Stream(eng.device), torch.cuda.Stream(eng.device)
+        # The ingest all-gathers get their OWN communicator: a process group runs its collectives one after the other on
+        # one internal stream, so on the join's group the tiny count exchange of batch i would queue behind the eight
+        # ingest all-gathers of batch i+1 (measured at 4 GPUs: 20 ms per batch instead of 6).
+        if self.world > 1 and dist.is_initialized() and getattr(self, "_ingest_group", None) is None:
+            self._ingest_group = dist.new_group(backend=dist.get_backend(self.group))
+        ingest = getattr(self, "_ingest_group", None)
 
         def upload(batch):
             with torch.cuda.stream(s_in):
-                tl = upload_replicated(eng, batch[0], self.rank, self.world, self.group)
-                tr = upload_replicated(eng, batch[1], self.rank, self.world, self.group)
+                tl = upload_replicated(eng, batch[0], self.rank, self.world, ingest)
+                tr = upload_replicated(eng, batch[1], self.rank, self.world, ingest)
                 ev = torch.cuda.Event()
                 ev.record(s_in)
             return tl, tr, ev
