@@ -24,6 +24,7 @@ _STATUS_NAMES = {
 STRAND_PLUS, STRAND_MINUS, STRAND_DOT, STRAND_QMARK, STRAND_OTHER0, STRAND_NULL = 0, 1, 2, 3, 4, 255
 INDEX_TIE_BY_END = 1
 OP_CONTAINS, OP_WITHIN = 1, 2
+KEY_NULL = -2147483648   # GIQLB_KEY_NULL
 
 
 class EngineUnavailable(RuntimeError):
@@ -102,6 +103,7 @@ PROTOTYPES = {
     "giqlb_nearest": (c_int, [_P, _P, _P, _P, _P, _P, c_int64, c_int32, c_int32, _P, c_int, c_int64, c_int, c_int,
                               _P, _P, _P, _P, c_int64, POINTER(c_int64)]),
     "giqlb_cluster": (c_int, [_P, _P, c_int64, _P]),
+    "giqlb_cluster_predicate": (c_int, [_P, _P, c_int64, _P, _P, c_int, _P]),
     "giqlb_merge": (c_int, [_P, _P, c_int64, _P, _P, _P, _P, _P, c_int64, POINTER(c_int64)]),
     "giqlb_disjoin": (c_int, [_P, _P, _P, _P, _P, c_int64, c_int32, c_int32, _P, c_int, _P, _P, _P, c_int64, POINTER(c_int64)]),
     "giqlb_shard_max_end": (c_int, [_P, _P, POINTER(ctypes.c_uint32)]),

@@ -40,21 +40,49 @@ __device__ __forceinline__ int32_t chrom_of(const LayoutView& V, uint32_t g) {
     return lo;
 }
 
+// Optional `predicate := cur <op> PREV(prev)` (cluster.py:281-299, 587-644): a row stays in the running cluster only when it
+// is adjacent to the running-max edge AND the comparison holds against its IMMEDIATE sorted predecessor.  The two
+// operand columns arrive as order-preserving int32 codes in sorted-row order (GIQLB_KEY_NULL = SQL NULL -> not TRUE).
+struct ClusterPredicate {
+    const int32_t* cur;    // code of the current row's operand, by sorted position (nullptr: no predicate)
+    const int32_t* prev;   // code of the PREV(...) operand, by sorted position
+    int op;
+};
+__device__ __forceinline__ bool predicate_holds(const ClusterPredicate& p, int64_t i) {
+    if (!p.cur) return true;
+    if (i == 0) return false;
+    const int32_t a = p.cur[i], b = p.prev[i - 1];
+    if (a == GIQLB_KEY_NULL || b == GIQLB_KEY_NULL) return false;
+    switch (p.op) {
+        case GIQLB_CMP_EQ: return a == b;
+        case GIQLB_CMP_NE: return a != b;
+        case GIQLB_CMP_LT: return a < b;
+        case GIQLB_CMP_LE: return a <= b;
+        case GIQLB_CMP_GT: return a > b;
+        default: return a >= b;
+    }
+}
+
 struct InClusterFlag {
     const uint32_t* gs;
     const uint32_t* pmax;
     LayoutView V;
     long long d;
     uint32_t carry;   // running max of end over the rows of EARLIER genome-range shards (0: none)
+    ClusterPredicate pred;
     __device__ unsigned long long operator()(int64_t i) const {
         const uint32_t s = gs[i];
         uint32_t pm = carry;
         if (i > 0) pm = max(pm, pmax[i - 1]);
         const uint32_t b = __ldg(V.base + chrom_of(V, s));
-        const bool joins = pm > b && (long long)pm + d >= (long long)s;
+        const bool joins = pm > b && (long long)pm + d >= (long long)s && predicate_holds(pred, i);
         return joins ? 0ull : 1ull;
     }
 };
+
+__global__ void gather_i32_kernel(const int32_t* __restrict__ src, const int32_t* __restrict__ rid, int64_t n, int32_t* __restrict__ dst) {
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) dst[i] = __ldg(src + rid[i]);
+}
 struct OutRunningCount {
     uint32_t* G;
     __device__ void operator()(int64_t i, unsigned long long excl, unsigned long long v) const { G[i] = (uint32_t)(excl + v); }
@@ -172,8 +200,13 @@ inline int grid_of(const giqlb_ctx* ctx, int64_t n, int per_thread) {
 inline LayoutView view_of(const giqlb_layout* lay) { return LayoutView{lay->d_base, lay->d_lo32, lay->n_codes}; }
 
 // flags -> running count G for rows [lo, hi) of the index; returns the block's cluster count in *total_dev
-int running_count(giqlb_ctx* ctx, const giqlb_index* X, int64_t lo, int64_t hi, long long d, uint32_t* G, uint32_t carry = 0) {
-    return launch_scan<OpAddU64>(ctx, hi - lo, InClusterFlag{X->gs + lo, X->pmax + lo, view_of(X->layout), d, carry},
+int running_count(giqlb_ctx* ctx, const giqlb_index* X, int64_t lo, int64_t hi, long long d, uint32_t* G, uint32_t carry = 0,
+                  ClusterPredicate pred = ClusterPredicate{nullptr, nullptr, 0}) {
+    if (pred.cur) {   // the operand arrays cover the whole index: a block starts a fresh partition, its first row has no predecessor
+        pred.cur += lo;
+        pred.prev += lo;
+    }
+    return launch_scan<OpAddU64>(ctx, hi - lo, InClusterFlag{X->gs + lo, X->pmax + lo, view_of(X->layout), d, carry, pred},
                                  OutRunningCount{G + lo});
 }
 
@@ -188,7 +221,22 @@ int check_index(giqlb_ctx* ctx, giqlb_index* X, const char* who) {
 
 }  // namespace
 
+static int cluster_impl(giqlb_ctx* ctx, giqlb_index* X, int64_t distance, const int32_t* cur_key_by_row, const int32_t* prev_key_by_row, int op,
+                        int32_t* cluster_id_by_input_row);
+
 extern "C" int giqlb_cluster(giqlb_ctx* ctx, giqlb_index* X, int64_t distance, int32_t* cluster_id_by_input_row) {
+    return cluster_impl(ctx, X, distance, nullptr, nullptr, 0, cluster_id_by_input_row);
+}
+
+extern "C" int giqlb_cluster_predicate(giqlb_ctx* ctx, giqlb_index* X, int64_t distance, const int32_t* cur_key_by_row,
+                                       const int32_t* prev_key_by_row, int op, int32_t* cluster_id_by_input_row) {
+    if (!ctx || !X || op < GIQLB_CMP_EQ || op > GIQLB_CMP_GE || (X->n > 0 && (!cur_key_by_row || !prev_key_by_row)))
+        return giqlb_fail(ctx, GIQLB_ERR_INVALID, "cluster_predicate: bad argument");
+    return cluster_impl(ctx, X, distance, cur_key_by_row, prev_key_by_row, op, cluster_id_by_input_row);
+}
+
+static int cluster_impl(giqlb_ctx* ctx, giqlb_index* X, int64_t distance, const int32_t* cur_key_by_row, const int32_t* prev_key_by_row, int op,
+                        int32_t* cluster_id_by_input_row) {
     if (!ctx || !X || (X->n > 0 && !cluster_id_by_input_row)) return giqlb_fail(ctx, GIQLB_ERR_INVALID, "cluster: bad argument");
     begin_call(ctx);
     GIQLB_TRY(check_index(ctx, X, "cluster"));
@@ -197,16 +245,25 @@ extern "C" int giqlb_cluster(giqlb_ctx* ctx, giqlb_index* X, int64_t distance, i
     GIQLB_TRY(giqlb_index_ensure_pmax(ctx, X));
     const long long d = distance > 0 ? (long long)distance : 0;   // cluster.py:266-272: the term is added only when > 0
     uint32_t *G = nullptr, *off = nullptr;
+    int32_t *kc = nullptr, *kp = nullptr;
     GIQLB_TRY(dev_alloc(ctx, &G, (size_t)n));
     int st = dev_alloc(ctx, &off, (size_t)X->layout->n_codes);
+    if (st == GIQLB_OK && cur_key_by_row) st = dev_alloc(ctx, &kc, (size_t)n);
+    if (st == GIQLB_OK && cur_key_by_row) st = dev_alloc(ctx, &kp, (size_t)n);
     const int nb = X->grouped_by_strand ? X->n_blocks : 1;
     const LayoutView V = view_of(X->layout);
-    {
+    if (st == GIQLB_OK) {
         PhaseSpan ps(ctx, GIQLB_PH_CLUSTER);
+        if (cur_key_by_row) {   // operand codes into sorted-row order
+            gather_i32_kernel<<<grid_of(ctx, n, 4), 256, 0, ctx->stream>>>(cur_key_by_row, X->rid, n, kc);
+            gather_i32_kernel<<<grid_of(ctx, n, 4), 256, 0, ctx->stream>>>(prev_key_by_row, X->rid, n, kp);
+            ctx->launches_this_call += 2;
+            ctx->stats.kernels_total += 2;
+        }
         for (int b = 0; b < nb && st == GIQLB_OK; b++) {
             const int64_t lo = X->grouped_by_strand ? X->block_off[b] : 0, hi = X->grouped_by_strand ? X->block_off[b + 1] : n;
             if (hi <= lo) continue;
-            st = running_count(ctx, X, lo, hi, d, G);
+            st = running_count(ctx, X, lo, hi, d, G, 0, ClusterPredicate{kc, kp, op});
             if (st != GIQLB_OK) break;
             cluster_chrom_offsets_kernel<<<(V.n_codes + 127) / 128, 128, 0, ctx->stream>>>(X->gs + lo, G + lo, hi - lo, V, off);
             ctx->launches_this_call++;
@@ -220,11 +277,13 @@ extern "C" int giqlb_cluster(giqlb_ctx* ctx, giqlb_index* X, int64_t distance, i
     }
     dev_free(ctx, G);
     dev_free(ctx, off);
+    dev_free(ctx, kc);
+    dev_free(ctx, kp);
     if (st != GIQLB_OK) return st;
     ctx->stats.rows_in[0] = n;
     ctx->stats.rows_in[1] = 0;
     ctx->stats.rows_out = n;
-    ctx->stats.algorithmic_bytes = 12 * n + (X->strand ? n : 0) + 4 * n;
+    ctx->stats.algorithmic_bytes = 12 * n + (X->strand ? n : 0) + 4 * n + (cur_key_by_row ? 16 * n : 0);
     return end_call(ctx);
 }
 

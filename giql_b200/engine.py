@@ -965,16 +965,41 @@ class Engine:
                 return lit
         raise KeyError(code)
 
-    def cluster(self, t: DeviceTable, distance: int = 0, stranded: bool = False) -> torch.Tensor:
-        """CLUSTER(interval[, distance][, stranded := true]) -> int32 cluster id per input row (1-based,
-        restarting per chrom[, strand] partition).  reference: src/giql/expanders/cluster.py:205-310, 430-434
-        (raw table coordinates: expressions.py:223-226)."""
+    @staticmethod
+    def predicate_codes(cur_values, prev_values):
+        """Order-preserving int32 codes of the two operand columns of ``predicate := cur <op> PREV(prev)``, ranked together
+        so that codes compare like the values; None / NaN-free NULLs become GIQLB_KEY_NULL."""
+        cur, prev = list(cur_values), list(prev_values)
+        values = sorted({v for v in cur if v is not None} | {v for v in prev if v is not None})
+        rank = {v: i for i, v in enumerate(values)}
+        null = _cabi.KEY_NULL
+        enc = lambda col: np.fromiter((null if v is None else rank[v] for v in col), dtype=np.int32, count=len(col))
+        return enc(cur), enc(prev)
+
+    def cluster(self, t: DeviceTable, distance: int = 0, stranded: bool = False, predicate=None) -> torch.Tensor:
+        """CLUSTER(interval[, distance][, stranded := true][, predicate := cur <op> PREV(prev)]) -> int32 cluster id per
+        input row (1-based, restarting per chrom[, strand] partition).  reference: src/giql/expanders/cluster.py:205-310,
+        430-434 (raw table coordinates: expressions.py:223-226).  ``predicate``: ``(cur_values, op, prev_values)`` with one
+        value per input row (host sequences) — the row also has to satisfy ``cur <op> PREV(prev)`` against its immediate
+        sorted predecessor to stay in the cluster (cluster.py:281-299)."""
         out = self._empty(t.n, torch.int32)
         if t.n == 0:
             return out
+        keys = None
+        if predicate is not None:
+            cur_values, op, prev_values = predicate
+            if op not in self._CMP_OPS:
+                raise ValueError(f"unknown comparison {op!r}")
+            if len(cur_values) != t.n or len(prev_values) != t.n:
+                raise ValueError("predicate columns must have one value per row")
+            kc, kp = self.predicate_codes(cur_values, prev_values)
+            keys = (self._dev(kc), self._dev(kp), self._CMP_OPS[op])
         lay, ix = self._self_index(t, stranded, raw=True)
         try:
-            self._check(self.lib.giqlb_cluster(self.ctx, ix.h, int(distance or 0), _ptr(out)))
+            if keys is None:
+                self._check(self.lib.giqlb_cluster(self.ctx, ix.h, int(distance or 0), _ptr(out)))
+            else:
+                self._check(self.lib.giqlb_cluster_predicate(self.ctx, ix.h, int(distance or 0), _ptr(keys[0]), _ptr(keys[1]), keys[2], _ptr(out)))
         finally:
             ix.free()
             lay.free()

@@ -91,8 +91,8 @@ class EngineBackend:
         res = self.e.nearest(self._table(Q, qcfg), self._table(T, tcfg), k=k, max_distance=max_distance, stranded=stranded, signed=signed)
         return tuple(x.cpu().numpy() for x in (res.query_rows, res.target_rows, res.distance, res.valid))
 
-    def cluster_array(self, T, distance=0, stranded=False):
-        return self.e.cluster(self._table(T, None), distance=distance, stranded=stranded).cpu().numpy()
+    def cluster_array(self, T, distance=0, stranded=False, predicate=None):
+        return self.e.cluster(self._table(T, None), distance=distance, stranded=stranded, predicate=predicate).cpu().numpy()
 
     # -- list flavour (shared with the oracle backend of the test-suite)
     def pairs(self, L, R, lcfg=None, rcfg=None):
@@ -118,8 +118,8 @@ class EngineBackend:
                              stranded=stranded, signed=signed)
         return res.rows()
 
-    def cluster(self, T, distance=0, stranded=False):
-        return self.cluster_array(T, distance, stranded).tolist()
+    def cluster(self, T, distance=0, stranded=False, predicate=None):
+        return self.cluster_array(T, distance, stranded, predicate).tolist()
 
     def merge(self, T, distance=0, stranded=False):
         return self.e.merge(self._table(T, None), distance=distance, stranded=stranded).rows()
@@ -277,10 +277,37 @@ class _Parser:
             if self.at("id") and (self.at("op", ":=", 1) or self.at("op", "=>", 1)):
                 key = self.take("id").lower()
                 self.take("op")
-                args[key] = self.scalar()
+                args[key] = self.predecessor_predicate() if key == "predicate" else self.scalar()
             else:
                 args.setdefault("_positional", []).append(self.scalar())
         return args
+
+    def predecessor_predicate(self):
+        """`predicate := <col> <op> PREV(<col>)` (either side may carry the PREV): the CLUSTER / MERGE gate against the
+        immediate sorted predecessor (src/giql/expanders/cluster.py:281-299, 587-644; PREV takes exactly one column and
+        does not nest, :618-630).  Normalised to {"cur", "op", "prev"}."""
+        def operand():
+            if self.at("id") and self.peek()[1].upper() == "PREV" and self.at("op", "(", 1):
+                self.take("id")
+                self.take("op", "(")
+                if self.at("id") and self.peek()[1].upper() == "PREV":
+                    raise ValueError("PREV() cannot be nested; a CLUSTER/MERGE predicate compares only the immediate predecessor.")
+                col = self.column_ref()
+                if self.at("op", ","):
+                    raise ValueError("PREV() takes exactly one column argument; got 2.")
+                self.take("op", ")")
+                return True, col[1]
+            return False, self.column_ref()[1]
+        lp, lcol = operand()
+        op = self.take("op")
+        rp, rcol = operand()
+        op = {"<>": "!=", "==": "="}.get(op, op)
+        if op not in ("=", "!=", "<", "<=", ">", ">=") or lp == rp:
+            raise UnsupportedQuery("predicate := must compare one column with PREV(column)")
+        if lp:                                                            # PREV(a) op b  ==  b op' PREV(a)
+            op = {"<": ">", "<=": ">=", ">": "<", ">=": "<="}.get(op, op)
+            return {"cur": rcol, "op": op, "prev": lcol}
+        return {"cur": lcol, "op": op, "prev": rcol}
 
     def scalar(self):
         if self.at("num"):
@@ -343,7 +370,7 @@ class _Parser:
                 self.take("op", ")")
                 pos = args.get("_positional", [])
                 item = {"kind": fn.lower(), "distance": int(pos[0]) if pos else int(args.get("distance", 0) or 0),
-                        "stranded": bool(args.get("stranded", False))}
+                        "stranded": bool(args.get("stranded", False)), "predicate": args.get("predicate")}
             elif fn == "COUNT":
                 self.take("op", "(")
                 self.take("op", "*")
@@ -625,6 +652,28 @@ def _nearest(be, Q: _Rel, T: _Rel, j):
     return (np.asarray([x[0] for x in res], dtype=np.int64), np.asarray([x[1] for x in res], dtype=np.int64), _column([x[2] for x in res]))
 
 
+def _cluster_ids(be, f, p) -> np.ndarray:
+    """CLUSTER ids of the frame's rows (src/giql/expanders/cluster.py:205-310, 430-434), with the optional
+    `predicate := cur <op> PREV(prev)` gate (:281-299)."""
+    a = f.order[0]
+    g = f.genomic(a)
+    if p["stranded"] and "strand" not in g:
+        raise ValueError("stranded := true needs a strand column")
+    if not p["stranded"]:
+        g.pop("strand", None)
+    if not len(f):
+        return np.zeros(0, np.int64)
+    pred = None
+    if p.get("predicate"):
+        q = p["predicate"]
+        pred = (f.column(f.resolve(None, q["cur"]), q["cur"]).tolist(), q["op"], f.column(f.resolve(None, q["prev"]), q["prev"]).tolist())
+    if hasattr(be, "cluster_array"):
+        return be.cluster_array(g, p["distance"], p["stranded"], pred).astype(np.int64) if pred else be.cluster_array(g, p["distance"], p["stranded"]).astype(np.int64)
+    lists = {k: v.tolist() for k, v in g.items()}
+    ids = be.cluster(lists, p["distance"], p["stranded"], pred) if pred else be.cluster(lists, p["distance"], p["stranded"])
+    return np.asarray(ids, dtype=np.int64)
+
+
 class Session:
     """Registered tables + ``execute(giql_query)``.  ``backend`` defaults to the CUDA engine on device 0."""
 
@@ -882,7 +931,18 @@ class Session:
             g = f.genomic(f.order[0])
             if m["stranded"] and "strand" not in g:
                 raise ValueError("MERGE(stranded := true) needs a strand column")
-            rows = be.merge(g, m["distance"], m["stranded"]) if len(f) else []
+            if m.get("predicate") and len(f):
+                # merge.py:201-239: MERGE is GROUP BY chrom[, strand], cluster id over the predicate-gated CLUSTER; the ids come
+                # from the engine, the (small) aggregation is finished here
+                ids = _cluster_ids(be, f, m)
+                agg: dict[tuple, list] = {}
+                strands = g["strand"].tolist() if m["stranded"] else [None] * len(ids)
+                for c, st, cid, s0, e0 in zip(g["chrom"].tolist(), strands, ids.tolist(), g["start"].tolist(), g["end"].tolist()):
+                    a = agg.setdefault((c, st, cid), [s0, e0, 0])
+                    a[0], a[1], a[2] = min(a[0], s0), max(a[1], e0), a[2] + 1
+                rows = [((c, st, v[0], v[1], v[2]) if m["stranded"] else (c, v[0], v[1], v[2])) for (c, st, _), v in agg.items()]
+            else:
+                rows = be.merge(g, m["distance"], m["stranded"]) if len(f) else []
             width = 4 if m["stranded"] else 3
             out = [tuple(r[:width]) + ((r[-1],) if "count_star" in kinds else ()) for r in rows]
             out.sort(key=lambda r: (r[0], r[width - 2]))
@@ -905,18 +965,7 @@ class Session:
                 cols.append(p.get("name", p["col"]))
                 arrays.append(f.column(a, p["col"]))
             elif p["kind"] == "cluster":
-                # src/giql/expanders/cluster.py:205-310, 430-434 over the rows the FROM clause produced
-                g = f.genomic(f.order[0])
-                if p["stranded"] and "strand" not in g:
-                    raise ValueError("CLUSTER(stranded := true) needs a strand column")
-                if not p["stranded"]:
-                    g.pop("strand", None)
-                if not len(f):
-                    ids = np.zeros(0, np.int64)
-                elif hasattr(be, "cluster_array"):
-                    ids = be.cluster_array(g, p["distance"], p["stranded"]).astype(np.int64)
-                else:
-                    ids = np.asarray(be.cluster({k: v.tolist() for k, v in g.items()}, p["distance"], p["stranded"]), dtype=np.int64)
+                ids = _cluster_ids(be, f, p)                            # over the rows the FROM clause produced
                 cols.append(p.get("name", "cluster"))
                 arrays.append(ids)
             elif p["kind"] == "distance":

@@ -297,6 +297,14 @@ int giqlb_nearest(giqlb_ctx* ctx, const giqlb_layout* lay, const int32_t* q_code
  *            out_strand (nullable) receives the strand code of each region, out_count (nullable) COUNT(*).
  * Rows with end < start are rejected (their grouping depends on the tie order of the executing engine). */
 int giqlb_cluster(giqlb_ctx* ctx, giqlb_index* X, int64_t distance, int32_t* cluster_id_by_input_row);
+/* CLUSTER(interval[, distance], predicate := <cur column> <op> PREV(<prev column>))  (cluster.py:281-299, 587-644): a row
+ * stays in the running cluster only when it is adjacent to the running-max edge AND the comparison holds against its
+ * immediate sorted predecessor (rows tied on start keep their input order).  The two operand columns are given as
+ * order-preserving int32 codes per input row (the host ranks the values of both columns together); GIQLB_KEY_NULL is
+ * SQL NULL, which makes the comparison not TRUE.  op: GIQLB_CMP_*. */
+#define GIQLB_KEY_NULL (-2147483647 - 1)
+int giqlb_cluster_predicate(giqlb_ctx* ctx, giqlb_index* ix, int64_t distance, const int32_t* cur_key_by_row,
+                            const int32_t* prev_key_by_row, int op, int32_t* cluster_id_by_input_row);
 int giqlb_merge(giqlb_ctx* ctx, giqlb_index* X, int64_t distance, int32_t* out_code, int32_t* out_start,
                 int32_t* out_end, uint8_t* out_strand, int64_t* out_count, int64_t capacity, int64_t* n_out_host);
 

@@ -266,8 +266,16 @@ def nearest(Q, T, k=1, max_distance=None, stranded=False, signed=False):
 #                   src/giql/expanders/merge.py:183-439)
 # --------------------------------------------------------------------------- #
 
-def cluster(T, distance=0, stranded=False):
+_PRED_OPS = {"=": lambda a, b: a == b, "!=": lambda a, b: a != b, "<>": lambda a, b: a != b, "<": lambda a, b: a < b,
+             "<=": lambda a, b: a <= b, ">": lambda a, b: a > b, ">=": lambda a, b: a >= b}
+
+
+def cluster(T, distance=0, stranded=False, predicate=None):
     """1-based cluster ids aligned to input rows; ids restart per partition.
+
+    ``predicate`` = (cur_values, op, prev_values): the row stays in the running cluster only when it is adjacent AND
+    ``cur[row] op prev[immediate sorted predecessor]`` is TRUE — ``PREV(col)`` is ``LAG(col)`` over the same
+    partition / order (cluster.py:281-299, 587-644); NULL operands (and the first row's NULL LAG) make it not TRUE.
 
     flag_i = 0 iff MAX(end) over strictly-preceding rows of the partition
     (+ distance when distance > 0, cluster.py:266-272) >= start_i, else 1 (first
@@ -288,12 +296,15 @@ def cluster(T, distance=0, stranded=False):
         rows = sorted(rows, key=lambda i: (T["start"][i], i))
         flags = []
         run_max = None
+        before = None
         for i in rows:
-            if run_max is not None and run_max + d >= T["start"][i]:
-                flags.append(0)
-            else:
-                flags.append(1)
+            keep = run_max is not None and run_max + d >= T["start"][i]
+            if keep and predicate is not None:
+                a, b = predicate[0][i], predicate[2][before]
+                keep = a is not None and b is not None and bool(_PRED_OPS[predicate[1]](a, b))
+            flags.append(0 if keep else 1)
             run_max = T["end"][i] if run_max is None else max(run_max, T["end"][i])
+            before = i
         # RANGE frame: peers (equal start) see the sum through the last peer
         csum, acc = [], 0
         for f in flags:
@@ -310,7 +321,7 @@ def cluster(T, distance=0, stranded=False):
     return ids
 
 
-def merge(T, distance=0, stranded=False):
+def merge(T, distance=0, stranded=False, predicate=None):
     """Merged rows ``(chrom[, strand], start, end, count)`` ordered by (chrom, start).
 
     reference: merge.py:216-239 (cluster), :293-308 (GROUP BY chrom[,strand],
@@ -318,7 +329,7 @@ def merge(T, distance=0, stranded=False):
     ``count`` is COUNT(*) per region (user aggregate commonly requested,
     tests/integration/datafusion/test_cross_target_oracle.py:1196-1315).
     """
-    ids = cluster(T, distance, stranded)
+    ids = cluster(T, distance, stranded, predicate)
     agg = {}
     for i, cid in enumerate(ids):
         key = (T["chrom"][i], T["strand"][i] if stranded else None, cid)

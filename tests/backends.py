@@ -59,11 +59,11 @@ class OracleBackend:
         return self.go.nearest(canonicalise(Q, qcfg), canonicalise(T, tcfg), k=k, max_distance=max_distance,
                                stranded=stranded, signed=signed)
 
-    def cluster(self, T, distance=0, stranded=False):
-        return self.go.cluster(T, distance, stranded)
+    def cluster(self, T, distance=0, stranded=False, predicate=None):
+        return self.go.cluster(T, distance, stranded, predicate)
 
-    def merge(self, T, distance=0, stranded=False):
-        return self.go.merge(T, distance, stranded)
+    def merge(self, T, distance=0, stranded=False, predicate=None):
+        return self.go.merge(T, distance, stranded, predicate)
 
     def disjoin(self, T, REF=None, tcfg=None, rcfg=None):
         return self.go.disjoin(canonicalise(T, tcfg), None if REF is None else canonicalise(REF, rcfg))

@@ -72,6 +72,12 @@ STATEMENTS = [
     "SELECT a.name, b.name FROM peaks a LEFT JOIN genes b ON a.interval INTERSECTS b.interval AND a.strand = b.strand WHERE a.start >= 1000",
     "SELECT a.name, b.name FROM peaks a JOIN genes b ON a.interval INTERSECTS b.interval WHERE a.strand = '+' AND b.start > a.start",
     "SELECT a.name, b.name FROM peaks a JOIN genes b ON a.interval WITHIN b.interval AND a.name <> b.name AND a.\"end\" <= b.\"end\"",
+    # predicate-gated clustering (cluster.py:281-299, 587-644)
+    "SELECT name, CLUSTER(interval, predicate := strand = PREV(strand)) AS cid FROM peaks",
+    "SELECT name, CLUSTER(interval, 50, predicate => PREV(\"end\") <= start) AS cid FROM peaks",
+    "SELECT name, CLUSTER(interval, stranded := true, predicate := name >= PREV(name)) AS cid FROM peaks",
+    "SELECT MERGE(interval, predicate := strand = PREV(strand)), COUNT(*) FROM peaks",
+    "SELECT MERGE(interval, 20, stranded := true, predicate := name <> PREV(name)) FROM peaks",
 ]
 
 
@@ -108,6 +114,30 @@ def test_parse_shapes():
 def test_declined_shapes(q):
     with pytest.raises(UnsupportedQuery):
         sessions(OracleBackend()).execute(q)
+
+
+def test_predicate_clustering_against_brute_force():
+    s = sessions(OracleBackend())
+    P = s.tables["peaks"].data
+    got = dict(s.execute(STATEMENTS[37]).rows)
+    for c in CHROMS:     # sweep per chromosome: adjacency against the running max end AND same strand as the immediate predecessor
+        rows = sorted((i for i in range(90) if P["chrom"][i] == c), key=lambda i: (P["start"][i], i))
+        cid, run_max, before, ids = 0, None, None, {}
+        for i in rows:
+            keep = run_max is not None and run_max >= P["start"][i] and P["strand"][i] == P["strand"][before]
+            cid += 0 if keep else 1
+            ids[i] = cid
+            run_max = P["end"][i] if run_max is None else max(run_max, P["end"][i])
+            before = i
+        starts = [P["start"][i] for i in rows]
+        for i in rows:   # peers (equal start) report the id of the last peer (RANGE frame of the SUM window)
+            last = max(j for j in rows if P["start"][j] == P["start"][i] and rows.index(j) >= rows.index(i)) if starts.count(P["start"][i]) > 1 else i
+            last = [j for j in rows if P["start"][j] == P["start"][i]][-1]
+            assert got[P["name"][i]] == ids[last], (c, i)
+    with pytest.raises(ValueError, match="cannot be nested"):
+        s.execute("SELECT CLUSTER(interval, predicate := strand = PREV(PREV(strand))) FROM peaks")
+    with pytest.raises(ValueError, match="exactly one column"):
+        s.execute("SELECT CLUSTER(interval, predicate := strand = PREV(strand, name)) FROM peaks")
 
 
 def test_errors_mirror_reference_messages():

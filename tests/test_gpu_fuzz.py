@@ -115,3 +115,19 @@ def test_distance_fuzz(shape, engine):
     for stranded in (False, True):
         for signed in (False, True):
             assert eb.distance(A, B, stranded=stranded, signed=signed) == ob.distance(A, B, stranded=stranded, signed=signed), (stranded, signed)
+
+
+@pytest.mark.parametrize("shape", [s for s in SHAPES if s != "degenerate"])
+@pytest.mark.parametrize("op,distance,stranded", [("=", 0, False), ("!=", 40, True), (">=", 0, False), ("<", 200, True)])
+def test_cluster_predicate_fuzz(shape, op, distance, stranded, engine):
+    """CLUSTER(..., predicate := cur <op> PREV(prev)) — giqlb_cluster_predicate against the oracle (whose predicate rule is
+    pinned to the reference's LAG rewrite on SQLite); NULL operands, string and integer operand columns"""
+    rng = np.random.default_rng(SHAPES.index(shape) * 13 + distance)
+    T = make(rng, 1800, shape)
+    n = len(T["start"])
+    cur = [None if i % 19 == 0 else int(v) for i, v in enumerate(rng.integers(0, 5, size=n))]
+    prev = [None if i % 29 == 0 else int(v) for i, v in enumerate(rng.integers(0, 5, size=n))]
+    ob, eb = OracleBackend(), EngineBackend(engine)
+    assert eb.cluster(T, distance, stranded, (cur, op, prev)) == [int(x) for x in ob.cluster(T, distance, stranded, (cur, op, prev))]
+    names = [["alpha", "beta", "gamma", None][i] for i in rng.integers(0, 4, size=n)]
+    assert eb.cluster(T, distance, stranded, (names, op, names)) == [int(x) for x in ob.cluster(T, distance, stranded, (names, op, names))]

@@ -92,3 +92,21 @@ def test_c_oracle_agrees_with_python_oracle(seed, c_oracle):
     assert np.array_equal(np.nonzero(ex)[0], go.semi_rows(L, R))
     ids = c_oracle.cluster(lc, L["start"], L["end"], len(names), distance=5)
     assert ids.tolist() == go.cluster(L, distance=5)
+
+
+@pytest.mark.parametrize("seed,op,distance,stranded", [(0, "=", 0, False), (1, "!=", 0, True), (2, ">=", 30, False), (3, "<", 0, False), (4, "=", 100, True)])
+def test_cluster_predicate_matches_reference_sql_shape_on_sqlite(seed, op, distance, stranded):
+    """`predicate := cur <op> PREV(prev)`: the oracle against the reference's LAG rewrite (cluster.py:281-310, 587-644)
+    executed on SQLite.  Starts are unique within a partition — with ties the reference's result depends on the engine's
+    tie order."""
+    rng = np.random.default_rng(seed)
+    n = 400
+    chrom = [["chr1", "chr2", "chr3"][i] for i in rng.integers(0, 3, size=n)]
+    start = rng.permutation(4000)[:n]
+    T = {"chrom": chrom, "start": start.tolist(), "end": (start + rng.integers(1, 60, size=n)).tolist(),
+         "strand": [["+", "-"][i] for i in rng.integers(0, 2, size=n)]}
+    cur = [None if i % 17 == 0 else int(v) for i, v in enumerate(rng.integers(0, 4, size=n))]
+    prev = [None if i % 23 == 0 else int(v) for i, v in enumerate(rng.integers(0, 4, size=n))]
+    assert go.cluster(T, distance, stranded, predicate=(cur, op, prev)) == so.cluster_predicate(T, cur, op, prev, distance, stranded)
+    names = [["a", "b", "c"][i] for i in rng.integers(0, 3, size=n)]
+    assert go.cluster(T, distance, stranded, predicate=(names, op, names)) == so.cluster_predicate(T, names, op, names, distance, stranded)
