@@ -77,7 +77,7 @@ def workload_name(rows):
 class ClockSampler:
     """Samples SM clock and throttle reasons of one GPU through NVML while the timed region runs."""
 
-    def __init__(self, index: int, period_s: float = 0.002):
+    def __init__(self, index: int, period_s: float = float(os.environ.get("GIQLB_BENCH_CLOCK_PERIOD_S", "0.002"))):
         self.index, self.period = index, period_s
         self.samples, self.reasons = [], set()
         self.max_mhz = None
