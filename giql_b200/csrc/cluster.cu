@@ -30,6 +30,21 @@ struct LayoutView {
     int32_t n_codes;
 };
 
+// One-entry memo for chrom_of: rows arrive sorted by linear coordinate, so consecutive lookups of a thread almost always fall
+// into the same chromosome's cell range [lo, hi) and skip the binary search.
+struct ChromMemo {
+    uint32_t lo = 1u, hi = 0u;   // empty range
+    int32_t c = 0;
+};
+__device__ __forceinline__ int32_t chrom_of(const LayoutView& V, uint32_t g);
+__device__ __forceinline__ int32_t chrom_of(const LayoutView& V, uint32_t g, ChromMemo& m) {
+    if (g >= m.lo && g < m.hi) return m.c;
+    m.c = chrom_of(V, g);
+    m.lo = __ldg(V.base + m.c);
+    m.hi = m.c + 1 < V.n_codes ? __ldg(V.base + m.c + 1) : 0xffffffffu;
+    return m.c;
+}
+
 // chromosome whose cell range holds linear coordinate g: last c with base[c] <= g
 __device__ __forceinline__ int32_t chrom_of(const LayoutView& V, uint32_t g) {
     int32_t lo = 0, hi = V.n_codes;   // answer in [0, n_codes)
@@ -70,11 +85,13 @@ struct InClusterFlag {
     long long d;
     uint32_t carry;   // running max of end over the rows of EARLIER genome-range shards (0: none)
     ClusterPredicate pred;
+    mutable ChromMemo memo;   // per-thread copy of the functor
     __device__ unsigned long long operator()(int64_t i) const {
         const uint32_t s = gs[i];
         uint32_t pm = carry;
         if (i > 0) pm = max(pm, pmax[i - 1]);
-        const uint32_t b = __ldg(V.base + chrom_of(V, s));
+        chrom_of(V, s, memo);
+        const uint32_t b = memo.lo;
         const bool joins = pm > b && (long long)pm + d >= (long long)s && predicate_holds(pred, i);
         return joins ? 0ull : 1ull;
     }
@@ -113,9 +130,10 @@ __device__ __forceinline__ int64_t last_peer(const uint32_t* __restrict__ gs, in
 __global__ void __launch_bounds__(256)
 cluster_ids_kernel(const uint32_t* __restrict__ gs, const int32_t* __restrict__ rid, const uint32_t* __restrict__ G,
                    const uint32_t* __restrict__ off, int64_t n, LayoutView V, int32_t* __restrict__ out_by_row) {
+    ChromMemo memo;
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
         const int64_t j = last_peer(gs, i, n);
-        const int32_t c = chrom_of(V, gs[i]);
+        const int32_t c = chrom_of(V, gs[i], memo);
         out_by_row[rid[i]] = (int32_t)(G[j] - off[c]);
     }
 }
@@ -161,9 +179,10 @@ __global__ void cluster_chrom_counts_kernel(const uint32_t* __restrict__ gs, con
 __global__ void cluster_ids_offset_kernel(const uint32_t* __restrict__ gs, const int32_t* __restrict__ rid, const uint32_t* __restrict__ G,
                                           const uint32_t* __restrict__ off, const uint32_t* __restrict__ id_offset, int64_t n, LayoutView V,
                                           int32_t* __restrict__ out_by_row) {
+    ChromMemo memo;
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
         const int64_t j = last_peer(gs, i, n);
-        const int32_t c = chrom_of(V, gs[i]);
+        const int32_t c = chrom_of(V, gs[i], memo);
         out_by_row[rid[i]] = (int32_t)(G[j] - off[c] + id_offset[c]);
     }
 }
