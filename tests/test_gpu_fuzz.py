@@ -1,6 +1,8 @@
 """Randomised parity sweep: every operator of the CUDA path against the CPU oracle over adversarial table shapes —
 tile-boundary sizes, hundreds of chromosomes, duplicates, nested and genome-spanning intervals (skewed outputs),
 zero- and negative-width rows, coordinates at the top of the int32 range, NULL strands.  Bit-exact comparisons."""
+import zlib
+
 import numpy as np
 import pytest
 
@@ -42,7 +44,7 @@ def no_strand(t):
 @pytest.mark.parametrize("shape", SHAPES)
 @pytest.mark.parametrize("nl,nr", [(1023, 1025), (2049, 300), (17, 4096)])
 def test_join_family_fuzz(shape, nl, nr, engine):
-    rng = np.random.default_rng(hash((shape, nl, nr)) % (2 ** 32))
+    rng = np.random.default_rng(zlib.crc32(repr((shape, nl, nr)).encode()))   # deterministic across processes (str hashes are salted)
     L, R = no_strand(make(rng, nl, shape)), no_strand(make(rng, nr, shape))
     ob = OracleBackend()
     for mode in ("two_pass", "single_pass"):

@@ -78,3 +78,18 @@ def test_synth_generators_are_valid_bed():
         assert t["names"] == sorted(t["names"], key=lambda s: s.encode())
     a, b = synth.peaks(1000, 1), synth.peaks(1000, 1)
     assert np.array_equal(a["start"], b["start"])   # seeded
+
+
+def test_bind_host_to_gpu_is_safe_without_a_gpu():
+    """the affinity helper never widens the allowed core set and degrades to a no-op when NVML / the GPU is absent"""
+    import os
+
+    import giql_b200
+
+    before = os.sched_getaffinity(0)
+    prev, new = giql_b200.bind_host_to_gpu(0)
+    try:
+        assert prev == before
+        assert new is None or (new and new <= before)
+    finally:
+        os.sched_setaffinity(0, before)
