@@ -21,6 +21,9 @@ constexpr int RS_IPT = GIQLB_RS_IPT;
 #ifndef GIQLB_RS_LOOKBACK
 #define GIQLB_RS_LOOKBACK 4      // predecessor tiles fetched per look-back step
 #endif
+#ifndef GIQLB_RS_LOOKBACK_WIDE
+#define GIQLB_RS_LOOKBACK_WIDE 4 // ... per step after the first (prefetched) one
+#endif
 #ifndef GIQLB_RS_BACKOFF_NS
 #define GIQLB_RS_BACKOFF_NS 20   // pause between polls of a predecessor tile that has not published yet
 #endif
@@ -39,6 +42,39 @@ constexpr uint32_t ST_FLAG_AGG = 1u << 30;
 constexpr uint32_t ST_FLAG_INCL = 2u << 30;
 constexpr uint32_t ST_VALUE_MASK = (1u << 30) - 1;
 constexpr uint32_t RS_SPIN_LIMIT = 1u << 26;
+
+// One look-back step over W predecessor status words sv[0] (nearest) .. sv[W-1]: adds what is published to `prefix`, moves
+// t, sets `done` at the first inclusive word; returns false when an unpublished word stopped the step early (retry).
+// W is a multiple of 4: far from the frontier all W words are plain aggregates, and since W flag fields of 1 << 30 sum to
+// a multiple of 2^32, adding the raw words adds exactly the W counts.
+template <int W>
+__device__ __forceinline__ bool lookback_step(const uint32_t (&sv)[W], int64_t& t, uint32_t& prefix, bool& done) {
+    static_assert(W % 4 == 0, "the raw-sum shortcut needs W * 2^30 == 0 mod 2^32");
+    uint32_t all_and = sv[0], all_or = sv[0], sum = sv[0];
+#pragma unroll
+    for (int j = 1; j < W; j++) {
+        all_and &= sv[j];
+        all_or |= sv[j];
+        sum += sv[j];
+    }
+    if ((all_and & ~ST_VALUE_MASK) == ST_FLAG_AGG && (all_or & ~ST_VALUE_MASK) == ST_FLAG_AGG) {
+        prefix += sum;
+        t -= W;
+        return true;
+    }
+    int used = 0;
+#pragma unroll
+    for (int j = 0; j < W; j++) {
+        if (done || used != j) continue;
+        const uint32_t flag = sv[j] & ~ST_VALUE_MASK;
+        if (flag == 0) continue;              // not published yet: retry from this tile
+        prefix += sv[j] & ST_VALUE_MASK;
+        used = j + 1;
+        if (flag == ST_FLAG_INCL) done = true;
+    }
+    t -= used;
+    return used == W;
+}
 
 // ---- histogram of all digits in one read ---------------------------------------------------------
 __global__ void __launch_bounds__(RS_THREADS)
@@ -215,25 +251,15 @@ rs_onesweep_kernel(const uint32_t* __restrict__ keys_in, const uint32_t* __restr
     if (tile > 0) {
         int64_t t = (int64_t)tile - 1;
         uint32_t spins = 0;
-        bool done = false, first = true;
+        bool done = false;
+        // first step: the four words prefetched above; then GIQLB_RS_LOOKBACK_WIDE predecessors per round trip
+        if (!lookback_step<GIQLB_RS_LOOKBACK>(pre, t, prefix, done) && !done) __nanosleep(GIQLB_RS_BACKOFF_NS);
         while (!done) {
-            uint32_t sv[GIQLB_RS_LOOKBACK];
+            uint32_t sv[GIQLB_RS_LOOKBACK_WIDE];
 #pragma unroll
-            for (int j = 0; j < GIQLB_RS_LOOKBACK; j++)
-                sv[j] = first ? pre[j] : (t - j >= 0 ? *(volatile uint32_t*)(status + (size_t)(t - j) * RS_RADIX + d_own) : (2u << 30));   // = ST_FLAG_INCL | 0
-            first = false;
-            int used = 0;
-#pragma unroll
-            for (int j = 0; j < GIQLB_RS_LOOKBACK; j++) {
-                if (done || used != j) continue;
-                const uint32_t flag = sv[j] & ~ST_VALUE_MASK;
-                if (flag == 0) continue;              // not published yet: retry from this tile
-                prefix += sv[j] & ST_VALUE_MASK;
-                used = j + 1;
-                if (flag == ST_FLAG_INCL) done = true;
-            }
-            t -= used;
-            if (!done && used < GIQLB_RS_LOOKBACK) {
+            for (int j = 0; j < GIQLB_RS_LOOKBACK_WIDE; j++)
+                sv[j] = t - j >= 0 ? *(volatile uint32_t*)(status + (size_t)(t - j) * RS_RADIX + d_own) : (2u << 30);   // = ST_FLAG_INCL | 0
+            if (!lookback_step<GIQLB_RS_LOOKBACK_WIDE>(sv, t, prefix, done) && !done) {
                 if (++spins > RS_SPIN_LIMIT) { *err_flag = 1; break; }
                 __nanosleep(GIQLB_RS_BACKOFF_NS);
             }
