@@ -598,7 +598,11 @@ class Engine:
         if depth < 2:
             raise ValueError("depth must be >= 2")
         main = self.stream
-        s_in, s_out = torch.cuda.Stream(self.device), torch.cuda.Stream(self.device)
+        # one upload and one download stream per engine, kept across calls: the caching allocator pools blocks per stream,
+        # so fresh streams on every call would make every call pay cudaMalloc again (measured: 22 ms instead of 8.6 ms a batch)
+        if getattr(self, "_copy_streams", None) is None:
+            self._copy_streams = (torch.cuda.Stream(self.device), torch.cuda.Stream(self.device))
+        s_in, s_out = self._copy_streams
 
         def upload(batch):
             with torch.cuda.stream(s_in):
