@@ -16,6 +16,10 @@ Recognised shapes (GIQL semantics cited per branch in :class:`Session`):
 * ``FROM a x JOIN b y ON x.chrom = y.chrom WHERE DISTANCE(x.interval, y.interval[, ...]) < n``
 * ``SELECT ..., CLUSTER(interval[, d][, stranded := true]) AS c FROM t``; ``SELECT MERGE(interval[, d][, stranded := true])[, COUNT(*)] FROM t``
 * ``FROM DISJOIN(t[, ref])``;  ``WITH name AS (SELECT * FROM t) ...``;  a derived table ``FROM (<query>) alias``
+* ``SELECT <left cols>, COUNT(*) | COUNT(y.col) FROM a x [LEFT] JOIN b y ON x.interval INTERSECTS y.interval GROUP BY <left cols>``
+  (count_overlaps: one per-row count probe, no pair list); any other ``GROUP BY cols`` with ``COUNT`` over the joined rows
+* residual ON-conjuncts ``AND x.col <op> y.col`` (same / opposite strand joins), ``WHERE col <op> col | literal``
+* ``CLUSTER / MERGE(interval, predicate := col <op> PREV(col))``
 * projections ``*``, ``x.*``, ``[x.]col [AS name]``, ``DISTANCE(x.interval, y.interval[, ...]) [AS name]``; ``DISTINCT``;
   ``ORDER BY col [DESC]``; ``LIMIT n``
 
@@ -232,8 +236,15 @@ class _Parser:
                 q["where"].append(self.condition())
                 if not self.accept("kw", "AND"):
                     break
-        if self.at("kw", "GROUP"):
-            raise UnsupportedQuery("GROUP BY is finished by the SQL engine, not by the built-in front-end")
+        q["group"] = []
+        if self.accept("kw", "GROUP"):
+            self.take("kw", "BY")
+            while True:
+                q["group"].append(self.column_ref())
+                if not self.accept("op", ","):
+                    break
+            if self.at("kw", "HAVING") or (self.at("id") and self.peek()[1].upper() == "HAVING"):
+                raise UnsupportedQuery("HAVING is finished by the SQL engine")
         if self.accept("kw", "ORDER"):
             self.take("kw", "BY")
             while True:
@@ -373,9 +384,12 @@ class _Parser:
                         "stranded": bool(args.get("stranded", False)), "predicate": args.get("predicate")}
             elif fn == "COUNT":
                 self.take("op", "(")
-                self.take("op", "*")
+                if self.accept("op", "*"):
+                    item = {"kind": "count_star"}
+                else:
+                    ref = self.column_ref()
+                    item = {"kind": "count_col", "alias": ref[0], "col": ref[1]}
                 self.take("op", ")")
-                item = {"kind": "count_star"}
             else:
                 raise UnsupportedQuery(f"function {fn} is not handled by the built-in front-end")
         else:
@@ -768,6 +782,9 @@ class Session:
             base = self._relation(q, src)
             f.add(src["alias"], base, np.arange(len(base), dtype=np.int64))
         where = list(q["where"])
+        fast = self._count_overlaps(q, f, where)
+        if fast is not None:
+            return fast
         for j in q["joins"]:
             if j["kind"] == "nearest":
                 self._join_nearest(q, f, j)
@@ -832,6 +849,93 @@ class Session:
         for w in where:
             self._filter(f, w)
         return self._finish(q, f)
+
+    def _count_overlaps(self, q, f: _Frame, where) -> Optional[Result]:
+        """The count_overlaps shape (src/giql/expanders/intersects_duckdb.py:432-548, 806-854):
+
+            SELECT <left columns>, COUNT(*) | COUNT(b.col) FROM a [LEFT] JOIN b ON a.interval INTERSECTS b.interval
+            GROUP BY <the same left columns>
+
+        bound to ONE per-left-row count probe (giqlb_intersects_count_rows) — no pair list is materialised — followed by the
+        sum over equal left keys.  Returns None when the statement is not of this shape (the generic path then groups the
+        joined rows)."""
+        if not q.get("group") or len(q["joins"]) != 1 or where or q["distinct"] or len(f.order) != 1:
+            return None
+        j = q["joins"][0]
+        if j["kind"] not in ("inner", "left") or j["source"]["kind"] != "table":
+            return None
+        conds = j.get("on") or []
+        la, ra = f.order[0], j["source"]["alias"]
+        if len(conds) != 1 or conds[0]["kind"] != "spatial" or conds[0]["op"] != "intersects" or {conds[0]["left"], conds[0]["right"]} != {la, ra}:
+            return None
+        left, right = f.rels[la], self._relation(q, j["source"])
+        keys, counters = [], []
+        for p in q["proj"]:
+            if p["kind"] == "col" and (p["alias"] in (None, la)) and p["col"] in left.data:
+                keys.append(p)
+            elif p["kind"] == "count_star" or (p["kind"] == "count_col" and p["alias"] == ra and p["col"] in right.data
+                                               and right.data[p["col"]].dtype != object):
+                counters.append(p)                                    # COUNT(b.col) over a NULL-free column counts the matches
+            else:
+                return None
+        group_cols = [c for a, c in q["group"] if a in (None, la)]
+        if len(group_cols) != len(q["group"]) or len(counters) != 1 or sorted(group_cols) != sorted(p["col"] for p in keys) or not keys:
+            return None
+        be = self.backend
+        n = len(left)
+        per_row = _counts(be, left.genomic(), right.genomic(), left.config, right.config).astype(np.int64) if n and len(right) else np.zeros(n, np.int64)
+        cnt = counters[0]
+        if j["kind"] == "left" and cnt["kind"] == "count_star":
+            per_row = np.maximum(per_row, 1)                            # the NULL-extended row of an unmatched left row counts once
+        cols = [left.data[p["col"]] for p in keys]
+        first: dict[tuple, int] = {}
+        total: list[int] = []
+        for i, key in enumerate(zip(*(c.tolist() for c in cols))):
+            g = first.setdefault(key, len(total))
+            if g == len(total):
+                total.append(0)
+            total[g] += int(per_row[i])
+        rows = [k + (total[g],) for k, g in first.items() if j["kind"] == "left" or total[g] > 0]
+        names = {id(p): p.get("name", p["col"]) for p in keys}
+        out_cols, arrays = [], []
+        for p in q["proj"]:
+            if p is cnt:
+                out_cols.append(p.get("name", "count"))
+                arrays.append(np.asarray([r[-1] for r in rows], dtype=np.int64))
+            else:
+                k = keys.index(p)
+                out_cols.append(names[id(p)])
+                arrays.append(_column([r[k] for r in rows]))
+        return self._order_limit(q, Result(out_cols, arrays))
+
+    def _group_count(self, q, f: _Frame) -> Result:
+        """generic GROUP BY <columns> with COUNT(*) / COUNT(col) over the joined rows"""
+        keys = [(f.resolve(a, c), c) for a, c in q["group"]]
+        key_cols = [f.column(a, c).tolist() for a, c in keys]
+        groups: dict[tuple, list[int]] = {}
+        for i, key in enumerate(zip(*key_cols)) if key_cols else []:
+            groups.setdefault(key, []).append(i)
+        out_cols, arrays = [], []
+        for p in q["proj"]:
+            if p["kind"] == "col":
+                a = f.resolve(p["alias"], p["col"])
+                if (a, p["col"]) not in keys:
+                    raise UnsupportedQuery(f"column {p['col']!r} must appear in GROUP BY")
+                k = keys.index((a, p["col"]))
+                out_cols.append(p.get("name", p["col"]))
+                arrays.append(_column([key[k] for key in groups]))
+            elif p["kind"] == "count_star":
+                out_cols.append(p.get("name", "count"))
+                arrays.append(np.asarray([len(v) for v in groups.values()], dtype=np.int64))
+            elif p["kind"] == "count_col":
+                a = f.resolve(p["alias"], p["col"])
+                vals = f.column(a, p["col"])
+                present = np.array([v is not None for v in vals], dtype=bool) if vals.dtype == object else np.ones(len(vals), bool)
+                out_cols.append(p.get("name", "count"))
+                arrays.append(np.asarray([int(present[v].sum()) for v in groups.values()], dtype=np.int64))
+            else:
+                raise UnsupportedQuery("GROUP BY supports grouped columns and COUNT only; other aggregates are finished by the SQL engine")
+        return self._order_limit(q, Result(out_cols, arrays))
 
     def _join_nearest(self, q, f: _Frame, j):
         """src/giql/expanders/nearest.py:336-397 — one engine call per NEAREST, joined back on the query row"""
@@ -948,8 +1052,10 @@ class Session:
             out.sort(key=lambda r: (r[0], r[width - 2]))
             cols = ["chrom"] + (["strand"] if m["stranded"] else []) + ["start", "end"] + (["count"] if "count_star" in kinds else [])
             return self._order_limit(q, Result(cols, [_column([r[i] for r in out]) for i in range(len(cols))]))
-        if "count_star" in kinds:
-            raise UnsupportedQuery("COUNT(*) outside MERGE is finished by the SQL engine")
+        if q.get("group"):
+            return self._group_count(q, f)
+        if kinds & {"count_star", "count_col"}:
+            raise UnsupportedQuery("COUNT without GROUP BY (outside MERGE) is finished by the SQL engine")
         cols: list[str] = []
         arrays: list[np.ndarray] = []
         for p in proj:

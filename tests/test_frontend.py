@@ -78,6 +78,12 @@ STATEMENTS = [
     "SELECT name, CLUSTER(interval, stranded := true, predicate := name >= PREV(name)) AS cid FROM peaks",
     "SELECT MERGE(interval, predicate := strand = PREV(strand)), COUNT(*) FROM peaks",
     "SELECT MERGE(interval, 20, stranded := true, predicate := name <> PREV(name)) FROM peaks",
+    # count_overlaps (intersects_duckdb.py:432-548, 806-854) and generic GROUP BY ... COUNT over the joined rows
+    "SELECT a.chrom, a.start, a.\"end\", COUNT(b.start) AS n FROM peaks a LEFT JOIN genes b ON a.interval INTERSECTS b.interval GROUP BY a.chrom, a.start, a.\"end\"",
+    "SELECT a.name, COUNT(*) AS n FROM peaks a JOIN genes b ON a.interval INTERSECTS b.interval GROUP BY a.name",
+    "SELECT a.name, COUNT(*) AS n FROM peaks a LEFT JOIN genes b ON a.interval INTERSECTS b.interval GROUP BY a.name",
+    "SELECT a.name, COUNT(b.name) AS n FROM peaks a LEFT JOIN genes b ON a.interval INTERSECTS b.interval AND a.strand = b.strand GROUP BY a.name",
+    "SELECT b.strand, COUNT(*) FROM peaks a JOIN genes b ON a.interval INTERSECTS b.interval GROUP BY b.strand",
 ]
 
 
@@ -101,7 +107,9 @@ def test_parse_shapes():
 
 
 @pytest.mark.parametrize("q", [
-    "SELECT a.name, COUNT(*) FROM peaks a JOIN genes b ON a.interval INTERSECTS b.interval GROUP BY a.name",
+    "SELECT a.name, SUM(b.start) FROM peaks a JOIN genes b ON a.interval INTERSECTS b.interval GROUP BY a.name",
+    "SELECT a.name, COUNT(*) FROM peaks a JOIN genes b ON a.interval INTERSECTS b.interval GROUP BY a.name HAVING COUNT(*) > 1",
+    "SELECT a.name, a.start, COUNT(*) FROM peaks a JOIN genes b ON a.interval INTERSECTS b.interval GROUP BY a.name",
     "SELECT name FROM peaks WHERE start + 1 > 100",
     "SELECT upper(name) FROM peaks",
     "SELECT a.name FROM peaks a JOIN genes b ON a.name = b.name",
@@ -138,6 +146,36 @@ def test_predicate_clustering_against_brute_force():
         s.execute("SELECT CLUSTER(interval, predicate := strand = PREV(PREV(strand))) FROM peaks")
     with pytest.raises(ValueError, match="exactly one column"):
         s.execute("SELECT CLUSTER(interval, predicate := strand = PREV(strand, name)) FROM peaks")
+
+
+def test_count_overlaps_and_group_by_against_brute_force():
+    from collections import Counter
+
+    s = sessions(OracleBackend())
+    P, G = s.tables["peaks"].data, s.tables["genes"].data
+    ov = [(i, j) for i in range(90) for j in range(60) if overlap(P, i, G, j)]
+    per_left = Counter(i for i, _ in ov)
+    want = {}
+    for i in range(90):      # equal left keys merge their counts; LEFT JOIN keeps the zero rows
+        k = (P["chrom"][i], P["start"][i], P["end"][i])
+        want[k] = want.get(k, 0) + per_left.get(i, 0)
+    got = s.execute(STATEMENTS[42])
+    assert got.columns == ["chrom", "start", "end", "n"] and sorted(got.rows) == sorted(k + (v,) for k, v in want.items())
+    assert sorted(s.execute(STATEMENTS[43]).rows) == sorted((P["name"][i], v) for i, v in per_left.items())
+    assert sorted(s.execute(STATEMENTS[44]).rows) == sorted((P["name"][i], max(per_left.get(i, 0), 1)) for i in range(90))
+    same = Counter(i for i, j in ov if P["strand"][i] == G["strand"][j])
+    assert sorted(s.execute(STATEMENTS[45]).rows) == sorted((P["name"][i], same.get(i, 0)) for i in range(90))
+    assert dict(s.execute(STATEMENTS[46]).rows) == dict(Counter(G["strand"][j] for _, j in ov))
+
+    class NoPairs(OracleBackend):     # the count_overlaps shape must not materialise the pair list
+        def pairs(self, *a, **k):
+            raise AssertionError("pair list requested")
+
+    fast = sessions(NoPairs())
+    assert sorted(fast.execute(STATEMENTS[42]).rows) == sorted(got.rows)
+    assert sorted(fast.execute(STATEMENTS[43]).rows) == sorted(s.execute(STATEMENTS[43]).rows)
+    with pytest.raises(AssertionError):
+        fast.execute(STATEMENTS[45])
 
 
 def test_errors_mirror_reference_messages():
