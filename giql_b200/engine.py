@@ -974,7 +974,10 @@ class Engine:
         """Order-preserving int32 codes of the two operand columns of ``predicate := cur <op> PREV(prev)``, ranked together
         so that codes compare like the values; None / NaN-free NULLs become GIQLB_KEY_NULL."""
         cur, prev = list(cur_values), list(prev_values)
-        values = sorted({v for v in cur if v is not None} | {v for v in prev if v is not None})
+        try:
+            values = sorted({v for v in cur if v is not None} | {v for v in prev if v is not None})
+        except TypeError as exc:
+            raise ValueError(f"predicate operands are not comparable: {exc}") from None
         rank = {v: i for i, v in enumerate(values)}
         null = _cabi.KEY_NULL
         enc = lambda col: np.fromiter((null if v is None else rank[v] for v in col), dtype=np.int32, count=len(col))

@@ -162,6 +162,22 @@ def _tokenize(text: str):
     return out
 
 
+def _int_arg(v, what: str, default=None):
+    if v is None:
+        return default
+    if isinstance(v, bool) or not isinstance(v, int):
+        raise ValueError(f"{what} must be an integer literal")
+    return v
+
+
+def _bool_arg(v, what: str) -> bool:
+    if v is None:
+        return False
+    if not isinstance(v, bool):
+        raise ValueError(f"{what} must be true or false")
+    return v
+
+
 class _Parser:
     def __init__(self, tokens):
         self.t, self.i = tokens, 0
@@ -343,8 +359,11 @@ class _Parser:
         if not (isinstance(ref, tuple) and ref[0] == "col" and ref[2] == "interval"):
             raise UnsupportedQuery("NEAREST needs reference := <alias>.interval")
         alias = self.alias()
-        return {"target": target, "ref_alias": ref[1], "alias": alias, "k": int(args.get("k", 1)), "max_distance": args.get("max_distance"),
-                "stranded": bool(args.get("stranded", False)), "signed": bool(args.get("signed", False))}
+        k = _int_arg(args.get("k"), "NEAREST k", 1)
+        if k < 1:
+            raise ValueError("NEAREST k must be >= 1")
+        return {"target": target, "ref_alias": ref[1], "alias": alias, "k": k, "max_distance": _int_arg(args.get("max_distance"), "NEAREST max_distance"),
+                "stranded": _bool_arg(args.get("stranded"), "stranded"), "signed": _bool_arg(args.get("signed"), "signed")}
 
     def column_ref(self):
         a = self.take("id")
@@ -363,7 +382,7 @@ class _Parser:
         self.take("op", ")")
         if a[1] != "interval" or b[1] != "interval":
             raise UnsupportedQuery("DISTANCE takes two <alias>.interval operands")
-        return {"a": a[0], "b": b[0], "stranded": bool(args.get("stranded", False)), "signed": bool(args.get("signed", False))}
+        return {"a": a[0], "b": b[0], "stranded": _bool_arg(args.get("stranded"), "stranded"), "signed": _bool_arg(args.get("signed"), "signed")}
 
     def projection(self):
         if self.accept("op", "*"):
@@ -380,8 +399,12 @@ class _Parser:
                 args = self.named_args()
                 self.take("op", ")")
                 pos = args.get("_positional", [])
-                item = {"kind": fn.lower(), "distance": int(pos[0]) if pos else int(args.get("distance", 0) or 0),
-                        "stranded": bool(args.get("stranded", False)), "predicate": args.get("predicate")}
+                if len(pos) > 1:
+                    raise ValueError(f"{fn} takes at most one positional distance")
+                item = {"kind": fn.lower(), "distance": _int_arg(pos[0] if pos else args.get("distance"), f"{fn} distance", 0),
+                        "stranded": _bool_arg(args.get("stranded"), "stranded"), "predicate": args.get("predicate")}
+                if item["predicate"] is not None and not isinstance(item["predicate"], dict):
+                    raise ValueError("predicate := must be a comparison")
             elif fn == "COUNT":
                 self.take("op", "(")
                 if self.accept("op", "*"):
@@ -617,7 +640,10 @@ def _residual(left: _Rel, right: _Rel, la, ra, cond) -> dict:
         return out
     lv = np.array([v is not None for v in lc], dtype=bool) if lc.dtype == object else np.ones(len(lc), bool)
     rv = np.array([v is not None for v in rc], dtype=bool) if rc.dtype == object else np.ones(len(rc), bool)
-    values = sorted(set(lc[lv].tolist()) | set(rc[rv].tolist()))         # mixed incomparable types raise, as SQL would
+    try:
+        values = sorted(set(lc[lv].tolist()) | set(rc[rv].tolist()))
+    except TypeError as exc:                                             # mixed incomparable types: a binder error in SQL
+        raise ValueError(f"cannot compare {c1!r} with {c2!r}: {exc}") from None
     rank = {v: i for i, v in enumerate(values)}
     out["l"] = np.fromiter((rank[v] if ok else 0 for v, ok in zip(lc.tolist(), lv)), dtype=np.int32, count=len(lc))
     out["r"] = np.fromiter((rank[v] if ok else 0 for v, ok in zip(rc.tolist(), rv)), dtype=np.int32, count=len(rc))
@@ -1013,7 +1039,10 @@ class Session:
             if a.dtype == object or b.dtype == object:
                 fn = {"<": lambda x, y: x < y, "<=": lambda x, y: x <= y, ">": lambda x, y: x > y, ">=": lambda x, y: x >= y,
                       "=": lambda x, y: x == y, "!=": lambda x, y: x != y}[op]
-                keep = np.fromiter((x is not None and y is not None and fn(x, y) for x, y in zip(a.tolist(), b.tolist())), dtype=bool, count=len(a))
+                try:
+                    keep = np.fromiter((x is not None and y is not None and fn(x, y) for x, y in zip(a.tolist(), b.tolist())), dtype=bool, count=len(a))
+                except TypeError as exc:
+                    raise ValueError(f"cannot compare the operands of {op!r}: {exc}") from None
             else:
                 keep = _CMP[op](a, b)
             f.take(keep)

@@ -304,3 +304,29 @@ def test_register_bed_runs_queries_from_text(engine):
     got = dev.execute("SELECT a.name, a.score, b.strand FROM peaks a JOIN genes b ON a.interval WITHIN b.interval")
     want = ref.execute("SELECT a.name, b.strand FROM peaks a JOIN genes b ON a.interval WITHIN b.interval")
     assert sorted((r[0], 0, r[1]) for r in want.rows) == sorted(got.rows)
+
+
+def test_mutated_statements_fail_cleanly():
+    """token-level mutations of every supported statement either run or are declined with UnsupportedQuery / ValueError —
+    never an internal error (the reference wraps pass failures into ValueError, src/giql/transpile.py:245-266)"""
+    s = sessions(OracleBackend())
+    rng = random.Random(7)
+    pool = ["SELECT", "FROM", "WHERE", "JOIN", "ON", "AND", "a", "b", "peaks", "genes", "interval", "INTERSECTS", "(", ")", ",", "*", ".",
+            "'chr1:1-5'", "5", "=", "<", "GROUP", "BY", "name", "start", "COUNT", "CLUSTER", "MERGE", "NEAREST", "LATERAL", "CROSS", "LEFT",
+            "AS", "ORDER", "LIMIT", ":=", "PREV", "predicate", "k", "reference", "DISJOIN", "DISTINCT", "ANY", "ALL", "IS", "NULL", "NOT", "DISTANCE"]
+    for q in STATEMENTS:
+        words = q.replace("(", " ( ").replace(")", " ) ").replace(",", " , ").split()
+        for _ in range(25):
+            w = list(words)
+            i = rng.randrange(len(w))
+            kind = rng.randrange(3)
+            if kind == 0:
+                del w[i]
+            elif kind == 1:
+                w.insert(i, rng.choice(pool))
+            else:
+                w[i] = rng.choice(pool)
+            try:
+                s.execute(" ".join(w))
+            except (UnsupportedQuery, ValueError):
+                pass
