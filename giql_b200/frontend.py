@@ -502,6 +502,19 @@ class Result:
     def to_pydict(self) -> dict:
         return {c: a.tolist() for c, a in zip(self.columns, self.arrays)}
 
+    def to_arrow(self):
+        """pyarrow Table (duplicate column names, legal in SQL, get a numeric suffix)"""
+        import pyarrow as pa
+
+        names, seen = [], {}
+        for c in self.columns:
+            seen[c] = seen.get(c, 0) + 1
+            names.append(c if seen[c] == 1 else f"{c}_{seen[c] - 1}")
+        return pa.table({n: pa.array(a.tolist()) for n, a in zip(names, self.arrays)})
+
+    def to_pandas(self):
+        return self.to_arrow().to_pandas()
+
     def __iter__(self):
         return iter(self.rows)
 

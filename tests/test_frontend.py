@@ -330,3 +330,25 @@ def test_mutated_statements_fail_cleanly():
                 s.execute(" ".join(w))
             except (UnsupportedQuery, ValueError):
                 pass
+
+
+def test_result_egress_and_dataframe_ingest():
+    import pyarrow as pa
+
+    s = sessions(OracleBackend())
+    res = s.execute("SELECT * FROM peaks a JOIN genes b ON a.interval INTERSECTS b.interval")
+    tab = res.to_arrow()
+    assert tab.num_rows == len(res) and tab.column_names[:5] == ["chrom", "start", "end", "name", "strand"] and "chrom_1" in tab.column_names
+    assert res.to_pandas().shape == (len(res), 10)
+    # Arrow and pandas tables register like mappings, Table(...) column mappings are honoured (src/giql/table.py:16-93)
+    P = make(11, 90)
+    arrow = pa.table({"seqname": P["chrom"], "lo": P["start"], "hi": P["end"], "label": P["name"]})
+    t = Session(OracleBackend())
+    t.register("p", arrow, Table("p", chrom_col="seqname", start_col="lo", end_col="hi", strand_col=None))
+    t.register("g", arrow.to_pandas(), Table("g", chrom_col="seqname", start_col="lo", end_col="hi", strand_col=None))
+    got = t.execute("SELECT a.label, b.label FROM p a JOIN g b ON a.interval INTERSECTS b.interval").rows
+    want = [(P["name"][i], P["name"][j]) for i in range(90) for j in range(90) if overlap(P, i, P, j)]
+    assert sorted(got) == sorted(want)
+    closed = Session(OracleBackend())
+    closed.register("p", {"chrom": ["c", "c"], "start": [1, 10], "end": [9, 20]}, Table("p", coordinate_system="1based", interval_type="closed"))
+    assert closed.execute("SELECT start FROM p WHERE interval INTERSECTS 'c:9-10'").rows == [(10,)]   # 1-based closed [10,20] = 0-based [9,20)
