@@ -378,7 +378,6 @@ def run_b200(args):
         return
 
     # ---- roofline of the dominant kernel group (per-launch, live CUDA events on the engine's stream) ----
-    lay_bits = 32
     sort_passes = 4
     phases = {}
     for name, (ms, n_launch) in prof.items():

@@ -850,7 +850,7 @@ class Session:
                         and {on["left"][0], on["right"][0]} == {la, ra}):
                     raise UnsupportedQuery("without a spatial predicate only the `a.chrom = b.chrom` equi-join is handled")
                 lc, rc = f.genomic(la)["chrom"], right.genomic()["chrom"]
-                names, codes = np.unique(np.concatenate([lc.astype(str), rc.astype(str)]), return_inverse=True)
+                _, codes = np.unique(np.concatenate([lc.astype(str), rc.astype(str)]), return_inverse=True)
                 cl, cr = codes[: len(lc)], codes[len(lc):]
                 by = np.argsort(cr, kind="stable")
                 lo, hi = np.searchsorted(cr[by], cl, "left"), np.searchsorted(cr[by], cl, "right")
