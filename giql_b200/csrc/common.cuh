@@ -28,6 +28,8 @@ struct giqlb_ctx {
     void* h_stage = nullptr;        // pinned staging buffer for small host -> device tables (GIQLB_STAGE_BYTES)
     int* d_err = nullptr;           // device int[4]: sticky kernel-side error flags ([0] look-back spin limit)
     giqlb_stats_t stats = {};
+    bool fused_pipeline = true;        // one-call pipelines: fused encode + observe, keys from raw columns (GIQLB_FUSED_PIPELINE=0 turns it off)
+    bool join_smem_opted_in = false;   // cudaFuncSetAttribute is per device: remembered per context, not per process
     int32_t launches_this_call = 0;
     // Scratch cache.  Every allocation of a context is used on ITS stream only, so a freed block can be handed
     // out again immediately (stream order protects it) without a driver call: dev_free parks the block here,
@@ -394,9 +396,15 @@ struct giqlb_prekeyed {
     int32_t* rows = nullptr;              // [n] their row ids
     unsigned long long* counters = nullptr;   // [4 + 512] as giqlb_index::d_counters
 };
+// remap (nullable): `code` still holds the dictionary encoder's parked table slots; the key-generation pass translates
+// them through slot2code and writes the codes back (it does nothing when *ok_flag == 0: the device-side ranking declined)
+struct giqlb_code_remap {
+    const int32_t* slot2code;
+    const int* ok_flag;
+};
 int giqlb_index_build_impl(giqlb_ctx* ctx, const giqlb_layout* lay, const int32_t* code, const int32_t* start,
                            const int32_t* end, const uint8_t* strand, const int32_t* rows, int64_t n, int32_t start_adj,
-                           int32_t end_adj, int flags, giqlb_prekeyed* pre, giqlb_index** out);
+                           int32_t end_adj, int flags, giqlb_prekeyed* pre, giqlb_index** out, const giqlb_code_remap* remap = nullptr);
 struct giqlb_dict_pending;
 #define GIQLB_ASYNC_DICT_MAX_CODES 1024   // upper bound of the code space while the dictionary is still on the device
 // defer_remap: leave the parked table slots in codes_l / codes_r; the caller translates them with
@@ -404,6 +412,8 @@ struct giqlb_dict_pending;
 int giqlb_dict_encode_async(giqlb_ctx* ctx, const int32_t* offs_l, const uint8_t* bytes_l, int64_t n_l, const int32_t* offs_r,
                             const uint8_t* bytes_r, int64_t n_r, int32_t* codes_l, int32_t* codes_r, giqlb_dict_pending** out,
                             bool defer_remap = false);
+int giqlb_dict_encode_observe_async(giqlb_ctx* ctx, const giqlb_table_t* L, const giqlb_table_t* R, giqlb_layout* lay,
+                                    giqlb_dict_pending** out);
 void giqlb_dict_pending_tables(const giqlb_dict_pending* p, const int32_t** slot2code, const int** ok_flag);
 int giqlb_layout_observe_remap(giqlb_ctx* ctx, giqlb_layout* lay, int32_t* code, const int32_t* start, const int32_t* end, int64_t n,
                                int32_t start_adj, int32_t end_adj, const int32_t* slot2code, const int* ok_flag);

@@ -154,16 +154,19 @@ layout_finalize_kernel(const long long* __restrict__ lohi, int32_t n_codes, long
 }
 
 // linearised start key + linearised end (unsorted), degenerate-row counters
-template <bool HIST>
+// REMAP: `code` still holds the dictionary encoder's parked table slots (fused encode + observe schedule); they are
+// translated through slot2code here and written back, so no separate pass rewrites the column.
+template <bool HIST, bool REMAP = false>
 __global__ void __launch_bounds__(256)
-index_keygen_kernel(const int32_t* __restrict__ code, const int32_t* __restrict__ start,
+index_keygen_kernel(const int32_t* code, const int32_t* __restrict__ start,
                     const int32_t* __restrict__ end, const int32_t* __restrict__ rows /* nullable: row selection */,
                     int64_t n, int32_t n_codes, int32_t sadj, int32_t eadj,
                     const uint32_t* __restrict__ base, const int32_t* __restrict__ lo32,
                     const int32_t* __restrict__ hi32, uint32_t* __restrict__ gs, uint32_t* __restrict__ ge,
                     unsigned long long* __restrict__ counters /* [0] end<=start [1] end<start [2] outside layout */,
                     uint32_t* __restrict__ ghist /* nullable: [4][256] digit counts of the start keys, for the sort */,
-                    int* __restrict__ err) {
+                    int* __restrict__ err, const int32_t* __restrict__ slot2code = nullptr, const int* __restrict__ ok_flag = nullptr) {
+    if (REMAP && !*ok_flag) return;
     __shared__ uint32_t s_hist[HIST ? 4 : 1][256];
     if (HIST) {
         for (int i = threadIdx.x; i < 4 * 256; i += blockDim.x) (&s_hist[0][0])[i] = 0;
@@ -173,6 +176,10 @@ index_keygen_kernel(const int32_t* __restrict__ code, const int32_t* __restrict_
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
         const int64_t r = rows ? (int64_t)rows[i] : i;
         int32_t c = code[r];
+        if (REMAP) {
+            c = __ldg(slot2code + c);
+            const_cast<int32_t*>(code)[r] = c;
+        }
         long long s = (long long)start[r] + sadj, e = (long long)end[r] + eadj;
         uint32_t ks = 0xffffffffu, ke = 0xffffffffu;
         if (c < 0 || c >= n_codes) {
@@ -491,7 +498,7 @@ extern "C" int giqlb_index_build_rows(giqlb_ctx* ctx, const giqlb_layout* lay, c
 // ownership of its buffers.
 int giqlb_index_build_impl(giqlb_ctx* ctx, const giqlb_layout* lay, const int32_t* code, const int32_t* start,
                            const int32_t* end, const uint8_t* strand, const int32_t* rows, int64_t n, int32_t start_adj,
-                           int32_t end_adj, int flags, giqlb_prekeyed* pre, giqlb_index** out) {
+                           int32_t end_adj, int flags, giqlb_prekeyed* pre, giqlb_index** out, const giqlb_code_remap* remap) {
     if (!ctx || !lay || !out || n < 0 || (n > 0 && (!code || !start || !end)))
         return giqlb_fail(ctx, GIQLB_ERR_INVALID, "index_build: bad argument");
     if (!lay->finalized) return giqlb_fail(ctx, GIQLB_ERR_INVALID, "index_build: layout not finalized");
@@ -547,7 +554,11 @@ int giqlb_index_build_impl(giqlb_ctx* ctx, const giqlb_layout* lay, const int32_
         int result_in_b = 0;
         if (!pre) {
         PhaseSpan ps(ctx, GIQLB_PH_KEYGEN);
-        if (key_hist)
+        if (remap && !rows)
+            index_keygen_kernel<false, true><<<grid_for(ctx, n, 256 * 4, 8), 256, 0, ctx->stream>>>(
+                code, start, end, nullptr, n, lay->n_codes, start_adj, end_adj, lay->d_base, lay->d_lo32, lay->d_hi32, ka, ge_u, counters, nullptr, ctx->d_err,
+                remap->slot2code, remap->ok_flag);
+        else if (key_hist)
             index_keygen_kernel<true><<<grid_for(ctx, n, 256 * 4, 8), 256, 0, ctx->stream>>>(
                 code, start, end, rows, n, lay->n_codes, start_adj, end_adj, lay->d_base, lay->d_lo32, lay->d_hi32, ka, ge_u, counters, key_hist, ctx->d_err);
         else

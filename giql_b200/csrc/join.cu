@@ -47,10 +47,27 @@ namespace {
 constexpr int JB = GIQLB_JOIN_THREADS;   // threads per CTA
 constexpr int JT = JB * 4;               // merged rows per tile (fast path) / left rows per tile (general path)
 constexpr int J_IPT = JT / JB;
-constexpr int J_EXT = 512;          // rows staged beyond the tile's own part of each table
+#ifndef GIQLB_JOIN_EXT
+#define GIQLB_JOIN_EXT 512
+#endif
+constexpr int J_EXT = GIQLB_JOIN_EXT;   // rows staged beyond the tile's own part of each table
 constexpr int JW = JT + J_EXT;      // staged window capacity per table
 constexpr int J_PART = 8192;        // output pairs per emit work unit
 constexpr int J_OPT = 8;            // consecutive outputs per thread in the emit loop
+#ifndef GIQLB_JOIN_RUN_WINDOW
+#define GIQLB_JOIN_RUN_WINDOW 32    // rows of the other window covered by the fixed-trip run-end search (longer runs: binary search)
+#endif
+constexpr int J_RUNW = GIQLB_JOIN_RUN_WINDOW;
+#ifndef GIQLB_JOIN_LOOKBACK_WORDS
+#define GIQLB_JOIN_LOOKBACK_WORDS 1 // predecessor tiles fetched per lane and look-back step (32 lanes: 128 tiles per L2 round trip)
+#endif
+constexpr int J_LB = GIQLB_JOIN_LOOKBACK_WORDS;
+#ifndef GIQLB_JOIN_TICKET
+#define GIQLB_JOIN_TICKET 0           // 1: tiles take tickets from an atomic counter (a tile then only waits on tiles already scheduled)
+#endif
+#ifndef GIQLB_JOIN_BACKOFF_NS
+#define GIQLB_JOIN_BACKOFF_NS 40     // pause between polls of predecessor tiles that have not published yet
+#endif
 
 struct JoinSide {
     const uint32_t* gs;
@@ -102,19 +119,42 @@ __device__ __forceinline__ int s_upper_bound_u64(const unsigned long long* a, in
 }
 
 // ---- merge-path partition: part[t] = number of L rows among the first t*JT rows of the merge -----------
-__global__ void __launch_bounds__(256)
-join_partition_kernel(const uint32_t* __restrict__ lgs, int64_t nl, const uint32_t* __restrict__ rgs, int64_t nr,
-                      int64_t n_tiles, int32_t* __restrict__ part) {
-    const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (t > n_tiles) return;
-    int64_t d = t * JT;
-    if (d > nl + nr) d = nl + nr;
+// recs (nullable) additionally receives the finished geometry of every tile — first rows, row counts and staged
+// window lengths, eight int32 — so that the fused kernel starts a tile with ONE 32-byte load instead of two
+// dependent loads and 64-bit min arithmetic on its critical path.
+struct __align__(16) TileRec {
+    int32_t x0, y0, nl, nr, wl, wr, pad0, pad1;
+};
+__device__ __forceinline__ int64_t merge_diagonal(const uint32_t* __restrict__ lgs, int64_t nl, const uint32_t* __restrict__ rgs, int64_t nr, int64_t d) {
     int64_t lo = d > nr ? d - nr : 0, hi = d < nl ? d : nl;
     while (lo < hi) {                      // L[mid] precedes R[d-1-mid] in the merge  <=>  more than mid L rows are taken
         int64_t mid = lo + ((hi - lo) >> 1);
         if (__ldg(lgs + mid) <= __ldg(rgs + (d - 1 - mid))) lo = mid + 1; else hi = mid;
     }
-    part[t] = (int32_t)lo;
+    return lo;
+}
+__global__ void __launch_bounds__(256)
+join_partition_kernel(const uint32_t* __restrict__ lgs, int64_t nl, const uint32_t* __restrict__ rgs, int64_t nr,
+                      int64_t n_tiles, int32_t* __restrict__ part, TileRec* __restrict__ recs) {
+    const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t > n_tiles) return;
+    const int64_t d0 = min(t * JT, nl + nr);
+    const int64_t x0 = merge_diagonal(lgs, nl, rgs, nr, d0);
+    part[t] = (int32_t)x0;
+    if (recs && t < n_tiles) {
+        const int64_t d1 = min((t + 1) * (int64_t)JT, nl + nr);
+        const int64_t x1 = merge_diagonal(lgs, nl, rgs, nr, d1);
+        const int64_t y0 = d0 - x0, y1 = d1 - x1;
+        TileRec r;
+        r.x0 = (int32_t)x0;
+        r.y0 = (int32_t)y0;
+        r.nl = (int32_t)(x1 - x0);
+        r.nr = (int32_t)(y1 - y0);
+        r.wl = (int32_t)min((int64_t)r.nl + J_EXT, nl - x0);
+        r.wr = (int32_t)min((int64_t)r.nr + J_EXT, nr - y0);
+        r.pad0 = r.pad1 = 0;
+        recs[t] = r;
+    }
 }
 
 struct TileGeom {
@@ -373,13 +413,16 @@ join_emit_kernel(JoinSide L, JoinSide R, const int32_t* __restrict__ part, int64
 // through HBM, and the capacity check is per tile (a tile that would overrun the buffer writes nothing; the
 // grand total tells the host how much room a retry needs).  Tiles whose output exceeds J_BIG pairs only
 // publish their offset and are emitted afterwards by a second kernel that shares each of them among many CTAs.
-constexpr int J_BIG = 8 * JT;          // tiles with more pairs are shared among CTAs by join_emit_big_kernel
+#ifndef GIQLB_JOIN_BIG
+#define GIQLB_JOIN_BIG (8 * JT)
+#endif
+constexpr int J_BIG = GIQLB_JOIN_BIG;  // tiles with more pairs are shared among CTAs by join_emit_big_kernel
 constexpr unsigned long long JF_FLAG_AGG = 1ull << 62;
 constexpr unsigned long long JF_FLAG_INCL = 2ull << 62;
 constexpr unsigned long long JF_VALUE_MASK = (1ull << 62) - 1;
 constexpr uint32_t JF_SPIN_LIMIT = 1u << 26;
 
-constexpr int J_STAGE = ((2 * (JW + 8) + 2 * (JT + 8)) / 2) & ~3;   // output pairs staged per window (aliases gs + ge)
+constexpr int J_STAGE = ((2 * (JW + 8) + 2 * (JT + 8)) / 2) & ~7;   // output pairs staged per window (aliases gs + ge)
 
 struct __align__(16) TileSmem {
     uint32_t gs[2][JW + 8];                  // staged start windows: [0] L, [1] R (16-byte aligned source => up to 3 lead-in rows)
@@ -393,11 +436,20 @@ struct __align__(16) TileSmem {
 };
 
 struct TileSlots {                           // fused kernel (tiles of <= J_BIG pairs): slot -> item lookup over the NON-EMPTY items
-    uint16_t off[JT + 2];                    // local exclusive output offsets of the non-empty items (merge order), then the total
-    uint16_t code[JT];                       // run start | class
-    uint16_t own[JT];                        // the item's index in its own table's window
+    uint2 ent[JT + 2];                       // merge order: .x = local exclusive output offset (bits 0..13) | class (bit 14) |
+                                             // (index of the run's first row in the row-id windows - offset) as int16 (bits 16..31),
+                                             // .y = the item's OWN row id (looked up once per item, not once per pair); then a sentinel
     uint16_t first_item[J_BIG / J_OPT + 2];  // non-empty item that owns the first slot of every J_OPT-slot chunk
 };
+constexpr uint32_t JE_OFF_MASK = 0x3FFFu, JE_CLASS_B = 0x4000u;
+static_assert(J_BIG < (int)JE_OFF_MASK, "a tile's local offsets must fit 14 bits");
+// Output staging window: one (left, right) row-id pair per slot, 8 bytes.  A thread of the expansion owns J_OPT = 8 consecutive
+// slots, so at step q the lanes of a half-warp (which share one 64-bit shared-memory transaction) would all hit the same two
+// banks.  XOR-ing the slot's low three bits with its 16-block number spreads every step over all banks, and keeps the flush's
+// consecutive-slot reads conflict-free (ncu, round 1: 48.8 M bank-conflict wavefronts on 29.9 M shared-memory instructions;
+// the shared-memory pipe was the kernel's limiter at 85 %).  For a chunk-aligned slot s0 the swizzled index of s0 + q is
+// stage_swz(s0) ^ q: one instruction per slot.
+__device__ __forceinline__ uint32_t stage_swz(uint32_t s) { return s ^ ((s >> 4) & 7u); }
 struct TileOffsets {                         // big-tile kernel: per-item offsets for the slot -> item search
     unsigned long long off[JT + 1];          // local exclusive output offsets of the tile's items (merge order)
     uint32_t code[JT];                       // run start | class of every item
@@ -440,6 +492,34 @@ __device__ __forceinline__ void tile_stage(TileSmem& sm, const TileGeom& g, cons
     window_copy(sm.rid[1], R.rid, g.y0, g.wr, &sm.bar[1]);
 }
 
+// The same by the first six lanes of warp 0, one bulk copy each (the whole warp must call): lane 0 arms both barriers
+// first, so the six copies are issued side by side instead of one after the other behind ~500 scalar instructions.
+__device__ __forceinline__ void tile_stage_warp(TileSmem& sm, const TileGeom& g, const JoinSide& L, const JoinSide& R) {
+    const uint32_t lane = lane_id();
+    if (lane == 0) {
+        uint32_t b0 = 0, b1 = 0;
+        if (g.wl > 0) b0 += window_bytes(g.x0, g.wl), b1 += window_bytes(g.x0, g.wl);
+        if (g.wr > 0) b0 += window_bytes(g.y0, g.wr), b1 += window_bytes(g.y0, g.wr);
+        if (g.nl > 0) b0 += window_bytes(g.x0, g.nl);
+        if (g.nr > 0) b0 += window_bytes(g.y0, g.nr);
+        cuda::ptx::mbarrier_arrive_expect_tx(cuda::ptx::sem_release, cuda::ptx::scope_cta, cuda::ptx::space_shared,
+                                             reinterpret_cast<uint64_t*>(&sm.bar[0]), b0);
+        cuda::ptx::mbarrier_arrive_expect_tx(cuda::ptx::sem_release, cuda::ptx::scope_cta, cuda::ptx::space_shared,
+                                             reinterpret_cast<uint64_t*>(&sm.bar[1]), b1);
+    }
+    __syncwarp();
+    if (lane < 6) {
+        const bool right = lane & 1;                                    // lanes 0, 2, 4: L windows; 1, 3, 5: R windows
+        const int what = (int)lane >> 1;                                // 0 starts, 1 ends (own rows only), 2 row ids
+        const int64_t first = right ? g.y0 : g.x0;
+        const int count = what == 1 ? (right ? g.nr : g.nl) : (right ? g.wr : g.wl);
+        const JoinSide& S = right ? R : L;
+        const void* src = what == 0 ? (const void*)S.gs : what == 1 ? (const void*)S.ge : (const void*)S.rid;
+        void* dst = what == 0 ? (void*)sm.gs[right] : what == 1 ? (void*)sm.ge[right] : (void*)sm.rid[right];
+        window_copy(dst, src, first, count, &sm.bar[what == 2 ? 1 : 0]);
+    }
+}
+
 // The thread's J_IPT consecutive rows of the tile's merge sequence: run start/class codes and exact run lengths.
 // Branch-free in the class: the row's own table and the other table are selected by index.
 __device__ __forceinline__ void tile_runs(const TileSmem& sm, const TileGeom& g, const JoinSide& L, const JoinSide& R,
@@ -465,22 +545,31 @@ __device__ __forceinline__ void tile_runs(const TileSmem& sm, const TileGeom& g,
     bool is_l[J_IPT];
     int start[J_IPT], h[J_IPT], lim[J_IPT];
     uint32_t xge[J_IPT];
+    // the heads of both windows ride in registers: one shared-memory load per merge step (the head that advanced), and one
+    // for the row's own end.  Reads at the window end stay inside the padded arrays and are guarded by the index tests.
+    uint32_t cl = gsl[i], cr = gsr[j];
 #pragma unroll
     for (int k = 0; k < J_IPT; k++) {
         const bool live = m0 + k < n_items;
-        const bool take_l = live && (j >= g.nr || (i < g.nl && gsl[i] <= gsr[j]));
+        const bool take_l = live && (j >= g.nr || (i < g.nl && cl <= cr));
         is_l[k] = take_l;
-        xge[k] = !live ? 0u : (take_l ? gel[i] : ger[j]);     // the row's own end (0: no row of the other table starts below it)
+        const uint32_t* ep = take_l ? gel + i : ger + j;
+        xge[k] = live ? *ep : 0u;                             // the row's own end (0: no row of the other table starts below it)
         start[k] = take_l ? j : i;
-        lim[k] = !live ? start[k] : min(start[k] + 32, take_l ? g.wr : g.wl);
+        lim[k] = !live ? start[k] : min(start[k] + J_RUNW, take_l ? g.wr : g.wl);
         h[k] = start[k];
         i += (live && take_l) ? 1 : 0;
         j += (live && !take_l) ? 1 : 0;
+        if (k + 1 < J_IPT) {
+            const uint32_t nv = *(take_l ? gsl + i : gsr + j);
+            cl = take_l ? nv : cl;
+            cr = take_l ? cr : nv;
+        }
     }
     // run end = first row of the other window whose start is >= the row's end.  Almost every run is a few rows long:
     // a fixed-trip (divergence-free) binary lifting over the next 32 rows
 #pragma unroll
-    for (int step = 16; step > 0; step >>= 1) {
+    for (int step = J_RUNW / 2; step > 0; step >>= 1) {
 #pragma unroll
         for (int k = 0; k < J_IPT; k++) {
             const uint32_t* ys = is_l[k] ? gsr : gsl;         // the other table's window
@@ -587,25 +676,31 @@ __device__ __forceinline__ void tile_emit(const TileSmem& sm, const TileOffsets&
 }
 
 // Item table of the tile over its NON-EMPTY items (compacted with the item count that rides in the high bits of the
-// block scan): offsets, codes, own indexes, and for every chunk of J_OPT output slots the entry owning its first slot
-// (written by that item itself, so the expansion below needs no search and its walk never meets an empty item).
-__device__ __forceinline__ void tile_slot_table(TileSlots& ts, const uint32_t (&code)[J_IPT], const uint32_t (&cnt)[J_IPT], uint32_t ex,
-                                                uint32_t ex_items, uint32_t tot, uint32_t tot_items) {
+// block scan): one packed entry per item — offset, class, where its run starts in the row-id windows, and the item's own
+// row id, read here once per item so that the expansion loads one row id per pair instead of two — and for every chunk of
+// J_OPT output slots the entry owning its first slot (written by that item itself, so the expansion below needs no search
+// and its walk never meets an empty item).  The row-id windows must have landed.
+__device__ __forceinline__ void tile_slot_table(const TileSmem& sm, TileSlots& ts, const TileGeom& g, const uint32_t (&code)[J_IPT],
+                                                const uint32_t (&cnt)[J_IPT], uint32_t ex, uint32_t ex_items, uint32_t tot, uint32_t tot_items) {
+    const int32_t* rid_all = &sm.rid[0][0];
+    const int l_off = (int)(g.x0 & 3), r_off = (JW + 8) + (int)(g.y0 & 3);     // first row of each window inside rid_all
     uint32_t o = ex, ci = ex_items;
 #pragma unroll
     for (int k = 0; k < J_IPT; k++) {
         if (cnt[k] == 0) continue;
         const int item = threadIdx.x * J_IPT + k;
-        ts.off[ci] = (uint16_t)o;
-        ts.code[ci] = (uint16_t)code[k];
-        ts.own[ci] = (uint16_t)(item - (int)(code[k] & 0x7FFFu));
+        const int start = (int)(code[k] & 0x7FFFu);
+        const bool class_b = (code[k] & J_CLASS_B) != 0;                       // item is an R row: its run lies in the L window
+        const int own = (class_b ? r_off : l_off) + (item - start);            // the item's own row
+        const int wrel = (class_b ? l_off : r_off) + start - (int)o;           // rid_all[wrel + slot] = the run's row for `slot`
+        ts.ent[ci] = make_uint2(o | (class_b ? JE_CLASS_B : 0u) | ((uint32_t)wrel << 16), (uint32_t)rid_all[own]);
         for (uint32_t q = (o + J_OPT - 1) / J_OPT; q * J_OPT < o + cnt[k]; q++) ts.first_item[q] = (uint16_t)ci;
         o += cnt[k];
         ci++;
     }
     if (threadIdx.x == JB - 1) {
-        ts.off[tot_items] = (uint16_t)tot;       // tot <= J_BIG < 2^16
-        ts.off[tot_items + 1] = 0xFFFFu;         // sentinel: the walk below never leaves the table
+        ts.ent[tot_items] = make_uint2(tot, 0u);         // tot <= J_BIG
+        ts.ent[tot_items + 1] = make_uint2(JE_OFF_MASK, 0u); // sentinel: the walk below never leaves the table
     }
 }
 
@@ -614,66 +709,120 @@ __device__ __forceinline__ void tile_slot_table(TileSlots& ts, const uint32_t (&
 template <bool CHECKED>
 __device__ __forceinline__ void tile_expand(TileSmem& sm, const TileSlots& ts, const TileGeom& g, const JoinSide& L, const JoinSide& R,
                                             uint32_t w0, uint32_t n, uint32_t n_threads) {
-    int32_t* stage_l = reinterpret_cast<int32_t*>(&sm.gs[0][0]);
-    int32_t* stage_r = stage_l + J_STAGE;
-    const int32_t* lrid = sm.rid[0] + (g.x0 & 3);
-    const int32_t* rrid = sm.rid[1] + (g.y0 & 3);
+    uint2* stage = reinterpret_cast<uint2*>(&sm.gs[0][0]);
+    const int32_t* rid_all = &sm.rid[0][0];
+    const int l_off = (int)(g.x0 & 3), r_off = (JW + 8) + (int)(g.y0 & 3);
     for (uint32_t s0 = w0 + threadIdx.x * J_OPT; s0 < w0 + n; s0 += n_threads * J_OPT) {
         uint32_t ci = ts.first_item[s0 / J_OPT];
-        uint32_t next = ts.off[ci + 1];
+        uint2 e = ts.ent[ci], nx = ts.ent[ci + 1];
+        const uint32_t pb = stage_swz(s0 - w0);                     // s0 - w0 is a multiple of J_OPT = 8
 #pragma unroll
         for (int q = 0; q < J_OPT; q++) {
             const uint32_t sl = s0 + q;
             if (sl < w0 + n) {
-                if (sl >= next) {                                   // exactly one step: entries are non-empty
+                if (sl >= (nx.x & JE_OFF_MASK)) {                   // exactly one step: entries are non-empty
                     ci++;
-                    next = ts.off[ci + 1];
+                    e = nx;
+                    nx = ts.ent[ci + 1];
                 }
-                const uint32_t cd = ts.code[ci];
-                const int w = (int)(cd & 0x7FFFu) + (int)(sl - ts.off[ci]);   // offset into the other table's window
-                const int own = ts.own[ci];
-                int32_t vl, vr;
-                if (!(cd & J_CLASS_B)) {                            // item is an L row; its run lies in R
-                    vl = lrid[own];
-                    vr = (!CHECKED || w < g.wr) ? rrid[w] : __ldg(R.rid + g.y0 + w);
-                } else {                                            // item is an R row; its run lies in L
-                    vr = rrid[own];
-                    vl = (!CHECKED || w < g.wl) ? lrid[w] : __ldg(L.rid + g.x0 + w);
-                }
-                stage_l[sl - w0] = vl;
-                stage_r[sl - w0] = vr;
+                const int idx = ((int)e.x >> 16) + (int)sl;         // the run's row for this slot, as an index into rid_all
+                const bool in_l = (e.x & JE_CLASS_B) != 0;
+                uint32_t other;
+                if (!CHECKED || idx < (in_l ? l_off + g.wl : r_off + g.wr)) other = (uint32_t)rid_all[idx];
+                else other = (uint32_t)(in_l ? __ldg(L.rid + g.x0 + (idx - l_off)) : __ldg(R.rid + g.y0 + (idx - r_off)));
+                stage[pb ^ (uint32_t)q] = in_l ? make_uint2(other, e.y) : make_uint2(e.y, other);
             }
         }
     }
 }
 
-// staging window -> global memory, 16-byte vector stores on 16-byte aligned global positions
+// staging window -> global memory: lane i of a warp moves slot base + i, so every store instruction of a warp writes 128
+// contiguous bytes per column at any alignment (no vector-alignment cases, one 64-bit shared-memory load per pair)
 __device__ __forceinline__ void tile_flush(const TileSmem& sm, unsigned long long g_w0, uint32_t n, int32_t* __restrict__ out_l,
-                                           int32_t* __restrict__ out_r, bool vec_ok) {
-    const int32_t* stage_l = reinterpret_cast<const int32_t*>(&sm.gs[0][0]);
-    const int32_t* stage_r = stage_l + J_STAGE;
-    const unsigned long long g_w1 = g_w0 + n;
-    const unsigned long long first = g_w0 & ~3ull;
-    for (unsigned long long gp = first + (unsigned long long)threadIdx.x * 4; gp < g_w1; gp += (unsigned long long)JB * 4) {
-        if (vec_ok && gp >= g_w0 && gp + 4 <= g_w1) {
-            const uint32_t sidx = (uint32_t)(gp - g_w0);
-            st_stream_u32x4(reinterpret_cast<uint4*>(out_l + gp), make_uint4(stage_l[sidx], stage_l[sidx + 1], stage_l[sidx + 2], stage_l[sidx + 3]));
-            st_stream_u32x4(reinterpret_cast<uint4*>(out_r + gp), make_uint4(stage_r[sidx], stage_r[sidx + 1], stage_r[sidx + 2], stage_r[sidx + 3]));
-        } else {
+                                           int32_t* __restrict__ out_r) {
+    const uint2* stage = reinterpret_cast<const uint2*>(&sm.gs[0][0]);
+    int32_t* __restrict__ ol = out_l + g_w0;
+    int32_t* __restrict__ orr = out_r + g_w0;
+    for (uint32_t i = threadIdx.x; i < n; i += JB) {
+        const uint2 v = stage[stage_swz(i)];
+        st_stream_u32(reinterpret_cast<uint32_t*>(ol + i), v.x);
+        st_stream_u32(reinterpret_cast<uint32_t*>(orr + i), v.y);
+    }
+}
+
+#ifdef GIQLB_JOIN_DEBUG_STATS
+// Per-phase cycle sums of the fused kernel (debug builds only; read with giqlb_debug_join_stats).
+// [0] tiles [1] ticket+geometry [2] bulk-copy wait [3] runs [4] scan [5] table [6] expand (thread 0) [7] barrier wait after expand (thread 0)
+// [8] flush [9] look-back (lane 31 of the last warp) [10] look-back steps [11] look-back polls [12] whole tile
+__device__ unsigned long long g_join_dbg[32];
+#define JDBG_T(var) const long long var = clock64()
+#define JDBG_ADD(slot, v) atomicAdd(&g_join_dbg[slot], (unsigned long long)(v))
+#else
+#define JDBG_T(var)
+#define JDBG_ADD(slot, v)
+#endif
+
+// Decoupled look-back of tile t, run by ONE warp: sums the pair counts of the tiles before t.  Every step fetches
+// 32 * J_LB predecessor status words in one L2 round trip (lane l owns the J_LB words nearest-first from base - l * J_LB)
+// and uses them up to the nearest word that already carries an inclusive prefix; it only waits for words nearer than
+// that one.  (Round 2, ncu: with 32 words per step the chain over the ~300 tiles in flight that had not yet published an
+// inclusive prefix took longer than the expansion it overlaps — 14 % of the kernel's stall samples sat at the barrier
+// behind it.)
+__device__ __forceinline__ unsigned long long tile_lookback(volatile unsigned long long* st, int64_t t, int* __restrict__ err_flag) {
+    constexpr uint32_t NONE = 1u << 20;
+    const int lane = (int)lane_id();
+    unsigned long long prefix = 0;
+    int64_t base = t - 1;
+    bool done = t == 0;
+    uint32_t spins = 0;
+    while (!done) {
+        unsigned long long sv[J_LB];
 #pragma unroll
-            for (int q = 0; q < 4; q++) {
-                const unsigned long long pq = gp + q;
-                if (pq >= g_w0 && pq < g_w1) {
-                    out_l[pq] = stage_l[pq - g_w0];
-                    out_r[pq] = stage_r[pq - g_w0];
-                }
+        for (int j = 0; j < J_LB; j++) {
+            const int64_t k = base - (int64_t)lane * J_LB - j;
+            sv[j] = 2ull << 62;                                          // before tile 0: an inclusive zero (= JF_FLAG_INCL)
+            if (k >= 0) sv[j] = st[k];
+        }
+        uint32_t first_incl;
+        while (true) {
+            uint32_t my_incl = NONE, my_unpub = NONE;
+#pragma unroll
+            for (int j = J_LB - 1; j >= 0; j--) {                        // descending: the nearest (smallest j) wins
+                const unsigned long long flag = sv[j] & ~JF_VALUE_MASK;
+                if (flag == JF_FLAG_INCL) my_incl = (uint32_t)(lane * J_LB + j);
+                if (flag == 0) my_unpub = (uint32_t)(lane * J_LB + j);
+            }
+            first_incl = __reduce_min_sync(FULL_MASK, my_incl);
+            const uint32_t first_unpub = __reduce_min_sync(FULL_MASK, my_unpub);
+            if (first_unpub >= first_incl) break;                        // every word nearer than the first inclusive one is published
+            if (lane == 0) JDBG_ADD(11, 1);
+            if (++spins > JF_SPIN_LIMIT) {
+                *err_flag = 1;
+                return prefix;
+            }
+            // poll again ONLY the words still needed (740 resident tiles re-reading whole windows would by themselves
+            // load the L2 with terabytes per second of status traffic)
+            __nanosleep(GIQLB_JOIN_BACKOFF_NS);
+#pragma unroll
+            for (int j = 0; j < J_LB; j++) {
+                const uint32_t pos = (uint32_t)(lane * J_LB + j);
+                if ((sv[j] & ~JF_VALUE_MASK) == 0 && pos < first_incl) sv[j] = st[base - (int64_t)pos];
             }
         }
+        unsigned long long part_sum = 0;
+#pragma unroll
+        for (int j = 0; j < J_LB; j++)
+            if ((uint32_t)(lane * J_LB + j) <= first_incl) part_sum += sv[j] & JF_VALUE_MASK;
+        prefix += warp_reduce_add<unsigned long long>(part_sum);
+        if (lane == 0) JDBG_ADD(10, 1);
+        if (first_incl != NONE) done = true;
+        else base -= 32 * J_LB;
     }
+    return prefix;
 }
 
 __global__ void __launch_bounds__(JB)
-join_fused_kernel(JoinSide L, JoinSide R, const int32_t* __restrict__ part, int64_t n_tiles,
+join_fused_kernel(JoinSide L, JoinSide R, const TileRec* __restrict__ recs, int64_t n_tiles,
                   unsigned long long* __restrict__ status, uint32_t* __restrict__ ticket, int32_t* __restrict__ out_l,
                   int32_t* __restrict__ out_r, int64_t capacity, unsigned long long* __restrict__ totals /* [0] pairs */,
                   uint32_t* __restrict__ big_count, uint32_t* __restrict__ big_tile, unsigned long long* __restrict__ big_off,
@@ -681,6 +830,8 @@ join_fused_kernel(JoinSide L, JoinSide R, const int32_t* __restrict__ part, int6
     extern __shared__ __align__(16) unsigned char dyn_smem[];   // > 48 KB with 512-thread tiles: dynamic, opted in by the host
     TileSmem& sm = *reinterpret_cast<TileSmem*>(dyn_smem);
     TileSlots& ts = *reinterpret_cast<TileSlots*>(dyn_smem + sizeof(TileSmem));
+    JDBG_T(c_begin);
+#if GIQLB_JOIN_TICKET
     if (threadIdx.x == 0) {
         sm.tile = atomicAdd(ticket, 1u);
         cuda::ptx::mbarrier_init(reinterpret_cast<uint64_t*>(&sm.bar[0]), 1);
@@ -689,15 +840,37 @@ join_fused_kernel(JoinSide L, JoinSide R, const int32_t* __restrict__ part, int6
     }
     __syncthreads();
     const int64_t t = sm.tile;
-    const TileGeom g = tile_geom(part, t, L.n, R.n);
+#else
+    // tile = block index: relies on CTAs being dispatched in blockIdx order, as cub::DeviceScan's look-back does; saves
+    // the ticket's L2 round trip and a block barrier at the head of every tile (the look-back's spin limit still bounds
+    // a wait on a tile that was never scheduled)
+    const int64_t t = blockIdx.x;
     if (threadIdx.x == 0) {
-        tile_stage(sm, g, L, R);
-        bar_wait(&sm.bar[0], 0);               // one thread polls the barrier; the others sleep at the hardware barrier below
+        cuda::ptx::mbarrier_init(reinterpret_cast<uint64_t*>(&sm.bar[0]), 1);
+        cuda::ptx::mbarrier_init(reinterpret_cast<uint64_t*>(&sm.bar[1]), 1);
+        cuda::ptx::fence_mbarrier_init(cuda::ptx::sem_release, cuda::ptx::scope_cluster);
+    }
+#endif
+    TileGeom g;
+    {
+        const int4* rp = reinterpret_cast<const int4*>(recs + t);
+        const int4 a = __ldg(rp), b = __ldg(rp + 1);
+        g.x0 = a.x; g.y0 = a.y; g.nl = a.z; g.nr = a.w; g.wl = b.x; g.wr = b.y;
+    }
+    JDBG_T(c_geom);
+    if (threadIdx.x < 32) {
+        __syncwarp();                          // lane 0's barrier initialisation precedes the other lanes' copies
+        tile_stage_warp(sm, g, L, R);
+        if (threadIdx.x == 0) bar_wait(&sm.bar[0], 0);   // one thread polls the barrier; the others sleep at the hardware barrier below
     }
     __syncthreads();
+    JDBG_T(c_loaded);
     uint32_t code[J_IPT], cnt[J_IPT];
     bool leaves = false;
     tile_runs(sm, g, L, R, code, cnt, &leaves);
+    JDBG_T(c_runs);
+    if (threadIdx.x == JB - 1) bar_wait(&sm.bar[1], 0);   // row ids have landed (also: never exit with bulk copies in flight); the
+                                                          // scan's barriers publish them to the block before the item table reads them
     // one block scan carries both the pair count (low 40 bits: < 1024 * 2^30) and the non-empty item count (high bits)
     unsigned long long sum = 0;
 #pragma unroll
@@ -707,45 +880,24 @@ join_fused_kernel(JoinSide L, JoinSide R, const int32_t* __restrict__ part, int6
     const unsigned long long tot = tot_packed & ((1ull << 40) - 1), ex64 = ex_packed & ((1ull << 40) - 1);
     const uint32_t tot_items = (uint32_t)(tot_packed >> 40), ex_items = (uint32_t)(ex_packed >> 40);
     const bool big = tot > (unsigned long long)J_BIG;
+    JDBG_T(c_scan);
     volatile unsigned long long* st = status;
     if (threadIdx.x == JB - 1) {
         st[t] = (t == 0 ? JF_FLAG_INCL : JF_FLAG_AGG) | tot;   // publish the tile's count as early as possible
-        bar_wait(&sm.bar[1], 0);               // row ids have landed (also: never exit with bulk copies in flight)
     }
     const uint32_t tot32 = (uint32_t)tot;
-    if (!big && tot32) tile_slot_table(ts, code, cnt, (uint32_t)ex64, ex_items, tot32, tot_items);
-    const bool checked = __syncthreads_or(leaves);   // item table complete, row ids visible; does any run leave the staged windows?
-    const bool vec_ok = ((reinterpret_cast<uintptr_t>(out_l) | reinterpret_cast<uintptr_t>(out_r)) & 15) == 0;
+    if (!big && tot32) tile_slot_table(sm, ts, g, code, cnt, (uint32_t)ex64, ex_items, tot32, tot_items);
+    const bool checked = __syncthreads_or(leaves);   // item table complete; does any run leave the staged windows?
+    JDBG_T(c_table);
     constexpr uint32_t N_EXPAND = JB - 32;     // warps 0..6 expand the tile while the last warp looks back
     static_assert(J_STAGE % J_OPT == 0, "windows start on chunk boundaries");
     if (threadIdx.x >= N_EXPAND) {
-        // The last warp sums the counts of the tiles before this one (decoupled look-back, 32 predecessors per step)
-        // while the other warps expand the tile.
+        // The last warp sums the counts of the tiles before this one (decoupled look-back) while the other warps expand the tile.
         const int lane = (int)lane_id();
-        unsigned long long prefix = 0;
-        int64_t base = t - 1;
-        bool done = t == 0;
-        uint32_t spins = 0;
-        while (!done) {
-            const int64_t k = base - lane;
-            unsigned long long sv = 2ull << 62;                      // before tile 0: an inclusive zero (= JF_FLAG_INCL)
-            if (k >= 0) sv = st[k];
-            while (__any_sync(FULL_MASK, (sv & ~JF_VALUE_MASK) == 0)) {   // a predecessor in the window has not published yet
-                if ((sv & ~JF_VALUE_MASK) == 0) {
-                    __nanosleep(20);
-                    sv = st[k];
-                }
-                if (++spins > JF_SPIN_LIMIT) {
-                    *err_flag = 1;
-                    sv |= JF_FLAG_INCL;
-                }
-            }
-            const uint32_t incl = __ballot_sync(FULL_MASK, (sv & ~JF_VALUE_MASK) == JF_FLAG_INCL);
-            const int first_incl = incl ? __ffs(incl) - 1 : 32;
-            prefix += warp_reduce_add<unsigned long long>(lane <= first_incl ? (sv & JF_VALUE_MASK) : 0ull);
-            if (incl) done = true;
-            else base -= 32;
-        }
+        const unsigned long long prefix = tile_lookback(st, t, err_flag);
+#ifdef GIQLB_JOIN_DEBUG_STATS
+        if (lane == 31) JDBG_ADD(9, clock64() - c_table);
+#endif
         if (lane == 31) {
             if (t > 0) st[t] = JF_FLAG_INCL | (prefix + tot);
             sm.tile_off = prefix;
@@ -762,7 +914,9 @@ join_fused_kernel(JoinSide L, JoinSide R, const int32_t* __restrict__ part, int6
         if (checked) tile_expand<true>(sm, ts, g, L, R, 0, n, N_EXPAND);
         else tile_expand<false>(sm, ts, g, L, R, 0, n, N_EXPAND);
     }
+    JDBG_T(c_expanded);
     __syncthreads();                           // first staging window complete, sm.tile_off published
+    JDBG_T(c_synced);
     if (big || tot32 == 0) return;
     const unsigned long long off_t = sm.tile_off;
     if (off_t + tot > (unsigned long long)capacity) return;   // the caller's buffer is too small: write nothing
@@ -774,8 +928,23 @@ join_fused_kernel(JoinSide L, JoinSide R, const int32_t* __restrict__ part, int6
             else tile_expand<false>(sm, ts, g, L, R, w0, n, JB);
             __syncthreads();
         }
-        tile_flush(sm, off_t + w0, n, out_l, out_r, vec_ok);
+        tile_flush(sm, off_t + w0, n, out_l, out_r);
     }
+#ifdef GIQLB_JOIN_DEBUG_STATS
+    if (threadIdx.x == 0) {
+        const long long c_end = clock64();
+        JDBG_ADD(0, 1);
+        JDBG_ADD(1, c_geom - c_begin);
+        JDBG_ADD(2, c_loaded - c_geom);
+        JDBG_ADD(3, c_runs - c_loaded);
+        JDBG_ADD(4, c_scan - c_runs);
+        JDBG_ADD(5, c_table - c_scan);
+        JDBG_ADD(6, c_expanded - c_table);
+        JDBG_ADD(7, c_synced - c_expanded);
+        JDBG_ADD(8, c_end - c_synced);
+        JDBG_ADD(12, c_end - c_begin);
+    }
+#endif
 }
 
 // Tiles with more than J_BIG pairs.  Their output is cut into J_PART-pair units that are dealt round-robin to the
@@ -935,6 +1104,17 @@ inline JoinSide side_of(const giqlb_index* ix) { return JoinSide{ix->gs, ix->ge,
 }  // namespace
 
 // ---- C ABI ------------------------------------------------------------------------------------------------
+#ifdef GIQLB_JOIN_DEBUG_STATS
+extern "C" int giqlb_debug_join_stats(unsigned long long* out32, int reset) {
+    cudaDeviceSynchronize();
+    cudaMemcpyFromSymbol(out32, g_join_dbg, sizeof(g_join_dbg));
+    if (reset) {
+        unsigned long long z[32] = {0};
+        cudaMemcpyToSymbol(g_join_dbg, z, sizeof(z));
+    }
+    return 0;
+}
+#endif
 extern "C" int giqlb_joinplan_free(giqlb_ctx* ctx, giqlb_joinplan* plan) {
     if (!plan) return GIQLB_OK;
     if (ctx) {
@@ -983,7 +1163,7 @@ static int plan_enqueue(giqlb_ctx* ctx, giqlb_index* L, giqlb_index* R, giqlb_jo
     } else if (st == GIQLB_OK) {
         {
             PhaseSpan ps(ctx, GIQLB_PH_JOIN_COUNT);
-            join_partition_kernel<<<(unsigned)ceil_div(n_tiles + 1, 256), 256, 0, ctx->stream>>>(L->gs, L->n, R->gs, R->n, n_tiles, p->part);
+            join_partition_kernel<<<(unsigned)ceil_div(n_tiles + 1, 256), 256, 0, ctx->stream>>>(L->gs, L->n, R->gs, R->n, n_tiles, p->part, nullptr);
             join_count_tiles_kernel<<<(unsigned)n_tiles, JB, 0, ctx->stream>>>(side_of(L), side_of(R), p->part, p->item_code, cnt);
             ctx->launches_this_call += 2;
             ctx->stats.kernels_total += 2;
@@ -1089,7 +1269,9 @@ int giqlb_intersects_join_impl(giqlb_ctx* ctx, giqlb_index* L, giqlb_index* R, i
         int32_t* part = nullptr;
         unsigned long long* status = nullptr;   // [n_tiles] look-back words | [n_tiles] big offsets | ticket, big count | [n_tiles] big tiles
         unsigned long long* totals = reinterpret_cast<unsigned long long*>(ctx->d_scalars);
+        TileRec* recs = nullptr;
         st = dev_alloc(ctx, &part, (size_t)n_tiles + 1);
+        if (st == GIQLB_OK) st = dev_alloc(ctx, &recs, (size_t)n_tiles + 1);
         if (st == GIQLB_OK) st = dev_alloc(ctx, &status, (size_t)4 * n_tiles + 2);
         if (st == GIQLB_OK) {
             unsigned long long* big_off = status + n_tiles;
@@ -1102,20 +1284,20 @@ int giqlb_intersects_join_impl(giqlb_ctx* ctx, giqlb_index* L, giqlb_index* R, i
             cudaMemsetAsync(totals, 0, 8, ctx->stream);
             {
                 PhaseSpan ps(ctx, GIQLB_PH_JOIN_COUNT);
-                join_partition_kernel<<<(unsigned)ceil_div(n_tiles + 1, 256), 256, 0, ctx->stream>>>(L->gs, L->n, R->gs, R->n, n_tiles, part);
+                join_partition_kernel<<<(unsigned)ceil_div(n_tiles + 1, 256), 256, 0, ctx->stream>>>(L->gs, L->n, R->gs, R->n, n_tiles, part, recs);
                 ctx->launches_this_call++;
                 ctx->stats.kernels_total++;
             }
             {
-                static bool smem_opted_in = false;   // per process: the kernels' dynamic shared memory limit
-                if (!smem_opted_in) {
+                // the dynamic shared-memory limit is a per-device function attribute; a context is bound to one device
+                if (!ctx->join_smem_opted_in) {
                     cudaFuncSetAttribute(join_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(TileSmem) + sizeof(TileSlots)));
                     cudaFuncSetAttribute(join_emit_big_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(TileSmem) + sizeof(TileOffsets)));
-                    smem_opted_in = true;
+                    ctx->join_smem_opted_in = true;
                 }
                 PhaseSpan ps(ctx, GIQLB_PH_JOIN_EMIT);
-                join_fused_kernel<<<(unsigned)n_tiles, JB, sizeof(TileSmem) + sizeof(TileSlots), ctx->stream>>>(side_of(L), side_of(R), part, n_tiles, status, ticket, out_l, out_r,
-                                                                             capacity, totals, big_count, big_tile, big_off, big_cnt, ctx->d_err);
+                join_fused_kernel<<<(unsigned)n_tiles, JB, sizeof(TileSmem) + sizeof(TileSlots), ctx->stream>>>(side_of(L), side_of(R), recs, n_tiles, status, ticket, out_l, out_r,
+                                                                                 capacity, totals, big_count, big_tile, big_off, big_cnt, ctx->d_err);
                 join_emit_big_kernel<<<ctx->sm_count * 2, JB, sizeof(TileSmem) + sizeof(TileOffsets), ctx->stream>>>(side_of(L), side_of(R), part, big_count, big_tile, big_off,
                                                                                 big_cnt, out_l, out_r, capacity);
                 cudaMemcpyAsync(ctx->h_scalars + 8, big_count, 4, cudaMemcpyDeviceToHost, ctx->stream);
@@ -1139,11 +1321,13 @@ int giqlb_intersects_join_impl(giqlb_ctx* ctx, giqlb_index* L, giqlb_index* R, i
         }
         if (st == GIQLB_OK && degenerate) {   // speculation failed: redo through the general path
             dev_free(ctx, part);
+            dev_free(ctx, recs);
             dev_free(ctx, status);
             return giqlb_intersects_join_impl(ctx, L, R, out_l, out_r, capacity, total_host, false);
         }
         ctx->stats.reserved = (int32_t)(ctx->h_scalars[8] & 0xffffffff);   // tiles delegated to the big-tile kernel
         dev_free(ctx, part);
+        dev_free(ctx, recs);
         dev_free(ctx, status);
     }
     if (st != GIQLB_OK) return st;

@@ -487,8 +487,11 @@ def _column(values) -> np.ndarray:
 class Result:
     """Columnar result: ``columns`` (names, duplicates allowed as in SQL) and ``arrays``; ``rows`` = list of tuples."""
 
-    def __init__(self, columns: list[str], arrays: list[np.ndarray]):
+    def __init__(self, columns: list[str], arrays: list[np.ndarray], sources: Optional[list] = None):
+        # sources[i] = (relation alias, column) an output column was projected from, None for computed columns: what a
+        # qualified ORDER BY key (``ORDER BY b.start``) resolves against when output names repeat
         self.columns, self.arrays = columns, arrays
+        self.sources = sources if sources is not None else [None] * len(columns)
 
     @property
     def rows(self) -> list[tuple]:
@@ -497,7 +500,7 @@ class Result:
         return list(zip(*(a.tolist() for a in self.arrays)))
 
     def take(self, sel) -> "Result":
-        return Result(self.columns, [a[sel] for a in self.arrays])
+        return Result(self.columns, [a[sel] for a in self.arrays], self.sources)
 
     def to_pydict(self) -> dict:
         return {c: a.tolist() for c, a in zip(self.columns, self.arrays)}
@@ -936,16 +939,18 @@ class Session:
             total[g] += int(per_row[i])
         rows = [k + (total[g],) for k, g in first.items() if j["kind"] == "left" or total[g] > 0]
         names = {id(p): p.get("name", p["col"]) for p in keys}
-        out_cols, arrays = [], []
+        out_cols, arrays, sources = [], [], []
         for p in q["proj"]:
             if p is cnt:
                 out_cols.append(p.get("name", "count"))
                 arrays.append(np.asarray([r[-1] for r in rows], dtype=np.int64))
+                sources.append(None)
             else:
                 k = keys.index(p)
                 out_cols.append(names[id(p)])
                 arrays.append(_column([r[k] for r in rows]))
-        return self._order_limit(q, Result(out_cols, arrays))
+                sources.append((la, p["col"]))
+        return self._order_limit(q, Result(out_cols, arrays, sources), f)
 
     def _group_count(self, q, f: _Frame) -> Result:
         """generic GROUP BY <columns> with COUNT(*) / COUNT(col) over the joined rows"""
@@ -954,8 +959,9 @@ class Session:
         groups: dict[tuple, list[int]] = {}
         for i, key in enumerate(zip(*key_cols)) if key_cols else []:
             groups.setdefault(key, []).append(i)
-        out_cols, arrays = [], []
+        out_cols, arrays, sources = [], [], []
         for p in q["proj"]:
+            sources.append(None)
             if p["kind"] == "col":
                 a = f.resolve(p["alias"], p["col"])
                 if (a, p["col"]) not in keys:
@@ -963,6 +969,7 @@ class Session:
                 k = keys.index((a, p["col"]))
                 out_cols.append(p.get("name", p["col"]))
                 arrays.append(_column([key[k] for key in groups]))
+                sources[-1] = (a, p["col"])
             elif p["kind"] == "count_star":
                 out_cols.append(p.get("name", "count"))
                 arrays.append(np.asarray([len(v) for v in groups.values()], dtype=np.int64))
@@ -974,7 +981,7 @@ class Session:
                 arrays.append(np.asarray([int(present[v].sum()) for v in groups.values()], dtype=np.int64))
             else:
                 raise UnsupportedQuery("GROUP BY supports grouped columns and COUNT only; other aggregates are finished by the SQL engine")
-        return self._order_limit(q, Result(out_cols, arrays))
+        return self._order_limit(q, Result(out_cols, arrays, sources), f)
 
     def _join_nearest(self, q, f: _Frame, j):
         """src/giql/expanders/nearest.py:336-397 — one engine call per NEAREST, joined back on the query row"""
@@ -1093,13 +1100,14 @@ class Session:
             out = [tuple(r[:width]) + ((r[-1],) if "count_star" in kinds else ()) for r in rows]
             out.sort(key=lambda r: (r[0], r[width - 2]))
             cols = ["chrom"] + (["strand"] if m["stranded"] else []) + ["start", "end"] + (["count"] if "count_star" in kinds else [])
-            return self._order_limit(q, Result(cols, [_column([r[i] for r in out]) for i in range(len(cols))]))
+            return self._order_limit(q, Result(cols, [_column([r[i] for r in out]) for i in range(len(cols))]), f)
         if q.get("group"):
             return self._group_count(q, f)
         if kinds & {"count_star", "count_col"}:
             raise UnsupportedQuery("COUNT without GROUP BY (outside MERGE) is finished by the SQL engine")
         cols: list[str] = []
         arrays: list[np.ndarray] = []
+        sources: list = []
         for p in proj:
             if p["kind"] == "star":
                 for a in ([p["alias"]] if p["alias"] else f.order):
@@ -1108,14 +1116,17 @@ class Session:
                     for c in f.schema(a):
                         cols.append(c)
                         arrays.append(f.column(a, c))
+                        sources.append((a, c))
             elif p["kind"] == "col":
                 a = f.resolve(p["alias"], p["col"])
                 cols.append(p.get("name", p["col"]))
                 arrays.append(f.column(a, p["col"]))
+                sources.append((a, p["col"]))
             elif p["kind"] == "cluster":
                 ids = _cluster_ids(be, f, p)                            # over the rows the FROM clause produced
                 cols.append(p.get("name", "cluster"))
                 arrays.append(ids)
+                sources.append(None)
             elif p["kind"] == "distance":
                 # src/giql/expanders/_distance.py:67-117 over the joined pairs
                 for a in (p["a"], p["b"]):
@@ -1126,28 +1137,49 @@ class Session:
                     raise UnsupportedQuery("DISTANCE over the NULL side of an outer join")
                 cols.append(p.get("name", "distance"))
                 arrays.append(_distance(be, f.rels[p["a"]], f.rels[p["b"]], ia, ib, p["stranded"], p["signed"]))
+                sources.append(None)
             else:
                 raise UnsupportedQuery(f"projection {p['kind']}")
-        res = Result(cols, arrays)
+        res = Result(cols, arrays, sources)
         if q["distinct"]:
             first: dict[tuple, int] = {}
             for i, r in enumerate(res.rows):
                 first.setdefault(r, i)
             res = res.take(np.fromiter(first.values(), dtype=np.int64, count=len(first)))
-        return self._order_limit(q, res)
+        return self._order_limit(q, res, f)
 
     @staticmethod
-    def _order_limit(q, res: Result) -> Result:
-        for (_alias, col), desc in reversed(q["order"]):
-            if col not in res.columns:
-                raise ValueError(f"ORDER BY column {col!r} is not in the select list")
-            key = res.arrays[res.columns.index(col)]
+    def _order_key(res: Result, alias, col, f) -> int:
+        """Output column an ORDER BY key names.  A qualified key (``b.start``) matches the column projected from that
+        relation; an unqualified one matches an output name (alias or column), which must then be unambiguous."""
+        if alias is not None:
+            a = f.resolve(alias, col) if f is not None else alias
+            hits = [i for i, src in enumerate(res.sources) if src == (a, col)]
+            if not hits:
+                raise ValueError(f"ORDER BY column {alias}.{col} is not in the select list")
+            return hits[0]                                                   # the same source projected twice holds equal values
+        hits = [i for i, name in enumerate(res.columns) if name == col]
+        if not hits:
+            raise ValueError(f"ORDER BY column {col!r} is not in the select list")
+        if len(hits) > 1 and len({res.sources[i] for i in hits}) > 1:
+            raise ValueError(f"ORDER BY column {col!r} is ambiguous: {len(hits)} output columns carry that name; qualify it")
+        return hits[0]
+
+    @staticmethod
+    def _order_limit(q, res: Result, f=None) -> Result:
+        for (alias, col), desc in reversed(q["order"]):
+            key = res.arrays[Session._order_key(res, alias, col, f)]
             if key.dtype == object:                                         # NULLs last, as DuckDB orders by default
                 vals = key.tolist()
                 some = sorted((i for i in range(len(vals)) if vals[i] is not None), key=lambda i: vals[i], reverse=desc)
                 perm = np.asarray(some + [i for i in range(len(vals)) if vals[i] is None], dtype=np.int64)
+            elif desc:
+                # descending and stable without negating the key (negation wraps unsigned / bool keys and INT64_MIN):
+                # sort on the negated dense rank
+                rank = np.unique(key, return_inverse=True)[1].astype(np.int64).reshape(-1)
+                perm = np.argsort(-rank, kind="stable")
             else:
-                perm = np.argsort(-key if desc else key, kind="stable")
+                perm = np.argsort(key, kind="stable")
             res = res.take(perm)
         if q["limit"] is not None:
             res = res.take(slice(0, q["limit"]))

@@ -9,7 +9,7 @@ from __future__ import annotations
 import re
 
 _POINT = re.compile(r"^([\w.]+):(\d+)$")
-_BRACKET = re.compile(r"^([\w.]+):\[(\d+),\s*(\d+)([\)\]])(?::([+-]))?$")
+_BRACKET = re.compile(r"^([\w.]+):\[(\d+),(\d+)([\)\]])(?::([+-]))?$")   # no blank after the comma: range_parser.py:84-86
 _DASH = re.compile(r"^([\w.]+):(\d+)-(\d+)(?::([+-]))?$")
 
 

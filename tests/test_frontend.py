@@ -352,3 +352,20 @@ def test_result_egress_and_dataframe_ingest():
     closed = Session(OracleBackend())
     closed.register("p", {"chrom": ["c", "c"], "start": [1, 10], "end": [9, 20]}, Table("p", coordinate_system="1based", interval_type="closed"))
     assert closed.execute("SELECT start FROM p WHERE interval INTERSECTS 'c:9-10'").rows == [(10,)]   # 1-based closed [10,20] = 0-based [9,20)
+
+
+def test_qualified_order_by_over_duplicate_output_names(oracle_session=None):
+    """``ORDER BY b.start`` over ``SELECT a.start, b.start`` must sort on b's column, not the first ``start``."""
+    from backends import OracleBackend
+    from giql_b200.frontend import Session
+
+    s = Session(OracleBackend())
+    s.register("a", {"chrom": ["c"] * 3, "start": [10, 20, 30], "end": [100, 100, 100]})
+    s.register("b", {"chrom": ["c"] * 3, "start": [40, 50, 60], "end": [70, 80, 90]})
+    q = "SELECT a.start, b.start FROM a JOIN b ON a.interval INTERSECTS b.interval ORDER BY b.start DESC, a.start LIMIT 4"
+    assert [tuple(r) for r in s.execute(q).rows] == [(10, 60), (20, 60), (30, 60), (10, 50)]
+    with pytest.raises(ValueError, match="ambiguous"):
+        s.execute("SELECT a.start, b.start FROM a JOIN b ON a.interval INTERSECTS b.interval ORDER BY start")
+    # an unqualified key naming one output column keeps working, DESC on unsigned-like keys does not wrap
+    got = s.execute("SELECT a.start AS s, b.start FROM a JOIN b ON a.interval INTERSECTS b.interval ORDER BY s DESC LIMIT 3").rows
+    assert [r[0] for r in got] == [30, 30, 30]
