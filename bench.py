@@ -203,6 +203,119 @@ def algorithmic_bytes(phase: str, n_full: int, n_local: int, pairs: int, sort_pa
     }.get(phase, 0)
 
 
+
+# ---- the other BASELINE configs (C3 / C4 / C5), reported beside the headline in the same JSON line ---------------------
+def other_configs(eng, rank, world, hbm_peak, rows_scale=1.0):
+    """BASELINE.json configs[2..4] on this run's GPUs: rows/s, algorithmic bytes and fraction of the measured
+    HBM peak.  Inputs are generated on the device (giql_b200/synth_torch.py: the §8(d) distributions, a torch random stream)
+    and arrive as dictionary codes; each timing is the median of 5 calls after 2 warm-ups (CUDA events on the engine's
+    stream) and includes the index build of the target / own table.  N = 1: SEMI / ANTI 50M x 1M, NEAREST k = 1 / 5 stranded
+    10M x 2M with DISTANCE, CLUSTER / MERGE over 200M reads.  N > 1: CLUSTER / MERGE over the same 200M reads, genome-range
+    sharded over the N ranks (three small NCCL all-gathers, no row exchange), totals checked against the single-GPU answer."""
+    import torch
+    import torch.distributed as dist
+
+    from giql_b200 import synth_torch as st
+
+    out = []
+    dev = eng.device
+
+    def table(T, strand=False, dictionary=None):
+        return eng.table_from_codes(T["code"], T["start"], T["end"], dictionary or T["names"], strand=T["strand_code"] if strand else None)
+
+    def timed(fn, reps=5, warm=2):
+        for _ in range(warm):
+            res = fn()
+        torch.cuda.synchronize()
+        ts = []
+        for _ in range(reps):
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record(eng.stream)
+            res = fn()
+            b.record(eng.stream)
+            torch.cuda.synchronize()
+            ts.append(a.elapsed_time(b))
+        return float(np.median(ts)), res
+
+    def emit(name, rows, ms, alg_bytes, **extra):
+        gbs = alg_bytes / (ms * 1e6)
+        line = {"config": name, "rows": rows, "ms": round(ms, 3), "rows_per_s": rows / (ms / 1e3), "algorithmic_bytes": int(alg_bytes),
+                "gbs": round(gbs, 1), "frac": round(gbs / hbm_peak, 4)}
+        line.update(extra)
+        out.append(line)
+        log(f"[bench] {name}: {ms:.3f} ms, {rows / (ms / 1e3) / 1e9:.2f} G rows/s, {gbs:.0f} GB/s = {gbs / hbm_peak:.3f} of HBM")
+
+    n5 = int(200_000_000 * rows_scale)
+    if world == 1:
+        nq, nt = int(50_000_000 * rows_scale), int(1_000_000 * rows_scale)
+        tq = table(st.peaks(nq, 20260105, dev))
+        tt = table(st.peaks(nt, 20260106, dev), dictionary=tq.dictionary)
+        ms, kept = timed(lambda: eng.semi(tq, tt))
+        emit(f"C3 SEMI {nq} x {nt}", nq, ms, 12 * (nq + nt) + 4 * int(kept.numel()), kept=int(kept.numel()))
+        ms, kept_a = timed(lambda: eng.anti(tq, tt))
+        emit(f"C3 ANTI {nq} x {nt}", nq, ms, 12 * (nq + nt) + 4 * int(kept_a.numel()), kept=int(kept_a.numel()))
+        assert int(kept.numel()) + int(kept_a.numel()) == nq
+        del tq, tt, kept, kept_a
+        nq, nt = int(10_000_000 * rows_scale), int(2_000_000 * rows_scale)
+        tq = table(st.peaks(nq, 20260107, dev), strand=True)
+        tt = table(st.genes(nt, 20260108, dev), strand=True, dictionary=tq.dictionary)
+        for k in (1, 5):
+            ms, res = timed(lambda: eng.nearest(tq, tt, k=k, stranded=True, signed=True))
+            emit(f"C4 NEAREST k={k} stranded+signed {nq} x {nt} (distance emitted)", nq, ms, 13 * (nq + nt) + 12 * len(res), emitted=len(res))
+        ms, _ = timed(lambda: eng.distance(tq, tt, res.query_rows.long(), res.target_rows.long(), stranded=True, signed=True))
+        emit("C4 DISTANCE over the k=5 pairs", len(res), ms, 29 * len(res))
+        del tq, tt, res
+        eng.trim()
+    T = st.reads(n5, 20260109, dev)
+    t = table(T)
+    del T
+    if world == 1:
+        ms, ids = timed(lambda: eng.cluster(t), reps=3, warm=1)
+        emit(f"C5 CLUSTER {n5} reads", n5, ms, 16 * n5, clusters_max_id=int(ids.max()))
+        del ids
+        ms, m = timed(lambda: eng.merge(t), reps=3, warm=1)
+        emit(f"C5 MERGE {n5} reads", n5, ms, 12 * n5 + 12 * len(m), regions=len(m))
+        assert int(m.count.sum()) == n5
+    else:
+        from giql_b200 import sharding
+
+        ops = sharding.EngineOps(eng)
+
+        def max_over_ranks(ms):
+            v = torch.tensor([ms], dtype=torch.float64, device=dev)
+            dist.all_reduce(v, op=dist.ReduceOp.MAX)
+            return float(v.item())
+
+        def sum_over_ranks(*vals):
+            v = torch.tensor(list(vals), dtype=torch.int64, device=dev)
+            dist.all_reduce(v, op=dist.ReduceOp.SUM)
+            return [int(x) for x in v.tolist()]
+
+        dist.barrier()
+        ms, ids = timed(lambda: sharding.sharded_cluster(ops, rank, world, t), reps=3, warm=1)
+        ms = max_over_ranks(ms)
+        owned, = sum_over_ranks(int((ids > 0).sum()))
+        ms_m, regs = timed(lambda: sharding.sharded_merge(ops, rank, world, t), reps=3, warm=1)
+        ms_m = max_over_ranks(ms_m)
+        n_regions, n_rows = sum_over_ranks(int(regs["start"].numel()), int(regs["count"].sum()))
+        # the single-GPU answer on rank 0's copy of the same table, for the totals
+        ref = [0, 0, 0]
+        if rank == 0:
+            m1 = eng.merge(t)
+            ref = [len(m1), int(m1.count.sum()), int(eng.cluster(t).max())]
+            del m1
+        r = torch.tensor(ref, dtype=torch.int64, device=dev)
+        dist.broadcast(r, 0)
+        ok = owned == n5 and n_rows == n5 and n_regions == int(r[0])
+        emit(f"C5 CLUSTER {n5} reads, genome-range sharded over {world} GPUs (NCCL)", n5, ms, 16 * n5, rows_owned=owned, totals_match_single_gpu=ok)
+        emit(f"C5 MERGE {n5} reads, genome-range sharded over {world} GPUs (NCCL)", n5, ms_m, 12 * n5 + 12 * n_regions, regions=n_regions,
+             single_gpu_regions=int(r[0]), totals_match_single_gpu=ok)
+        assert ok, f"sharded CLUSTER/MERGE totals differ from the single-GPU answer: rows {owned}/{n_rows} of {n5}, regions {n_regions} vs {int(r[0])}"
+    del t
+    eng.trim()
+    return out
+
+
 def run_b200(args):
     import torch
     import torch.distributed as dist
@@ -372,6 +485,20 @@ def run_b200(args):
     e2e_ms = 1e3 * float(e2e_s.item()) / args.steps
     d2h_bytes = 8 * pairs_local
 
+    # ---- the other BASELINE configs (all ranks take part in the sharded CLUSTER / MERGE leg) ----
+    others = None
+    if not args.no_other:
+        del dev, flush
+        eng.trim()
+        torch.cuda.empty_cache()
+        try:
+            others = other_configs(eng, rank, world, hbm_peak, args.other_scale)
+        except Exception as exc:   # noqa: BLE001 — the headline line must survive a failure here; the failure is reported in it
+            if world > 1:
+                raise
+            others = [{"error": f"{type(exc).__name__}: {exc}"}]
+            log(f"[bench] other_configs failed: {others[0]['error']}")
+
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -448,6 +575,7 @@ def run_b200(args):
         "phases": phases,
         "clocks": clocks.summary(),
         "cpu_baseline": cpu,
+        "other_configs": others,
     }
     print(json.dumps(line), flush=True)
     if world > 1:
@@ -462,6 +590,8 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--rows", type=int, default=ROWS_DEFAULT, help="rows per table (default: the 10M of BASELINE configs[1])")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--no-other", action="store_true", help="skip the other BASELINE configs (C3 / C4 / C5)")
+    ap.add_argument("--other-scale", type=float, default=1.0, help="row-count scale of the other BASELINE configs")
     ap.add_argument("--no-bind", action="store_true", help="do not pin the process to the GPU-local CPU cores")
     ap.add_argument("--no-pipeline", action="store_true", help="e2e: one synchronous call per step instead of Engine.intersects_batches")
     ap.add_argument("--join-mode", default="auto", choices=["auto", "two_pass", "single_pass"],

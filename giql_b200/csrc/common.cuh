@@ -28,7 +28,6 @@ struct giqlb_ctx {
     void* h_stage = nullptr;        // pinned staging buffer for small host -> device tables (GIQLB_STAGE_BYTES)
     int* d_err = nullptr;           // device int[4]: sticky kernel-side error flags ([0] look-back spin limit)
     giqlb_stats_t stats = {};
-    bool fused_pipeline = true;        // one-call pipelines: fused encode + observe, keys from raw columns (GIQLB_FUSED_PIPELINE=0 turns it off)
     bool join_smem_opted_in = false;   // cudaFuncSetAttribute is per device: remembered per context, not per process
     int32_t launches_this_call = 0;
     // Scratch cache.  Every allocation of a context is used on ITS stream only, so a freed block can be handed
@@ -124,6 +123,15 @@ struct giqlb_index {
     int64_t n_negative = 0;      // rows with end <  start
     bool resolved = true;        // false: the counts still sit in d_counters (giqlb_index_resolve fetches them)
     unsigned long long* d_counters = nullptr;   // [3] end<=start, end<start, rows outside the layout
+    // lazily built bucket directories (giqlb_index_ensure_dirs): for every strand block with rows, dir[slot][b] = first
+    // block-relative position whose value is >= b << dir_shift, over gs / pmax / ge_sorted.  A search then starts inside one
+    // bucket (about one row) instead of walking log2(n) dependent loads from the whole array.
+    uint32_t* dir_gs = nullptr;
+    uint32_t* dir_pmax = nullptr;
+    uint32_t* dir_ges = nullptr;
+    int32_t* d_dir_slot = nullptr;   // device [GIQLB_MAX_STRAND_CODES]: strand block -> directory slot, -1 for empty blocks
+    int dir_shift = 0;
+    uint32_t dir_stride = 0;         // entries per slot = (layout extent >> dir_shift) + 2
     bool tie_by_end = false;     // equal starts are ordered by end
     bool grouped_by_strand = false;
     int32_t n_blocks = 1;                                   // strand blocks (1 when not grouped)
@@ -304,6 +312,18 @@ __device__ __forceinline__ I upper_bound_dev(const T* __restrict__ a, I lo, I hi
     return lo;
 }
 
+// Searches through a bucket directory (see giqlb_index::dir_*): tab[b] = first index with a[idx] >= b << shift, so the
+// answer for x lies in [tab[b], tab[b + 1]] with b = x >> shift.  The directory covers the layout's extent only: larger
+// x are clamped into the last bucket `last` (= entries - 2; tab[last + 1] = n), which stays exact.
+__device__ __forceinline__ int64_t dir_lower_bound(const uint32_t* __restrict__ tab, int shift, uint32_t last, const uint32_t* __restrict__ a, uint32_t x) {
+    const uint32_t b = min(x >> shift, last);
+    return lower_bound_dev<uint32_t, int64_t>(a, (int64_t)__ldg(tab + b), (int64_t)__ldg(tab + b + 1), x);
+}
+__device__ __forceinline__ int64_t dir_upper_bound(const uint32_t* __restrict__ tab, int shift, uint32_t last, const uint32_t* __restrict__ a, uint32_t x) {
+    const uint32_t b = min(x >> shift, last);
+    return upper_bound_dev<uint32_t, int64_t>(a, (int64_t)__ldg(tab + b), (int64_t)__ldg(tab + b + 1), x);
+}
+
 // streaming (read-once) loads / stores that do not pollute L1
 __device__ __forceinline__ uint32_t ld_stream_u32(const uint32_t* p) {
     uint32_t v;
@@ -396,15 +416,9 @@ struct giqlb_prekeyed {
     int32_t* rows = nullptr;              // [n] their row ids
     unsigned long long* counters = nullptr;   // [4 + 512] as giqlb_index::d_counters
 };
-// remap (nullable): `code` still holds the dictionary encoder's parked table slots; the key-generation pass translates
-// them through slot2code and writes the codes back (it does nothing when *ok_flag == 0: the device-side ranking declined)
-struct giqlb_code_remap {
-    const int32_t* slot2code;
-    const int* ok_flag;
-};
 int giqlb_index_build_impl(giqlb_ctx* ctx, const giqlb_layout* lay, const int32_t* code, const int32_t* start,
                            const int32_t* end, const uint8_t* strand, const int32_t* rows, int64_t n, int32_t start_adj,
-                           int32_t end_adj, int flags, giqlb_prekeyed* pre, giqlb_index** out, const giqlb_code_remap* remap = nullptr);
+                           int32_t end_adj, int flags, giqlb_prekeyed* pre, giqlb_index** out);
 struct giqlb_dict_pending;
 #define GIQLB_ASYNC_DICT_MAX_CODES 1024   // upper bound of the code space while the dictionary is still on the device
 // defer_remap: leave the parked table slots in codes_l / codes_r; the caller translates them with
@@ -412,8 +426,6 @@ struct giqlb_dict_pending;
 int giqlb_dict_encode_async(giqlb_ctx* ctx, const int32_t* offs_l, const uint8_t* bytes_l, int64_t n_l, const int32_t* offs_r,
                             const uint8_t* bytes_r, int64_t n_r, int32_t* codes_l, int32_t* codes_r, giqlb_dict_pending** out,
                             bool defer_remap = false);
-int giqlb_dict_encode_observe_async(giqlb_ctx* ctx, const giqlb_table_t* L, const giqlb_table_t* R, giqlb_layout* lay,
-                                    giqlb_dict_pending** out);
 void giqlb_dict_pending_tables(const giqlb_dict_pending* p, const int32_t** slot2code, const int** ok_flag);
 int giqlb_layout_observe_remap(giqlb_ctx* ctx, giqlb_layout* lay, int32_t* code, const int32_t* start, const int32_t* end, int64_t n,
                                int32_t start_adj, int32_t end_adj, const int32_t* slot2code, const int* ok_flag);
@@ -424,3 +436,5 @@ int giqlb_intersects_join_impl(giqlb_ctx* ctx, giqlb_index* L, giqlb_index* R, i
 int giqlb_index_ensure_pmax(giqlb_ctx* ctx, giqlb_index* ix);
 int giqlb_index_resolve(giqlb_ctx* ctx, giqlb_index* a, giqlb_index* b);
 int giqlb_index_ensure_end_sorted(giqlb_ctx* ctx, giqlb_index* ix);
+// bucket directories over gs (always), pmax and ge_sorted (on request; they must exist already)
+int giqlb_index_ensure_dirs(giqlb_ctx* ctx, giqlb_index* ix, bool want_pmax, bool want_ges);

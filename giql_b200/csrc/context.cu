@@ -1,7 +1,5 @@
 // context.cu — context lifetime, error/statistics plumbing and small generic device utilities
 // (exclusive scan of tile counts, running max, flag compaction).
-#include <stdlib.h>
-
 #include "common.cuh"
 #include "scan.cuh"
 
@@ -23,8 +21,6 @@ extern "C" int giqlb_create(int device, void* cuda_stream, giqlb_ctx** out) {
     // NULL selects the legacy default stream: the caller's other work on that stream (PyTorch's default
     // stream has handle 0) stays ordered with ours.  The library never creates a stream of its own.
     ctx->stream = (cudaStream_t)cuda_stream;
-    // A/B knob read once per context (the default is the measured winner)
-    if (const char* v = getenv("GIQLB_FUSED_PIPELINE")) ctx->fused_pipeline = v[0] != '0';
     if (cudaMallocHost((void**)&ctx->h_scalars, 64 * sizeof(int64_t)) != cudaSuccess ||
         cudaMallocHost(&ctx->h_stage, GIQLB_STAGE_BYTES) != cudaSuccess ||
         cudaMalloc((void**)&ctx->d_scalars, 64 * sizeof(int64_t)) != cudaSuccess ||

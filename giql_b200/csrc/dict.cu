@@ -102,11 +102,9 @@ struct DictCache {
 };
 
 // Resolves the name (w0, w1, len <= 16; zero padded) of global row g to its slot of the global table, through the cache.
-// *centry receives the cache entry that holds the name afterwards, or -1 (resolved through the global table only).
 __device__ __forceinline__ uint32_t cached_resolve(DictCache& c, const StrTable& A, const StrTable& B, unsigned long long* __restrict__ slots,
                                                    uint32_t cap_mask, const uint8_t* __restrict__ name, uint64_t w0, uint64_t w1, int len,
-                                                   int64_t g, unsigned int* __restrict__ n_distinct, int* centry = nullptr) {
-    if (centry) *centry = -1;
+                                                   int64_t g, unsigned int* __restrict__ n_distinct) {
     // 32-bit mix for the cache index (the 64-bit hash is only needed on a miss)
     const uint32_t lo = (uint32_t)w0, hi = (uint32_t)(w0 >> 32);
     uint32_t h = (lo ^ (hi * 0x9E3779B1u) ^ ((uint32_t)w1 * 0x85EBCA6Bu) ^ (uint32_t)(w1 >> 32) ^ (uint32_t)len) * 0xC2B2AE35u;
@@ -123,10 +121,7 @@ __device__ __forceinline__ uint32_t cached_resolve(DictCache& c, const StrTable&
         }
         if (v == DI_PENDING) break;                        // another thread is filling this entry (almost surely with this very name):
                                                            // resolve globally and do NOT insert, or the cache fills up with duplicates
-        if ((v & ~DI_SLOT_MASK) == want_len && k == w0 && (len <= 8 || c.k1[ci] == w1)) {   // PENDING never matches: its top bits are all ones
-            if (centry) *centry = ci;
-            return v & DI_SLOT_MASK;
-        }
+        if ((v & ~DI_SLOT_MASK) == want_len && k == w0 && (len <= 8 || c.k1[ci] == w1)) return v & DI_SLOT_MASK;   // PENDING never matches: its top bits are all ones
         ci = (ci + 1) & (DI_CACHE - 1);
     }
     const uint32_t slot = global_resolve(A, B, slots, cap_mask, name, len, hash_short(w0, w1, len), g, n_distinct);
@@ -135,7 +130,6 @@ __device__ __forceinline__ uint32_t cached_resolve(DictCache& c, const StrTable&
         c.k1[free_at] = w1;
         __threadfence_block();
         *(volatile uint32_t*)&c.meta[free_at] = slot | want_len;
-        if (centry) *centry = free_at;
     }
     return slot;
 }
@@ -207,84 +201,14 @@ __device__ __forceinline__ void dict_stage_async(const StrTable& A, const StrTab
     for (int i = threadIdx.x; i < n_vec; i += DI_THREADS) cp_async_16(reinterpret_cast<uint4*>(st.bytes) + i, src + i);
 }
 
-// What the fused encode + observe pass needs beside the names: the coordinate columns of both tables and where the
-// per-slot extents, degenerate-row counters and widest intervals go (giqlb_layout takes them from there).
-struct DictObserve {
-    const int32_t* start[2];
-    const int32_t* end[2];
-    int32_t sadj[2], eadj[2];
-    long long* lohi_slot;                     // [2 * cap]: per table slot, lo (init INT64_MAX) then hi (init INT64_MIN)
-    unsigned long long* counters[2];          // per table: [0] end <= start, [1] end < start (the layout's observe slots)
-    unsigned long long* max_width[2];         // per table: widest interval
-    int* err;                                 // sticky flags ([1]: a coordinate outside [-2^30, 2^31 - 4])
-    uint32_t cap;
-};
-struct ObserveAcc {
-    unsigned int degenerate = 0, negative = 0;
-    long long widest = 0;
-    bool bad = false;
-};
-// extents by cache entry in shared memory (read-before-atomic: after the first few rows almost no row improves a bound);
-// rows resolved through the global table only fold into the per-slot arrays directly
-__device__ __forceinline__ void observe_fold(long long* __restrict__ lohi_slot, uint32_t cap, int32_t* s_lo, int32_t* s_hi, int32_t sadj,
-                                             int32_t eadj, int centry, uint32_t slot, int32_t s0, int32_t e0, ObserveAcc& acc) {
-    const long long s = (long long)s0 + sadj, e = (long long)e0 + eadj;
-    if (e - s > acc.widest) acc.widest = e - s;
-    const long long lo = s < e ? s : e, hi = s < e ? e : s;
-    if (lo < -(1ll << 30) || hi > (1ll << 31) - 4) {
-        acc.bad = true;
-        return;
-    }
-    acc.degenerate += e <= s;
-    acc.negative += e < s;
-    if (centry >= 0) {
-        if ((int32_t)lo < s_lo[centry]) atomicMin(&s_lo[centry], (int32_t)lo);
-        if ((int32_t)hi > s_hi[centry]) atomicMax(&s_hi[centry], (int32_t)hi);
-    } else if (slot < cap) {
-        if (lo < *(volatile long long*)&lohi_slot[slot]) atomicMin(&lohi_slot[slot], lo);
-        if (hi > *(volatile long long*)&lohi_slot[cap + slot]) atomicMax(&lohi_slot[cap + slot], hi);
-    }
-}
-// folds a thread's accumulators into the table's counters (warp-aggregated) and clears them
-__device__ __forceinline__ void observe_flush(ObserveAcc& acc, unsigned long long* __restrict__ counters, unsigned long long* __restrict__ max_width,
-                                              int* __restrict__ err) {
-    if (acc.bad) err[1] = 1;
-    long long widest = acc.widest;
-#pragma unroll
-    for (int d = 16; d > 0; d >>= 1) widest = max(widest, __shfl_xor_sync(FULL_MASK, widest, d));
-    if (lane_id() == 0 && widest > 0 && (unsigned long long)widest > *(volatile unsigned long long*)max_width)
-        atomicMax(max_width, (unsigned long long)widest);
-    if (__any_sync(FULL_MASK, acc.degenerate != 0)) {
-        const unsigned int dg = warp_reduce_add(acc.degenerate), ng = warp_reduce_add(acc.negative);
-        if (lane_id() == 0) {
-            atomicAdd(&counters[0], (unsigned long long)dg);
-            if (ng) atomicAdd(&counters[1], (unsigned long long)ng);
-        }
-    }
-    acc = ObserveAcc();
-}
-
-// OBSERVE: the same pass also reads the rows' start / end and folds them into per-slot coordinate extents, the
-// degenerate-row counters and the widest interval — what the separate layout-observe pass over both tables computed
-// (one read of 17 B/row instead of 9 + 12).
-template <bool OBSERVE>
-__global__ void __launch_bounds__(DI_THREADS, 5)   // shared memory (43.6 KB) admits five CTAs per SM: 48 registers each
+__global__ void __launch_bounds__(DI_THREADS)
 dict_insert_kernel(StrTable A, StrTable B, unsigned long long* __restrict__ slots, uint32_t cap_mask,
-                   int32_t* __restrict__ slot_a, int32_t* __restrict__ slot_b, unsigned int* __restrict__ n_distinct, DictObserve O) {
+                   int32_t* __restrict__ slot_a, int32_t* __restrict__ slot_b, unsigned int* __restrict__ n_distinct) {
     extern __shared__ __align__(16) uint8_t s_dyn[];
     DictStage* stage = reinterpret_cast<DictStage*>(s_dyn);                 // two stages: one being read, one in flight
     DictCache& cache = *reinterpret_cast<DictCache*>(s_dyn + 2 * sizeof(DictStage));
-    __shared__ int32_t s_lo[OBSERVE ? DI_CACHE : 1], s_hi[OBSERVE ? DI_CACHE : 1];
-    ObserveAcc acc;            // of the table the CTA is currently in: chunks come in ascending order, so it changes at most once
-    bool acc_in_b = false;
 
-    for (int i = threadIdx.x; i < DI_CACHE; i += DI_THREADS) {
-        cache.meta[i] = DI_EMPTY;
-        if (OBSERVE) {
-            s_lo[i] = INT32_MAX;
-            s_hi[i] = INT32_MIN;
-        }
-    }
+    for (int i = threadIdx.x; i < DI_CACHE; i += DI_THREADS) cache.meta[i] = DI_EMPTY;
     const int chunks_a = (int)((A.n + DI_ROWS - 1) / DI_ROWS), chunks_b = (int)((B.n + DI_ROWS - 1) / DI_ROWS);
     const int total = chunks_a + chunks_b, stride = gridDim.x;
     int chunk = blockIdx.x;
@@ -294,10 +218,6 @@ dict_insert_kernel(StrTable A, StrTable B, unsigned long long* __restrict__ slot
     DictChunk nxt = dict_chunk(A, B, chunk + stride, chunks_a, total);
     for (int it = 0; cur.valid; it++, chunk += stride) {
         DictStage& st = stage[it & 1];
-        if (OBSERVE && cur.in_b != acc_in_b) {                  // the CTA moves on to table B: hand in table A's counters
-            observe_flush(acc, O.counters[0], O.max_width[0], O.err);
-            acc_in_b = true;
-        }
         dict_stage_async(A, B, nxt, stage[(it & 1) ^ 1]);       // that stage was released by the barrier ending the previous iteration
         cp_async_commit();
         const DictChunk after = dict_chunk(A, B, chunk + 2 * stride, chunks_a, total);   // its two scalar loads overlap this chunk's work
@@ -324,57 +244,33 @@ dict_insert_kernel(StrTable A, StrTable B, unsigned long long* __restrict__ slot
             const int k = threadIdx.x * 4;
             const int4 o4 = reinterpret_cast<const int4*>(st.offs)[threadIdx.x];
             const int32_t o[5] = {o4.x, o4.y, o4.z, o4.w, st.offs[k + 4]};
-            int32_t res[4], ce[4];
-            int32_t sv[4] = {0, 0, 0, 0}, ev[4] = {0, 0, 0, 0};
-            const int32_t sadj = cur.in_b ? O.sadj[1] : O.sadj[0], eadj = cur.in_b ? O.eadj[1] : O.eadj[0];
-            if (OBSERVE) {   // the rows' coordinates: issued before the name look-ups so that their latency hides behind them
-                const int32_t* sp = (cur.in_b ? O.start[1] : O.start[0]) + r0 + k;
-                const int32_t* ep = (cur.in_b ? O.end[1] : O.end[0]) + r0 + k;
-                if (((reinterpret_cast<uintptr_t>(sp) | reinterpret_cast<uintptr_t>(ep)) & 15) == 0) {
-                    const int4 s4 = __ldg(reinterpret_cast<const int4*>(sp)), e4 = __ldg(reinterpret_cast<const int4*>(ep));
-                    sv[0] = s4.x; sv[1] = s4.y; sv[2] = s4.z; sv[3] = s4.w;
-                    ev[0] = e4.x; ev[1] = e4.y; ev[2] = e4.z; ev[3] = e4.w;
-                } else {
-#pragma unroll
-                    for (int q = 0; q < 4; q++) {
-                        sv[q] = __ldg(sp + q);
-                        ev[q] = __ldg(ep + q);
-                    }
-                }
-            }
+            int32_t res[4];
 #pragma unroll
             for (int q = 0; q < 4; q++) {
                 const int len = o[q + 1] - o[q];
-                ce[q] = -1;
                 if (len <= 16) {
                     uint64_t w0, w1;
                     staged_name(st.bytes, o[q] - a0, len, w0, w1);
-                    res[q] = (int32_t)cached_resolve(cache, A, B, slots, cap_mask, T.bytes + o[q], w0, w1, len, g0 + k + q, n_distinct,
-                                                     OBSERVE ? &ce[q] : nullptr);
+                    res[q] = (int32_t)cached_resolve(cache, A, B, slots, cap_mask, T.bytes + o[q], w0, w1, len, g0 + k + q, n_distinct);
                 } else {
                     const uint8_t* sp = T.bytes + o[q];
                     res[q] = (int32_t)global_resolve(A, B, slots, cap_mask, sp, len, hash_global_name(sp, len), g0 + k + q, n_distinct);
                 }
-                if (OBSERVE) observe_fold(O.lohi_slot, O.cap, s_lo, s_hi, sadj, eadj, ce[q], (uint32_t)res[q], sv[q], ev[q], acc);
             }
             reinterpret_cast<int4*>(out)[threadIdx.x] = make_int4(res[0], res[1], res[2], res[3]);
         } else {
             for (int k = threadIdx.x; k < rows; k += DI_THREADS) {
                 const int32_t o = st.offs[k], len = st.offs[k + 1] - o;
                 uint32_t slot;
-                int ce = -1;
                 if (staged && len <= 16) {
                     uint64_t w0, w1;
                     staged_name(st.bytes, o - a0, len, w0, w1);
-                    slot = cached_resolve(cache, A, B, slots, cap_mask, T.bytes + o, w0, w1, len, g0 + k, n_distinct, OBSERVE ? &ce : nullptr);
+                    slot = cached_resolve(cache, A, B, slots, cap_mask, T.bytes + o, w0, w1, len, g0 + k, n_distinct);
                 } else {
                     const uint8_t* sp = T.bytes + o;
                     slot = global_resolve(A, B, slots, cap_mask, sp, len, hash_global_name(sp, len), g0 + k, n_distinct);
                 }
                 out[k] = (int32_t)slot;
-                if (OBSERVE)
-                    observe_fold(O.lohi_slot, O.cap, s_lo, s_hi, cur.in_b ? O.sadj[1] : O.sadj[0], cur.in_b ? O.eadj[1] : O.eadj[0], ce, slot,
-                                 (cur.in_b ? O.start[1] : O.start[0])[r0 + k], (cur.in_b ? O.end[1] : O.end[0])[r0 + k], acc);
             }
         }
         __syncthreads();   // this stage may be refilled from the next iteration on
@@ -382,18 +278,6 @@ dict_insert_kernel(StrTable A, StrTable B, unsigned long long* __restrict__ slot
         nxt = after;
     }
     cp_async_wait<0>();
-    if (OBSERVE) {
-        __syncthreads();
-        for (int i = threadIdx.x; i < DI_CACHE; i += DI_THREADS) {   // per-entry extents -> per-slot extents
-            const uint32_t v = cache.meta[i];
-            if (v == DI_EMPTY || v == DI_PENDING) continue;
-            const uint32_t slot = v & DI_SLOT_MASK;
-            if (slot >= O.cap) continue;
-            if (s_lo[i] != INT32_MAX) atomicMin(&O.lohi_slot[slot], (long long)s_lo[i]);
-            if (s_hi[i] != INT32_MIN) atomicMax(&O.lohi_slot[O.cap + slot], (long long)s_hi[i]);
-        }
-        observe_flush(acc, acc_in_b ? O.counters[1] : O.counters[0], acc_in_b ? O.max_width[1] : O.max_width[0], O.err);
-    }
 }
 
 constexpr size_t DI_SMEM = 2 * sizeof(DictStage) + sizeof(DictCache);
@@ -471,26 +355,6 @@ dict_rank_kernel(const unsigned long long* __restrict__ cursor /* [0] bytes [1] 
     ent_rank[e] = rank;
 }
 
-__global__ void dict_lohi_init_kernel(long long* lohi_slot, uint32_t cap) {
-    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < cap) {
-        lohi_slot[i] = INT64_MAX;
-        lohi_slot[cap + i] = INT64_MIN;
-    }
-}
-
-// per-slot extents (fused encode + observe pass) -> per-code extents of the layout, through the device-side ranking
-__global__ void __launch_bounds__(DR_MAX)
-dict_slot_extents_kernel(const unsigned long long* __restrict__ cursor, const int32_t* __restrict__ ent, const int32_t* __restrict__ ent_rank,
-                         const int* __restrict__ ok_flag, const long long* __restrict__ lohi_slot, uint32_t cap, long long* __restrict__ lohi_code,
-                         int32_t n_codes) {
-    if (!*ok_flag || threadIdx.x >= cursor[1]) return;
-    const int32_t slot = ent[threadIdx.x], code = ent_rank[threadIdx.x];
-    if (code < 0 || code >= n_codes) return;
-    lohi_code[code] = lohi_slot[slot];
-    lohi_code[n_codes + code] = lohi_slot[cap + slot];
-}
-
 }  // namespace
 
 // ---- asynchronous encode: no host round trip ---------------------------------------------------------------------------
@@ -501,7 +365,6 @@ struct giqlb_dict_pending {
     uint8_t* name_buf = nullptr;
     int32_t *ent = nullptr, *slot2code = nullptr, *ent_rank = nullptr;
     int* ok_flag = nullptr;
-    unsigned long long* lohi_slot = nullptr;   // fused encode + observe: per-slot coordinate extents [2 * cap]
     uint32_t cap = 0, max_entries = 0, name_cap = 0;
 };
 
@@ -537,7 +400,7 @@ int giqlb_dict_encode_async(giqlb_ctx* ctx, const int32_t* offs_l, const uint8_t
     const unsigned grid = (unsigned)(chunks < cap_blocks ? chunks : cap_blocks);
     {
         PhaseSpan ps(ctx, GIQLB_PH_DICT);
-        dict_insert_kernel<false><<<grid, DI_THREADS, DI_SMEM, ctx->stream>>>(A, B, p->slots, p->cap - 1, codes_l, codes_r, n_distinct, DictObserve{});
+        dict_insert_kernel<<<grid, DI_THREADS, DI_SMEM, ctx->stream>>>(A, B, p->slots, p->cap - 1, codes_l, codes_r, n_distinct);
         dict_collect_kernel<<<(p->cap + 255) / 256, 256, 0, ctx->stream>>>(A, B, p->slots, p->cap, p->name_buf, p->name_cap, cursor, p->ent,
                                                                            p->max_entries);
         dict_rank_kernel<<<1, DR_MAX, 0, ctx->stream>>>(cursor, p->name_buf, p->name_cap, p->ent, p->max_entries, p->cap, p->slot2code,
@@ -566,86 +429,6 @@ int giqlb_dict_encode_async(giqlb_ctx* ctx, const int32_t* offs_l, const uint8_t
     ctx->stats.rows_in[1] = n_r;
     ctx->stats.rows_out = n_l + n_r;
     ctx->stats.algorithmic_bytes = 8 * (n_l + n_r);
-    *out = p;
-    return end_call(ctx);
-}
-
-// Fused variant for the one-call pipelines: the insert pass also observes the coordinate columns of both tables, and a
-// last small kernel hands the per-chromosome extents to `lay` (created for GIQLB_ASYNC_DICT_MAX_CODES codes), so no
-// separate layout-observe pass reads the tables.  The parked table slots stay in codes_l / codes_r (translate them with
-// the tables of giqlb_dict_pending_tables).
-int giqlb_dict_encode_observe_async(giqlb_ctx* ctx, const giqlb_table_t* L, const giqlb_table_t* R, giqlb_layout* lay,
-                                    giqlb_dict_pending** out) {
-    *out = nullptr;
-    if (L->n + R->n == 0 || !ctx->h_stage || lay->finalized || lay->n_codes < DR_MAX) return GIQLB_ERR_INVALID;
-    if (((reinterpret_cast<uintptr_t>(L->codes) | reinterpret_cast<uintptr_t>(R->codes)) & 15) != 0) return GIQLB_ERR_INVALID;
-    if (lay->observed.size() + 2 > GIQLB_MAX_OBSERVED - 1) return GIQLB_ERR_INVALID;
-    begin_call(ctx);
-    giqlb_dict_pending* p = new (std::nothrow) giqlb_dict_pending();
-    if (!p) return GIQLB_ERR_NOMEM;
-    p->cap = 1u << 14;
-    p->max_entries = DR_MAX;
-    p->name_cap = 32768;
-    StrTable A{L->chrom_offsets, L->chrom_bytes, L->n}, B{R->chrom_offsets, R->chrom_bytes, R->n};
-    unsigned long long* cursor = reinterpret_cast<unsigned long long*>(ctx->d_scalars + 24);
-    unsigned int* n_distinct = reinterpret_cast<unsigned int*>(ctx->d_scalars + 26);
-    int st = dev_alloc(ctx, &p->slots, (size_t)p->cap);
-    if (st == GIQLB_OK) st = dev_alloc(ctx, &p->name_buf, p->name_cap);
-    if (st == GIQLB_OK) st = dev_alloc(ctx, &p->ent, 3 * (size_t)p->max_entries);
-    if (st == GIQLB_OK) st = dev_alloc(ctx, &p->slot2code, (size_t)p->cap);
-    if (st == GIQLB_OK) st = dev_alloc(ctx, &p->ent_rank, (size_t)p->max_entries);
-    if (st == GIQLB_OK) st = dev_alloc(ctx, &p->ok_flag, 4);
-    if (st == GIQLB_OK) st = dev_alloc(ctx, &p->lohi_slot, 2 * (size_t)p->cap);
-    if (st != GIQLB_OK) {
-        giqlb_dict_finish(ctx, p, nullptr, nullptr);
-        return st;
-    }
-    cudaMemsetAsync(p->slots, 0, (size_t)p->cap * 8, ctx->stream);
-    cudaMemsetAsync(p->slot2code, 0xFF, (size_t)p->cap * 4, ctx->stream);
-    cudaMemsetAsync(cursor, 0, 3 * 8, ctx->stream);
-    const size_t slot_l = lay->observed.size(), slot_r = slot_l + 1;
-    DictObserve O;
-    O.start[0] = L->start; O.start[1] = R->start;
-    O.end[0] = L->end; O.end[1] = R->end;
-    O.sadj[0] = L->start_adj; O.sadj[1] = R->start_adj;
-    O.eadj[0] = L->end_adj; O.eadj[1] = R->end_adj;
-    O.lohi_slot = reinterpret_cast<long long*>(p->lohi_slot);
-    O.counters[0] = lay->d_obs + 2 * slot_l; O.counters[1] = lay->d_obs + 2 * slot_r;
-    O.max_width[0] = lay->d_obs + 2 * GIQLB_MAX_OBSERVED + slot_l;
-    O.max_width[1] = lay->d_obs + 2 * GIQLB_MAX_OBSERVED + slot_r;
-    O.err = ctx->d_err;
-    O.cap = p->cap;
-    const int64_t chunks = ceil_div(L->n, DI_ROWS) + ceil_div(R->n, DI_ROWS), cap_blocks = (int64_t)ctx->sm_count * 5;
-    const unsigned grid = (unsigned)(chunks < cap_blocks ? chunks : cap_blocks);
-    {
-        PhaseSpan ps(ctx, GIQLB_PH_DICT);
-        dict_lohi_init_kernel<<<(p->cap + 255) / 256, 256, 0, ctx->stream>>>(reinterpret_cast<long long*>(p->lohi_slot), p->cap);
-        dict_insert_kernel<true><<<grid, DI_THREADS, DI_SMEM, ctx->stream>>>(A, B, p->slots, p->cap - 1, L->codes, R->codes, n_distinct, O);
-        dict_collect_kernel<<<(p->cap + 255) / 256, 256, 0, ctx->stream>>>(A, B, p->slots, p->cap, p->name_buf, p->name_cap, cursor, p->ent,
-                                                                           p->max_entries);
-        dict_rank_kernel<<<1, DR_MAX, 0, ctx->stream>>>(cursor, p->name_buf, p->name_cap, p->ent, p->max_entries, p->cap, p->slot2code,
-                                                        p->ent_rank, p->ok_flag);
-        dict_slot_extents_kernel<<<1, DR_MAX, 0, ctx->stream>>>(cursor, p->ent, p->ent_rank, p->ok_flag, reinterpret_cast<const long long*>(p->lohi_slot),
-                                                                p->cap, reinterpret_cast<long long*>(lay->d_lohi), lay->n_codes);
-        ctx->launches_this_call += 5;
-        ctx->stats.kernels_total += 5;
-    }
-    lay->observed.push_back({L->codes, L->n, L->start_adj, L->end_adj, -1, -1});
-    lay->observed.push_back({R->codes, R->n, R->start_adj, R->end_adj, -1, -1});
-    unsigned char* h = reinterpret_cast<unsigned char*>(ctx->h_stage);
-    cudaMemcpyAsync(h, cursor, 24, cudaMemcpyDeviceToHost, ctx->stream);
-    cudaMemcpyAsync(h + 32, p->ok_flag, 4, cudaMemcpyDeviceToHost, ctx->stream);
-    cudaMemcpyAsync(h + 64, p->ent, 3 * (size_t)p->max_entries * 4, cudaMemcpyDeviceToHost, ctx->stream);
-    cudaMemcpyAsync(h + 64 + 12 * (size_t)p->max_entries, p->ent_rank, (size_t)p->max_entries * 4, cudaMemcpyDeviceToHost, ctx->stream);
-    cudaMemcpyAsync(h + 64 + 16 * (size_t)p->max_entries, p->name_buf, p->name_cap, cudaMemcpyDeviceToHost, ctx->stream);
-    if (cudaGetLastError() != cudaSuccess) {
-        giqlb_dict_finish(ctx, p, nullptr, nullptr);
-        return giqlb_fail(ctx, GIQLB_ERR_CUDA, "dict_encode_observe_async: launch failed");
-    }
-    ctx->stats.rows_in[0] = L->n;
-    ctx->stats.rows_in[1] = R->n;
-    ctx->stats.rows_out = L->n + R->n;
-    ctx->stats.algorithmic_bytes = 16 * (L->n + R->n);
     *out = p;
     return end_call(ctx);
 }
@@ -681,7 +464,7 @@ int giqlb_dict_finish(giqlb_ctx* ctx, giqlb_dict_pending* p, giqlb_dict** dict_o
         }
     }
     dev_free(ctx, p->slots); dev_free(ctx, p->name_buf); dev_free(ctx, p->ent); dev_free(ctx, p->slot2code);
-    dev_free(ctx, p->ent_rank); dev_free(ctx, p->ok_flag); dev_free(ctx, p->lohi_slot);
+    dev_free(ctx, p->ent_rank); dev_free(ctx, p->ok_flag);
     delete p;
     return st;
 }
@@ -730,7 +513,7 @@ extern "C" int giqlb_dict_encode(giqlb_ctx* ctx, const int32_t* offs_l, const ui
         cudaMemsetAsync(cursor, 0, 3 * 8, ctx->stream);
         {
             PhaseSpan ps(ctx, GIQLB_PH_DICT);
-            dict_insert_kernel<false><<<grid, DI_THREADS, DI_SMEM, ctx->stream>>>(A, B, slots, cap - 1, codes_l, codes_r, n_distinct, DictObserve{});
+            dict_insert_kernel<<<grid, DI_THREADS, DI_SMEM, ctx->stream>>>(A, B, slots, cap - 1, codes_l, codes_r, n_distinct);
             dict_collect_kernel<<<(cap + 255) / 256, 256, 0, ctx->stream>>>(A, B, slots, cap, name_buf, name_cap, cursor, ent,
                                                                             (uint32_t)max_entries);
             ctx->launches_this_call += 2;

@@ -154,19 +154,16 @@ layout_finalize_kernel(const long long* __restrict__ lohi, int32_t n_codes, long
 }
 
 // linearised start key + linearised end (unsorted), degenerate-row counters
-// REMAP: `code` still holds the dictionary encoder's parked table slots (fused encode + observe schedule); they are
-// translated through slot2code here and written back, so no separate pass rewrites the column.
-template <bool HIST, bool REMAP = false>
+template <bool HIST>
 __global__ void __launch_bounds__(256)
-index_keygen_kernel(const int32_t* code, const int32_t* __restrict__ start,
+index_keygen_kernel(const int32_t* __restrict__ code, const int32_t* __restrict__ start,
                     const int32_t* __restrict__ end, const int32_t* __restrict__ rows /* nullable: row selection */,
                     int64_t n, int32_t n_codes, int32_t sadj, int32_t eadj,
                     const uint32_t* __restrict__ base, const int32_t* __restrict__ lo32,
                     const int32_t* __restrict__ hi32, uint32_t* __restrict__ gs, uint32_t* __restrict__ ge,
                     unsigned long long* __restrict__ counters /* [0] end<=start [1] end<start [2] outside layout */,
                     uint32_t* __restrict__ ghist /* nullable: [4][256] digit counts of the start keys, for the sort */,
-                    int* __restrict__ err, const int32_t* __restrict__ slot2code = nullptr, const int* __restrict__ ok_flag = nullptr) {
-    if (REMAP && !*ok_flag) return;
+                    int* __restrict__ err) {
     __shared__ uint32_t s_hist[HIST ? 4 : 1][256];
     if (HIST) {
         for (int i = threadIdx.x; i < 4 * 256; i += blockDim.x) (&s_hist[0][0])[i] = 0;
@@ -176,10 +173,6 @@ index_keygen_kernel(const int32_t* code, const int32_t* __restrict__ start,
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
         const int64_t r = rows ? (int64_t)rows[i] : i;
         int32_t c = code[r];
-        if (REMAP) {
-            c = __ldg(slot2code + c);
-            const_cast<int32_t*>(code)[r] = c;
-        }
         long long s = (long long)start[r] + sadj, e = (long long)end[r] + eadj;
         uint32_t ks = 0xffffffffu, ke = 0xffffffffu;
         if (c < 0 || c >= n_codes) {
@@ -275,6 +268,31 @@ struct OutScatterRow {
         }
     }
 };
+
+// Bucket directory of an ascending array in one coalesced pass: row j, the first row of its bucket run, fills every
+// entry from the bucket after its predecessor's up to its own (tab[b] = first position with a value >= b << shift);
+// the thread of j == n fills the tail with n.  Gaps of empty buckets are filled by the whole warp, 32 entries per step,
+// so one long gap does not serialise on a single thread.  Values beyond the directory fall into its last bucket.
+__global__ void __launch_bounds__(256)
+bucket_dir_kernel(const uint32_t* __restrict__ a, int64_t n, int shift, uint32_t stride, uint32_t* __restrict__ tab) {
+    const long long last_entry = (long long)stride - 1, last_bucket = (long long)stride - 2;
+    const int64_t span = ((n + 1 + 31) / 32) * 32;                     // whole warps stay in the loop together
+    for (int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; j < span; j += (int64_t)gridDim.x * blockDim.x) {
+        long long first = 1, last = 0;                                // empty range for the padding lanes
+        if (j <= n) {
+            first = j == 0 ? 0 : min((long long)(a[j - 1] >> shift), last_bucket) + 1;
+            last = j == n ? last_entry : min((long long)(a[j] >> shift), last_bucket);
+        }
+        uint32_t todo = __ballot_sync(FULL_MASK, last >= first);
+        while (todo) {
+            const int src = __ffs(todo) - 1;
+            todo &= todo - 1;
+            const long long f = __shfl_sync(FULL_MASK, first, src), l = __shfl_sync(FULL_MASK, last, src);
+            const uint32_t v = (uint32_t)__shfl_sync(FULL_MASK, (long long)j, src);
+            for (long long b = f + lane_id(); b <= l; b += 32) tab[b] = v;
+        }
+    }
+}
 
 inline int grid_for(const giqlb_ctx* ctx, int64_t n, int threads, int per_sm) {
     int64_t want = ceil_div(n, threads);
@@ -453,6 +471,10 @@ extern "C" int giqlb_index_free(giqlb_ctx* ctx, giqlb_index* ix) {
         dev_free(ctx, ix->pos_by_end);
         dev_free(ctx, ix->d_block_off);
         dev_free(ctx, ix->d_counters);
+        dev_free(ctx, ix->dir_gs);
+        dev_free(ctx, ix->dir_pmax);
+        dev_free(ctx, ix->dir_ges);
+        dev_free(ctx, ix->d_dir_slot);
     }
     delete ix;
     return GIQLB_OK;
@@ -498,7 +520,7 @@ extern "C" int giqlb_index_build_rows(giqlb_ctx* ctx, const giqlb_layout* lay, c
 // ownership of its buffers.
 int giqlb_index_build_impl(giqlb_ctx* ctx, const giqlb_layout* lay, const int32_t* code, const int32_t* start,
                            const int32_t* end, const uint8_t* strand, const int32_t* rows, int64_t n, int32_t start_adj,
-                           int32_t end_adj, int flags, giqlb_prekeyed* pre, giqlb_index** out, const giqlb_code_remap* remap) {
+                           int32_t end_adj, int flags, giqlb_prekeyed* pre, giqlb_index** out) {
     if (!ctx || !lay || !out || n < 0 || (n > 0 && (!code || !start || !end)))
         return giqlb_fail(ctx, GIQLB_ERR_INVALID, "index_build: bad argument");
     if (!lay->finalized) return giqlb_fail(ctx, GIQLB_ERR_INVALID, "index_build: layout not finalized");
@@ -554,11 +576,7 @@ int giqlb_index_build_impl(giqlb_ctx* ctx, const giqlb_layout* lay, const int32_
         int result_in_b = 0;
         if (!pre) {
         PhaseSpan ps(ctx, GIQLB_PH_KEYGEN);
-        if (remap && !rows)
-            index_keygen_kernel<false, true><<<grid_for(ctx, n, 256 * 4, 8), 256, 0, ctx->stream>>>(
-                code, start, end, nullptr, n, lay->n_codes, start_adj, end_adj, lay->d_base, lay->d_lo32, lay->d_hi32, ka, ge_u, counters, nullptr, ctx->d_err,
-                remap->slot2code, remap->ok_flag);
-        else if (key_hist)
+        if (key_hist)
             index_keygen_kernel<true><<<grid_for(ctx, n, 256 * 4, 8), 256, 0, ctx->stream>>>(
                 code, start, end, rows, n, lay->n_codes, start_adj, end_adj, lay->d_base, lay->d_lo32, lay->d_hi32, ka, ge_u, counters, key_hist, ctx->d_err);
         else
@@ -703,6 +721,8 @@ extern "C" int giqlb_index_group_by_strand(giqlb_ctx* ctx, giqlb_index* ix) {
         // derived arrays are stale now
         dev_free(ctx, ix->pmax); dev_free(ctx, ix->ge_sorted); dev_free(ctx, ix->pos_by_end);
         ix->pmax = nullptr; ix->ge_sorted = nullptr; ix->pos_by_end = nullptr;
+        dev_free(ctx, ix->dir_gs); dev_free(ctx, ix->dir_pmax); dev_free(ctx, ix->dir_ges); dev_free(ctx, ix->d_dir_slot);
+        ix->dir_gs = ix->dir_pmax = ix->dir_ges = nullptr; ix->d_dir_slot = nullptr;
     }
     GIQLB_TRY(dev_alloc(ctx, &ix->d_block_off, (size_t)GIQLB_MAX_STRAND_CODES + 1));
     CUDA_TRY(ctx, cudaMemcpyAsync(ix->d_block_off, ix->block_off, sizeof(ix->block_off), cudaMemcpyHostToDevice, ctx->stream));
@@ -751,6 +771,46 @@ int giqlb_index_ensure_end_sorted(giqlb_ctx* ctx, giqlb_index* ix) {
         ix->ge_sorted = nullptr; ix->pos_by_end = nullptr;
     }
     return st;
+}
+
+// Bucket directories of the index's ascending arrays, one slot per strand block that holds rows.  The bucket width is
+// chosen so that there are about as many buckets as rows (at most 2^24): a search through the directory reads two
+// adjacent table entries and then a handful of rows, all in one or two cache lines.
+int giqlb_index_ensure_dirs(giqlb_ctx* ctx, giqlb_index* ix, bool want_pmax, bool want_ges) {
+    if ((want_pmax && !ix->pmax) || (want_ges && !ix->ge_sorted)) return giqlb_fail(ctx, GIQLB_ERR_INVALID, "index dirs: derived array missing");
+    const int nb = ix->grouped_by_strand ? ix->n_blocks : 1;
+    int slots = 0;
+    int32_t h_slot[GIQLB_MAX_STRAND_CODES];
+    for (int b = 0; b < GIQLB_MAX_STRAND_CODES; b++) {
+        const bool has = b < nb && (ix->grouped_by_strand ? ix->block_off[b + 1] > ix->block_off[b] : ix->n > 0);
+        h_slot[b] = has ? slots++ : -1;
+    }
+    if (!ix->d_dir_slot) {
+        int bits = 1;
+        while (bits < 24 && (1ll << bits) < ix->n) bits++;
+        ix->dir_shift = 32 - bits;
+        const uint64_t extent = ix->layout && ix->layout->total_extent ? ix->layout->total_extent : 0xffffffffull;
+        ix->dir_stride = (uint32_t)((extent > 0xffffffffull ? 0xffffffffull : extent) >> ix->dir_shift) + 2u;
+        GIQLB_TRY(dev_alloc(ctx, &ix->d_dir_slot, (size_t)GIQLB_MAX_STRAND_CODES));
+        memcpy(ctx->h_stage, h_slot, sizeof(h_slot));   // pinned staging buffer: the copy below is asynchronous
+        CUDA_TRY(ctx, cudaMemcpyAsync(ix->d_dir_slot, ctx->h_stage, sizeof(h_slot), cudaMemcpyHostToDevice, ctx->stream));
+        CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));   // the staging buffer is reused by later calls
+    }
+    struct Want { bool on; uint32_t** tab; const uint32_t* arr; } wants[3] = {
+        {true, &ix->dir_gs, ix->gs}, {want_pmax, &ix->dir_pmax, ix->pmax}, {want_ges, &ix->dir_ges, ix->ge_sorted}};
+    for (auto& w : wants) {
+        if (!w.on || *w.tab || slots == 0) continue;
+        GIQLB_TRY(dev_alloc(ctx, w.tab, (size_t)slots * ix->dir_stride));
+        PhaseSpan ps(ctx, GIQLB_PH_PROBE);
+        for (int b = 0; b < nb; b++) {
+            if (h_slot[b] < 0) continue;
+            const int64_t lo = ix->grouped_by_strand ? ix->block_off[b] : 0, hi = ix->grouped_by_strand ? ix->block_off[b + 1] : ix->n;
+            bucket_dir_kernel<<<grid_for(ctx, hi - lo + 1, 256, 16), 256, 0, ctx->stream>>>(w.arr + lo, hi - lo, ix->dir_shift, ix->dir_stride,
+                                                                                              *w.tab + (size_t)h_slot[b] * ix->dir_stride);
+            LAUNCH_CHECK(ctx);
+        }
+    }
+    return GIQLB_OK;
 }
 
 // Fetches the degenerate-row counts of up to two indexes in ONE round trip (no-op when already known).

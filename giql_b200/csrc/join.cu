@@ -436,13 +436,13 @@ struct __align__(16) TileSmem {
 };
 
 struct TileSlots {                           // fused kernel (tiles of <= J_BIG pairs): slot -> item lookup over the NON-EMPTY items
-    uint2 ent[JT + 2];                       // merge order: .x = local exclusive output offset (bits 0..13) | class (bit 14) |
+    uint2 ent[JT + 2];                       // merge order: .x = local exclusive output offset (bits 0..14) | class (bit 15) |
                                              // (index of the run's first row in the row-id windows - offset) as int16 (bits 16..31),
                                              // .y = the item's OWN row id (looked up once per item, not once per pair); then a sentinel
     uint16_t first_item[J_BIG / J_OPT + 2];  // non-empty item that owns the first slot of every J_OPT-slot chunk
 };
-constexpr uint32_t JE_OFF_MASK = 0x3FFFu, JE_CLASS_B = 0x4000u;
-static_assert(J_BIG < (int)JE_OFF_MASK, "a tile's local offsets must fit 14 bits");
+constexpr uint32_t JE_OFF_MASK = 0x7FFFu, JE_CLASS_B = 0x8000u;
+static_assert(J_BIG < (int)JE_OFF_MASK, "a tile's local offsets must fit 15 bits");
 // Output staging window: one (left, right) row-id pair per slot, 8 bytes.  A thread of the expansion owns J_OPT = 8 consecutive
 // slots, so at step q the lanes of a half-warp (which share one 64-bit shared-memory transaction) would all hit the same two
 // banks.  XOR-ing the slot's low three bits with its 16-block number spreads every step over all banks, and keeps the flush's
@@ -1064,15 +1064,25 @@ join_emit_general_kernel(JoinSide L, JoinSide R, const uint32_t* __restrict__ pm
 }
 
 // ---- SEMI / ANTI and per-row counts, probing from the raw (unsorted) left columns --------------------
+// The left rows arrive in input order, so neighbouring threads search unrelated places of the index: a plain binary
+// search is ~20 dependent L2 round trips per row.  The searches go through the index's bucket directories instead (two
+// adjacent table entries, then a handful of rows of one or two cache lines).
+struct ProbeDirs {
+    const uint32_t* gs;    // directory over rgs
+    const uint32_t* ges;   // directory over rge_sorted (count probes of proper right tables)
+    int shift;
+    uint32_t last;         // last bucket of a directory (entries - 2)
+};
+
 __global__ void __launch_bounds__(256)
-probe_exists_kernel(ProbeCols P, const uint32_t* __restrict__ rgs, const uint32_t* __restrict__ pmax, int64_t nr,
+probe_exists_kernel(ProbeCols P, const uint32_t* __restrict__ rgs, const uint32_t* __restrict__ pmax, int64_t nr, ProbeDirs D,
                     uint8_t* __restrict__ exists) {
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < P.n; i += (int64_t)gridDim.x * blockDim.x) {
         uint32_t gs, ge;
         uint8_t e = 0;
         if (nr > 0 && probe_linearise(P, i, gs, ge)) {
-            int64_t ub = lower_bound_dev<uint32_t, int64_t>(rgs, 0, nr, ge);   // rows with r.gs < l.ge
-            e = ub > 0 && __ldg(pmax + ub - 1) > gs;                           // ... one of which ends after l.gs
+            const int64_t ub = dir_lower_bound(D.gs, D.shift, D.last, rgs, ge);          // rows with r.gs < l.ge
+            e = ub > 0 && __ldg(pmax + ub - 1) > gs;                             // ... one of which ends after l.gs
         }
         exists[i] = e;
     }
@@ -1081,15 +1091,15 @@ probe_exists_kernel(ProbeCols P, const uint32_t* __restrict__ rgs, const uint32_
 __global__ void __launch_bounds__(256)
 probe_count_kernel(ProbeCols P, const uint32_t* __restrict__ rgs, const uint32_t* __restrict__ rge,
                    const uint32_t* __restrict__ pmax, const uint32_t* __restrict__ rge_sorted, int64_t nr,
-                   int r_has_degenerate, long long* __restrict__ counts) {
+                   int r_has_degenerate, ProbeDirs D, long long* __restrict__ counts) {
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < P.n; i += (int64_t)gridDim.x * blockDim.x) {
         uint32_t gs, ge;
         long long c = 0;
         if (nr > 0 && probe_linearise(P, i, gs, ge)) {
-            int64_t ub = lower_bound_dev<uint32_t, int64_t>(rgs, 0, nr, ge);
+            const int64_t ub = dir_lower_bound(D.gs, D.shift, D.last, rgs, ge);
             if (!r_has_degenerate && ge >= gs) {
                 // #{r.gs < l.ge} - #{r.ge <= l.gs}: every r ending at or before l.gs also starts before l.ge
-                c = ub - upper_bound_dev<uint32_t, int64_t>(rge_sorted, 0, nr, gs);
+                c = ub - dir_upper_bound(D.ges, D.shift, D.last, rge_sorted, gs);
             } else {
                 int64_t lb = upper_bound_dev<uint32_t, int64_t>(pmax, 0, ub, gs);
                 for (int64_t k = lb; k < ub; k++) c += __ldg(rge + k) > gs;
@@ -1348,11 +1358,13 @@ extern "C" int giqlb_intersects_exists(giqlb_ctx* ctx, const giqlb_layout* lay, 
     ProbeCols P;
     GIQLB_TRY(probe_cols(ctx, lay, code, start, end, n, start_adj, end_adj, &P));
     GIQLB_TRY(giqlb_index_ensure_pmax(ctx, R));
+    if (n > 0 && R->n > 0) GIQLB_TRY(giqlb_index_ensure_dirs(ctx, R, false, false));
     if (n > 0) {
         int64_t blocks = ceil_div(n, 256 * 4);
         int64_t cap = (int64_t)ctx->sm_count * 16;
         PhaseSpan ps(ctx, GIQLB_PH_PROBE);
-        probe_exists_kernel<<<(unsigned)(blocks < cap ? blocks : cap), 256, 0, ctx->stream>>>(P, R->gs, R->pmax, R->n, exists_by_row);
+        probe_exists_kernel<<<(unsigned)(blocks < cap ? blocks : cap), 256, 0, ctx->stream>>>(P, R->gs, R->pmax, R->n, ProbeDirs{R->dir_gs, nullptr, R->dir_shift, R->dir_stride - 2},
+                                                                                                exists_by_row);
         LAUNCH_CHECK(ctx);
     }
     ctx->stats.rows_in[0] = n;
@@ -1375,12 +1387,13 @@ extern "C" int giqlb_intersects_count_rows(giqlb_ctx* ctx, const giqlb_layout* l
     GIQLB_TRY(giqlb_index_resolve(ctx, R, nullptr));
     const int r_deg = R->n_degenerate > 0;
     if (!r_deg) GIQLB_TRY(giqlb_index_ensure_end_sorted(ctx, R));
+    if (n > 0 && R->n > 0) GIQLB_TRY(giqlb_index_ensure_dirs(ctx, R, false, !r_deg));
     if (n > 0) {
         int64_t blocks = ceil_div(n, 256 * 4);
         int64_t cap = (int64_t)ctx->sm_count * 16;
         PhaseSpan ps(ctx, GIQLB_PH_PROBE);
         probe_count_kernel<<<(unsigned)(blocks < cap ? blocks : cap), 256, 0, ctx->stream>>>(
-            P, R->gs, R->ge, R->pmax, R->ge_sorted, R->n, r_deg, (long long*)counts_by_row);
+            P, R->gs, R->ge, R->pmax, R->ge_sorted, R->n, r_deg, ProbeDirs{R->dir_gs, R->dir_ges, R->dir_shift, R->dir_stride - 2}, (long long*)counts_by_row);
         LAUNCH_CHECK(ctx);
     }
     ctx->stats.rows_in[0] = n;

@@ -36,6 +36,13 @@ struct TargetView {
     const int32_t* pos_by_end;   // block-relative position of each sorted end
     const int64_t* block_off;    // device [257]; nullptr when not grouped
     int64_t n;
+    // bucket directories over gs / pmax / ge_sorted of every strand block (giqlb_index_ensure_dirs)
+    const uint32_t* dir_gs;
+    const uint32_t* dir_pmax;
+    const uint32_t* dir_ges;
+    const int32_t* dir_slot;
+    int dir_shift;
+    uint32_t dir_stride;
 };
 
 struct NearestArgs {
@@ -45,23 +52,31 @@ struct NearestArgs {
     int signed_;
 };
 
+// `order` (nullable): the query rows sorted by linear start.  Thread x then handles row order[x], so neighbouring threads
+// search neighbouring places of the target index (their loads share cache lines) instead of ~80 unrelated L2 round trips
+// each; its k result slots are x * k .. x * k + k - 1, written straight into the output arrays (with every query row
+// yielding exactly k rows — the common case — they need no compaction afterwards).
 __global__ void __launch_bounds__(128)
-nearest_kernel(ProbeCols Q, const uint8_t* __restrict__ q_strand, TargetView T, NearestArgs A,
-               int32_t* __restrict__ tmp_t, int32_t* __restrict__ tmp_d, uint8_t* __restrict__ tmp_v,
-               uint32_t* __restrict__ cnt) {
-    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < Q.n; i += (int64_t)gridDim.x * blockDim.x) {
+nearest_kernel(ProbeCols Q, const uint8_t* __restrict__ q_strand, const uint32_t* __restrict__ order, TargetView T, NearestArgs A,
+               int32_t* __restrict__ tmp_q, int32_t* __restrict__ tmp_t, int32_t* __restrict__ tmp_d, uint8_t* __restrict__ tmp_v,
+               uint32_t* __restrict__ cnt, unsigned long long* __restrict__ total) {
+    unsigned long long emitted = 0;
+    for (int64_t x = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; x < Q.n; x += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t i = order ? (int64_t)order[x] : x;
         uint32_t n_out = 0;
-        const int64_t slot0 = i * A.k;
+        const int64_t slot0 = x * A.k;
         uint32_t qs_lin, qe_lin;
         const uint8_t sq = A.stranded ? q_strand[i] : (uint8_t)GIQLB_STRAND_PLUS;
         int64_t blo = 0, bhi = T.n;
         bool any = T.n > 0 && probe_linearise(Q, i, qs_lin, qe_lin);
+        int slot = 0;
         if (any && A.stranded) {
             if (sq == GIQLB_STRAND_NULL) any = false;   // NULL = anything is never true
             else {
                 blo = T.block_off[sq];
                 bhi = T.block_off[sq + 1];
                 any = bhi > blo;
+                slot = any ? T.dir_slot[sq] : 0;
             }
         }
         if (any) {
@@ -73,6 +88,8 @@ nearest_kernel(ProbeCols Q, const uint8_t* __restrict__ q_strand, TargetView T, 
             const uint32_t* ge = T.ge + blo;
             const int32_t* rid = T.rid + blo;
             const int64_t nb = bhi - blo;
+            const uint32_t* dgs = T.dir_gs + (size_t)slot * T.dir_stride;
+            const uint32_t dlast = T.dir_stride - 2;
             // canonical coordinate of a linear one on chromosome c
             auto canon = [&](uint32_t g) { return lo_c + (long long)g - (long long)cb_lo - 1; };
             const bool null_dist = A.stranded && (sq == GIQLB_STRAND_DOT || sq == GIQLB_STRAND_QMARK);
@@ -80,23 +97,24 @@ nearest_kernel(ProbeCols Q, const uint8_t* __restrict__ q_strand, TargetView T, 
                 long long d = 0;
                 bool ok = !null_dist && giqlb_distance_dev(qs, qe, sq, canon(gs[pos]), canon(ge[pos]), sq, A.stranded != 0,
                                                            A.signed_ != 0, &d);
+                tmp_q[slot0 + n_out] = (int32_t)i;
                 tmp_t[slot0 + n_out] = rid[pos];
                 tmp_d[slot0 + n_out] = ok ? (int32_t)d : 0;
                 tmp_v[slot0 + n_out] = ok ? 1 : 0;
                 n_out++;
             };
-            const int64_t ub = lower_bound_dev<uint32_t, int64_t>(gs, 0, nb, qe_lin);   // first row with t.start >= q.end
+            const int64_t ub = dir_lower_bound(dgs, T.dir_shift, dlast, gs, qe_lin);   // first row with t.start >= q.end
             if (null_dist) {
                 // every distance is NULL: ORDER BY degenerates to (start, end) over the chromosome's rows of the block,
                 // and ABS(NULL) <= max_distance keeps nothing (nearest.py:330-331)
                 if (A.max_distance < 0) {
-                    int64_t j = upper_bound_dev<uint32_t, int64_t>(gs, 0, nb, cb_lo);
+                    int64_t j = dir_upper_bound(dgs, T.dir_shift, dlast, gs, cb_lo);
                     for (; j < nb && n_out < (uint32_t)A.k && gs[j] < cb_hi; j++) emit(j);
                 }
             } else {
                 // 1. overlaps, in index order
                 const uint32_t* pmax = T.pmax + blo;
-                int64_t j = upper_bound_dev<uint32_t, int64_t>(pmax, 0, ub, qs_lin);   // first row whose running max end > q.start
+                int64_t j = min(ub, dir_upper_bound(T.dir_pmax + (size_t)slot * T.dir_stride, T.dir_shift, dlast, pmax, qs_lin));   // first row whose running max end > q.start
                 for (; j < ub && n_out < (uint32_t)A.k; j++)
                     if (ge[j] > qs_lin) emit(j);
                 // 2. merge of the upstream and downstream streams
@@ -104,7 +122,8 @@ nearest_kernel(ProbeCols Q, const uint8_t* __restrict__ q_strand, TargetView T, 
                     const uint32_t* ges = T.ge_sorted + blo;
                     const int32_t* pbe = T.pos_by_end + blo;
                     int64_t dn = ub;                                                                  // downstream cursor
-                    int64_t up_hi = upper_bound_dev<uint32_t, int64_t>(ges, 0, nb, qs_lin);          // rows with t.end <= q.start: [.., up_hi)
+                    const uint32_t* dges = T.dir_ges + (size_t)slot * T.dir_stride;
+                    int64_t up_hi = dir_upper_bound(dges, T.dir_shift, dlast, ges, qs_lin);                  // rows with t.end <= q.start: [.., up_hi)
                     int64_t grp_lo = up_hi, grp_cur = up_hi;                                          // current tie group [grp_cur, up_hi) is empty
                     const long long maxd = A.max_distance;
                     while (n_out < (uint32_t)A.k) {
@@ -126,7 +145,7 @@ nearest_kernel(ProbeCols Q, const uint8_t* __restrict__ q_strand, TargetView T, 
                             const uint32_t v = ges[grp_lo - 1];
                             if (v <= cb_lo) break;   // left the chromosome
                             up_hi = grp_lo;
-                            grp_lo = lower_bound_dev<uint32_t, int64_t>(ges, 0, up_hi, v);
+                            grp_lo = dir_lower_bound(dges, T.dir_shift, dlast, ges, v);
                             grp_cur = grp_lo;
                         }
                         if (dn < nb && gs[dn] < cb_hi) m_dn = canon(gs[dn]) - qe + 1;
@@ -146,15 +165,28 @@ nearest_kernel(ProbeCols Q, const uint8_t* __restrict__ q_strand, TargetView T, 
                 }
             }
         }
-        cnt[i] = n_out;
+        cnt[x] = n_out;
+        emitted += n_out;
     }
+    emitted = warp_reduce_add(emitted);
+    if (lane_id() == 0 && emitted) atomicAdd(total, emitted);
 }
 
 struct InCnt {
     const uint32_t* cnt;
     __device__ unsigned long long operator()(int64_t i) const { return cnt[i]; }
 };
+// linear start of every query row (clamped into its chromosome's guard cells; rows that cannot match sort last)
+__global__ void __launch_bounds__(256)
+nearest_query_keys_kernel(ProbeCols Q, uint32_t* __restrict__ keys) {
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < Q.n; i += (int64_t)gridDim.x * blockDim.x) {
+        uint32_t gs, ge;
+        keys[i] = probe_linearise(Q, i, gs, ge) ? gs : 0xffffffffu;
+    }
+}
+
 struct OutCompactNearest {
+    const int32_t* tmp_q;
     const int32_t* tmp_t;
     const int32_t* tmp_d;
     const uint8_t* tmp_v;
@@ -165,7 +197,7 @@ struct OutCompactNearest {
     int64_t n;
     __device__ void operator()(int64_t i, unsigned long long excl, unsigned long long v) const {
         for (unsigned long long j = 0; j < v; j++) {
-            out_q[excl + j] = (int32_t)i;
+            out_q[excl + j] = tmp_q[i * k + j];
             out_t[excl + j] = tmp_t[i * k + j];
             out_d[excl + j] = tmp_d[i * k + j];
             out_v[excl + j] = tmp_v[i * k + j];
@@ -199,35 +231,75 @@ extern "C" int giqlb_nearest(giqlb_ctx* ctx, const giqlb_layout* lay, const int3
     GIQLB_TRY(probe_cols(ctx, lay, q_code, q_start, q_end, n_q, q_start_adj, q_end_adj, &Q));
     GIQLB_TRY(giqlb_index_ensure_pmax(ctx, T));
     GIQLB_TRY(giqlb_index_ensure_end_sorted(ctx, T));
-    int32_t *tmp_t = nullptr, *tmp_d = nullptr;
-    uint8_t* tmp_v = nullptr;
+    if (T->n > 0) GIQLB_TRY(giqlb_index_ensure_dirs(ctx, T, true, true));
     uint32_t* cnt = nullptr;
+    uint32_t *ka = nullptr, *kb = nullptr, *va = nullptr, *vb = nullptr;
+    const uint32_t* order = nullptr;
     unsigned long long* total = reinterpret_cast<unsigned long long*>(ctx->d_scalars + 10);
     const size_t slots = (size_t)k * (size_t)n_q;
-    int st = dev_alloc(ctx, &tmp_t, slots);
-    if (st == GIQLB_OK) st = dev_alloc(ctx, &tmp_d, slots);
-    if (st == GIQLB_OK) st = dev_alloc(ctx, &tmp_v, slots);
-    if (st == GIQLB_OK) st = dev_alloc(ctx, &cnt, (size_t)n_q);
+    int st = dev_alloc(ctx, &cnt, (size_t)n_q);
+    // query rows in the order of their linear start (one key pass + the radix sort: ~0.4 ms per 10 M rows, against
+    // searches that are several times faster once neighbouring threads share their cache lines)
+    if (st == GIQLB_OK && n_q >= 4096 && n_q < (1ll << 30) && T->n > 0) {
+        st = dev_alloc(ctx, &ka, (size_t)n_q);
+        if (st == GIQLB_OK) st = dev_alloc(ctx, &kb, (size_t)n_q);
+        if (st == GIQLB_OK) st = dev_alloc(ctx, &va, (size_t)n_q);
+        if (st == GIQLB_OK) st = dev_alloc(ctx, &vb, (size_t)n_q);
+        if (st == GIQLB_OK) {
+            {
+                PhaseSpan ps(ctx, GIQLB_PH_KEYGEN);
+                int64_t blocks = ceil_div(n_q, 256 * 4), cap = (int64_t)ctx->sm_count * 8;
+                nearest_query_keys_kernel<<<(unsigned)(blocks < cap ? blocks : cap), 256, 0, ctx->stream>>>(Q, ka);
+                LAUNCH_CHECK(ctx);
+            }
+            int in_b = 0;
+            st = giqlb_radix_sort_pairs_u32(ctx, ka, va, kb, vb, n_q, 0, lay->key_bits, 1, &in_b);
+            order = in_b ? vb : va;
+        }
+    }
     if (st == GIQLB_OK) {
         PhaseSpan ps(ctx, GIQLB_PH_NEAREST);
         cudaMemsetAsync(total, 0, 8, ctx->stream);
         TargetView V{T->gs, T->ge, T->rid, T->strand, T->pmax, T->ge_sorted, T->pos_by_end,
-                     T->grouped_by_strand ? T->d_block_off : nullptr, T->n};
+                     T->grouped_by_strand ? T->d_block_off : nullptr, T->n,
+                     T->dir_gs, T->dir_pmax, T->dir_ges, T->d_dir_slot, T->dir_shift, T->dir_stride};
         NearestArgs A{k, max_distance < 0 ? -1ll : (long long)max_distance, stranded != 0, signed_ != 0};
         int64_t blocks = ceil_div(n_q, 128), cap = (int64_t)ctx->sm_count * 32;
-        nearest_kernel<<<(unsigned)(blocks < cap ? blocks : cap), 128, 0, ctx->stream>>>(Q, q_strand, V, A, tmp_t, tmp_d, tmp_v, cnt);
+        // results land in the output arrays themselves, k slots per query row
+        nearest_kernel<<<(unsigned)(blocks < cap ? blocks : cap), 128, 0, ctx->stream>>>(Q, q_strand, order, V, A, out_q, out_t, out_dist, out_valid, cnt, total);
         ctx->launches_this_call++;
         ctx->stats.kernels_total++;
         if (cudaGetLastError() != cudaSuccess) st = giqlb_fail(ctx, GIQLB_ERR_CUDA, "nearest: launch failed");
-        if (st == GIQLB_OK)
-            st = launch_scan<OpAddU64>(ctx, n_q, InCnt{cnt},
-                                       OutCompactNearest{tmp_t, tmp_d, tmp_v, k, out_q, out_t, out_dist, out_valid, total, n_q});
     }
-    if (st == GIQLB_OK) st = fetch_scalars(ctx, total, 1);
-    dev_free(ctx, tmp_t);
-    dev_free(ctx, tmp_d);
-    dev_free(ctx, tmp_v);
+    if (st == GIQLB_OK) st = fetch_scalars_checked(ctx, total, 1);
+    if (st == GIQLB_OK && (unsigned long long)ctx->h_scalars[0] != (unsigned long long)slots) {
+        // some query rows found fewer than k candidates: close the gaps (copy the slotted rows aside, compact them back)
+        int32_t *tmp_q = nullptr, *tmp_t = nullptr, *tmp_d = nullptr;
+        uint8_t* tmp_v = nullptr;
+        st = dev_alloc(ctx, &tmp_q, slots);
+        if (st == GIQLB_OK) st = dev_alloc(ctx, &tmp_t, slots);
+        if (st == GIQLB_OK) st = dev_alloc(ctx, &tmp_d, slots);
+        if (st == GIQLB_OK) st = dev_alloc(ctx, &tmp_v, slots);
+        if (st == GIQLB_OK) {
+            cudaMemcpyAsync(tmp_q, out_q, slots * 4, cudaMemcpyDeviceToDevice, ctx->stream);
+            cudaMemcpyAsync(tmp_t, out_t, slots * 4, cudaMemcpyDeviceToDevice, ctx->stream);
+            cudaMemcpyAsync(tmp_d, out_dist, slots * 4, cudaMemcpyDeviceToDevice, ctx->stream);
+            cudaMemcpyAsync(tmp_v, out_valid, slots, cudaMemcpyDeviceToDevice, ctx->stream);
+            PhaseSpan ps(ctx, GIQLB_PH_NEAREST);
+            st = launch_scan<OpAddU64>(ctx, n_q, InCnt{cnt},
+                                       OutCompactNearest{tmp_q, tmp_t, tmp_d, tmp_v, k, out_q, out_t, out_dist, out_valid, total, n_q});
+        }
+        if (st == GIQLB_OK) st = fetch_scalars_checked(ctx, total, 1);
+        dev_free(ctx, tmp_q);
+        dev_free(ctx, tmp_t);
+        dev_free(ctx, tmp_d);
+        dev_free(ctx, tmp_v);
+    }
     dev_free(ctx, cnt);
+    dev_free(ctx, ka);
+    dev_free(ctx, kb);
+    dev_free(ctx, va);
+    dev_free(ctx, vb);
     if (st != GIQLB_OK) return st;
     *n_out_host = ctx->h_scalars[0];
     ctx->stats.rows_in[0] = n_q;

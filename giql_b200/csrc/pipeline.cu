@@ -11,58 +11,6 @@
 // src/giql/expanders/intersects_duckdb.py:1283-1334 (reference).
 #include "common.cuh"
 
-// The fused schedule (round 2): ONE read of the names and coordinates encodes the dictionary and observes the layout
-// (dict_insert_kernel<OBSERVE>), and the key-generation pass of the index build translates the parked dictionary slots
-// into codes — two passes over the raw tables before the sort instead of three.  (Also measured and dropped: carrying the
-// linear end through the sort as a second payload and computing the first pass's keys from the raw columns.  The
-// 120 MB of (key, row id, end) triples per table no longer fit the 126 MB L2 the way the 80 MB of pairs do, and a pass
-// went from 70 to 132 us.)
-// Returns GIQLB_ERR_INVALID (nothing enqueued that matters) when the fused encode cannot run; the caller then takes
-// the stage-by-stage schedule below.  *fallback = 1: the device declined to order the dictionary — redo on the host path.
-static int tables_fused(giqlb_ctx* ctx, giqlb_table_t* L, giqlb_table_t* R, int32_t* out_l, int32_t* out_r, int64_t capacity,
-                        int64_t* total_host, giqlb_dict** dict_out, int* fallback) {
-    *fallback = 0;
-    giqlb_layout* lay = nullptr;
-    giqlb_dict_pending* pend = nullptr;
-    giqlb_dict* dict = nullptr;
-    giqlb_index *il = nullptr, *ir = nullptr;
-    const int32_t* slot2code = nullptr;
-    const int* ok_flag = nullptr;
-    int st = giqlb_layout_create(ctx, GIQLB_ASYNC_DICT_MAX_CODES, 0, &lay);
-    if (st == GIQLB_OK) {
-        st = giqlb_dict_encode_observe_async(ctx, L, R, lay, &pend);
-        if (st != GIQLB_OK) {   // not applicable (or out of memory): nothing of consequence was enqueued
-            giqlb_layout_free(ctx, lay);
-            return GIQLB_ERR_INVALID;
-        }
-        giqlb_dict_pending_tables(pend, &slot2code, &ok_flag);
-    }
-    const giqlb_code_remap remap{slot2code, ok_flag};
-    if (st == GIQLB_OK) st = giqlb_layout_finalize_async(ctx, lay);
-    if (st == GIQLB_OK) st = giqlb_index_build_impl(ctx, lay, L->codes, L->start, L->end, nullptr, nullptr, L->n, L->start_adj, L->end_adj, 0, nullptr, &il, &remap);
-    if (st == GIQLB_OK) st = giqlb_index_build_impl(ctx, lay, R->codes, R->start, R->end, nullptr, nullptr, R->n, R->start_adj, R->end_adj, 0, nullptr, &ir, &remap);
-    if (st == GIQLB_OK) st = giqlb_intersects_join_impl(ctx, il, ir, out_l, out_r, capacity, total_host, true);
-    char msg[sizeof(ctx->err)];
-    memcpy(msg, ctx->err, sizeof(msg));
-    giqlb_index_free(ctx, il);
-    giqlb_index_free(ctx, ir);
-    giqlb_layout_free(ctx, lay);
-    if (pend) {   // the join's round trip also landed the names (or the device's refusal to order them)
-        if (st != GIQLB_OK && st != GIQLB_ERR_CAPACITY) cudaStreamSynchronize(ctx->stream);
-        const int st2 = giqlb_dict_finish(ctx, pend, &dict, fallback);
-        if (*fallback) {
-            cudaMemsetAsync(ctx->d_err, 0, 4 * sizeof(int), ctx->stream);
-            return GIQLB_OK;
-        }
-        if (st == GIQLB_OK) st = st2;
-    }
-    if (dict && (st == GIQLB_OK || st == GIQLB_ERR_CAPACITY)) L->codes_valid = R->codes_valid = 1;
-    if (dict_out) *dict_out = dict;
-    else giqlb_dict_free(dict);
-    if (st != GIQLB_OK) memcpy(ctx->err, msg, sizeof(msg));
-    return st;
-}
-
 static int tables_impl(giqlb_ctx* ctx, giqlb_table_t* L, giqlb_table_t* R, int32_t n_codes, int32_t* out_l, int32_t* out_r,
                        int64_t capacity, int64_t* total_host, giqlb_dict** dict_out, bool async_dict) {
     giqlb_dict* dict = nullptr;
@@ -74,13 +22,6 @@ static int tables_impl(giqlb_ctx* ctx, giqlb_table_t* L, giqlb_table_t* R, int32
     int st = GIQLB_OK;
     const bool same = L == R;
     const bool encode = !L->codes_valid;
-    if (encode && !same && async_dict && ctx->fused_pipeline) {
-        int fallback = 0;
-        st = tables_fused(ctx, L, R, out_l, out_r, capacity, total_host, dict_out, &fallback);
-        if (fallback) return tables_impl(ctx, L, R, n_codes, out_l, out_r, capacity, total_host, dict_out, false);
-        if (st != GIQLB_ERR_INVALID) return st;
-        st = GIQLB_OK;   // the fused encode does not apply here: stage by stage
-    }
     if (encode) {
         const int32_t* ro = same ? nullptr : R->chrom_offsets;
         const uint8_t* rb = same ? nullptr : R->chrom_bytes;

@@ -45,6 +45,13 @@ def lib():
         _lib.giql_oracle_merge.restype = i64
         _lib.giql_oracle_merge.argtypes = tbl + [ctypes.c_int32, i64, i32p, i32p, i32p, i64p, ctypes.c_int]
         _lib.giql_oracle_max_threads.restype = ctypes.c_int
+        _lib.giql_oracle_contains_join.restype = i64
+        _lib.giql_oracle_contains_join.argtypes = tbl + tbl + [ctypes.c_int32, i64, i32p, i32p, ctypes.c_int]
+        _lib.giql_oracle_nearest.restype = i64
+        _lib.giql_oracle_nearest.argtypes = (tbl + [u8p]) + (tbl + [u8p]) + [ctypes.c_int32, ctypes.c_int32, i64, ctypes.c_int, ctypes.c_int,
+                                                                          i32p, i32p, i64p, u8p, ctypes.c_int]
+        _lib.giql_oracle_disjoin.restype = i64
+        _lib.giql_oracle_disjoin.argtypes = tbl + tbl + [ctypes.c_int32, ctypes.c_int, i64p, i64p, i32p, i32p, i32p, ctypes.c_int]
     return _lib
 
 
@@ -126,3 +133,63 @@ def merge(part, start, end, n_parts, distance=0, threads=0):
     m = lib().giql_oracle_merge(n, _p(part), _p(start), _p(end), n_parts, int(distance),
                                 _p(op), _p(os_), _p(oe), _p(oc), threads)
     return op[:m], os_[:m], oe[:m], oc[:m]
+
+
+def spatial_pairs(lc, ls, le, rc, rs, re, n_codes, op="contains", threads=0):
+    """(P, 2) sorted (left_row, right_row) pairs of the CONTAINS / WITHIN column join (intersects.py:155-166)."""
+    lc, ls, le, rc, rs, re = map(_i32, (lc, ls, le, rc, rs, re))
+    if op == "within":                                   # l WITHIN r  <=>  r CONTAINS l
+        out = spatial_pairs(rc, rs, re, lc, ls, le, n_codes, "contains", threads)
+        packed = np.sort((out[:, 1] << 32) | out[:, 0])
+        return np.stack([packed >> 32, packed & 0xFFFFFFFF], axis=1)
+    if op != "contains":
+        raise ValueError(op)
+    if len(rs) and (re < rs).any():
+        raise ValueError("the C oracle's CONTAINS needs end >= start on the contained side")
+    total = lib().giql_oracle_contains_join(len(ls), _p(lc), _p(ls), _p(le), len(rs), _p(rc), _p(rs), _p(re), n_codes, 0, None, None, threads)
+    out_l, out_r = np.empty(max(total, 1), np.int32), np.empty(max(total, 1), np.int32)
+    lib().giql_oracle_contains_join(len(ls), _p(lc), _p(ls), _p(le), len(rs), _p(rc), _p(rs), _p(re), n_codes, int(total), _p(out_l), _p(out_r),
+                                    threads)
+    packed = np.sort((out_l[:total].astype(np.int64) << 32) | out_r[:total].astype(np.int64))
+    return np.stack([packed >> 32, packed & 0xFFFFFFFF], axis=1)
+
+
+def nearest(qc, qs, qe, tc, ts, te, n_codes, k=1, max_distance=None, q_strand=None, t_strand=None, stranded=False, signed=False, threads=0):
+    """(query_row, target_row, distance, valid) arrays of the LATERAL NEAREST form; proper intervals only.
+    Strand columns are giql_b200's uint8 codes (0 '+', 1 '-', 2 '.', 3 '?', >= 4 other literals, 255 NULL)."""
+    qc, qs, qe, tc, ts, te = map(_i32, (qc, qs, qe, tc, ts, te))
+    if (len(qs) and (qe <= qs).any()) or (len(ts) and (te <= ts).any()):
+        raise ValueError("the C oracle's NEAREST needs start < end on both sides")
+    use = stranded and q_strand is not None and t_strand is not None
+    qst = np.ascontiguousarray(q_strand, dtype=np.uint8) if use else None
+    tst = np.ascontiguousarray(t_strand, dtype=np.uint8) if use else None
+    cap = max(int(k) * len(qs), 1)
+    oq, ot = np.empty(cap, np.int32), np.empty(cap, np.int32)
+    od, ov = np.empty(cap, np.int64), np.empty(cap, np.uint8)
+    m = lib().giql_oracle_nearest(len(qs), _p(qc), _p(qs), _p(qe), _p(qst) if use else None, len(ts), _p(tc), _p(ts), _p(te),
+                                  _p(tst) if use else None, n_codes, int(k), -1 if max_distance is None else int(max_distance), int(use),
+                                  int(bool(signed)), _p(oq), _p(ot), _p(od), _p(ov), threads)
+    if m < 0:
+        raise MemoryError("oracle allocation failed")
+    return oq[:m], ot[:m], od[:m], ov[:m].astype(bool)
+
+
+def disjoin(tc, ts, te, rc=None, rs=None, re=None, n_codes=0, threads=0):
+    """(target_row, seg_start, seg_end) arrays sorted by (row, start); reference None = the target itself."""
+    tc, ts, te = map(_i32, (tc, ts, te))
+    self_ref = rc is None
+    if self_ref:
+        rc, rs, re = tc, ts, te
+    rc, rs, re = map(_i32, (rc, rs, re))
+    if len(rs) and (re < rs).any():
+        raise ValueError("the C oracle's DISJOIN needs start <= end on the reference")
+    counts = np.zeros(max(len(ts), 1), dtype=np.int64)
+    args = (len(ts), _p(tc), _p(ts), _p(te), len(rs), _p(rc), _p(rs), _p(re), n_codes, int(self_ref))
+    total = lib().giql_oracle_disjoin(*args, _p(counts), None, None, None, None, threads)
+    if total < 0:
+        raise MemoryError("oracle allocation failed")
+    offs = np.zeros(len(ts) + 1, dtype=np.int64)
+    np.cumsum(counts[: len(ts)], out=offs[1:])
+    row, s, e = (np.empty(max(total, 1), np.int32) for _ in range(3))
+    lib().giql_oracle_disjoin(*args, _p(counts), _p(offs), _p(row), _p(s), _p(e), threads)
+    return row[:total], s[:total], e[:total]

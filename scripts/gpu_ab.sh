@@ -16,7 +16,7 @@ for spec in "$@"; do
   if [ $runtest = 1 ]; then
     env "${E[@]}" timeout 600 python -m pytest tests -m gpu -x -q > gpurun_out/pytest_${TAG}_$label.log 2>&1; echo "[$label] pytest rc=$? $(tail -1 gpurun_out/pytest_${TAG}_$label.log)"
   fi
-  env "${E[@]}" timeout 300 python bench.py --steps 10 --warmup 3 --no-cpu > gpurun_out/ab_${TAG}_$label.json 2> gpurun_out/ab_${TAG}_$label.err; rc=$?
+  env "${E[@]}" timeout 300 python bench.py --steps 10 --warmup 3 --no-cpu --no-other > gpurun_out/ab_${TAG}_$label.json 2> gpurun_out/ab_${TAG}_$label.err; rc=$?
   python - "$label" gpurun_out/ab_${TAG}_$label.json $rc <<'PY'
 import json, sys
 label, path, rc = sys.argv[1:4]

@@ -61,4 +61,5 @@ if "c5" in only:
     t = table(synth.reads(n, 9))
     probe(f"CLUSTER {n}", lambda: eng.cluster(t))
     probe(f"MERGE {n}", lambda: eng.merge(t))
-    probe(f"DISJOIN {n // 10}", lambda: eng.disjoin(table(synth.peaks(n // 10, 10))))
+    td = table(synth.peaks(n // 10, 10))                    # built outside the timed lambda (round 1 timed the host generator)
+    probe(f"DISJOIN {n // 10}", lambda: eng.disjoin(td))

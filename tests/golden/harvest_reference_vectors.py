@@ -211,3 +211,45 @@ def main():
 
 if __name__ == "__main__":
     main()
+
+
+def harvest_disjoin_usage_matrix():
+    """The reference's DISJOIN usage matrix (tests/test_usage_patterns.py:143-171): 15 semantic profiles x 2 modes x 26 query
+    patterns, each with the rows DuckDB produced for the transpiled SQL, snapshotted in
+    tests/manifests/test_usage_patterns.TestDisjoinUsageMatrix...yaml.  The queries and fixtures are rendered by importing the
+    reference's own tests/usage_patterns.py (its only giql import, giql.table, is sqlglot-free and is loaded directly)."""
+    import types
+
+    import yaml
+
+    pkg = types.ModuleType("giql")
+    pkg.__path__ = [str(REF / "src/giql")]
+    sys.modules.setdefault("giql", pkg)
+    spec = importlib.util.spec_from_file_location("giql.table", REF / "src/giql/table.py")
+    mod = importlib.util.module_from_spec(spec)
+    sys.modules["giql.table"] = mod
+    spec.loader.exec_module(mod)
+    spec = importlib.util.spec_from_file_location("ref_usage_patterns", REF / "tests/usage_patterns.py")
+    up = importlib.util.module_from_spec(spec)
+    sys.modules["ref_usage_patterns"] = up
+    spec.loader.exec_module(up)
+    manifest = yaml.safe_load((REF / "tests/manifests/test_usage_patterns.TestDisjoinUsageMatrix."
+                                     "test_disjoin_pattern_executes_to_snapshot_across_profiles.yaml").read_text())
+    cases = []
+    for profile in up.DISJOIN_PROFILES:
+        for mode, usage in (("self", profile.self_usage), ("reference", profile.reference_usage)):
+            tables = []
+            for t in usage.tables:
+                tables.append(t if isinstance(t, str) else {k: getattr(t, k) for k in ("name", "genomic_col", "chrom_col", "start_col", "end_col",
+                                                                                         "strand_col", "coordinate_system", "interval_type")})
+            fixtures = [{"name": f.name, "columns": [list(c) for c in f.columns], "rows": [list(r) for r in f.rows]} for f in usage.fixtures]
+            for pattern in up.templated_patterns(usage):
+                key = f"{profile.profile_id}-{mode}-duckdb-{pattern.name}"
+                if key not in manifest:
+                    continue
+                cases.append({"key": key, "profile": profile.profile_id, "mode": mode, "pattern": pattern.name, "xfail": pattern in usage.xfails,
+                              "query": up.render(pattern, usage), "tables": tables, "fixtures": fixtures, "expected": manifest[key]})
+    (OUT / "disjoin_usage_matrix.json").write_text(json.dumps({
+        "source": "tests/test_usage_patterns.py:143-171 + tests/manifests/test_usage_patterns.TestDisjoinUsageMatrix...yaml (duckdb rows)",
+        "cases": cases}, indent=0))
+    return len(cases)

@@ -110,3 +110,57 @@ def test_cluster_predicate_matches_reference_sql_shape_on_sqlite(seed, op, dista
     assert go.cluster(T, distance, stranded, predicate=(cur, op, prev)) == so.cluster_predicate(T, cur, op, prev, distance, stranded)
     names = [["a", "b", "c"][i] for i in rng.integers(0, 3, size=n)]
     assert go.cluster(T, distance, stranded, predicate=(names, op, names)) == so.cluster_predicate(T, names, op, names, distance, stranded)
+
+
+# ---- the C restatement's NEAREST / DISJOIN / CONTAINS against the pure-Python restatement (pinned above) --------
+def _rand_table(rng, n, n_chrom=3, span=2000, wmax=300, strands=False):
+    chrom = rng.integers(0, n_chrom, n).astype(np.int32)
+    start = rng.integers(0, span, n).astype(np.int32)
+    end = (start + rng.integers(1, wmax, n)).astype(np.int32)
+    T = {"chrom": [f"c{c}" for c in chrom], "start": start.tolist(), "end": end.tolist()}
+    code = {"code": chrom, "start": start, "end": end}
+    if strands:
+        sc = rng.choice(np.array([0, 1, 2, 255], dtype=np.uint8), n, p=[0.45, 0.45, 0.05, 0.05])
+        T["strand"] = [{0: "+", 1: "-", 2: ".", 255: None}[int(v)] for v in sc]
+        code["strand"] = sc
+    return T, code
+
+
+@pytest.mark.parametrize("seed,k,maxd,stranded,signed", [(1, 1, None, False, False), (2, 3, None, False, True), (3, 5, 150, False, False),
+                                                         (4, 2, None, True, False), (5, 4, None, True, True), (6, 3, 400, True, True)])
+def test_c_oracle_nearest_equals_python_oracle(c_oracle, seed, k, maxd, stranded, signed):
+    from oracle import giql_oracle as go
+
+    rng = np.random.default_rng(seed)
+    Q, qc = _rand_table(rng, 150, strands=stranded)
+    T, tc = _rand_table(rng, 120, strands=stranded)
+    want = go.nearest(Q, T, k=k, max_distance=maxd, stranded=stranded, signed=signed)
+    q, t, d, v = c_oracle.nearest(qc["code"], qc["start"], qc["end"], tc["code"], tc["start"], tc["end"], 3, k=k, max_distance=maxd,
+                                  q_strand=qc.get("strand"), t_strand=tc.get("strand"), stranded=stranded, signed=signed)
+    got = [(int(a), int(b), int(c) if ok else None) for a, b, c, ok in zip(q, t, d, v)]
+    assert got == want
+
+
+@pytest.mark.parametrize("seed,self_ref", [(1, True), (2, False), (3, False)])
+def test_c_oracle_disjoin_equals_python_oracle(c_oracle, seed, self_ref):
+    from oracle import giql_oracle as go
+
+    rng = np.random.default_rng(seed)
+    T, tc = _rand_table(rng, 200)
+    R, rc = _rand_table(rng, 150)
+    want = go.disjoin(T, None if self_ref else R)
+    args = () if self_ref else (rc["code"], rc["start"], rc["end"])
+    row, s, e = c_oracle.disjoin(tc["code"], tc["start"], tc["end"], *args, n_codes=3)
+    assert sorted(zip(row.tolist(), s.tolist(), e.tolist())) == want
+
+
+@pytest.mark.parametrize("op", ["contains", "within"])
+def test_c_oracle_spatial_joins_equal_python_oracle(c_oracle, op):
+    from oracle import giql_oracle as go
+
+    rng = np.random.default_rng(9)
+    L, lc = _rand_table(rng, 300, wmax=600)
+    R, rc = _rand_table(rng, 300, wmax=200)
+    want = sorted((int(a), int(b)) for a, b in go.join_pairs(L, R, op))
+    got = c_oracle.spatial_pairs(lc["code"], lc["start"], lc["end"], rc["code"], rc["start"], rc["end"], 3, op)
+    assert [tuple(r) for r in got.tolist()] == want and len(want) > 20
