@@ -153,6 +153,23 @@ def cpu_join(A, B, threads: int):
     return int(total), time.perf_counter() - t0
 
 
+def duckdb_baseline(A, B, threads: int, repeats: int = 3):
+    """The reference's own path — giql.transpile(dialect="duckdb") executed by DuckDB on the host cores — when duckdb (and
+    giql) are importable on this box; None otherwise (today: neither is installed in the image)."""
+    from oracle import duckdb_oracle as do
+
+    if not do.available():
+        return None
+    try:
+        pairs, seconds, _ = do.intersects_join_timed(A, B, threads, plan="iejoin", repeats=repeats)
+    except Exception as exc:   # noqa: BLE001 — a broken DuckDB install must not take the bench line down
+        log(f"[bench] duckdb baseline failed ({type(exc).__name__}: {exc}); falling back to the C restatement")
+        return None
+    return {"value": pairs / seconds, "unit": UNIT, "cores": threads, "kind": "duckdb" if do.have_giql() else "duckdb-restated-sql",
+            "sample": f"full workload, best of {repeats} after 1 warm-up ({seconds:.2f}s): {do.label(threads)}, "
+                      "CREATE TEMP TABLE out AS <final SELECT of the per-chromosome IEJoin plan>", "pairs": pairs, "seconds": seconds}
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -162,6 +179,20 @@ def run_reference(args):
     c_oracle.build()
     threads = c_oracle.default_threads()
     A, B = make_workload(args.rows)
+    duck = duckdb_baseline(A, B, threads, repeats=max(1, min(args.steps, 3)))
+    if duck is not None:
+        # the true reference path exists on this box: GIQL's transpiled SQL on DuckDB
+        line = {
+            "impl": "reference", "metric": METRIC, "value": duck["value"], "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": 1e3 * duck["seconds"], "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+            "dtype": "int32", "data": "synthetic",
+            "config": {"workload": workload_name(args.rows), "pairs": duck["pairs"], "note": "reference arm = " + duck["sample"]},
+            "cpu_baseline": {k: duck[k] for k in ("value", "unit", "cores", "kind", "sample")},
+            "e2e": {"value": duck["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0,
+        }
+        print(json.dumps(line), flush=True)
+        return
     for _ in range(args.warmup):
         cpu_join(A, B, threads)
     times, total = [], 0
@@ -549,6 +580,11 @@ def run_b200(args):
         assert total == pairs, f"CPU restatement found {total} pairs, GPU {pairs}"
         cpu = {"value": total / dt, "unit": UNIT, "cores": threads, "kind": "port",
                "sample": f"full workload, 1 run after 1 warm-up ({dt:.2f}s): C/OpenMP restatement, NOT DuckDB (duckdb/sqlglot absent)"}
+        duck = duckdb_baseline(A, B, threads)
+        if duck is not None:
+            assert duck["pairs"] == pairs, f"DuckDB found {duck['pairs']} pairs, GPU {pairs}"
+            cpu = {k: duck[k] for k in ("value", "unit", "cores", "kind", "sample")}
+            cpu["port_value"] = total / dt   # the C restatement beside it
 
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),

@@ -340,7 +340,9 @@ extern "C" int giqlb_merge(giqlb_ctx* ctx, giqlb_index* X, int64_t distance, int
     for (size_t k = 0; k < blk_lo.size() && st == GIQLB_OK; k++)
         if (cudaMemcpyAsync(&totals[k], G + blk_hi[k] - 1, 4, cudaMemcpyDeviceToHost, ctx->stream) != cudaSuccess)
             st = giqlb_fail(ctx, GIQLB_ERR_CUDA, "merge: copy failed");
-    if (st == GIQLB_OK && cudaStreamSynchronize(ctx->stream) != cudaSuccess) st = giqlb_fail(ctx, GIQLB_ERR_CUDA, "merge: sync failed");
+    // the synchronisation also brings the sticky kernel-side flags back (a look-back that hit its spin limit must not
+    // pass silently as wrong region counts)
+    if (st == GIQLB_OK) st = fetch_scalars_checked(ctx, ctx->d_scalars, 1);
     int64_t total = 0;
     for (uint32_t t : totals) total += t;
     *n_out_host = total;
@@ -470,7 +472,7 @@ extern "C" int giqlb_merge_shard(giqlb_ctx* ctx, giqlb_index* X, int64_t distanc
             ctx->launches_this_call++;
             ctx->stats.kernels_total++;
             cudaMemcpyAsync(ctx->h_scalars + 4, G + n - 1, 4, cudaMemcpyDeviceToHost, ctx->stream);
-            st = fetch_scalars(ctx, head, 3);
+            st = fetch_scalars_checked(ctx, head, 3);
         }
     }
     int64_t total = 0;

@@ -6,6 +6,7 @@
 #include <stdio.h>
 #include <string.h>
 
+#include <iterator>
 #include <map>
 #include <string>
 #include <unordered_map>
@@ -126,6 +127,11 @@ struct giqlb_index {
     // lazily built bucket directories (giqlb_index_ensure_dirs): for every strand block with rows, dir[slot][b] = first
     // block-relative position whose value is >= b << dir_shift, over gs / pmax / ge_sorted.  A search then starts inside one
     // bucket (about one row) instead of walking log2(n) dependent loads from the whole array.
+    // lazily built block maxima of ge (giqlb_index_ensure_block_max): bmax1[b] = max ge over rows [32 b, 32 b + 32),
+    // bmax2[b] over rows [1024 b, 1024 b + 1024).  "Next row at or after j whose end exceeds x" skips whole blocks with them, so
+    // one chromosome-spanning row does not turn every later probe into a scan of the chromosome.
+    uint32_t* bmax1 = nullptr;
+    uint32_t* bmax2 = nullptr;
     uint32_t* dir_gs = nullptr;
     uint32_t* dir_pmax = nullptr;
     uint32_t* dir_ges = nullptr;
@@ -235,8 +241,27 @@ static inline void begin_call(giqlb_ctx* ctx) {
     ctx->launches_this_call = 0;
     ctx->err[0] = 0;
 }
+// Parked scratch above this many bytes is handed back to the driver when a call ends (largest blocks first): PyTorch's
+// allocator, which owns every input and output buffer, cannot see or reclaim what the library parks.
+#ifndef GIQLB_SCRATCH_PARK_LIMIT
+#define GIQLB_SCRATCH_PARK_LIMIT (4ull << 30)
+#endif
+static inline void cache_trim_to(giqlb_ctx* ctx, size_t limit) {
+    size_t parked = 0;
+    for (auto& kv : ctx->cache_free) parked += kv.first;
+    if (parked <= limit) return;
+    cudaStreamSynchronize(ctx->stream);   // a parked block may still be in use by work enqueued on the stream
+    while (parked > limit && !ctx->cache_free.empty()) {
+        auto it = std::prev(ctx->cache_free.end());
+        cudaFree(it->second);
+        parked -= it->first;
+        ctx->cache_bytes -= it->first;
+        ctx->cache_free.erase(it);
+    }
+}
 static inline int end_call(giqlb_ctx* ctx, int status = GIQLB_OK) {
     ctx->stats.kernels_launched = ctx->launches_this_call;
+    cache_trim_to(ctx, GIQLB_SCRATCH_PARK_LIMIT);
     return status;
 }
 
@@ -278,6 +303,7 @@ static inline int fetch_scalars_checked(giqlb_ctx* ctx, const void* d_src, int n
     if (e[0] || e[1] || e[3]) {
         cudaMemsetAsync(ctx->d_err, 0, 4 * sizeof(int), ctx->stream);
         if (e[1] == 2) return giqlb_fail(ctx, GIQLB_ERR_RANGE, "layout: the summed chromosome extent does not fit the 32-bit linear coordinate");
+        if (e[1] == 3) return giqlb_fail(ctx, GIQLB_ERR_RANGE, "nearest: a distance does not fit the int32 output column");
         if (e[1]) return giqlb_fail(ctx, GIQLB_ERR_RANGE, "layout: a row has a chromosome code outside the dictionary or a coordinate outside [-2^30, 2^31-4]");
         if (e[3]) return giqlb_fail(ctx, GIQLB_ERR_RANGE, "index: rows lie outside the layout (observe the table before finalize)");
         return giqlb_fail(ctx, GIQLB_ERR_INTERNAL, "look-back spin limit exceeded (kernel-side)");
@@ -322,6 +348,27 @@ __device__ __forceinline__ int64_t dir_lower_bound(const uint32_t* __restrict__ 
 __device__ __forceinline__ int64_t dir_upper_bound(const uint32_t* __restrict__ tab, int shift, uint32_t last, const uint32_t* __restrict__ a, uint32_t x) {
     const uint32_t b = min(x >> shift, last);
     return upper_bound_dev<uint32_t, int64_t>(a, (int64_t)__ldg(tab + b), (int64_t)__ldg(tab + b + 1), x);
+}
+
+// First position in [j, hi) whose ge exceeds thr (hi when there is none), skipping 32- and 1024-row blocks whose maximum
+// does not (giqlb_index::bmax1 / bmax2; a block straddling hi is judged by its full maximum, which only skips less).
+__device__ __forceinline__ int64_t next_end_above(const uint32_t* __restrict__ ge, const uint32_t* __restrict__ m1,
+                                                  const uint32_t* __restrict__ m2, int64_t j, int64_t hi, uint32_t thr) {
+    while (j < hi) {
+        const int64_t bend = min(hi, (j | 31) + 1);
+        if ((j & 31) != 0 || __ldg(m1 + (j >> 5)) > thr) {
+            for (; j < bend; j++)
+                if (__ldg(ge + j) > thr) return j;
+        } else {
+            j = bend;
+        }
+        while (j < hi) {                                        // j is 32-aligned here
+            if ((j & 1023) == 0 && __ldg(m2 + (j >> 10)) <= thr) { j += 1024; continue; }
+            if (__ldg(m1 + (j >> 5)) <= thr) { j += 32; continue; }
+            break;
+        }
+    }
+    return hi;
 }
 
 // streaming (read-once) loads / stores that do not pollute L1
@@ -438,3 +485,4 @@ int giqlb_index_resolve(giqlb_ctx* ctx, giqlb_index* a, giqlb_index* b);
 int giqlb_index_ensure_end_sorted(giqlb_ctx* ctx, giqlb_index* ix);
 // bucket directories over gs (always), pmax and ge_sorted (on request; they must exist already)
 int giqlb_index_ensure_dirs(giqlb_ctx* ctx, giqlb_index* ix, bool want_pmax, bool want_ges);
+int giqlb_index_ensure_block_max(giqlb_ctx* ctx, giqlb_index* ix);

@@ -190,7 +190,7 @@ extern "C" int giqlb_select_rows(giqlb_ctx* ctx, const uint8_t* flags, int64_t n
         GIQLB_TRY((launch_scan<OpAddU64>(ctx, n, InFlagEq{flags, want}, OutCompact{out_rows, total, n})));
     }
     if (n_out_host) {
-        GIQLB_TRY(fetch_scalars(ctx, total, 1));
+        GIQLB_TRY(fetch_scalars_checked(ctx, total, 1));
         *n_out_host = ctx->h_scalars[0];
     }
     ctx->stats.rows_in[0] = n;

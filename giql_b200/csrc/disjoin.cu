@@ -28,6 +28,8 @@ struct DisjoinView {
     const uint32_t* pmax;
     int64_t n_r;
     int filter;             // 1: keep only covered segments (reference is not the target itself)
+    const uint8_t* cov;     // filter only: cov[j] = some reference row covers breakpoint bp[j] (computed once per call, so a
+                            // segment that starts at a breakpoint needs one byte instead of a search)
 };
 
 __device__ __forceinline__ bool covered(const DisjoinView& V, uint32_t p) {
@@ -64,26 +66,89 @@ __device__ __forceinline__ unsigned long long for_each_segment(const ProbeCols& 
     int64_t hi = lower_bound_dev<uint32_t, int64_t>(V.bp, lo, V.n_bp, ge);        // first bp >= t.end
     if (hi < lo) hi = lo;
     long long seg_s = ts;
-    uint32_t seg_s_lin = gs;
     for (int64_t j = lo; j <= hi; j++) {
         const uint32_t cut_lin = j < hi ? __ldg(V.bp + j) : ge;
         const long long cut = j < hi ? lo_c + (long long)(cut_lin - b1) : te;
-        if (!V.filter || covered(V, seg_s_lin)) {
+        if (!V.filter || (j == lo ? covered(V, gs) : __ldg(V.cov + j - 1) != 0)) {
             f(n, seg_s, cut);
             n++;
         }
         seg_s = cut;
-        seg_s_lin = cut_lin;
     }
     return n;
 }
 
-struct InSegCount {
-    ProbeCols T;
-    DisjoinView V;
-    __device__ unsigned long long operator()(int64_t i) const {
-        return for_each_segment(T, V, i, [](unsigned long long, long long, long long) {});
+// A target row cut by more than DJ_HEAVY breakpoints (a chromosome-spanning interval) is not walked by its own thread —
+// ~10^5 cuts, each with a coverage search, serialised while the rest of the grid has finished — but by the lanes of its
+// warp together: candidate segment j of the row is independent of the others (its start is breakpoint j - 1), so 32 of
+// them are tested per step and written in order through a ballot prefix.
+constexpr int64_t DJ_HEAVY = 64;
+
+struct RowCuts {
+    long long ts, te, lo_c;
+    uint32_t gs, ge, b1;
+    int64_t lo, hi;          // interior cuts bp[lo, hi): segments j = lo .. hi
+};
+// true when the row takes the breakpoint walk (proper interval on a chromosome that has reference rows)
+__device__ __forceinline__ bool row_cuts(const ProbeCols& T, const DisjoinView& V, int64_t i, RowCuts& r) {
+    r.ts = (long long)T.start[i] + T.sadj;
+    r.te = (long long)T.end[i] + T.eadj;
+    if (r.te <= r.ts || V.n_r <= 0 || !probe_linearise(T, i, r.gs, r.ge)) return false;
+    const int32_t c = T.code[i];
+    r.lo_c = __ldg(T.lo32 + c);
+    r.b1 = __ldg(T.base + c) + 1u;
+    r.lo = upper_bound_dev<uint32_t, int64_t>(V.bp, 0, V.n_bp, r.gs);
+    r.hi = lower_bound_dev<uint32_t, int64_t>(V.bp, r.lo, V.n_bp, r.ge);
+    if (r.hi < r.lo) r.hi = r.lo;
+    return true;
+}
+// candidate segment j of a walked row: canonical (start, end) and whether it is kept
+__device__ __forceinline__ bool cut_segment(const DisjoinView& V, const RowCuts& r, int64_t j, long long& s, long long& e) {
+    const uint32_t s_lin = j == r.lo ? r.gs : __ldg(V.bp + j - 1);
+    s = j == r.lo ? r.ts : r.lo_c + (long long)(s_lin - r.b1);
+    e = j < r.hi ? r.lo_c + (long long)(__ldg(V.bp + j) - r.b1) : r.te;
+    return !V.filter || (j == r.lo ? covered(V, s_lin) : __ldg(V.cov + j - 1) != 0);
+}
+
+__global__ void __launch_bounds__(256)
+disjoin_cover_kernel(DisjoinView V, uint8_t* __restrict__ cov) {
+    for (int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; j < V.n_bp; j += (int64_t)gridDim.x * blockDim.x)
+        cov[j] = covered(V, V.bp[j]) ? 1 : 0;
+}
+
+__global__ void __launch_bounds__(256)
+disjoin_count_kernel(ProbeCols T, DisjoinView V, unsigned long long* __restrict__ cnt) {
+    for (int64_t base = (int64_t)blockIdx.x * blockDim.x; base < T.n; base += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t i = base + threadIdx.x;
+        const bool live = i < T.n;
+        RowCuts r;
+        const bool heavy = live && row_cuts(T, V, i, r) && r.hi - r.lo + 1 > DJ_HEAVY;
+        unsigned long long n = 0;
+        if (live && !heavy) n = for_each_segment(T, V, i, [](unsigned long long, long long, long long) {});
+        uint32_t todo = __ballot_sync(FULL_MASK, heavy);
+        while (todo) {
+            const int src = __ffs(todo) - 1;
+            todo &= todo - 1;
+            RowCuts b;
+            b.ts = __shfl_sync(FULL_MASK, r.ts, src); b.te = __shfl_sync(FULL_MASK, r.te, src); b.lo_c = __shfl_sync(FULL_MASK, r.lo_c, src);
+            b.gs = __shfl_sync(FULL_MASK, r.gs, src); b.ge = __shfl_sync(FULL_MASK, r.ge, src); b.b1 = __shfl_sync(FULL_MASK, r.b1, src);
+            b.lo = __shfl_sync(FULL_MASK, r.lo, src); b.hi = __shfl_sync(FULL_MASK, r.hi, src);
+            unsigned long long c = 0;
+#pragma unroll 4
+            for (int64_t j = b.lo + lane_id(); j <= b.hi; j += 32) {
+                long long s, e;
+                c += cut_segment(V, b, j, s, e);
+            }
+            c = warp_reduce_add(c);
+            if ((int)lane_id() == src) n = c;
+        }
+        if (live) cnt[i] = n;
     }
+}
+
+struct InCounts {
+    const unsigned long long* cnt;
+    __device__ unsigned long long operator()(int64_t i) const { return cnt[i]; }
 };
 struct OutOffsets {
     unsigned long long* off;
@@ -98,13 +163,51 @@ struct OutOffsets {
 __global__ void __launch_bounds__(256)
 disjoin_emit_kernel(ProbeCols T, DisjoinView V, const unsigned long long* __restrict__ off, int32_t* __restrict__ out_row,
                     int32_t* __restrict__ out_start, int32_t* __restrict__ out_end) {
-    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < T.n; i += (int64_t)gridDim.x * blockDim.x) {
-        const unsigned long long o = off[i];
-        for_each_segment(T, V, i, [&](unsigned long long k, long long s, long long e) {
-            out_row[o + k] = (int32_t)i;
-            out_start[o + k] = (int32_t)s;
-            out_end[o + k] = (int32_t)e;
-        });
+    const uint32_t lt_mask = (1u << lane_id()) - 1u;
+    for (int64_t base = (int64_t)blockIdx.x * blockDim.x; base < T.n; base += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t i = base + threadIdx.x;
+        const bool live = i < T.n;
+        RowCuts r;
+        const bool heavy = live && row_cuts(T, V, i, r) && r.hi - r.lo + 1 > DJ_HEAVY;
+        const unsigned long long o = live ? off[i] : 0ull;
+        if (live && !heavy)
+            for_each_segment(T, V, i, [&](unsigned long long k, long long s, long long e) {
+                out_row[o + k] = (int32_t)i;
+                out_start[o + k] = (int32_t)s;
+                out_end[o + k] = (int32_t)e;
+            });
+        uint32_t todo = __ballot_sync(FULL_MASK, heavy);
+        while (todo) {
+            const int src = __ffs(todo) - 1;
+            todo &= todo - 1;
+            RowCuts b;
+            b.ts = __shfl_sync(FULL_MASK, r.ts, src); b.te = __shfl_sync(FULL_MASK, r.te, src); b.lo_c = __shfl_sync(FULL_MASK, r.lo_c, src);
+            b.gs = __shfl_sync(FULL_MASK, r.gs, src); b.ge = __shfl_sync(FULL_MASK, r.ge, src); b.b1 = __shfl_sync(FULL_MASK, r.b1, src);
+            b.lo = __shfl_sync(FULL_MASK, r.lo, src); b.hi = __shfl_sync(FULL_MASK, r.hi, src);
+            const int32_t row = (int32_t)__shfl_sync(FULL_MASK, i, src);
+            unsigned long long bo = __shfl_sync(FULL_MASK, o, src);
+            for (int64_t j0 = b.lo; j0 <= b.hi; j0 += 128) {   // four 32-segment steps per iteration: their loads are in flight together
+                bool keep[4];
+                long long sgs[4], sge[4];
+#pragma unroll
+                for (int u = 0; u < 4; u++) {
+                    const int64_t j = j0 + 32 * u + lane_id();
+                    sgs[u] = sge[u] = 0;
+                    keep[u] = j <= b.hi && cut_segment(V, b, j, sgs[u], sge[u]);
+                }
+#pragma unroll
+                for (int u = 0; u < 4; u++) {
+                    const uint32_t m = __ballot_sync(FULL_MASK, keep[u]);
+                    if (keep[u]) {
+                        const unsigned long long pos = bo + __popc(m & lt_mask);
+                        out_row[pos] = row;
+                        out_start[pos] = (int32_t)sgs[u];
+                        out_end[pos] = (int32_t)sge[u];
+                    }
+                    bo += __popc(m);
+                }
+            }
+        }
     }
 }
 
@@ -169,17 +272,34 @@ extern "C" int giqlb_disjoin(giqlb_ctx* ctx, const giqlb_layout* lay, const int3
                 cudaMemsetAsync(total, 0, 8, ctx->stream);
                 st = launch_scan<OpAddU64>(ctx, 2 * nr, InIsNew{sorted}, OutUnique{sorted, bp, total, 2 * nr});
             }
-            if (st == GIQLB_OK) st = fetch_scalars(ctx, total, 1);
+            if (st == GIQLB_OK) st = fetch_scalars_checked(ctx, total, 1);
             if (st == GIQLB_OK) n_bp = ctx->h_scalars[0];
         }
     }
-    DisjoinView V{bp, n_bp, REF->gs, REF->pmax, nr, self_reference ? 0 : 1};
+    uint8_t* cov = nullptr;
+    DisjoinView V{bp, n_bp, REF->gs, REF->pmax, nr, self_reference ? 0 : 1, nullptr};
+    if (st == GIQLB_OK && V.filter && n_bp > 0) {
+        st = dev_alloc(ctx, &cov, (size_t)n_bp);
+        if (st == GIQLB_OK) {
+            int64_t blocks = ceil_div(n_bp, 256), cap = (int64_t)ctx->sm_count * 16;
+            disjoin_cover_kernel<<<(unsigned)(blocks < cap ? blocks : cap), 256, 0, ctx->stream>>>(V, cov);
+            ctx->launches_this_call++;
+            ctx->stats.kernels_total++;
+            V.cov = cov;
+        }
+    }
+    unsigned long long* cnt = nullptr;
     if (st == GIQLB_OK) st = dev_alloc(ctx, &off, (size_t)n_t);
+    if (st == GIQLB_OK) st = dev_alloc(ctx, &cnt, (size_t)n_t);
     if (st == GIQLB_OK) {
         cudaMemsetAsync(total, 0, 8, ctx->stream);
-        st = launch_scan<OpAddU64>(ctx, n_t, InSegCount{T, V}, OutOffsets{off, total, n_t});
+        int64_t blocks = ceil_div(n_t, 256), cap = (int64_t)ctx->sm_count * 16;
+        disjoin_count_kernel<<<(unsigned)(blocks < cap ? blocks : cap), 256, 0, ctx->stream>>>(T, V, cnt);
+        ctx->launches_this_call++;
+        ctx->stats.kernels_total++;
+        st = launch_scan<OpAddU64>(ctx, n_t, InCounts{cnt}, OutOffsets{off, total, n_t});
     }
-    if (st == GIQLB_OK) st = fetch_scalars(ctx, total, 1);
+    if (st == GIQLB_OK) st = fetch_scalars_checked(ctx, total, 1);
     int64_t n_out = st == GIQLB_OK ? ctx->h_scalars[0] : 0;
     if (st == GIQLB_OK) {
         *n_out_host = n_out;
@@ -193,7 +313,7 @@ extern "C" int giqlb_disjoin(giqlb_ctx* ctx, const giqlb_layout* lay, const int3
         ctx->stats.kernels_total++;
         if (cudaGetLastError() != cudaSuccess) st = giqlb_fail(ctx, GIQLB_ERR_CUDA, "disjoin: emit launch failed");
     }
-    dev_free(ctx, ka); dev_free(ctx, kb); dev_free(ctx, va); dev_free(ctx, vb); dev_free(ctx, bp); dev_free(ctx, off);
+    dev_free(ctx, ka); dev_free(ctx, kb); dev_free(ctx, va); dev_free(ctx, vb); dev_free(ctx, bp); dev_free(ctx, off); dev_free(ctx, cnt); dev_free(ctx, cov);
     if (st != GIQLB_OK) return st;
     ctx->stats.rows_in[0] = n_t;
     ctx->stats.rows_in[1] = nr;

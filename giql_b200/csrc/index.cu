@@ -294,6 +294,19 @@ bucket_dir_kernel(const uint32_t* __restrict__ a, int64_t n, int shift, uint32_t
     }
 }
 
+// block maxima of ge: one warp per 32-row block (bmax1), then one warp per 32 entries of bmax1 (bmax2)
+__global__ void __launch_bounds__(256)
+block_max_kernel(const uint32_t* __restrict__ in, int64_t n, uint32_t* __restrict__ out, int64_t n_out) {
+    const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5, n_warps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    for (int64_t b = warp; b < n_out; b += n_warps) {
+        const int64_t i = b * 32 + lane_id();
+        uint32_t v = i < n ? in[i] : 0u;
+#pragma unroll
+        for (int d = 16; d > 0; d >>= 1) v = max(v, __shfl_xor_sync(FULL_MASK, v, d));
+        if (lane_id() == 0) out[b] = v;
+    }
+}
+
 inline int grid_for(const giqlb_ctx* ctx, int64_t n, int threads, int per_sm) {
     int64_t want = ceil_div(n, threads);
     int64_t cap = (int64_t)ctx->sm_count * per_sm;
@@ -471,6 +484,8 @@ extern "C" int giqlb_index_free(giqlb_ctx* ctx, giqlb_index* ix) {
         dev_free(ctx, ix->pos_by_end);
         dev_free(ctx, ix->d_block_off);
         dev_free(ctx, ix->d_counters);
+        dev_free(ctx, ix->bmax1);
+        dev_free(ctx, ix->bmax2);
         dev_free(ctx, ix->dir_gs);
         dev_free(ctx, ix->dir_pmax);
         dev_free(ctx, ix->dir_ges);
@@ -723,6 +738,8 @@ extern "C" int giqlb_index_group_by_strand(giqlb_ctx* ctx, giqlb_index* ix) {
         ix->pmax = nullptr; ix->ge_sorted = nullptr; ix->pos_by_end = nullptr;
         dev_free(ctx, ix->dir_gs); dev_free(ctx, ix->dir_pmax); dev_free(ctx, ix->dir_ges); dev_free(ctx, ix->d_dir_slot);
         ix->dir_gs = ix->dir_pmax = ix->dir_ges = nullptr; ix->d_dir_slot = nullptr;
+        dev_free(ctx, ix->bmax1); dev_free(ctx, ix->bmax2);
+        ix->bmax1 = ix->bmax2 = nullptr;
     }
     GIQLB_TRY(dev_alloc(ctx, &ix->d_block_off, (size_t)GIQLB_MAX_STRAND_CODES + 1));
     CUDA_TRY(ctx, cudaMemcpyAsync(ix->d_block_off, ix->block_off, sizeof(ix->block_off), cudaMemcpyHostToDevice, ctx->stream));
@@ -771,6 +788,24 @@ int giqlb_index_ensure_end_sorted(giqlb_ctx* ctx, giqlb_index* ix) {
         ix->ge_sorted = nullptr; ix->pos_by_end = nullptr;
     }
     return st;
+}
+
+int giqlb_index_ensure_block_max(giqlb_ctx* ctx, giqlb_index* ix) {
+    if (ix->bmax1 || ix->n == 0) return GIQLB_OK;
+    const int64_t n1 = ceil_div(ix->n, 32), n2 = ceil_div(n1, 32);
+    GIQLB_TRY(dev_alloc(ctx, &ix->bmax1, (size_t)n1 + 32));   // padded: bmax2's last warp reads a full 32 entries
+    int st = dev_alloc(ctx, &ix->bmax2, (size_t)n2 + 1);
+    if (st != GIQLB_OK) {
+        dev_free(ctx, ix->bmax1);
+        ix->bmax1 = nullptr;
+        return st;
+    }
+    PhaseSpan ps(ctx, GIQLB_PH_SCAN_MAX);
+    block_max_kernel<<<grid_for(ctx, n1 * 32, 256, 16), 256, 0, ctx->stream>>>(ix->ge, ix->n, ix->bmax1, n1);
+    LAUNCH_CHECK(ctx);
+    block_max_kernel<<<grid_for(ctx, n2 * 32, 256, 16), 256, 0, ctx->stream>>>(ix->bmax1, n1, ix->bmax2, n2);
+    LAUNCH_CHECK(ctx);
+    return GIQLB_OK;
 }
 
 // Bucket directories of the index's ascending arrays, one slot per strand block that holds rows.  The bucket width is

@@ -38,6 +38,7 @@
 #include <cuda/ptx>
 
 #include "common.cuh"
+#include "scan.cuh"
 
 namespace {
 
@@ -1002,8 +1003,8 @@ __device__ __forceinline__ void general_candidates(uint32_t lgs, uint32_t lge, c
 }
 
 __global__ void __launch_bounds__(JB)
-join_count_tiles_general_kernel(JoinSide L, JoinSide R, const uint32_t* __restrict__ pmax,
-                                unsigned long long* __restrict__ tile_cnt) {
+join_count_tiles_general_kernel(JoinSide L, JoinSide R, const uint32_t* __restrict__ pmax, const uint32_t* __restrict__ m1,
+                                const uint32_t* __restrict__ m2, unsigned long long* __restrict__ tile_cnt) {
     __shared__ unsigned long long s_red[JB / 32];
     const int64_t base = (int64_t)blockIdx.x * JT;
     unsigned long long cnt = 0;
@@ -1014,7 +1015,9 @@ join_count_tiles_general_kernel(JoinSide L, JoinSide R, const uint32_t* __restri
             uint32_t lgs = L.gs[i], lge = L.ge[i];
             int64_t lo, hi;
             general_candidates(lgs, lge, R.gs, pmax, R.n, lo, hi);
-            for (int64_t k = lo; k < hi; k++) cnt += __ldg(R.ge + k) > lgs;
+            // candidates are visited through the block maxima of R.ge, so a long right row early on the chromosome does
+            // not make every later left row test all the rows in between
+            for (int64_t k = next_end_above(R.ge, m1, m2, lo, hi, lgs); k < hi; k = next_end_above(R.ge, m1, m2, k + 1, hi, lgs)) cnt++;
         }
     }
     cnt = warp_reduce_add(cnt);
@@ -1028,8 +1031,8 @@ join_count_tiles_general_kernel(JoinSide L, JoinSide R, const uint32_t* __restri
 }
 
 __global__ void __launch_bounds__(JB)
-join_emit_general_kernel(JoinSide L, JoinSide R, const uint32_t* __restrict__ pmax, int64_t n_tiles,
-                         const unsigned long long* __restrict__ tile_off, int32_t* __restrict__ out_l,
+join_emit_general_kernel(JoinSide L, JoinSide R, const uint32_t* __restrict__ pmax, const uint32_t* __restrict__ m1,
+                         const uint32_t* __restrict__ m2, int64_t n_tiles, const unsigned long long* __restrict__ tile_off, int32_t* __restrict__ out_l,
                          int32_t* __restrict__ out_r, int64_t capacity) {
     __shared__ unsigned long long s_scratch[JB / 32 + 2];
     if ((long long)tile_off[n_tiles] > capacity) return;
@@ -1044,19 +1047,17 @@ join_emit_general_kernel(JoinSide L, JoinSide R, const uint32_t* __restrict__ pm
         if (i < L.n) {
             lgs = L.gs[i];
             general_candidates(lgs, L.ge[i], R.gs, pmax, R.n, lo, hi);
-            for (int64_t k = lo; k < hi; k++) cnt += __ldg(R.ge + k) > lgs;
+            for (int64_t k = next_end_above(R.ge, m1, m2, lo, hi, lgs); k < hi; k = next_end_above(R.ge, m1, m2, k + 1, hi, lgs)) cnt++;
         }
         unsigned long long tot;
         unsigned long long o = carry + block_excl_scan_add<unsigned long long>(cnt, s_scratch, &tot);
         carry += tot;
         if (cnt) {
             int32_t lr = L.rid[i];
-            for (int64_t k = lo; k < hi; k++) {
-                if (__ldg(R.ge + k) > lgs) {
-                    out_l[o] = lr;
-                    out_r[o] = R.rid[k];
-                    o++;
-                }
+            for (int64_t k = next_end_above(R.ge, m1, m2, lo, hi, lgs); k < hi; k = next_end_above(R.ge, m1, m2, k + 1, hi, lgs)) {
+                out_l[o] = lr;
+                out_r[o] = R.rid[k];
+                o++;
             }
         }
         __syncthreads();
@@ -1091,7 +1092,8 @@ probe_exists_kernel(ProbeCols P, const uint32_t* __restrict__ rgs, const uint32_
 __global__ void __launch_bounds__(256)
 probe_count_kernel(ProbeCols P, const uint32_t* __restrict__ rgs, const uint32_t* __restrict__ rge,
                    const uint32_t* __restrict__ pmax, const uint32_t* __restrict__ rge_sorted, int64_t nr,
-                   int r_has_degenerate, ProbeDirs D, long long* __restrict__ counts) {
+                   int r_has_degenerate, ProbeDirs D, const uint32_t* __restrict__ m1, const uint32_t* __restrict__ m2,
+                   long long* __restrict__ counts) {
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < P.n; i += (int64_t)gridDim.x * blockDim.x) {
         uint32_t gs, ge;
         long long c = 0;
@@ -1102,12 +1104,35 @@ probe_count_kernel(ProbeCols P, const uint32_t* __restrict__ rgs, const uint32_t
                 c = ub - dir_upper_bound(D.ges, D.shift, D.last, rge_sorted, gs);
             } else {
                 int64_t lb = upper_bound_dev<uint32_t, int64_t>(pmax, 0, ub, gs);
-                for (int64_t k = lb; k < ub; k++) c += __ldg(rge + k) > gs;
+                for (int64_t k = next_end_above(rge, m1, m2, lb, ub, gs); k < ub; k = next_end_above(rge, m1, m2, k + 1, ub, gs)) c++;
             }
         }
         counts[i] = c;
     }
 }
+
+// ---- proper / degenerate split of an index ---------------------------------------------------------------------------
+// One stable compaction pass deals the rows of a sorted index into two sorted sub-indexes: proper rows (end > start) and
+// degenerate ones.  The join then runs its fast path on the proper rows and the literal-predicate scan only where a
+// degenerate row is involved, instead of sending the whole join down the general path for one zero-width row.
+struct InIsProper {
+    const uint32_t *gs, *ge;
+    __device__ unsigned long long operator()(int64_t i) const { return ge[i] > gs[i] ? 1ull : 0ull; }
+};
+struct OutSplitRows {
+    const uint32_t *gs, *ge;
+    const int32_t* rid;
+    uint32_t *pgs, *pge, *dgs, *dge;
+    int32_t *prid, *drid;
+    __device__ void operator()(int64_t i, unsigned long long excl, unsigned long long v) const {
+        if (v) {
+            pgs[excl] = gs[i]; pge[excl] = ge[i]; prid[excl] = rid[i];
+        } else {
+            const int64_t d = i - (int64_t)excl;
+            dgs[d] = gs[i]; dge[d] = ge[i]; drid[d] = rid[i];
+        }
+    }
+};
 
 inline JoinSide side_of(const giqlb_index* ix) { return JoinSide{ix->gs, ix->ge, ix->rid, ix->n}; }
 
@@ -1163,9 +1188,10 @@ static int plan_enqueue(giqlb_ctx* ctx, giqlb_index* L, giqlb_index* R, giqlb_jo
             st = giqlb_fail(ctx, GIQLB_ERR_CUDA, "intersects: memset failed");
     } else if (st == GIQLB_OK && p->general) {
         st = giqlb_index_ensure_pmax(ctx, R);
+        if (st == GIQLB_OK) st = giqlb_index_ensure_block_max(ctx, R);
         if (st == GIQLB_OK) {
             PhaseSpan ps(ctx, GIQLB_PH_JOIN_COUNT);
-            join_count_tiles_general_kernel<<<(unsigned)n_tiles, JB, 0, ctx->stream>>>(side_of(L), side_of(R), R->pmax, cnt);
+            join_count_tiles_general_kernel<<<(unsigned)n_tiles, JB, 0, ctx->stream>>>(side_of(L), side_of(R), R->pmax, R->bmax1, R->bmax2, cnt);
             ctx->launches_this_call++;
             ctx->stats.kernels_total++;
         }
@@ -1198,7 +1224,7 @@ static int emit_enqueue(giqlb_ctx* ctx, giqlb_joinplan* p, int32_t* out_l, int32
     if (n_tiles == 0) return GIQLB_OK;
     PhaseSpan ps(ctx, GIQLB_PH_JOIN_EMIT);
     if (p->general) {
-        join_emit_general_kernel<<<(unsigned)n_tiles, JB, 0, ctx->stream>>>(side_of(p->L), side_of(p->R), p->R->pmax, n_tiles,
+        join_emit_general_kernel<<<(unsigned)n_tiles, JB, 0, ctx->stream>>>(side_of(p->L), side_of(p->R), p->R->pmax, p->R->bmax1, p->R->bmax2, n_tiles,
                                                                             p->tile_off, out_l, out_r, capacity);
     } else {
         const int64_t cap = (int64_t)ctx->sm_count * 8;
@@ -1215,6 +1241,79 @@ static void join_stats(giqlb_ctx* ctx, const giqlb_index* L, const giqlb_index* 
     ctx->stats.rows_in[1] = R->n;
     ctx->stats.rows_out = total;
     ctx->stats.algorithmic_bytes = 12 * (L->n + R->n) + 8 * total;
+}
+
+static giqlb_index* sub_index(const giqlb_index* ix, int64_t n, int64_t n_degenerate) {
+    giqlb_index* s = new (std::nothrow) giqlb_index();
+    if (!s) return nullptr;
+    s->n = n;
+    s->layout = ix->layout;
+    s->tie_by_end = ix->tie_by_end;
+    s->n_degenerate = n_degenerate;
+    s->n_negative = 0;            // not tracked for the parts (only n_degenerate steers the join)
+    s->resolved = true;
+    s->block_off[1] = n;
+    for (int i = 2; i <= GIQLB_MAX_STRAND_CODES; i++) s->block_off[i] = n;
+    return s;
+}
+
+static int index_split(giqlb_ctx* ctx, const giqlb_index* ix, giqlb_index** proper, giqlb_index** degenerate) {
+    using namespace giqlb_scan;
+    *proper = sub_index(ix, ix->n - ix->n_degenerate, 0);
+    *degenerate = sub_index(ix, ix->n_degenerate, ix->n_degenerate);
+    if (!*proper || !*degenerate) return GIQLB_ERR_NOMEM;
+    giqlb_index *P = *proper, *D = *degenerate;
+    int st = dev_alloc(ctx, &P->gs, (size_t)P->n + 1);
+    if (st == GIQLB_OK) st = dev_alloc(ctx, &P->ge, (size_t)P->n + 1);
+    if (st == GIQLB_OK) st = dev_alloc(ctx, &P->rid, (size_t)P->n + 1);
+    if (st == GIQLB_OK) st = dev_alloc(ctx, &D->gs, (size_t)D->n + 1);
+    if (st == GIQLB_OK) st = dev_alloc(ctx, &D->ge, (size_t)D->n + 1);
+    if (st == GIQLB_OK) st = dev_alloc(ctx, &D->rid, (size_t)D->n + 1);
+    if (st == GIQLB_OK && ix->n > 0) {
+        PhaseSpan ps(ctx, GIQLB_PH_SELECT);
+        st = launch_scan<OpAddU64>(ctx, ix->n, InIsProper{ix->gs, ix->ge}, OutSplitRows{ix->gs, ix->ge, ix->rid, P->gs, P->ge, D->gs, D->ge, P->rid, D->rid});
+    }
+    return st;
+}
+
+// Join with degenerate rows (end <= start) on either side: the proper rows of both tables take the fused fast path; the
+// literal predicate is scanned only for (degenerate L rows x all R rows) and (proper L rows x degenerate R rows) — the
+// three parts are disjoint and cover every pair.  Pairs land back to back in out_l / out_r.
+static int join_with_degenerate_rows(giqlb_ctx* ctx, giqlb_index* L, giqlb_index* R, int32_t* out_l, int32_t* out_r, int64_t capacity,
+                                     int64_t* total_out) {
+    giqlb_index *lp = nullptr, *ld = nullptr, *rp = nullptr, *rd = nullptr;
+    giqlb_joinplan *plan_a = nullptr, *plan_b = nullptr;
+    int64_t t_fast = 0, t_a = 0, t_b = 0;
+    int st = index_split(ctx, L, &lp, &ld);
+    if (st == GIQLB_OK) st = index_split(ctx, R, &rp, &rd);
+    if (st == GIQLB_OK) {   // 1. proper x proper: the fused single-pass join (reports the exact total even when it does not fit)
+        st = giqlb_intersects_join_impl(ctx, lp, rp, out_l, out_r, capacity, &t_fast, false);
+        if (st == GIQLB_ERR_CAPACITY) st = GIQLB_OK;
+    }
+    if (st == GIQLB_OK && ld->n > 0 && R->n > 0) {   // 2. degenerate L rows against the whole right table
+        st = plan_enqueue(ctx, ld, R, &plan_a);
+        if (st == GIQLB_OK) st = fetch_scalars_checked(ctx, ctx->d_scalars, 1);
+        if (st == GIQLB_OK) t_a = ctx->h_scalars[0];
+    }
+    if (st == GIQLB_OK && lp->n > 0 && rd->n > 0) {  // 3. proper L rows against the degenerate right rows
+        st = plan_enqueue(ctx, lp, rd, &plan_b);
+        if (st == GIQLB_OK) st = fetch_scalars_checked(ctx, ctx->d_scalars, 1);
+        if (st == GIQLB_OK) t_b = ctx->h_scalars[0];
+    }
+    const int64_t total = t_fast + t_a + t_b;
+    if (st == GIQLB_OK && total <= capacity) {
+        if (plan_a && t_a > 0) st = emit_enqueue(ctx, plan_a, out_l + t_fast, out_r + t_fast, t_a);
+        if (st == GIQLB_OK && plan_b && t_b > 0) st = emit_enqueue(ctx, plan_b, out_l + t_fast + t_a, out_r + t_fast + t_a, t_b);
+        if (st == GIQLB_OK && cudaStreamSynchronize(ctx->stream) != cudaSuccess) st = giqlb_fail(ctx, GIQLB_ERR_CUDA, "intersects_join: sync failed");
+    }
+    giqlb_joinplan_free(ctx, plan_a);
+    giqlb_joinplan_free(ctx, plan_b);
+    giqlb_index_free(ctx, lp);
+    giqlb_index_free(ctx, ld);
+    giqlb_index_free(ctx, rp);
+    giqlb_index_free(ctx, rd);
+    *total_out = st == GIQLB_OK ? total : -1;
+    return st;
 }
 
 extern "C" int giqlb_intersects_plan(giqlb_ctx* ctx, giqlb_index* L, giqlb_index* R, giqlb_joinplan** out,
@@ -1266,8 +1365,11 @@ int giqlb_intersects_join_impl(giqlb_ctx* ctx, giqlb_index* L, giqlb_index* R, i
     if (!speculate) GIQLB_TRY(giqlb_index_resolve(ctx, L, R));
     int64_t total = 0;
     int st = GIQLB_OK;
-    if (!speculate && (empty || L->n_degenerate + R->n_degenerate > 0)) {
-        // degenerate rows: two-pass general path (the emit kernel writes nothing when the total exceeds `capacity`)
+    if (!speculate && !empty && L->n_degenerate + R->n_degenerate > 0 && L->n_degenerate < L->n && R->n_degenerate < R->n) {
+        // some degenerate rows: fast path for the proper rows, literal-predicate scan only where a degenerate row takes part
+        st = join_with_degenerate_rows(ctx, L, R, out_l, out_r, capacity, &total);
+    } else if (!speculate && (empty || L->n_degenerate + R->n_degenerate > 0)) {
+        // a table of degenerate rows only: two-pass general path (the emit kernel writes nothing when the total exceeds `capacity`)
         giqlb_joinplan* p = nullptr;
         GIQLB_TRY(plan_enqueue(ctx, L, R, &p));
         st = capacity > 0 ? emit_enqueue(ctx, p, out_l, out_r, capacity) : GIQLB_OK;
@@ -1388,12 +1490,14 @@ extern "C" int giqlb_intersects_count_rows(giqlb_ctx* ctx, const giqlb_layout* l
     const int r_deg = R->n_degenerate > 0;
     if (!r_deg) GIQLB_TRY(giqlb_index_ensure_end_sorted(ctx, R));
     if (n > 0 && R->n > 0) GIQLB_TRY(giqlb_index_ensure_dirs(ctx, R, false, !r_deg));
+    if (r_deg) GIQLB_TRY(giqlb_index_ensure_block_max(ctx, R));
     if (n > 0) {
         int64_t blocks = ceil_div(n, 256 * 4);
         int64_t cap = (int64_t)ctx->sm_count * 16;
         PhaseSpan ps(ctx, GIQLB_PH_PROBE);
         probe_count_kernel<<<(unsigned)(blocks < cap ? blocks : cap), 256, 0, ctx->stream>>>(
-            P, R->gs, R->ge, R->pmax, R->ge_sorted, R->n, r_deg, ProbeDirs{R->dir_gs, R->dir_ges, R->dir_shift, R->dir_stride - 2}, (long long*)counts_by_row);
+            P, R->gs, R->ge, R->pmax, R->ge_sorted, R->n, r_deg, ProbeDirs{R->dir_gs, R->dir_ges, R->dir_shift, R->dir_stride - 2}, R->bmax1, R->bmax2,
+            (long long*)counts_by_row);
         LAUNCH_CHECK(ctx);
     }
     ctx->stats.rows_in[0] = n;

@@ -37,6 +37,8 @@ struct TargetView {
     const int64_t* block_off;    // device [257]; nullptr when not grouped
     int64_t n;
     // bucket directories over gs / pmax / ge_sorted of every strand block (giqlb_index_ensure_dirs)
+    const uint32_t* bmax1;       // block maxima of ge over 32 / 1024 rows (giqlb_index_ensure_block_max)
+    const uint32_t* bmax2;
     const uint32_t* dir_gs;
     const uint32_t* dir_pmax;
     const uint32_t* dir_ges;
@@ -59,7 +61,7 @@ struct NearestArgs {
 __global__ void __launch_bounds__(128)
 nearest_kernel(ProbeCols Q, const uint8_t* __restrict__ q_strand, const uint32_t* __restrict__ order, TargetView T, NearestArgs A,
                int32_t* __restrict__ tmp_q, int32_t* __restrict__ tmp_t, int32_t* __restrict__ tmp_d, uint8_t* __restrict__ tmp_v,
-               uint32_t* __restrict__ cnt, unsigned long long* __restrict__ total) {
+               uint32_t* __restrict__ cnt, unsigned long long* __restrict__ total, int* __restrict__ err) {
     unsigned long long emitted = 0;
     for (int64_t x = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; x < Q.n; x += (int64_t)gridDim.x * blockDim.x) {
         const int64_t i = order ? (int64_t)order[x] : x;
@@ -99,6 +101,7 @@ nearest_kernel(ProbeCols Q, const uint8_t* __restrict__ q_strand, const uint32_t
                                                            A.signed_ != 0, &d);
                 tmp_q[slot0 + n_out] = (int32_t)i;
                 tmp_t[slot0 + n_out] = rid[pos];
+                if (ok && (d > INT32_MAX || d < INT32_MIN)) err[1] = 3;   // reported as GIQLB_ERR_RANGE by the checked fetch
                 tmp_d[slot0 + n_out] = ok ? (int32_t)d : 0;
                 tmp_v[slot0 + n_out] = ok ? 1 : 0;
                 n_out++;
@@ -115,8 +118,14 @@ nearest_kernel(ProbeCols Q, const uint8_t* __restrict__ q_strand, const uint32_t
                 // 1. overlaps, in index order
                 const uint32_t* pmax = T.pmax + blo;
                 int64_t j = min(ub, dir_upper_bound(T.dir_pmax + (size_t)slot * T.dir_stride, T.dir_shift, dlast, pmax, qs_lin));   // first row whose running max end > q.start
-                for (; j < ub && n_out < (uint32_t)A.k; j++)
-                    if (ge[j] > qs_lin) emit(j);
+                // (rows are visited through the block maxima of ge: behind one long target row the running max stays high
+                //  for the rest of the chromosome, and a plain scan would test every row before the query)
+                while (n_out < (uint32_t)A.k) {
+                    j = next_end_above(T.ge, T.bmax1, T.bmax2, blo + j, blo + ub, qs_lin) - blo;
+                    if (j >= ub) break;
+                    emit(j);
+                    j++;
+                }
                 // 2. merge of the upstream and downstream streams
                 if (n_out < (uint32_t)A.k) {
                     const uint32_t* ges = T.ge_sorted + blo;
@@ -232,6 +241,7 @@ extern "C" int giqlb_nearest(giqlb_ctx* ctx, const giqlb_layout* lay, const int3
     GIQLB_TRY(giqlb_index_ensure_pmax(ctx, T));
     GIQLB_TRY(giqlb_index_ensure_end_sorted(ctx, T));
     if (T->n > 0) GIQLB_TRY(giqlb_index_ensure_dirs(ctx, T, true, true));
+    GIQLB_TRY(giqlb_index_ensure_block_max(ctx, T));
     uint32_t* cnt = nullptr;
     uint32_t *ka = nullptr, *kb = nullptr, *va = nullptr, *vb = nullptr;
     const uint32_t* order = nullptr;
@@ -261,12 +271,12 @@ extern "C" int giqlb_nearest(giqlb_ctx* ctx, const giqlb_layout* lay, const int3
         PhaseSpan ps(ctx, GIQLB_PH_NEAREST);
         cudaMemsetAsync(total, 0, 8, ctx->stream);
         TargetView V{T->gs, T->ge, T->rid, T->strand, T->pmax, T->ge_sorted, T->pos_by_end,
-                     T->grouped_by_strand ? T->d_block_off : nullptr, T->n,
+                     T->grouped_by_strand ? T->d_block_off : nullptr, T->n, T->bmax1, T->bmax2,
                      T->dir_gs, T->dir_pmax, T->dir_ges, T->d_dir_slot, T->dir_shift, T->dir_stride};
         NearestArgs A{k, max_distance < 0 ? -1ll : (long long)max_distance, stranded != 0, signed_ != 0};
         int64_t blocks = ceil_div(n_q, 128), cap = (int64_t)ctx->sm_count * 32;
         // results land in the output arrays themselves, k slots per query row
-        nearest_kernel<<<(unsigned)(blocks < cap ? blocks : cap), 128, 0, ctx->stream>>>(Q, q_strand, order, V, A, out_q, out_t, out_dist, out_valid, cnt, total);
+        nearest_kernel<<<(unsigned)(blocks < cap ? blocks : cap), 128, 0, ctx->stream>>>(Q, q_strand, order, V, A, out_q, out_t, out_dist, out_valid, cnt, total, ctx->d_err);
         ctx->launches_this_call++;
         ctx->stats.kernels_total++;
         if (cudaGetLastError() != cudaSuccess) st = giqlb_fail(ctx, GIQLB_ERR_CUDA, "nearest: launch failed");

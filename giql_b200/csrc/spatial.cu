@@ -38,6 +38,35 @@ __device__ __forceinline__ void candidates(uint32_t xgs, uint32_t xge, const Sid
     hi = upper_bound_dev<uint32_t, int64_t>(Y.gs, lo, Y.n, top);
 }
 
+// A container row with more than SP_HEAVY candidates (a chromosome-spanning interval) is not walked by its own thread:
+// the lanes of its warp take its candidate run together, 32 rows per step, so one long row costs the warp a few thousand
+// steps instead of serialising ~10^5 dependent loads on one thread while the rest of the grid has finished.
+constexpr int64_t SP_HEAVY = 128;
+
+__device__ __forceinline__ unsigned long long warp_count_contained(const uint32_t* __restrict__ yge, int64_t lo, int64_t hi, uint32_t xge) {
+    unsigned long long c = 0;
+#pragma unroll 8
+    for (int64_t k = lo + lane_id(); k < hi; k += 32) c += __ldg(yge + k) <= xge;   // independent loads: eight in flight per lane
+    return warp_reduce_add(c);
+}
+
+// per-thread count of row i's contained candidates; heavy runs are counted by the whole warp (all lanes must call)
+__device__ __forceinline__ unsigned long long count_row(const Side& Y, bool live, int64_t lo, int64_t hi, uint32_t xge) {
+    const bool heavy = live && hi - lo > SP_HEAVY;
+    unsigned long long cnt = 0;
+    if (live && !heavy)
+        for (int64_t k = lo; k < hi; k++) cnt += __ldg(Y.ge + k) <= xge;
+    uint32_t todo = __ballot_sync(FULL_MASK, heavy);
+    while (todo) {
+        const int src = __ffs(todo) - 1;
+        todo &= todo - 1;
+        const unsigned long long c = warp_count_contained(Y.ge, __shfl_sync(FULL_MASK, lo, src), __shfl_sync(FULL_MASK, hi, src),
+                                                          __shfl_sync(FULL_MASK, xge, src));
+        if ((int)lane_id() == src) cnt = c;
+    }
+    return cnt;
+}
+
 __global__ void __launch_bounds__(SPB)
 contains_count_kernel(Side X, Side Y, const uint32_t* __restrict__ base, int32_t n_codes, int y_has_negative,
                       unsigned long long* __restrict__ tile_cnt) {
@@ -47,12 +76,14 @@ contains_count_kernel(Side X, Side Y, const uint32_t* __restrict__ base, int32_t
 #pragma unroll 1
     for (int j = 0; j < SP_IPT; j++) {
         const int64_t i = t0 + j * SPB + threadIdx.x;
-        if (i < X.n) {
-            const uint32_t xgs = X.gs[i], xge = X.ge[i];
-            int64_t lo, hi;
-            candidates(xgs, xge, Y, base, n_codes, y_has_negative, lo, hi);
-            for (int64_t k = lo; k < hi; k++) cnt += __ldg(Y.ge + k) <= xge;
+        const bool live = i < X.n;
+        int64_t lo = 0, hi = 0;
+        uint32_t xge = 0;
+        if (live) {
+            xge = X.ge[i];
+            candidates(X.gs[i], xge, Y, base, n_codes, y_has_negative, lo, hi);
         }
+        cnt += count_row(Y, live, lo, hi, xge);
     }
     cnt = warp_reduce_add(cnt);
     if (lane_id() == 0) s_red[warp_id()] = cnt;
@@ -70,28 +101,59 @@ contains_emit_kernel(Side X, Side Y, const uint32_t* __restrict__ base, int32_t 
     __shared__ unsigned long long s_scratch[SPB / 32 + 2];
     const int64_t t0 = (int64_t)blockIdx.x * SPT;
     unsigned long long carry = tile_off[blockIdx.x];
+    const uint32_t lt_mask = (1u << lane_id()) - 1u;
 #pragma unroll 1
     for (int j = 0; j < SP_IPT; j++) {
         const int64_t i = t0 + j * SPB + threadIdx.x;
-        unsigned long long cnt = 0;
+        const bool live = i < X.n;
         int64_t lo = 0, hi = 0;
         uint32_t xge = 0;
-        if (i < X.n) {
+        if (live) {
             xge = X.ge[i];
             candidates(X.gs[i], xge, Y, base, n_codes, y_has_negative, lo, hi);
-            for (int64_t k = lo; k < hi; k++) cnt += __ldg(Y.ge + k) <= xge;
         }
+        const unsigned long long cnt = count_row(Y, live, lo, hi, xge);
         unsigned long long tot;
         unsigned long long o = carry + block_excl_scan_add<unsigned long long>(cnt, s_scratch, &tot);
         carry += tot;
-        if (cnt) {
-            const int32_t xr = X.rid[i];
+        const bool heavy = live && hi - lo > SP_HEAVY;
+        const int32_t xr = live ? X.rid[i] : 0;
+        if (cnt && !heavy) {
             for (int64_t k = lo; k < hi; k++)
                 if (__ldg(Y.ge + k) <= xge) {
                     out_x[o] = xr;
                     out_y[o] = Y.rid[k];
                     o++;
                 }
+        }
+        uint32_t todo = __ballot_sync(FULL_MASK, heavy && cnt);
+        while (todo) {                               // heavy rows: the warp emits the run together, in candidate order
+            const int src = __ffs(todo) - 1;
+            todo &= todo - 1;
+            const int64_t blo = __shfl_sync(FULL_MASK, lo, src), bhi = __shfl_sync(FULL_MASK, hi, src);
+            const uint32_t bxge = __shfl_sync(FULL_MASK, xge, src);
+            const int32_t bxr = __shfl_sync(FULL_MASK, xr, src);
+            unsigned long long bo = __shfl_sync(FULL_MASK, o, src);
+            for (int64_t k0 = blo; k0 < bhi; k0 += 128) {     // four 32-row steps per iteration: their loads are in flight together
+                bool keep[4];
+                int32_t yr[4];
+#pragma unroll
+                for (int u = 0; u < 4; u++) {
+                    const int64_t k = k0 + 32 * u + lane_id();
+                    keep[u] = k < bhi && __ldg(Y.ge + k) <= bxge;
+                    yr[u] = k < bhi ? __ldg(Y.rid + k) : 0;
+                }
+#pragma unroll
+                for (int u = 0; u < 4; u++) {
+                    const uint32_t m = __ballot_sync(FULL_MASK, keep[u]);
+                    if (keep[u]) {
+                        const unsigned long long pos = bo + __popc(m & lt_mask);
+                        out_x[pos] = bxr;
+                        out_y[pos] = yr[u];
+                    }
+                    bo += __popc(m);
+                }
+            }
         }
         __syncthreads();
     }

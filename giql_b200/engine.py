@@ -368,7 +368,14 @@ class Engine:
         return t.to(self.device, non_blocking=pinned)
 
     def _empty(self, n: int, dtype) -> torch.Tensor:
-        return torch.empty(max(int(n), 0), dtype=dtype, device=self.device)
+        try:
+            return torch.empty(max(int(n), 0), dtype=dtype, device=self.device)
+        except torch.cuda.OutOfMemoryError:
+            # the library parks its scratch buffers per context where torch's allocator cannot see them: hand them back
+            # and retry once
+            self.trim()
+            torch.cuda.empty_cache()
+            return torch.empty(max(int(n), 0), dtype=dtype, device=self.device)
 
     # ---- ingest -----------------------------------------------------------------------------------
     def strand_codes(self, col) -> np.ndarray:
@@ -693,8 +700,9 @@ class Engine:
                                                   ctypes.byref(total), ctypes.byref(dict_h))
             if dict_h.value:
                 d = self._take_dictionary(dict_h)
-                left.dictionary = right.dictionary = d
-                n_codes, enc_l = len(d), True
+                if st in (_cabi.OK, _cabi.ERR_CAPACITY):      # the C side marks the codes valid on these two only (pipeline.cu):
+                    left.dictionary = right.dictionary = d    # on any other status the code columns may still hold parked slots
+                    n_codes, enc_l = len(d), True
             if st == _cabi.OK:
                 return PairResult(out_l[: total.value], out_r[: total.value])
             if st != _cabi.ERR_CAPACITY:
@@ -719,8 +727,9 @@ class Engine:
                                                           _ptr(out_l), _ptr(out_r), cap, ctypes.byref(total), ctypes.byref(dict_h))
             if dict_h.value:
                 d = self._take_dictionary(dict_h)
-                left.dictionary = right.dictionary = d
-                n_codes = len(d)
+                if st in (_cabi.OK, _cabi.ERR_CAPACITY):      # see _intersects_one_call
+                    left.dictionary = right.dictionary = d
+                    n_codes = len(d)
             if st == _cabi.OK:
                 return PairResult(out_l[: total.value], out_r[: total.value])
             if st != _cabi.ERR_CAPACITY:

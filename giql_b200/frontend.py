@@ -285,7 +285,19 @@ class _Parser:
         if name.upper() == "DISJOIN" and self.at("op", "("):
             self.take("op", "(")
             target = self.take("id")
-            ref = self.take("id") if self.accept("op", ",") else None
+            ref = None
+            if self.accept("op", ","):
+                # DISJOIN(t, reference := r) / reference => r (src/giql/expressions.py:386-413: one positional argument only)
+                if not (self.at("id") and (self.at("op", ":=", 1) or self.at("op", "=>", 1))):
+                    raise ValueError("DISJOIN accepts at most one positional argument (the target table); got 2. "
+                                     "Pass the reference set as 'reference := ...'.")
+                key = self.take("id").lower()
+                if key != "reference":
+                    raise ValueError(f"DISJOIN got unexpected named argument(s): {key}. Valid arguments: reference.")
+                self.take("op")
+                if self.at("op", "("):
+                    raise UnsupportedQuery("DISJOIN with a subquery reference is finished by the SQL engine")
+                ref = self.take("id")
             self.take("op", ")")
             return {"kind": "disjoin", "table": target, "reference": ref, "alias": self.alias() or target}
         return {"kind": "table", "table": name, "alias": self.alias() or name}
@@ -1103,8 +1115,12 @@ class Session:
             return self._order_limit(q, Result(cols, [_column([r[i] for r in out]) for i in range(len(cols))]), f)
         if q.get("group"):
             return self._group_count(q, f)
+        if kinds == {"count_star"} and not q.get("having"):
+            # SELECT COUNT(*) [AS n] FROM <rows the FROM clause produced>: one row, also over an empty input
+            cols = [p.get("name", "count") for p in proj]
+            return self._order_limit(q, Result(cols, [np.asarray([len(f)], dtype=np.int64) for _ in proj]), f)
         if kinds & {"count_star", "count_col"}:
-            raise UnsupportedQuery("COUNT without GROUP BY (outside MERGE) is finished by the SQL engine")
+            raise UnsupportedQuery("COUNT mixed with other projections without GROUP BY is finished by the SQL engine")
         cols: list[str] = []
         arrays: list[np.ndarray] = []
         sources: list = []

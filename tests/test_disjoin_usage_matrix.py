@@ -1,0 +1,66 @@
+"""The reference's DISJOIN usage matrix (abdenlab/giql tests/test_usage_patterns.py:143-171) against this repo's front-end:
+15 semantic profiles (point / adjacent / nested / identical intervals, duplicate targets, many / single chromosomes,
+reference gaps / supersets, empty target / reference, custom columns, 1-based closed and mixed encodings) x self / reference
+mode x 26 query patterns, with the rows DuckDB returned for the transpiled SQL as snapshotted by the reference
+(tests/golden/disjoin_usage_matrix.json, harvested by harvest_reference_vectors.py).  The front-end is not a SQL engine: the
+shapes it declines (windows, set operations, CTEs, chained table functions ...) raise UnsupportedQuery and are counted;
+every shape it executes must reproduce the snapshot exactly."""
+import json
+from collections import Counter
+from pathlib import Path
+
+import pytest
+
+from backends import OracleBackend
+from giql_b200.frontend import Session, UnsupportedQuery
+from giql_b200.table import Table
+
+CASES = json.loads((Path(__file__).resolve().parent / "golden" / "disjoin_usage_matrix.json").read_text())["cases"]
+
+
+def _run(case, backend):
+    sess = Session(backend)
+    cfgs = {t["name"]: Table(**t) for t in case["tables"] if isinstance(t, dict)}
+    for f in case["fixtures"]:
+        cols = [c[0] for c in f["columns"]]
+        sess.register(f["name"], {c: [r[i] for r in f["rows"]] for i, c in enumerate(cols)}, cfgs.get(f["name"]), columns=cols)
+    rows = sess.execute(case["query"]).rows
+    return sorted(([list(r) for r in rows]), key=repr)
+
+
+def _sweep(backend):
+    outcome, wrong = Counter(), []
+    for case in CASES:
+        try:
+            got = _run(case, backend)
+        except UnsupportedQuery:
+            outcome["declined:" + case["pattern"]] += 1
+            continue
+        if got == case["expected"]:
+            outcome["ok:" + case["pattern"]] += 1
+        else:
+            wrong.append((case["key"], case["query"], got[:3], case["expected"][:3]))
+    return outcome, wrong
+
+
+def test_matrix_is_complete():
+    assert len(CASES) == 690 and len({c["profile"] for c in CASES}) == 15 and {c["mode"] for c in CASES} == {"self", "reference"}
+
+
+def test_every_executed_pattern_reproduces_the_duckdb_snapshot_oracle_backend():
+    outcome, wrong = _sweep(OracleBackend())
+    assert not wrong, wrong[:5]
+    ok = sum(v for k, v in outcome.items() if k.startswith("ok:"))
+    assert ok >= 290, dict(outcome)
+    # the plain table-function shapes are never declined, in any profile or mode
+    for pattern in ("STANDALONE", "ALIASED_PROJECTION"):
+        assert outcome["ok:" + pattern] == 30, (pattern, dict(outcome))
+
+
+@pytest.mark.gpu
+def test_every_executed_pattern_reproduces_the_duckdb_snapshot_on_the_gpu(engine):
+    from giql_b200.frontend import EngineBackend
+
+    outcome, wrong = _sweep(EngineBackend(engine))
+    assert not wrong, wrong[:5]
+    assert sum(v for k, v in outcome.items() if k.startswith("ok:")) >= 290

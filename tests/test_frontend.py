@@ -59,7 +59,7 @@ STATEMENTS = [
     "SELECT MERGE(interval, 30), COUNT(*) FROM peaks",
     "SELECT MERGE(interval, stranded := true) FROM peaks",
     "SELECT name, disjoin_start, disjoin_end FROM DISJOIN(peaks)",
-    "SELECT name, disjoin_start, disjoin_end FROM DISJOIN(peaks, genes)",
+    "SELECT name, disjoin_start, disjoin_end FROM DISJOIN(peaks, reference := genes)",
     "WITH hot AS (SELECT a.chrom, a.start, a.\"end\", a.name FROM peaks a SEMI JOIN genes b ON a.interval INTERSECTS b.interval) "
     "SELECT MERGE(interval) FROM hot",
     "SELECT name, start FROM peaks WHERE interval INTERSECTS 'chr1:0-100000' ORDER BY start DESC LIMIT 5",

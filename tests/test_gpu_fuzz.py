@@ -70,6 +70,16 @@ def test_stranded_residual_fuzz(shape, engine):
         assert sorted(zip(gl.tolist(), gr.tolist())) == want
 
 
+def _tied_outside(T, Q, q, key, t, stranded):
+    """True when a target row NOT emitted shares (start, end) — hence the full ORDER BY key — with emitted row t on the
+    query's chromosome (and strand): the k-th place is then order-ambiguous in the reference itself."""
+    for j in range(len(T["start"])):
+        if j != t and T["chrom"][j] == T["chrom"][t] and T["start"][j] == T["start"][t] and T["end"][j] == T["end"][t]:
+            if not stranded or "strand" not in T or T["strand"][j] == T["strand"][t]:
+                return True
+    return False
+
+
 @pytest.mark.parametrize("shape", [s for s in SHAPES if s != "degenerate"])
 @pytest.mark.parametrize("k,maxd,stranded,signed", [(1, None, False, False), (3, None, True, True), (2, 150, False, True), (4, 40, True, False)])
 def test_nearest_fuzz(shape, k, maxd, stranded, signed, engine):
@@ -91,7 +101,18 @@ def test_nearest_fuzz(shape, k, maxd, stranded, signed, engine):
     for q in g:
         nk = lambda d: (d is None, d or 0)
         assert sorted((d for d, _ in g[q]), key=nk) == sorted((d for d, _ in w[q]), key=nk), (shape, q)
-    assert got == want or all(len(g[q]) == len(w[q]) for q in g)
+    # targets: the full ORDER BY key (|distance|, start, end) of every emitted row must agree position by position, and the
+    # target row itself wherever that key is unique among the query's candidates (engine and oracle both break full-key ties
+    # by target row id, so in practice the rows are identical; the weaker statement is what the reference guarantees)
+    full = lambda t, d: ((d is None, abs(d or 0)), int(T["start"][t]), int(T["end"][t]))
+    for q in g:
+        gk = sorted((full(t, d), t) for d, t in g[q])
+        wk = sorted((full(t, d), t) for d, t in w[q])
+        assert [k for k, _ in gk] == [k for k, _ in wk], (shape, q)
+        keys = [k for k, _ in wk]
+        for (k1, t1), (k2, t2) in zip(gk, wk):
+            if keys.count(k1) == 1 and not _tied_outside(T, Q, q, k1, t2, stranded):
+                assert t1 == t2, (shape, q, k1)
 
 
 @pytest.mark.parametrize("shape", [s for s in SHAPES if s != "degenerate"])

@@ -680,3 +680,50 @@ def test_join_from_bed_equals_join_from_columns(engine, tmp_path):
     cb = engine.table({"chrom": B["chrom"], "start": B["start"], "end": B["end"], "strand": B["strand"]})
     assert np.array_equal(engine.intersects(ta, tb).sorted_packed(), engine.intersects(ca, cb).sorted_packed())
     assert np.array_equal(engine.intersects_stranded(ta, tb).sorted_packed(), engine.intersects_stranded(ca, cb).sorted_packed())
+
+
+def test_one_chromosome_spanning_row_does_not_serialise_the_operators(engine, c_oracle):
+    """SURVEY §7's skew hazard: one chr1-spanning interval among 300k rows of each table.  Every operator must still give the
+    oracle's answer, and — measured by scripts/skew_probe.py at 1M rows, profiles/r02_skew_probe.txt — at most a small
+    multiple of its time on the same tables without that row (before round 2: NEAREST k=5 x11, DISJOIN x44 / x344, CONTAINS x23)."""
+    import time
+
+    import torch
+
+    from giql_b200 import synth
+
+    A, B = synth.peaks(300_000, 51), synth.peaks(300_000, 52)
+    ta0 = engine.table_from_codes(A["code"], A["start"], A["end"], A["names"])
+    tb0 = engine.table_from_codes(B["code"], B["start"], B["end"], ta0.dictionary)
+    for T in (A, B):
+        T["start"][0], T["end"][0], T["code"][0] = 0, int(synth.LENGTHS[0]) - 1, 0
+    ta = engine.table_from_codes(A["code"], A["start"], A["end"], A["names"])
+    tb = engine.table_from_codes(B["code"], B["start"], B["end"], ta.dictionary)
+    n = len(A["names"])
+    exp = c_oracle.intersects_pairs(A["code"], A["start"], A["end"], B["code"], B["start"], B["end"], n)
+    assert np.array_equal(engine.intersects(ta, tb).sorted_packed(), (exp[:, 0] << 32) | exp[:, 1])
+    q, t, d, v = c_oracle.nearest(A["code"], A["start"], A["end"], B["code"], B["start"], B["end"], n, k=5)
+    res = engine.nearest(ta, tb, k=5)
+    got = sorted(zip(res.query_rows.cpu().tolist(), np.abs(res.distance.cpu().numpy()).tolist()))
+    assert got == sorted(zip(q.tolist(), np.abs(d).tolist()))
+    row, s, e = c_oracle.disjoin(A["code"], A["start"], A["end"], B["code"], B["start"], B["end"], n_codes=n)
+    seg = engine.disjoin(ta, tb)
+    gd = np.stack([seg.target_rows.cpu().numpy(), seg.start.cpu().numpy(), seg.end.cpu().numpy()], axis=1).astype(np.int64)
+    assert np.array_equal(gd[np.lexsort((gd[:, 1], gd[:, 0]))], np.stack([row, s, e], axis=1).astype(np.int64))
+    for op, fn in (("contains", engine.contains), ("within", engine.within)):
+        expc = c_oracle.spatial_pairs(A["code"], A["start"], A["end"], B["code"], B["start"], B["end"], n, op)
+        assert np.array_equal(fn(ta, tb).sorted_packed(), (expc[:, 0] << 32) | expc[:, 1])
+
+    def ms(fn):
+        fn()
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for _ in range(3):
+            fn()
+        torch.cuda.synchronize()
+        return (time.perf_counter() - t0) / 3
+
+    for name, fn in (("nearest k=5", lambda a, b: engine.nearest(a, b, k=5)), ("disjoin", lambda a, b: engine.disjoin(a, b)),
+                     ("contains", lambda a, b: engine.contains(a, b)), ("intersects", lambda a, b: engine.intersects(a, b))):
+        uniform, skewed = ms(lambda: fn(ta0, tb0)), ms(lambda: fn(ta, tb))
+        assert skewed < 6 * uniform + 2e-3, (name, uniform, skewed)      # generous: wall clock of a shared box; see the probe for numbers
