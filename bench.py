@@ -554,10 +554,15 @@ def run_b200(args):
     roofline = {"bound": "hbm", "kernel": dom, "achieved": round(achieved, 1), "peak": hbm_peak, "unit": "GB/s",
                 "frac": round(achieved / hbm_peak, 4), "traffic": None, "peak_source": peak_src,
                 "ms_per_launch": round(per_launch_ms, 4), "algorithmic_bytes_per_launch": int(per_launch_bytes)}
+    # DRAM bytes per launch cannot be measured without a profiler: the figure comes from the committed ncu capture of the
+    # same command at N = 1 (profiles/traffic.json names the capture), and is left null for sharded runs, whose launches
+    # move a different number of rows
     traffic_file = ROOT / "profiles" / "traffic.json"
-    if traffic_file.exists():
+    if traffic_file.exists() and world == 1:
         try:
-            roofline["traffic"] = json.loads(traffic_file.read_text()).get(dom)
+            tj = json.loads(traffic_file.read_text())
+            roofline["traffic"] = tj.get(dom)
+            roofline["traffic_source"] = tj.get("_source", {}).get(dom)
         except Exception:
             pass
     join_ms = sum(phases[p]["ms_per_step"] for p in ("join_count", "join_scan", "join_emit") if p in phases)

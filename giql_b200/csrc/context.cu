@@ -140,20 +140,67 @@ struct OutInclMax {
     __device__ void operator()(int64_t i, uint32_t excl, uint32_t v) const { p[i] = excl > v ? excl : v; }
 };
 
-struct InFlagEq {
-    const uint8_t* f;
-    int want;
-    __device__ unsigned long long operator()(int64_t i) const { return (f[i] != 0) == (want != 0) ? 1ull : 0ull; }
-};
-struct OutCompact {
-    int32_t* rows;
-    unsigned long long* total;
-    int64_t n;
-    __device__ void operator()(int64_t i, unsigned long long excl, unsigned long long v) const {
-        if (v) rows[excl] = (int32_t)i;
-        if (i == n - 1) *total = excl + v;
+// ---- flag compaction (giqlb_select_rows): ids of the rows whose byte flag is (non)zero, ascending -------------------
+// Specialised two-pass compaction instead of the generic element-wise scan: a thread owns 32 consecutive flag bytes (two
+// 16-byte loads), counts its matches with byte-compare + popcount, and the emit pass recomputes the same counts, scans
+// them in the block and writes each thread's ids in order.  50 M flags: 0.30 ms -> the two reads of the flags.
+constexpr int SEL_THREADS = 256;
+constexpr int SEL_PER_THREAD = 32;
+constexpr int SEL_TILE = SEL_THREADS * SEL_PER_THREAD;
+
+// the thread's 32 flags as a bit mask of matches (bit b = flag at offset b matches `want`)
+__device__ __forceinline__ uint32_t sel_mask(const uint8_t* __restrict__ flags, int64_t first, int64_t n, int want, bool vec) {
+    uint32_t m = 0;
+    if (first >= n) return 0u;
+    if (vec && first + SEL_PER_THREAD <= n) {
+        const uint4 a = __ldg(reinterpret_cast<const uint4*>(flags + first)), b = __ldg(reinterpret_cast<const uint4*>(flags + first) + 1);
+        const uint32_t w[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+#pragma unroll
+        for (int k = 0; k < 8; k++) {
+            const uint32_t nz = __vcmpne4(w[k], 0u);                       // 0xFF per non-zero byte
+            const uint32_t bits = (nz & 0x01u) | ((nz >> 7) & 0x02u) | ((nz >> 14) & 0x04u) | ((nz >> 21) & 0x08u);
+            m |= bits << (4 * k);
+        }
+    } else {
+        for (int k = 0; k < SEL_PER_THREAD && first + k < n; k++) m |= (flags[first + k] != 0 ? 1u : 0u) << k;
     }
-};
+    if (!want) {
+        const int64_t live = n - first;
+        m = ~m & (live >= 32 ? 0xffffffffu : ((1u << live) - 1u));
+    }
+    return m;
+}
+
+__global__ void __launch_bounds__(SEL_THREADS)
+sel_count_kernel(const uint8_t* __restrict__ flags, int64_t n, int want, unsigned long long* __restrict__ tile_cnt) {
+    __shared__ unsigned int s_red[SEL_THREADS / 32];
+    const bool vec = (reinterpret_cast<uintptr_t>(flags) & 15) == 0;
+    const int64_t first = (int64_t)blockIdx.x * SEL_TILE + (int64_t)threadIdx.x * SEL_PER_THREAD;
+    unsigned int c = __popc(sel_mask(flags, first, n, want, vec));
+    c = warp_reduce_add(c);
+    if (lane_id() == 0) s_red[warp_id()] = c;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        unsigned long long t = 0;
+        for (int w = 0; w < SEL_THREADS / 32; w++) t += s_red[w];
+        tile_cnt[blockIdx.x] = t;
+    }
+}
+
+__global__ void __launch_bounds__(SEL_THREADS)
+sel_emit_kernel(const uint8_t* __restrict__ flags, int64_t n, int want, const unsigned long long* __restrict__ tile_off, int32_t* __restrict__ rows) {
+    __shared__ unsigned int scratch[SEL_THREADS / 32 + 2];
+    const bool vec = (reinterpret_cast<uintptr_t>(flags) & 15) == 0;
+    const int64_t first = (int64_t)blockIdx.x * SEL_TILE + (int64_t)threadIdx.x * SEL_PER_THREAD;
+    uint32_t m = sel_mask(flags, first, n, want, vec);
+    unsigned int tot;
+    unsigned long long o = tile_off[blockIdx.x] + block_excl_scan_add<unsigned int>(__popc(m), scratch, &tot);
+    while (m) {
+        const int b = __ffs(m) - 1;
+        m &= m - 1;
+        rows[o++] = (int32_t)(first + b);
+    }
+}
 }  // namespace
 
 // out has n + 1 entries; out[n] (and *total_dev when given) receive the grand total.
@@ -185,9 +232,27 @@ extern "C" int giqlb_select_rows(giqlb_ctx* ctx, const uint8_t* flags, int64_t n
     begin_call(ctx);
     unsigned long long* total = reinterpret_cast<unsigned long long*>(ctx->d_scalars + 8);
     CUDA_TRY(ctx, cudaMemsetAsync(total, 0, 8, ctx->stream));
-    {
-        PhaseSpan ps(ctx, GIQLB_PH_SELECT);
-        GIQLB_TRY((launch_scan<OpAddU64>(ctx, n, InFlagEq{flags, want}, OutCompact{out_rows, total, n})));
+    if (n > 0) {
+        const int64_t n_tiles = ceil_div(n, SEL_TILE);
+        unsigned long long *cnt = nullptr, *off = nullptr;
+        GIQLB_TRY(dev_alloc(ctx, &cnt, (size_t)n_tiles + 1));
+        int st = dev_alloc(ctx, &off, (size_t)n_tiles + 1);
+        if (st == GIQLB_OK) {
+            PhaseSpan ps(ctx, GIQLB_PH_SELECT);
+            sel_count_kernel<<<(unsigned)n_tiles, SEL_THREADS, 0, ctx->stream>>>(flags, n, want, cnt);
+            ctx->launches_this_call++;
+            ctx->stats.kernels_total++;
+            st = giqlb_excl_scan_u64(ctx, cnt, off, n_tiles, total);
+            if (st == GIQLB_OK) {
+                sel_emit_kernel<<<(unsigned)n_tiles, SEL_THREADS, 0, ctx->stream>>>(flags, n, want, off, out_rows);
+                ctx->launches_this_call++;
+                ctx->stats.kernels_total++;
+                if (cudaGetLastError() != cudaSuccess) st = giqlb_fail(ctx, GIQLB_ERR_CUDA, "select_rows: launch failed");
+            }
+        }
+        dev_free(ctx, cnt);
+        dev_free(ctx, off);
+        GIQLB_TRY(st);
     }
     if (n_out_host) {
         GIQLB_TRY(fetch_scalars_checked(ctx, total, 1));
