@@ -226,8 +226,10 @@ def algorithmic_bytes(phase: str, n_full: int, n_local: int, pairs: int, sort_pa
         "shard": 12 * n_full + 12 * n_local,       # sampled histogram + fused select/keygen: read the columns, write keys + row ids
         "keygen": 12 * n_local + 8 * n_local,      # read code/start/end, write linear start + linear end
         "sort_hist": 4 * n_local,                  # read keys once
-        "sort_pass": 16 * n_local * sort_passes,   # keys + row ids in and out, per 8-bit digit pass
-        "gather": 12 * n_local,                    # read row id + gathered end, write end
+        "sort_pass": int(16 * n_local * sort_passes),   # keys + row ids in and out, per 8-bit digit pass
+        # after a full sort: read row id + gathered end, write end.  After the short-window sort (three passes): the finishing
+        # pass reads key + row id + gathered end and writes key, row id and end
+        "gather": (12 if sort_passes >= 4 else 24) * n_local,
         "join_count": 8 * n_local,                 # merge-path partition (or the count pass of the two-pass API)
         "join_scan": 0,
         "join_emit": 12 * n_local + 8 * pairs,
@@ -536,7 +538,8 @@ def run_b200(args):
         return
 
     # ---- roofline of the dominant kernel group (per-launch, live CUDA events on the engine's stream) ----
-    sort_passes = 4
+    # digit passes per table as launched (three when the one-call path took the short-window sort, four otherwise)
+    sort_passes = prof["sort_pass"][1] / args.steps / 2 if prof.get("sort_pass", (0, 0))[1] > 0 else 4
     phases = {}
     for name, (ms, n_launch) in prof.items():
         if n_launch <= 0:
@@ -602,7 +605,7 @@ def run_b200(args):
                    "l2": "inputs (340 MB) exceed the 126 MB L2 and a 512 MB buffer is rewritten between timed steps",
                    "timing": "value: K steps, CUDA events per step, no instrumentation; phases/roofline: the same K steps repeated with "
                              "CUDA-event spans around every kernel group (ms_per_step_with_spans = %.4f)" % (sum(prof_step_ms) / len(prof_step_ms)),
-                   "step": "dict_encode + layout + radix-sort index x2 + join (" + args.join_mode + ": the warm-up call sizes the pair buffer "
+                   "step": "dict_encode + layout + radix-sort index x2 (upper-bits digit passes + one window-finishing pass that also gathers the ends) + join (" + args.join_mode + ": the warm-up call sizes the pair buffer "
                            "with count+scan+emit; timed calls run the fused single-pass count/offset/emit kernel into a buffer of 1.25x "
                            "the previous total, overflow checked on the device)"},
         "e2e": {"value": pairs / (e2e_ms / 1e3), "unit": UNIT, "ms_per_step": e2e_ms, "ms_per_step_synchronous": e2e_sync_ms, "ms_per_step_pipelined": e2e_pipelined_ms, "schedule": e2e_mode,

@@ -30,6 +30,7 @@ struct giqlb_ctx {
     int* d_err = nullptr;           // device int[4]: sticky kernel-side error flags ([0] look-back spin limit)
     giqlb_stats_t stats = {};
     bool join_smem_opted_in = false;   // cudaFuncSetAttribute is per device: remembered per context, not per process
+    int full_sort_credit = 0;          // > 0: the next index builds skip the short-window sort (a dense table was seen; see index.cu)
     int32_t launches_this_call = 0;
     // Scratch cache.  Every allocation of a context is used on ITS stream only, so a freed block can be handed
     // out again immediately (stream order protects it) without a driver call: dev_free parks the block here,
@@ -123,7 +124,9 @@ struct giqlb_index {
     int64_t n_degenerate = 0;    // rows with end <= start (host copy; valid when `resolved`)
     int64_t n_negative = 0;      // rows with end <  start
     bool resolved = true;        // false: the counts still sit in d_counters (giqlb_index_resolve fetches them)
-    unsigned long long* d_counters = nullptr;   // [3] end<=start, end<start, rows outside the layout
+    bool sort_unfinished = false;   // the short-window sort met a dense window: gs/ge/rid are NOT in order, rebuild (host copy of d_counters[3])
+    unsigned long long* d_counters = nullptr;   // [4] end<=start, end<start, rows outside the layout, rows in windows too dense for
+                                                // the short-window sort (GIQLB_INDEX_SORT_SHORT_WINDOWS builds only)
     // lazily built bucket directories (giqlb_index_ensure_dirs): for every strand block with rows, dir[slot][b] = first
     // block-relative position whose value is >= b << dir_shift, over gs / pmax / ge_sorted.  A search then starts inside one
     // bucket (about one row) instead of walking log2(n) dependent loads from the whole array.
@@ -482,6 +485,13 @@ int giqlb_intersects_join_impl(giqlb_ctx* ctx, giqlb_index* L, giqlb_index* R, i
                                int64_t* total_host, bool speculative);
 int giqlb_index_ensure_pmax(giqlb_ctx* ctx, giqlb_index* ix);
 int giqlb_index_resolve(giqlb_ctx* ctx, giqlb_index* a, giqlb_index* b);
+// Internal giqlb_index_build flag (never part of the C-ABI: callers must be able to rebuild the index).  Sort the start keys on
+// bits [8, key_bits) only — one radix pass fewer — and let one finishing pass order every run of equal upper bits ("window" of
+// 256 linear positions) by its low byte while it gathers the ends.  Windows holding more than 32 rows are not finished: the
+// build then counts their rows in d_counters[3], the index is NOT sorted, and the consumer (pipeline.cu) must skip it, rebuild
+// without the flag and go on with ctx->full_sort_credit set.
+#define GIQLB_INDEX_SORT_SHORT_WINDOWS 0x100
+#define GIQLB_RETRY_FULL_SORT 1   // internal status of giqlb_intersects_join_impl: an index came back with sort_unfinished
 int giqlb_index_ensure_end_sorted(giqlb_ctx* ctx, giqlb_index* ix);
 // bucket directories over gs (always), pmax and ge_sorted (on request; they must exist already)
 int giqlb_index_ensure_dirs(giqlb_ctx* ctx, giqlb_index* ix, bool want_pmax, bool want_ges);

@@ -247,6 +247,141 @@ gather_kernel(const T* __restrict__ src, const uint32_t* __restrict__ idx, T* __
         dst[i] = src[idx[i]];
 }
 
+// Finishing pass of the short-window sort (GIQLB_INDEX_SORT_SHORT_WINDOWS): k3 / v3 are ordered (stably) by key >> 8.  A row's
+// final position inside its window of equal upper bits is the number of window rows with a smaller key plus the earlier rows
+// with the same key, which is exactly where the fourth stable radix pass would have put it.  Windows are short (2 rows on
+// average at 10 M rows over a human genome), so a warp ranks 32 consecutive rows at once with votes: one ballot marks the window
+// heads, eight ballots over the bits of the low byte give every lane the lanes of its window that hold a smaller / an equal
+// byte.  The warp then moves on to the last head it saw, so no window is ever cut by a group boundary and nothing loops per row
+// (measured: rows walking left and right through shared memory cost 223 instructions per row).  Windows of 32 rows or more are
+// left as they are and counted in counters[3]: the build is then unfinished and the caller rebuilds with the full sort.  The same
+// kernel fetches every row's linear end, which replaces the separate gather over the sorted row ids.
+constexpr int SF_THREADS = 256;
+constexpr int SF_WARPS = SF_THREADS / 32;
+constexpr int SF_IPT = 8;
+constexpr int SF_TILE = SF_THREADS * SF_IPT;
+constexpr int SF_HALO = 32;          // rows after the tile that a window begun inside the tile may reach
+constexpr int SF_CHUNK = SF_TILE / SF_WARPS;
+constexpr int SF_LEAD = 4;           // sk[SF_LEAD + e] = key of tile row e (16-byte aligned for vector staging); sk[SF_LEAD - 1] = the row before
+constexpr uint32_t SF_NONE = 0xffffu;
+
+// one step of the bit-serial comparison of the low bytes inside a window: lanes whose byte has bit `mask` set vote; lanes of my
+// window equal to me so far (eq) that lack a bit I have are smaller (lt), those that differ from me in this bit leave eq
+__device__ __forceinline__ void sf_vote_bit(uint32_t k, uint32_t mask, uint32_t& eq, uint32_t& lt) {
+    const bool bit = (k & mask) != 0u;
+    const uint32_t m = __ballot_sync(FULL_MASK, bit);
+    const uint32_t own = bit ? 0xffffffffu : 0u;
+    lt |= eq & ~m & own;
+    eq &= ~(m ^ own);
+}
+
+__global__ void __launch_bounds__(SF_THREADS)
+sort_finish_kernel(const uint32_t* __restrict__ k3, const uint32_t* __restrict__ v3, int64_t n, const uint32_t* __restrict__ ge_rows,
+                   uint32_t* __restrict__ gs, uint32_t* __restrict__ rid, uint32_t* __restrict__ ge,
+                   unsigned long long* __restrict__ counters) {
+    __shared__ __align__(16) uint32_t sk[SF_LEAD + SF_TILE + SF_HALO + 32];   // + 32: a group may read (and ignore) past the halo
+    __shared__ __align__(4) uint16_t dst[SF_TILE + SF_HALO];   // tile-relative destination of row e, SF_NONE: the row belongs to the previous tile
+    const int64_t base = (int64_t)blockIdx.x * SF_TILE;
+    const int rows_here = (int)min((int64_t)(SF_TILE + SF_HALO), n - base);   // rows of the array staged in sk
+    const uint32_t* const k_t = k3 + base;
+    if (rows_here == SF_TILE + SF_HALO) {
+        for (int j = threadIdx.x; j < (SF_TILE + SF_HALO) / 4; j += SF_THREADS)
+            reinterpret_cast<uint4*>(sk + SF_LEAD)[j] = __ldg(reinterpret_cast<const uint4*>(k_t) + j);
+    } else {
+        for (int j = threadIdx.x; j < rows_here; j += SF_THREADS) sk[SF_LEAD + j] = __ldg(k_t + j);
+    }
+    // the row before the tile decides whether tile row 0 begins a window; before row 0 of the array: anything with other upper bits
+    if (threadIdx.x == 0) sk[SF_LEAD - 1] = base > 0 ? __ldg(k_t - 1) : ~__ldg(k_t);
+    for (int j = threadIdx.x; j < (SF_TILE + SF_HALO) / 2; j += SF_THREADS) reinterpret_cast<uint32_t*>(dst)[j] = SF_NONE | (SF_NONE << 16);
+    // the row ids and (random gathers) the ends of the tile's rows are requested now and arrive while the ranks are worked out
+    const uint32_t* const v_t = v3 + base;
+    uint32_t val[SF_IPT], end_of[SF_IPT];
+#pragma unroll
+    for (int r = 0; r < SF_IPT; r++) {
+        const int e = r * SF_THREADS + threadIdx.x;
+        val[r] = e < rows_here ? ld_stream_u32(v_t + e) : 0u;
+    }
+#pragma unroll
+    for (int r = 0; r < SF_IPT; r++) end_of[r] = __ldg(ge_rows + val[r]);   // (row 0's end for slots past the array: never stored)
+    __syncthreads();
+
+    // ---- ranks: warp w owns the windows whose first row lies in its chunk of the tile
+    const int lane = (int)lane_id();
+    const int chunk_end = ((int)warp_id() + 1) * SF_CHUNK;
+    const uint32_t below = (1u << lane) - 1u, upto = below | (1u << lane);
+    const uint32_t* const skp = sk + SF_LEAD + lane;
+    uint16_t* const dstp = dst + lane;
+    int p = chunk_end - SF_CHUNK;
+    bool aligned = false;      // lane 0 of the group is the first row of a window
+    bool own = false;          // rows passed over while not aligned are this warp's (a window of 32 rows or more) or an earlier warp's
+    unsigned int dense = 0;
+    while (p < rows_here && (p < chunk_end || (own && !aligned))) {
+        const uint32_t k = skp[p];
+        const bool head = p + lane >= rows_here || (k ^ skp[p - 1]) > 255u;    // a slot past the array closes the last window
+        const uint32_t heads = __ballot_sync(FULL_MASK, head);
+        if (!aligned) {
+            const int skip = heads ? __ffs(heads) - 1 : 32;
+            if (own && lane < skip) {      // the tail of a window too long to order here: the rows stay where they are
+                dstp[p] = (uint16_t)(p + lane);
+                dense++;
+            }
+            p += skip;
+            aligned = skip < 32;
+            continue;
+        }
+        const int q = 31 - __clz(heads);   // rows [0, q) of the group are whole windows (lane 0 is a head)
+        if (q == 0) {
+            dstp[p] = (uint16_t)(p + lane);   // all 32 lanes are rows of one window (a slot past the array would be a head)
+            dense++;
+            p += 32;
+            aligned = false;
+            own = true;
+            continue;
+        }
+        const int ws = 31 - __clz(heads & upto);                 // head of this lane's window
+        const int we = lane + __ffs((heads >> 1) >> lane);       // head of the next window (lanes < q have one)
+        uint32_t eq = ((1u << we) - 1u) & ~((1u << ws) - 1u);    // lanes of the window with the same byte so far (junk for lanes >= q)
+        uint32_t lt = 0;                                         // ... with a smaller byte
+        sf_vote_bit(k, 0x80u, eq, lt);
+        sf_vote_bit(k, 0x40u, eq, lt);
+        sf_vote_bit(k, 0x20u, eq, lt);
+        sf_vote_bit(k, 0x10u, eq, lt);
+        sf_vote_bit(k, 0x08u, eq, lt);
+        sf_vote_bit(k, 0x04u, eq, lt);
+        sf_vote_bit(k, 0x02u, eq, lt);
+        sf_vote_bit(k, 0x01u, eq, lt);
+        if (lane < q && p + lane < rows_here) dstp[p] = (uint16_t)(p + ws + __popc(lt) + __popc(eq & below));   // (slots past the array are heads too)
+        p += q;
+    }
+    dense = warp_reduce_add(dense);
+    if (lane == 0 && dense) atomicAdd(&counters[3], (unsigned long long)dense);
+    __syncthreads();
+
+    // ---- move: row e of the tile (and of the rows after it that this tile ranked) goes to dst[e], with its row id and its end
+    uint32_t* const gs_t = gs + base;
+    uint32_t* const rid_t = rid + base;
+    uint32_t* const ge_t = ge + base;
+#pragma unroll
+    for (int r = 0; r < SF_IPT; r++) {
+        const int e = r * SF_THREADS + threadIdx.x;
+        const uint32_t to = dst[e];
+        if (to == SF_NONE) continue;
+        gs_t[to] = sk[SF_LEAD + e];
+        rid_t[to] = val[r];
+        ge_t[to] = end_of[r];
+    }
+    if (threadIdx.x < SF_HALO) {       // rows after the tile that belong to a window begun inside it
+        const int e = SF_TILE + threadIdx.x;
+        const uint32_t t = dst[e];
+        if (t != SF_NONE) {
+            const uint32_t v = v_t[e];
+            gs_t[t] = sk[SF_LEAD + e];
+            rid_t[t] = v;
+            ge_t[t] = __ldg(ge_rows + v);
+        }
+    }
+}
+
 __global__ void __launch_bounds__(256)
 remap_rows_kernel(int32_t* __restrict__ rid, const int32_t* __restrict__ rows, int64_t n) {
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
@@ -543,14 +678,14 @@ extern "C" int giqlb_index_info(giqlb_ctx* ctx, giqlb_index* ix, int64_t* n_dege
 extern "C" int giqlb_index_build(giqlb_ctx* ctx, const giqlb_layout* lay, const int32_t* code, const int32_t* start,
                                  const int32_t* end, const uint8_t* strand, int64_t n, int32_t start_adj,
                                  int32_t end_adj, int flags, giqlb_index** out) {
-    return giqlb_index_build_impl(ctx, lay, code, start, end, strand, nullptr, n, start_adj, end_adj, flags, nullptr, out);
+    return giqlb_index_build_impl(ctx, lay, code, start, end, strand, nullptr, n, start_adj, end_adj, flags & 0xff, nullptr, out);
 }
 
 // `rows` (nullable) selects and orders the rows that are indexed; the index then carries rows[i] as row id.
 extern "C" int giqlb_index_build_rows(giqlb_ctx* ctx, const giqlb_layout* lay, const int32_t* code, const int32_t* start,
                                       const int32_t* end, const uint8_t* strand, const int32_t* rows, int64_t n,
                                       int32_t start_adj, int32_t end_adj, int flags, giqlb_index** out) {
-    return giqlb_index_build_impl(ctx, lay, code, start, end, strand, rows, n, start_adj, end_adj, flags, nullptr, out);
+    return giqlb_index_build_impl(ctx, lay, code, start, end, strand, rows, n, start_adj, end_adj, flags & 0xff, nullptr, out);
 }
 
 // `pre` (nullable): the keys were already generated by a fused select + keygen pass (shard.cu); the builder takes
@@ -569,6 +704,12 @@ int giqlb_index_build_impl(giqlb_ctx* ctx, const giqlb_layout* lay, const int32_
     ix->n = n;
     ix->layout = lay;
     ix->tie_by_end = (flags & GIQLB_INDEX_TIE_BY_END) != 0;
+    // one radix pass fewer when the caller can rebuild (see GIQLB_INDEX_SORT_SHORT_WINDOWS); pointless below two passes
+    bool short_windows = (flags & GIQLB_INDEX_SORT_SHORT_WINDOWS) && !ix->tie_by_end && !pre && lay->key_bits > 16 && n > 0;
+    if (short_windows && ctx->full_sort_credit > 0) {
+        ctx->full_sort_credit--;
+        short_windows = false;
+    }
     ix->block_off[1] = n;
     for (int i = 2; i <= GIQLB_MAX_STRAND_CODES; i++) ix->block_off[i] = n;
 
@@ -648,9 +789,21 @@ int giqlb_index_build_impl(giqlb_ctx* ctx, const giqlb_layout* lay, const int32_
         } else {
             // (measured: letting the last pass gather the linear ends costs 34 us/pass and saves a 28 us gather kernel,
             //  so the fused variant stays off)
-            IB_TRY(giqlb_radix_sort_pairs_u32(ctx, ka, va, kb, vb, n, 0, lay->key_bits, 1, &result_in_b, key_hist,
-                                              GIQLB_SORT_GATHERS_END ? ge_u : nullptr, GIQLB_SORT_GATHERS_END ? ix->ge : nullptr));
-            ge_gathered = GIQLB_SORT_GATHERS_END != 0;
+            IB_TRY(giqlb_radix_sort_pairs_u32(ctx, ka, va, kb, vb, n, short_windows ? 8 : 0, lay->key_bits, 1, &result_in_b, key_hist,
+                                              GIQLB_SORT_GATHERS_END && !short_windows ? ge_u : nullptr,
+                                              GIQLB_SORT_GATHERS_END && !short_windows ? ix->ge : nullptr));
+            ge_gathered = GIQLB_SORT_GATHERS_END != 0 || short_windows;
+            if (short_windows) {
+                // (k3, v3) -> the other buffer pair, in final order, with the ends
+                uint32_t *k3 = result_in_b ? kb : ka, *v3 = result_in_b ? vb : va;
+                uint32_t *k4 = result_in_b ? ka : kb, *v4 = result_in_b ? va : vb;
+                PhaseSpan ps(ctx, GIQLB_PH_GATHER);
+                sort_finish_kernel<<<(unsigned)ceil_div(n, SF_TILE), SF_THREADS, 0, ctx->stream>>>(k3, v3, n, ge_u, k4, v4, ix->ge, counters);
+                ctx->launches_this_call++;
+                ctx->stats.kernels_total++;
+                IB_CUDA(cudaGetLastError());
+                result_in_b ^= 1;
+            }
         }
         if (result_in_b) {
             ix->gs = kb; ix->rid = reinterpret_cast<int32_t*>(vb);
@@ -695,6 +848,7 @@ int giqlb_index_build_impl(giqlb_ctx* ctx, const giqlb_layout* lay, const int32_
     // Rows outside the layout raise the sticky flag checked at the next host round trip.
     ix->resolved = false;
     for (const auto& o : lay->observed) {
+        if (short_windows) break;   // d_counters[3] has to be looked at before the index is trusted
         if (o.code != code || o.sadj != start_adj || o.eadj != end_adj || o.n_degenerate < 0) continue;
         if (o.n_degenerate == 0 || (!rows && o.n == n)) {
             ix->n_degenerate = o.n_degenerate;
@@ -875,7 +1029,7 @@ int giqlb_index_resolve(giqlb_ctx* ctx, giqlb_index* a, giqlb_index* b) {
     giqlb_index* todo[2] = {a && !a->resolved ? a : nullptr, b && !b->resolved && b != a ? b : nullptr};
     if (!todo[0] && !todo[1]) return GIQLB_OK;
     for (int k = 0; k < 2; k++)
-        if (todo[k]) CUDA_TRY(ctx, cudaMemcpyAsync(ctx->h_scalars + 32 + 4 * k, todo[k]->d_counters, 3 * 8, cudaMemcpyDeviceToHost, ctx->stream));
+        if (todo[k]) CUDA_TRY(ctx, cudaMemcpyAsync(ctx->h_scalars + 32 + 4 * k, todo[k]->d_counters, 4 * 8, cudaMemcpyDeviceToHost, ctx->stream));
     CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
     for (int k = 0; k < 2; k++) {
         if (!todo[k]) continue;
@@ -883,6 +1037,8 @@ int giqlb_index_resolve(giqlb_ctx* ctx, giqlb_index* a, giqlb_index* b) {
         todo[k]->n_degenerate = c[0];
         todo[k]->n_negative = c[1];
         todo[k]->resolved = true;
+        todo[k]->sort_unfinished = c[3] != 0;
+        if (c[3] != 0) return giqlb_fail(ctx, GIQLB_ERR_INTERNAL, "index: short-window sort left %lld rows unordered and the caller did not rebuild", (long long)c[3]);
         if (c[2] != 0) {
             cudaMemsetAsync(ctx->d_err + 3, 0, sizeof(int), ctx->stream);
             return giqlb_fail(ctx, GIQLB_ERR_RANGE, "index: %lld rows lie outside the layout (observe the table before finalize)", (long long)c[2]);

@@ -136,9 +136,22 @@ __device__ __forceinline__ int64_t merge_diagonal(const uint32_t* __restrict__ l
 }
 __global__ void __launch_bounds__(256)
 join_partition_kernel(const uint32_t* __restrict__ lgs, int64_t nl, const uint32_t* __restrict__ rgs, int64_t nr,
-                      int64_t n_tiles, int32_t* __restrict__ part, TileRec* __restrict__ recs) {
+                      int64_t n_tiles, int32_t* __restrict__ part, TileRec* __restrict__ recs,
+                      const unsigned long long* __restrict__ unfinished_l = nullptr, const unsigned long long* __restrict__ unfinished_r = nullptr) {
     const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (t > n_tiles) return;
+    if ((unfinished_l && *unfinished_l) || (unfinished_r && *unfinished_r)) {
+        // an index built with GIQLB_INDEX_SORT_SHORT_WINDOWS is not in order: nothing may be derived from it.  nl < 0 tells
+        // the fused kernel to leave at once; the host sees the counter with the pair total and rebuilds.
+        part[t] = 0;
+        if (recs && t < n_tiles) {
+            TileRec r;
+            r.x0 = r.y0 = r.wl = r.wr = r.pad0 = r.pad1 = 0;
+            r.nl = r.nr = -1;
+            recs[t] = r;
+        }
+        return;
+    }
     const int64_t d0 = min(t * JT, nl + nr);
     const int64_t x0 = merge_diagonal(lgs, nl, rgs, nr, d0);
     part[t] = (int32_t)x0;
@@ -858,6 +871,7 @@ join_fused_kernel(JoinSide L, JoinSide R, const TileRec* __restrict__ recs, int6
         const int4 a = __ldg(rp), b = __ldg(rp + 1);
         g.x0 = a.x; g.y0 = a.y; g.nl = a.z; g.nr = a.w; g.wl = b.x; g.wr = b.y;
     }
+    if (g.nl < 0) return;   // the partition kernel refused an index whose sort is unfinished (uniform over the grid)
     JDBG_T(c_geom);
     if (threadIdx.x < 32) {
         __syncwarp();                          // lane 0's barrier initialisation precedes the other lanes' copies
@@ -1396,7 +1410,8 @@ int giqlb_intersects_join_impl(giqlb_ctx* ctx, giqlb_index* L, giqlb_index* R, i
             cudaMemsetAsync(totals, 0, 8, ctx->stream);
             {
                 PhaseSpan ps(ctx, GIQLB_PH_JOIN_COUNT);
-                join_partition_kernel<<<(unsigned)ceil_div(n_tiles + 1, 256), 256, 0, ctx->stream>>>(L->gs, L->n, R->gs, R->n, n_tiles, part, recs);
+                join_partition_kernel<<<(unsigned)ceil_div(n_tiles + 1, 256), 256, 0, ctx->stream>>>(
+                    L->gs, L->n, R->gs, R->n, n_tiles, part, recs, !L->resolved ? L->d_counters + 3 : nullptr, !R->resolved ? R->d_counters + 3 : nullptr);
                 ctx->launches_this_call++;
                 ctx->stats.kernels_total++;
             }
@@ -1420,16 +1435,25 @@ int giqlb_intersects_join_impl(giqlb_ctx* ctx, giqlb_index* L, giqlb_index* R, i
         }
         giqlb_index* pending[2] = {!L->resolved ? L : nullptr, !R->resolved && R != L ? R : nullptr};
         for (int k = 0; k < 2 && st == GIQLB_OK; k++)   // the degenerate-row counts ride along with the pair total
-            if (pending[k]) cudaMemcpyAsync(ctx->h_scalars + 32 + 4 * k, pending[k]->d_counters, 3 * 8, cudaMemcpyDeviceToHost, ctx->stream);
+            if (pending[k]) cudaMemcpyAsync(ctx->h_scalars + 32 + 4 * k, pending[k]->d_counters, 4 * 8, cudaMemcpyDeviceToHost, ctx->stream);
         if (st == GIQLB_OK) st = fetch_scalars_checked(ctx, totals, 1);
         total = st == GIQLB_OK ? ctx->h_scalars[0] : -1;
-        bool degenerate = false;
+        bool degenerate = false, unfinished = false;
         for (int k = 0; k < 2 && st == GIQLB_OK; k++) {
             if (!pending[k]) continue;
             pending[k]->n_degenerate = ctx->h_scalars[32 + 4 * k];
             pending[k]->n_negative = ctx->h_scalars[33 + 4 * k];
             pending[k]->resolved = true;
+            pending[k]->sort_unfinished = ctx->h_scalars[35 + 4 * k] != 0;
+            unfinished = unfinished || pending[k]->sort_unfinished;
             degenerate = degenerate || pending[k]->n_degenerate > 0;
+        }
+        if (st == GIQLB_OK && unfinished) {   // the kernels above did nothing; only the builder of the indexes can go on
+            dev_free(ctx, part);
+            dev_free(ctx, recs);
+            dev_free(ctx, status);
+            end_call(ctx);
+            return GIQLB_RETRY_FULL_SORT;
         }
         if (st == GIQLB_OK && degenerate) {   // speculation failed: redo through the general path
             dev_free(ctx, part);

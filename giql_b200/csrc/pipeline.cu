@@ -11,8 +11,13 @@
 // src/giql/expanders/intersects_duckdb.py:1283-1334 (reference).
 #include "common.cuh"
 
+#ifndef GIQLB_PIPELINE_SHORT_WINDOW_SORT
+#define GIQLB_PIPELINE_SHORT_WINDOW_SORT 1   // 0: always the full four-pass sort (A/B switch)
+#endif
+
 static int tables_impl(giqlb_ctx* ctx, giqlb_table_t* L, giqlb_table_t* R, int32_t n_codes, int32_t* out_l, int32_t* out_r,
                        int64_t capacity, int64_t* total_host, giqlb_dict** dict_out, bool async_dict) {
+    const int32_t n_codes_in = n_codes;
     giqlb_dict* dict = nullptr;
     giqlb_dict_pending* pend = nullptr;
     const int32_t* slot2code = nullptr;
@@ -41,9 +46,13 @@ static int tables_impl(giqlb_ctx* ctx, giqlb_table_t* L, giqlb_table_t* R, int32
     if (st == GIQLB_OK) st = giqlb_layout_observe_remap(ctx, lay, L->codes, L->start, L->end, L->n, L->start_adj, L->end_adj, slot2code, ok_flag);
     if (st == GIQLB_OK && !same) st = giqlb_layout_observe_remap(ctx, lay, R->codes, R->start, R->end, R->n, R->start_adj, R->end_adj, slot2code, ok_flag);
     if (st == GIQLB_OK) st = giqlb_layout_finalize_async(ctx, lay);   // no round trip: errors surface with the pair total
-    if (st == GIQLB_OK) st = giqlb_index_build(ctx, lay, L->codes, L->start, L->end, nullptr, L->n, L->start_adj, L->end_adj, 0, &il);
-    if (st == GIQLB_OK && !same) st = giqlb_index_build(ctx, lay, R->codes, R->start, R->end, nullptr, R->n, R->start_adj, R->end_adj, 0, &ir);
+    // the indexes are private to this call and can be rebuilt here, so they may take the sort with one radix pass fewer
+    const int ix_flags = GIQLB_PIPELINE_SHORT_WINDOW_SORT ? GIQLB_INDEX_SORT_SHORT_WINDOWS : 0;
+    if (st == GIQLB_OK) st = giqlb_index_build_impl(ctx, lay, L->codes, L->start, L->end, nullptr, nullptr, L->n, L->start_adj, L->end_adj, ix_flags, nullptr, &il);
+    if (st == GIQLB_OK && !same) st = giqlb_index_build_impl(ctx, lay, R->codes, R->start, R->end, nullptr, nullptr, R->n, R->start_adj, R->end_adj, ix_flags, nullptr, &ir);
     if (st == GIQLB_OK) st = giqlb_intersects_join_impl(ctx, il, same ? il : ir, out_l, out_r, capacity, total_host, true);
+    const bool resort = st == GIQLB_RETRY_FULL_SORT;   // a window of 256 positions holds more rows than the finishing pass orders
+    if (resort) st = GIQLB_OK;
     // keep the failing call's message across the clean-up calls
     char msg[sizeof(ctx->err)];
     memcpy(msg, ctx->err, sizeof(msg));
@@ -60,6 +69,13 @@ static int tables_impl(giqlb_ctx* ctx, giqlb_table_t* L, giqlb_table_t* R, int32
             return tables_impl(ctx, L, R, n_codes, out_l, out_r, capacity, total_host, dict_out, false);
         }
         if (st == GIQLB_OK) st = st2;
+    }
+    if (resort && st == GIQLB_OK) {
+        // redo the call with fully sorted indexes, and keep sorting fully for a while: tables like this one (deep coverage,
+        // amplicons) tend to come in series.  The chromosome codes are encoded again from the names when they were encoded here.
+        giqlb_dict_free(dict);
+        ctx->full_sort_credit = 64;
+        return tables_impl(ctx, L, R, n_codes_in, out_l, out_r, capacity, total_host, dict_out, async_dict);
     }
     if (encode && dict && (st == GIQLB_OK || st == GIQLB_ERR_CAPACITY)) L->codes_valid = R->codes_valid = 1;
     if (dict_out) *dict_out = dict;

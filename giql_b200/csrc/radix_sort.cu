@@ -307,9 +307,10 @@ int giqlb_radix_sort_pairs_u32(giqlb_ctx* ctx, uint32_t* keys_a, uint32_t* vals_
     uint32_t* tickets = ghist + (size_t)n_passes * RS_RADIX;
     uint32_t* status = ghist + head_words;
 
-    if (hist_dev && begin_bit == 0) {
+    if (hist_dev && begin_bit % 8 == 0 && begin_bit / 8 + n_passes <= RS_MAX_PASSES) {
         // the producer of the keys already counted every digit (index_keygen_kernel): [4][256] for bits 0..31
-        CUDA_TRY(ctx, cudaMemcpyAsync(ghist, hist_dev, (size_t)n_passes * RS_RADIX * sizeof(uint32_t), cudaMemcpyDeviceToDevice, ctx->stream));
+        CUDA_TRY(ctx, cudaMemcpyAsync(ghist, hist_dev + (size_t)(begin_bit / 8) * RS_RADIX, (size_t)n_passes * RS_RADIX * sizeof(uint32_t),
+                                      cudaMemcpyDeviceToDevice, ctx->stream));
     } else {
         int64_t hb_want = ceil_div(n, RS_THREADS * 16), hb_cap = (int64_t)ctx->sm_count * 8;
         int hist_blocks = (int)(hb_want < hb_cap ? hb_want : hb_cap);

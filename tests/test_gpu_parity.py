@@ -727,3 +727,40 @@ def test_one_chromosome_spanning_row_does_not_serialise_the_operators(engine, c_
                      ("contains", lambda a, b: engine.contains(a, b)), ("intersects", lambda a, b: engine.intersects(a, b))):
         uniform, skewed = ms(lambda: fn(ta0, tb0)), ms(lambda: fn(ta, tb))
         assert skewed < 6 * uniform + 2e-3, (name, uniform, skewed)      # generous: wall clock of a shared box; see the probe for numbers
+
+
+def test_short_window_sort_and_dense_window_resort(c_oracle):
+    """The one-call path sorts the start keys on bits 8.. only and orders every window of 256 linear positions in one finishing
+    pass; a window holding more than 32 rows (deep coverage, amplicons) makes it rebuild both indexes with the full sort and
+    keep sorting fully for a while.  The pairs must be the oracle's either way, and the launch counts must show which sort ran."""
+    import giql_b200
+
+    eng = giql_b200.Engine(0)                       # a fresh context: no full-sort credit yet
+    eng._pair_capacity = 1 << 23
+    rng = np.random.default_rng(4242)
+
+    def table(n, dense_rows=0):
+        s = rng.integers(0, 200_000_000, size=n).astype(np.int32)
+        if dense_rows:                                # many rows starting inside two neighbouring windows, equal starts included
+            s[:dense_rows] = 77_000_000 + rng.integers(0, 300, size=dense_rows)
+        e = (s + rng.integers(1, 400, size=n)).astype(np.int32)
+        return {"code": rng.integers(0, 3, size=n).astype(np.int32), "start": s, "end": e}
+
+    def run(A, B):
+        eng.profile(True)
+        eng.profile_read()
+        ta = eng.table_from_codes(A["code"], A["start"], A["end"], ["c1", "c2", "c3"])
+        tb = eng.table_from_codes(B["code"], B["start"], B["end"], ta.dictionary)
+        got = eng.intersects(ta, tb).sorted_packed()
+        passes = eng.profile_read()["sort_pass"][1]
+        eng.profile(False)
+        exp = c_oracle.intersects_pairs(A["code"], A["start"], A["end"], B["code"], B["start"], B["end"], 3)
+        assert np.array_equal(got, (exp[:, 0] << 32) | exp[:, 1])
+        return passes
+
+    sparse = (table(200_000), table(150_000))
+    assert run(*sparse) == 6                          # three passes per table + the finishing pass
+    dense = (table(200_000, dense_rows=5_000), table(150_000))
+    assert run(*dense) == 6 + 8                       # the attempt, then the rebuild with four passes per table
+    assert run(*sparse) == 8                          # credit: full sort without an attempt
+    assert run(table(50_000, dense_rows=40_000), table(60_000, dense_rows=100)) == 8
