@@ -115,6 +115,8 @@ PROTOTYPES = {
                                    ctypes.c_uint32, _P, POINTER(c_int64)]),
     "giqlb_distance": (c_int, [_P, _P, _P, _P, _P, _P, _P, _P, _P, c_int64, c_int, c_int,
                                c_int32, c_int32, c_int32, c_int32, _P, _P]),
+    "giqlb_distance_rows": (c_int, [_P, _P, _P, _P, _P, c_int64, _P, _P, _P, _P, c_int64, _P, _P, c_int64, c_int, c_int,
+                                    c_int32, c_int32, c_int32, c_int32, _P, _P]),
 }
 
 PHASES = ["dict", "layout", "keygen", "sort_hist", "sort_pass", "gather", "scan_max", "join_count", "join_scan",

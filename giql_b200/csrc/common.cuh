@@ -307,6 +307,7 @@ static inline int fetch_scalars_checked(giqlb_ctx* ctx, const void* d_src, int n
         cudaMemsetAsync(ctx->d_err, 0, 4 * sizeof(int), ctx->stream);
         if (e[1] == 2) return giqlb_fail(ctx, GIQLB_ERR_RANGE, "layout: the summed chromosome extent does not fit the 32-bit linear coordinate");
         if (e[1] == 3) return giqlb_fail(ctx, GIQLB_ERR_RANGE, "nearest: a distance does not fit the int32 output column");
+        if (e[1] == 4) return giqlb_fail(ctx, GIQLB_ERR_INVALID, "distance_rows: a row id lies outside its table");
         if (e[1]) return giqlb_fail(ctx, GIQLB_ERR_RANGE, "layout: a row has a chromosome code outside the dictionary or a coordinate outside [-2^30, 2^31-4]");
         if (e[3]) return giqlb_fail(ctx, GIQLB_ERR_RANGE, "index: rows lie outside the layout (observe the table before finalize)");
         return giqlb_fail(ctx, GIQLB_ERR_INTERNAL, "look-back spin limit exceeded (kernel-side)");

@@ -992,6 +992,31 @@ class Engine:
         enc = lambda col: np.fromiter((null if v is None else rank[v] for v in col), dtype=np.int32, count=len(col))
         return enc(cur), enc(prev)
 
+    def _predicate_codes_device(self, cur_values, prev_values):
+        """The same codes for NUMERIC operand columns (numpy arrays or torch tensors of one integer or one floating kind),
+        ranked on the device: no per-row Python, usable at the 200 M rows of BASELINE configs[4].  NaN is the NULL of a
+        floating column.  Returns None for anything else (lists, objects, mixed kinds): the host path above ranks those."""
+        cols = []
+        for v in (cur_values, prev_values):
+            if isinstance(v, np.ndarray) and v.dtype.kind in "iuf" and v.ndim == 1:
+                v = torch.from_numpy(np.ascontiguousarray(v))
+            if not isinstance(v, torch.Tensor) or v.ndim != 1 or v.dtype == torch.bool or v.dtype.is_complex:
+                return None
+            cols.append(v.to(self.device, non_blocking=True))
+        if cols[0].dtype.is_floating_point != cols[1].dtype.is_floating_point:
+            return None
+        both = torch.cat([c.to(torch.float64 if c.dtype.is_floating_point else torch.int64) for c in cols])
+        codes = torch.full((both.numel(),), _cabi.KEY_NULL, dtype=torch.int32, device=self.device)
+        known = ~torch.isnan(both) if both.dtype.is_floating_point else None
+        vals = both[known] if known is not None else both
+        inv = torch.unique(vals, sorted=True, return_inverse=True)[1].to(torch.int32)
+        if known is not None:
+            codes[known] = inv
+        else:
+            codes = inv
+        n = cols[0].numel()
+        return codes[:n].contiguous(), codes[n:].contiguous()
+
     def cluster(self, t: DeviceTable, distance: int = 0, stranded: bool = False, predicate=None) -> torch.Tensor:
         """CLUSTER(interval[, distance][, stranded := true][, predicate := cur <op> PREV(prev)]) -> int32 cluster id per
         input row (1-based, restarting per chrom[, strand] partition).  reference: src/giql/expanders/cluster.py:205-310,
@@ -1008,8 +1033,12 @@ class Engine:
                 raise ValueError(f"unknown comparison {op!r}")
             if len(cur_values) != t.n or len(prev_values) != t.n:
                 raise ValueError("predicate columns must have one value per row")
-            kc, kp = self.predicate_codes(cur_values, prev_values)
-            keys = (self._dev(kc), self._dev(kp), self._CMP_OPS[op])
+            dev_keys = self._predicate_codes_device(cur_values, prev_values)
+            if dev_keys is not None:
+                keys = (dev_keys[0], dev_keys[1], self._CMP_OPS[op])
+            else:
+                kc, kp = self.predicate_codes(cur_values, prev_values)
+                keys = (self._dev(kc), self._dev(kp), self._CMP_OPS[op])
         lay, ix = self._self_index(t, stranded, raw=True)
         try:
             if keys is None:
@@ -1083,20 +1112,25 @@ class Engine:
         """
         self.encode(a, b)
 
-        def take(t, rows):
-            return t if rows is None or t is None else t.index_select(0, rows.to(torch.int64))
+        def rows32(rows, limit):
+            if rows is None:
+                return None, limit
+            r = rows if rows.dtype == torch.int32 else rows.to(torch.int32)
+            return r.contiguous(), int(r.numel())
 
-        cols_a = [take(x, a_rows) for x in (a.codes, a.start, a.end, a.strand)]
-        cols_b = [take(x, b_rows) for x in (b.codes, b.start, b.end, b.strand)]
-        n = int(cols_a[1].numel())
-        if int(cols_b[1].numel()) != n:
+        ra, na = rows32(a_rows, a.n)
+        rb, nb = rows32(b_rows, b.n)
+        if na != nb:
             raise ValueError("paired row selections differ in length")
-        use_strand = bool(stranded) and cols_a[3] is not None and cols_b[3] is not None
+        n = na
+        use_strand = bool(stranded) and a.strand is not None and b.strand is not None
         out = self._empty(n, torch.int32)
         valid = self._empty(n, torch.uint8)
         (asj, aej), (bsj, bej) = a.offsets, b.offsets
-        self._check(self.lib.giqlb_distance(
-            self.ctx, _ptr(cols_a[0]), _ptr(cols_a[1]), _ptr(cols_a[2]), _ptr(cols_a[3]) if use_strand else None,
-            _ptr(cols_b[0]), _ptr(cols_b[1]), _ptr(cols_b[2]), _ptr(cols_b[3]) if use_strand else None,
+        # the row selections are gathered inside the kernel (giqlb_distance_rows): no gathered copies of the six columns
+        self._check(self.lib.giqlb_distance_rows(
+            self.ctx, _ptr(a.codes), _ptr(a.start), _ptr(a.end), _ptr(a.strand) if use_strand else None, a.n,
+            _ptr(b.codes), _ptr(b.start), _ptr(b.end), _ptr(b.strand) if use_strand else None, b.n,
+            _ptr(ra) if ra is not None else None, _ptr(rb) if rb is not None else None,
             n, int(use_strand), int(bool(signed)), asj, aej, bsj, bej, _ptr(out), _ptr(valid)))
         return out, valid

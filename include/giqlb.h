@@ -360,6 +360,15 @@ int giqlb_distance(giqlb_ctx* ctx, const int32_t* a_code, const int32_t* a_start
                    const int32_t* b_end, const uint8_t* b_strand, int64_t n, int stranded, int signed_,
                    int32_t a_start_adj, int32_t a_end_adj, int32_t b_start_adj, int32_t b_end_adj,
                    int32_t* out, uint8_t* valid);
+/* The same over SELECTED pairs: pair i is (row a_rows[i] of table a, row b_rows[i] of table b), e.g. the two columns of a join
+ * result (DISTANCE in the select list of an INTERSECTS / NEAREST query, src/giql/expanders/_distance.py:22-117 applied to the
+ * joined rows).  a_rows / b_rows may each be NULL (= row i).  The columns are gathered inside the kernel.  a_n / b_n are the
+ * table sizes: a row id outside its table is GIQLB_ERR_INVALID, never a wild read. */
+int giqlb_distance_rows(giqlb_ctx* ctx, const int32_t* a_code, const int32_t* a_start, const int32_t* a_end,
+                        const uint8_t* a_strand, int64_t a_n, const int32_t* b_code, const int32_t* b_start,
+                        const int32_t* b_end, const uint8_t* b_strand, int64_t b_n, const int32_t* a_rows,
+                        const int32_t* b_rows, int64_t n, int stranded, int signed_, int32_t a_start_adj,
+                        int32_t a_end_adj, int32_t b_start_adj, int32_t b_end_adj, int32_t* out, uint8_t* valid);
 
 #ifdef __cplusplus
 }

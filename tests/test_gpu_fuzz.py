@@ -154,3 +154,54 @@ def test_cluster_predicate_fuzz(shape, op, distance, stranded, engine):
     assert eb.cluster(T, distance, stranded, (cur, op, prev)) == [int(x) for x in ob.cluster(T, distance, stranded, (cur, op, prev))]
     names = [["alpha", "beta", "gamma", None][i] for i in rng.integers(0, 4, size=n)]
     assert eb.cluster(T, distance, stranded, (names, op, names)) == [int(x) for x in ob.cluster(T, distance, stranded, (names, op, names))]
+
+
+def test_distance_over_selected_rows_is_the_gathered_distance(engine):
+    """Engine.distance(a, b, a_rows, b_rows) (giqlb_distance_rows: the kernel gathers the columns) equals DISTANCE over the
+    gathered tables, one-sided selections included; a row id outside its table is an error, not a wild read"""
+    import torch
+
+    from giql_b200._cabi import EngineError
+
+    rng = np.random.default_rng(991)
+    A, B = make(rng, 700, "uniform", strands=("+", "-", ".", None)), make(rng, 500, "nested", strands=("+", "-"))
+    ob, eb = OracleBackend(), EngineBackend(engine)
+    ia, ib = rng.integers(0, 700, size=3000), rng.integers(0, 500, size=3000)
+    take = lambda T, idx: {k: [v[i] for i in idx] for k, v in T.items() if not k.startswith("__")}
+    for stranded, signed in ((False, False), (True, True), (True, False)):
+        d, v = eb.distance_arrays(A, B, ia, ib, stranded=stranded, signed=signed)
+        got = [int(x) if ok else None for x, ok in zip(d.tolist(), v.tolist())]
+        assert got == ob.distance(take(A, ia), take(B, ib), stranded=stranded, signed=signed)
+    ta, tb = eb._table(A, None), eb._table(B, None)
+    rows = torch.from_numpy(ib[:700]).to(engine.device)                       # only the b side selected: a row i with b row rows[i]
+    d, v = engine.distance(ta, tb, None, rows)
+    want = ob.distance(take(A, range(700)), take(B, ib[:700]))
+    assert [int(x) if ok else None for x, ok in zip(d.cpu().tolist(), v.cpu().tolist())] == want
+    bad = torch.tensor([0, 1, 700], dtype=torch.int32, device=engine.device)  # table a has rows 0..699
+    with pytest.raises(EngineError):
+        engine.distance(ta, tb, bad, bad[:3] * 0)
+    d, v = engine.distance(ta, tb, bad * 0, bad * 0)                          # the engine keeps working afterwards
+    assert d.numel() == 3
+
+
+@pytest.mark.parametrize("kind", ["int64", "float64", "int32"])
+def test_numeric_predicate_columns_rank_on_the_device(kind, engine):
+    """numeric predicate operand columns (numpy / torch) are ranked on the device; the codes — hence the clusters — equal
+    the host ranking of the same values as Python lists, NaN standing in for NULL"""
+    rng = np.random.default_rng(17)
+    T = make(rng, 2500, "dups")
+    n = len(T["start"])
+    cur = rng.integers(-3, 4, size=n).astype(kind)
+    prev = rng.integers(-3, 4, size=n).astype(kind)
+    as_list = lambda a: a.tolist()
+    if kind == "float64":
+        cur[::17] = np.nan
+        prev[::23] = np.nan
+        as_list = lambda a: [None if np.isnan(x) else float(x) for x in a]
+    dev = engine._predicate_codes_device(cur, prev)
+    host = engine.predicate_codes(as_list(cur), as_list(prev))
+    assert dev is not None and np.array_equal(dev[0].cpu().numpy(), host[0]) and np.array_equal(dev[1].cpu().numpy(), host[1])
+    assert engine._predicate_codes_device(as_list(cur), prev) is None            # lists stay on the host path
+    ob, eb = OracleBackend(), EngineBackend(engine)
+    for op in ("=", "<", ">="):
+        assert eb.cluster(T, 25, False, (cur, op, prev)) == [int(x) for x in ob.cluster(T, 25, False, (as_list(cur), op, as_list(prev)))]
