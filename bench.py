@@ -295,7 +295,7 @@ def other_configs(eng, rank, world, hbm_peak, rows_scale=1.0):
         for k in (1, 5):
             ms, res = timed(lambda: eng.nearest(tq, tt, k=k, stranded=True, signed=True))
             emit(f"C4 NEAREST k={k} stranded+signed {nq} x {nt} (distance emitted)", nq, ms, 13 * (nq + nt) + 12 * len(res), emitted=len(res))
-        ms, _ = timed(lambda: eng.distance(tq, tt, res.query_rows.long(), res.target_rows.long(), stranded=True, signed=True))
+        ms, _ = timed(lambda: eng.distance(tq, tt, res.query_rows, res.target_rows, stranded=True, signed=True))
         emit("C4 DISTANCE over the k=5 pairs", len(res), ms, 29 * len(res))
         del tq, tt, res
         eng.trim()

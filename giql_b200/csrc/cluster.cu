@@ -134,7 +134,7 @@ cluster_ids_kernel(const uint32_t* __restrict__ gs, const int32_t* __restrict__ 
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
         const int64_t j = last_peer(gs, i, n);
         const int32_t c = chrom_of(V, gs[i], memo);
-        out_by_row[rid[i]] = (int32_t)(G[j] - off[c]);
+        out_by_row[rid ? (int64_t)rid[i] : i] = (int32_t)(G[j] - off[c]);   // rid == nullptr: ids in sorted-row order
     }
 }
 
@@ -183,7 +183,7 @@ __global__ void cluster_ids_offset_kernel(const uint32_t* __restrict__ gs, const
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
         const int64_t j = last_peer(gs, i, n);
         const int32_t c = chrom_of(V, gs[i], memo);
-        out_by_row[rid[i]] = (int32_t)(G[j] - off[c] + id_offset[c]);
+        out_by_row[rid ? (int64_t)rid[i] : i] = (int32_t)(G[j] - off[c] + id_offset[c]);
     }
 }
 
@@ -214,6 +214,52 @@ __global__ void fill_u8_kernel(uint8_t* p, uint8_t v, int64_t n) {
 inline int grid_of(const giqlb_ctx* ctx, int64_t n, int per_thread) {
     int64_t want = ceil_div(n, 256 * per_thread), cap = (int64_t)ctx->sm_count * 8;
     return (int)(want < 1 ? 1 : (want < cap ? want : cap));
+}
+
+// out[row[i]] = val[i] for a permutation `row` of [0, n).  Done directly, this is n random 4-byte writes: beyond the L2 (126 MB)
+// every one of them costs a DRAM sector, and at 200 M rows the scatter alone took 10 ms (22 G writes/s).  Partitioning the pairs
+// on the top 8 bits of the row id first, so that the writes fall into L2-resident 4 MB windows, hardly helps (7.1 ms: sub-sector
+// writes are slow in L2 as well).  What works is to sort the (row, val) pairs on all but the lowest 4 bits of the row id with the
+// radix sort (three passes of 1.3 ms at 200 M rows): neighbouring threads then write into the same two sectors and the scatter
+// itself drops to 0.4 ms — 4.6 ms in all.
+// (Row ids of a genome-range shard run over the whole table, not [0, n): the sort then sees only their lower bits and rows
+// of several windows interleave — less locality, same result.)
+#ifndef GIQLB_BINNED_SCATTER_MIN
+#define GIQLB_BINNED_SCATTER_MIN (24ll << 20)   // rows: the output no longer fits L2 comfortably
+#endif
+__global__ void __launch_bounds__(256)
+scatter_u32_kernel(const uint32_t* __restrict__ row, const uint32_t* __restrict__ val, int64_t n, uint32_t* __restrict__ out) {
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) out[row[i]] = val[i];
+}
+
+inline bool binned_scatter_wanted(int64_t n) { return n >= GIQLB_BINNED_SCATTER_MIN; }
+
+// `val` is scratch of the caller (n entries, sorted-row order) and is left in an unspecified state
+int scatter_by_row(giqlb_ctx* ctx, const int32_t* rid, uint32_t* val, int64_t n, int32_t* out) {
+    uint32_t *ka = nullptr, *kb = nullptr, *vb = nullptr;
+    GIQLB_TRY(dev_alloc(ctx, &kb, (size_t)n));
+    int st = dev_alloc(ctx, &vb, (size_t)n);
+    if (st == GIQLB_OK) {
+        int bits = 0;
+        while (bits < 32 && (1ll << bits) < n) bits++;
+        const int shift = bits > 12 ? 4 : 0;
+        int in_b = 0;
+        // the passes ping-pong between (ka, val) and (kb, vb): the index's own row ids must stay intact, hence the copy
+        st = dev_alloc(ctx, &ka, (size_t)n);
+        if (st == GIQLB_OK && cudaMemcpyAsync(ka, rid, (size_t)n * 4, cudaMemcpyDeviceToDevice, ctx->stream) != cudaSuccess)
+            st = giqlb_fail(ctx, GIQLB_ERR_CUDA, "scatter_by_row: copy failed");
+        if (st == GIQLB_OK) st = giqlb_radix_sort_pairs_u32(ctx, ka, val, kb, vb, n, shift, bits, 0, &in_b);
+        if (st == GIQLB_OK) {
+            scatter_u32_kernel<<<grid_of(ctx, n, 4), 256, 0, ctx->stream>>>(in_b ? kb : ka, in_b ? vb : val, n, reinterpret_cast<uint32_t*>(out));
+            ctx->launches_this_call++;
+            ctx->stats.kernels_total++;
+            if (cudaGetLastError() != cudaSuccess) st = giqlb_fail(ctx, GIQLB_ERR_CUDA, "scatter_by_row: launch failed");
+        }
+    }
+    dev_free(ctx, ka);
+    dev_free(ctx, kb);
+    dev_free(ctx, vb);
+    return st;
 }
 
 inline LayoutView view_of(const giqlb_layout* lay) { return LayoutView{lay->d_base, lay->d_lo32, lay->n_codes}; }
@@ -287,11 +333,26 @@ static int cluster_impl(giqlb_ctx* ctx, giqlb_index* X, int64_t distance, const 
             cluster_chrom_offsets_kernel<<<(V.n_codes + 127) / 128, 128, 0, ctx->stream>>>(X->gs + lo, G + lo, hi - lo, V, off);
             ctx->launches_this_call++;
             ctx->stats.kernels_total++;
-            cluster_ids_kernel<<<grid_of(ctx, hi - lo, 4), 256, 0, ctx->stream>>>(X->gs + lo, X->rid + lo, G + lo, off, hi - lo, V,
-                                                                                 cluster_id_by_input_row);
-            ctx->launches_this_call++;
-            ctx->stats.kernels_total++;
-            if (cudaGetLastError() != cudaSuccess) st = giqlb_fail(ctx, GIQLB_ERR_CUDA, "cluster: launch failed");
+            if (binned_scatter_wanted(hi - lo)) {
+                // ids in sorted-row order first (sequential writes, into their own array: G[j] of a later peer is still read), then
+                // the partitioned scatter to input-row order
+                uint32_t* ids = nullptr;
+                st = dev_alloc(ctx, &ids, (size_t)(hi - lo));
+                if (st == GIQLB_OK) {
+                    cluster_ids_kernel<<<grid_of(ctx, hi - lo, 4), 256, 0, ctx->stream>>>(X->gs + lo, nullptr, G + lo, off, hi - lo, V,
+                                                                                         reinterpret_cast<int32_t*>(ids));
+                    ctx->launches_this_call++;
+                    ctx->stats.kernels_total++;
+                    st = scatter_by_row(ctx, X->rid + lo, ids, hi - lo, cluster_id_by_input_row);
+                }
+                dev_free(ctx, ids);
+            } else {
+                cluster_ids_kernel<<<grid_of(ctx, hi - lo, 4), 256, 0, ctx->stream>>>(X->gs + lo, X->rid + lo, G + lo, off, hi - lo, V,
+                                                                                     cluster_id_by_input_row);
+                ctx->launches_this_call++;
+                ctx->stats.kernels_total++;
+            }
+            if (st == GIQLB_OK && cudaGetLastError() != cudaSuccess) st = giqlb_fail(ctx, GIQLB_ERR_CUDA, "cluster: launch failed");
         }
     }
     dev_free(ctx, G);
@@ -434,11 +495,21 @@ extern "C" int giqlb_cluster_shard(giqlb_ctx* ctx, giqlb_index* X, int64_t dista
                 st = giqlb_fail(ctx, GIQLB_ERR_CUDA, "cluster_shard: offset copy failed");
             if (st == GIQLB_OK) {
                 cluster_chrom_offsets_kernel<<<(nc + 127) / 128, 128, 0, ctx->stream>>>(X->gs, G, n, V, off);
-                cluster_ids_offset_kernel<<<grid_of(ctx, n, 4), 256, 0, ctx->stream>>>(X->gs, X->rid, G, off, aux, n, V, cluster_id_by_input_row);
+                if (binned_scatter_wanted(n)) {
+                    uint32_t* ids = nullptr;
+                    st = dev_alloc(ctx, &ids, (size_t)n);
+                    if (st == GIQLB_OK) {
+                        cluster_ids_offset_kernel<<<grid_of(ctx, n, 4), 256, 0, ctx->stream>>>(X->gs, nullptr, G, off, aux, n, V, reinterpret_cast<int32_t*>(ids));
+                        st = scatter_by_row(ctx, X->rid, ids, n, cluster_id_by_input_row);
+                    }
+                    dev_free(ctx, ids);
+                } else {
+                    cluster_ids_offset_kernel<<<grid_of(ctx, n, 4), 256, 0, ctx->stream>>>(X->gs, X->rid, G, off, aux, n, V, cluster_id_by_input_row);
+                }
                 ctx->launches_this_call += 2;
                 ctx->stats.kernels_total += 2;
                 // id_offset_by_code_host is pageable caller memory: wait before returning
-                if (cudaStreamSynchronize(ctx->stream) != cudaSuccess || cudaGetLastError() != cudaSuccess)
+                if (st == GIQLB_OK && (cudaStreamSynchronize(ctx->stream) != cudaSuccess || cudaGetLastError() != cudaSuccess))
                     st = giqlb_fail(ctx, GIQLB_ERR_CUDA, "cluster_shard: launch failed");
             }
         }

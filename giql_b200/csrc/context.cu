@@ -18,6 +18,9 @@ extern "C" int giqlb_create(int device, void* cuda_stream, giqlb_ctx** out) {
     }
     int sms = 0;
     if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device) == cudaSuccess && sms > 0) ctx->sm_count = sms;
+    size_t mem_free = 0, mem_total = 0;
+    ctx->park_limit = GIQLB_SCRATCH_PARK_LIMIT;
+    if (cudaMemGetInfo(&mem_free, &mem_total) == cudaSuccess && mem_total / 8 > ctx->park_limit) ctx->park_limit = mem_total / 8;
     // NULL selects the legacy default stream: the caller's other work on that stream (PyTorch's default
     // stream has handle 0) stays ordered with ours.  The library never creates a stream of its own.
     ctx->stream = (cudaStream_t)cuda_stream;

@@ -17,6 +17,9 @@ namespace {
 // 1: the key generation kernel also counts the four radix digit histograms of the start keys (shared-memory
 // atomics), which saves the sort's own histogram pass over the keys (0.061 ms at 2 x 10M rows against +0.013 ms in
 // keygen).  Round 1 measured this slower with the scalar keygen; with the 4-rows-per-thread keygen it wins.
+#ifndef GIQLB_SORT_CARRY_END_MIN
+#define GIQLB_SORT_CARRY_END_MIN (24ll << 20)   // rows: three 4-byte columns no longer fit the 126 MB L2
+#endif
 #ifndef GIQLB_KEYGEN_HIST
 #define GIQLB_KEYGEN_HIST 1
 #endif
@@ -705,7 +708,7 @@ int giqlb_index_build_impl(giqlb_ctx* ctx, const giqlb_layout* lay, const int32_
     ix->layout = lay;
     ix->tie_by_end = (flags & GIQLB_INDEX_TIE_BY_END) != 0;
     // one radix pass fewer when the caller can rebuild (see GIQLB_INDEX_SORT_SHORT_WINDOWS); pointless below two passes
-    bool short_windows = (flags & GIQLB_INDEX_SORT_SHORT_WINDOWS) && !ix->tie_by_end && !pre && lay->key_bits > 16 && n > 0;
+    bool short_windows = (flags & GIQLB_INDEX_SORT_SHORT_WINDOWS) && !ix->tie_by_end && !pre && lay->key_bits > 16 && n > 0 && n < GIQLB_SORT_CARRY_END_MIN;
     if (short_windows && ctx->full_sort_credit > 0) {
         ctx->full_sort_credit--;
         short_windows = false;
@@ -789,10 +792,19 @@ int giqlb_index_build_impl(giqlb_ctx* ctx, const giqlb_layout* lay, const int32_
         } else {
             // (measured: letting the last pass gather the linear ends costs 34 us/pass and saves a 28 us gather kernel,
             //  so the fused variant stays off)
+            // tables beyond the L2: the ends travel through the sort as a second payload (1.5 x the bytes of every pass) instead of
+            // being gathered afterwards through the sorted row ids, one random DRAM sector each (200 M rows: +2.6 ms against 5.0 ms)
+            const bool carry_end = n >= GIQLB_SORT_CARRY_END_MIN && !short_windows;
+            const bool fused_gather = GIQLB_SORT_GATHERS_END && !short_windows && !carry_end;
             IB_TRY(giqlb_radix_sort_pairs_u32(ctx, ka, va, kb, vb, n, short_windows ? 8 : 0, lay->key_bits, 1, &result_in_b, key_hist,
-                                              GIQLB_SORT_GATHERS_END && !short_windows ? ge_u : nullptr,
-                                              GIQLB_SORT_GATHERS_END && !short_windows ? ix->ge : nullptr));
-            ge_gathered = GIQLB_SORT_GATHERS_END != 0 || short_windows;
+                                              fused_gather ? ge_u : nullptr, fused_gather ? ix->ge : nullptr,
+                                              carry_end ? ge_u : nullptr, carry_end ? ix->ge : nullptr));
+            if (carry_end && !result_in_b) {   // the sorted ends lie beside the sorted keys: in the first buffer after an even number of passes
+                uint32_t* t = ge_u;
+                ge_u = ix->ge;
+                ix->ge = t;
+            }
+            ge_gathered = fused_gather || short_windows || carry_end;
             if (short_windows) {
                 // (k3, v3) -> the other buffer pair, in final order, with the ends
                 uint32_t *k3 = result_in_b ? kb : ka, *v3 = result_in_b ? vb : va;

@@ -123,11 +123,13 @@ rs_histogram_kernel(const uint32_t* __restrict__ keys, int64_t n, int begin_bit,
 // gather_dst at the row's sorted position, which saves the separate gather pass.
 // IPT keys per thread: 16 (4096-key tiles) for large inputs; 8 (2048-key tiles) when the input has fewer tiles than the
 // GPU has resident CTA slots, where the pass time is one tile's lifetime and shorter tiles finish sooner.
-template <bool IDENTITY_VALS, bool GATHER, int IPT>
+// EXTRA: a second 32-bit payload (extra_in -> extra_out) travels with every row.  Used for the linear ends of tables too large
+// for the L2: gathering them afterwards through the sorted row ids is one random DRAM sector per row (5 ms at 200 M rows).
+template <bool IDENTITY_VALS, bool GATHER, int IPT, bool EXTRA = false>
 __global__ void __launch_bounds__(RS_THREADS, IPT >= 16 ? GIQLB_RS_CTAS_PER_SM : 6)
 rs_onesweep_kernel(const uint32_t* __restrict__ keys_in, const uint32_t* __restrict__ vals_in,
                    uint32_t* __restrict__ keys_out, uint32_t* __restrict__ vals_out, int64_t n, int shift,
-                   const uint32_t* __restrict__ gather_src, uint32_t* __restrict__ gather_dst,
+                   const uint32_t* __restrict__ gather_src /* EXTRA: extra_in */, uint32_t* __restrict__ gather_dst /* EXTRA: extra_out */,
                    const uint32_t* __restrict__ ghist /* this pass, [256] */,
                    uint32_t* __restrict__ status /* this pass, [tiles][256] */,
                    uint32_t* __restrict__ ticket, int* __restrict__ err_flag) {
@@ -278,6 +280,22 @@ rs_onesweep_kernel(const uint32_t* __restrict__ keys_in, const uint32_t* __restr
         vals_out[out] = v;
         if (GATHER) gather_dst[out] = __ldg(gather_src + v);
     }
+    if (EXTRA) {
+        // the second payload takes the same route through s_vals once the first has left it
+        __syncthreads();
+#pragma unroll
+        for (int i = 0; i < IPT; i++) {
+            const uint32_t d = (key[i] >> shift) & 255u;
+            const uint32_t pos = s_digit_excl[d] + s_warp_hist[w][d] + rank[i];
+            const int li = warp_off + i * 32 + l;
+            s_vals[pos] = li < tile_n ? ld_stream_u32(gather_src + tile_base + li) : 0u;
+        }
+        __syncthreads();
+        for (int j = threadIdx.x; j < tile_n; j += RS_THREADS) {
+            const uint32_t d = (s_keys[j] >> shift) & 255u;
+            gather_dst[(int64_t)(s_global_base[d] + j)] = s_vals[j];
+        }
+    }
 }
 
 }  // namespace
@@ -287,7 +305,8 @@ rs_onesweep_kernel(const uint32_t* __restrict__ keys_in, const uint32_t* __restr
 // i itself (vals_a is scratch and is not read by the first pass).
 int giqlb_radix_sort_pairs_u32(giqlb_ctx* ctx, uint32_t* keys_a, uint32_t* vals_a, uint32_t* keys_b,
                                uint32_t* vals_b, int64_t n, int begin_bit, int end_bit, int identity_vals,
-                               int* result_in_b, const uint32_t* hist_dev, const uint32_t* gather_src, uint32_t* gather_dst) {
+                               int* result_in_b, const uint32_t* hist_dev, const uint32_t* gather_src, uint32_t* gather_dst,
+                               uint32_t* extra_a, uint32_t* extra_b) {
     *result_in_b = 0;
     if (n >= (int64_t)ST_VALUE_MASK) return giqlb_fail(ctx, GIQLB_ERR_INVALID, "radix sort: n=%lld too large", (long long)n);
     int n_passes = (end_bit - begin_bit + 7) / 8;
@@ -319,7 +338,10 @@ int giqlb_radix_sort_pairs_u32(giqlb_ctx* ctx, uint32_t* keys_a, uint32_t* vals_
         LAUNCH_CHECK(ctx);
     }
 
-    uint32_t *kin = keys_a, *vin = vals_a, *kout = keys_b, *vout = vals_b;
+    // extra_a / extra_b: a second payload that ping-pongs with the keys (its result lies beside them: extra_b iff *result_in_b)
+    const bool extra = extra_a && extra_b;
+    if (extra && gather_src) return giqlb_fail(ctx, GIQLB_ERR_INVALID, "radix sort: a carried payload and a gathered one exclude each other");
+    uint32_t *kin = keys_a, *vin = vals_a, *kout = keys_b, *vout = vals_b, *ein = extra_a, *eout = extra_b;
     PhaseSpan ps_passes(ctx, GIQLB_PH_SORT_PASS);
     for (int p = 0; p < n_passes; p++) {
         const int shift = begin_bit + 8 * p;
@@ -335,16 +357,29 @@ int giqlb_radix_sort_pairs_u32(giqlb_ctx* ctx, uint32_t* keys_a, uint32_t* vals_
             rs_onesweep_kernel<IDV, GTH, RS_IPT><<<(unsigned)tiles, RS_THREADS, 0, ctx->stream>>>(kin, vin, kout, vout, n, shift, gather_src,      \
                                                                                                   gather_dst, gh, st, tickets + p, ctx->d_err);    \
     } while (0)
-        if (p == 0 && identity_vals) {
+#define RS_LAUNCH_EXTRA(IDV)                                                                                                                    \
+    do {                                                                                                                                        \
+        if (small)                                                                                                                              \
+            rs_onesweep_kernel<IDV, false, RS_IPT / 2, true><<<(unsigned)tiles, RS_THREADS, 0, ctx->stream>>>(kin, vin, kout, vout, n, shift, ein, eout, \
+                                                                                                              gh, st, tickets + p, ctx->d_err);  \
+        else                                                                                                                                    \
+            rs_onesweep_kernel<IDV, false, RS_IPT, true><<<(unsigned)tiles, RS_THREADS, 0, ctx->stream>>>(kin, vin, kout, vout, n, shift, ein, eout,     \
+                                                                                                          gh, st, tickets + p, ctx->d_err);      \
+    } while (0)
+        if (extra) {
+            if (p == 0 && identity_vals) RS_LAUNCH_EXTRA(true); else RS_LAUNCH_EXTRA(false);
+        } else if (p == 0 && identity_vals) {
             if (gather) RS_LAUNCH(true, true); else RS_LAUNCH(true, false);
         } else {
             if (gather) RS_LAUNCH(false, true); else RS_LAUNCH(false, false);
         }
 #undef RS_LAUNCH
+#undef RS_LAUNCH_EXTRA
         LAUNCH_CHECK(ctx);
         uint32_t* t;
         t = kin; kin = kout; kout = t;
         t = vin; vin = vout; vout = t;
+        t = ein; ein = eout; eout = t;
         *result_in_b ^= 1;
     }
     dev_free(ctx, ghist);

@@ -8,7 +8,7 @@ sys.path.insert(0, str(Path(__file__).resolve().parent.parent))
 import torch
 
 import giql_b200
-from giql_b200 import synth
+from giql_b200 import synth_torch
 
 ap = argparse.ArgumentParser()
 ap.add_argument("--scale", type=float, default=0.25)
@@ -16,6 +16,12 @@ ap.add_argument("--only", default="c3,c4,c5")
 args = ap.parse_args()
 only = set(args.only.split(","))
 eng = giql_b200.Engine(0)
+
+
+class synth:   # the bench's device-side generators (the host ones take minutes at 200 M rows)
+    peaks = staticmethod(lambda n, seed: synth_torch.peaks(n, seed, eng.device))
+    genes = staticmethod(lambda n, seed: synth_torch.genes(n, seed, eng.device))
+    reads = staticmethod(lambda n, seed: synth_torch.reads(n, seed, eng.device))
 
 
 def table(T, strand=False, dictionary=None):
