@@ -431,8 +431,9 @@ struct OutScatterRow {
 
 // Bucket directory of an ascending array in one coalesced pass: row j, the first row of its bucket run, fills every
 // entry from the bucket after its predecessor's up to its own (tab[b] = first position with a value >= b << shift);
-// the thread of j == n fills the tail with n.  Gaps of empty buckets are filled by the whole warp, 32 entries per step,
-// so one long gap does not serialise on a single thread.  Values beyond the directory fall into its last bucket.
+// the thread of j == n fills the tail with n.  Longer gaps of empty buckets are filled by the whole warp, 32 entries per step,
+// so one long gap does not serialise on a single thread (and short ones do not serialise the warp: a warp-cooperative turn
+// for every lane made the kernel 32 steps per 32 rows).  Values beyond the directory fall into its last bucket.
 __global__ void __launch_bounds__(256)
 bucket_dir_kernel(const uint32_t* __restrict__ a, int64_t n, int shift, uint32_t stride, uint32_t* __restrict__ tab) {
     const long long last_entry = (long long)stride - 1, last_bucket = (long long)stride - 2;
@@ -443,7 +444,11 @@ bucket_dir_kernel(const uint32_t* __restrict__ a, int64_t n, int shift, uint32_t
             first = j == 0 ? 0 : min((long long)(a[j - 1] >> shift), last_bucket) + 1;
             last = j == n ? last_entry : min((long long)(a[j] >> shift), last_bucket);
         }
-        uint32_t todo = __ballot_sync(FULL_MASK, last >= first);
+        // a few entries (the usual case at about one row per bucket): the lane writes them itself
+        const long long len = last - first + 1;
+        if (len > 0 && len <= 4)
+            for (long long b = first; b <= last; b++) tab[b] = (uint32_t)j;
+        uint32_t todo = __ballot_sync(FULL_MASK, len > 4);
         while (todo) {
             const int src = __ffs(todo) - 1;
             todo &= todo - 1;
@@ -452,6 +457,11 @@ bucket_dir_kernel(const uint32_t* __restrict__ a, int64_t n, int shift, uint32_t
             for (long long b = f + lane_id(); b <= l; b += 32) tab[b] = v;
         }
     }
+}
+
+struct DirSlots { int32_t slot[GIQLB_MAX_STRAND_CODES]; };
+__global__ void dir_slots_kernel(DirSlots s, int32_t* __restrict__ out) {
+    if (threadIdx.x < GIQLB_MAX_STRAND_CODES) out[threadIdx.x] = s.slot[threadIdx.x];
 }
 
 // block maxima of ge: one warp per 32-row block (bmax1), then one warp per 32 entries of bmax1 (bmax2)
@@ -1015,9 +1025,10 @@ int giqlb_index_ensure_dirs(giqlb_ctx* ctx, giqlb_index* ix, bool want_pmax, boo
         const uint64_t extent = ix->layout && ix->layout->total_extent ? ix->layout->total_extent : 0xffffffffull;
         ix->dir_stride = (uint32_t)((extent > 0xffffffffull ? 0xffffffffull : extent) >> ix->dir_shift) + 2u;
         GIQLB_TRY(dev_alloc(ctx, &ix->d_dir_slot, (size_t)GIQLB_MAX_STRAND_CODES));
-        memcpy(ctx->h_stage, h_slot, sizeof(h_slot));   // pinned staging buffer: the copy below is asynchronous
-        CUDA_TRY(ctx, cudaMemcpyAsync(ix->d_dir_slot, ctx->h_stage, sizeof(h_slot), cudaMemcpyHostToDevice, ctx->stream));
-        CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));   // the staging buffer is reused by later calls
+        DirSlots ds;
+        memcpy(ds.slot, h_slot, sizeof(h_slot));
+        dir_slots_kernel<<<1, GIQLB_MAX_STRAND_CODES, 0, ctx->stream>>>(ds, ix->d_dir_slot);   // the table rides in the kernel arguments: no staging buffer, no wait
+        LAUNCH_CHECK(ctx);
     }
     struct Want { bool on; uint32_t** tab; const uint32_t* arr; } wants[3] = {
         {true, &ix->dir_gs, ix->gs}, {want_pmax, &ix->dir_pmax, ix->pmax}, {want_ges, &ix->dir_ges, ix->ge_sorted}};
