@@ -137,6 +137,8 @@ struct giqlb_index {
     uint32_t* bmax1 = nullptr;
     uint32_t* bmax2 = nullptr;
     uint32_t* dir_gs = nullptr;
+    uint4* dir_exists = nullptr;     // lazily built (giqlb_index_ensure_exists_dir): per bucket of dir_gs one 32-byte sector with the first two
+                                     // rows' starts and running maxima — it answers most SEMI / ANTI probes alone (plain indexes only)
     uint32_t* dir_pmax = nullptr;
     uint32_t* dir_ges = nullptr;
     int32_t* d_dir_slot = nullptr;   // device [GIQLB_MAX_STRAND_CODES]: strand block -> directory slot, -1 for empty blocks
@@ -401,18 +403,28 @@ __device__ __forceinline__ void st_stream_u32x4(uint4* p, uint4 v) {
 // linearise one probe row; coordinates are clamped into the chromosome's guard cells, which preserves
 // every comparison against indexed rows of that chromosome.  Returns false when the chromosome holds no
 // indexed row at all (or the code is outside the dictionary): nothing can match.
-__device__ __forceinline__ bool probe_linearise(const ProbeCols& P, int64_t i, uint32_t& gs, uint32_t& ge) {
-    int32_t c = P.code[i];
+__device__ __forceinline__ int32_t add_sat_s32(int32_t a, int32_t b) {
+    int32_t r;
+    asm("add.sat.s32 %0, %1, %2;" : "=r"(r) : "r"(a), "r"(b));
+    return r;
+}
+// Linear coordinates of a probe interval: canonical offsets applied, both ends clamped to [lo - 1, hi + 1] of the row's
+// chromosome.  All in 32 bits (this sits on the path of every probe row; the 64-bit version cost ~60 instructions): the layout
+// admits coordinates in [-2^30, 2^31 - 4] only, so lo - 1 and hi + 1 cannot wrap, and an offset that would carry the column
+// value past INT32_MIN / MAX saturates there — beyond the clamp on either side, so the result is the same.
+__device__ __forceinline__ bool probe_linearise_values(const ProbeCols& P, int32_t c, int32_t start, int32_t end, uint32_t& gs, uint32_t& ge) {
     if (c < 0 || c >= P.n_codes) return false;
-    long long lo = __ldg(P.lo32 + c), hi = __ldg(P.hi32 + c);
+    const int32_t lo = __ldg(P.lo32 + c), hi = __ldg(P.hi32 + c);
     if (hi < lo) return false;
-    long long s = (long long)P.start[i] + P.sadj, e = (long long)P.end[i] + P.eadj;
-    s = s < lo - 1 ? lo - 1 : (s > hi + 1 ? hi + 1 : s);
-    e = e < lo - 1 ? lo - 1 : (e > hi + 1 ? hi + 1 : e);
-    uint32_t b = __ldg(P.base + c) + 1u;
+    const int32_t s = max(min(add_sat_s32(start, P.sadj), hi + 1), lo - 1);
+    const int32_t e = max(min(add_sat_s32(end, P.eadj), hi + 1), lo - 1);
+    const uint32_t b = __ldg(P.base + c) + 1u;
     gs = b + (uint32_t)(s - lo);   // lo - 1 maps to the lower guard cell (wraps to b - 1)
     ge = b + (uint32_t)(e - lo);
     return true;
+}
+__device__ __forceinline__ bool probe_linearise(const ProbeCols& P, int64_t i, uint32_t& gs, uint32_t& ge) {
+    return probe_linearise_values(P, P.code[i], P.start[i], P.end[i], gs, ge);
 }
 
 template <typename T>
@@ -500,3 +512,4 @@ int giqlb_index_ensure_end_sorted(giqlb_ctx* ctx, giqlb_index* ix);
 // bucket directories over gs (always), pmax and ge_sorted (on request; they must exist already)
 int giqlb_index_ensure_dirs(giqlb_ctx* ctx, giqlb_index* ix, bool want_pmax, bool want_ges);
 int giqlb_index_ensure_block_max(giqlb_ctx* ctx, giqlb_index* ix);
+int giqlb_index_ensure_exists_dir(giqlb_ctx* ctx, giqlb_index* ix);

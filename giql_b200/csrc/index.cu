@@ -459,6 +459,29 @@ bucket_dir_kernel(const uint32_t* __restrict__ a, int64_t n, int shift, uint32_t
     }
 }
 
+// "Is there a row starting below x whose end lies above y" needs, after the directory, the rows of the bucket and the running
+// maximum before the answer: three dependent loads at unrelated addresses for every probe row.  Almost every bucket holds at
+// most two rows, so what the probe needs is stored beside the bucket's first position p = tab[b], one 32-byte sector per bucket:
+//   [2 b]     = {p, gs[p], pmax[p - 1], pmax[p]}        [2 b + 1] = {gs[p + 1], pmax[p + 1], 0, 0}
+// (gs = 0xffffffff and pmax = the last running maximum past the last row, pmax[-1] = 0).
+__global__ void __launch_bounds__(256)
+exists_dir_kernel(const uint32_t* __restrict__ tab, uint32_t entries, const uint32_t* __restrict__ gs, const uint32_t* __restrict__ pmax,
+                  int64_t n, uint4* __restrict__ out) {
+    for (uint32_t b = blockIdx.x * blockDim.x + threadIdx.x; b < entries; b += gridDim.x * blockDim.x) {
+        const uint32_t p = tab[b];
+        uint4 e, f;
+        e.x = p;
+        e.y = p < n ? gs[p] : 0xffffffffu;
+        e.z = p > 0 ? pmax[p - 1] : 0u;
+        e.w = p < n ? pmax[p] : e.z;
+        f.x = (int64_t)p + 1 < n ? gs[p + 1] : 0xffffffffu;
+        f.y = (int64_t)p + 1 < n ? pmax[p + 1] : e.w;
+        f.z = f.w = 0u;
+        out[2 * (size_t)b] = e;
+        out[2 * (size_t)b + 1] = f;
+    }
+}
+
 struct DirSlots { int32_t slot[GIQLB_MAX_STRAND_CODES]; };
 __global__ void dir_slots_kernel(DirSlots s, int32_t* __restrict__ out) {
     if (threadIdx.x < GIQLB_MAX_STRAND_CODES) out[threadIdx.x] = s.slot[threadIdx.x];
@@ -657,6 +680,7 @@ extern "C" int giqlb_index_free(giqlb_ctx* ctx, giqlb_index* ix) {
         dev_free(ctx, ix->bmax1);
         dev_free(ctx, ix->bmax2);
         dev_free(ctx, ix->dir_gs);
+        dev_free(ctx, ix->dir_exists);
         dev_free(ctx, ix->dir_pmax);
         dev_free(ctx, ix->dir_ges);
         dev_free(ctx, ix->d_dir_slot);
@@ -936,6 +960,8 @@ extern "C" int giqlb_index_group_by_strand(giqlb_ctx* ctx, giqlb_index* ix) {
         ix->pmax = nullptr; ix->ge_sorted = nullptr; ix->pos_by_end = nullptr;
         dev_free(ctx, ix->dir_gs); dev_free(ctx, ix->dir_pmax); dev_free(ctx, ix->dir_ges); dev_free(ctx, ix->d_dir_slot);
         ix->dir_gs = ix->dir_pmax = ix->dir_ges = nullptr; ix->d_dir_slot = nullptr;
+        dev_free(ctx, ix->dir_exists);
+        ix->dir_exists = nullptr;
         dev_free(ctx, ix->bmax1); dev_free(ctx, ix->bmax2);
         ix->bmax1 = ix->bmax2 = nullptr;
     }
@@ -1044,6 +1070,18 @@ int giqlb_index_ensure_dirs(giqlb_ctx* ctx, giqlb_index* ix, bool want_pmax, boo
             LAUNCH_CHECK(ctx);
         }
     }
+    return GIQLB_OK;
+}
+
+// dir_exists of a plain index (requires pmax; builds dir_gs when missing)
+int giqlb_index_ensure_exists_dir(giqlb_ctx* ctx, giqlb_index* ix) {
+    if (ix->dir_exists || ix->n == 0) return GIQLB_OK;
+    if (ix->grouped_by_strand || !ix->pmax) return giqlb_fail(ctx, GIQLB_ERR_INVALID, "index exists-dir: plain index with pmax required");
+    GIQLB_TRY(giqlb_index_ensure_dirs(ctx, ix, false, false));
+    GIQLB_TRY(dev_alloc(ctx, &ix->dir_exists, (size_t)2 * ix->dir_stride));
+    PhaseSpan ps(ctx, GIQLB_PH_PROBE);
+    exists_dir_kernel<<<grid_for(ctx, ix->dir_stride, 256, 16), 256, 0, ctx->stream>>>(ix->dir_gs, ix->dir_stride, ix->gs, ix->pmax, ix->n, ix->dir_exists);
+    LAUNCH_CHECK(ctx);
     return GIQLB_OK;
 }
 

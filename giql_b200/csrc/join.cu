@@ -1089,15 +1089,33 @@ struct ProbeDirs {
     uint32_t last;         // last bucket of a directory (entries - 2)
 };
 
+// One probe row against dir_exists: exists <=> pmax[ub - 1] > l.gs with ub = number of rows with r.gs < l.ge.
+// f0 = {p, gs[p], pmax[p - 1], pmax[p]}, f1 = {gs[p + 1], pmax[p + 1]}, p = first row of the bucket of l.ge or later.
+__device__ __forceinline__ uint8_t exists_resolve(uint4 f0, uint4 f1, uint32_t b, uint32_t gs, uint32_t ge, const ProbeDirs& D,
+                                                 const uint32_t* __restrict__ rgs, const uint32_t* __restrict__ pmax) {
+    if (ge <= f0.y) return f0.z > gs;                     // ub = p (pmax[-1] = 0 is below every linear coordinate that can overlap)
+    if (f0.w > gs) return 1;                              // row p starts below l.ge: ub > p, and pmax only grows
+    if (ge <= f1.x) return 0;                             // ub = p + 1
+    if (f1.y > gs) return 1;
+    const int64_t p1 = (int64_t)__ldg(D.gs + b + 1);      // three or more rows of this bucket start below l.ge?
+    if (p1 <= (int64_t)f0.x + 2) return 0;
+    const int64_t ub = lower_bound_dev<uint32_t, int64_t>(rgs, (int64_t)f0.x + 2, p1, ge);
+    return __ldg(pmax + ub - 1) > gs;
+}
+
+// (measured, 50 M probe rows against 1 M: two or four rows per thread with their directory loads in flight together run SLOWER —
+//  0.48 / 0.67 ms against 0.46 — and so does nothing at 64 resident warps: the kernel sits at the rate at which the L2 serves
+//  random sectors, about 120 G/s, which also bounds the plain gather kernels)
 __global__ void __launch_bounds__(256)
 probe_exists_kernel(ProbeCols P, const uint32_t* __restrict__ rgs, const uint32_t* __restrict__ pmax, int64_t nr, ProbeDirs D,
-                    uint8_t* __restrict__ exists) {
+                    const uint4* __restrict__ fat /* giqlb_index::dir_exists */, uint8_t* __restrict__ exists) {
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < P.n; i += (int64_t)gridDim.x * blockDim.x) {
         uint32_t gs, ge;
         uint8_t e = 0;
         if (nr > 0 && probe_linearise(P, i, gs, ge)) {
-            const int64_t ub = dir_lower_bound(D.gs, D.shift, D.last, rgs, ge);          // rows with r.gs < l.ge
-            e = ub > 0 && __ldg(pmax + ub - 1) > gs;                             // ... one of which ends after l.gs
+            const uint32_t b = min(ge >> D.shift, D.last);
+            const uint4* fp = fat + 2 * (size_t)b;
+            e = exists_resolve(__ldg(fp), __ldg(fp + 1), b, gs, ge, D, rgs, pmax);
         }
         exists[i] = e;
     }
@@ -1484,13 +1502,13 @@ extern "C" int giqlb_intersects_exists(giqlb_ctx* ctx, const giqlb_layout* lay, 
     ProbeCols P;
     GIQLB_TRY(probe_cols(ctx, lay, code, start, end, n, start_adj, end_adj, &P));
     GIQLB_TRY(giqlb_index_ensure_pmax(ctx, R));
-    if (n > 0 && R->n > 0) GIQLB_TRY(giqlb_index_ensure_dirs(ctx, R, false, false));
+    if (n > 0 && R->n > 0) GIQLB_TRY(giqlb_index_ensure_exists_dir(ctx, R));
     if (n > 0) {
         int64_t blocks = ceil_div(n, 256 * 4);
         int64_t cap = (int64_t)ctx->sm_count * 16;
         PhaseSpan ps(ctx, GIQLB_PH_PROBE);
         probe_exists_kernel<<<(unsigned)(blocks < cap ? blocks : cap), 256, 0, ctx->stream>>>(P, R->gs, R->pmax, R->n, ProbeDirs{R->dir_gs, nullptr, R->dir_shift, R->dir_stride - 2},
-                                                                                                exists_by_row);
+                                                                                                R->dir_exists, exists_by_row);
         LAUNCH_CHECK(ctx);
     }
     ctx->stats.rows_in[0] = n;
