@@ -113,6 +113,8 @@ PROTOTYPES = {
                                  POINTER(ctypes.c_uint32)]),
     "giqlb_shard_select": (c_int, [_P, _P, _P, _P, _P, c_int64, c_int32, c_int32, ctypes.c_uint32, ctypes.c_uint32,
                                    ctypes.c_uint32, _P, POINTER(c_int64)]),
+    "giqlb_index_build_range": (c_int, [_P, _P, _P, _P, _P, c_int64, c_int32, c_int32, ctypes.c_uint32, ctypes.c_uint32, c_int,
+                                        POINTER(_P)]),
     "giqlb_distance": (c_int, [_P, _P, _P, _P, _P, _P, _P, _P, _P, c_int64, c_int, c_int,
                                c_int32, c_int32, c_int32, c_int32, _P, _P]),
     "giqlb_distance_rows": (c_int, [_P, _P, _P, _P, _P, c_int64, _P, _P, _P, _P, c_int64, _P, _P, c_int64, c_int, c_int,

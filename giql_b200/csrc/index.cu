@@ -753,6 +753,7 @@ int giqlb_index_build_impl(giqlb_ctx* ctx, const giqlb_layout* lay, const int32_
     uint32_t *ka = nullptr, *kb = nullptr, *va = nullptr, *vb = nullptr, *ge_u = nullptr, *gs_u = nullptr;
     int32_t* pre_rows = nullptr;   // selection buffer handed over by a fused select + keygen pass
     bool ge_gathered = false;      // the last sort pass already wrote ix->ge
+    bool rows_are_payload = false; // the sort carried the caller's row ids, not positions in the selection
     unsigned long long* counters = nullptr;
     uint32_t* key_hist = nullptr;
     int st = GIQLB_OK;
@@ -830,7 +831,11 @@ int giqlb_index_build_impl(giqlb_ctx* ctx, const giqlb_layout* lay, const int32_
             // being gathered afterwards through the sorted row ids, one random DRAM sector each (200 M rows: +2.6 ms against 5.0 ms)
             const bool carry_end = n >= GIQLB_SORT_CARRY_END_MIN && !short_windows;
             const bool fused_gather = GIQLB_SORT_GATHERS_END && !short_windows && !carry_end;
-            IB_TRY(giqlb_radix_sort_pairs_u32(ctx, ka, va, kb, vb, n, short_windows ? 8 : 0, lay->key_bits, 1, &result_in_b, key_hist,
+            // with the ends carried nothing needs a row's position in the selection any more, so the sort can carry the caller's
+            // row ids themselves instead of positions that are translated afterwards (a random gather: 2.2 ms at 100 M rows)
+            rows_are_payload = carry_end && rows != nullptr;
+            if (rows_are_payload) IB_CUDA(cudaMemcpyAsync(va, rows, (size_t)n * 4, cudaMemcpyDeviceToDevice, ctx->stream));
+            IB_TRY(giqlb_radix_sort_pairs_u32(ctx, ka, va, kb, vb, n, short_windows ? 8 : 0, lay->key_bits, rows_are_payload ? 0 : 1, &result_in_b, key_hist,
                                               fused_gather ? ge_u : nullptr, fused_gather ? ix->ge : nullptr,
                                               carry_end ? ge_u : nullptr, carry_end ? ix->ge : nullptr));
             if (carry_end && !result_in_b) {   // the sorted ends lie beside the sorted keys: in the first buffer after an even number of passes
@@ -866,7 +871,7 @@ int giqlb_index_build_impl(giqlb_ctx* ctx, const giqlb_layout* lay, const int32_
             ctx->stats.kernels_total++;
             IB_CUDA(cudaGetLastError());
         }
-        if (rows) {   // positions in the selection -> caller's row ids
+        if (rows && !rows_are_payload) {   // positions in the selection -> caller's row ids
             remap_rows_kernel<<<grid_for(ctx, n, 256 * 4, 8), 256, 0, ctx->stream>>>(ix->rid, rows, n);
             ctx->launches_this_call++;
             ctx->stats.kernels_total++;

@@ -259,11 +259,14 @@ extern "C" int giqlb_shard_cuts(giqlb_ctx* ctx, const giqlb_layout* lay, const i
     cudaMemsetAsync(cuts, 0, ((size_t)world + 1) * 8, ctx->stream);
     if (n > 0) {
         PhaseSpan ps(ctx, GIQLB_PH_SHARD);
-        int64_t blocks = ceil_div(n, SH_THREADS * 8), cap = (int64_t)ctx->sm_count * 2;
-        shard_hist_kernel<<<(unsigned)(blocks < cap ? blocks : cap), SH_THREADS, 0, ctx->stream>>>(P, 1, hist, hist + n_bins, ctx->d_err);
+        // a caller that does not ask for the widest interval (CLUSTER / MERGE shards replicate nothing) gets its cuts from a
+        // 1-in-16 sample of the rows, like the one-call sharded join: the same cuts on every rank, balance error ~ 1 / sqrt(n / 16)
+        const int64_t stride = !max_width_host && n >= (1 << 20) ? 16 : 1, n_samp = ceil_div(n, stride);
+        int64_t blocks = ceil_div(n_samp, SH_THREADS * 8), cap = (int64_t)ctx->sm_count * 6;
+        shard_hist_kernel<<<(unsigned)(blocks < 1 ? 1 : (blocks < cap ? blocks : cap)), SH_THREADS, 0, ctx->stream>>>(P, stride, hist, hist + n_bins, ctx->d_err);
         ctx->launches_this_call++;
         ctx->stats.kernels_total++;
-        shard_cuts_kernel<<<1, 1024, 0, ctx->stream>>>(hist, n_bins, n, world, cuts);
+        shard_cuts_kernel<<<1, 1024, 0, ctx->stream>>>(hist, n_bins, n_samp, world, cuts);
         ctx->launches_this_call++;
         ctx->stats.kernels_total++;
     }
@@ -318,6 +321,62 @@ extern "C" int giqlb_shard_select(giqlb_ctx* ctx, const giqlb_layout* lay, const
     ctx->stats.rows_out = *n_out_host;
     ctx->stats.algorithmic_bytes = 12 * n + 4 * *n_out_host;
     return end_call(ctx);
+}
+
+// Index of the rows whose linear start lies in [gs_lo, gs_hi) (and whose end lies above ge_gt), in one go: the fused select +
+// keygen pass (the table is read once, keys and row ids come out compacted), one round trip for the selection size, then
+// the sort.  What giqlb_shard_select + giqlb_index_build_rows do in three passes over the rows (select, keygen through
+// the row ids, remap of the sorted positions to row ids).
+struct RangeCuts { uint32_t v[3]; };
+__global__ void range_cuts_kernel(RangeCuts c, uint32_t* __restrict__ out) {
+    if (threadIdx.x < 3) out[threadIdx.x] = c.v[threadIdx.x];
+}
+
+extern "C" int giqlb_index_build_range(giqlb_ctx* ctx, const giqlb_layout* lay, const int32_t* code, const int32_t* start,
+                                       const int32_t* end, int64_t n, int32_t start_adj, int32_t end_adj, uint32_t gs_lo,
+                                       uint32_t gs_hi, int flags, giqlb_index** out) {
+    if (!ctx || !out) return giqlb_fail(ctx, GIQLB_ERR_INVALID, "index_build_range: bad argument");
+    *out = nullptr;
+    begin_call(ctx);
+    ProbeCols P;
+    GIQLB_TRY(probe_cols(ctx, lay, code, start, end, n, start_adj, end_adj, &P));
+    giqlb_prekeyed pre;
+    uint32_t* cuts32 = nullptr;
+    int st = dev_alloc(ctx, &cuts32, 4);
+    if (st == GIQLB_OK) st = dev_alloc(ctx, &pre.gs, (size_t)(n > 0 ? n : 1));
+    if (st == GIQLB_OK) st = dev_alloc(ctx, &pre.ge, (size_t)(n > 0 ? n : 1));
+    if (st == GIQLB_OK) st = dev_alloc(ctx, &pre.rows, (size_t)(n > 0 ? n : 1));
+    if (st == GIQLB_OK) st = dev_alloc(ctx, &pre.counters, 4 + 512);
+    if (st == GIQLB_OK && cudaMemsetAsync(pre.counters, 0, (4 + 512) * 8, ctx->stream) != cudaSuccess) st = giqlb_fail(ctx, GIQLB_ERR_CUDA, "index_build_range: memset failed");
+    int64_t n_sel = 0, deg = 0, neg = 0;
+    if (st == GIQLB_OK) {
+        PhaseSpan ps(ctx, GIQLB_PH_SHARD);
+        RangeCuts rc;
+        rc.v[0] = gs_lo; rc.v[1] = gs_hi; rc.v[2] = 0u;       // world = 1, rank = 0, side 0: starts in [lo, hi), no width bound needed
+        range_cuts_kernel<<<1, 32, 0, ctx->stream>>>(rc, cuts32);
+        if (n > 0) {
+            const int64_t blocks = ceil_div(n, SH_THREADS * 4), cap = (int64_t)ctx->sm_count * 8;
+            shard_select_keygen_kernel<<<(unsigned)(blocks < cap ? blocks : cap), SH_THREADS, 0, ctx->stream>>>(
+                P, cuts32, 1, 0, 0, pre.gs, pre.ge, pre.rows, pre.counters, ctx->d_err);
+        }
+        ctx->launches_this_call += 2;
+        ctx->stats.kernels_total += 2;
+        if (cudaGetLastError() != cudaSuccess) st = giqlb_fail(ctx, GIQLB_ERR_CUDA, "index_build_range: launch failed");
+    }
+    if (st == GIQLB_OK) {
+        cudaMemcpyAsync(ctx->h_scalars + 40, pre.counters, 4 * 8, cudaMemcpyDeviceToHost, ctx->stream);
+        st = fetch_scalars_checked(ctx, ctx->d_scalars, 1);
+        deg = ctx->h_scalars[40]; neg = ctx->h_scalars[41]; n_sel = ctx->h_scalars[43];
+    }
+    if (st == GIQLB_OK) st = giqlb_index_build_impl(ctx, lay, code, start, end, nullptr, pre.rows, n_sel, start_adj, end_adj, flags & 0xff, &pre, out);
+    if (st == GIQLB_OK) {
+        (*out)->n_degenerate = deg;
+        (*out)->n_negative = neg;
+        (*out)->resolved = true;
+    }
+    dev_free(ctx, pre.gs); dev_free(ctx, pre.ge); dev_free(ctx, pre.rows); dev_free(ctx, pre.counters);
+    dev_free(ctx, cuts32);
+    return st;
 }
 
 // ---- the rank-local hot path in one call --------------------------------------------------------------------------

@@ -269,12 +269,18 @@ class _Layout:
 
 class _Index:
     def __init__(self, engine: "Engine", layout: _Layout, t: DeviceTable, raw: bool = False, with_strand: bool = False,
-                 tie_by_end: bool = False, rows: Optional[torch.Tensor] = None):
+                 tie_by_end: bool = False, rows: Optional[torch.Tensor] = None, start_range: Optional[tuple] = None):
         self.e = engine
         self.layout = layout   # keep the layout alive as long as the index
         self.rows = rows       # ... and the row selection until the stream has consumed it
         self.h = ctypes.c_void_p()
         sadj, eadj = (0, 0) if raw else t.offsets
+        if start_range is not None:   # the rows whose linear start lies in [lo, hi): a genome-range shard, selected and keyed in one pass
+            if with_strand or tie_by_end or rows is not None:
+                raise ValueError("a start-range index takes no strand grouping, end ties or row selection")
+            engine._check(engine.lib.giqlb_index_build_range(engine.ctx, layout.h, _ptr(t.codes), _ptr(t.start), _ptr(t.end), t.n, sadj, eadj,
+                                                            int(start_range[0]), int(start_range[1]), 0, ctypes.byref(self.h)))
+            return
         strand = t.strand if with_strand else None
         if with_strand and strand is None:
             raise ValueError("stranded := true requires a strand column on the table")

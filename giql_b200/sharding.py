@@ -332,9 +332,9 @@ def _engine_cm_plan(self, table, world):
     lay.observe(table, raw=True)
     lay.finalize()
     cuts = (ctypes.c_uint32 * (world + 1))()
-    mw = ctypes.c_uint32()
+    # no widest-interval request: CLUSTER / MERGE shards replicate no rows, and the cuts may then come from a sample of the rows
     self.e._check(self.e.lib.giqlb_shard_cuts(self.e.ctx, lay.h, table.codes.data_ptr(), table.start.data_ptr(), table.end.data_ptr(),
-                                              table.n, 0, 0, world, cuts, ctypes.byref(mw)))
+                                              table.n, 0, 0, world, cuts, None))
     return {"layout": lay, "cuts": list(cuts), "table": table, "index": {}, "n_codes": len(d)}
 
 
@@ -343,11 +343,8 @@ def _engine_cm_index(self, plan, g):
 
     if g not in plan["index"]:
         t, lay = plan["table"], plan["layout"]
-        rows = self.e._empty(t.n, torch.int32)
-        n_out = ctypes.c_int64()
-        self.e._check(self.e.lib.giqlb_shard_select(self.e.ctx, lay.h, t.codes.data_ptr(), t.start.data_ptr(), t.end.data_ptr(), t.n, 0, 0,
-                                                    plan["cuts"][g], plan["cuts"][g + 1], 0, rows.data_ptr(), ctypes.byref(n_out)))
-        plan["index"][g] = _Index(self.e, lay, t, raw=True, rows=rows[: n_out.value])
+        # one library call: fused select + keygen of the shard's rows, sort (giqlb_index_build_range)
+        plan["index"][g] = _Index(self.e, lay, t, raw=True, start_range=(plan["cuts"][g], plan["cuts"][g + 1]))
     return plan["index"][g]
 
 

@@ -338,7 +338,9 @@ int giqlb_merge_shard(giqlb_ctx* ctx, giqlb_index* X, int64_t distance, uint32_t
 /* ---- genome-range sharding of a join across GPUs ------------------------------
  * Every rank holds both tables and the same finalized layout.  shard_cuts(): histogram of the LEFT
  * table's linearised starts (2^19-cell bins) -> cuts_host[world + 1] (cuts[0] = 0, cuts[world] = 2^32 - 1) such that every
- * range [cuts[g], cuts[g+1]) holds ~n/world left rows; max_width_host = widest left interval (cells).
+ * range [cuts[g], cuts[g+1]) holds ~n/world left rows; max_width_host = widest left interval (cells).  max_width_host may be
+ * NULL (a caller that replicates no rows, e.g. CLUSTER / MERGE shards): tables of 2^20 rows or more are then histogrammed
+ * from every 16th row only.
  * Deterministic: every rank computes identical cuts without any exchange.
  * shard_select(): ids of the rows with  gs_lo <= linear start < gs_hi  AND  linear end > ge_gt, in unspecified order
  *   (slices of ascending ids; the index build sorts the selection anyway).
@@ -351,6 +353,14 @@ int giqlb_shard_cuts(giqlb_ctx* ctx, const giqlb_layout* lay, const int32_t* cod
 int giqlb_shard_select(giqlb_ctx* ctx, const giqlb_layout* lay, const int32_t* code, const int32_t* start,
                        const int32_t* end, int64_t n, int32_t start_adj, int32_t end_adj, uint32_t gs_lo,
                        uint32_t gs_hi, uint32_t ge_gt, int32_t* out_rows, int64_t* n_out_host);
+
+/* The sorted index of the rows of a table whose linear start lies in [gs_lo, gs_hi) — a genome-range shard of CLUSTER / MERGE
+ * (same partition rule as above; src/giql/expanders/cluster.py:205-310, merge.py:183-439 run per partition) — built in one
+ * call: fused select + key generation (one read of the columns), one round trip for the shard's size, sort.  Row ids of the
+ * index are row ids of the TABLE.  Equivalent to giqlb_shard_select(ge_gt = 0) + giqlb_index_build_rows. */
+int giqlb_index_build_range(giqlb_ctx* ctx, const giqlb_layout* lay, const int32_t* code, const int32_t* start,
+                            const int32_t* end, int64_t n, int32_t start_adj, int32_t end_adj, uint32_t gs_lo,
+                            uint32_t gs_hi, int flags, giqlb_index** out);
 
 /* ---- DISTANCE (elementwise over already-paired rows) ------------------------------------------
  * out[i] = distance, valid[i] = 0 for SQL NULL.  strands may be NULL when !stranded.  *_adj are the

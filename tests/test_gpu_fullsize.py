@@ -91,6 +91,34 @@ def test_c5_cluster_merge_50m_reads(engine, c_oracle):
     assert len(m) == len(wp)
     assert np.array_equal(m.code.cpu().numpy(), wp) and np.array_equal(m.start.cpu().numpy(), ws)
     assert np.array_equal(m.end.cpu().numpy(), we) and np.array_equal(m.count.cpu().numpy(), wc)
+    # the same through two genome-range shards (one GPU playing both ranks; 25 M rows a shard: the range index carries ends and
+    # table row ids through its sort): ids of the shards add up to the oracle's, regions stitch to the oracle's
+    from giql_b200 import sharding
+
+    ops = sharding.EngineOps(engine)
+    plan = ops.cm_plan(t, 2)
+    try:
+        max_ends = [ops.cm_max_end(plan, g) for g in range(2)]
+        carries = [sharding.carry_before(max_ends, g) for g in range(2)]
+        counts = [ops.cm_cluster_counts(plan, g, 0, carries[g]) for g in range(2)]
+        total = np.zeros(len(R["start"]), dtype=np.int64)
+        for g in range(2):
+            total += ops.cm_cluster_ids(plan, g, 0, carries[g], sharding.id_offsets(counts, g)).cpu().numpy()
+        assert np.array_equal(total, want)
+        parts = [ops.cm_merge(plan, g, 0, carries[g]) for g in range(2)]
+        infos = [(int(reg["start"].numel()), *head) for reg, head in parts]
+        extra = sharding.stitch_heads(infos)
+        rows = []
+        for g, (reg, _) in enumerate(parts):
+            cnt, end_ = reg["count"].cpu().numpy().copy(), reg["end"].cpu().numpy().copy()
+            if extra[g][0]:
+                cnt[-1] += extra[g][0]
+                end_[-1] = max(int(end_[-1]), extra[g][1])
+            rows.append(np.stack([reg["code"].cpu().numpy(), reg["start"].cpu().numpy(), end_, cnt], axis=1).astype(np.int64))
+        got = np.concatenate(rows)
+        assert np.array_equal(got, np.stack([wp, ws, we, wc], axis=1).astype(np.int64))
+    finally:
+        ops.cm_release(plan)
 
 
 def test_disjoin_and_containment_2m(engine, c_oracle):
