@@ -125,6 +125,7 @@ struct giqlb_index {
     int64_t n_degenerate = 0;    // rows with end <= start (host copy; valid when `resolved`)
     int64_t n_negative = 0;      // rows with end <  start
     bool resolved = true;        // false: the counts still sit in d_counters (giqlb_index_resolve fetches them)
+    bool maybe_unfinished = false;  // built with GIQLB_INDEX_SORT_SHORT_WINDOWS and d_counters[3] not looked at yet: consumers must check first
     bool sort_unfinished = false;   // the short-window sort met a dense window: gs/ge/rid are NOT in order, rebuild (host copy of d_counters[3])
     unsigned long long* d_counters = nullptr;   // [4] end<=start, end<start, rows outside the layout, rows in windows too dense for
                                                 // the short-window sort (GIQLB_INDEX_SORT_SHORT_WINDOWS builds only)

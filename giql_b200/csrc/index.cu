@@ -742,7 +742,7 @@ int giqlb_index_build_impl(giqlb_ctx* ctx, const giqlb_layout* lay, const int32_
     ix->layout = lay;
     ix->tie_by_end = (flags & GIQLB_INDEX_TIE_BY_END) != 0;
     // one radix pass fewer when the caller can rebuild (see GIQLB_INDEX_SORT_SHORT_WINDOWS); pointless below two passes
-    bool short_windows = (flags & GIQLB_INDEX_SORT_SHORT_WINDOWS) && !ix->tie_by_end && !pre && lay->key_bits > 16 && n > 0 && n < GIQLB_SORT_CARRY_END_MIN;
+    bool short_windows = (flags & GIQLB_INDEX_SORT_SHORT_WINDOWS) && !ix->tie_by_end && lay->key_bits > 16 && n > 0 && n < GIQLB_SORT_CARRY_END_MIN;
     if (short_windows && ctx->full_sort_credit > 0) {
         ctx->full_sort_credit--;
         short_windows = false;
@@ -788,6 +788,8 @@ int giqlb_index_build_impl(giqlb_ctx* ctx, const giqlb_layout* lay, const int32_
     IB_TRY(dev_alloc(ctx, &vb, (size_t)n));
     IB_TRY(dev_alloc(ctx, &ix->ge, (size_t)n));
     if (!pre) IB_CUDA(cudaMemsetAsync(counters, 0, (4 + 512) * 8, ctx->stream));
+    else if (short_windows) IB_CUDA(cudaMemsetAsync(counters + 3, 0, 8, ctx->stream));   // the selection size (known to the caller by now) makes room for the dense-window count
+    ix->maybe_unfinished = short_windows;
     if (n > 0) {
         int result_in_b = 0;
         if (!pre) {
@@ -899,7 +901,6 @@ int giqlb_index_build_impl(giqlb_ctx* ctx, const giqlb_layout* lay, const int32_
     // Rows outside the layout raise the sticky flag checked at the next host round trip.
     ix->resolved = false;
     for (const auto& o : lay->observed) {
-        if (short_windows) break;   // d_counters[3] has to be looked at before the index is trusted
         if (o.code != code || o.sadj != start_adj || o.eadj != end_adj || o.n_degenerate < 0) continue;
         if (o.n_degenerate == 0 || (!rows && o.n == n)) {
             ix->n_degenerate = o.n_degenerate;
@@ -1092,7 +1093,8 @@ int giqlb_index_ensure_exists_dir(giqlb_ctx* ctx, giqlb_index* ix) {
 
 // Fetches the degenerate-row counts of up to two indexes in ONE round trip (no-op when already known).
 int giqlb_index_resolve(giqlb_ctx* ctx, giqlb_index* a, giqlb_index* b) {
-    giqlb_index* todo[2] = {a && !a->resolved ? a : nullptr, b && !b->resolved && b != a ? b : nullptr};
+    giqlb_index* todo[2] = {a && (!a->resolved || a->maybe_unfinished) ? a : nullptr,
+                            b && (!b->resolved || b->maybe_unfinished) && b != a ? b : nullptr};
     if (!todo[0] && !todo[1]) return GIQLB_OK;
     for (int k = 0; k < 2; k++)
         if (todo[k]) CUDA_TRY(ctx, cudaMemcpyAsync(ctx->h_scalars + 32 + 4 * k, todo[k]->d_counters, 4 * 8, cudaMemcpyDeviceToHost, ctx->stream));
@@ -1100,11 +1102,19 @@ int giqlb_index_resolve(giqlb_ctx* ctx, giqlb_index* a, giqlb_index* b) {
     for (int k = 0; k < 2; k++) {
         if (!todo[k]) continue;
         const int64_t* c = ctx->h_scalars + 32 + 4 * k;
-        todo[k]->n_degenerate = c[0];
-        todo[k]->n_negative = c[1];
-        todo[k]->resolved = true;
-        todo[k]->sort_unfinished = c[3] != 0;
-        if (c[3] != 0) return giqlb_fail(ctx, GIQLB_ERR_INTERNAL, "index: short-window sort left %lld rows unordered and the caller did not rebuild", (long long)c[3]);
+        if (!todo[k]->resolved) {
+            todo[k]->n_degenerate = c[0];
+            todo[k]->n_negative = c[1];
+            todo[k]->resolved = true;
+        }
+        if (todo[k]->maybe_unfinished) {
+            todo[k]->maybe_unfinished = false;
+            todo[k]->sort_unfinished = c[3] != 0;
+        }
+        if (todo[k]->sort_unfinished) {   // only the builder of the index can go on (pipeline.cu, shard.cu): internal status
+            giqlb_fail(ctx, GIQLB_ERR_INTERNAL, "index: short-window sort left rows unordered and the caller did not rebuild");
+            return GIQLB_RETRY_FULL_SORT;
+        }
         if (c[2] != 0) {
             cudaMemsetAsync(ctx->d_err + 3, 0, sizeof(int), ctx->stream);
             return giqlb_fail(ctx, GIQLB_ERR_RANGE, "index: %lld rows lie outside the layout (observe the table before finalize)", (long long)c[2]);

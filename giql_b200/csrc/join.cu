@@ -1393,8 +1393,15 @@ int giqlb_intersects_join_impl(giqlb_ctx* ctx, giqlb_index* L, giqlb_index* R, i
     if (L->grouped_by_strand || R->grouped_by_strand)
         return giqlb_fail(ctx, GIQLB_ERR_INVALID, "intersects: strand-grouped indexes are not accepted");
     const bool empty = L->n == 0 || R->n == 0;
-    const bool speculate = speculative && !empty && (!L->resolved || !R->resolved);
-    if (!speculate) GIQLB_TRY(giqlb_index_resolve(ctx, L, R));
+    // maybe_unfinished: an index sorted with GIQLB_INDEX_SORT_SHORT_WINDOWS whose dense-window count has not come back yet.  The
+    // fused path below checks it on the device and brings it back with the pair total; every other path looks first.
+    const bool unchecked = L->maybe_unfinished || R->maybe_unfinished;
+    const bool known = L->resolved && R->resolved;
+    const bool speculate = !empty && ((speculative && !known) || (unchecked && known && L->n_degenerate + R->n_degenerate == 0));
+    if (!speculate) {
+        const int rs = giqlb_index_resolve(ctx, L, R);
+        if (rs != GIQLB_OK) return rs;   // (GIQLB_RETRY_FULL_SORT included)
+    }
     int64_t total = 0;
     int st = GIQLB_OK;
     if (!speculate && !empty && L->n_degenerate + R->n_degenerate > 0 && L->n_degenerate < L->n && R->n_degenerate < R->n) {
@@ -1429,7 +1436,7 @@ int giqlb_intersects_join_impl(giqlb_ctx* ctx, giqlb_index* L, giqlb_index* R, i
             {
                 PhaseSpan ps(ctx, GIQLB_PH_JOIN_COUNT);
                 join_partition_kernel<<<(unsigned)ceil_div(n_tiles + 1, 256), 256, 0, ctx->stream>>>(
-                    L->gs, L->n, R->gs, R->n, n_tiles, part, recs, !L->resolved ? L->d_counters + 3 : nullptr, !R->resolved ? R->d_counters + 3 : nullptr);
+                    L->gs, L->n, R->gs, R->n, n_tiles, part, recs, L->maybe_unfinished ? L->d_counters + 3 : nullptr, R->maybe_unfinished ? R->d_counters + 3 : nullptr);
                 ctx->launches_this_call++;
                 ctx->stats.kernels_total++;
             }
@@ -1451,7 +1458,7 @@ int giqlb_intersects_join_impl(giqlb_ctx* ctx, giqlb_index* L, giqlb_index* R, i
             }
             if (cudaGetLastError() != cudaSuccess) st = giqlb_fail(ctx, GIQLB_ERR_CUDA, "intersects_join: launch failed");
         }
-        giqlb_index* pending[2] = {!L->resolved ? L : nullptr, !R->resolved && R != L ? R : nullptr};
+        giqlb_index* pending[2] = {!L->resolved || L->maybe_unfinished ? L : nullptr, (!R->resolved || R->maybe_unfinished) && R != L ? R : nullptr};
         for (int k = 0; k < 2 && st == GIQLB_OK; k++)   // the degenerate-row counts ride along with the pair total
             if (pending[k]) cudaMemcpyAsync(ctx->h_scalars + 32 + 4 * k, pending[k]->d_counters, 4 * 8, cudaMemcpyDeviceToHost, ctx->stream);
         if (st == GIQLB_OK) st = fetch_scalars_checked(ctx, totals, 1);
@@ -1459,10 +1466,15 @@ int giqlb_intersects_join_impl(giqlb_ctx* ctx, giqlb_index* L, giqlb_index* R, i
         bool degenerate = false, unfinished = false;
         for (int k = 0; k < 2 && st == GIQLB_OK; k++) {
             if (!pending[k]) continue;
-            pending[k]->n_degenerate = ctx->h_scalars[32 + 4 * k];
-            pending[k]->n_negative = ctx->h_scalars[33 + 4 * k];
-            pending[k]->resolved = true;
-            pending[k]->sort_unfinished = ctx->h_scalars[35 + 4 * k] != 0;
+            if (!pending[k]->resolved) {
+                pending[k]->n_degenerate = ctx->h_scalars[32 + 4 * k];
+                pending[k]->n_negative = ctx->h_scalars[33 + 4 * k];
+                pending[k]->resolved = true;
+            }
+            if (pending[k]->maybe_unfinished) {
+                pending[k]->maybe_unfinished = false;
+                pending[k]->sort_unfinished = ctx->h_scalars[35 + 4 * k] != 0;
+            }
             unfinished = unfinished || pending[k]->sort_unfinished;
             degenerate = degenerate || pending[k]->n_degenerate > 0;
         }

@@ -385,6 +385,7 @@ extern "C" int giqlb_index_build_range(giqlb_ctx* ctx, const giqlb_layout* lay, 
 // names, layout extent, selection sizes, pair total.
 static int sharded_impl(giqlb_ctx* ctx, giqlb_table_t* L, giqlb_table_t* R, int32_t n_codes, int world, int rank, int32_t* out_l,
                         int32_t* out_r, int64_t capacity, int64_t* total_host, giqlb_dict** dict_out, bool async_dict) {
+    const int32_t n_codes_in = n_codes;
     giqlb_dict* dict = nullptr;
     giqlb_dict_pending* pend = nullptr;
     const int32_t* slot2code = nullptr;
@@ -488,15 +489,18 @@ static int sharded_impl(giqlb_ctx* ctx, giqlb_table_t* L, giqlb_table_t* R, int3
     for (int k = 0; k < 2 && st == GIQLB_OK; k++) {
         giqlb_index** dst = k == 0 ? &il : &ir;
         const int64_t deg = ctx->h_scalars[40 + 4 * k], neg = ctx->h_scalars[41 + 4 * k];
+        // private indexes that can be rebuilt here: three radix passes + the window-finishing pass (index.cu)
         st = giqlb_index_build_impl(ctx, lay, T[k]->codes, T[k]->start, T[k]->end, nullptr, pre[k].rows, n_sel[k], T[k]->start_adj,
-                                    T[k]->end_adj, 0, &pre[k], dst);
+                                    T[k]->end_adj, GIQLB_INDEX_SORT_SHORT_WINDOWS, &pre[k], dst);
         if (st == GIQLB_OK) {   // the counters came back with the selection sizes
             (*dst)->n_degenerate = deg;
             (*dst)->n_negative = neg;
             (*dst)->resolved = true;
         }
     }
-    if (st == GIQLB_OK) st = giqlb_intersects_join(ctx, il, ir, out_l, out_r, capacity, total_host);
+    if (st == GIQLB_OK) st = giqlb_intersects_join_impl(ctx, il, ir, out_l, out_r, capacity, total_host, false);
+    const bool resort = st == GIQLB_RETRY_FULL_SORT;   // a dense window: redo the call with fully sorted indexes (see pipeline.cu)
+    if (resort) st = GIQLB_OK;
     char msg[sizeof(ctx->err)];
     memcpy(msg, ctx->err, sizeof(msg));
     for (int k = 0; k < 2; k++) {
@@ -506,6 +510,11 @@ static int sharded_impl(giqlb_ctx* ctx, giqlb_table_t* L, giqlb_table_t* R, int3
     giqlb_index_free(ctx, il);
     giqlb_index_free(ctx, ir);
     giqlb_layout_free(ctx, lay);
+    if (resort && st == GIQLB_OK) {
+        giqlb_dict_free(dict);
+        ctx->full_sort_credit = 64;
+        return sharded_impl(ctx, L, R, n_codes_in, world, rank, out_l, out_r, capacity, total_host, dict_out, async_dict);
+    }
     if (encode && dict && (st == GIQLB_OK || st == GIQLB_ERR_CAPACITY)) L->codes_valid = R->codes_valid = 1;
     if (dict_out) *dict_out = dict;
     else giqlb_dict_free(dict);

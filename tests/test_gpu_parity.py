@@ -764,3 +764,13 @@ def test_short_window_sort_and_dense_window_resort(c_oracle):
     assert run(*dense) == 6 + 8                       # the attempt, then the rebuild with four passes per table
     assert run(*sparse) == 8                          # credit: full sort without an attempt
     assert run(table(50_000, dense_rows=40_000), table(60_000, dense_rows=100)) == 8
+
+    # the sharded one-call path (giqlb_intersects_tables_sharded) takes the same sort and the same way out
+    eng2 = giql_b200.Engine(0)
+    eng2._pair_capacity = 1 << 23
+    for A, B in (sparse, dense, sparse):
+        ta = eng2.table_from_codes(A["code"], A["start"], A["end"], ["c1", "c2", "c3"])
+        tb = eng2.table_from_codes(B["code"], B["start"], B["end"], ta.dictionary)
+        parts = [eng2.intersects_shard(ta, tb, 2, g).sorted_packed() for g in range(2)]
+        exp = c_oracle.intersects_pairs(A["code"], A["start"], A["end"], B["code"], B["start"], B["end"], 3)
+        assert np.array_equal(np.sort(np.concatenate(parts)), (exp[:, 0] << 32) | exp[:, 1])
