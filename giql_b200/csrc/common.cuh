@@ -30,6 +30,7 @@ struct giqlb_ctx {
     int* d_err = nullptr;           // device int[4]: sticky kernel-side error flags ([0] look-back spin limit)
     giqlb_stats_t stats = {};
     bool join_smem_opted_in = false;   // cudaFuncSetAttribute is per device: remembered per context, not per process
+    bool dict_smem_opted_in = false;
     int full_sort_credit = 0;          // > 0: the next index builds skip the short-window sort (a dense table was seen; see index.cu)
     int32_t launches_this_call = 0;
     // Scratch cache.  Every allocation of a context is used on ITS stream only, so a freed block can be handed
