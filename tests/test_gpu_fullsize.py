@@ -38,6 +38,23 @@ def test_c2_headline_join_is_the_exact_multiset(engine, c_oracle):
     assert ta.dictionary.names == sorted(A["names"], key=lambda s: s.encode())
 
 
+def test_one_call_join_with_a_table_beyond_the_l2(engine, c_oracle):
+    """26 M x 2 M through the one-call path: the larger index takes the full sort with the ends carried as a second payload
+    (tables of 24 M rows and more), the smaller one the three-pass sort; the sorted multiset of pairs must be the oracle's"""
+    A, B = synth.peaks(26_000_000, 20260111), synth.peaks(2_000_000, 20260112)
+    ta = engine.table_from_codes(A["code"], A["start"], A["end"], A["names"])
+    tb = engine.table_from_codes(B["code"], B["start"], B["end"], ta.dictionary)
+    for left, right, swap in ((ta, tb, False), (tb, ta, True)):
+        got = engine.intersects(left, right).sorted_packed()
+        L, R = (B, A) if swap else (A, B)
+        total, out_l, out_r = c_oracle.intersects_join_timed(L["code"], L["start"], L["end"], R["code"], R["start"], R["end"], len(A["names"]),
+                                                             capacity=len(got) + 1024)
+        assert total == len(got) > 1_000_000
+        exp = (out_l[:total].astype(np.int64) << 32) | out_r[:total].astype(np.int64)
+        exp.sort()
+        assert np.array_equal(got, exp)
+
+
 def test_c3_semi_anti_50m_by_1m(engine, c_oracle):
     Q, T = synth.peaks(50_000_000, 20260105), synth.peaks(1_000_000, 20260106)
     tq = engine.table_from_codes(Q["code"], Q["start"], Q["end"], Q["names"])
