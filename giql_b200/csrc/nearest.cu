@@ -59,7 +59,8 @@ struct NearestArgs {
 // each; its k result slots are x * k .. x * k + k - 1, written straight into the output arrays (with every query row
 // yielding exactly k rows — the common case — they need no compaction afterwards).
 __global__ void __launch_bounds__(128)
-nearest_kernel(ProbeCols Q, const uint8_t* __restrict__ q_strand, const uint32_t* __restrict__ order, TargetView T, NearestArgs A,
+nearest_kernel(ProbeCols Q, const uint8_t* __restrict__ q_strand, const uint32_t* __restrict__ order, const int4* __restrict__ packed,
+               TargetView T, NearestArgs A,
                int32_t* __restrict__ tmp_q, int32_t* __restrict__ tmp_t, int32_t* __restrict__ tmp_d, uint8_t* __restrict__ tmp_v,
                uint32_t* __restrict__ cnt, unsigned long long* __restrict__ total, int* __restrict__ err) {
     unsigned long long emitted = 0;
@@ -68,9 +69,19 @@ nearest_kernel(ProbeCols Q, const uint8_t* __restrict__ q_strand, const uint32_t
         uint32_t n_out = 0;
         const int64_t slot0 = x * A.k;
         uint32_t qs_lin, qe_lin;
-        const uint8_t sq = A.stranded ? q_strand[i] : (uint8_t)GIQLB_STRAND_PLUS;
+        // the query row: from its packed record when the rows are visited in key order, from the columns otherwise
+        int32_t q_code, q_start, q_end;
+        uint8_t sq;
+        if (packed) {
+            const int4 r = __ldg(packed + i);
+            q_code = r.x; q_start = r.y; q_end = r.z;
+            sq = A.stranded ? (uint8_t)r.w : (uint8_t)GIQLB_STRAND_PLUS;
+        } else {
+            q_code = Q.code[i]; q_start = Q.start[i]; q_end = Q.end[i];
+            sq = A.stranded ? q_strand[i] : (uint8_t)GIQLB_STRAND_PLUS;
+        }
         int64_t blo = 0, bhi = T.n;
-        bool any = T.n > 0 && probe_linearise(Q, i, qs_lin, qe_lin);
+        bool any = T.n > 0 && probe_linearise_values(Q, q_code, q_start, q_end, qs_lin, qe_lin);
         int slot = 0;
         if (any && A.stranded) {
             if (sq == GIQLB_STRAND_NULL) any = false;   // NULL = anything is never true
@@ -82,10 +93,10 @@ nearest_kernel(ProbeCols Q, const uint8_t* __restrict__ q_strand, const uint32_t
             }
         }
         if (any) {
-            const int32_t c = Q.code[i];
+            const int32_t c = q_code;
             const uint32_t cb_lo = __ldg(Q.base + c), cb_hi = __ldg(Q.base + c + 1);
             const long long lo_c = __ldg(Q.lo32 + c);
-            const long long qs = (long long)Q.start[i] + Q.sadj, qe = (long long)Q.end[i] + Q.eadj;
+            const long long qs = (long long)q_start + Q.sadj, qe = (long long)q_end + Q.eadj;
             const uint32_t* gs = T.gs + blo;
             const uint32_t* ge = T.ge + blo;
             const int32_t* rid = T.rid + blo;
@@ -185,12 +196,16 @@ struct InCnt {
     const uint32_t* cnt;
     __device__ unsigned long long operator()(int64_t i) const { return cnt[i]; }
 };
-// linear start of every query row (clamped into its chromosome's guard cells; rows that cannot match sort last)
+// linear start of every query row (clamped into its chromosome's guard cells; rows that cannot match sort last), and the row
+// itself as one 16-byte record {code, start, end, strand}: the search kernel visits the rows in key order, i.e. at random, and
+// fetches one sector per query instead of one per column (ncu: 2.0 GB of DRAM reads for 10 M queries before, four sectors each)
 __global__ void __launch_bounds__(256)
-nearest_query_keys_kernel(ProbeCols Q, uint32_t* __restrict__ keys) {
+nearest_query_keys_kernel(ProbeCols Q, const uint8_t* __restrict__ q_strand, uint32_t* __restrict__ keys, int4* __restrict__ packed) {
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < Q.n; i += (int64_t)gridDim.x * blockDim.x) {
+        const int32_t c = Q.code[i], s = Q.start[i], e = Q.end[i];
         uint32_t gs, ge;
-        keys[i] = probe_linearise(Q, i, gs, ge) ? gs : 0xffffffffu;
+        keys[i] = probe_linearise_values(Q, c, s, e, gs, ge) ? gs : 0xffffffffu;
+        packed[i] = make_int4(c, s, e, q_strand ? (int)q_strand[i] : (int)GIQLB_STRAND_PLUS);
     }
 }
 
@@ -244,6 +259,7 @@ extern "C" int giqlb_nearest(giqlb_ctx* ctx, const giqlb_layout* lay, const int3
     GIQLB_TRY(giqlb_index_ensure_block_max(ctx, T));
     uint32_t* cnt = nullptr;
     uint32_t *ka = nullptr, *kb = nullptr, *va = nullptr, *vb = nullptr;
+    int4* packed = nullptr;
     const uint32_t* order = nullptr;
     unsigned long long* total = reinterpret_cast<unsigned long long*>(ctx->d_scalars + 10);
     const size_t slots = (size_t)k * (size_t)n_q;
@@ -255,11 +271,12 @@ extern "C" int giqlb_nearest(giqlb_ctx* ctx, const giqlb_layout* lay, const int3
         if (st == GIQLB_OK) st = dev_alloc(ctx, &kb, (size_t)n_q);
         if (st == GIQLB_OK) st = dev_alloc(ctx, &va, (size_t)n_q);
         if (st == GIQLB_OK) st = dev_alloc(ctx, &vb, (size_t)n_q);
+        if (st == GIQLB_OK) st = dev_alloc(ctx, &packed, (size_t)n_q);
         if (st == GIQLB_OK) {
             {
                 PhaseSpan ps(ctx, GIQLB_PH_KEYGEN);
                 int64_t blocks = ceil_div(n_q, 256 * 4), cap = (int64_t)ctx->sm_count * 8;
-                nearest_query_keys_kernel<<<(unsigned)(blocks < cap ? blocks : cap), 256, 0, ctx->stream>>>(Q, ka);
+                nearest_query_keys_kernel<<<(unsigned)(blocks < cap ? blocks : cap), 256, 0, ctx->stream>>>(Q, stranded ? q_strand : nullptr, ka, packed);
                 LAUNCH_CHECK(ctx);
             }
             int in_b = 0;
@@ -276,7 +293,7 @@ extern "C" int giqlb_nearest(giqlb_ctx* ctx, const giqlb_layout* lay, const int3
         NearestArgs A{k, max_distance < 0 ? -1ll : (long long)max_distance, stranded != 0, signed_ != 0};
         int64_t blocks = ceil_div(n_q, 128), cap = (int64_t)ctx->sm_count * 32;
         // results land in the output arrays themselves, k slots per query row
-        nearest_kernel<<<(unsigned)(blocks < cap ? blocks : cap), 128, 0, ctx->stream>>>(Q, q_strand, order, V, A, out_q, out_t, out_dist, out_valid, cnt, total, ctx->d_err);
+        nearest_kernel<<<(unsigned)(blocks < cap ? blocks : cap), 128, 0, ctx->stream>>>(Q, q_strand, order, order ? packed : nullptr, V, A, out_q, out_t, out_dist, out_valid, cnt, total, ctx->d_err);
         ctx->launches_this_call++;
         ctx->stats.kernels_total++;
         if (cudaGetLastError() != cudaSuccess) st = giqlb_fail(ctx, GIQLB_ERR_CUDA, "nearest: launch failed");
@@ -306,6 +323,7 @@ extern "C" int giqlb_nearest(giqlb_ctx* ctx, const giqlb_layout* lay, const int3
         dev_free(ctx, tmp_v);
     }
     dev_free(ctx, cnt);
+    dev_free(ctx, packed);
     dev_free(ctx, ka);
     dev_free(ctx, kb);
     dev_free(ctx, va);
