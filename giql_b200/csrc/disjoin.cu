@@ -30,6 +30,8 @@ struct DisjoinView {
     int filter;             // 1: keep only covered segments (reference is not the target itself)
     const uint8_t* cov;     // filter only: cov[j] = some reference row covers breakpoint bp[j] (computed once per call, so a
                             // segment that starts at a breakpoint needs one byte instead of a search)
+    const uint32_t* cov_before;   // filter only: cov_before[j] = cov[0] + .. + cov[j - 1], j = 0 .. n_bp: the number of kept segments
+                                  // among any run of a row's cuts is a difference of two entries (count and output slot in O(1))
 };
 
 __device__ __forceinline__ bool covered(const DisjoinView& V, uint32_t p) {
@@ -116,33 +118,24 @@ disjoin_cover_kernel(DisjoinView V, uint8_t* __restrict__ cov) {
         cov[j] = covered(V, V.bp[j]) ? 1 : 0;
 }
 
+// kept segments of a walked row among j = lo + 1 .. j_last (the ones that start at a breakpoint)
+__device__ __forceinline__ unsigned long long kept_after_first(const DisjoinView& V, const RowCuts& r, int64_t j_last) {
+    if (j_last <= r.lo) return 0ull;
+    return V.filter ? (unsigned long long)(__ldg(V.cov_before + j_last) - __ldg(V.cov_before + r.lo)) : (unsigned long long)(j_last - r.lo);
+}
+
 __global__ void __launch_bounds__(256)
 disjoin_count_kernel(ProbeCols T, DisjoinView V, unsigned long long* __restrict__ cnt) {
-    for (int64_t base = (int64_t)blockIdx.x * blockDim.x; base < T.n; base += (int64_t)gridDim.x * blockDim.x) {
-        const int64_t i = base + threadIdx.x;
-        const bool live = i < T.n;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < T.n; i += (int64_t)gridDim.x * blockDim.x) {
         RowCuts r;
-        const bool heavy = live && row_cuts(T, V, i, r) && r.hi - r.lo + 1 > DJ_HEAVY;
-        unsigned long long n = 0;
-        if (live && !heavy) n = for_each_segment(T, V, i, [](unsigned long long, long long, long long) {});
-        uint32_t todo = __ballot_sync(FULL_MASK, heavy);
-        while (todo) {
-            const int src = __ffs(todo) - 1;
-            todo &= todo - 1;
-            RowCuts b;
-            b.ts = __shfl_sync(FULL_MASK, r.ts, src); b.te = __shfl_sync(FULL_MASK, r.te, src); b.lo_c = __shfl_sync(FULL_MASK, r.lo_c, src);
-            b.gs = __shfl_sync(FULL_MASK, r.gs, src); b.ge = __shfl_sync(FULL_MASK, r.ge, src); b.b1 = __shfl_sync(FULL_MASK, r.b1, src);
-            b.lo = __shfl_sync(FULL_MASK, r.lo, src); b.hi = __shfl_sync(FULL_MASK, r.hi, src);
-            unsigned long long c = 0;
-#pragma unroll 4
-            for (int64_t j = b.lo + lane_id(); j <= b.hi; j += 32) {
-                long long s, e;
-                c += cut_segment(V, b, j, s, e);
-            }
-            c = warp_reduce_add(c);
-            if ((int)lane_id() == src) n = c;
+        unsigned long long n;
+        if (row_cuts(T, V, i, r) && r.hi - r.lo + 1 > DJ_HEAVY) {
+            // a heavily cut row is not walked to be counted: the first segment is tested, the others are a difference of prefix counts
+            n = (!V.filter || covered(V, r.gs) ? 1ull : 0ull) + kept_after_first(V, r, r.hi);
+        } else {
+            n = for_each_segment(T, V, i, [](unsigned long long, long long, long long) {});
         }
-        if (live) cnt[i] = n;
+        cnt[i] = n;
     }
 }
 
@@ -160,22 +153,47 @@ struct OutOffsets {
     }
 };
 
+// Rows cut more than DJ_SUPER times (a chromosome-spanning target: ~10^5 cuts) are not even a warp's job: the emit kernel
+// records them, and a second kernel deals their segments to the whole grid — the output slot of segment j is the row's offset
+// plus a difference of prefix counts, so every thread can place its segment without knowing the others'.
+constexpr int64_t DJ_SUPER = 4096;
+constexpr uint32_t DJ_SUPER_MAX = 4096;   // list entries; rows beyond that take the warp path
+struct SuperRow {
+    RowCuts r;
+    unsigned long long o;
+    int32_t row;
+    uint32_t keep0;
+};
+
 __global__ void __launch_bounds__(256)
 disjoin_emit_kernel(ProbeCols T, DisjoinView V, const unsigned long long* __restrict__ off, int32_t* __restrict__ out_row,
-                    int32_t* __restrict__ out_start, int32_t* __restrict__ out_end) {
+                    int32_t* __restrict__ out_start, int32_t* __restrict__ out_end, SuperRow* __restrict__ super_rows,
+                    uint32_t* __restrict__ n_super) {
     const uint32_t lt_mask = (1u << lane_id()) - 1u;
     for (int64_t base = (int64_t)blockIdx.x * blockDim.x; base < T.n; base += (int64_t)gridDim.x * blockDim.x) {
         const int64_t i = base + threadIdx.x;
         const bool live = i < T.n;
         RowCuts r;
-        const bool heavy = live && row_cuts(T, V, i, r) && r.hi - r.lo + 1 > DJ_HEAVY;
+        bool heavy = live && row_cuts(T, V, i, r) && r.hi - r.lo + 1 > DJ_HEAVY;
         const unsigned long long o = live ? off[i] : 0ull;
-        if (live && !heavy)
+        if (heavy && r.hi - r.lo + 1 > DJ_SUPER) {
+            const uint32_t slot = atomicAdd(n_super, 1u);
+            if (slot < DJ_SUPER_MAX) {
+                SuperRow sr;
+                sr.r = r;
+                sr.o = o;
+                sr.row = (int32_t)i;
+                sr.keep0 = !V.filter || covered(V, r.gs) ? 1u : 0u;
+                super_rows[slot] = sr;
+                heavy = false;             // (not walked here)
+            }
+        } else if (live && !heavy) {
             for_each_segment(T, V, i, [&](unsigned long long k, long long s, long long e) {
                 out_row[o + k] = (int32_t)i;
                 out_start[o + k] = (int32_t)s;
                 out_end[o + k] = (int32_t)e;
             });
+        }
         uint32_t todo = __ballot_sync(FULL_MASK, heavy);
         while (todo) {
             const int src = __ffs(todo) - 1;
@@ -212,10 +230,43 @@ disjoin_emit_kernel(ProbeCols T, DisjoinView V, const unsigned long long* __rest
 }
 
 __global__ void __launch_bounds__(256)
+disjoin_emit_super_kernel(DisjoinView V, const SuperRow* __restrict__ super_rows, const uint32_t* __restrict__ n_super,
+                          int32_t* __restrict__ out_row, int32_t* __restrict__ out_start, int32_t* __restrict__ out_end) {
+    const uint32_t n = min(*n_super, DJ_SUPER_MAX);
+    const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x, stride = (int64_t)gridDim.x * blockDim.x;
+    for (uint32_t k = 0; k < n; k++) {
+        const SuperRow sr = super_rows[k];
+        for (int64_t j = sr.r.lo + tid; j <= sr.r.hi; j += stride) {
+            long long s, e;
+            const bool keep = j == sr.r.lo ? sr.keep0 != 0 : cut_segment(V, sr.r, j, s, e);
+            if (!keep) continue;
+            if (j == sr.r.lo) cut_segment(V, sr.r, j, s, e);     // (coordinates of the first segment; its coverage was tested once)
+            const unsigned long long pos = sr.o + (j == sr.r.lo ? 0ull : sr.keep0 + kept_after_first(V, sr.r, j - 1));
+            out_row[pos] = sr.row;
+            out_start[pos] = (int32_t)s;
+            out_end[pos] = (int32_t)e;
+        }
+    }
+}
+
+__global__ void __launch_bounds__(256)
 concat_kernel(const uint32_t* __restrict__ a, const uint32_t* __restrict__ b, int64_t n, uint32_t* __restrict__ out) {
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < 2 * n; i += (int64_t)gridDim.x * blockDim.x)
         out[i] = i < n ? a[i] : b[i - n];
 }
+
+struct InCov {
+    const uint8_t* cov;
+    __device__ unsigned long long operator()(int64_t i) const { return cov[i]; }
+};
+struct OutCovBefore {
+    uint32_t* before;
+    int64_t n;
+    __device__ void operator()(int64_t i, unsigned long long excl, unsigned long long v) const {
+        before[i] = (uint32_t)excl;
+        if (i == n - 1) before[n] = (uint32_t)(excl + v);
+    }
+};
 
 struct InIsNew {
     const uint32_t* k;
@@ -277,7 +328,7 @@ extern "C" int giqlb_disjoin(giqlb_ctx* ctx, const giqlb_layout* lay, const int3
         }
     }
     uint8_t* cov = nullptr;
-    DisjoinView V{bp, n_bp, REF->gs, REF->pmax, nr, self_reference ? 0 : 1, nullptr};
+    DisjoinView V{bp, n_bp, REF->gs, REF->pmax, nr, self_reference ? 0 : 1, nullptr, nullptr};
     if (st == GIQLB_OK && V.filter && n_bp > 0) {
         st = dev_alloc(ctx, &cov, (size_t)n_bp);
         if (st == GIQLB_OK) {
@@ -288,6 +339,15 @@ extern "C" int giqlb_disjoin(giqlb_ctx* ctx, const giqlb_layout* lay, const int3
             V.cov = cov;
         }
     }
+    uint32_t* cov_before = nullptr;
+    if (st == GIQLB_OK && V.cov) {
+        st = dev_alloc(ctx, &cov_before, (size_t)n_bp + 1);
+        if (st == GIQLB_OK) st = launch_scan<OpAddU64>(ctx, n_bp, InCov{cov}, OutCovBefore{cov_before, n_bp});
+        V.cov_before = cov_before;
+    }
+    SuperRow* super_rows = nullptr;
+    uint32_t* n_super = reinterpret_cast<uint32_t*>(ctx->d_scalars + 12);
+    if (st == GIQLB_OK) st = dev_alloc(ctx, &super_rows, (size_t)DJ_SUPER_MAX);
     unsigned long long* cnt = nullptr;
     if (st == GIQLB_OK) st = dev_alloc(ctx, &off, (size_t)n_t);
     if (st == GIQLB_OK) st = dev_alloc(ctx, &cnt, (size_t)n_t);
@@ -308,12 +368,14 @@ extern "C" int giqlb_disjoin(giqlb_ctx* ctx, const giqlb_layout* lay, const int3
     }
     if (st == GIQLB_OK && n_out > 0) {
         int64_t blocks = ceil_div(n_t, 256), cap = (int64_t)ctx->sm_count * 16;
-        disjoin_emit_kernel<<<(unsigned)(blocks < cap ? blocks : cap), 256, 0, ctx->stream>>>(T, V, off, out_row, out_start, out_end);
-        ctx->launches_this_call++;
-        ctx->stats.kernels_total++;
+        cudaMemsetAsync(n_super, 0, 4, ctx->stream);
+        disjoin_emit_kernel<<<(unsigned)(blocks < cap ? blocks : cap), 256, 0, ctx->stream>>>(T, V, off, out_row, out_start, out_end, super_rows, n_super);
+        disjoin_emit_super_kernel<<<ctx->sm_count * 8, 256, 0, ctx->stream>>>(V, super_rows, n_super, out_row, out_start, out_end);
+        ctx->launches_this_call += 2;
+        ctx->stats.kernels_total += 2;
         if (cudaGetLastError() != cudaSuccess) st = giqlb_fail(ctx, GIQLB_ERR_CUDA, "disjoin: emit launch failed");
     }
-    dev_free(ctx, ka); dev_free(ctx, kb); dev_free(ctx, va); dev_free(ctx, vb); dev_free(ctx, bp); dev_free(ctx, off); dev_free(ctx, cnt); dev_free(ctx, cov);
+    dev_free(ctx, ka); dev_free(ctx, kb); dev_free(ctx, va); dev_free(ctx, vb); dev_free(ctx, bp); dev_free(ctx, off); dev_free(ctx, cnt); dev_free(ctx, cov); dev_free(ctx, cov_before); dev_free(ctx, super_rows);
     if (st != GIQLB_OK) return st;
     ctx->stats.rows_in[0] = n_t;
     ctx->stats.rows_in[1] = nr;

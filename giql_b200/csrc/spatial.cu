@@ -50,11 +50,35 @@ __device__ __forceinline__ unsigned long long warp_count_contained(const uint32_
     return warp_reduce_add(c);
 }
 
-// per-thread count of row i's contained candidates; heavy runs are counted by the whole warp (all lanes must call)
-__device__ __forceinline__ unsigned long long count_row(const Side& Y, bool live, int64_t lo, int64_t hi, uint32_t xge) {
-    const bool heavy = live && hi - lo > SP_HEAVY;
+// Containers with more than SP_SUPER candidates (a chromosome-spanning interval: ~10^5) are the whole CTA's job: a warp alone
+// walks them at one 128-row step per L2 round trip (1.1 ms for one such row among 1 M, three walks), 256 threads with eight
+// loads each in flight do it in a tenth of that.  Up to SP_SUPER_SLOTS of them per 256-row step of the tile; more take the warp path.
+constexpr int64_t SP_SUPER = 4096;
+constexpr int SP_SUPER_SLOTS = 8;
+struct SuperRows {
+    int n;
+    int64_t lo[SP_SUPER_SLOTS], hi[SP_SUPER_SLOTS];
+    uint32_t xge[SP_SUPER_SLOTS];
+    int32_t xr[SP_SUPER_SLOTS];
+    unsigned long long cnt[SP_SUPER_SLOTS], out[SP_SUPER_SLOTS], cursor[SP_SUPER_SLOTS];
+};
+
+// per-thread count of row i's contained candidates; heavy runs are counted by the whole warp, super-heavy ones by the whole
+// CTA (ALL threads of the CTA must call, with the same `sr`).  *slot = the row's entry in sr (-1: none).
+__device__ __forceinline__ unsigned long long count_row(const Side& Y, bool live, int64_t lo, int64_t hi, uint32_t xge, SuperRows& sr, int* slot) {
+    if (threadIdx.x == 0) sr.n = 0;
+    __syncthreads();
+    *slot = -1;
+    if (live && hi - lo > SP_SUPER) {
+        const int e = atomicAdd(&sr.n, 1);
+        if (e < SP_SUPER_SLOTS) {
+            sr.lo[e] = lo; sr.hi[e] = hi; sr.xge[e] = xge; sr.cnt[e] = 0ull; sr.cursor[e] = 0ull;
+            *slot = e;
+        }
+    }
+    const bool heavy = live && hi - lo > SP_HEAVY && *slot < 0;
     unsigned long long cnt = 0;
-    if (live && !heavy)
+    if (live && hi - lo <= SP_HEAVY)
         for (int64_t k = lo; k < hi; k++) cnt += __ldg(Y.ge + k) <= xge;
     uint32_t todo = __ballot_sync(FULL_MASK, heavy);
     while (todo) {
@@ -64,6 +88,19 @@ __device__ __forceinline__ unsigned long long count_row(const Side& Y, bool live
                                                           __shfl_sync(FULL_MASK, xge, src));
         if ((int)lane_id() == src) cnt = c;
     }
+    __syncthreads();
+    const int n_super = min(sr.n, SP_SUPER_SLOTS);
+    for (int e = 0; e < n_super; e++) {
+        const int64_t blo = sr.lo[e], bhi = sr.hi[e];
+        const uint32_t bx = sr.xge[e];
+        unsigned long long c = 0;
+#pragma unroll 8
+        for (int64_t k = blo + threadIdx.x; k < bhi; k += SPB) c += __ldg(Y.ge + k) <= bx;
+        c = warp_reduce_add(c);
+        if (lane_id() == 0 && c) atomicAdd(&sr.cnt[e], c);
+    }
+    __syncthreads();
+    if (*slot >= 0) cnt = sr.cnt[*slot];
     return cnt;
 }
 
@@ -71,6 +108,7 @@ __global__ void __launch_bounds__(SPB)
 contains_count_kernel(Side X, Side Y, const uint32_t* __restrict__ base, int32_t n_codes, int y_has_negative,
                       unsigned long long* __restrict__ tile_cnt) {
     __shared__ unsigned long long s_red[SPB / 32];
+    __shared__ SuperRows s_super;
     unsigned long long cnt = 0;
     const int64_t t0 = (int64_t)blockIdx.x * SPT;
 #pragma unroll 1
@@ -83,7 +121,8 @@ contains_count_kernel(Side X, Side Y, const uint32_t* __restrict__ base, int32_t
             xge = X.ge[i];
             candidates(X.gs[i], xge, Y, base, n_codes, y_has_negative, lo, hi);
         }
-        cnt += count_row(Y, live, lo, hi, xge);
+        int slot;
+        cnt += count_row(Y, live, lo, hi, xge, s_super, &slot);
     }
     cnt = warp_reduce_add(cnt);
     if (lane_id() == 0) s_red[warp_id()] = cnt;
@@ -99,6 +138,7 @@ __global__ void __launch_bounds__(SPB)
 contains_emit_kernel(Side X, Side Y, const uint32_t* __restrict__ base, int32_t n_codes, int y_has_negative,
                      const unsigned long long* __restrict__ tile_off, int32_t* __restrict__ out_x, int32_t* __restrict__ out_y) {
     __shared__ unsigned long long s_scratch[SPB / 32 + 2];
+    __shared__ SuperRows s_super;
     const int64_t t0 = (int64_t)blockIdx.x * SPT;
     unsigned long long carry = tile_off[blockIdx.x];
     const uint32_t lt_mask = (1u << lane_id()) - 1u;
@@ -112,13 +152,18 @@ contains_emit_kernel(Side X, Side Y, const uint32_t* __restrict__ base, int32_t 
             xge = X.ge[i];
             candidates(X.gs[i], xge, Y, base, n_codes, y_has_negative, lo, hi);
         }
-        const unsigned long long cnt = count_row(Y, live, lo, hi, xge);
+        int slot;
+        const unsigned long long cnt = count_row(Y, live, lo, hi, xge, s_super, &slot);
         unsigned long long tot;
         unsigned long long o = carry + block_excl_scan_add<unsigned long long>(cnt, s_scratch, &tot);
         carry += tot;
-        const bool heavy = live && hi - lo > SP_HEAVY;
+        const bool heavy = live && hi - lo > SP_HEAVY && slot < 0;
         const int32_t xr = live ? X.rid[i] : 0;
-        if (cnt && !heavy) {
+        if (slot >= 0) {
+            s_super.out[slot] = o;
+            s_super.xr[slot] = xr;
+        }
+        if (cnt && live && hi - lo <= SP_HEAVY) {
             for (int64_t k = lo; k < hi; k++)
                 if (__ldg(Y.ge + k) <= xge) {
                     out_x[o] = xr;
@@ -152,6 +197,39 @@ contains_emit_kernel(Side X, Side Y, const uint32_t* __restrict__ base, int32_t 
                         out_y[pos] = yr[u];
                     }
                     bo += __popc(m);
+                }
+            }
+        }
+        __syncthreads();
+        // super-heavy rows: the whole CTA emits the run; slots are claimed per warp from a shared cursor, so the order of a
+        // row's pairs is not the candidate order (pair order is unspecified anyway)
+        const int n_super = min(s_super.n, SP_SUPER_SLOTS);
+        for (int e = 0; e < n_super; e++) {
+            const int64_t blo = s_super.lo[e], bhi = s_super.hi[e];
+            const uint32_t bx = s_super.xge[e];
+            const int32_t bxr = s_super.xr[e];
+            const unsigned long long bo = s_super.out[e];
+            const int64_t span = ((bhi - blo + 4 * SPB - 1) / (4 * SPB)) * (4 * SPB);     // whole warps stay in the loop together
+            for (int64_t k0 = 0; k0 < span; k0 += 4 * SPB) {
+                bool keep[4];
+                int32_t yr[4];
+#pragma unroll
+                for (int u = 0; u < 4; u++) {
+                    const int64_t k = blo + k0 + u * SPB + threadIdx.x;
+                    keep[u] = k < bhi && __ldg(Y.ge + k) <= bx;
+                    yr[u] = k < bhi ? __ldg(Y.rid + k) : 0;
+                }
+#pragma unroll
+                for (int u = 0; u < 4; u++) {
+                    const uint32_t m = __ballot_sync(FULL_MASK, keep[u]);
+                    unsigned long long wbase = 0;
+                    if (lane_id() == 0 && m) wbase = atomicAdd(&s_super.cursor[e], (unsigned long long)__popc(m));
+                    wbase = __shfl_sync(FULL_MASK, wbase, 0);
+                    if (keep[u]) {
+                        const unsigned long long pos = bo + wbase + __popc(m & lt_mask);
+                        out_x[pos] = bxr;
+                        out_y[pos] = yr[u];
+                    }
                 }
             }
         }

@@ -710,6 +710,10 @@ def test_one_chromosome_spanning_row_does_not_serialise_the_operators(engine, c_
     seg = engine.disjoin(ta, tb)
     gd = np.stack([seg.target_rows.cpu().numpy(), seg.start.cpu().numpy(), seg.end.cpu().numpy()], axis=1).astype(np.int64)
     assert np.array_equal(gd[np.lexsort((gd[:, 1], gd[:, 0]))], np.stack([row, s, e], axis=1).astype(np.int64))
+    row, s, e = c_oracle.disjoin(A["code"], A["start"], A["end"], n_codes=n)          # self mode: no coverage filter, same super-row path
+    seg = engine.disjoin(ta)
+    gd = np.stack([seg.target_rows.cpu().numpy(), seg.start.cpu().numpy(), seg.end.cpu().numpy()], axis=1).astype(np.int64)
+    assert np.array_equal(gd[np.lexsort((gd[:, 1], gd[:, 0]))], np.stack([row, s, e], axis=1).astype(np.int64))
     for op, fn in (("contains", engine.contains), ("within", engine.within)):
         expc = c_oracle.spatial_pairs(A["code"], A["start"], A["end"], B["code"], B["start"], B["end"], n, op)
         assert np.array_equal(fn(ta, tb).sorted_packed(), (expc[:, 0] << 32) | expc[:, 1])
