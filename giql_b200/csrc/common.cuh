@@ -305,10 +305,8 @@ static inline int probe_cols(giqlb_ctx* ctx, const giqlb_layout* lay, const int3
 }
 
 // fetch_scalars + the sticky kernel-side error flags in the same round trip
-static inline int fetch_scalars_checked(giqlb_ctx* ctx, const void* d_src, int n_words) {
-    CUDA_TRY(ctx, cudaMemcpyAsync(ctx->h_scalars, d_src, (size_t)n_words * 8, cudaMemcpyDeviceToHost, ctx->stream));
-    CUDA_TRY(ctx, cudaMemcpyAsync(ctx->h_scalars + 60, ctx->d_err, 4 * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
-    CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+// the sticky kernel-side error flags as copied to h_scalars + 60 -> status (and the flags are cleared)
+static inline int decode_err_flags(giqlb_ctx* ctx) {
     const int* e = reinterpret_cast<const int*>(ctx->h_scalars + 60);
     if (e[0] || e[1] || e[3]) {
         cudaMemsetAsync(ctx->d_err, 0, 4 * sizeof(int), ctx->stream);
@@ -320,6 +318,12 @@ static inline int fetch_scalars_checked(giqlb_ctx* ctx, const void* d_src, int n
         return giqlb_fail(ctx, GIQLB_ERR_INTERNAL, "look-back spin limit exceeded (kernel-side)");
     }
     return GIQLB_OK;
+}
+static inline int fetch_scalars_checked(giqlb_ctx* ctx, const void* d_src, int n_words) {
+    CUDA_TRY(ctx, cudaMemcpyAsync(ctx->h_scalars, d_src, (size_t)n_words * 8, cudaMemcpyDeviceToHost, ctx->stream));
+    CUDA_TRY(ctx, cudaMemcpyAsync(ctx->h_scalars + 60, ctx->d_err, 4 * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+    CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    return decode_err_flags(ctx);
 }
 
 // ---- device helpers ------------------------------------------------------------------------------

@@ -20,31 +20,24 @@ constexpr int SH_MAX_BINS = 8192;
 constexpr int SH_THREADS = 256;
 
 // exact linearisation of a row of an OBSERVED table (no clamping); false when the row lies outside the layout
-__device__ __forceinline__ bool row_linearise(const ProbeCols& P, int64_t i, uint32_t& gs, uint32_t& ge) {
-    int32_t c = P.code[i];
+// (32-bit arithmetic as in probe_linearise_values: an offset that would carry the value past INT32_MAX / MIN saturates there,
+//  outside every [lo, hi] the layout admits, so such a row is rejected either way)
+__device__ __forceinline__ bool vals_linearise(const ProbeCols& P, int32_t c, int32_t s0, int32_t e0, uint32_t& gs, uint32_t& ge) {
     if (c < 0 || c >= P.n_codes) return false;
-    long long lo = __ldg(P.lo32 + c), hi = __ldg(P.hi32 + c);
-    long long s = (long long)P.start[i] + P.sadj, e = (long long)P.end[i] + P.eadj;
+    const int32_t lo = __ldg(P.lo32 + c), hi = __ldg(P.hi32 + c);
+    const int32_t s = add_sat_s32(s0, P.sadj), e = add_sat_s32(e0, P.eadj);
     if (s < lo || s > hi || e < lo || e > hi) return false;
-    uint32_t b = __ldg(P.base + c) + 1u;
+    const uint32_t b = __ldg(P.base + c) + 1u;
     gs = b + (uint32_t)(s - lo);
     ge = b + (uint32_t)(e - lo);
     return true;
+}
+__device__ __forceinline__ bool row_linearise(const ProbeCols& P, int64_t i, uint32_t& gs, uint32_t& ge) {
+    return vals_linearise(P, P.code[i], P.start[i], P.end[i], gs, ge);
 }
 
 // `stride` > 1 histograms every stride-th row only (a deterministic sample: every rank takes the same rows); the
 // widest interval then comes from the layout's observe pass instead of this kernel.
-// the same from values already in registers
-__device__ __forceinline__ bool vals_linearise(const ProbeCols& P, int32_t c, int32_t s0, int32_t e0, uint32_t& gs, uint32_t& ge) {
-    if (c < 0 || c >= P.n_codes) return false;
-    long long lo = __ldg(P.lo32 + c), hi = __ldg(P.hi32 + c);
-    long long s = (long long)s0 + P.sadj, e = (long long)e0 + P.eadj;
-    if (s < lo || s > hi || e < lo || e > hi) return false;
-    uint32_t b = __ldg(P.base + c) + 1u;
-    gs = b + (uint32_t)(s - lo);
-    ge = b + (uint32_t)(e - lo);
-    return true;
-}
 
 __global__ void __launch_bounds__(SH_THREADS)
 shard_hist_kernel(ProbeCols P, int64_t stride, uint32_t* __restrict__ hist, uint32_t* __restrict__ max_width, int* __restrict__ err) {
@@ -441,7 +434,7 @@ static int sharded_impl(giqlb_ctx* ctx, giqlb_table_t* L, giqlb_table_t* R, int3
                 // a 1-in-16 sample of the left rows places the cuts (balance error ~ 1/sqrt(n/16) of a shard); the widest
                 // left interval, needed for the right-side replication bound, comes from the observe pass (slot 0 = L)
                 const int64_t stride = L->n >= (1 << 20) ? 16 : 1, n_samp = ceil_div(L->n, stride);
-                int64_t blocks = ceil_div(n_samp, SH_THREADS * 8), hcap = (int64_t)ctx->sm_count * 2;
+                int64_t blocks = ceil_div(n_samp, SH_THREADS * 8), hcap = (int64_t)ctx->sm_count * 6;
                 shard_hist_kernel<<<(unsigned)(blocks < 1 ? 1 : (blocks < hcap ? blocks : hcap)), SH_THREADS, 0, ctx->stream>>>(
                     P[0], stride, hist, hist + n_bins, ctx->d_err);
                 shard_cuts_kernel<<<1, 1024, 0, ctx->stream>>>(hist, n_bins, n_samp, world, cuts64);
@@ -461,7 +454,9 @@ static int sharded_impl(giqlb_ctx* ctx, giqlb_table_t* L, giqlb_table_t* R, int3
             }
             if (cudaGetLastError() != cudaSuccess) st = giqlb_fail(ctx, GIQLB_ERR_CUDA, "intersects_tables_sharded: launch failed");
         }
-        // ONE round trip: both selection sizes (and the sticky error flags)
+        // ONE round trip: both selection sizes (and the sticky error flags).  (Measured at 4 GPUs: bringing the two sizes back
+        // behind separate events, so that the left index build is enqueued while the right table is still being selected,
+        // changed nothing: 1.06 vs 1.03 ms median.)
         if (st == GIQLB_OK) {
             cudaMemcpyAsync(ctx->h_scalars + 40, pre[0].counters, 4 * 8, cudaMemcpyDeviceToHost, ctx->stream);
             cudaMemcpyAsync(ctx->h_scalars + 44, pre[1].counters, 4 * 8, cudaMemcpyDeviceToHost, ctx->stream);
