@@ -781,7 +781,7 @@ int giqlb_index_build_impl(giqlb_ctx* ctx, const giqlb_layout* lay, const int32_
         IB_TRY(dev_alloc(ctx, &ge_u, (size_t)n));
     }
     counters = ix->d_counters;
-    // (measured: counting the digits inside keygen costs more than the separate histogram pass saves; kept switchable)
+    // the key generation pass counts the sort's digit histograms as well (GIQLB_KEYGEN_HIST; not for pre-keyed or end-tied builds)
     key_hist = GIQLB_KEYGEN_HIST && !ix->tie_by_end && !pre ? reinterpret_cast<uint32_t*>(ix->d_counters + 4) : nullptr;
     IB_TRY(dev_alloc(ctx, &kb, (size_t)n));
     IB_TRY(dev_alloc(ctx, &va, (size_t)n));
@@ -827,8 +827,8 @@ int giqlb_index_build_impl(giqlb_ctx* ctx, const giqlb_layout* lay, const int32_
             uint32_t* rk = r2 ? k3 : k2;
             result_in_b = (rk == kb) ? 1 : 0;
         } else {
-            // (measured: letting the last pass gather the linear ends costs 34 us/pass and saves a 28 us gather kernel,
-            //  so the fused variant stays off)
+            // (measured twice: letting the last radix pass gather the linear ends costs 72 us per 10 M-row pass and saves a 56 us gather
+            //  kernel, so GIQLB_SORT_GATHERS_END stays off)
             // tables beyond the L2: the ends travel through the sort as a second payload (1.5 x the bytes of every pass) instead of
             // being gathered afterwards through the sorted row ids, one random DRAM sector each (200 M rows: +2.6 ms against 5.0 ms)
             const bool carry_end = n >= GIQLB_SORT_CARRY_END_MIN && !short_windows;
