@@ -23,6 +23,7 @@ _STATUS_NAMES = {
 
 STRAND_PLUS, STRAND_MINUS, STRAND_DOT, STRAND_QMARK, STRAND_OTHER0, STRAND_NULL = 0, 1, 2, 3, 4, 255
 INDEX_TIE_BY_END = 1
+INDEX_NO_ROW_IDS = 2
 OP_CONTAINS, OP_WITHIN = 1, 2
 KEY_NULL = -2147483648   # GIQLB_KEY_NULL
 

@@ -305,6 +305,7 @@ static int cluster_impl(giqlb_ctx* ctx, giqlb_index* X, int64_t distance, const 
     if (!ctx || !X || (X->n > 0 && !cluster_id_by_input_row)) return giqlb_fail(ctx, GIQLB_ERR_INVALID, "cluster: bad argument");
     begin_call(ctx);
     GIQLB_TRY(check_index(ctx, X, "cluster"));
+    GIQLB_TRY(require_row_ids(ctx, X, "cluster"));
     const int64_t n = X->n;
     if (n == 0) return end_call(ctx);
     GIQLB_TRY(giqlb_index_ensure_pmax(ctx, X));
@@ -467,6 +468,7 @@ extern "C" int giqlb_cluster_shard(giqlb_ctx* ctx, giqlb_index* X, int64_t dista
     if (!ctx || !X) return giqlb_fail(ctx, GIQLB_ERR_INVALID, "cluster_shard: bad argument");
     begin_call(ctx);
     GIQLB_TRY(shard_index_ok(ctx, X, "cluster_shard"));
+    if (cluster_id_by_input_row) GIQLB_TRY(require_row_ids(ctx, X, "cluster_shard"));
     const int32_t nc = X->layout->n_codes;
     if (counts_by_code_host) memset(counts_by_code_host, 0, (size_t)nc * 4);
     const int64_t n = X->n;

@@ -515,6 +515,11 @@ int giqlb_layout_finalize_async(giqlb_ctx* ctx, giqlb_layout* lay);
 int giqlb_intersects_join_impl(giqlb_ctx* ctx, giqlb_index* L, giqlb_index* R, int32_t* out_l, int32_t* out_r, int64_t capacity,
                                int64_t* total_host, bool speculative);
 int giqlb_index_ensure_pmax(giqlb_ctx* ctx, giqlb_index* ix);
+// operators that report input rows cannot take an index built with GIQLB_INDEX_NO_ROW_IDS
+static inline int require_row_ids(giqlb_ctx* ctx, const giqlb_index* ix, const char* who) {
+    if (ix && ix->n > 0 && !ix->rid) return giqlb_fail(ctx, GIQLB_ERR_INVALID, "%s: the index was built with GIQLB_INDEX_NO_ROW_IDS", who);
+    return GIQLB_OK;
+}
 int giqlb_index_resolve(giqlb_ctx* ctx, giqlb_index* a, giqlb_index* b);
 // Internal giqlb_index_build flag (never part of the C-ABI: callers must be able to rebuild the index).  Sort the start keys on
 // bits [8, key_bits) only — one radix pass fewer — and let one finishing pass order every run of equal upper bits ("window" of

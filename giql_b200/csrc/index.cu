@@ -754,6 +754,7 @@ int giqlb_index_build_impl(giqlb_ctx* ctx, const giqlb_layout* lay, const int32_
     int32_t* pre_rows = nullptr;   // selection buffer handed over by a fused select + keygen pass
     bool ge_gathered = false;      // the last sort pass already wrote ix->ge
     bool rows_are_payload = false; // the sort carried the caller's row ids, not positions in the selection
+    bool no_row_ids = false;       // GIQLB_INDEX_NO_ROW_IDS took effect: the index has no rid column
     unsigned long long* counters = nullptr;
     uint32_t* key_hist = nullptr;
     int st = GIQLB_OK;
@@ -836,15 +837,25 @@ int giqlb_index_build_impl(giqlb_ctx* ctx, const giqlb_layout* lay, const int32_
             // with the ends carried nothing needs a row's position in the selection any more, so the sort can carry the caller's
             // row ids themselves instead of positions that are translated afterwards (a random gather: 2.2 ms at 100 M rows)
             rows_are_payload = carry_end && rows != nullptr;
-            if (rows_are_payload) IB_CUDA(cudaMemcpyAsync(va, rows, (size_t)n * 4, cudaMemcpyDeviceToDevice, ctx->stream));
-            IB_TRY(giqlb_radix_sort_pairs_u32(ctx, ka, va, kb, vb, n, short_windows ? 8 : 0, lay->key_bits, rows_are_payload ? 0 : 1, &result_in_b, key_hist,
-                                              fused_gather ? ge_u : nullptr, fused_gather ? ix->ge : nullptr,
-                                              carry_end ? ge_u : nullptr, carry_end ? ix->ge : nullptr));
+            // GIQLB_INDEX_NO_ROW_IDS: the ends are the ONLY payload (no row ids: 16 instead of 24 bytes per row and pass)
+            const bool ends_only = carry_end && (flags & GIQLB_INDEX_NO_ROW_IDS) && !strand;
+            if (ends_only) {
+                dev_free(ctx, va);                 // the value buffers of the sort are the end buffers
+                dev_free(ctx, vb);
+                va = vb = nullptr;
+                IB_TRY(giqlb_radix_sort_pairs_u32(ctx, ka, ge_u, kb, ix->ge, n, 0, lay->key_bits, 0, &result_in_b, key_hist));
+            } else {
+                if (rows_are_payload) IB_CUDA(cudaMemcpyAsync(va, rows, (size_t)n * 4, cudaMemcpyDeviceToDevice, ctx->stream));
+                IB_TRY(giqlb_radix_sort_pairs_u32(ctx, ka, va, kb, vb, n, short_windows ? 8 : 0, lay->key_bits, rows_are_payload ? 0 : 1, &result_in_b, key_hist,
+                                                  fused_gather ? ge_u : nullptr, fused_gather ? ix->ge : nullptr,
+                                                  carry_end ? ge_u : nullptr, carry_end ? ix->ge : nullptr));
+            }
             if (carry_end && !result_in_b) {   // the sorted ends lie beside the sorted keys: in the first buffer after an even number of passes
                 uint32_t* t = ge_u;
                 ge_u = ix->ge;
                 ix->ge = t;
             }
+            no_row_ids = ends_only;
             ge_gathered = fused_gather || short_windows || carry_end;
             if (short_windows) {
                 // (k3, v3) -> the other buffer pair, in final order, with the ends
@@ -865,6 +876,7 @@ int giqlb_index_build_impl(giqlb_ctx* ctx, const giqlb_layout* lay, const int32_
             ix->gs = ka; ix->rid = reinterpret_cast<int32_t*>(va);
             ka = nullptr; va = nullptr;
         }
+        if (no_row_ids) ix->rid = nullptr;   // (va / vb were released before the sort)
         PhaseSpan ps_g(ctx, GIQLB_PH_GATHER);
         if (!ge_gathered) {
             gather_kernel<uint32_t><<<grid_for(ctx, n, 256 * 4, 8), 256, 0, ctx->stream>>>(
@@ -873,7 +885,7 @@ int giqlb_index_build_impl(giqlb_ctx* ctx, const giqlb_layout* lay, const int32_
             ctx->stats.kernels_total++;
             IB_CUDA(cudaGetLastError());
         }
-        if (rows && !rows_are_payload) {   // positions in the selection -> caller's row ids
+        if (rows && !rows_are_payload && !no_row_ids) {   // positions in the selection -> caller's row ids
             remap_rows_kernel<<<grid_for(ctx, n, 256 * 4, 8), 256, 0, ctx->stream>>>(ix->rid, rows, n);
             ctx->launches_this_call++;
             ctx->stats.kernels_total++;
@@ -929,6 +941,7 @@ extern "C" int giqlb_index_group_by_strand(giqlb_ctx* ctx, giqlb_index* ix) {
     using namespace giqlb_scan;
     if (!ctx || !ix) return giqlb_fail(ctx, GIQLB_ERR_INVALID, "group_by_strand: bad argument");
     if (!ix->strand) return giqlb_fail(ctx, GIQLB_ERR_INVALID, "group_by_strand: index was built without a strand column");
+    GIQLB_TRY(require_row_ids(ctx, ix, "group_by_strand"));
     if (ix->grouped_by_strand) return GIQLB_OK;
     begin_call(ctx);
     const int64_t n = ix->n;

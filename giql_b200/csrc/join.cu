@@ -1197,6 +1197,8 @@ extern "C" int giqlb_joinplan_free(giqlb_ctx* ctx, giqlb_joinplan* plan) {
 // Enqueues partition + count + scan.  The pair total lands in ctx->d_scalars[0].
 static int plan_enqueue(giqlb_ctx* ctx, giqlb_index* L, giqlb_index* R, giqlb_joinplan** out) {
     if (L->layout != R->layout) return giqlb_fail(ctx, GIQLB_ERR_INVALID, "intersects: indexes were built on different layouts");
+    GIQLB_TRY(require_row_ids(ctx, L, "intersects"));
+    GIQLB_TRY(require_row_ids(ctx, R, "intersects"));
     if (L->grouped_by_strand || R->grouped_by_strand)
         return giqlb_fail(ctx, GIQLB_ERR_INVALID, "intersects: strand-grouped indexes are not accepted");
     GIQLB_TRY(giqlb_index_resolve(ctx, L, R));
@@ -1390,6 +1392,8 @@ int giqlb_intersects_join_impl(giqlb_ctx* ctx, giqlb_index* L, giqlb_index* R, i
         return giqlb_fail(ctx, GIQLB_ERR_INVALID, "intersects_join: bad argument");
     begin_call(ctx);
     if (L->layout != R->layout) return giqlb_fail(ctx, GIQLB_ERR_INVALID, "intersects: indexes were built on different layouts");
+    GIQLB_TRY(require_row_ids(ctx, L, "intersects"));
+    GIQLB_TRY(require_row_ids(ctx, R, "intersects"));
     if (L->grouped_by_strand || R->grouped_by_strand)
         return giqlb_fail(ctx, GIQLB_ERR_INVALID, "intersects: strand-grouped indexes are not accepted");
     const bool empty = L->n == 0 || R->n == 0;

@@ -240,6 +240,7 @@ extern "C" int giqlb_nearest(giqlb_ctx* ctx, const giqlb_layout* lay, const int3
     if (!ctx || !T || !n_out_host || k < 1 || n_q < 0) return giqlb_fail(ctx, GIQLB_ERR_INVALID, "nearest: bad argument");
     if (T->layout != lay) return giqlb_fail(ctx, GIQLB_ERR_INVALID, "nearest: target index was built on a different layout");
     if (!T->tie_by_end) return giqlb_fail(ctx, GIQLB_ERR_INVALID, "nearest: target index must be built with GIQLB_INDEX_TIE_BY_END");
+    GIQLB_TRY(require_row_ids(ctx, T, "nearest"));
     if (stranded && (!q_strand || !T->strand || !T->grouped_by_strand))
         return giqlb_fail(ctx, GIQLB_ERR_INVALID, "nearest: stranded needs a query strand column and a strand-grouped target index");
     if (!stranded && T->grouped_by_strand) return giqlb_fail(ctx, GIQLB_ERR_INVALID, "nearest: unstranded search over a strand-grouped index");

@@ -244,6 +244,8 @@ extern "C" int giqlb_spatial_join(giqlb_ctx* ctx, giqlb_index* L, giqlb_index* R
     if (!ctx || !L || !R || !total_host || capacity < 0 || (op != GIQLB_OP_CONTAINS && op != GIQLB_OP_WITHIN))
         return giqlb_fail(ctx, GIQLB_ERR_INVALID, "spatial_join: bad argument");
     if (L->layout != R->layout) return giqlb_fail(ctx, GIQLB_ERR_INVALID, "spatial_join: indexes were built on different layouts");
+    GIQLB_TRY(require_row_ids(ctx, L, "spatial_join"));
+    GIQLB_TRY(require_row_ids(ctx, R, "spatial_join"));
     if (L->grouped_by_strand || R->grouped_by_strand) return giqlb_fail(ctx, GIQLB_ERR_INVALID, "spatial_join: strand-grouped indexes are not accepted");
     begin_call(ctx);
     GIQLB_TRY(giqlb_index_resolve(ctx, L, R));

@@ -269,7 +269,8 @@ class _Layout:
 
 class _Index:
     def __init__(self, engine: "Engine", layout: _Layout, t: DeviceTable, raw: bool = False, with_strand: bool = False,
-                 tie_by_end: bool = False, rows: Optional[torch.Tensor] = None, start_range: Optional[tuple] = None):
+                 tie_by_end: bool = False, rows: Optional[torch.Tensor] = None, start_range: Optional[tuple] = None,
+                 row_ids: bool = True):
         self.e = engine
         self.layout = layout   # keep the layout alive as long as the index
         self.rows = rows       # ... and the row selection until the stream has consumed it
@@ -279,12 +280,13 @@ class _Index:
             if with_strand or tie_by_end or rows is not None:
                 raise ValueError("a start-range index takes no strand grouping, end ties or row selection")
             engine._check(engine.lib.giqlb_index_build_range(engine.ctx, layout.h, _ptr(t.codes), _ptr(t.start), _ptr(t.end), t.n, sadj, eadj,
-                                                            int(start_range[0]), int(start_range[1]), 0, ctypes.byref(self.h)))
+                                                            int(start_range[0]), int(start_range[1]), 0 if row_ids else _cabi.INDEX_NO_ROW_IDS,
+                                                            ctypes.byref(self.h)))
             return
         strand = t.strand if with_strand else None
         if with_strand and strand is None:
             raise ValueError("stranded := true requires a strand column on the table")
-        flags = _cabi.INDEX_TIE_BY_END if tie_by_end else 0
+        flags = (_cabi.INDEX_TIE_BY_END if tie_by_end else 0) | (0 if row_ids else _cabi.INDEX_NO_ROW_IDS)
         n = t.n if rows is None else int(rows.numel())
         engine._check(engine.lib.giqlb_index_build_rows(engine.ctx, layout.h, _ptr(t.codes), _ptr(t.start), _ptr(t.end),
                                                        _ptr(strand), _ptr(rows), n, sadj, eadj, flags, ctypes.byref(self.h)))
@@ -965,12 +967,12 @@ class Engine:
         return NearestResult(out_q[:m], out_t[:m], out_d[:m], out_v[:m])
 
     # ---- CLUSTER / MERGE ---------------------------------------------------------------------------
-    def _self_index(self, t: DeviceTable, stranded: bool, raw: bool, tie_by_end: bool = False):
+    def _self_index(self, t: DeviceTable, stranded: bool, raw: bool, tie_by_end: bool = False, row_ids: bool = True):
         d = self.encode(t)
         lay = _Layout(self, len(d))
         lay.observe(t, raw=raw)
         lay.finalize()
-        ix = _Index(self, lay, t, raw=raw, with_strand=stranded, tie_by_end=tie_by_end)
+        ix = _Index(self, lay, t, raw=raw, with_strand=stranded, tie_by_end=tie_by_end, row_ids=row_ids)
         if stranded:
             self._check(self.lib.giqlb_index_group_by_strand(self.ctx, ix.h))
         return lay, ix
@@ -1066,7 +1068,7 @@ class Engine:
         count = self._empty(n, torch.int64)
         m = ctypes.c_int64(0)
         if n:
-            lay, ix = self._self_index(t, stranded, raw=True)
+            lay, ix = self._self_index(t, stranded, raw=True, row_ids=False)   # regions, not rows: no row-id payload in the sort
             try:
                 self._check(self.lib.giqlb_merge(self.ctx, ix.h, int(distance or 0), _ptr(code), _ptr(start), _ptr(end),
                                                  _ptr(strand), _ptr(count), n, ctypes.byref(m)))

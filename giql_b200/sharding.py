@@ -308,6 +308,8 @@ def sharded_merge(ops, rank: int, world: int, table, distance: int = 0, group=No
     """The merged regions that START in this rank's genome range, with the rows of later shards that continue the
     last one folded in.  Returns a dict of equally long tensors: code, start, end, count."""
     plan = ops.cm_plan(table, world)
+    if isinstance(plan, dict):
+        plan["row_ids"] = False        # MERGE never maps a sorted position back to an input row
     try:
         max_ends = [v[0] for v in _all_gather_ints([ops.cm_max_end(plan, rank)], world, ops.device, group)]
         carry = carry_before(max_ends, rank)
@@ -343,8 +345,10 @@ def _engine_cm_index(self, plan, g):
 
     if g not in plan["index"]:
         t, lay = plan["table"], plan["layout"]
-        # one library call: fused select + keygen of the shard's rows, sort (giqlb_index_build_range)
-        plan["index"][g] = _Index(self.e, lay, t, raw=True, start_range=(plan["cuts"][g], plan["cuts"][g + 1]))
+        # one library call: fused select + keygen of the shard's rows, sort (giqlb_index_build_range); a plan made for MERGE
+        # (plan["row_ids"] = False) asks for no row ids: regions, not rows, come out of it
+        plan["index"][g] = _Index(self.e, lay, t, raw=True, start_range=(plan["cuts"][g], plan["cuts"][g + 1]),
+                                  row_ids=plan.get("row_ids", True))
     return plan["index"][g]
 
 

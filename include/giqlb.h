@@ -159,6 +159,11 @@ int giqlb_layout_tables(const giqlb_layout* lay, const uint32_t** base_dev, cons
  * strand may be NULL.  start_adj/end_adj are the canonical.py:16-52 offsets (raw + adj = canonical).
  * flags: GIQLB_INDEX_TIE_BY_END orders equal starts by end (NEAREST's ORDER BY start, end). */
 #define GIQLB_INDEX_TIE_BY_END 1
+/* GIQLB_INDEX_NO_ROW_IDS: the caller will not ask which input row a sorted position came from (MERGE returns regions, not rows:
+ * src/giql/expanders/merge.py:183-439).  Tables too large for the L2 are then sorted with the linear end as the only payload
+ * (16 instead of 24 bytes per row and pass); giqlb_index_columns reports a NULL row-id column.  A hint: smaller tables and
+ * strand-carrying indexes keep their row ids. */
+#define GIQLB_INDEX_NO_ROW_IDS 2
 int giqlb_index_build(giqlb_ctx* ctx, const giqlb_layout* lay, const int32_t* code, const int32_t* start,
                       const int32_t* end, const uint8_t* strand, int64_t n, int32_t start_adj,
                       int32_t end_adj, int flags, giqlb_index** out);
