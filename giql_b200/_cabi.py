@@ -104,6 +104,7 @@ PROTOTYPES = {
     "giqlb_nearest": (c_int, [_P, _P, _P, _P, _P, _P, c_int64, c_int32, c_int32, _P, c_int, c_int64, c_int, c_int,
                               _P, _P, _P, _P, c_int64, POINTER(c_int64)]),
     "giqlb_cluster": (c_int, [_P, _P, c_int64, _P]),
+    "giqlb_cluster_table": (c_int, [_P, _P, c_int64, _P, _P, c_int64, c_int32, _P]),
     "giqlb_cluster_predicate": (c_int, [_P, _P, c_int64, _P, _P, c_int, _P]),
     "giqlb_merge": (c_int, [_P, _P, c_int64, _P, _P, _P, _P, _P, c_int64, POINTER(c_int64)]),
     "giqlb_disjoin": (c_int, [_P, _P, _P, _P, _P, c_int64, c_int32, c_int32, _P, c_int, _P, _P, _P, c_int64, POINTER(c_int64)]),

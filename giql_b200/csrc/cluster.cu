@@ -262,6 +262,53 @@ int scatter_by_row(giqlb_ctx* ctx, const int32_t* rid, uint32_t* val, int64_t n,
     return st;
 }
 
+// CLUSTER ids by search instead of by scatter.  When the clusters are few (deep-coverage reads: 200 M rows fall into ~2 000
+// clusters) an input row finds its id by itself: the number of cluster starts at or below its own linear start, minus the
+// starts before its chromosome.  The rows are read and the ids written in INPUT order — coalesced — and nothing has to travel
+// back through the sorted row ids (three radix passes + a scatter: 4.6 ms at 200 M rows against 1 ms here).
+#ifndef GIQLB_CLUSTER_SEARCH_MAX
+#define GIQLB_CLUSTER_SEARCH_MAX (4ll << 20)   // cluster starts: 16 MB of keys, resident in L2
+#endif
+__global__ void __launch_bounds__(256)
+cluster_starts_kernel(const uint32_t* __restrict__ gs, const uint32_t* __restrict__ G, int64_t n, uint32_t* __restrict__ starts) {
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        const uint32_t g = G[i];
+        if (i == 0 ? g != 0u : g != G[i - 1]) starts[g - 1] = gs[i];
+    }
+}
+// before[c] = cluster starts below chromosome c's cell range
+__global__ void cluster_before_kernel(const uint32_t* __restrict__ base, int32_t n_codes, const uint32_t* __restrict__ starts, int64_t n_starts,
+                                      uint32_t* __restrict__ before) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c < n_codes) before[c] = (uint32_t)lower_bound_dev<uint32_t, int64_t>(starts, 0, n_starts, __ldg(base + c));
+}
+// first index in [0, n) with a[idx] > x, 32-bit (n <= GIQLB_CLUSTER_SEARCH_MAX): branch-free halving
+__device__ __forceinline__ uint32_t upper_bound_u32(const uint32_t* __restrict__ a, uint32_t n, uint32_t x) {
+    uint32_t lo = 0;
+    while (n > 0) {
+        const uint32_t half = n >> 1;
+        const bool right = __ldg(a + lo + half) <= x;
+        lo = right ? lo + half + 1 : lo;
+        n = right ? n - half - 1 : half;
+    }
+    return lo;
+}
+__global__ void __launch_bounds__(256)
+cluster_ids_search_kernel(const int32_t* __restrict__ code, const int32_t* __restrict__ start, int64_t n, int32_t start_adj,
+                          const uint32_t* __restrict__ base, const int32_t* __restrict__ lo32, int32_t n_codes,
+                          const uint32_t* __restrict__ starts, uint32_t n_starts, const uint32_t* __restrict__ before,
+                          int32_t* __restrict__ out) {
+    for (int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; r < n; r += (int64_t)gridDim.x * blockDim.x) {
+        const int32_t c = code[r];
+        if (c < 0 || c >= n_codes) {     // cannot happen for an observed table; keep the kernel memory-safe
+            out[r] = 0;
+            continue;
+        }
+        const uint32_t key = __ldg(base + c) + 1u + (uint32_t)(add_sat_s32(start[r], start_adj) - __ldg(lo32 + c));
+        out[r] = (int32_t)(upper_bound_u32(starts, n_starts, key) - __ldg(before + c));
+    }
+}
+
 inline LayoutView view_of(const giqlb_layout* lay) { return LayoutView{lay->d_base, lay->d_lo32, lay->n_codes}; }
 
 // flags -> running count G for rows [lo, hi) of the index; returns the block's cluster count in *total_dev
@@ -286,8 +333,9 @@ int check_index(giqlb_ctx* ctx, giqlb_index* X, const char* who) {
 
 }  // namespace
 
+// G_ready (nullable): the running cluster count of an ungrouped index, already computed by the caller (ownership passes on)
 static int cluster_impl(giqlb_ctx* ctx, giqlb_index* X, int64_t distance, const int32_t* cur_key_by_row, const int32_t* prev_key_by_row, int op,
-                        int32_t* cluster_id_by_input_row);
+                        int32_t* cluster_id_by_input_row, uint32_t* G_ready = nullptr);
 
 extern "C" int giqlb_cluster(giqlb_ctx* ctx, giqlb_index* X, int64_t distance, int32_t* cluster_id_by_input_row) {
     return cluster_impl(ctx, X, distance, nullptr, nullptr, 0, cluster_id_by_input_row);
@@ -300,19 +348,83 @@ extern "C" int giqlb_cluster_predicate(giqlb_ctx* ctx, giqlb_index* X, int64_t d
     return cluster_impl(ctx, X, distance, cur_key_by_row, prev_key_by_row, op, cluster_id_by_input_row);
 }
 
-static int cluster_impl(giqlb_ctx* ctx, giqlb_index* X, int64_t distance, const int32_t* cur_key_by_row, const int32_t* prev_key_by_row, int op,
-                        int32_t* cluster_id_by_input_row) {
-    if (!ctx || !X || (X->n > 0 && !cluster_id_by_input_row)) return giqlb_fail(ctx, GIQLB_ERR_INVALID, "cluster: bad argument");
+extern "C" int giqlb_cluster_table(giqlb_ctx* ctx, giqlb_index* X, int64_t distance, const int32_t* code, const int32_t* start, int64_t n,
+                                   int32_t start_adj, int32_t* cluster_id_by_input_row) {
+    if (!ctx || !X || n != X->n || (n > 0 && (!code || !start || !cluster_id_by_input_row)))
+        return giqlb_fail(ctx, GIQLB_ERR_INVALID, "cluster_table: bad argument (the index must cover all n rows of the table)");
+    // small tables: the direct scatter of the ids is cheap, and the search path would add a round trip
+    if (X->grouped_by_strand || !binned_scatter_wanted(n)) return giqlb_cluster(ctx, X, distance, cluster_id_by_input_row);
     begin_call(ctx);
     GIQLB_TRY(check_index(ctx, X, "cluster"));
-    GIQLB_TRY(require_row_ids(ctx, X, "cluster"));
-    const int64_t n = X->n;
     if (n == 0) return end_call(ctx);
     GIQLB_TRY(giqlb_index_ensure_pmax(ctx, X));
-    const long long d = distance > 0 ? (long long)distance : 0;   // cluster.py:266-272: the term is added only when > 0
-    uint32_t *G = nullptr, *off = nullptr;
-    int32_t *kc = nullptr, *kp = nullptr;
+    const long long d = distance > 0 ? (long long)distance : 0;
+    uint32_t *G = nullptr, *starts = nullptr, *before = nullptr;
     GIQLB_TRY(dev_alloc(ctx, &G, (size_t)n));
+    const LayoutView V = view_of(X->layout);
+    int st;
+    int64_t n_starts = 0;
+    {
+        PhaseSpan ps(ctx, GIQLB_PH_CLUSTER);
+        st = running_count(ctx, X, 0, n, d, G);
+    }
+    if (st == GIQLB_OK) {   // how many clusters?  (the round trip also checks the scan's sticky flags)
+        cudaMemcpyAsync(ctx->h_scalars + 48, G + (n - 1), 4, cudaMemcpyDeviceToHost, ctx->stream);
+        st = fetch_scalars_checked(ctx, ctx->d_scalars, 1);
+        n_starts = (int64_t)(*reinterpret_cast<const uint32_t*>(ctx->h_scalars + 48));
+    }
+    if (st == GIQLB_OK && n_starts <= GIQLB_CLUSTER_SEARCH_MAX) {
+        st = dev_alloc(ctx, &starts, (size_t)(n_starts > 0 ? n_starts : 1));
+        if (st == GIQLB_OK) st = dev_alloc(ctx, &before, (size_t)V.n_codes + 1);
+        if (st == GIQLB_OK) {
+            PhaseSpan ps(ctx, GIQLB_PH_CLUSTER);
+            cluster_starts_kernel<<<grid_of(ctx, n, 4), 256, 0, ctx->stream>>>(X->gs, G, n, starts);
+            cluster_before_kernel<<<(V.n_codes + 127) / 128, 128, 0, ctx->stream>>>(V.base, V.n_codes, starts, n_starts, before);
+            cluster_ids_search_kernel<<<grid_of(ctx, n, 4), 256, 0, ctx->stream>>>(code, start, n, start_adj, V.base, V.lo32, V.n_codes, starts,
+                                                                                 (uint32_t)n_starts, before, cluster_id_by_input_row);
+            ctx->launches_this_call += 3;
+            ctx->stats.kernels_total += 3;
+            if (cudaGetLastError() != cudaSuccess) st = giqlb_fail(ctx, GIQLB_ERR_CUDA, "cluster_table: launch failed");
+        }
+        dev_free(ctx, G);
+        dev_free(ctx, starts);
+        dev_free(ctx, before);
+        if (st != GIQLB_OK) return st;
+        ctx->stats.rows_in[0] = n;
+        ctx->stats.rows_in[1] = 0;
+        ctx->stats.rows_out = n;
+        ctx->stats.algorithmic_bytes = 12 * n + 4 * n;
+        return end_call(ctx);
+    }
+    if (st != GIQLB_OK) {
+        dev_free(ctx, G);
+        return st;
+    }
+    // many clusters: the ids travel back through the sorted row ids (the running count is handed over, not recomputed)
+    return cluster_impl(ctx, X, distance, nullptr, nullptr, 0, cluster_id_by_input_row, G);
+}
+
+static int cluster_impl(giqlb_ctx* ctx, giqlb_index* X, int64_t distance, const int32_t* cur_key_by_row, const int32_t* prev_key_by_row, int op,
+                        int32_t* cluster_id_by_input_row, uint32_t* G_ready) {
+    if (!ctx || !X || (X->n > 0 && !cluster_id_by_input_row)) {
+        dev_free(ctx, G_ready);
+        return giqlb_fail(ctx, GIQLB_ERR_INVALID, "cluster: bad argument");
+    }
+    begin_call(ctx);
+    const int64_t n = X->n;
+    {
+        int pre = check_index(ctx, X, "cluster");
+        if (pre == GIQLB_OK) pre = require_row_ids(ctx, X, "cluster");
+        if (pre == GIQLB_OK && n > 0) pre = giqlb_index_ensure_pmax(ctx, X);
+        if (pre != GIQLB_OK || n == 0) {
+            dev_free(ctx, G_ready);
+            return pre != GIQLB_OK ? pre : end_call(ctx);
+        }
+    }
+    const long long d = distance > 0 ? (long long)distance : 0;   // cluster.py:266-272: the term is added only when > 0
+    uint32_t *G = G_ready, *off = nullptr;
+    int32_t *kc = nullptr, *kp = nullptr;
+    if (!G) GIQLB_TRY(dev_alloc(ctx, &G, (size_t)n));
     int st = dev_alloc(ctx, &off, (size_t)X->layout->n_codes);
     if (st == GIQLB_OK && cur_key_by_row) st = dev_alloc(ctx, &kc, (size_t)n);
     if (st == GIQLB_OK && cur_key_by_row) st = dev_alloc(ctx, &kp, (size_t)n);
@@ -329,7 +441,7 @@ static int cluster_impl(giqlb_ctx* ctx, giqlb_index* X, int64_t distance, const 
         for (int b = 0; b < nb && st == GIQLB_OK; b++) {
             const int64_t lo = X->grouped_by_strand ? X->block_off[b] : 0, hi = X->grouped_by_strand ? X->block_off[b + 1] : n;
             if (hi <= lo) continue;
-            st = running_count(ctx, X, lo, hi, d, G, 0, ClusterPredicate{kc, kp, op});
+            if (!G_ready) st = running_count(ctx, X, lo, hi, d, G, 0, ClusterPredicate{kc, kp, op});
             if (st != GIQLB_OK) break;
             cluster_chrom_offsets_kernel<<<(V.n_codes + 127) / 128, 128, 0, ctx->stream>>>(X->gs + lo, G + lo, hi - lo, V, off);
             ctx->launches_this_call++;

@@ -1049,7 +1049,10 @@ class Engine:
                 keys = (self._dev(kc), self._dev(kp), self._CMP_OPS[op])
         lay, ix = self._self_index(t, stranded, raw=True)
         try:
-            if keys is None:
+            if keys is None and not stranded:
+                # plain index over the whole table: few clusters are resolved per input row by search (giqlb_cluster_table)
+                self._check(self.lib.giqlb_cluster_table(self.ctx, ix.h, int(distance or 0), _ptr(t.codes), _ptr(t.start), t.n, 0, _ptr(out)))
+            elif keys is None:
                 self._check(self.lib.giqlb_cluster(self.ctx, ix.h, int(distance or 0), _ptr(out)))
             else:
                 self._check(self.lib.giqlb_cluster_predicate(self.ctx, ix.h, int(distance or 0), _ptr(keys[0]), _ptr(keys[1]), keys[2], _ptr(out)))

@@ -302,6 +302,12 @@ int giqlb_nearest(giqlb_ctx* ctx, const giqlb_layout* lay, const int32_t* q_code
  *            out_strand (nullable) receives the strand code of each region, out_count (nullable) COUNT(*).
  * Rows with end < start are rejected (their grouping depends on the tie order of the executing engine). */
 int giqlb_cluster(giqlb_ctx* ctx, giqlb_index* X, int64_t distance, int32_t* cluster_id_by_input_row);
+/* The same for an index that covers ALL n rows of a table, given that table's raw chromosome-code and start columns (the
+ * offsets the index was built with): when the clusters are few, every input row finds its id by searching its own start among
+ * the cluster starts, in input order, instead of the ids travelling back through the sorted row ids.  Identical results;
+ * strand-grouped indexes and many-cluster tables take giqlb_cluster's path. */
+int giqlb_cluster_table(giqlb_ctx* ctx, giqlb_index* X, int64_t distance, const int32_t* code, const int32_t* start, int64_t n,
+                        int32_t start_adj, int32_t* cluster_id_by_input_row);
 /* CLUSTER(interval[, distance], predicate := <cur column> <op> PREV(<prev column>))  (cluster.py:281-299, 587-644): a row
  * stays in the running cluster only when it is adjacent to the running-max edge AND the comparison holds against its
  * immediate sorted predecessor (rows tied on start keep their input order).  The two operand columns are given as

@@ -53,6 +53,19 @@ def test_one_call_join_with_a_table_beyond_the_l2(engine, c_oracle):
         exp = (out_l[:total].astype(np.int64) << 32) | out_r[:total].astype(np.int64)
         exp.sort()
         assert np.array_equal(got, exp)
+    # CLUSTER over the 26 M peaks: ~3 x 10^5 clusters, found per input row by search (giqlb_cluster_table); the same rows cut down
+    # to 2 bp: tens of millions of clusters, whose ids return through the sorted scatter.  MERGE sorts without row ids at this size
+    ids = engine.cluster(ta).cpu().numpy()
+    want = c_oracle.cluster(A["code"], A["start"], A["end"], len(A["names"]))
+    assert np.array_equal(ids, want)
+    short_end = (A["start"] + 2).astype(np.int32)
+    tc = engine.table_from_codes(A["code"], A["start"], short_end, ta.dictionary)
+    want = c_oracle.cluster(A["code"], A["start"], short_end, len(A["names"]))
+    assert int(want.astype(np.int64).sum()) > 0 and len(np.unique(want)) > 200_000   # ids restart per chromosome: many clusters each
+    assert np.array_equal(engine.cluster(tc).cpu().numpy(), want)
+    m = engine.merge(ta)
+    wp, ws, we, wc = c_oracle.merge(A["code"], A["start"], A["end"], len(A["names"]))
+    assert len(m) == len(wp) and np.array_equal(m.start.cpu().numpy(), ws) and np.array_equal(m.count.cpu().numpy(), wc)
 
 
 def test_c3_semi_anti_50m_by_1m(engine, c_oracle):
