@@ -47,10 +47,11 @@ scan_lookback_kernel(int64_t n, In in, Out out, unsigned long long* __restrict__
     const uint32_t w = warp_id(), l = lane_id();
 
     T v[SC_IPT];
+    In in_regs = in;   // a functor with per-thread state (a `mutable` memo) must not live in the kernel's parameter space
 #pragma unroll
     for (int j = 0; j < SC_IPT; j++) {
         int64_t i = base + j * SC_THREADS + tid;
-        v[j] = i < n ? in(i) : Op::identity();
+        v[j] = i < n ? in_regs(i) : Op::identity();
         s_val[sc_pad(j * SC_THREADS + tid)] = v[j];
     }
     __syncthreads();
