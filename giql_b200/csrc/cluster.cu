@@ -589,12 +589,21 @@ extern "C" int giqlb_cluster_shard(giqlb_ctx* ctx, giqlb_index* X, int64_t dista
     const long long d = distance > 0 ? (long long)distance : 0;
     const LayoutView V = view_of(X->layout);
     uint32_t *G = nullptr, *off = nullptr, *aux = nullptr;
-    int st = dev_alloc(ctx, &G, (size_t)n);
+    // the running count of the previous call on this index (same distance, same carry) is reused: counts first, ids second
+    const bool reuse = X->shard_G && X->shard_G_distance == d && X->shard_G_carry == carry;
+    int st = GIQLB_OK;
+    if (reuse) {
+        G = X->shard_G;
+    } else {
+        dev_free(ctx, X->shard_G);
+        X->shard_G = nullptr;
+        st = dev_alloc(ctx, &G, (size_t)n);
+    }
     if (st == GIQLB_OK) st = dev_alloc(ctx, &off, (size_t)nc);
     if (st == GIQLB_OK) st = dev_alloc(ctx, &aux, (size_t)nc);
     if (st == GIQLB_OK) {
         PhaseSpan ps(ctx, GIQLB_PH_CLUSTER);
-        st = running_count(ctx, X, 0, n, d, G, carry);
+        if (!reuse) st = running_count(ctx, X, 0, n, d, G, carry);
         if (st == GIQLB_OK && counts_by_code_host) {
             cluster_chrom_counts_kernel<<<(nc + 127) / 128, 128, 0, ctx->stream>>>(X->gs, G, n, V, aux);
             ctx->launches_this_call++;
@@ -628,7 +637,14 @@ extern "C" int giqlb_cluster_shard(giqlb_ctx* ctx, giqlb_index* X, int64_t dista
             }
         }
     }
-    dev_free(ctx, G);
+    if (st == GIQLB_OK && !cluster_id_by_input_row) {   // a counts-only call: the ids call usually follows
+        X->shard_G = G;
+        X->shard_G_distance = d;
+        X->shard_G_carry = carry;
+    } else {
+        dev_free(ctx, G);
+        X->shard_G = nullptr;
+    }
     dev_free(ctx, off);
     dev_free(ctx, aux);
     return st == GIQLB_OK ? end_call(ctx) : st;

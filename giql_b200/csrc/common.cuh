@@ -139,6 +139,11 @@ struct giqlb_index {
     uint32_t* bmax1 = nullptr;
     uint32_t* bmax2 = nullptr;
     uint32_t* dir_gs = nullptr;
+    // giqlb_cluster_shard is called twice per shard (cluster counts, then — after the ranks exchanged them — the ids): the running
+    // cluster count of the first call is kept for the second (valid for the same distance and carry)
+    uint32_t* shard_G = nullptr;
+    long long shard_G_distance = -1;
+    uint32_t shard_G_carry = 0;
     uint4* dir_exists = nullptr;     // lazily built (giqlb_index_ensure_exists_dir): per bucket of dir_gs one 32-byte sector with the first two
                                      // rows' starts and running maxima — it answers most SEMI / ANTI probes alone (plain indexes only)
     uint32_t* dir_pmax = nullptr;

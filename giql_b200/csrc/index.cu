@@ -681,6 +681,7 @@ extern "C" int giqlb_index_free(giqlb_ctx* ctx, giqlb_index* ix) {
         dev_free(ctx, ix->bmax2);
         dev_free(ctx, ix->dir_gs);
         dev_free(ctx, ix->dir_exists);
+        dev_free(ctx, ix->shard_G);
         dev_free(ctx, ix->dir_pmax);
         dev_free(ctx, ix->dir_ges);
         dev_free(ctx, ix->d_dir_slot);
@@ -981,6 +982,8 @@ extern "C" int giqlb_index_group_by_strand(giqlb_ctx* ctx, giqlb_index* ix) {
         ix->dir_gs = ix->dir_pmax = ix->dir_ges = nullptr; ix->d_dir_slot = nullptr;
         dev_free(ctx, ix->dir_exists);
         ix->dir_exists = nullptr;
+        dev_free(ctx, ix->shard_G);
+        ix->shard_G = nullptr;
         dev_free(ctx, ix->bmax1); dev_free(ctx, ix->bmax2);
         ix->bmax1 = ix->bmax2 = nullptr;
     }
