@@ -46,7 +46,10 @@ namespace {
 #define GIQLB_JOIN_THREADS 256
 #endif
 constexpr int JB = GIQLB_JOIN_THREADS;   // threads per CTA
-constexpr int JT = JB * 4;               // merged rows per tile (fast path) / left rows per tile (general path)
+#ifndef GIQLB_JOIN_IPT
+#define GIQLB_JOIN_IPT 4
+#endif
+constexpr int JT = JB * GIQLB_JOIN_IPT;   // merged rows per tile (fast path) / left rows per tile (general path)
 constexpr int J_IPT = JT / JB;
 #ifndef GIQLB_JOIN_EXT
 #define GIQLB_JOIN_EXT 512
@@ -260,8 +263,11 @@ join_count_tiles_kernel(JoinSide L, JoinSide R, const int32_t* __restrict__ part
             cnt += (unsigned long long)c;
         }
     }
-    static_assert(J_IPT == 4, "item codes are stored as one uint4 per thread");
-    reinterpret_cast<uint4*>(item_code + (size_t)blockIdx.x * JT)[threadIdx.x] = make_uint4(code[0], code[1], code[2], code[3]);
+    static_assert(J_IPT % 4 == 0, "item codes are stored as uint4s, J_IPT / 4 per thread");
+#pragma unroll
+    for (int q = 0; q < J_IPT / 4; q++)
+        reinterpret_cast<uint4*>(item_code + (size_t)blockIdx.x * JT)[threadIdx.x * (J_IPT / 4) + q] =
+            make_uint4(code[4 * q], code[4 * q + 1], code[4 * q + 2], code[4 * q + 3]);
     cnt = warp_reduce_add(cnt);
     if (lane_id() == 0) s_red[warp_id()] = cnt;
     __syncthreads();
@@ -341,8 +347,12 @@ join_emit_kernel(JoinSide L, JoinSide R, const int32_t* __restrict__ part, int64
         for (int i = threadIdx.x; i < g.wl; i += JB) s_lrid[i] = __ldg(L.rid + g.x0 + i);
         for (int i = threadIdx.x; i < g.wr; i += JB) s_rrid[i] = __ldg(R.rid + g.y0 + i);
         // the thread's four items: run lengths from the count pass (exact end re-derived when saturated)
-        const uint4 cv = reinterpret_cast<const uint4*>(item_code + (size_t)t * JT)[threadIdx.x];
-        const uint32_t code[J_IPT] = {cv.x, cv.y, cv.z, cv.w};
+        uint32_t code[J_IPT];
+#pragma unroll
+        for (int q = 0; q < J_IPT / 4; q++) {
+            const uint4 cv = reinterpret_cast<const uint4*>(item_code + (size_t)t * JT)[threadIdx.x * (J_IPT / 4) + q];
+            code[4 * q] = cv.x; code[4 * q + 1] = cv.y; code[4 * q + 2] = cv.z; code[4 * q + 3] = cv.w;
+        }
         unsigned long long c[J_IPT], sum = 0;
 #pragma unroll
         for (int k = 0; k < J_IPT; k++) {
