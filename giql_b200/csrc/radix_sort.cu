@@ -9,14 +9,23 @@
 // stages the tile in shared memory in digit order and writes it out in coalesced runs.
 // HBM traffic: 4 B/key (histogram) + 16 B/key/pass (keys+payload in and out).
 #include "common.cuh"
+#include <type_traits>
 
 namespace {
 
-constexpr int RS_THREADS = 256;
-constexpr int RS_WARPS = RS_THREADS / 32;
-#ifndef GIQLB_RS_IPT
-#define GIQLB_RS_IPT 16
+// threads per CTA of the digit passes (the first 256 of them also own one digit each); the tile stays 4096 keys
+// (measured: 512 threads x 8 keys at three CTAs per SM — 48 resident warps — 77 us per pass against 69 us at 256 x 16)
+#ifndef GIQLB_RS_THREADS
+#define GIQLB_RS_THREADS 256
 #endif
+constexpr int RS_THREADS = GIQLB_RS_THREADS;
+constexpr int RS_WARPS = RS_THREADS / 32;
+constexpr int RS_HIST_THREADS = 256;
+#ifndef GIQLB_RS_IPT
+#define GIQLB_RS_IPT (4096 / GIQLB_RS_THREADS)
+#endif
+// per-warp digit counters: a warp holds at most 32 * IPT keys, so 16 bits do when there are many warps
+typedef std::conditional<(RS_WARPS > 8), uint16_t, uint32_t>::type rs_hist_t;
 constexpr int RS_IPT = GIQLB_RS_IPT;
 #ifndef GIQLB_RS_LOOKBACK
 #define GIQLB_RS_LOOKBACK 4      // predecessor tiles fetched per look-back step
@@ -77,20 +86,20 @@ __device__ __forceinline__ bool lookback_step(const uint32_t (&sv)[W], int64_t& 
 }
 
 // ---- histogram of all digits in one read ---------------------------------------------------------
-__global__ void __launch_bounds__(RS_THREADS)
+__global__ void __launch_bounds__(RS_HIST_THREADS)
 rs_histogram_kernel(const uint32_t* __restrict__ keys, int64_t n, int begin_bit, int n_passes,
                     uint32_t* __restrict__ ghist /* [n_passes][256] */) {
     // RS_HIST_COPIES private copies, chosen by lane: the shared-memory atomics are the bottleneck of this kernel and
     // lanes of one warp that hit the same bin serialise (the high digits of genome coordinates are far from uniform)
     __shared__ uint32_t sh_all[RS_HIST_COPIES][RS_MAX_PASSES][RS_RADIX];
-    for (int i = threadIdx.x; i < RS_HIST_COPIES * RS_MAX_PASSES * RS_RADIX; i += RS_THREADS) (&sh_all[0][0][0])[i] = 0;
+    for (int i = threadIdx.x; i < RS_HIST_COPIES * RS_MAX_PASSES * RS_RADIX; i += RS_HIST_THREADS) (&sh_all[0][0][0])[i] = 0;
     uint32_t (*sh)[RS_RADIX] = sh_all[threadIdx.x & (RS_HIST_COPIES - 1)];
     __syncthreads();
     // scalar head up to the first 16-byte boundary (sub-ranges of a larger array need not be aligned), vector body, scalar tail
     const int64_t head = min(n, (int64_t)((16 - (reinterpret_cast<uintptr_t>(keys) & 15)) & 15) >> 2);
     const int64_t n_vec = (n - head) >> 2;
     const uint4* kv = reinterpret_cast<const uint4*>(keys + head);
-    for (int64_t i = (int64_t)blockIdx.x * RS_THREADS + threadIdx.x; i < n_vec; i += (int64_t)gridDim.x * RS_THREADS) {
+    for (int64_t i = (int64_t)blockIdx.x * RS_HIST_THREADS + threadIdx.x; i < n_vec; i += (int64_t)gridDim.x * RS_HIST_THREADS) {
         uint4 k = ld_stream_u32x4(kv + i);
         uint32_t kk[4] = {k.x, k.y, k.z, k.w};
 #pragma unroll
@@ -109,7 +118,7 @@ rs_histogram_kernel(const uint32_t* __restrict__ keys, int64_t n, int begin_bit,
         }
     }
     __syncthreads();
-    for (int i = threadIdx.x; i < n_passes * RS_RADIX; i += RS_THREADS) {
+    for (int i = threadIdx.x; i < n_passes * RS_RADIX; i += RS_HIST_THREADS) {
         uint32_t c = 0;
 #pragma unroll
         for (int q = 0; q < RS_HIST_COPIES; q++) c += (&sh_all[q][0][0])[i];
@@ -126,14 +135,14 @@ rs_histogram_kernel(const uint32_t* __restrict__ keys, int64_t n, int begin_bit,
 // EXTRA: a second 32-bit payload (extra_in -> extra_out) travels with every row.  Used for the linear ends of tables too large
 // for the L2: gathering them afterwards through the sorted row ids is one random DRAM sector per row (5 ms at 200 M rows).
 template <bool IDENTITY_VALS, bool GATHER, int IPT, bool EXTRA = false>
-__global__ void __launch_bounds__(RS_THREADS, IPT >= 16 ? GIQLB_RS_CTAS_PER_SM : 6)
+__global__ void __launch_bounds__(RS_THREADS, RS_THREADS * IPT >= 4096 ? GIQLB_RS_CTAS_PER_SM : 6)
 rs_onesweep_kernel(const uint32_t* __restrict__ keys_in, const uint32_t* __restrict__ vals_in,
                    uint32_t* __restrict__ keys_out, uint32_t* __restrict__ vals_out, int64_t n, int shift,
                    const uint32_t* __restrict__ gather_src /* EXTRA: extra_in */, uint32_t* __restrict__ gather_dst /* EXTRA: extra_out */,
                    const uint32_t* __restrict__ ghist /* this pass, [256] */,
                    uint32_t* __restrict__ status /* this pass, [tiles][256] */,
                    uint32_t* __restrict__ ticket, int* __restrict__ err_flag) {
-    __shared__ uint32_t s_warp_hist[RS_WARPS][RS_RADIX];   // per-warp digit counters -> warp-exclusive offsets
+    __shared__ rs_hist_t s_warp_hist[RS_WARPS][RS_RADIX];   // per-warp digit counters -> warp-exclusive offsets
     __shared__ uint32_t s_keys[(RS_THREADS * IPT)];
     __shared__ uint32_t s_vals[(RS_THREADS * IPT)];
     __shared__ uint32_t s_digit_excl[RS_RADIX];            // tile-local exclusive digit offsets
@@ -194,7 +203,7 @@ rs_onesweep_kernel(const uint32_t* __restrict__ keys_in, const uint32_t* __restr
         uint32_t base = 0;
         if ((int)l == leader) {
             base = s_warp_hist[w][d];
-            s_warp_hist[w][d] = base + __popc(peers);
+            s_warp_hist[w][d] = (rs_hist_t)(base + __popc(peers));
         }
         base = __shfl_sync(FULL_MASK, base, leader);
         rank[i] = base + __popc(peers & lt_mask);
@@ -202,34 +211,37 @@ rs_onesweep_kernel(const uint32_t* __restrict__ keys_in, const uint32_t* __restr
     }
     __syncthreads();
 
-    // thread d: turn per-warp counts into warp-exclusive offsets, get the tile's count of digit d
-    const uint32_t d_own = threadIdx.x;
+    // thread d (the first 256 threads): turn per-warp counts into warp-exclusive offsets, get the tile's count of digit d
+    const bool owns_digit = RS_THREADS == RS_RADIX || threadIdx.x < RS_RADIX;
+    const uint32_t d_own = owns_digit ? threadIdx.x : 0u;
     uint32_t count = 0;
-#pragma unroll
-    for (int ww = 0; ww < RS_WARPS; ww++) {
-        uint32_t c = s_warp_hist[ww][d_own];
-        s_warp_hist[ww][d_own] = count;
-        count += c;
-    }
-    if (d_own == 255u) count -= (uint32_t)((RS_THREADS * IPT) - tile_n);   // padding keys are all-ones -> digit 255
     uint32_t* my_status = status + (size_t)tile * RS_RADIX + d_own;
-    if (tile == 0) {
-        *(volatile uint32_t*)my_status = ST_FLAG_INCL | count;
-    } else {
-        *(volatile uint32_t*)my_status = ST_FLAG_AGG | count;
-    }
-    // first look-back step issued now: its L2 round trip overlaps the two block scans and the shared-memory scatter
     uint32_t pre[GIQLB_RS_LOOKBACK];
+    if (owns_digit) {
 #pragma unroll
-    for (int j = 0; j < GIQLB_RS_LOOKBACK; j++)
-        pre[j] = (int64_t)tile - 1 - j >= 0 ? *(volatile uint32_t*)(status + (size_t)(tile - 1 - j) * RS_RADIX + d_own) : (2u << 30);
-    // tile-local exclusive offsets over digits, and global start of each digit bin
+        for (int ww = 0; ww < RS_WARPS; ww++) {
+            uint32_t c = s_warp_hist[ww][d_own];
+            s_warp_hist[ww][d_own] = (rs_hist_t)count;
+            count += c;
+        }
+        if (d_own == 255u) count -= (uint32_t)((RS_THREADS * IPT) - tile_n);   // padding keys are all-ones -> digit 255
+        if (tile == 0) {
+            *(volatile uint32_t*)my_status = ST_FLAG_INCL | count;
+        } else {
+            *(volatile uint32_t*)my_status = ST_FLAG_AGG | count;
+        }
+        // first look-back step issued now: its L2 round trip overlaps the two block scans and the shared-memory scatter
+#pragma unroll
+        for (int j = 0; j < GIQLB_RS_LOOKBACK; j++)
+            pre[j] = (int64_t)tile - 1 - j >= 0 ? *(volatile uint32_t*)(status + (size_t)(tile - 1 - j) * RS_RADIX + d_own) : (2u << 30);
+    }
+    // tile-local exclusive offsets over digits, and global start of each digit bin (threads without a digit add nothing)
     uint32_t tot;
     uint32_t dex = block_excl_scan_add<uint32_t>(count, s_scan, &tot);
     __syncthreads();
     uint32_t gtot;
-    uint32_t gstart = block_excl_scan_add<uint32_t>(ghist[d_own], s_scan, &gtot);
-    s_digit_excl[d_own] = dex;
+    uint32_t gstart = block_excl_scan_add<uint32_t>(owns_digit ? ghist[d_own] : 0u, s_scan, &gtot);
+    if (owns_digit) s_digit_excl[d_own] = dex;
 
     __syncthreads();   // s_digit_excl and the warp-exclusive offsets are complete
 
@@ -250,7 +262,7 @@ rs_onesweep_kernel(const uint32_t* __restrict__ keys_in, const uint32_t* __restr
     // decoupled look-back over earlier tiles for digit d_own; four predecessors are fetched per step so that the
     // chain of dependent L2 round trips is four times shorter
     uint32_t prefix = 0;
-    if (tile > 0) {
+    if (tile > 0 && owns_digit) {
         int64_t t = (int64_t)tile - 1;
         uint32_t spins = 0;
         bool done = false;
@@ -268,7 +280,7 @@ rs_onesweep_kernel(const uint32_t* __restrict__ keys_in, const uint32_t* __restr
         }
         *(volatile uint32_t*)my_status = ST_FLAG_INCL | (prefix + count);
     }
-    s_global_base[d_own] = (int32_t)(gstart + prefix - dex);
+    if (owns_digit) s_global_base[d_own] = (int32_t)(gstart + prefix - dex);
     __syncthreads();
     // write out: consecutive slots of one digit are consecutive in global memory
     for (int j = threadIdx.x; j < tile_n; j += RS_THREADS) {
@@ -331,10 +343,10 @@ int giqlb_radix_sort_pairs_u32(giqlb_ctx* ctx, uint32_t* keys_a, uint32_t* vals_
         CUDA_TRY(ctx, cudaMemcpyAsync(ghist, hist_dev + (size_t)(begin_bit / 8) * RS_RADIX, (size_t)n_passes * RS_RADIX * sizeof(uint32_t),
                                       cudaMemcpyDeviceToDevice, ctx->stream));
     } else {
-        int64_t hb_want = ceil_div(n, RS_THREADS * 16), hb_cap = (int64_t)ctx->sm_count * 8;
+        int64_t hb_want = ceil_div(n, RS_HIST_THREADS * 16), hb_cap = (int64_t)ctx->sm_count * 8;
         int hist_blocks = (int)(hb_want < hb_cap ? hb_want : hb_cap);
         PhaseSpan ps(ctx, GIQLB_PH_SORT_HIST);
-        rs_histogram_kernel<<<hist_blocks, RS_THREADS, 0, ctx->stream>>>(keys_a, n, begin_bit, n_passes, ghist);
+        rs_histogram_kernel<<<hist_blocks, RS_HIST_THREADS, 0, ctx->stream>>>(keys_a, n, begin_bit, n_passes, ghist);
         LAUNCH_CHECK(ctx);
     }
 
