@@ -538,3 +538,4 @@ int giqlb_index_ensure_end_sorted(giqlb_ctx* ctx, giqlb_index* ix);
 int giqlb_index_ensure_dirs(giqlb_ctx* ctx, giqlb_index* ix, bool want_pmax, bool want_ges);
 int giqlb_index_ensure_block_max(giqlb_ctx* ctx, giqlb_index* ix);
 int giqlb_index_ensure_exists_dir(giqlb_ctx* ctx, giqlb_index* ix);
+int giqlb_bucket_dir_build(giqlb_ctx* ctx, const uint32_t* arr, int64_t n, uint64_t extent, int* shift, uint32_t* stride, uint32_t** tab);

@@ -1095,6 +1095,20 @@ int giqlb_index_ensure_dirs(giqlb_ctx* ctx, giqlb_index* ix, bool want_pmax, boo
     return GIQLB_OK;
 }
 
+// Bucket directory of any ascending device array (not only an index's own): tab[b] = first position with a value >= b << shift,
+// about one bucket per element (at most 2^24), values beyond `extent` fall into the last bucket.  The caller frees *tab.
+int giqlb_bucket_dir_build(giqlb_ctx* ctx, const uint32_t* arr, int64_t n, uint64_t extent, int* shift, uint32_t* stride, uint32_t** tab) {
+    int bits = 1;
+    while (bits < 24 && (1ll << bits) < n) bits++;
+    *shift = 32 - bits;
+    const uint64_t ext = extent ? extent : 0xffffffffull;
+    *stride = (uint32_t)((ext > 0xffffffffull ? 0xffffffffull : ext) >> *shift) + 2u;
+    GIQLB_TRY(dev_alloc(ctx, tab, (size_t)*stride));
+    bucket_dir_kernel<<<grid_for(ctx, n + 1, 256, 16), 256, 0, ctx->stream>>>(arr, n, *shift, *stride, *tab);
+    LAUNCH_CHECK(ctx);
+    return GIQLB_OK;
+}
+
 // dir_exists of a plain index (requires pmax; builds dir_gs when missing)
 int giqlb_index_ensure_exists_dir(giqlb_ctx* ctx, giqlb_index* ix) {
     if (ix->dir_exists || ix->n == 0) return GIQLB_OK;
