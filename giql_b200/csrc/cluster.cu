@@ -318,7 +318,7 @@ int running_count(giqlb_ctx* ctx, const giqlb_index* X, int64_t lo, int64_t hi, 
         pred.cur += lo;
         pred.prev += lo;
     }
-    return launch_scan<OpAddU64>(ctx, hi - lo, InClusterFlag{X->gs + lo, X->pmax + lo, view_of(X->layout), d, carry, pred},
+    return launch_scan<OpAddU32>(ctx, hi - lo, InClusterFlag{X->gs + lo, X->pmax + lo, view_of(X->layout), d, carry, pred},
                                  OutRunningCount{G + lo});
 }
 

@@ -157,6 +157,11 @@ struct OpMaxU32 {
     __device__ static T identity() { return 0u; }
     __device__ static T combine(T a, T b) { return a > b ? a : b; }
 };
+struct OpAddU32 {   // sums known to stay below 2^32 (row counts: tables hold fewer than 2^30 rows); half the registers and shared memory
+    typedef uint32_t T;
+    __device__ static T identity() { return 0u; }
+    __device__ static T combine(T a, T b) { return a + b; }
+};
 struct OpAddU64 {
     typedef unsigned long long T;
     __device__ static T identity() { return 0ull; }
