@@ -155,7 +155,8 @@ int giqlb_layout_tables(const giqlb_layout* lay, const uint32_t** base_dev, cons
  * error reported as GIQLB_ERR_RANGE by the next call that returns a host value (plan/join, index_info, sync).
  * observe() and index_build() of one table must use the same offsets. */
 /* ---- sorted index -----------------------------------------------------------------------------
- * LSD radix sort of the linearised start with carried row ids; then gathers the linearised end.
+ * LSD radix sort of the linearised start with carried row ids; then gathers the linearised end (tables of 24 M rows and
+ * more carry the end through the sort as a second payload instead: a gather beyond the L2 costs a DRAM sector per row).
  * strand may be NULL.  start_adj/end_adj are the canonical.py:16-52 offsets (raw + adj = canonical).
  * flags: GIQLB_INDEX_TIE_BY_END orders equal starts by end (NEAREST's ORDER BY start, end). */
 #define GIQLB_INDEX_TIE_BY_END 1
