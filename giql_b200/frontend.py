@@ -11,15 +11,17 @@ Recognised shapes (GIQL semantics cited per branch in :class:`Session`):
 
 * ``FROM a [x] [INNER|LEFT|SEMI|ANTI] JOIN b [y] ON x.interval INTERSECTS|CONTAINS|WITHIN y.interval`` and the comma form
   ``FROM a x, b y WHERE x.interval INTERSECTS y.interval``
-* ``FROM t WHERE interval INTERSECTS|CONTAINS|WITHIN 'chr1:100-200'`` and ``... INTERSECTS ANY|ALL(...)``
-* ``FROM a x CROSS JOIN LATERAL NEAREST(b, reference := x.interval[, k, max_distance, stranded, signed]) [y]`` (repeatable)
-* ``FROM a x JOIN b y ON x.chrom = y.chrom WHERE DISTANCE(x.interval, y.interval[, ...]) < n``
+* ``FROM t WHERE interval INTERSECTS|CONTAINS|WITHIN 'chr1:100-200'`` and ``... INTERSECTS|CONTAINS|WITHIN ANY|ALL(...)``
+* ``FROM a x CROSS JOIN LATERAL NEAREST(b, reference := x.interval[, k, max_distance, stranded, signed]) [y]`` (repeatable);
+  the standalone placement ``FROM NEAREST(b, reference := 'chr1:350-360'[, k, max_distance, signed]) [y]``
+* ``FROM a x JOIN b y ON x.chrom = y.chrom WHERE DISTANCE(x.interval, y.interval[, ...]) < n``; the plain cross join
+  ``FROM a x, b y`` / ``a x CROSS JOIN b y`` feeding ``DISTANCE`` in the select list (bounded product)
 * ``SELECT ..., CLUSTER(interval[, d][, stranded := true]) AS c FROM t``; ``SELECT MERGE(interval[, d][, stranded := true])[, COUNT(*)] FROM t``
 * ``FROM DISJOIN(t[, ref])``;  ``WITH name AS (SELECT * FROM t) ...``;  a derived table ``FROM (<query>) alias``
 * ``SELECT <left cols>, COUNT(*) | COUNT(y.col) FROM a x [LEFT] JOIN b y ON x.interval INTERSECTS y.interval GROUP BY <left cols>``
   (count_overlaps: one per-row count probe, no pair list); any other ``GROUP BY cols`` with ``COUNT`` over the joined rows
 * residual ON-conjuncts ``AND x.col <op> y.col`` (same / opposite strand joins), ``WHERE col <op> col | literal``
-* ``CLUSTER / MERGE(interval, predicate := col <op> PREV(col))``
+* ``CLUSTER / MERGE(interval, predicate := col <op> PREV(col))`` and conjunctions of such equalities
 * projections ``*``, ``x.*``, ``[x.]col [AS name]``, ``DISTANCE(x.interval, y.interval[, ...]) [AS name]``; ``DISTINCT``;
   ``ORDER BY col [DESC]``; ``LIMIT n``
 
@@ -36,6 +38,9 @@ import torch
 
 from .ranges import parse_range
 from .table import Table, canonical_offsets
+
+
+_CROSS_JOIN_LIMIT = 1 << 24     # rows of `FROM a, b` without any join predicate the front-end will materialise
 
 
 class UnsupportedQuery(ValueError):
@@ -231,8 +236,11 @@ class _Parser:
             if self.accept("op", ","):
                 q["joins"].append({"kind": "comma", "source": self.source()})
             elif self.at("kw", "CROSS"):
-                self.take("kw", "CROSS"); self.take("kw", "JOIN"); self.take("kw", "LATERAL")
-                q["joins"].append({"kind": "nearest", **self.nearest_call()})
+                self.take("kw", "CROSS"); self.take("kw", "JOIN")
+                if self.accept("kw", "LATERAL"):
+                    q["joins"].append({"kind": "nearest", **self.nearest_call()})
+                else:                                                    # `a CROSS JOIN b` == `a, b`
+                    q["joins"].append({"kind": "comma", "source": self.source()})
             elif self.at("kw", "JOIN") or self.at("kw", "INNER") or self.at("kw", "LEFT") or self.at("kw", "SEMI") or self.at("kw", "ANTI"):
                 kind = "inner"
                 if not self.at("kw", "JOIN"):
@@ -282,6 +290,24 @@ class _Parser:
             self.accept("kw", "AS")
             return {"kind": "subquery", "query": sub, "alias": self.take("id")}
         name = self.take("id")
+        if name.upper() == "NEAREST" and self.at("op", "("):
+            # standalone placement: `FROM NEAREST(target, reference := 'chr1:350-360', k := 2)` — the literal range is the one
+            # query interval (src/giql/expanders/nearest.py:343-350, 782-817; the literal is canonical 0-based half-open)
+            self.take("op", "(")
+            target = self.take("id")
+            args = self.named_args()
+            self.take("op", ")")
+            ref = args.get("reference")
+            if not isinstance(ref, str):
+                raise UnsupportedQuery("a NEAREST in FROM takes a literal range as its reference")
+            if _bool_arg(args.get("stranded"), "stranded"):
+                raise UnsupportedQuery("stranded NEAREST with a literal reference is finished by the SQL engine")
+            k = _int_arg(args.get("k"), "NEAREST k", 1)
+            if k < 1:
+                raise ValueError("NEAREST k must be >= 1")
+            return {"kind": "nearest_literal", "table": target, "range": ref, "k": k, "stranded": False,
+                    "max_distance": _int_arg(args.get("max_distance"), "NEAREST max_distance"),
+                    "signed": _bool_arg(args.get("signed"), "signed"), "alias": self.alias() or target}
         if name.upper() == "DISJOIN" and self.at("op", "("):
             self.take("op", "(")
             target = self.take("id")
@@ -337,16 +363,27 @@ class _Parser:
                 self.take("op", ")")
                 return True, col[1]
             return False, self.column_ref()[1]
-        lp, lcol = operand()
-        op = self.take("op")
-        rp, rcol = operand()
-        op = {"<>": "!=", "==": "="}.get(op, op)
-        if op not in ("=", "!=", "<", "<=", ">", ">=") or lp == rp:
-            raise UnsupportedQuery("predicate := must compare one column with PREV(column)")
-        if lp:                                                            # PREV(a) op b  ==  b op' PREV(a)
-            op = {"<": ">", "<=": ">=", ">": "<", ">=": "<="}.get(op, op)
-            return {"cur": rcol, "op": op, "prev": lcol}
-        return {"cur": lcol, "op": op, "prev": rcol}
+        def comparison():
+            lp, lcol = operand()
+            op = self.take("op")
+            rp, rcol = operand()
+            op = {"<>": "!=", "==": "="}.get(op, op)
+            if op not in ("=", "!=", "<", "<=", ">", ">=") or lp == rp:
+                raise UnsupportedQuery("predicate := must compare one column with PREV(column)")
+            if lp:                                                        # PREV(a) op b  ==  b op' PREV(a)
+                op = {"<": ">", "<=": ">=", ">": "<", ">=": "<="}.get(op, op)
+                return {"cur": rcol, "op": op, "prev": lcol}
+            return {"cur": lcol, "op": op, "prev": rcol}
+        terms = [comparison()]
+        while self.accept("kw", "AND"):
+            terms.append(comparison())
+        if len(terms) == 1:
+            return terms[0]
+        # `a = PREV(a) AND b = PREV(b)`: a conjunction of equalities is ONE equality of the column tuples (a tuple with a NULL
+        # component is NULL: the conjunction is then not TRUE).  Other conjunctions need a boolean expression evaluator.
+        if any(t["op"] != "=" for t in terms):
+            raise UnsupportedQuery("predicate := takes one comparison with PREV(column), or a conjunction of equalities")
+        return {"cur": [t["cur"] for t in terms], "op": "=", "prev": [t["prev"] for t in terms]}
 
     def scalar(self):
         if self.at("num"):
@@ -734,7 +771,13 @@ def _cluster_ids(be, f, p) -> np.ndarray:
     pred = None
     if p.get("predicate"):
         q = p["predicate"]
-        pred = (f.column(f.resolve(None, q["cur"]), q["cur"]).tolist(), q["op"], f.column(f.resolve(None, q["prev"]), q["prev"]).tolist())
+
+        def operand(cols):
+            if not isinstance(cols, list):
+                return f.column(f.resolve(None, cols), cols).tolist()
+            parts = [f.column(f.resolve(None, c), c).tolist() for c in cols]
+            return [None if any(v is None for v in t) else t for t in zip(*parts)]
+        pred = (operand(q["cur"]), q["op"], operand(q["prev"]))
     if hasattr(be, "cluster_array"):
         return be.cluster_array(g, p["distance"], p["stranded"], pred).astype(np.int64) if pred else be.cluster_array(g, p["distance"], p["stranded"]).astype(np.int64)
     lists = {k: v.tolist() for k, v in g.items()}
@@ -832,6 +875,14 @@ class Session:
                 "disjoin_chrom": t.genomic()["chrom"][rows],
                 "disjoin_start": np.asarray([s[1] - sadj for s in segs], dtype=np.int64),
                 "disjoin_end": np.asarray([s[2] - eadj for s in segs], dtype=np.int64)})
+        elif src["kind"] == "nearest_literal":
+            tgt = self._relation(q, {"kind": "table", "table": src["table"]})
+            chrom, start, end = parse_range(src["range"])
+            one = _Rel(["chrom", "start", "end"], {"chrom": _column([chrom]), "start": _column([start]), "end": _column([end])})
+            ti, dist = np.zeros(0, np.int64), np.zeros(0, np.int64)
+            if len(tgt):
+                _, ti, dist = _nearest(be, one, tgt, src)              # one query row: the engine's rank order is the output order
+            f.add(src["alias"], tgt, ti, {"distance": dist})
         else:
             base = self._relation(q, src)
             f.add(src["alias"], base, np.arange(len(base), dtype=np.int64))
@@ -847,6 +898,7 @@ class Session:
             ra, la = j["source"]["alias"], f.order[0]
             left = f.rels[la]
             conds, kind = list(j.get("on") or []), j["kind"]
+            comma = kind == "comma"
             if kind == "comma":
                 # `FROM a, b WHERE a.interval INTERSECTS b.interval [AND a.x = b.x]`: the WHERE conjuncts over both tables are the ON
                 between = lambda w: (w["kind"] == "spatial" and {w["left"], w["right"]} == {la, ra}) or \
@@ -857,6 +909,15 @@ class Session:
             compares = [c for c in conds if c["kind"] == "compare"]
             if len(spatial) + len(compares) != len(conds) or len(spatial) > 1:
                 raise UnsupportedQuery("JOIN ... ON takes one spatial predicate and column comparisons between the two tables")
+            if comma and not conds:
+                # plain cross join (`FROM a, b` feeding DISTANCE in the select list, docs/dialect/distance-operators.rst): every
+                # pairing is an output row, so the product is built as two row-id columns; large products belong to the SQL engine
+                if len(f) * len(right) > _CROSS_JOIN_LIMIT:
+                    raise UnsupportedQuery(f"a cross join of {len(f)} x {len(right)} rows is finished by the SQL engine")
+                n_left = len(f)
+                f.take(np.repeat(np.arange(n_left), len(right)))
+                f.add(ra, right, np.tile(np.arange(len(right), dtype=np.int64), n_left))
+                continue
             if not spatial:
                 # chromosome equi-join feeding DISTANCE (docs/dialect/distance-operators.rst:130-155): quadratic by nature
                 on = compares[0] if len(compares) == 1 else None
@@ -1033,12 +1094,11 @@ class Session:
                 else:
                     keep = _exists(be, rel.genomic(), lit, rel.config, None)
             else:
-                if len(ranges) != 1:
-                    raise UnsupportedQuery("CONTAINS / WITHIN take one literal range")
-                # the column join against the one-row table of the literal (intersects.py:155-166 on a literal operand)
+                # the column join against the table of the literals (intersects.py:155-166 on a literal operand); several
+                # ranges: per-range predicates OR-ed for ANY, AND-ed for ALL (:243-270) = at least one / every literal row hit
                 hit, _ = _pairs(be, rel.genomic(), lit, w["op"], rel.config, None)
-                keep = np.zeros(len(rel), bool)
-                keep[np.asarray(hit, dtype=np.int64)] = True
+                per_row = np.bincount(np.asarray(hit, dtype=np.int64), minlength=len(rel))
+                keep = per_row == len(ranges) if w["quant"] == "ALL" else per_row > 0
             ix = f.idx[alias]
             f.take((ix >= 0) & keep[np.maximum(ix, 0)] if len(keep) else np.zeros(len(ix), bool))
         elif w["kind"] == "distance_cmp":

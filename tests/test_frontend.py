@@ -84,6 +84,15 @@ STATEMENTS = [
     "SELECT a.name, COUNT(*) AS n FROM peaks a LEFT JOIN genes b ON a.interval INTERSECTS b.interval GROUP BY a.name",
     "SELECT a.name, COUNT(b.name) AS n FROM peaks a LEFT JOIN genes b ON a.interval INTERSECTS b.interval AND a.strand = b.strand GROUP BY a.name",
     "SELECT b.strand, COUNT(*) FROM peaks a JOIN genes b ON a.interval INTERSECTS b.interval GROUP BY b.strand",
+    # shapes of the reference's coordinate-space / bedtools / cluster-predicate integration tests (tests/test_reference_replay.py)
+    "SELECT name FROM peaks WHERE interval CONTAINS ANY('chr1:700-710', 'chr2:300-305')",
+    "SELECT name FROM peaks WHERE interval WITHIN ALL('chr1:0-1500', 'chr1:100-2500')",
+    "SELECT a.name, b.name, DISTANCE(a.interval, b.interval) AS d FROM peaks a, genes b",
+    "SELECT a.name, b.name, DISTANCE(a.interval, b.interval, stranded := true, signed := true) AS d FROM peaks a CROSS JOIN genes b WHERE a.chrom = b.chrom",
+    "SELECT name, distance FROM NEAREST(genes, reference := 'chr1:350-360', k := 4)",
+    "SELECT name, distance FROM NEAREST(genes, reference := 'chr2:900-1000', k := 3, signed := true, max_distance := 200) n",
+    "SELECT name, CLUSTER(interval, predicate := strand = PREV(strand) AND chrom = PREV(chrom)) AS cid FROM peaks",
+    "SELECT MERGE(interval, predicate := strand = PREV(strand) AND name = PREV(name)) FROM peaks",
 ]
 
 
@@ -115,7 +124,8 @@ def test_parse_shapes():
     "SELECT a.name FROM peaks a JOIN genes b ON a.name = b.name",
     "SELECT a.name FROM peaks a SEMI JOIN genes b ON a.interval CONTAINS b.interval",
     "SELECT a.name FROM peaks a CROSS JOIN LATERAL NEAREST(genes, k := 1) b",
-    "SELECT name FROM peaks WHERE interval CONTAINS ANY('chr1:1-2', 'chr1:3-4')",
+    "SELECT name FROM NEAREST(genes, reference := 'chr1:350-360', k := 2, stranded := true)",
+    "SELECT name, CLUSTER(interval, predicate := strand = PREV(strand) AND start > PREV(start)) AS cid FROM peaks",
     "SELECT MERGE(interval), name FROM peaks",
     "UPDATE peaks SET start = 0",
 ])
@@ -269,6 +279,54 @@ def test_residual_join_predicates_against_brute_force():
     want = sorted((N["name"][i], G["name"][j]) for i in range(40) for j in range(60)
                   if overlap(N, i, G, j) and N["strand"][i] is not None and N["strand"][i] != G["strand"][j])
     assert sorted(got) == want
+
+
+def test_cross_join_standalone_nearest_and_set_predicates_against_brute_force():
+    s = sessions(OracleBackend())
+    P, G = make(11, 90), make(12, 60)
+    # plain cross join: every pairing, DISTANCE per pairing (NULL across chromosomes)
+    rows = s.execute("SELECT a.name, b.name, DISTANCE(a.interval, b.interval) AS d FROM peaks a, genes b").rows
+    assert len(rows) == 90 * 60
+
+    def dist(i, j):
+        if P["chrom"][i] != G["chrom"][j]:
+            return None
+        if P["start"][i] < G["end"][j] and G["start"][j] < P["end"][i]:
+            return 0
+        return G["start"][j] - P["end"][i] + 1 if P["end"][i] <= G["start"][j] else P["start"][i] - G["end"][j] + 1
+    assert sorted(rows, key=repr) == sorted(((f"f{i}", f"f{j}", dist(i, j)) for i in range(90) for j in range(60)), key=repr)
+    assert s.execute("SELECT a.name FROM peaks a CROSS JOIN genes b").rows == [(f"f{i}",) for i in range(90) for _ in range(60)]
+    # a product beyond the limit is the SQL engine's business
+    import giql_b200.frontend as fe
+    old, fe._CROSS_JOIN_LIMIT = fe._CROSS_JOIN_LIMIT, 1000
+    try:
+        with pytest.raises(UnsupportedQuery):
+            s.execute("SELECT a.name FROM peaks a, genes b")
+    finally:
+        fe._CROSS_JOIN_LIMIT = old
+    # standalone NEAREST: the literal is the one query interval; rows come back in rank order (|distance|, start, end)
+    got = s.execute("SELECT name, distance FROM NEAREST(genes, reference := 'chr1:350-360', k := 4)").rows
+    cand = []
+    for j in range(60):
+        if G["chrom"][j] != "chr1":
+            continue
+        d = 0 if (350 < G["end"][j] and G["start"][j] < 360) else (G["start"][j] - 360 + 1 if 360 <= G["start"][j] else 350 - G["end"][j] + 1)
+        cand.append((d, G["start"][j], G["end"][j], j))
+    cand.sort()
+    assert got == [(f"f{j}", d) for d, _, _, j in cand[:4]]
+    assert s.execute("SELECT name FROM NEAREST(genes, reference := 'chr7:1-2', k := 4)").rows == []
+    assert len(s.execute("SELECT * FROM NEAREST(genes, reference := 'chr1:350-360', k := 1000)").rows) == sum(c == "chr1" for c in G["chrom"])
+    # CONTAINS / WITHIN over several literals: OR for ANY, AND for ALL (src/giql/expanders/intersects.py:243-270)
+    lits = [("chr1", 700, 710), ("chr2", 300, 305)]
+    want = [f"f{i}" for i in range(90) if any(P["chrom"][i] == c and P["start"][i] <= a and P["end"][i] >= b for c, a, b in lits)]
+    assert sorted(r[0] for r in s.execute("SELECT name FROM peaks WHERE interval CONTAINS ANY('chr1:700-710', 'chr2:300-305')").rows) == sorted(want)
+    lits = [("chr1", 0, 1500), ("chr1", 100, 2500)]
+    want = [f"f{i}" for i in range(90) if all(P["chrom"][i] == c and P["start"][i] >= a and P["end"][i] <= b for c, a, b in lits)]
+    assert want and sorted(r[0] for r in s.execute("SELECT name FROM peaks WHERE interval WITHIN ALL('chr1:0-1500', 'chr1:100-2500')").rows) == sorted(want)
+    # a conjunction of equalities gates like the equality of the column tuples
+    a = s.execute("SELECT name, CLUSTER(interval, predicate := strand = PREV(strand) AND chrom = PREV(chrom)) AS cid FROM peaks").rows
+    b = s.execute("SELECT name, CLUSTER(interval, predicate := strand = PREV(strand)) AS cid FROM peaks").rows
+    assert a == b                                                # the chromosome never changes inside a partition
 
 
 @pytest.mark.gpu
