@@ -1222,7 +1222,22 @@ class Session:
             for i, r in enumerate(res.rows):
                 first.setdefault(r, i)
             res = res.take(np.fromiter(first.values(), dtype=np.int64, count=len(first)))
-        return self._order_limit(q, res, f)
+            return self._order_limit(q, res, f)
+        # ORDER BY over a column the select list does not carry (legal without DISTINCT; the reference's IEJoin path projects
+        # such keys itself, src/giql/expanders/intersects_duckdb.py:1339-1400): sort on a hidden column of the joined rows
+        shown = len(cols)
+        for (alias, col), _ in q["order"]:
+            try:
+                self._order_key(res, alias, col, f)
+            except ValueError as exc:
+                if "ambiguous" in str(exc):
+                    raise
+                a = f.resolve(alias, col)
+                res = Result(res.columns + [f"__order_{len(res.columns)}"], res.arrays + [f.column(a, col)], res.sources + [(a, col)])
+                if alias is None:                                     # an unqualified hidden key is found by its name
+                    res.columns[-1] = col
+        res = self._order_limit(q, res, f)
+        return Result(res.columns[:shown], res.arrays[:shown], res.sources[:shown])
 
     @staticmethod
     def _order_key(res: Result, alias, col, f) -> int:

@@ -13,7 +13,14 @@ here; the script exits non-zero).  Every call of a verified test is written to `
 
     python tests/golden/replay_reference_tests.py            # in the build container (/root/reference mounted)
 
-Modules replayed: cluster_predicate/test_cluster_predicate.py, coordinate_space/test_{distance,nearest,disjoin}_
+A second group of reference tests has no fixture helper: it creates tables on ``duckdb.connect(":memory:")``, calls
+``transpile(query, tables=..., dialect="duckdb")`` and executes the SQL text (tests/test_duckdb_iejoin.py — the DuckDB IEJoin
+path with its hypothesis properties against ``_python_overlap`` —, tests/test_intersects_join.py, tests/expanders/
+test_cluster.py, tests/expanders/test_merge.py).  For those a stand-in ``duckdb`` module records CREATE TABLE / INSERT /
+executemany, the stand-in ``transpile`` returns an opaque plan token, and ``conn.execute(token)`` runs the GIQL query on the
+front-end.  A test that looks INSIDE the SQL text (``"SET VARIABLE" in sql``, EXPLAIN, column types) is ``not_replayable``.
+
+Modules replayed through ``giql_query``: cluster_predicate/test_cluster_predicate.py, coordinate_space/test_{distance,nearest,disjoin}_
 coordinate_space.py, bedtools/test_contains.py, bedtools/test_within.py.  The other bedtools tests compare with the
 ``bedtools`` binary at run time (absent here) and are not replayable.  ``giql`` itself is not importable (sqlglot is
 absent): ``giql.table`` / ``giql.constants`` — sqlglot-free — are loaded from the reference tree by path.
@@ -41,6 +48,16 @@ MODULES = [
     "tests.integration.bedtools.test_contains",
     "tests.integration.bedtools.test_within",
 ]
+DUCKDB_MODULES = [
+    "tests.test_duckdb_iejoin",
+    "tests.test_intersects_join",
+    "tests.expanders.test_cluster",
+    "tests.expanders.test_merge",
+]
+MAX_STORED_CALLS = 4            # per test (hypothesis properties run hundreds of examples)
+SKIP = {   # tests that cannot be judged through the stand-ins
+    "test_transpile_should_inject_lag_calc_columns_deterministically": "spawns Python subprocesses that import giql (sqlglot)",
+}
 COLUMNS = ["chrom", "start", "end", "name", "score", "strand"]      # bedtools/utils/duckdb_loader.py:18-27
 
 
@@ -66,6 +83,7 @@ def install_reference_stubs():
 
     giql.transpile = transpile
     for pkg, path in [("tests", REF / "tests"), ("tests.integration", REF / "tests/integration"),
+                      ("tests.expanders", REF / "tests/expanders"),
                       ("tests.integration.cluster_predicate", REF / "tests/integration/cluster_predicate"),
                       ("tests.integration.coordinate_space", REF / "tests/integration/coordinate_space"),
                       ("tests.integration.bedtools", REF / "tests/integration/bedtools"),
@@ -89,8 +107,9 @@ def run_query(backend, query: str, tables: list[dict], data: dict) -> list[tuple
 
     sess = Session(backend)
     cfgs = {t["name"]: Table(**t) for t in tables if len(t) > 1}
-    for name, rows in data.items():
-        sess.register(name, {c: [r[i] for r in rows] for i, c in enumerate(COLUMNS)}, cfgs.get(name), columns=COLUMNS)
+    for name, t in data.items():
+        cols, rows = t["columns"], t["rows"]
+        sess.register(name, {c: [r[i] for r in rows] for i, c in enumerate(cols)}, cfgs.get(name), columns=cols)
     return [tuple(r) for r in sess.execute(query).rows]
 
 
@@ -100,10 +119,242 @@ class Recorder:
 
     def __call__(self, query, *, tables, **table_data):
         specs = [_table_spec(t) for t in tables]
-        data = {name: [list(r.to_tuple() if hasattr(r, "to_tuple") else r) for r in rows] for name, rows in table_data.items()}
+        data = {name: {"columns": COLUMNS, "rows": [list(r.to_tuple() if hasattr(r, "to_tuple") else r) for r in rows]}
+                for name, rows in table_data.items()}
         rows = run_query(self.backend, query, specs, data)
         self.calls.append({"query": query, "tables": specs, "data": data, "rows": [list(r) for r in rows]})
         return rows
+
+
+# ---- the DuckDB stand-in -------------------------------------------------------------------------------------------
+class NotReplayable(Exception):
+    """the test inspects the SQL text, the plan or the column types: nothing this engine has a counterpart for"""
+
+
+def _opaque(name):
+    def method(self, *a, **k):
+        raise NotReplayable(f"the test inspects the transpiled SQL text ({name})")
+    return method
+
+
+class PlanToken(str):
+    """What the stand-in ``transpile`` returns: executable by FakeConn, opaque to everything else."""
+    plan: dict
+
+    def __new__(cls, plan):
+        self = super().__new__(cls, "<giql_b200 plan token>")
+        self.plan = plan
+        return self
+
+
+for _m in ("__contains__", "upper", "lower", "split", "count", "find", "index", "startswith", "endswith", "replace", "strip",
+           "splitlines", "__getitem__", "__iter__", "__len__", "__add__", "__radd__", "__mod__", "format", "partition", "rstrip"):
+    setattr(PlanToken, _m, _opaque(_m))
+
+
+class _TypeProbe:
+    def __str__(self):
+        raise NotReplayable("the test reads DuckDB column types")
+    __repr__ = __str__
+
+
+class FakeResult:
+    def __init__(self, columns, rows):
+        self.description = [(c, _TypeProbe()) for c in columns]
+        self._rows = rows
+
+    def fetchall(self):
+        return list(self._rows)
+
+    def fetchone(self):
+        return self._rows[0] if self._rows else None
+
+
+import ast as _ast
+import re as _re
+
+from _pytest import outcomes as _pytest_outcomes
+
+_CREATE = _re.compile(r"^\s*CREATE\s+(?:OR\s+REPLACE\s+)?(?:TEMP(?:ORARY)?\s+)?TABLE\s+(?:IF\s+NOT\s+EXISTS\s+)?\"?(\w+)\"?\s*\((.*)\)\s*;?\s*$", _re.I | _re.S)
+_INSERT = _re.compile(r"^\s*INSERT\s+INTO\s+\"?(\w+)\"?\s+VALUES\s*(.*?);?\s*$", _re.I | _re.S)
+_DROP = _re.compile(r"^\s*DROP\s+TABLE\s+(?:IF\s+EXISTS\s+)?\"?(\w+)\"?\s*;?\s*$", _re.I)
+
+
+class FakeConn:
+    """Records the tables a test builds; executes plan tokens on giql_b200.Session."""
+
+    def __init__(self, backend, log):
+        self.backend, self.log, self.tables = backend, log, {}
+
+    def execute(self, sql, params=None):
+        if isinstance(sql, PlanToken):
+            return self._run(sql.plan)
+        text = str.__str__(sql)
+        m = _CREATE.match(text)
+        if m:
+            cols = []
+            for part in _re.split(r",(?![^()]*\))", m.group(2)):
+                part = part.strip()
+                if part:
+                    cols.append(part.split()[0].strip('"'))
+            self.tables[m.group(1)] = {"columns": cols, "rows": []}
+            return FakeResult([], [])
+        m = _DROP.match(text)
+        if m:
+            self.tables.pop(m.group(1), None)
+            return FakeResult([], [])
+        m = _INSERT.match(text)
+        if m and m.group(1) in self.tables and params is None:
+            body = _re.sub(r"\bNULL\b", "None", m.group(2), flags=_re.I)
+            rows = _ast.literal_eval("[" + body + "]")
+            self.tables[m.group(1)]["rows"].extend(tuple(r) if isinstance(r, tuple) else (r,) for r in rows)
+            return FakeResult([], [])
+        if m and m.group(1) in self.tables and params is not None:
+            self.tables[m.group(1)]["rows"].append(tuple(params))
+            return FakeResult([], [])
+        raise NotReplayable(f"raw SQL on the connection: {' '.join(text.split())[:60]}")
+
+    def executemany(self, sql, rows):
+        m = _INSERT.match(sql)
+        if not (m and m.group(1) in self.tables):
+            raise NotReplayable(f"raw SQL on the connection: {sql[:60]}")
+        self.tables[m.group(1)]["rows"].extend(tuple(r) for r in rows)
+
+    def close(self):
+        pass
+
+    def _run(self, plan):
+        from giql_b200.frontend import Session
+        from giql_b200.table import Table
+
+        sess = Session(self.backend)
+        cfgs = {t["name"]: Table(**t) for t in plan["tables"] if len(t) > 1}
+        data = {}
+        for name, t in self.tables.items():
+            cols = t["columns"]
+            sess.register(name, {c: [r[i] for r in t["rows"]] for i, c in enumerate(cols)}, cfgs.get(name), columns=cols)
+            data[name] = {"columns": cols, "rows": [list(r) for r in t["rows"]]}
+        res = sess.execute(plan["query"])
+        rows = [tuple(r) for r in res.rows]
+        self.log.append({"query": plan["query"], "tables": plan["tables"], "data": data, "rows": [list(r) for r in rows]})
+        return FakeResult(res.columns, rows)
+
+
+def install_duckdb_stubs(backend, log):
+    """``duckdb.connect`` -> FakeConn, ``giql.transpile`` / ``giql.transpile.transpile`` -> plan tokens."""
+    duckdb = types.ModuleType("duckdb")
+    duckdb.connect = lambda *a, **k: FakeConn(backend, log)
+    duckdb.__version__ = "0.0-replay"
+
+    class Error(Exception):                      # `pytest.raises(duckdb.Error)`: an engine-side binder error has no counterpart
+        pass
+    duckdb.Error = duckdb.BinderException = Error
+    sys.modules["duckdb"] = duckdb
+
+    def transpile(query, tables=None, dialect=None, **kw):
+        if kw:
+            raise NotReplayable(f"transpile keyword {sorted(kw)} has no counterpart here")
+        return PlanToken({"query": query, "tables": [_table_spec(t) for t in (tables or [])], "dialect": dialect})
+
+    giql = sys.modules["giql"]
+    mod = types.ModuleType("giql.transpile")
+    mod.transpile = transpile
+
+    class _Callable(types.ModuleType):           # `from giql import transpile` and `from giql.transpile import transpile` both work
+        def __call__(self, *a, **k):
+            return transpile(*a, **k)
+    mod.__class__ = _Callable
+    sys.modules["giql.transpile"] = mod
+    giql.transpile = mod
+
+
+def _fixture_function(obj):
+    for attr in ("__wrapped__", "_fixture_function"):
+        if hasattr(obj, attr):
+            return getattr(obj, attr)
+    if hasattr(obj, "_get_wrapped_function"):
+        return obj._get_wrapped_function()
+    return obj
+
+
+def _resolve_fixture(mod, name, backend, log, cache):
+    if name in cache:
+        return cache[name]
+    if name == "conn" or name == "duckdb_connection":
+        cache[name] = FakeConn(backend, log)
+        return cache[name]
+    obj = getattr(mod, name, None)
+    if obj is None:
+        raise NotReplayable(f"fixture {name}")
+    fn = _fixture_function(obj)
+    args = {p: _resolve_fixture(mod, p, backend, log, cache) for p in inspect.signature(fn).parameters}
+    val = fn(**args)
+    if inspect.isgenerator(val):
+        val = next(val)
+    cache[name] = val
+    return val
+
+
+def replay_duckdb(backend):
+    """tests that build tables on a DuckDB connection and execute transpiled SQL"""
+    from giql_b200.frontend import UnsupportedQuery
+
+    results = []
+    log: list = []
+    install_duckdb_stubs(backend, log)
+    for modname in DUCKDB_MODULES:
+        mod = importlib.import_module(modname)
+        src = modname.replace(".", "/") + ".py"
+        owners = [(None, mod)] + [(c, c) for n, c in vars(mod).items() if inspect.isclass(c) and n.startswith("Test")]
+        for cls, holder in owners:
+            for name, fn in vars(holder).items():
+                if not (name.startswith("test_") and callable(fn)) or inspect.isclass(fn):
+                    continue
+                for params in _parametrizations(fn, cls):
+                    entry = {"test": f"{src}::{cls.__name__ + '::' if cls else ''}{name}", "params": {k: repr(v) for k, v in params.items()}}
+                    del log[:]
+                    if name in SKIP:
+                        entry["outcome"] = "not_replayable: " + SKIP[name]
+                        results.append(entry)
+                        continue
+                    try:
+                        inner = getattr(fn, "hypothesis", None)
+                        sig_fn = inner.inner_test if inner is not None else fn
+                        given = set(getattr(inner, "_given_kwargs", {}) or {}) if inner is not None else set()
+                        wanted = [p for p in inspect.signature(sig_fn).parameters if p not in ("self", *params) and p not in given]
+                        cache: dict = {}
+                        kwargs = {p: _resolve_fixture(mod, p, backend, log, cache) for p in wanted}
+                        if cls:
+                            fn(cls(), **kwargs, **params)
+                        else:
+                            fn(**kwargs, **params)
+                        if not log:
+                            entry["outcome"] = "not_replayable: the test executes nothing"
+                        else:
+                            entry["outcome"], entry["executed"] = "verified", len(log)
+                            entry["calls"] = [dict(c) for c in log[:MAX_STORED_CALLS]]
+                    except UnsupportedQuery as e:
+                        entry["outcome"] = f"declined: {e}"
+                    except NotReplayable as e:
+                        entry["outcome"] = f"not_replayable: {e}"
+                    except AssertionError as e:
+                        entry["outcome"], entry["calls"] = f"failed: {str(e)[:300]}", [dict(c) for c in log[-2:]]
+                    except _pytest_outcomes.OutcomeException as e:   # pytest.raises(...) around transpile(): a transpile-time check
+                        entry["outcome"] = f"not_replayable: expects a transpile-time outcome ({str(e)[:80]})"
+                    except ModuleNotFoundError as e:             # datafusion / pybedtools back ends of the same test
+                        entry["outcome"] = f"not_replayable: {e}"
+                    except BaseExceptionGroup as e:              # hypothesis: several distinct failures
+                        subs = list(e.exceptions)
+                        if all(isinstance(x, UnsupportedQuery) for x in subs):
+                            entry["outcome"] = f"declined: {subs[0]}"
+                        elif all(isinstance(x, (UnsupportedQuery, NotReplayable)) for x in subs):
+                            entry["outcome"] = f"not_replayable: {subs[0]}"
+                        else:
+                            entry["outcome"] = f"failed: {[str(x)[:100] for x in subs]}"
+                    except Exception as e:                       # noqa: BLE001 — reported, never hidden
+                        entry["outcome"] = f"error: {type(e).__name__}: {str(e)[:200]}"
+                    results.append(entry)
+    return results
 
 
 def _parametrizations(fn, cls):
@@ -165,7 +416,7 @@ def main():
     install_reference_stubs()
     from backends import OracleBackend
 
-    results = replay(OracleBackend())
+    results = replay(OracleBackend()) + replay_duckdb(OracleBackend())
     tally = {}
     for r in results:
         key = r["outcome"].split(":")[0]
@@ -180,7 +431,7 @@ def main():
            "tally": tally, "tests": results}
     OUT.write_text(json.dumps(doc, indent=1, default=str) + "\n")
     print(f"wrote {OUT} ({OUT.stat().st_size} bytes)")
-    return 1 if tally.get("failed") else 0
+    return 1 if tally.get("failed") or tally.get("error") else 0
 
 
 if __name__ == "__main__":
