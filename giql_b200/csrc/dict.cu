@@ -10,8 +10,9 @@
 // name bytes in shared memory with coalesced loads, and resolves every row to a slot of a global
 // open-addressing table whose slots hold (representative row + 1).  Names of up to 16 bytes — all real
 // chromosome names — are compared as two 64-bit words against a small per-CTA cache of names already
-// resolved, so after the first few rows a lookup touches shared memory only; a cache miss (or a longer
-// name) probes the global table: one CAS claims an empty slot, otherwise the bytes are compared with the
+// resolved (256 16-byte entries; the home entry and a second, independent position are loaded and tested
+// together, so a lookup is two shared-memory loads whatever the other names hash to), so after the first
+// few rows a lookup touches shared memory only; a cache miss (or a longer name) probes the global table: one CAS claims an empty slot, otherwise the bytes are compared with the
 // representative's — exact, no reliance on hash uniqueness.  The row's slot is parked in the output array.
 // Pass 2 gathers the distinct names into a small buffer; the host sorts them (one round trip for the whole
 // call) and uploads a slot -> code table.  Pass 3 rewrites the parked slots into codes.
@@ -24,10 +25,37 @@ namespace {
 
 constexpr int DI_THREADS = 256;
 constexpr int DI_ROWS = 1024;          // rows per CTA chunk
-constexpr int DI_BYTES = 16384;        // staged name bytes per chunk (longer chunks read global memory directly)
-// (measured on the 24-name C2 tables: 8 / 9 bits 0.19 ms, 10 bits 0.152 ms against 0.160 ms at 7 — not monotone, left at 7)
+#ifndef GIQLB_DICT_V4
+#define GIQLB_DICT_V4 1                // 16-byte cache entries probed two at a time, hit test first (0: the round-1 cache; A/B switch)
+#endif
+#ifndef GIQLB_DICT_TWO_CHOICE
+#define GIQLB_DICT_TWO_CHOICE 1        // V4: the second probed entry is an independent hash position instead of the neighbour
+#endif
+#ifndef GIQLB_DICT_MAX_PROBES
+#define GIQLB_DICT_MAX_PROBES 32       // cache entries examined before a lookup goes to the global table (a FULL cache — more
+                                       // names than entries — would otherwise be scanned end to end by every miss)
+#endif
+#ifndef GIQLB_DICT_WIDE_SLOTS
+#define GIQLB_DICT_WIDE_SLOTS 0        // 1: global table slots carry the (<= 16-byte) name beside the representative row (measured:
+                                       // 3 000 names 8.5 -> 7.0 ms, but 24 names 0.130 -> 0.140 ms: three dependent L2 round trips
+                                       // where the byte comparison through the representative row runs out of L1)
+#endif
+#ifndef GIQLB_DICT_LOAD_CAP
+#define GIQLB_DICT_LOAD_CAP 0          // 1: the per-CTA cache stops inserting at half full
+#endif
+#ifndef GIQLB_DICT_STAGE_BYTES
+#define GIQLB_DICT_STAGE_BYTES 14336   // + the 6 KB cache = 43.1 KB: five CTAs per SM (names average <= 14 bytes per row, else the
+                                       // chunk is staged synchronously)
+#endif
+constexpr int DI_BYTES = GIQLB_DICT_STAGE_BYTES;   // staged name bytes per chunk (longer chunks read global memory directly)
+// Measured, 2 x 10 M rows (scripts/dict_probe.py, bench.py's dict phase): the round-1 cache (128 entries of separate key /
+// packed-word arrays, one probe loop) 0.161 ms for the 24 UCSC names, and its time moved with how those 24 names happened to hash
+// (8 / 9 bits 0.19 ms, 10 bits 0.152 ms); 194 names (alt contigs) overflowed it and took 11.7 ms, 3 000 scaffolds 11.6 ms.  Now:
+// 256 16-byte entries, the home entry and a second independent position tested together before any loop, at most 32 further
+// probes: 0.130 ms, 1.5 ms and 8.5 ms; the same with 128 entries 0.22 ms (the 24 names collide), with 512 entries and 8 KB of
+// staged bytes 0.128 ms but RefSeq-style 12-byte names then miss the staging buffer (0.65 ms against 0.30).
 #ifndef GIQLB_DICT_CACHE_BITS
-#define GIQLB_DICT_CACHE_BITS 7
+#define GIQLB_DICT_CACHE_BITS (GIQLB_DICT_V4 ? 8 : 7)
 #endif
 constexpr int DI_CACHE = 1 << GIQLB_DICT_CACHE_BITS;   // per-CTA cache entries
 constexpr int DC_MAX_ENTRIES = 4096;   // distinct names gathered in the first round trip
@@ -58,33 +86,58 @@ __device__ __forceinline__ uint64_t hash_long(const uint8_t* __restrict__ p, int
     }
     return mix64(h);
 }
-__device__ __forceinline__ uint64_t hash_global_name(const uint8_t* __restrict__ p, int len) {
-    if (len > 16) return hash_long(p, len);
-    uint64_t w[2] = {0, 0};
-    for (int i = 0; i < len; i++) w[i >> 3] |= (uint64_t)p[i] << (8 * (i & 7));
-    return hash_short(w[0], w[1], len);
-}
-
 __device__ __forceinline__ bool same_bytes(const uint8_t* __restrict__ a, const uint8_t* __restrict__ b, int len) {
     for (int i = 0; i < len; i++)
         if (a[i] != b[i]) return false;
     return true;
 }
 
-// Global table: returns the slot of the name (s, len), inserting representative row g when it is new.
+// Global table: returns the slot of the name (s, len), inserting representative row g when it is new.  A slot is DS_WORDS
+// 64-bit words — one 32-byte sector: [0] representative row + 1 (0 = free; claimed with one CAS), [1] [2] the zero-padded
+// words of a name of <= 16 bytes, [3] its length + 1, published LAST with release semantics (0 = not published, or a longer
+// name).  A short name is therefore compared against a published entry in registers, from the one sector the probe loads;
+// only unpublished entries and names longer than 16 bytes are compared byte by byte through the representative row.  (Round
+// 2, scripts/dict_probe.py: with 194 contig names — more than the per-CTA cache held — every row took the byte-by-byte
+// route, ~20 dependent global loads, and 2 x 10 M rows encoded in 11.7 ms against 0.29 ms for 24 names.)
+constexpr int DS_WORDS = GIQLB_DICT_WIDE_SLOTS ? 4 : 1;
+
+__device__ __forceinline__ void st_release_u64(unsigned long long* p, unsigned long long v) {
+    asm volatile("st.release.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+
 __device__ __forceinline__ uint32_t global_resolve(const StrTable& A, const StrTable& B, unsigned long long* __restrict__ slots,
                                                    uint32_t cap_mask, const uint8_t* __restrict__ s, int len, uint64_t h, int64_t g,
-                                                   unsigned int* __restrict__ n_distinct) {
+                                                   unsigned int* __restrict__ n_distinct, uint64_t w0, uint64_t w1) {
     uint32_t slot = (uint32_t)(h >> 24) & cap_mask;
+    const bool is_short = GIQLB_DICT_WIDE_SLOTS && len <= 16;   // the caller passes (w0, w1) for these
     for (uint32_t probes = 0; probes <= cap_mask; probes++) {
-        unsigned long long w = *(volatile unsigned long long*)&slots[slot];
+        unsigned long long* e = slots + (size_t)slot * DS_WORDS;
+        unsigned long long w = *(volatile unsigned long long*)&e[0];
         if (w == 0) {
-            unsigned long long prev = atomicCAS(&slots[slot], 0ull, (unsigned long long)g + 1ull);
+            unsigned long long prev = atomicCAS(&e[0], 0ull, (unsigned long long)g + 1ull);
             if (prev == 0) {
+                if (is_short) {
+                    *(volatile unsigned long long*)&e[1] = w0;
+                    *(volatile unsigned long long*)&e[2] = w1;
+                    st_release_u64(&e[3], (unsigned long long)len + 1ull);
+                }
                 atomicAdd(n_distinct, 1u);
                 return slot;
             }
             w = prev;
+        }
+        if (is_short) {
+            // The words are loaded only after the tag has been seen non-zero (a control dependency: the loads below are issued
+            // after this one has returned; all of them are served by the L2, the coherence point), and the writer released the
+            // tag after the words.  An acquiring load here put a fence on every lookup: +9 % on the 24-name encode.
+            const unsigned long long tag = *(volatile unsigned long long*)&e[3];
+            if (tag != 0) {                          // a published short name: exact comparison in registers
+                if (tag == (unsigned long long)len + 1ull && *(volatile unsigned long long*)&e[1] == w0 &&
+                    *(volatile unsigned long long*)&e[2] == w1)
+                    return slot;
+                slot = (slot + 1) & cap_mask;
+                continue;
+            }
         }
         const int64_t rg = (int64_t)w - 1;
         const StrTable& RT = rg >= A.n ? B : A;
@@ -96,9 +149,111 @@ __device__ __forceinline__ uint32_t global_resolve(const StrTable& A, const StrT
     return cap_mask;   // table full: cannot happen, the host keeps the load factor <= 1/2 and re-runs otherwise
 }
 
+// A name read straight from global memory (chunks that were not staged, names longer than 16 bytes).
+__device__ __forceinline__ uint32_t resolve_unstaged(const StrTable& A, const StrTable& B, unsigned long long* __restrict__ slots,
+                                                     uint32_t cap_mask, const uint8_t* __restrict__ p, int len, int64_t g,
+                                                     unsigned int* __restrict__ n_distinct) {
+    if (len > 16) return global_resolve(A, B, slots, cap_mask, p, len, hash_long(p, len), g, n_distinct, 0, 0);
+    uint64_t w[2] = {0, 0};
+    for (int i = 0; i < len; i++) w[i >> 3] |= (uint64_t)p[i] << (8 * (i & 7));
+    return global_resolve(A, B, slots, cap_mask, p, len, hash_short(w[0], w[1], len), g, n_distinct, w[0], w[1]);
+}
+
 constexpr uint32_t DI_EMPTY = 0xFFFFFFFFu, DI_PENDING = 0xFFFFFFFEu;
 constexpr uint32_t DI_SLOT_BITS = 27, DI_SLOT_MASK = (1u << DI_SLOT_BITS) - 1u;   // cache word = slot | len << 27 (len <= 16)
 
+#if GIQLB_DICT_V4
+// Per-CTA cache of resolved names, open addressing over DI_CACHE entries.  An entry is ONE 16-byte word — the name's first
+// eight bytes and the packed (global slot | len << 27) — so a probe is one shared-memory load, and a lookup loads the home
+// entry and its neighbour together and tests them for a hit before anything else: the 24 names of a genome spread over the
+// table with the odd collision, and a warp pays for the longest probe chain among its lanes.  Names of 9..16 bytes keep
+// their second word in k1.  (ncu, round 2: the probe loop was 37 % of the kernel's 162 instructions per row.)
+struct __align__(16) DictEnt {
+    unsigned long long k0;
+    uint32_t meta;             // DI_EMPTY / DI_PENDING / (global slot | len << 27)
+    uint32_t pad;
+};
+struct DictCache {
+    DictEnt e[DI_CACHE];
+    unsigned long long k1[DI_CACHE];
+    uint32_t count;            // entries filled: inserts stop at half the table, so probe chains stay short and a miss finds an
+                               // EMPTY entry after a few probes; later names are served by the global table
+};
+
+__device__ __forceinline__ uint4 lds_volatile_v4(const void* p) {
+    uint4 v;
+    asm volatile("ld.volatile.shared.v4.u32 {%0, %1, %2, %3}, [%4];"
+                 : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w)
+                 : "r"((uint32_t)__cvta_generic_to_shared(p))
+                 : "memory");
+    return v;
+}
+
+__device__ __forceinline__ void dict_cache_init(DictCache& c) {
+    // k0 = all ones: an entry whose packed word has been published always carries its own key (the key is written first,
+    // then a block-level fence, then the packed word), and an unpublished one can never pass the length test
+    for (int i = threadIdx.x; i < DI_CACHE; i += DI_THREADS) {
+        c.e[i].k0 = ~0ull;
+        c.e[i].meta = DI_EMPTY;
+        c.e[i].pad = 0;
+    }
+    if (threadIdx.x == 0) c.count = 0;
+}
+
+__device__ __forceinline__ uint32_t cached_resolve(DictCache& c, const StrTable& A, const StrTable& B, unsigned long long* __restrict__ slots,
+                                                   uint32_t cap_mask, const uint8_t* __restrict__ name, uint64_t w0, uint64_t w1, int len,
+                                                   int64_t g, unsigned int* __restrict__ n_distinct) {
+    const uint32_t lo = (uint32_t)w0, hi = (uint32_t)(w0 >> 32);
+    const uint32_t h = (lo ^ (hi * 0x9E3779B1u) ^ ((uint32_t)w1 * 0x85EBCA6Bu) ^ (uint32_t)(w1 >> 32) ^ (uint32_t)len) * 0xC2B2AE35u;
+    int ci = (int)(h >> (32 - GIQLB_DICT_CACHE_BITS));
+#if GIQLB_DICT_TWO_CHOICE
+    // second, independent position: a name whose home entry is taken goes THERE (and on linearly from there), so two names
+    // that share a home entry do not also push each other along one chain
+    int cj = (int)((h * 0x9E3779B1u) >> (32 - GIQLB_DICT_CACHE_BITS));
+    cj = cj == ci ? (ci + 1) & (DI_CACHE - 1) : cj;
+#else
+    const int cj = (ci + 1) & (DI_CACHE - 1);
+#endif
+    const uint32_t want_len = (uint32_t)len << DI_SLOT_BITS;
+    {
+        const uint4 a = lds_volatile_v4(&c.e[ci]), b = lds_volatile_v4(&c.e[cj]);
+        // EMPTY and PENDING carry 31 in the length bits: they never match a length <= 16
+        const bool hit_a = a.x == lo && a.y == hi && (a.z & ~DI_SLOT_MASK) == want_len;
+        const bool hit_b = b.x == lo && b.y == hi && (b.z & ~DI_SLOT_MASK) == want_len;
+        if (len <= 8) {
+            if (hit_a) return a.z & DI_SLOT_MASK;
+            if (hit_b) return b.z & DI_SLOT_MASK;       // an entry that carries this name and length IS this name's entry
+        } else {
+            if (hit_a && *(volatile unsigned long long*)&c.k1[ci] == w1) return a.z & DI_SLOT_MASK;
+            if (hit_b && *(volatile unsigned long long*)&c.k1[cj] == w1) return b.z & DI_SLOT_MASK;
+        }
+    }
+    int free_at = -1;
+#pragma unroll 1
+    for (int p = 0; p < (DI_CACHE < GIQLB_DICT_MAX_PROBES ? DI_CACHE : GIQLB_DICT_MAX_PROBES); p++) {
+        const uint4 a = lds_volatile_v4(&c.e[ci]);
+        if (a.z == DI_EMPTY) {
+            free_at = ci;
+            break;
+        }
+        if (a.z == DI_PENDING) break;                      // another thread is filling this entry (almost surely with this very name):
+                                                           // resolve globally and do NOT insert, or the cache fills up with duplicates
+        if ((a.z & ~DI_SLOT_MASK) == want_len && a.x == lo && a.y == hi && (len <= 8 || *(volatile unsigned long long*)&c.k1[ci] == w1))
+            return a.z & DI_SLOT_MASK;
+        ci = p == 0 ? cj : (ci + 1) & (DI_CACHE - 1);      // probe sequence: home, second position, then linearly from there
+    }
+    const uint32_t slot = global_resolve(A, B, slots, cap_mask, name, len, hash_short(w0, w1, len), g, n_distinct, w0, w1);
+    if (free_at >= 0 && slot <= DI_SLOT_MASK && (!GIQLB_DICT_LOAD_CAP || *(volatile uint32_t*)&c.count < (uint32_t)(DI_CACHE / 2)) &&
+        atomicCAS(&c.e[free_at].meta, DI_EMPTY, DI_PENDING) == DI_EMPTY) {
+        atomicAdd(&c.count, 1u);
+        *(volatile unsigned long long*)&c.e[free_at].k0 = w0;
+        *(volatile unsigned long long*)&c.k1[free_at] = w1;
+        __threadfence_block();
+        *(volatile uint32_t*)&c.e[free_at].meta = slot | want_len;
+    }
+    return slot;
+}
+#else
 // Per-CTA cache of resolved names (open addressing over DI_CACHE entries): key words + one packed word.
 struct DictCache {
     unsigned long long k0[DI_CACHE], k1[DI_CACHE];
@@ -116,7 +271,7 @@ __device__ __forceinline__ uint32_t cached_resolve(DictCache& c, const StrTable&
     const uint32_t want_len = (uint32_t)len << DI_SLOT_BITS;
     int free_at = -1;
 #pragma unroll 1
-    for (int p = 0; p < DI_CACHE; p++) {
+    for (int p = 0; p < (DI_CACHE < GIQLB_DICT_MAX_PROBES ? DI_CACHE : GIQLB_DICT_MAX_PROBES); p++) {
         const uint32_t v = *(volatile uint32_t*)&c.meta[ci];
         const unsigned long long k = c.k0[ci];             // issued together with the meta load
         if (v == DI_EMPTY) {
@@ -128,7 +283,7 @@ __device__ __forceinline__ uint32_t cached_resolve(DictCache& c, const StrTable&
         if ((v & ~DI_SLOT_MASK) == want_len && k == w0 && (len <= 8 || c.k1[ci] == w1)) return v & DI_SLOT_MASK;   // PENDING never matches: its top bits are all ones
         ci = (ci + 1) & (DI_CACHE - 1);
     }
-    const uint32_t slot = global_resolve(A, B, slots, cap_mask, name, len, hash_short(w0, w1, len), g, n_distinct);
+    const uint32_t slot = global_resolve(A, B, slots, cap_mask, name, len, hash_short(w0, w1, len), g, n_distinct, w0, w1);
     if (free_at >= 0 && slot <= DI_SLOT_MASK && atomicCAS(&c.meta[free_at], DI_EMPTY, DI_PENDING) == DI_EMPTY) {
         c.k0[free_at] = w0;
         c.k1[free_at] = w1;
@@ -137,6 +292,11 @@ __device__ __forceinline__ uint32_t cached_resolve(DictCache& c, const StrTable&
     }
     return slot;
 }
+
+__device__ __forceinline__ void dict_cache_init(DictCache& c) {
+    for (int i = threadIdx.x; i < DI_CACHE; i += DI_THREADS) c.meta[i] = DI_EMPTY;
+}
+#endif
 
 // name of <= 16 bytes at byte offset so of the staged buffer, as two zero-padded little-endian words
 __device__ __forceinline__ void staged_name(const uint8_t* s_bytes, int so, int len, uint64_t& w0, uint64_t& w1) {
@@ -150,7 +310,15 @@ __device__ __forceinline__ void staged_name(const uint8_t* s_bytes, int so, int 
         w1 = (uint64_t)__funnelshift_r(t2, t3, sh) | ((uint64_t)__funnelshift_r(t3, t4, sh) << 32);
         if (len < 16) w1 &= ~0ull >> (128 - 8 * len);
     } else {
+#if GIQLB_DICT_V4
+        // zero padding in 32-bit halves (a 64-bit variable shift is several instructions): nb bits of the name are kept
+        const uint32_t nb = 8u * (uint32_t)len;                                      // 0 .. 64
+        const uint32_t mlo = nb >= 32u ? 0xFFFFFFFFu : ((1u << nb) - 1u);
+        const uint32_t mhi = nb >= 64u ? 0xFFFFFFFFu : (nb <= 32u ? 0u : ((1u << (nb - 32u)) - 1u));
+        w0 = (uint64_t)((uint32_t)w0 & mlo) | ((uint64_t)((uint32_t)(w0 >> 32) & mhi) << 32);
+#else
         w0 = len ? w0 & (~0ull >> (64 - 8 * len)) : 0ull;
+#endif
     }
 }
 
@@ -212,7 +380,7 @@ dict_insert_kernel(StrTable A, StrTable B, unsigned long long* __restrict__ slot
     DictStage* stage = reinterpret_cast<DictStage*>(s_dyn);                 // two stages: one being read, one in flight
     DictCache& cache = *reinterpret_cast<DictCache*>(s_dyn + 2 * sizeof(DictStage));
 
-    for (int i = threadIdx.x; i < DI_CACHE; i += DI_THREADS) cache.meta[i] = DI_EMPTY;
+    dict_cache_init(cache);
     const int chunks_a = (int)((A.n + DI_ROWS - 1) / DI_ROWS), chunks_b = (int)((B.n + DI_ROWS - 1) / DI_ROWS);
     const int total = chunks_a + chunks_b, stride = gridDim.x;
     int chunk = blockIdx.x;
@@ -258,7 +426,7 @@ dict_insert_kernel(StrTable A, StrTable B, unsigned long long* __restrict__ slot
                     res[q] = (int32_t)cached_resolve(cache, A, B, slots, cap_mask, T.bytes + o[q], w0, w1, len, g0 + k + q, n_distinct);
                 } else {
                     const uint8_t* sp = T.bytes + o[q];
-                    res[q] = (int32_t)global_resolve(A, B, slots, cap_mask, sp, len, hash_global_name(sp, len), g0 + k + q, n_distinct);
+                    res[q] = (int32_t)resolve_unstaged(A, B, slots, cap_mask, sp, len, g0 + k + q, n_distinct);
                 }
             }
             reinterpret_cast<int4*>(out)[threadIdx.x] = make_int4(res[0], res[1], res[2], res[3]);
@@ -272,7 +440,7 @@ dict_insert_kernel(StrTable A, StrTable B, unsigned long long* __restrict__ slot
                     slot = cached_resolve(cache, A, B, slots, cap_mask, T.bytes + o, w0, w1, len, g0 + k, n_distinct);
                 } else {
                     const uint8_t* sp = T.bytes + o;
-                    slot = global_resolve(A, B, slots, cap_mask, sp, len, hash_global_name(sp, len), g0 + k, n_distinct);
+                    slot = resolve_unstaged(A, B, slots, cap_mask, sp, len, g0 + k, n_distinct);
                 }
                 out[k] = (int32_t)slot;
             }
@@ -300,7 +468,7 @@ __global__ void dict_collect_kernel(StrTable A, StrTable B, const unsigned long 
                                     int32_t* __restrict__ ent /* [3][max_entries]: slot, offset, length */, uint32_t max_entries) {
     uint32_t slot = blockIdx.x * blockDim.x + threadIdx.x;
     if (slot >= cap) return;
-    unsigned long long w = slots[slot];
+    unsigned long long w = slots[(size_t)slot * DS_WORDS];
     if (w == 0) return;
     const int64_t rg = (int64_t)w - 1;
     const StrTable& RT = rg >= A.n ? B : A;
@@ -394,7 +562,7 @@ int giqlb_dict_encode_async(giqlb_ctx* ctx, const int32_t* offs_l, const uint8_t
     StrTable A{offs_l, bytes_l, n_l}, B{offs_r, bytes_r, n_r};
     unsigned long long* cursor = reinterpret_cast<unsigned long long*>(ctx->d_scalars + 24);
     unsigned int* n_distinct = reinterpret_cast<unsigned int*>(ctx->d_scalars + 26);
-    int st = dev_alloc(ctx, &p->slots, (size_t)p->cap);
+    int st = dev_alloc(ctx, &p->slots, (size_t)p->cap * DS_WORDS);
     if (st == GIQLB_OK) st = dev_alloc(ctx, &p->name_buf, p->name_cap);
     if (st == GIQLB_OK) st = dev_alloc(ctx, &p->ent, 3 * (size_t)p->max_entries);
     if (st == GIQLB_OK) st = dev_alloc(ctx, &p->slot2code, (size_t)p->cap);
@@ -404,10 +572,10 @@ int giqlb_dict_encode_async(giqlb_ctx* ctx, const int32_t* offs_l, const uint8_t
         giqlb_dict_finish(ctx, p, nullptr, nullptr);
         return st;
     }
-    cudaMemsetAsync(p->slots, 0, (size_t)p->cap * 8, ctx->stream);
+    cudaMemsetAsync(p->slots, 0, (size_t)p->cap * DS_WORDS * 8, ctx->stream);
     cudaMemsetAsync(p->slot2code, 0xFF, (size_t)p->cap * 4, ctx->stream);
     cudaMemsetAsync(cursor, 0, 3 * 8, ctx->stream);
-    const int64_t chunks = ceil_div(n_l, DI_ROWS) + ceil_div(n_r, DI_ROWS), cap_blocks = (int64_t)ctx->sm_count * 5;   // 5 CTAs of 43.6 KB shared memory are resident per SM
+    const int64_t chunks = ceil_div(n_l, DI_ROWS) + ceil_div(n_r, DI_ROWS), cap_blocks = (int64_t)ctx->sm_count * 5;   // 5 CTAs of 43.1 KB shared memory are resident per SM
     const unsigned grid = (unsigned)(chunks < cap_blocks ? chunks : cap_blocks);
     {
         PhaseSpan ps(ctx, GIQLB_PH_DICT);
@@ -506,7 +674,7 @@ extern "C" int giqlb_dict_encode(giqlb_ctx* ctx, const int32_t* offs_l, const ui
     int st = GIQLB_OK;
     uint32_t cap = 1u << 14;
     size_t max_entries = DC_MAX_ENTRIES, name_cap = DC_NAME_CAP;
-    const int64_t chunks = ceil_div(n_l, DI_ROWS) + ceil_div(n_r, DI_ROWS), cap_blocks = (int64_t)ctx->sm_count * 5;   // 5 CTAs of 43.6 KB shared memory are resident per SM
+    const int64_t chunks = ceil_div(n_l, DI_ROWS) + ceil_div(n_r, DI_ROWS), cap_blocks = (int64_t)ctx->sm_count * 5;   // 5 CTAs of 43.1 KB shared memory are resident per SM
     const unsigned grid = (unsigned)(chunks < cap_blocks ? chunks : cap_blocks);
     std::vector<uint8_t> h_names;
     std::vector<int32_t> h_ent;
@@ -517,11 +685,11 @@ extern "C" int giqlb_dict_encode(giqlb_ctx* ctx, const int32_t* offs_l, const ui
     for (int round = 0; round < 4; round++) {
         dev_free(ctx, slots); dev_free(ctx, name_buf); dev_free(ctx, ent);
         slots = nullptr; name_buf = nullptr; ent = nullptr;
-        st = dev_alloc(ctx, &slots, (size_t)cap);
+        st = dev_alloc(ctx, &slots, (size_t)cap * DS_WORDS);
         if (st == GIQLB_OK) st = dev_alloc(ctx, &name_buf, name_cap);
         if (st == GIQLB_OK) st = dev_alloc(ctx, &ent, 3 * max_entries);
         if (st != GIQLB_OK) break;
-        cudaMemsetAsync(slots, 0, (size_t)cap * 8, ctx->stream);
+        cudaMemsetAsync(slots, 0, (size_t)cap * DS_WORDS * 8, ctx->stream);
         cudaMemsetAsync(cursor, 0, 3 * 8, ctx->stream);
         {
             PhaseSpan ps(ctx, GIQLB_PH_DICT);
