@@ -302,6 +302,21 @@ def replay_duckdb(backend):
     results = []
     log: list = []
     install_duckdb_stubs(backend, log)
+    try:   # the reference's hypothesis properties run derandomised: the same examples every time, so a replay is repeatable
+        import hypothesis
+
+        hypothesis.settings.register_profile("giqlb_replay", derandomize=True, database=None)
+        hypothesis.settings.load_profile("giqlb_replay")
+    except ImportError:
+        hypothesis = None
+    try:
+        return _replay_duckdb_modules(backend, log, results, UnsupportedQuery)
+    finally:
+        if hypothesis is not None:
+            hypothesis.settings.load_profile("default")
+
+
+def _replay_duckdb_modules(backend, log, results, UnsupportedQuery):
     for modname in DUCKDB_MODULES:
         mod = importlib.import_module(modname)
         src = modname.replace(".", "/") + ".py"
