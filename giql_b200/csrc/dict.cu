@@ -165,9 +165,10 @@ constexpr uint32_t DI_SLOT_BITS = 27, DI_SLOT_MASK = (1u << DI_SLOT_BITS) - 1u; 
 #if GIQLB_DICT_V4
 // Per-CTA cache of resolved names, open addressing over DI_CACHE entries.  An entry is ONE 16-byte word — the name's first
 // eight bytes and the packed (global slot | len << 27) — so a probe is one shared-memory load, and a lookup loads the home
-// entry and its neighbour together and tests them for a hit before anything else: the 24 names of a genome spread over the
-// table with the odd collision, and a warp pays for the longest probe chain among its lanes.  Names of 9..16 bytes keep
-// their second word in k1.  (ncu, round 2: the probe loop was 37 % of the kernel's 162 instructions per row.)
+// entry and a second, independently hashed entry together and tests them for a hit before anything else: the 24 names of a
+// genome spread over the table with the odd collision, and a warp pays for the longest probe chain among its lanes.  Names
+// of 9..16 bytes keep their second word in k1.  (ncu, round 2: the probe loop was 37 % of the kernel's 162 instructions per
+// row; with this cache the kernel executes 75.7 M warp instructions instead of 98.5 M, profiles/r02s_kernels.csv.)
 struct __align__(16) DictEnt {
     unsigned long long k0;
     uint32_t meta;             // DI_EMPTY / DI_PENDING / (global slot | len << 27)
@@ -176,8 +177,8 @@ struct __align__(16) DictEnt {
 struct DictCache {
     DictEnt e[DI_CACHE];
     unsigned long long k1[DI_CACHE];
-    uint32_t count;            // entries filled: inserts stop at half the table, so probe chains stay short and a miss finds an
-                               // EMPTY entry after a few probes; later names are served by the global table
+    uint32_t count;            // entries filled; with GIQLB_DICT_LOAD_CAP inserts stop at half the table (measured: no gain, the
+                               // bound on the probe sequence below is what keeps a full cache cheap)
 };
 
 __device__ __forceinline__ uint4 lds_volatile_v4(const void* p) {
