@@ -281,6 +281,10 @@ class _Parser:
                     break
         if self.accept("kw", "LIMIT"):
             q["limit"] = self.take("num")
+        q["offset"] = 0
+        if self.at("id") and self.peek()[1].upper() == "OFFSET":
+            self.take("id")
+            q["offset"] = self.take("num")
         return q
 
     def source(self):
@@ -436,6 +440,11 @@ class _Parser:
     def projection(self):
         if self.accept("op", "*"):
             return {"kind": "star", "alias": None}
+        if self.at("num") or self.at("str"):                               # a literal select-list item: `1 AS extra`, `'x' AS tag`
+            item = {"kind": "const", "value": self.take()}
+            if self.accept("kw", "AS"):
+                item["name"] = self.take("id")
+            return item
         if self.at("id") and self.at("op", "(", 1):
             fn = self.take("id").upper()
             if fn == "DISTANCE":
@@ -478,6 +487,15 @@ class _Parser:
             op = self.take("op")
             return {"kind": "distance_cmp", **d, "op": op, "value": self.take("num")}
         left = self.column_ref()
+        if self.at("id") and self.peek()[1].upper() == "BETWEEN":
+            self.take("id")
+            if not (self.at("num") or self.at("str")):
+                raise UnsupportedQuery("BETWEEN takes literal bounds")
+            lo = self.take()
+            self.take("kw", "AND")
+            if not (self.at("num") or self.at("str")):
+                raise UnsupportedQuery("BETWEEN takes literal bounds")
+            return {"kind": "between", "col": left, "lo": lo, "hi": self.take()}
         if self.accept("kw", "IS"):
             neg = self.accept("kw", "NOT")
             self.take("kw", "NULL")
@@ -1101,6 +1119,9 @@ class Session:
                 keep = per_row == len(ranges) if w["quant"] == "ALL" else per_row > 0
             ix = f.idx[alias]
             f.take((ix >= 0) & keep[np.maximum(ix, 0)] if len(keep) else np.zeros(len(ix), bool))
+        elif w["kind"] == "between":                                   # col BETWEEN lo AND hi == col >= lo AND col <= hi
+            self._filter(f, {"kind": "compare_literal", "op": ">=", "col": w["col"], "value": w["lo"]})
+            self._filter(f, {"kind": "compare_literal", "op": "<=", "col": w["col"], "value": w["hi"]})
         elif w["kind"] == "distance_cmp":
             for a in (w["a"], w["b"]):
                 if a not in f.rels:
@@ -1198,6 +1219,11 @@ class Session:
                 cols.append(p.get("name", p["col"]))
                 arrays.append(f.column(a, p["col"]))
                 sources.append((a, p["col"]))
+            elif p["kind"] == "const":
+                v = p["value"]
+                cols.append(p.get("name", str(v)))
+                arrays.append(np.full(len(f), v, dtype=object if isinstance(v, str) else np.int64))
+                sources.append(None)
             elif p["kind"] == "cluster":
                 ids = _cluster_ids(be, f, p)                            # over the rows the FROM clause produced
                 cols.append(p.get("name", "cluster"))
@@ -1272,6 +1298,7 @@ class Session:
             else:
                 perm = np.argsort(key, kind="stable")
             res = res.take(perm)
-        if q["limit"] is not None:
-            res = res.take(slice(0, q["limit"]))
+        off = q.get("offset") or 0
+        if q["limit"] is not None or off:
+            res = res.take(slice(off, None if q["limit"] is None else off + q["limit"]))
         return res
