@@ -20,6 +20,13 @@ test_cluster.py, tests/expanders/test_merge.py).  For those a stand-in ``duckdb`
 executemany, the stand-in ``transpile`` returns an opaque plan token, and ``conn.execute(token)`` runs the GIQL query on the
 front-end.  A test that looks INSIDE the SQL text (``"SET VARIABLE" in sql``, EXPLAIN, column types) is ``not_replayable``.
 
+The bedtools suite (tests/integration/bedtools/test_{cluster,merge,distance,nearest,strand_aware,intersect}.py) compares GIQL
+with the ``bedtools`` binary through ``utils/bedtools_wrapper.py`` (pybedtools).  Neither is installed, so the wrapper module is
+replaced by a stand-in written from bedtools' documented behaviour — ``merge`` (overlapping or book-ended features, ``-s``),
+``intersect`` (``-u``, ``-v``, ``-wa -wb``, ``-loj``, ``-c``; ``-s`` / ``-S``; at least one shared base), ``closest -d -t first
+[-k] [-s|-S]`` (0 for overlap, gap + 1 otherwise) — an implementation independent of this repo's oracle and engine.  Options the
+stand-in does not model (overlap fractions, ``-wo``) make the test ``not_replayable``.
+
 Modules replayed through ``giql_query``: cluster_predicate/test_cluster_predicate.py, coordinate_space/test_{distance,nearest,disjoin}_
 coordinate_space.py, bedtools/test_contains.py, bedtools/test_within.py.  The other bedtools tests compare with the
 ``bedtools`` binary at run time (absent here) and are not replayable.  ``giql`` itself is not importable (sqlglot is
@@ -49,6 +56,12 @@ MODULES = [
     "tests.integration.bedtools.test_within",
 ]
 DUCKDB_MODULES = [
+    "tests.integration.bedtools.test_cluster",
+    "tests.integration.bedtools.test_merge",
+    "tests.integration.bedtools.test_distance",
+    "tests.integration.bedtools.test_nearest",
+    "tests.integration.bedtools.test_strand_aware",
+    "tests.integration.bedtools.test_intersect",
     "tests.test_duckdb_iejoin",
     "tests.test_intersects_join",
     "tests.expanders.test_cluster",
@@ -240,6 +253,92 @@ class FakeConn:
         return FakeResult(res.columns, rows)
 
 
+def _bedtools_standin():
+    """``tests.integration.bedtools.utils.bedtools_wrapper`` without pybedtools: BED semantics restated (see module docstring)."""
+    mod = types.ModuleType("tests.integration.bedtools.utils.bedtools_wrapper")
+
+    class BedtoolsError(Exception):
+        pass
+
+    def norm(iv):                                    # what a BED6 round trip through bedtools does to a tuple
+        iv = tuple(iv)
+        if len(iv) == 3:
+            return (iv[0], int(iv[1]), int(iv[2]), None, None, None)
+        c, s, e, name, score, strand = iv[:6]
+        return (c, int(s), int(e), None if name in (None, ".") else name, 0 if score is None else int(score),
+                None if strand in (None, ".") else strand)
+
+    def overlap(a, b):
+        return a[0] == b[0] and a[1] < b[2] and b[1] < a[2]
+
+    def strands_ok(a, b, mode):
+        if mode == "same":                           # an unknown strand ('.') matches nothing under -s
+            return a[5] is not None and a[5] == b[5]
+        if mode == "opposite":
+            return a[5] is not None and b[5] is not None and a[5] != b[5]
+        return True
+
+    def merge(intervals, strand_mode=None):
+        rows = sorted(norm(i) for i in intervals)
+        groups = {}
+        for r in rows:
+            groups.setdefault((r[0], r[5] if strand_mode == "same" else None), []).append(r)
+        out = []
+        for (chrom, _), g in groups.items():
+            cur_s, cur_e = g[0][1], g[0][2]
+            for r in g[1:]:
+                if r[1] <= cur_e:                    # overlapping or book-ended
+                    cur_e = max(cur_e, r[2])
+                else:
+                    out.append((chrom, cur_s, cur_e))
+                    cur_s, cur_e = r[1], r[2]
+            out.append((chrom, cur_s, cur_e))
+        return sorted(out)
+
+    def intersect(intervals_a, intervals_b, strand_mode=None, *, loj=False, inverse=False, write_both=False, count=False,
+                  write_overlap=False, write_all_overlap=False, fraction_a=None, fraction_b=None, reciprocal=False):
+        if write_overlap or write_all_overlap or fraction_a is not None or fraction_b is not None or reciprocal:
+            raise NotReplayable("bedtools intersect option outside the stand-in (-wo / -wao / -f / -F / -r)")
+        A, B = [norm(i) for i in intervals_a], [norm(i) for i in intervals_b]
+        out = []
+        for a in A:
+            hits = [b for b in B if overlap(a, b) and strands_ok(a, b, strand_mode)]
+            if loj:
+                out.extend(a + b for b in hits) if hits else out.append(a + (None,) * 6)
+            elif inverse:
+                if not hits:
+                    out.append(a)
+            elif write_both:
+                out.extend(a + b for b in hits)
+            elif count:
+                out.append(a + (len(hits),))
+            elif hits:
+                out.append(a)
+        return out
+
+    def closest(intervals_a, intervals_b, strand_mode=None, k=1):
+        A, B = sorted(norm(i) for i in intervals_a), sorted(norm(i) for i in intervals_b)
+        out = []
+        for a in A:
+            cand = []
+            for pos, b in enumerate(B):
+                if b[0] != a[0] or not strands_ok(a, b, strand_mode):
+                    continue
+                d = 0 if overlap(a, b) else (b[1] - a[2] + 1 if b[1] >= a[2] else a[1] - b[2] + 1)
+                cand.append((d, pos, b))
+            if not cand:
+                raise NotReplayable("bedtools closest without a candidate on the chromosome prints '.' fields")
+            cand.sort(key=lambda t: (t[0], t[1]))
+            if k == 1:
+                out.append(a + cand[0][2] + (cand[0][0],))                       # -t first
+            else:
+                out.extend(a + b + (d,) for d, _, b in cand[:k])
+        return out
+
+    mod.BedtoolsError, mod.merge, mod.intersect, mod.closest = BedtoolsError, merge, intersect, closest
+    return mod
+
+
 def install_duckdb_stubs(backend, log):
     """``duckdb.connect`` -> FakeConn, ``giql.transpile`` / ``giql.transpile.transpile`` -> plan tokens."""
     duckdb = types.ModuleType("duckdb")
@@ -256,6 +355,7 @@ def install_duckdb_stubs(backend, log):
             raise NotReplayable(f"transpile keyword {sorted(kw)} has no counterpart here")
         return PlanToken({"query": query, "tables": [_table_spec(t) for t in (tables or [])], "dialect": dialect})
 
+    sys.modules["tests.integration.bedtools.utils.bedtools_wrapper"] = _bedtools_standin()
     giql = sys.modules["giql"]
     mod = types.ModuleType("giql.transpile")
     mod.transpile = transpile
@@ -283,6 +383,15 @@ def _resolve_fixture(mod, name, backend, log, cache):
     if name == "conn" or name == "duckdb_connection":
         cache[name] = FakeConn(backend, log)
         return cache[name]
+    if name == "giql_query":                        # tests/integration/bedtools/conftest.py:34-61 on the stand-in connection
+        conn = _resolve_fixture(mod, "duckdb_connection", backend, log, cache)
+
+        def giql_query(query, *, tables, **table_data):
+            for tname, intervals in table_data.items():
+                conn.tables[tname] = {"columns": COLUMNS, "rows": [tuple(i.to_tuple() if hasattr(i, "to_tuple") else i) for i in intervals]}
+            return conn.execute(sys.modules["giql"].transpile(query, tables=tables, dialect="duckdb")).fetchall()
+        cache[name] = giql_query
+        return giql_query
     obj = getattr(mod, name, None)
     if obj is None:
         raise NotReplayable(f"fixture {name}")
