@@ -62,6 +62,8 @@ DUCKDB_MODULES = [
     "tests.integration.bedtools.test_nearest",
     "tests.integration.bedtools.test_strand_aware",
     "tests.integration.bedtools.test_intersect",
+    "tests.integration.bedtools.test_intersect_property",
+    "tests.integration.bedtools.test_nearest_property",
     "tests.test_duckdb_iejoin",
     "tests.test_intersects_join",
     "tests.expanders.test_cluster",
