@@ -64,6 +64,8 @@ DUCKDB_MODULES = [
     "tests.integration.bedtools.test_intersect",
     "tests.integration.bedtools.test_intersect_property",
     "tests.integration.bedtools.test_nearest_property",
+    "tests.integration.datafusion.test_cross_target_oracle",
+    "tests.integration.datafusion.test_cross_target_encodings",
     "tests.test_duckdb_iejoin",
     "tests.test_intersects_join",
     "tests.expanders.test_cluster",
@@ -99,6 +101,7 @@ def install_reference_stubs():
     giql.transpile = transpile
     for pkg, path in [("tests", REF / "tests"), ("tests.integration", REF / "tests/integration"),
                       ("tests.expanders", REF / "tests/expanders"),
+                      ("tests.integration.datafusion", REF / "tests/integration/datafusion"),
                       ("tests.integration.cluster_predicate", REF / "tests/integration/cluster_predicate"),
                       ("tests.integration.coordinate_space", REF / "tests/integration/coordinate_space"),
                       ("tests.integration.bedtools", REF / "tests/integration/bedtools"),
@@ -358,6 +361,7 @@ def install_duckdb_stubs(backend, log):
         return PlanToken({"query": query, "tables": [_table_spec(t) for t in (tables or [])], "dialect": dialect})
 
     sys.modules["tests.integration.bedtools.utils.bedtools_wrapper"] = _bedtools_standin()
+    sys.modules.setdefault("datafusion", types.ModuleType("datafusion"))     # importorskip() only: nothing of it is called
     giql = sys.modules["giql"]
     mod = types.ModuleType("giql.transpile")
     mod.transpile = transpile
@@ -385,6 +389,21 @@ def _resolve_fixture(mod, name, backend, log, cache):
     if name == "conn" or name == "duckdb_connection":
         cache[name] = FakeConn(backend, log)
         return cache[name]
+    if name == "cross_target_oracle":               # tests/integration/conftest.py:62-160: rows compared with `expected` in the
+        normalize = importlib.import_module("tests.integration._oracle").normalize      # reference's own normal form
+
+        def oracle(query, *, expected, tables=None, columns=(("chrom", "utf8"), ("start", "int64"), ("end", "int64")),
+                   targets=("generic", "datafusion", "duckdb"), engines=None, **table_data):
+            specs = [_table_spec(t) for t in (tables if tables is not None else list(table_data))]
+            cols = [c[0] for c in columns]
+            data = {tname: {"columns": cols, "rows": [list(r) for r in rows]} for tname, rows in table_data.items()}
+            rows = run_query(backend, query, specs, data)
+            log.append({"query": query, "tables": specs, "data": data, "rows": [list(r) for r in rows]})
+            got, want = normalize(rows), normalize(expected)
+            assert got == want, f"rows differ from the expected set: got {got[:6]}, expected {want[:6]}"
+            return {t: got for t in targets}
+        cache[name] = oracle
+        return oracle
     if name == "giql_query":                        # tests/integration/bedtools/conftest.py:34-61 on the stand-in connection
         conn = _resolve_fixture(mod, "duckdb_connection", backend, log, cache)
 
@@ -467,7 +486,7 @@ def _replay_duckdb_modules(backend, log, results, UnsupportedQuery):
                         entry["outcome"], entry["calls"] = f"failed: {str(e)[:300]}", [dict(c) for c in log[-2:]]
                     except _pytest_outcomes.OutcomeException as e:   # pytest.raises(...) around transpile(): a transpile-time check
                         entry["outcome"] = f"not_replayable: expects a transpile-time outcome ({str(e)[:80]})"
-                    except ModuleNotFoundError as e:             # datafusion / pybedtools back ends of the same test
+                    except ImportError as e:                     # datafusion / pybedtools back ends of the same test
                         entry["outcome"] = f"not_replayable: {e}"
                     except BaseExceptionGroup as e:              # hypothesis: several distinct failures
                         subs = list(e.exceptions)
