@@ -1172,11 +1172,18 @@ class Session:
         if "merge" in kinds:
             # src/giql/expanders/merge.py:183-439: (chrom[, strand], start, end[, COUNT(*)]), default ORDER BY chrom, start
             m = next(p for p in proj if p["kind"] == "merge")
-            if any(p["kind"] not in ("merge", "count_star") for p in proj) or q["distinct"]:
-                raise UnsupportedQuery("MERGE is bound for `SELECT MERGE(interval...)[, COUNT(*)] FROM t`")
             g = f.genomic(f.order[0])
             if m["stranded"] and "strand" not in g:
                 raise ValueError("MERGE(stranded := true) needs a strand column")
+            # the partition keys may be named beside MERGE and in a GROUP BY — `SELECT chrom, MERGE(interval) FROM t GROUP BY chrom`:
+            # the reference folds them into its own grouping and emits each once (merge.py:320-439); anything else changes the
+            # grouping and belongs to the SQL engine
+            cfg = f.rels[f.order[0]].config or Table("t")
+            keys = {cfg.chrom_col.lower()} | ({cfg.strand_col.lower()} if m["stranded"] and cfg.strand_col else set())
+            is_key = lambda p: p["kind"] == "col" and p["col"].lower() in keys and p.get("name", p["col"]).lower() == p["col"].lower()
+            if any(p["kind"] not in ("merge", "count_star") and not is_key(p) for p in proj) or q["distinct"] or \
+                    any(c.lower() not in keys for _, c in q.get("group") or []):
+                raise UnsupportedQuery("MERGE is bound for `SELECT [chrom, [strand,]] MERGE(interval...)[, COUNT(*)] FROM t [GROUP BY chrom[, strand]]`")
             if m.get("predicate") and len(f):
                 # merge.py:201-239: MERGE is GROUP BY chrom[, strand], cluster id over the predicate-gated CLUSTER; the ids come
                 # from the engine, the (small) aggregation is finished here
@@ -1192,7 +1199,10 @@ class Session:
             width = 4 if m["stranded"] else 3
             out = [tuple(r[:width]) + ((r[-1],) if "count_star" in kinds else ()) for r in rows]
             out.sort(key=lambda r: (r[0], r[width - 2]))
-            cols = ["chrom"] + (["strand"] if m["stranded"] else []) + ["start", "end"] + (["count"] if "count_star" in kinds else [])
+            # the regions carry the table's own column names (merge.py:302-307: MIN(start) AS <start_col>, MAX(end) AS <end_col>)
+            count_name = next((p.get("name", "count") for p in proj if p["kind"] == "count_star"), None)
+            cols = [cfg.chrom_col] + ([cfg.strand_col] if m["stranded"] else []) + [cfg.start_col, cfg.end_col] + \
+                   ([count_name] if count_name is not None else [])
             return self._order_limit(q, Result(cols, [_column([r[i] for r in out]) for i in range(len(cols))]), f)
         if q.get("group"):
             return self._group_count(q, f)
