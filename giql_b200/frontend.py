@@ -19,7 +19,8 @@ Recognised shapes (GIQL semantics cited per branch in :class:`Session`):
 * ``SELECT ..., CLUSTER(interval[, d][, stranded := true]) AS c FROM t``; ``SELECT MERGE(interval[, d][, stranded := true])[, COUNT(*)] FROM t``
 * ``FROM DISJOIN(t[, ref])``;  ``WITH name AS (SELECT * FROM t) ...``;  a derived table ``FROM (<query>) alias``
 * ``SELECT <left cols>, COUNT(*) | COUNT(y.col) FROM a x [LEFT] JOIN b y ON x.interval INTERSECTS y.interval GROUP BY <left cols>``
-  (count_overlaps: one per-row count probe, no pair list); any other ``GROUP BY cols`` with ``COUNT`` over the joined rows
+  (count_overlaps: one per-row count probe, no pair list); any other ``GROUP BY cols`` with ``COUNT / SUM / MIN / MAX / AVG /
+  COUNT(DISTINCT)`` over the joined rows and ``HAVING <aggregate> <op> <number> [AND ...]``
 * residual ON-conjuncts ``AND x.col <op> y.col`` (same / opposite strand joins), ``WHERE col <op> col | literal``
 * ``CLUSTER / MERGE(interval, predicate := col <op> PREV(col))`` and conjunctions of such equalities
 * projections ``*``, ``x.*``, ``[x.]col [AS name]``, ``DISTANCE(x.interval, y.interval[, ...]) [AS name]``; ``DISTINCT``;
@@ -40,6 +41,7 @@ from .ranges import parse_range
 from .table import Table, canonical_offsets
 
 
+_AGGREGATES = ("COUNT", "SUM", "MIN", "MAX", "AVG")
 _CROSS_JOIN_LIMIT = 1 << 24     # rows of `FROM a, b` without any join predicate the front-end will materialise
 
 
@@ -267,8 +269,20 @@ class _Parser:
                 q["group"].append(self.column_ref())
                 if not self.accept("op", ","):
                     break
-            if self.at("kw", "HAVING") or (self.at("id") and self.peek()[1].upper() == "HAVING"):
-                raise UnsupportedQuery("HAVING is finished by the SQL engine")
+            q["having"] = []
+            if self.at("id") and self.peek()[1].upper() == "HAVING":
+                # HAVING <aggregate> <op> <number> [AND ...]: a filter over the groups
+                self.take("id")
+                while True:
+                    if not (self.at("id") and self.peek()[1].upper() in _AGGREGATES and self.at("op", "(", 1)):
+                        raise UnsupportedQuery("HAVING compares aggregates with numbers; anything else is finished by the SQL engine")
+                    item = self.aggregate_args(self.take("id").upper())
+                    op = self.take("op")
+                    if not self.at("num"):
+                        raise UnsupportedQuery("HAVING compares aggregates with numbers; anything else is finished by the SQL engine")
+                    q["having"].append({"item": item, "op": op, "value": self.take("num")})
+                    if not self.accept("kw", "AND"):
+                        break
         if self.accept("kw", "ORDER"):
             self.take("kw", "BY")
             while True:
@@ -437,6 +451,24 @@ class _Parser:
             raise UnsupportedQuery("DISTANCE takes two <alias>.interval operands")
         return {"a": a[0], "b": b[0], "stranded": _bool_arg(args.get("stranded"), "stranded"), "signed": _bool_arg(args.get("signed"), "signed")}
 
+    def aggregate_args(self, fn: str) -> dict:
+        """`( * | [DISTINCT] col )` after COUNT / SUM / MIN / MAX / AVG: the aggregates of the reference's IEJoin whitelist
+        (src/giql/expanders/intersects_duckdb.py:618-804 lets GROUP BY + aggregates + HAVING through to the fast path)"""
+        self.take("op", "(")
+        if fn == "COUNT" and self.accept("op", "*"):
+            item = {"kind": "count_star"}
+        else:
+            distinct = self.accept("kw", "DISTINCT")
+            ref = self.column_ref()
+            if fn == "COUNT" and not distinct:
+                item = {"kind": "count_col", "alias": ref[0], "col": ref[1]}
+            else:
+                if distinct and fn != "COUNT":
+                    raise UnsupportedQuery(f"{fn}(DISTINCT ...) is finished by the SQL engine")
+                item = {"kind": "agg", "fn": "COUNT_DISTINCT" if distinct else fn, "alias": ref[0], "col": ref[1]}
+        self.take("op", ")")
+        return item
+
     def projection(self):
         if self.accept("op", "*"):
             return {"kind": "star", "alias": None}
@@ -463,14 +495,8 @@ class _Parser:
                         "stranded": _bool_arg(args.get("stranded"), "stranded"), "predicate": args.get("predicate")}
                 if item["predicate"] is not None and not isinstance(item["predicate"], dict):
                     raise ValueError("predicate := must be a comparison")
-            elif fn == "COUNT":
-                self.take("op", "(")
-                if self.accept("op", "*"):
-                    item = {"kind": "count_star"}
-                else:
-                    ref = self.column_ref()
-                    item = {"kind": "count_col", "alias": ref[0], "col": ref[1]}
-                self.take("op", ")")
+            elif fn in _AGGREGATES:
+                item = self.aggregate_args(fn)
             else:
                 raise UnsupportedQuery(f"function {fn} is not handled by the built-in front-end")
         else:
@@ -1044,12 +1070,45 @@ class Session:
         return self._order_limit(q, Result(out_cols, arrays, sources), f)
 
     def _group_count(self, q, f: _Frame) -> Result:
-        """generic GROUP BY <columns> with COUNT(*) / COUNT(col) over the joined rows"""
+        """generic GROUP BY <columns> with COUNT / SUM / MIN / MAX / AVG over the joined rows, and HAVING over the groups (the
+        aggregation the reference's fast path leaves to DuckDB around the pair relation, intersects_duckdb.py:1339-1400)"""
         keys = [(f.resolve(a, c), c) for a, c in q["group"]]
         key_cols = [f.column(a, c).tolist() for a, c in keys]
         groups: dict[tuple, list[int]] = {}
         for i, key in enumerate(zip(*key_cols)) if key_cols else []:
             groups.setdefault(key, []).append(i)
+        members = [np.asarray(v, dtype=np.int64) for v in groups.values()]
+
+        def aggregate(p) -> np.ndarray:
+            if p["kind"] == "count_star":
+                return np.asarray([len(v) for v in members], dtype=np.int64)
+            a = f.resolve(p["alias"], p["col"])
+            vals = f.column(a, p["col"])
+            if p["kind"] == "count_col":
+                present = np.array([v is not None for v in vals], dtype=bool) if vals.dtype == object else np.ones(len(vals), bool)
+                return np.asarray([int(present[v].sum()) for v in members], dtype=np.int64)
+            if p["fn"] in ("SUM", "AVG") and vals.dtype.kind not in "iufb" and any(isinstance(x, str) for x in vals.tolist()):
+                raise ValueError(f"{p['fn']} needs a numeric column, {p['col']!r} holds strings")
+            out = []
+            for v in members:                                         # NULLs are skipped; no value at all -> NULL (COUNT: 0)
+                xs = [x for x in vals[v].tolist() if x is not None]
+                fn = p["fn"]
+                if fn == "COUNT_DISTINCT":
+                    out.append(len(set(xs)))
+                elif not xs:
+                    out.append(None)
+                elif fn == "SUM":
+                    out.append(sum(xs))
+                elif fn == "MIN":
+                    out.append(min(xs))
+                elif fn == "MAX":
+                    out.append(max(xs))
+                else:
+                    out.append(sum(xs) / len(xs))                     # AVG is a DOUBLE
+            if p["fn"] == "AVG" and all(x is not None for x in out):
+                return np.asarray(out, dtype=np.float64)
+            return _column(out)
+
         out_cols, arrays, sources = [], [], []
         for p in q["proj"]:
             sources.append(None)
@@ -1061,18 +1120,24 @@ class Session:
                 out_cols.append(p.get("name", p["col"]))
                 arrays.append(_column([key[k] for key in groups]))
                 sources[-1] = (a, p["col"])
-            elif p["kind"] == "count_star":
-                out_cols.append(p.get("name", "count"))
-                arrays.append(np.asarray([len(v) for v in groups.values()], dtype=np.int64))
-            elif p["kind"] == "count_col":
-                a = f.resolve(p["alias"], p["col"])
-                vals = f.column(a, p["col"])
-                present = np.array([v is not None for v in vals], dtype=bool) if vals.dtype == object else np.ones(len(vals), bool)
-                out_cols.append(p.get("name", "count"))
-                arrays.append(np.asarray([int(present[v].sum()) for v in groups.values()], dtype=np.int64))
+            elif p["kind"] in ("count_star", "count_col", "agg"):
+                default = "count" if p["kind"] != "agg" else p["fn"].lower()
+                out_cols.append(p.get("name", default))
+                arrays.append(aggregate(p))
             else:
-                raise UnsupportedQuery("GROUP BY supports grouped columns and COUNT only; other aggregates are finished by the SQL engine")
-        return self._order_limit(q, Result(out_cols, arrays, sources), f)
+                raise UnsupportedQuery("GROUP BY supports grouped columns and COUNT / SUM / MIN / MAX / AVG; other expressions are finished by the SQL engine")
+        res = Result(out_cols, arrays, sources)
+        for h in q.get("having") or []:
+            if h["op"] not in _CMP:
+                raise UnsupportedQuery(f"HAVING comparison {h['op']}")
+            vals = aggregate(h["item"])
+            if vals.dtype == object:
+                keep = np.array([x is not None and bool(_CMP[h["op"]](x, h["value"])) for x in vals.tolist()], dtype=bool)
+            else:
+                keep = _CMP[h["op"]](vals, h["value"])
+            res = res.take(keep)
+            members = [m for m, k in zip(members, keep.tolist()) if k]
+        return self._order_limit(q, res, f)
 
     def _join_nearest(self, q, f: _Frame, j):
         """src/giql/expanders/nearest.py:336-397 — one engine call per NEAREST, joined back on the query row"""

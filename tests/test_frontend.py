@@ -116,8 +116,9 @@ def test_parse_shapes():
 
 
 @pytest.mark.parametrize("q", [
-    "SELECT a.name, SUM(b.start) FROM peaks a JOIN genes b ON a.interval INTERSECTS b.interval GROUP BY a.name",
-    "SELECT a.name, COUNT(*) FROM peaks a JOIN genes b ON a.interval INTERSECTS b.interval GROUP BY a.name HAVING COUNT(*) > 1",
+    "SELECT a.name, SUM(b.start + 1) FROM peaks a JOIN genes b ON a.interval INTERSECTS b.interval GROUP BY a.name",
+    "SELECT a.name, COUNT(*) FROM peaks a JOIN genes b ON a.interval INTERSECTS b.interval GROUP BY a.name HAVING COUNT(*) > a.name",
+    "SELECT a.name, SUM(DISTINCT b.start) FROM peaks a JOIN genes b ON a.interval INTERSECTS b.interval GROUP BY a.name",
     "SELECT a.name, a.start, COUNT(*) FROM peaks a JOIN genes b ON a.interval INTERSECTS b.interval GROUP BY a.name",
     "SELECT name FROM peaks WHERE start + 1 > 100",
     "SELECT upper(name) FROM peaks",
@@ -279,6 +280,32 @@ def test_residual_join_predicates_against_brute_force():
     want = sorted((N["name"][i], G["name"][j]) for i in range(40) for j in range(60)
                   if overlap(N, i, G, j) and N["strand"][i] is not None and N["strand"][i] != G["strand"][j])
     assert sorted(got) == want
+
+
+def test_group_by_aggregates_and_having_against_brute_force():
+    s = sessions(OracleBackend())
+    P, G = make(11, 90), make(12, 60)
+    pairs = [(i, j) for i in range(90) for j in range(60) if overlap(P, i, G, j)]
+    by = {}
+    for i, j in pairs:
+        by.setdefault(P["name"][i], []).append(j)
+    got = s.execute("SELECT a.name, COUNT(*) AS n, SUM(b.start) AS s, MIN(b.start) AS lo, MAX(b.\"end\") AS hi, AVG(b.start) AS m, "
+                    "COUNT(DISTINCT b.chrom) AS d FROM peaks a JOIN genes b ON a.interval INTERSECTS b.interval GROUP BY a.name")
+    assert got.columns == ["name", "n", "s", "lo", "hi", "m", "d"]
+    want = {k: (len(v), sum(G["start"][j] for j in v), min(G["start"][j] for j in v), max(G["end"][j] for j in v),
+                sum(G["start"][j] for j in v) / len(v), len({G["chrom"][j] for j in v})) for k, v in by.items()}
+    assert {r[0]: tuple(r[1:]) for r in got.rows} == want
+    # HAVING filters the groups; several conditions are AND-ed
+    got = s.execute("SELECT a.name, COUNT(*) AS n FROM peaks a JOIN genes b ON a.interval INTERSECTS b.interval "
+                    "GROUP BY a.name HAVING COUNT(*) >= 2 AND SUM(b.start) < 100000 ORDER BY n DESC, name LIMIT 5")
+    keep = sorted(((k, len(v)) for k, v in by.items() if len(v) >= 2 and sum(G["start"][j] for j in v) < 100000), key=lambda r: (-r[1], r[0]))
+    assert got.rows == keep[:5]
+    # aggregates over the NULL side of a LEFT JOIN skip the NULLs: SUM / MIN are NULL for unmatched rows, COUNT(col) is 0
+    got = s.execute("SELECT a.name, SUM(b.start) AS s, COUNT(b.start) AS n FROM peaks a LEFT JOIN genes b ON a.interval INTERSECTS b.interval GROUP BY a.name")
+    rows = {r[0]: r[1:] for r in got.rows}
+    assert len(rows) == 90 and all(rows[f"f{i}"] == ((sum(G["start"][j] for j in by[f"f{i}"]), len(by[f"f{i}"])) if f"f{i}" in by else (None, 0)) for i in range(90))
+    with pytest.raises(ValueError):
+        s.execute("SELECT a.name, SUM(b.name) FROM peaks a JOIN genes b ON a.interval INTERSECTS b.interval GROUP BY a.name")
 
 
 def test_cross_join_standalone_nearest_and_set_predicates_against_brute_force():
