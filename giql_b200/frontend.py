@@ -17,7 +17,7 @@ Recognised shapes (GIQL semantics cited per branch in :class:`Session`):
 * ``FROM a x JOIN b y ON x.chrom = y.chrom WHERE DISTANCE(x.interval, y.interval[, ...]) < n``; the plain cross join
   ``FROM a x, b y`` / ``a x CROSS JOIN b y`` feeding ``DISTANCE`` in the select list (bounded product)
 * ``SELECT ..., CLUSTER(interval[, d][, stranded := true]) AS c FROM t``; ``SELECT MERGE(interval[, d][, stranded := true])[, COUNT(*)] FROM t``
-* ``FROM DISJOIN(t[, ref])``;  ``WITH name AS (SELECT * FROM t) ...``;  a derived table ``FROM (<query>) alias``
+* ``FROM DISJOIN(t[, reference := r | (<query>)])``;  ``WITH name AS (SELECT * FROM t) ...``;  a derived table ``FROM (<query>) alias``
 * ``SELECT <left cols>, COUNT(*) | COUNT(y.col) FROM a x [LEFT] JOIN b y ON x.interval INTERSECTS y.interval GROUP BY <left cols>``
   (count_overlaps: one per-row count probe, no pair list); any other ``GROUP BY cols`` with ``COUNT / SUM / MIN / MAX / AVG /
   COUNT(DISTINCT)`` over the joined rows and ``HAVING <aggregate> <op> <number> [AND ...]``
@@ -339,9 +339,13 @@ class _Parser:
                 if key != "reference":
                     raise ValueError(f"DISJOIN got unexpected named argument(s): {key}. Valid arguments: reference.")
                 self.take("op")
-                if self.at("op", "("):
-                    raise UnsupportedQuery("DISJOIN with a subquery reference is finished by the SQL engine")
-                ref = self.take("id")
+                if self.accept("op", "("):
+                    # reference := (<query>): the subquery's chrom / start / end columns are the reference set, read as canonical
+                    # 0-based half-open coordinates — a derived relation has no Table encoding (disjoin.py:255-270)
+                    ref = {"subquery": self.query()}
+                    self.take("op", ")")
+                else:
+                    ref = self.take("id")
             self.take("op", ")")
             return {"kind": "disjoin", "table": target, "reference": ref, "alias": self.alias() or target}
         return {"kind": "table", "table": name, "alias": self.alias() or name}
@@ -909,7 +913,13 @@ class Session:
         if src["kind"] == "disjoin":
             # DISJOIN(t[, ref])   (src/giql/expanders/disjoin.py:102-202; output in the target's encoding, :139-141)
             t = self._relation(q, {"kind": "table", "table": src["table"]})
-            ref = self._relation(q, {"kind": "table", "table": src["reference"]}) if src["reference"] else None
+            if isinstance(src["reference"], dict):
+                sub = src["reference"]["subquery"]
+                sub.setdefault("ctes", {})
+                sub["ctes"] = {**q["ctes"], **sub["ctes"]}
+                ref = self._derived(self._run(sub))
+            else:
+                ref = self._relation(q, {"kind": "table", "table": src["reference"]}) if src["reference"] else None
             sadj, eadj = canonical_offsets(t.config)
             segs = []
             if len(t) and (ref is None or len(ref)):
