@@ -11,6 +11,8 @@ Recognised shapes (GIQL semantics cited per branch in :class:`Session`):
 
 * ``FROM a [x] [INNER|LEFT|SEMI|ANTI] JOIN b [y] ON x.interval INTERSECTS|CONTAINS|WITHIN y.interval`` and the comma form
   ``FROM a x, b y WHERE x.interval INTERSECTS y.interval``
+* the same join with the overlap predicate spelled out over any columns, ``ON x.chrom = y.c AND x.start < y.e AND x.end > y.s``
+  (what the generic expander writes for INTERSECTS), also against ``DISJOIN(...)`` as a join source
 * ``FROM t WHERE interval INTERSECTS|CONTAINS|WITHIN 'chr1:100-200'`` and ``... INTERSECTS|CONTAINS|WITHIN ANY|ALL(...)``
 * ``FROM a x CROSS JOIN LATERAL NEAREST(b, reference := x.interval[, k, max_distance, stranded, signed]) [y]`` (repeatable);
   the standalone placement ``FROM NEAREST(b, reference := 'chr1:350-360'[, k, max_distance, signed]) [y]``
@@ -948,7 +950,11 @@ class Session:
             if j["kind"] == "nearest":
                 self._join_nearest(q, f, j)
                 continue
-            right = self._relation(q, j["source"])
+            if j["source"]["kind"] == "disjoin":                      # `... JOIN DISJOIN(t[, ref]) AS d ON ...`: the segments as a relation
+                right = self._derived(self._run({"distinct": False, "proj": [{"kind": "star", "alias": None}], "joins": [], "where": [],
+                                                 "order": [], "limit": None, "offset": 0, "group": [], "source": j["source"], "ctes": q["ctes"]}))
+            else:
+                right = self._relation(q, j["source"])
             ra, la = j["source"]["alias"], f.order[0]
             left = f.rels[la]
             conds, kind = list(j.get("on") or []), j["kind"]
@@ -971,6 +977,17 @@ class Session:
                 n_left = len(f)
                 f.take(np.repeat(np.arange(n_left), len(right)))
                 f.add(ra, right, np.tile(np.arange(len(right), dtype=np.int64), n_left))
+                continue
+            overlap = self._literal_overlap_join(f, right, ra, compares) if not spatial and kind in ("inner", "left") else None
+            if overlap is not None:
+                # `ON x.chrom = y.chrom AND x.start < y.end AND x.end > y.start` over any three columns of each side: the predicate
+                # the generic expander writes for INTERSECTS (src/giql/expanders/intersects.py:149-154), spelled out by the user —
+                # e.g. DISJOIN's segments joined back to an annotation table.  Raw columns: no coordinate canonicalisation.
+                Lg, Rg = overlap
+                l, r = _pairs(be, Lg, Rg, "intersects", None, None) if len(f) and len(right) else (np.zeros(0, np.int64),) * 2
+                rep, rrow = _expand(np.arange(len(f), dtype=np.int64), l, r, keep_unmatched=(kind == "left"))
+                f.take(rep)
+                f.add(ra, right, rrow)
                 continue
             if not spatial:
                 # chromosome equi-join feeding DISTANCE (docs/dialect/distance-operators.rst:130-155): quadratic by nature
@@ -1018,6 +1035,42 @@ class Session:
         for w in where:
             self._filter(f, w)
         return self._finish(q, f)
+
+    @staticmethod
+    def _literal_overlap_join(f: _Frame, right: _Rel, ra: str, compares):
+        """Recognises the three-conjunct overlap predicate between the rows joined so far and table ``ra``; returns the two
+        (chrom, start, end) column sets — the left one aligned with the frame's rows — or None."""
+        if len(compares) != 3:
+            return None
+        flip = {"<": ">", ">": "<", "=": "="}
+        eq = lt = gt = None
+        for c in compares:
+            (la_, lc), (ra_, rc), op = c["left"], c["right"], c["op"]
+            if op not in flip or la_ is None or ra_ is None:
+                return None
+            if la_ == ra and ra_ != ra:                                  # orient: frame side first
+                la_, lc, ra_, rc, op = ra_, rc, la_, lc, flip[op]
+            if ra_ != ra or la_ == ra or la_ not in f.rels or rc not in right.data:
+                return None
+            if not (lc in f.extra[la_] or lc in f.rels[la_].data):
+                return None
+            slot = {"=": "eq", "<": "lt", ">": "gt"}[op]
+            if slot == "eq" and eq is None:
+                eq = (la_, lc, rc)
+            elif slot == "lt" and lt is None:
+                lt = (la_, lc, rc)                                       # frame.start < right.end
+            elif slot == "gt" and gt is None:
+                gt = (la_, lc, rc)                                       # frame.end > right.start
+            else:
+                return None
+        if eq is None or lt is None or gt is None:
+            return None
+        Lg = {"chrom": f.column(eq[0], eq[1]), "start": f.column(lt[0], lt[1]), "end": f.column(gt[0], gt[1])}
+        Rg = {"chrom": right.data[eq[2]], "start": right.data[gt[2]], "end": right.data[lt[2]]}
+        for g in (Lg, Rg):
+            if len(g["chrom"]) and (g["start"].dtype.kind not in "iu" or g["end"].dtype.kind not in "iu" or any(v is None for v in g["chrom"].tolist())):
+                return None                                              # NULLs or non-integer coordinates: the SQL engine's business
+        return Lg, Rg
 
     def _count_overlaps(self, q, f: _Frame, where) -> Optional[Result]:
         """The count_overlaps shape (src/giql/expanders/intersects_duckdb.py:432-548, 806-854):
