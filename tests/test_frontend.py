@@ -308,6 +308,27 @@ def test_group_by_aggregates_and_having_against_brute_force():
         s.execute("SELECT a.name, SUM(b.name) FROM peaks a JOIN genes b ON a.interval INTERSECTS b.interval GROUP BY a.name")
 
 
+def test_spelled_out_overlap_predicate_is_the_interval_join():
+    s = sessions(OracleBackend())
+    P, G = make(11, 90), make(12, 60)
+    want = sorted((f"f{i}", f"f{j}") for i in range(90) for j in range(60) if overlap(P, i, G, j))
+    spatial = sorted(s.execute("SELECT a.name, b.name FROM peaks a JOIN genes b ON a.interval INTERSECTS b.interval").rows)
+    assert spatial == want
+    for on in ("a.chrom = b.chrom AND a.start < b.\"end\" AND a.\"end\" > b.start",
+               "b.start < a.\"end\" AND b.chrom = a.chrom AND b.\"end\" > a.start"):          # either orientation, any order
+        assert sorted(s.execute(f"SELECT a.name, b.name FROM peaks a JOIN genes b ON {on}").rows) == want
+    left = s.execute("SELECT a.name, b.name FROM peaks a LEFT JOIN genes b ON a.chrom = b.chrom AND a.start < b.\"end\" AND a.\"end\" > b.start").rows
+    hit = {a for a, _ in want}
+    assert sorted(r for r in left if r[1] is not None) == want and sorted(r[0] for r in left if r[1] is None) == sorted(f"f{i}" for i in range(90) if f"f{i}" not in hit)
+    # closed comparisons are a different predicate: left to the SQL engine
+    with pytest.raises(UnsupportedQuery):
+        s.execute("SELECT a.name FROM peaks a JOIN genes b ON a.chrom = b.chrom AND a.start <= b.\"end\" AND a.\"end\" >= b.start")
+    # DISJOIN's segments joined back to their parents: every segment lies inside at least its own row
+    rows = s.execute("SELECT d.disjoin_start, d.disjoin_end, t.start, t.\"end\" FROM DISJOIN(peaks) AS d JOIN peaks AS t "
+                     "ON t.chrom = d.disjoin_chrom AND t.start < d.disjoin_end AND t.\"end\" > d.disjoin_start").rows
+    assert rows and all(ts < de and te > ds for ds, de, ts, te in rows)
+
+
 def test_cross_join_standalone_nearest_and_set_predicates_against_brute_force():
     s = sessions(OracleBackend())
     P, G = make(11, 90), make(12, 60)
