@@ -143,7 +143,8 @@ class EngineBackend:
 
 
 # ---- tokenizer / parser -------------------------------------------------------------------------------------------------
-_TOKEN = re.compile(r"""\s*(?:(?P<str>'(?:[^']|'')*')|(?P<qid>"[^"]*")|(?P<num>-?\d+)|(?P<op>:=|=>|<=|>=|<>|!=|[(),.*=<>;])|(?P<id>[A-Za-z_][A-Za-z_0-9]*))""")
+_TOKEN = re.compile(r"""\s*(?:(?P<str>'(?:[^']|'')*')|(?P<qid>"[^"]*")|(?P<num>-?\d+(?:\.\d+)?)|(?P<op>:=|=>|<=|>=|<>|!=|[(),.*=<>;])|(?P<id>[A-Za-z_][A-Za-z_0-9]*))""")
+_COMMENT = re.compile(r"('(?:[^']|'')*'|\"[^\"]*\")|--[^\n]*")
 _KEYWORDS = {"SELECT", "DISTINCT", "FROM", "WHERE", "JOIN", "INNER", "LEFT", "SEMI", "ANTI", "CROSS", "LATERAL", "ON", "AS", "AND",
              "ORDER", "BY", "LIMIT", "DESC", "ASC", "WITH", "INTERSECTS", "CONTAINS", "WITHIN", "ANY", "ALL", "SOME", "IS", "NULL", "NOT",
              "OUTER", "GROUP"}
@@ -151,7 +152,7 @@ _KEYWORDS = {"SELECT", "DISTINCT", "FROM", "WHERE", "JOIN", "INNER", "LEFT", "SE
 
 def _tokenize(text: str):
     out, pos = [], 0
-    text = text.strip().rstrip(";")
+    text = _COMMENT.sub(lambda m: m.group(1) or " ", text).strip().rstrip(";")   # `-- ...` comments (string literals are kept)
     while pos < len(text):
         m = _TOKEN.match(text, pos)
         if not m or m.end() == pos:
@@ -162,7 +163,7 @@ def _tokenize(text: str):
         elif m.group("qid") is not None:
             out.append(("id", m.group("qid")[1:-1]))
         elif m.group("num") is not None:
-            out.append(("num", int(m.group("num"))))
+            out.append(("num", float(m.group("num")) if "." in m.group("num") else int(m.group("num"))))
         elif m.group("op") is not None:
             out.append(("op", m.group("op")))
         else:
@@ -296,19 +297,21 @@ class _Parser:
                 if not self.accept("op", ","):
                     break
         if self.accept("kw", "LIMIT"):
-            q["limit"] = self.take("num")
+            q["limit"] = _int_arg(self.take("num"), "LIMIT")
         q["offset"] = 0
         if self.at("id") and self.peek()[1].upper() == "OFFSET":
             self.take("id")
-            q["offset"] = self.take("num")
+            q["offset"] = _int_arg(self.take("num"), "OFFSET")
         return q
 
     def source(self):
         if self.accept("op", "("):
             sub = self.query()
             self.take("op", ")")
-            self.accept("kw", "AS")
-            return {"kind": "subquery", "query": sub, "alias": self.take("id")}
+            had_as = self.accept("kw", "AS")
+            named = had_as or (self.at("id") and self.peek()[1].upper() not in ("OFFSET", "HAVING"))
+            alias = self.take("id") if named else f"__subquery{self.i}"                    # `FROM (<query>)` without a name
+            return {"kind": "subquery", "query": sub, "alias": alias}
         name = self.take("id")
         if name.upper() == "NEAREST" and self.at("op", "("):
             # standalone placement: `FROM NEAREST(target, reference := 'chr1:350-360', k := 2)` — the literal range is the one
@@ -513,12 +516,34 @@ class _Parser:
         return item
 
     def condition(self):
+        if self.accept("kw", "NOT"):
+            # `WHERE NOT interval INTERSECTS ANY(...)` (docs/dialect/quantifiers.rst): the literal-range predicates can be negated
+            inner = self.condition()
+            if inner["kind"] != "literal":
+                raise UnsupportedQuery("NOT is bound for predicates against literal ranges")
+            inner["negated"] = not inner.get("negated", False)
+            return inner
         if self.at("id") and self.peek()[1].upper() == "DISTANCE" and self.at("op", "(", 1):
             self.take("id")
             d = self.distance_call()
             op = self.take("op")
             return {"kind": "distance_cmp", **d, "op": op, "value": self.take("num")}
         left = self.column_ref()
+        negated_in = self.at("kw", "NOT") and self.at("id", None, 1) and self.peek(1)[1].upper() == "IN"
+        if negated_in or (self.at("id") and self.peek()[1].upper() == "IN"):
+            if negated_in:
+                self.take("kw", "NOT")
+            self.take("id")
+            self.take("op", "(")
+            values = []
+            while True:
+                if not (self.at("num") or self.at("str")):
+                    raise UnsupportedQuery("IN takes a list of literals")
+                values.append(self.take())
+                if not self.accept("op", ","):
+                    break
+            self.take("op", ")")
+            return {"kind": "in_list", "col": left, "values": values, "negated": bool(negated_in)}
         if self.at("id") and self.peek()[1].upper() == "BETWEEN":
             self.take("id")
             if not (self.at("num") or self.at("str")):
@@ -1245,8 +1270,16 @@ class Session:
                 hit, _ = _pairs(be, rel.genomic(), lit, w["op"], rel.config, None)
                 per_row = np.bincount(np.asarray(hit, dtype=np.int64), minlength=len(rel))
                 keep = per_row == len(ranges) if w["quant"] == "ALL" else per_row > 0
+            if w.get("negated"):
+                keep = ~keep
             ix = f.idx[alias]
             f.take((ix >= 0) & keep[np.maximum(ix, 0)] if len(keep) else np.zeros(len(ix), bool))
+        elif w["kind"] == "in_list":                                   # col [NOT] IN (literals); a NULL operand drops the row either way
+            col = f.column(f.resolve(*w["col"]), w["col"][1])
+            values = set(w["values"])
+            hit = np.fromiter((x in values for x in col.tolist()), dtype=bool, count=len(col))
+            known = np.fromiter((x is not None for x in col.tolist()), dtype=bool, count=len(col))
+            f.take(known & (hit != w["negated"]))
         elif w["kind"] == "between":                                   # col BETWEEN lo AND hi == col >= lo AND col <= hi
             self._filter(f, {"kind": "compare_literal", "op": ">=", "col": w["col"], "value": w["lo"]})
             self._filter(f, {"kind": "compare_literal", "op": "<=", "col": w["col"], "value": w["hi"]})
@@ -1276,7 +1309,7 @@ class Session:
                 raise UnsupportedQuery(f"comparison {op}")
             lc = w["left"] if w["kind"] == "compare" else w["col"]
             a = f.column(f.resolve(*lc), lc[1])
-            b = f.column(f.resolve(*w["right"]), w["right"][1]) if w["kind"] == "compare" else np.full(len(a), w["value"], dtype=object if isinstance(w["value"], str) else np.int64)
+            b = f.column(f.resolve(*w["right"]), w["right"][1]) if w["kind"] == "compare" else np.full(len(a), w["value"], dtype=object if isinstance(w["value"], str) else np.float64 if isinstance(w["value"], float) else np.int64)
             if a.dtype == object or b.dtype == object:
                 fn = {"<": lambda x, y: x < y, "<=": lambda x, y: x <= y, ">": lambda x, y: x > y, ">=": lambda x, y: x >= y,
                       "=": lambda x, y: x == y, "!=": lambda x, y: x != y}[op]
