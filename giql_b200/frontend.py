@@ -25,8 +25,9 @@ Recognised shapes (GIQL semantics cited per branch in :class:`Session`):
   COUNT(DISTINCT)`` over the joined rows and ``HAVING <aggregate> <op> <number> [AND ...]``
 * residual ON-conjuncts ``AND x.col <op> y.col`` (same / opposite strand joins), ``WHERE col <op> col | literal``
 * ``CLUSTER / MERGE(interval, predicate := col <op> PREV(col))`` and conjunctions of such equalities
-* projections ``*``, ``x.*``, ``[x.]col [AS name]``, ``DISTANCE(x.interval, y.interval[, ...]) [AS name]``; ``DISTINCT``;
-  ``ORDER BY col [DESC]``; ``LIMIT n``
+* projections ``*``, ``x.*``, ``[x.]col [AS name]``, ``DISTANCE(x.interval, y.interval[, ...]) [AS name]``, literals and arithmetic
+  (``end - start AS length``, ``LEAST`` / ``GREATEST`` / ``ABS``) — also inside aggregates and WHERE comparisons; ``DISTINCT``;
+  ``ORDER BY col [DESC]``; ``LIMIT n [OFFSET m]``; ``col BETWEEN a AND b``, ``col [NOT] IN (...)``, ``NOT <literal-range predicate>``
 
 A *backend* supplies the operators on plain dict tables (``{"chrom": [...], "start": [...], "end": [...], ...}``):
 :class:`EngineBackend` is the product (CUDA through the C ABI); the test-suite plugs its CPU oracle in the same seat.
@@ -143,7 +144,7 @@ class EngineBackend:
 
 
 # ---- tokenizer / parser -------------------------------------------------------------------------------------------------
-_TOKEN = re.compile(r"""\s*(?:(?P<str>'(?:[^']|'')*')|(?P<qid>"[^"]*")|(?P<num>-?\d+(?:\.\d+)?)|(?P<op>:=|=>|<=|>=|<>|!=|[(),.*=<>;])|(?P<id>[A-Za-z_][A-Za-z_0-9]*))""")
+_TOKEN = re.compile(r"""\s*(?:(?P<str>'(?:[^']|'')*')|(?P<qid>"[^"]*")|(?P<num>-?\d+(?:\.\d+)?)|(?P<op>:=|=>|<=|>=|<>|!=|[(),.*=<>;+\-/])|(?P<id>[A-Za-z_][A-Za-z_0-9]*))""")
 _COMMENT = re.compile(r"('(?:[^']|'')*'|\"[^\"]*\")|--[^\n]*")
 _KEYWORDS = {"SELECT", "DISTINCT", "FROM", "WHERE", "JOIN", "INNER", "LEFT", "SEMI", "ANTI", "CROSS", "LATERAL", "ON", "AS", "AND",
              "ORDER", "BY", "LIMIT", "DESC", "ASC", "WITH", "INTERSECTS", "CONTAINS", "WITHIN", "ANY", "ALL", "SOME", "IS", "NULL", "NOT",
@@ -163,7 +164,12 @@ def _tokenize(text: str):
         elif m.group("qid") is not None:
             out.append(("id", m.group("qid")[1:-1]))
         elif m.group("num") is not None:
-            out.append(("num", float(m.group("num")) if "." in m.group("num") else int(m.group("num"))))
+            text_num = m.group("num")
+            if text_num[0] == "-" and out and (out[-1][0] in ("num", "str") or out[-1] == ("op", ")") or
+                                               (out[-1][0] == "id" and out[-1][1].upper() not in ("BETWEEN", "IN", "OFFSET", "HAVING"))):
+                out.append(("op", "-"))                                   # `a -5`, `(x) -1`: binary minus, not a signed literal
+                text_num = text_num[1:]
+            out.append(("num", float(text_num) if "." in text_num else int(text_num)))
         elif m.group("op") is not None:
             out.append(("op", m.group("op")))
         else:
@@ -460,6 +466,51 @@ class _Parser:
             raise UnsupportedQuery("DISTANCE takes two <alias>.interval operands")
         return {"a": a[0], "b": b[0], "stranded": _bool_arg(args.get("stranded"), "stranded"), "signed": _bool_arg(args.get("signed"), "signed")}
 
+    # arithmetic over columns and numbers — `end - start`, `0.5 * (a.end - a.start)`, LEAST / GREATEST — as the reference's
+    # recipes write it (docs/recipes/*.rst: SUM(end - start) coverage, overlap-fraction filters)
+    def at_arith(self) -> bool:
+        return self.at("op", "+") or self.at("op", "-") or self.at("op", "*") or self.at("op", "/")
+
+    def expr(self, first=None):
+        left = self.term(first)
+        while self.at("op", "+") or self.at("op", "-"):
+            op = self.take("op")
+            left = ("bin", op, left, self.term())
+        return left
+
+    def term(self, first=None):
+        left = first if first is not None else self.factor()
+        while self.at("op", "*") or self.at("op", "/"):
+            op = self.take("op")
+            left = ("bin", op, left, self.factor())
+        return left
+
+    def factor(self):
+        if self.accept("op", "-"):
+            return ("neg", self.factor())
+        if self.accept("op", "("):
+            e = self.expr()
+            self.take("op", ")")
+            return e
+        if self.at("num"):
+            return ("num", self.take("num"))
+        if self.at("id") and self.at("op", "(", 1):
+            fn = self.take("id").upper()
+            if fn not in ("LEAST", "GREATEST", "ABS"):
+                raise UnsupportedQuery(f"function {fn} is not handled by the built-in front-end")
+            self.take("op", "(")
+            args = [self.expr()]
+            while self.accept("op", ","):
+                args.append(self.expr())
+            self.take("op", ")")
+            if fn == "ABS" and len(args) != 1:
+                raise ValueError("ABS takes one argument")
+            return ("fn", fn, args)
+        ref = self.column_ref()
+        if ref[1] == "*":
+            raise UnsupportedQuery("`*` is not an operand")
+        return ("col", ref[0], ref[1])
+
     def aggregate_args(self, fn: str) -> dict:
         """`( * | [DISTINCT] col )` after COUNT / SUM / MIN / MAX / AVG: the aggregates of the reference's IEJoin whitelist
         (src/giql/expanders/intersects_duckdb.py:618-804 lets GROUP BY + aggregates + HAVING through to the fast path)"""
@@ -468,21 +519,31 @@ class _Parser:
             item = {"kind": "count_star"}
         else:
             distinct = self.accept("kw", "DISTINCT")
-            ref = self.column_ref()
-            if fn == "COUNT" and not distinct:
-                item = {"kind": "count_col", "alias": ref[0], "col": ref[1]}
+            e = self.expr()
+            if e[0] != "col":                                             # SUM(end - start)
+                if distinct or fn == "COUNT":
+                    raise UnsupportedQuery(f"{fn}({'DISTINCT ' if distinct else ''}<expression>) is finished by the SQL engine")
+                item = {"kind": "agg", "fn": fn, "alias": None, "col": "<expression>", "expr": e}
+            elif fn == "COUNT" and not distinct:
+                item = {"kind": "count_col", "alias": e[1], "col": e[2]}
             else:
                 if distinct and fn != "COUNT":
                     raise UnsupportedQuery(f"{fn}(DISTINCT ...) is finished by the SQL engine")
-                item = {"kind": "agg", "fn": "COUNT_DISTINCT" if distinct else fn, "alias": ref[0], "col": ref[1]}
+                item = {"kind": "agg", "fn": "COUNT_DISTINCT" if distinct else fn, "alias": e[1], "col": e[2]}
         self.take("op", ")")
         return item
 
     def projection(self):
         if self.accept("op", "*"):
             return {"kind": "star", "alias": None}
-        if self.at("num") or self.at("str"):                               # a literal select-list item: `1 AS extra`, `'x' AS tag`
-            item = {"kind": "const", "value": self.take()}
+        if self.at("str") or (self.at("num") and not (self.at("op", "+", 1) or self.at("op", "-", 1) or self.at("op", "*", 1) or self.at("op", "/", 1))):
+            item = {"kind": "const", "value": self.take()}                 # a literal select-list item: `1 AS extra`, `'x' AS tag`
+            if self.accept("kw", "AS"):
+                item["name"] = self.take("id")
+            return item
+        if self.at("num") or self.at("op", "(") or self.at("op", "-") or \
+                (self.at("id") and self.at("op", "(", 1) and self.peek()[1].upper() in ("LEAST", "GREATEST", "ABS")):
+            item = {"kind": "expr", "expr": self.expr()}
             if self.accept("kw", "AS"):
                 item["name"] = self.take("id")
             return item
@@ -511,11 +572,16 @@ class _Parser:
         else:
             ref = self.column_ref()
             item = {"kind": "star", "alias": ref[0]} if ref[1] == "*" else {"kind": "col", "alias": ref[0], "col": ref[1]}
+            if item["kind"] == "col" and self.at_arith():                  # `end - start AS length`
+                item = {"kind": "expr", "expr": self.expr(("col", ref[0], ref[1]))}
         if self.accept("kw", "AS"):
             item["name"] = self.take("id")
         return item
 
     def condition(self):
+        if self.at("num") or self.at("op", "(") or self.at("op", "-") or \
+                (self.at("id") and self.at("op", "(", 1) and self.peek()[1].upper() in ("LEAST", "GREATEST", "ABS")):
+            return self.expr_comparison(self.expr())                       # `( LEAST(a.end, b.end) - GREATEST(a.start, b.start) ) >= ...`
         if self.accept("kw", "NOT"):
             # `WHERE NOT interval INTERSECTS ANY(...)` (docs/dialect/quantifiers.rst): the literal-range predicates can be negated
             inner = self.condition()
@@ -529,6 +595,8 @@ class _Parser:
             op = self.take("op")
             return {"kind": "distance_cmp", **d, "op": op, "value": self.take("num")}
         left = self.column_ref()
+        if self.at_arith():                                               # `disjoin_end - disjoin_start >= 50`
+            return self.expr_comparison(self.expr(("col", left[0], left[1])))
         negated_in = self.at("kw", "NOT") and self.at("id", None, 1) and self.peek(1)[1].upper() == "IN"
         if negated_in or (self.at("id") and self.peek()[1].upper() == "IN"):
             if negated_in:
@@ -576,10 +644,20 @@ class _Parser:
                 raise UnsupportedQuery("spatial predicates compare two genomic columns or a column and a literal range")
             return {"kind": "spatial", "op": op, "left": left[0], "right": right[0]}
         op = self.take("op")
-        if self.at("num") or self.at("str"):
+        if self.at("str") or (self.at("num") and not (self.at("op", "+", 1) or self.at("op", "-", 1) or self.at("op", "*", 1) or self.at("op", "/", 1))):
             return {"kind": "compare_literal", "op": op, "col": left, "value": self.take()}
+        if self.at("num") or self.at("op", "(") or self.at("op", "-") or (self.at("id") and self.at("op", "(", 1)):
+            return {"kind": "compare_expr", "op": op, "left": ("col", left[0], left[1]), "right": self.expr()}
         right = self.column_ref()
+        if self.at_arith():
+            return {"kind": "compare_expr", "op": op, "left": ("col", left[0], left[1]), "right": self.expr(("col", right[0], right[1]))}
         return {"kind": "compare", "op": op, "left": left, "right": right}
+
+    def expr_comparison(self, left):
+        op = self.take("op")
+        if op in ("+", "-", "*", "/", "(", ")", ",", "."):
+            raise UnsupportedQuery(f"expected a comparison, found {op!r}")
+        return {"kind": "compare_expr", "op": op, "left": left, "right": self.expr()}
 
 
 def parse(query: str) -> dict:
@@ -858,6 +936,44 @@ def _cluster_ids(be, f, p) -> np.ndarray:
     lists = {k: v.tolist() for k, v in g.items()}
     ids = be.cluster(lists, p["distance"], p["stranded"], pred) if pred else be.cluster(lists, p["distance"], p["stranded"])
     return np.asarray(ids, dtype=np.int64)
+
+
+def _eval_expr(f: "_Frame", e) -> np.ndarray:
+    """An arithmetic expression over the frame's rows.  NULL operands give NULL (object column with None); integer arithmetic
+    stays in int64, `/` is a DOUBLE division as in DuckDB."""
+    kind = e[0]
+    if kind == "num":
+        return np.full(len(f), e[1], dtype=np.float64 if isinstance(e[1], float) else np.int64)
+    if kind == "col":
+        return f.column(f.resolve(e[1], e[2]), e[2])
+    if kind == "neg":
+        return _arith("-", np.zeros(len(f), np.int64), _eval_expr(f, e[1]))
+    if kind == "bin":
+        return _arith(e[1], _eval_expr(f, e[2]), _eval_expr(f, e[3]))
+    if kind == "fn":
+        args = [_eval_expr(f, a) for a in e[2]]
+        if e[1] == "ABS":
+            return _arith("abs", args[0], args[0])
+        out = args[0]
+        for a in args[1:]:
+            out = _arith("min" if e[1] == "LEAST" else "max", out, a)
+        return out
+    raise UnsupportedQuery(f"expression node {kind}")
+
+
+def _arith(op: str, a: np.ndarray, b: np.ndarray) -> np.ndarray:
+    fns = {"+": np.add, "-": np.subtract, "*": np.multiply, "/": np.true_divide, "min": np.minimum, "max": np.maximum,
+           "abs": lambda x, _: np.abs(x)}
+    if a.dtype != object and b.dtype != object:
+        if a.dtype.kind not in "iuf" or b.dtype.kind not in "iuf":
+            raise ValueError(f"arithmetic needs numeric operands, got {a.dtype} and {b.dtype}")
+        return fns[op](a, b)
+    py = {"+": lambda x, y: x + y, "-": lambda x, y: x - y, "*": lambda x, y: x * y, "/": lambda x, y: x / y, "min": min, "max": max,
+          "abs": lambda x, _: abs(x)}[op]
+    try:                                                                  # NULL in, NULL out
+        return _column([None if x is None or y is None else py(x, y) for x, y in zip(a.tolist(), b.tolist())])
+    except TypeError as exc:
+        raise ValueError(f"arithmetic needs numeric operands: {exc}") from None
 
 
 class Session:
@@ -1165,13 +1281,14 @@ class Session:
         groups: dict[tuple, list[int]] = {}
         for i, key in enumerate(zip(*key_cols)) if key_cols else []:
             groups.setdefault(key, []).append(i)
+        if not keys:
+            groups[()] = list(range(len(f)))                               # the global aggregate: one row, also over no rows
         members = [np.asarray(v, dtype=np.int64) for v in groups.values()]
 
         def aggregate(p) -> np.ndarray:
             if p["kind"] == "count_star":
                 return np.asarray([len(v) for v in members], dtype=np.int64)
-            a = f.resolve(p["alias"], p["col"])
-            vals = f.column(a, p["col"])
+            vals = _eval_expr(f, p["expr"]) if p.get("expr") is not None else f.column(f.resolve(p["alias"], p["col"]), p["col"])
             if p["kind"] == "count_col":
                 present = np.array([v is not None for v in vals], dtype=bool) if vals.dtype == object else np.ones(len(vals), bool)
                 return np.asarray([int(present[v].sum()) for v in members], dtype=np.int64)
@@ -1274,6 +1391,21 @@ class Session:
                 keep = ~keep
             ix = f.idx[alias]
             f.take((ix >= 0) & keep[np.maximum(ix, 0)] if len(keep) else np.zeros(len(ix), bool))
+        elif w["kind"] == "compare_expr":                              # arithmetic on either side; a NULL operand drops the row
+            op = {"<>": "!=", "==": "="}.get(w["op"], w["op"])
+            if op not in _CMP:
+                raise UnsupportedQuery(f"comparison {op}")
+            a, b = _eval_expr(f, w["left"]), _eval_expr(f, w["right"])
+            if a.dtype == object or b.dtype == object:
+                py = {"<": lambda x, y: x < y, "<=": lambda x, y: x <= y, ">": lambda x, y: x > y, ">=": lambda x, y: x >= y,
+                      "=": lambda x, y: x == y, "!=": lambda x, y: x != y}[op]
+                try:
+                    keep = np.fromiter((x is not None and y is not None and py(x, y) for x, y in zip(a.tolist(), b.tolist())), dtype=bool, count=len(a))
+                except TypeError as exc:
+                    raise ValueError(f"cannot compare the operands of {op!r}: {exc}") from None
+            else:
+                keep = _CMP[op](a, b)
+            f.take(keep)
         elif w["kind"] == "in_list":                                   # col [NOT] IN (literals); a NULL operand drops the row either way
             col = f.column(f.resolve(*w["col"]), w["col"][1])
             values = set(w["values"])
@@ -1371,8 +1503,10 @@ class Session:
             # SELECT COUNT(*) [AS n] FROM <rows the FROM clause produced>: one row, also over an empty input
             cols = [p.get("name", "count") for p in proj]
             return self._order_limit(q, Result(cols, [np.asarray([len(f)], dtype=np.int64) for _ in proj]), f)
-        if kinds & {"count_star", "count_col"}:
-            raise UnsupportedQuery("COUNT mixed with other projections without GROUP BY is finished by the SQL engine")
+        if kinds and kinds <= {"count_star", "count_col", "agg"}:
+            return self._group_count(q, f)                                 # aggregates only, no GROUP BY: one group over all rows
+        if kinds & {"count_star", "count_col", "agg"}:
+            raise UnsupportedQuery("aggregates mixed with other projections without GROUP BY are finished by the SQL engine")
         cols: list[str] = []
         arrays: list[np.ndarray] = []
         sources: list = []
@@ -1390,6 +1524,10 @@ class Session:
                 cols.append(p.get("name", p["col"]))
                 arrays.append(f.column(a, p["col"]))
                 sources.append((a, p["col"]))
+            elif p["kind"] == "expr":
+                cols.append(p.get("name", "expr"))
+                arrays.append(_eval_expr(f, p["expr"]))
+                sources.append(None)
             elif p["kind"] == "const":
                 v = p["value"]
                 cols.append(p.get("name", str(v)))

@@ -116,11 +116,11 @@ def test_parse_shapes():
 
 
 @pytest.mark.parametrize("q", [
-    "SELECT a.name, SUM(b.start + 1) FROM peaks a JOIN genes b ON a.interval INTERSECTS b.interval GROUP BY a.name",
+    "SELECT a.name, STRING_AGG(b.name, ',') FROM peaks a JOIN genes b ON a.interval INTERSECTS b.interval GROUP BY a.name",
     "SELECT a.name, COUNT(*) FROM peaks a JOIN genes b ON a.interval INTERSECTS b.interval GROUP BY a.name HAVING COUNT(*) > a.name",
     "SELECT a.name, SUM(DISTINCT b.start) FROM peaks a JOIN genes b ON a.interval INTERSECTS b.interval GROUP BY a.name",
     "SELECT a.name, a.start, COUNT(*) FROM peaks a JOIN genes b ON a.interval INTERSECTS b.interval GROUP BY a.name",
-    "SELECT name FROM peaks WHERE start + 1 > 100",
+    "SELECT name, CASE WHEN start > 100 THEN 'far' ELSE 'near' END FROM peaks",
     "SELECT upper(name) FROM peaks",
     "SELECT a.name FROM peaks a JOIN genes b ON a.name = b.name",
     "SELECT a.name FROM peaks a SEMI JOIN genes b ON a.interval CONTAINS b.interval",
@@ -306,6 +306,32 @@ def test_group_by_aggregates_and_having_against_brute_force():
     assert len(rows) == 90 and all(rows[f"f{i}"] == ((sum(G["start"][j] for j in by[f"f{i}"]), len(by[f"f{i}"])) if f"f{i}" in by else (None, 0)) for i in range(90))
     with pytest.raises(ValueError):
         s.execute("SELECT a.name, SUM(b.name) FROM peaks a JOIN genes b ON a.interval INTERSECTS b.interval GROUP BY a.name")
+
+
+def test_arithmetic_in_projections_filters_and_aggregates():
+    s = sessions(OracleBackend())
+    P, G = make(11, 90), make(12, 60)
+    got = s.execute('SELECT name, "end" - start AS length, 2 * (start + 1) AS twice FROM peaks WHERE "end" - start >= 50 AND start + 1 > 100').rows
+    want = [(P["name"][i], P["end"][i] - P["start"][i], 2 * (P["start"][i] + 1)) for i in range(90)
+            if P["end"][i] - P["start"][i] >= 50 and P["start"][i] + 1 > 100]
+    assert got == want and want
+    # coverage per chromosome, as in the reference's clustering recipe (docs/recipes/clustering.rst)
+    got = s.execute('WITH merged AS (SELECT MERGE(interval) FROM peaks) SELECT chrom, COUNT(*) AS n, SUM("end" - start) AS bp FROM merged GROUP BY chrom').rows
+    regions = OracleBackend().merge(P)
+    want = {}
+    for c, a, b, _ in regions:
+        n, bp = want.get(c, (0, 0))
+        want[c] = (n + 1, bp + b - a)
+    assert {r[0]: tuple(r[1:]) for r in got} == want
+    # the overlap-fraction filter of the intersect recipe: overlap length against half of A's length
+    got = sorted(s.execute('SELECT a.name, b.name FROM peaks a, genes b WHERE a.interval INTERSECTS b.interval AND '
+                           '( LEAST(a."end", b."end") - GREATEST(a.start, b.start) ) >= 0.5 * (a."end" - a.start)').rows)
+    want = sorted((f"f{i}", f"f{j}") for i in range(90) for j in range(60) if overlap(P, i, G, j)
+                  and min(P["end"][i], G["end"][j]) - max(P["start"][i], G["start"][j]) >= 0.5 * (P["end"][i] - P["start"][i]))
+    assert got == want and want
+    assert s.execute("SELECT start -5 AS x, -start AS y, ABS(0 - start) AS z FROM peaks LIMIT 1").rows == [(P["start"][0] - 5, -P["start"][0], P["start"][0])]
+    with pytest.raises(ValueError):
+        s.execute("SELECT name + 1 FROM peaks")
 
 
 def test_spelled_out_overlap_predicate_is_the_interval_join():
