@@ -19,6 +19,7 @@ Recognised shapes (GIQL semantics cited per branch in :class:`Session`):
 * ``FROM a x JOIN b y ON x.chrom = y.chrom WHERE DISTANCE(x.interval, y.interval[, ...]) < n``; the plain cross join
   ``FROM a x, b y`` / ``a x CROSS JOIN b y`` feeding ``DISTANCE`` in the select list (bounded product)
 * ``SELECT ..., CLUSTER(interval[, d][, stranded := true]) AS c FROM t``; ``SELECT MERGE(interval[, d][, stranded := true])[, COUNT(*)] FROM t``
+* ``<select> UNION [ALL] | EXCEPT | INTERSECT <select>`` (also as a CTE or derived table feeding an operator)
 * ``FROM DISJOIN(t[, reference := r | (<query>)])``;  ``WITH name AS (SELECT * FROM t) ...``;  a derived table ``FROM (<query>) alias``
 * ``SELECT <left cols>, COUNT(*) | COUNT(y.col) FROM a x [LEFT] JOIN b y ON x.interval INTERSECTS y.interval GROUP BY <left cols>``
   (count_overlaps: one per-row count probe, no pair list); any other ``GROUP BY cols`` with ``COUNT / SUM / MIN / MAX / AVG /
@@ -45,6 +46,7 @@ from .table import Table, canonical_offsets
 
 
 _AGGREGATES = ("COUNT", "SUM", "MIN", "MAX", "AVG")
+_SET_OPS = ("UNION", "EXCEPT", "INTERSECT")
 _CROSS_JOIN_LIMIT = 1 << 24     # rows of `FROM a, b` without any join predicate the front-end will materialise
 
 
@@ -232,6 +234,18 @@ class _Parser:
                     break
         q = self.select()
         q["ctes"] = ctes
+        # <select> {UNION [ALL] | EXCEPT | INTERSECT <select>}: a trailing ORDER BY / LIMIT / OFFSET belongs to the whole set operation
+        while self.at("id") and self.peek()[1].upper() in _SET_OPS:
+            op = self.take("id").upper()
+            keep_all = self.accept("kw", "ALL")
+            if keep_all and op != "UNION":
+                raise UnsupportedQuery(f"{op} ALL is finished by the SQL engine")
+            right = self.select()
+            right["ctes"] = ctes
+            node = {"setop": op, "all": keep_all, "left": q, "right": right, "ctes": ctes,
+                    "order": right["order"], "limit": right["limit"], "offset": right.get("offset", 0)}
+            right["order"], right["limit"], right["offset"] = [], None, 0
+            q = node
         return q
 
     def select(self):
@@ -364,7 +378,7 @@ class _Parser:
     def alias(self):
         if self.accept("kw", "AS"):
             return self.take("id")
-        if self.at("id"):
+        if self.at("id") and self.peek()[1].upper() not in _SET_OPS + ("OFFSET", "HAVING"):
             return self.take("id")
         return None
 
@@ -1050,6 +1064,8 @@ class Session:
         return self.tables[name]
 
     def _run(self, q) -> Result:
+        if "setop" in q:
+            return self._set_operation(q)
         be = self.backend
         src = q["source"]
         f = _Frame()
@@ -1176,6 +1192,23 @@ class Session:
         for w in where:
             self._filter(f, w)
         return self._finish(q, f)
+
+    def _set_operation(self, q) -> Result:
+        """UNION [ALL] / EXCEPT / INTERSECT of two results (bag for UNION ALL, sets otherwise, as in SQL); names come from the left."""
+        a, b = self._run(q["left"]), self._run(q["right"])
+        if len(a.columns) != len(b.columns):
+            raise ValueError(f"{q['setop']}: the two queries return {len(a.columns)} and {len(b.columns)} columns")
+        ra, rb = a.rows, b.rows
+        if q["setop"] == "UNION":
+            rows = ra + rb if q["all"] else list(dict.fromkeys(ra + rb))
+        elif q["setop"] == "EXCEPT":
+            gone = set(rb)
+            rows = [r for r in dict.fromkeys(ra) if r not in gone]
+        else:
+            both = set(rb)
+            rows = [r for r in dict.fromkeys(ra) if r in both]
+        res = Result(list(a.columns), [_column([r[i] for r in rows]) for i in range(len(a.columns))])
+        return self._order_limit(q, res, None)
 
     @staticmethod
     def _literal_overlap_join(f: _Frame, right: _Rel, ra: str, compares):

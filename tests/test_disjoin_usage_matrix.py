@@ -59,7 +59,7 @@ def test_every_executed_pattern_reproduces_the_duckdb_snapshot_oracle_backend():
     outcome, wrong = _sweep(OracleBackend())
     assert not wrong, wrong[:5]
     ok = sum(v for k, v in outcome.items() if k.startswith("ok:"))
-    assert ok >= 600, dict(outcome)
+    assert ok >= 660, dict(outcome)
     # the plain table-function shapes are never declined, in any profile or mode
     for pattern in ("STANDALONE", "ALIASED_PROJECTION"):
         assert outcome["ok:" + pattern] == 30, (pattern, dict(outcome))

@@ -334,6 +334,25 @@ def test_arithmetic_in_projections_filters_and_aggregates():
         s.execute("SELECT name + 1 FROM peaks")
 
 
+def test_set_operations():
+    s = sessions(OracleBackend())
+    P, G = make(11, 90), make(12, 60)
+    rows = s.execute("SELECT chrom AS c FROM peaks UNION ALL SELECT chrom AS c FROM genes ORDER BY c").rows
+    assert rows == sorted((c,) for c in P["chrom"] + G["chrom"])
+    assert sorted(s.execute("SELECT chrom FROM peaks UNION SELECT chrom FROM genes").rows) == sorted({(c,) for c in P["chrom"] + G["chrom"]})
+    semi = {r[0] for r in s.execute("SELECT a.name FROM peaks a SEMI JOIN genes b ON a.interval INTERSECTS b.interval").rows}
+    anti = s.execute("SELECT name FROM peaks EXCEPT SELECT a.name FROM peaks a SEMI JOIN genes b ON a.interval INTERSECTS b.interval").rows
+    assert sorted(r[0] for r in anti) == sorted(set(P["name"]) - semi)
+    both = s.execute("SELECT name FROM peaks INTERSECT SELECT a.name FROM peaks a SEMI JOIN genes b ON a.interval INTERSECTS b.interval").rows
+    assert sorted(r[0] for r in both) == sorted(semi)
+    # a set operation as a CTE feeds the operators like any table (docs/recipes/intersect.rst: several B files)
+    merged = s.execute('WITH u AS (SELECT chrom, start, "end" FROM peaks UNION ALL SELECT chrom, start, "end" FROM genes) SELECT MERGE(interval) FROM u').rows
+    both_tables = {k: P[k] + G[k] for k in ("chrom", "start", "end")}
+    assert merged == sorted((c, a, b) for c, a, b, _ in OracleBackend().merge(both_tables))
+    with pytest.raises(ValueError):
+        s.execute("SELECT chrom FROM peaks UNION SELECT chrom, start FROM genes")
+
+
 def test_spelled_out_overlap_predicate_is_the_interval_join():
     s = sessions(OracleBackend())
     P, G = make(11, 90), make(12, 60)
