@@ -581,6 +581,22 @@ class _Parser:
                     raise ValueError("predicate := must be a comparison")
             elif fn in _AGGREGATES:
                 item = self.aggregate_args(fn)
+                if self.at("id") and self.peek()[1].upper() == "OVER":
+                    # <aggregate> OVER (PARTITION BY cols): the group's value on every row of the group; an ORDER BY inside the
+                    # window (running aggregates) is the SQL engine's business
+                    self.take("id")
+                    self.take("op", "(")
+                    part = []
+                    if self.at("id") and self.peek()[1].upper() == "PARTITION":
+                        self.take("id")
+                        self.take("kw", "BY")
+                        part.append(self.column_ref())
+                        while self.accept("op", ","):
+                            part.append(self.column_ref())
+                    if not self.at("op", ")"):
+                        raise UnsupportedQuery("a window with ORDER BY / a frame is finished by the SQL engine")
+                    self.take("op", ")")
+                    item = {"kind": "window", "agg": item, "partition": part}
             else:
                 raise UnsupportedQuery(f"function {fn} is not handled by the built-in front-end")
         else:
@@ -990,6 +1006,37 @@ def _arith(op: str, a: np.ndarray, b: np.ndarray) -> np.ndarray:
         raise ValueError(f"arithmetic needs numeric operands: {exc}") from None
 
 
+def _aggregate(f: "_Frame", p, members) -> np.ndarray:
+    """one value per group of frame rows (``members``: row-index arrays) for a COUNT / SUM / MIN / MAX / AVG item"""
+    if p["kind"] == "count_star":
+        return np.asarray([len(v) for v in members], dtype=np.int64)
+    vals = _eval_expr(f, p["expr"]) if p.get("expr") is not None else f.column(f.resolve(p["alias"], p["col"]), p["col"])
+    if p["kind"] == "count_col":
+        present = np.array([v is not None for v in vals], dtype=bool) if vals.dtype == object else np.ones(len(vals), bool)
+        return np.asarray([int(present[v].sum()) for v in members], dtype=np.int64)
+    if p["fn"] in ("SUM", "AVG") and vals.dtype.kind not in "iufb" and any(isinstance(x, str) for x in vals.tolist()):
+        raise ValueError(f"{p['fn']} needs a numeric column, {p['col']!r} holds strings")
+    out = []
+    for v in members:                                         # NULLs are skipped; no value at all -> NULL (COUNT: 0)
+        xs = [x for x in vals[v].tolist() if x is not None]
+        fn = p["fn"]
+        if fn == "COUNT_DISTINCT":
+            out.append(len(set(xs)))
+        elif not xs:
+            out.append(None)
+        elif fn == "SUM":
+            out.append(sum(xs))
+        elif fn == "MIN":
+            out.append(min(xs))
+        elif fn == "MAX":
+            out.append(max(xs))
+        else:
+            out.append(sum(xs) / len(xs))                     # AVG is a DOUBLE
+    if p["fn"] == "AVG" and all(x is not None for x in out):
+        return np.asarray(out, dtype=np.float64)
+    return _column(out)
+
+
 class Session:
     """Registered tables + ``execute(giql_query)``.  ``backend`` defaults to the CUDA engine on device 0."""
 
@@ -1318,34 +1365,7 @@ class Session:
             groups[()] = list(range(len(f)))                               # the global aggregate: one row, also over no rows
         members = [np.asarray(v, dtype=np.int64) for v in groups.values()]
 
-        def aggregate(p) -> np.ndarray:
-            if p["kind"] == "count_star":
-                return np.asarray([len(v) for v in members], dtype=np.int64)
-            vals = _eval_expr(f, p["expr"]) if p.get("expr") is not None else f.column(f.resolve(p["alias"], p["col"]), p["col"])
-            if p["kind"] == "count_col":
-                present = np.array([v is not None for v in vals], dtype=bool) if vals.dtype == object else np.ones(len(vals), bool)
-                return np.asarray([int(present[v].sum()) for v in members], dtype=np.int64)
-            if p["fn"] in ("SUM", "AVG") and vals.dtype.kind not in "iufb" and any(isinstance(x, str) for x in vals.tolist()):
-                raise ValueError(f"{p['fn']} needs a numeric column, {p['col']!r} holds strings")
-            out = []
-            for v in members:                                         # NULLs are skipped; no value at all -> NULL (COUNT: 0)
-                xs = [x for x in vals[v].tolist() if x is not None]
-                fn = p["fn"]
-                if fn == "COUNT_DISTINCT":
-                    out.append(len(set(xs)))
-                elif not xs:
-                    out.append(None)
-                elif fn == "SUM":
-                    out.append(sum(xs))
-                elif fn == "MIN":
-                    out.append(min(xs))
-                elif fn == "MAX":
-                    out.append(max(xs))
-                else:
-                    out.append(sum(xs) / len(xs))                     # AVG is a DOUBLE
-            if p["fn"] == "AVG" and all(x is not None for x in out):
-                return np.asarray(out, dtype=np.float64)
-            return _column(out)
+        aggregate = lambda p: _aggregate(f, p, members)
 
         out_cols, arrays, sources = [], [], []
         for p in q["proj"]:
@@ -1557,6 +1577,22 @@ class Session:
                 cols.append(p.get("name", p["col"]))
                 arrays.append(f.column(a, p["col"]))
                 sources.append((a, p["col"]))
+            elif p["kind"] == "window":
+                part = [f.column(f.resolve(a, c), c).tolist() for a, c in p["partition"]]
+                groups: dict[tuple, list[int]] = {}
+                for i, key in enumerate(zip(*part)) if part else []:
+                    groups.setdefault(key, []).append(i)
+                if not part:
+                    groups[()] = list(range(len(f)))
+                members = [np.asarray(v, dtype=np.int64) for v in groups.values()]
+                per_group = _aggregate(f, p["agg"], members)
+                out = np.empty(len(f), dtype=per_group.dtype)
+                for g, v in enumerate(members):
+                    out[v] = per_group[g]
+                default = "count" if p["agg"]["kind"] != "agg" else p["agg"]["fn"].lower()
+                cols.append(p.get("name", default))
+                arrays.append(out)
+                sources.append(None)
             elif p["kind"] == "expr":
                 cols.append(p.get("name", "expr"))
                 arrays.append(_eval_expr(f, p["expr"]))
