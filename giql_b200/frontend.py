@@ -292,20 +292,20 @@ class _Parser:
                 q["group"].append(self.column_ref())
                 if not self.accept("op", ","):
                     break
-            q["having"] = []
-            if self.at("id") and self.peek()[1].upper() == "HAVING":
-                # HAVING <aggregate> <op> <number> [AND ...]: a filter over the groups
-                self.take("id")
-                while True:
-                    if not (self.at("id") and self.peek()[1].upper() in _AGGREGATES and self.at("op", "(", 1)):
-                        raise UnsupportedQuery("HAVING compares aggregates with numbers; anything else is finished by the SQL engine")
-                    item = self.aggregate_args(self.take("id").upper())
-                    op = self.take("op")
-                    if not self.at("num"):
-                        raise UnsupportedQuery("HAVING compares aggregates with numbers; anything else is finished by the SQL engine")
-                    q["having"].append({"item": item, "op": op, "value": self.take("num")})
-                    if not self.accept("kw", "AND"):
-                        break
+        q["having"] = []
+        if self.at("id") and self.peek()[1].upper() == "HAVING":
+            # HAVING <aggregate> <op> <number> [AND ...]: a filter over the groups
+            self.take("id")
+            while True:
+                if not (self.at("id") and self.peek()[1].upper() in _AGGREGATES and self.at("op", "(", 1)):
+                    raise UnsupportedQuery("HAVING compares aggregates with numbers; anything else is finished by the SQL engine")
+                item = self.aggregate_args(self.take("id").upper())
+                op = self.take("op")
+                if not self.at("num"):
+                    raise UnsupportedQuery("HAVING compares aggregates with numbers; anything else is finished by the SQL engine")
+                q["having"].append({"item": item, "op": op, "value": self.take("num")})
+                if not self.accept("kw", "AND"):
+                    break
         if self.accept("kw", "ORDER"):
             self.take("kw", "BY")
             while True:
@@ -1169,6 +1169,13 @@ class Session:
                     (w["kind"] == "compare" and {w["left"][0], w["right"][0]} == {la, ra})
                 conds, kind = [w for w in where if between(w)], "inner"
                 where = [w for w in where if not between(w)]
+            single_side = [c for c in conds if c["kind"] in ("compare_literal", "between", "in_list", "is_null", "compare_expr")]
+            if single_side and kind == "inner":
+                # `ON a.interval INTERSECTS b.interval AND a.score > 10`: on an INNER join a conjunct over one row (or an expression
+                # of the joined row) filters the joined rows exactly like WHERE does (intersects_duckdb.py:1239-1243 keeps such
+                # residuals inside every per-chromosome branch); outer / SEMI / ANTI joins change meaning and stay declined
+                where = where + single_side
+                conds = [c for c in conds if c not in single_side]
             spatial = [c for c in conds if c["kind"] == "spatial"]
             compares = [c for c in conds if c["kind"] == "compare"]
             if len(spatial) + len(compares) != len(conds) or len(spatial) > 1:
@@ -1543,6 +1550,10 @@ class Session:
             else:
                 rows = be.merge(g, m["distance"], m["stranded"]) if len(f) else []
             width = 4 if m["stranded"] else 3
+            for h in q.get("having") or []:                                 # HAVING COUNT(*) <op> n over the merged regions
+                if h["item"]["kind"] != "count_star" or h["op"] not in _CMP:
+                    raise UnsupportedQuery("HAVING over MERGE is bound for COUNT(*) comparisons")
+                rows = [r for r in rows if bool(_CMP[h["op"]](r[-1], h["value"]))]
             out = [tuple(r[:width]) + ((r[-1],) if "count_star" in kinds else ()) for r in rows]
             out.sort(key=lambda r: (r[0], r[width - 2]))
             # the regions carry the table's own column names (merge.py:302-307: MIN(start) AS <start_col>, MAX(end) AS <end_col>)
@@ -1560,6 +1571,8 @@ class Session:
             return self._group_count(q, f)                                 # aggregates only, no GROUP BY: one group over all rows
         if kinds & {"count_star", "count_col", "agg"}:
             raise UnsupportedQuery("aggregates mixed with other projections without GROUP BY are finished by the SQL engine")
+        if q.get("having"):
+            raise UnsupportedQuery("HAVING without aggregates in the select list is finished by the SQL engine")
         cols: list[str] = []
         arrays: list[np.ndarray] = []
         sources: list = []

@@ -63,7 +63,7 @@ def _check(backend, only=None):
 def test_golden_file_holds_only_verified_or_declined_tests():
     outcomes = {t["outcome"].split(":")[0] for t in DOC["tests"]}
     assert outcomes <= {"verified", "declined", "not_replayable"}, outcomes
-    assert len(VERIFIED) >= 370 and len(CALLS) >= len(VERIFIED)
+    assert len(VERIFIED) >= 371 and len(CALLS) >= len(VERIFIED)
     # every replayed module contributes
     for part in ("cluster_predicate", "test_distance_coordinate_space", "test_nearest_coordinate_space",
                  "test_disjoin_coordinate_space", "test_contains", "test_within", "test_duckdb_iejoin", "test_intersects_join",
