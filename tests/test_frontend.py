@@ -520,3 +520,30 @@ def test_qualified_order_by_over_duplicate_output_names(oracle_session=None):
     # an unqualified key naming one output column keeps working, DESC on unsigned-like keys does not wrap
     got = s.execute("SELECT a.start AS s, b.start FROM a JOIN b ON a.interval INTERSECTS b.interval ORDER BY s DESC LIMIT 3").rows
     assert [r[0] for r in got] == [30, 30, 30]
+
+
+@pytest.mark.skipif(not __import__("pathlib").Path("/root/reference/docs/dialect").is_dir(), reason="reference tree not mounted")
+def test_documented_examples_parse():
+    """Every ``.. code-block:: sql`` statement of the reference's dialect pages, recipes and quickstart: at least 150 of the 178
+    are accepted by the built-in parser (the rest: CASE, STRING_AGG / ROUND / RANK, ordered windows, placeholders like
+    ``MERGE(interval, distance)``); a regression net for the grammar, not a semantic check."""
+    import glob
+    import re
+
+    files = glob.glob("/root/reference/docs/dialect/*.rst") + glob.glob("/root/reference/docs/recipes/*.rst") + ["/root/reference/docs/quickstart.rst"]
+    total = accepted = 0
+    for path in files:
+        for m in re.finditer(r"\.\. code-block:: sql\n\n((?:[ \t]+.*\n|\n)+)", open(path).read()):
+            block = "\n".join(line[3:] if line.startswith("   ") else line for line in m.group(1).split("\n"))
+            for stmt in re.split(r";\s*\n|\n\s*\n", block):
+                body = " ".join(line for line in stmt.strip().split("\n") if not line.strip().startswith("--")).strip()
+                if not body.upper().startswith(("SELECT", "WITH")):
+                    continue
+                total += 1
+                try:
+                    parse(stmt.strip())
+                    accepted += 1
+                except (UnsupportedQuery, ValueError):
+                    pass
+    assert total >= 170 and accepted >= 150, (total, accepted)
+
