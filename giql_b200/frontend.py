@@ -18,7 +18,7 @@ Recognised shapes (GIQL semantics cited per branch in :class:`Session`):
   the standalone placement ``FROM NEAREST(b, reference := 'chr1:350-360'[, k, max_distance, signed]) [y]``
 * ``FROM a x JOIN b y ON x.chrom = y.chrom WHERE DISTANCE(x.interval, y.interval[, ...]) < n``; the plain cross join
   ``FROM a x, b y`` / ``a x CROSS JOIN b y`` feeding ``DISTANCE`` in the select list (bounded product)
-* ``SELECT ..., CLUSTER(interval[, d][, stranded := true]) AS c FROM t``; ``SELECT MERGE(interval[, d][, stranded := true])[, COUNT(*)] FROM t``
+* ``SELECT ..., CLUSTER(interval[, d][, stranded := true]) AS c FROM t``; ``SELECT MERGE(interval[, d][, stranded := true])[, COUNT(*) | SUM | MIN | MAX | AVG(col) ...] FROM t [HAVING COUNT(*) ...]``
 * ``<select> UNION [ALL] | EXCEPT | INTERSECT <select>`` (also as a CTE or derived table feeding an operator)
 * ``FROM DISJOIN(t[, reference := r | (<query>)])``;  ``WITH name AS (SELECT * FROM t) ...``;  a derived table ``FROM (<query>) alias``
 * ``SELECT <left cols>, COUNT(*) | COUNT(y.col) FROM a x [LEFT] JOIN b y ON x.interval INTERSECTS y.interval GROUP BY <left cols>``
@@ -1534,32 +1534,41 @@ class Session:
             cfg = f.rels[f.order[0]].config or Table("t")
             keys = {cfg.chrom_col.lower()} | ({cfg.strand_col.lower()} if m["stranded"] and cfg.strand_col else set())
             is_key = lambda p: p["kind"] == "col" and p["col"].lower() in keys and p.get("name", p["col"]).lower() == p["col"].lower()
-            if any(p["kind"] not in ("merge", "count_star") and not is_key(p) for p in proj) or q["distinct"] or \
+            user_aggs = [p for p in proj if p["kind"] in ("count_col", "agg")]
+            if any(p["kind"] not in ("merge", "count_star", "count_col", "agg") and not is_key(p) for p in proj) or q["distinct"] or \
                     any(c.lower() not in keys for _, c in q.get("group") or []):
-                raise UnsupportedQuery("MERGE is bound for `SELECT [chrom, [strand,]] MERGE(interval...)[, COUNT(*)] FROM t [GROUP BY chrom[, strand]]`")
-            if m.get("predicate") and len(f):
-                # merge.py:201-239: MERGE is GROUP BY chrom[, strand], cluster id over the predicate-gated CLUSTER; the ids come
-                # from the engine, the (small) aggregation is finished here
+                raise UnsupportedQuery("MERGE is bound for `SELECT [chrom, [strand,]] MERGE(interval...)[, <aggregates>] FROM t [GROUP BY chrom[, strand]]`")
+            width = 4 if m["stranded"] else 3
+            members: list[np.ndarray] = []
+            if (m.get("predicate") or user_aggs) and len(f):
+                # merge.py:201-239: MERGE is GROUP BY chrom[, strand], cluster id over the (predicate-gated) CLUSTER.  With a
+                # predicate, or with user aggregates beside MERGE (`MERGE(interval), AVG(score)`, merge.py:320-439), the cluster ids
+                # come from the engine and the small per-region aggregation is finished here
                 ids = _cluster_ids(be, f, m)
                 agg: dict[tuple, list] = {}
                 strands = g["strand"].tolist() if m["stranded"] else [None] * len(ids)
-                for c, st, cid, s0, e0 in zip(g["chrom"].tolist(), strands, ids.tolist(), g["start"].tolist(), g["end"].tolist()):
-                    a = agg.setdefault((c, st, cid), [s0, e0, 0])
+                for i_row, (c, st, cid, s0, e0) in enumerate(zip(g["chrom"].tolist(), strands, ids.tolist(), g["start"].tolist(), g["end"].tolist())):
+                    a = agg.setdefault((c, st, cid), [s0, e0, 0, []])
                     a[0], a[1], a[2] = min(a[0], s0), max(a[1], e0), a[2] + 1
+                    a[3].append(i_row)
                 rows = [((c, st, v[0], v[1], v[2]) if m["stranded"] else (c, v[0], v[1], v[2])) for (c, st, _), v in agg.items()]
+                members = [np.asarray(v[3], dtype=np.int64) for v in agg.values()]
             else:
                 rows = be.merge(g, m["distance"], m["stranded"]) if len(f) else []
-            width = 4 if m["stranded"] else 3
+            extra = [_aggregate(f, p, members).tolist() if members else [] for p in user_aggs]      # one list per aggregate, region-aligned
+            rows = [tuple(r) + tuple(col[k] for col in extra) for k, r in enumerate(rows)]
+            n_fixed = width + 1                                             # chrom[, strand], start, end, row count
             for h in q.get("having") or []:                                 # HAVING COUNT(*) <op> n over the merged regions
                 if h["item"]["kind"] != "count_star" or h["op"] not in _CMP:
                     raise UnsupportedQuery("HAVING over MERGE is bound for COUNT(*) comparisons")
-                rows = [r for r in rows if bool(_CMP[h["op"]](r[-1], h["value"]))]
-            out = [tuple(r[:width]) + ((r[-1],) if "count_star" in kinds else ()) for r in rows]
+                rows = [r for r in rows if bool(_CMP[h["op"]](r[width], h["value"]))]
+            out = [tuple(r[:width]) + ((r[width],) if "count_star" in kinds else ()) + tuple(r[n_fixed:]) for r in rows]
             out.sort(key=lambda r: (r[0], r[width - 2]))
             # the regions carry the table's own column names (merge.py:302-307: MIN(start) AS <start_col>, MAX(end) AS <end_col>)
             count_name = next((p.get("name", "count") for p in proj if p["kind"] == "count_star"), None)
             cols = [cfg.chrom_col] + ([cfg.strand_col] if m["stranded"] else []) + [cfg.start_col, cfg.end_col] + \
-                   ([count_name] if count_name is not None else [])
+                   ([count_name] if count_name is not None else []) + \
+                   [p.get("name", "count" if p["kind"] == "count_col" else p["fn"].lower()) for p in user_aggs]
             return self._order_limit(q, Result(cols, [_column([r[i] for r in out]) for i in range(len(cols))]), f)
         if q.get("group"):
             return self._group_count(q, f)

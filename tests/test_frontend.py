@@ -334,6 +334,30 @@ def test_arithmetic_in_projections_filters_and_aggregates():
         s.execute("SELECT name + 1 FROM peaks")
 
 
+def test_user_aggregates_beside_merge():
+    """`SELECT MERGE(interval), COUNT(*), AVG(col) ...` (docs/dialect/aggregation-operators.rst; merge.py:320-439): per merged
+    region, the aggregate over the rows that were merged into it"""
+    s = sessions(OracleBackend())
+    P = make(11, 90)
+    P["score"] = [None if i % 7 == 0 else i for i in range(90)]
+    s.register("scored", P)
+    got = s.execute('SELECT MERGE(interval, 10), COUNT(*) AS n, SUM(score) AS total, MIN(start) AS lo, COUNT(score) AS known, '
+                    'SUM("end" - start) AS bp FROM scored')
+    assert got.columns == ["chrom", "start", "end", "n", "total", "lo", "known", "bp"]
+    regions = sorted(OracleBackend().merge({k: P[k] for k in ("chrom", "start", "end")}, 10))
+    want = []
+    for c, a, b, n in regions:
+        rows = [i for i in range(90) if P["chrom"][i] == c and a <= P["start"][i] and P["end"][i] <= b]
+        assert len(rows) == n
+        known = [P["score"][i] for i in rows if P["score"][i] is not None]
+        want.append((c, a, b, n, sum(known) if known else None, min(P["start"][i] for i in rows), len(known),
+                     sum(P["end"][i] - P["start"][i] for i in rows)))
+    assert got.rows == want
+    # HAVING COUNT(*) filters the regions; the plain MERGE is unchanged by the extra machinery
+    assert s.execute("SELECT MERGE(interval, 10), COUNT(*) AS n FROM scored HAVING COUNT(*) >= 3").rows == [r[:4] for r in want if r[3] >= 3]
+    assert s.execute("SELECT MERGE(interval, 10) FROM scored").rows == [r[:3] for r in want]
+
+
 def test_set_operations():
     s = sessions(OracleBackend())
     P, G = make(11, 90), make(12, 60)
