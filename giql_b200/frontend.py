@@ -45,7 +45,7 @@ from .ranges import parse_range
 from .table import Table, canonical_offsets
 
 
-_AGGREGATES = ("COUNT", "SUM", "MIN", "MAX", "AVG")
+_AGGREGATES = ("COUNT", "SUM", "MIN", "MAX", "AVG", "STRING_AGG")
 _SET_OPS = ("UNION", "EXCEPT", "INTERSECT")
 _CROSS_JOIN_LIMIT = 1 << 24     # rows of `FROM a, b` without any join predicate the front-end will materialise
 
@@ -534,7 +534,12 @@ class _Parser:
         else:
             distinct = self.accept("kw", "DISTINCT")
             e = self.expr()
-            if e[0] != "col":                                             # SUM(end - start)
+            if fn == "STRING_AGG":                                        # STRING_AGG(col, 'sep'): the names merged into a region
+                if e[0] != "col" or distinct:
+                    raise UnsupportedQuery("STRING_AGG takes a column and a separator")
+                self.take("op", ",")
+                item = {"kind": "agg", "fn": "STRING_AGG", "alias": e[1], "col": e[2], "sep": self.take("str")}
+            elif e[0] != "col":                                           # SUM(end - start)
                 if distinct or fn == "COUNT":
                     raise UnsupportedQuery(f"{fn}({'DISTINCT ' if distinct else ''}<expression>) is finished by the SQL engine")
                 item = {"kind": "agg", "fn": fn, "alias": None, "col": "<expression>", "expr": e}
@@ -1022,6 +1027,8 @@ def _aggregate(f: "_Frame", p, members) -> np.ndarray:
         fn = p["fn"]
         if fn == "COUNT_DISTINCT":
             out.append(len(set(xs)))
+        elif fn == "STRING_AGG":
+            out.append(p["sep"].join(str(x) for x in xs) if xs else None)
         elif not xs:
             out.append(None)
         elif fn == "SUM":

@@ -116,7 +116,7 @@ def test_parse_shapes():
 
 
 @pytest.mark.parametrize("q", [
-    "SELECT a.name, STRING_AGG(b.name, ',') FROM peaks a JOIN genes b ON a.interval INTERSECTS b.interval GROUP BY a.name",
+    "SELECT a.name, UPPER(b.name) FROM peaks a JOIN genes b ON a.interval INTERSECTS b.interval",
     "SELECT a.name, COUNT(*) FROM peaks a JOIN genes b ON a.interval INTERSECTS b.interval GROUP BY a.name HAVING COUNT(*) > a.name",
     "SELECT a.name, SUM(DISTINCT b.start) FROM peaks a JOIN genes b ON a.interval INTERSECTS b.interval GROUP BY a.name",
     "SELECT a.name, a.start, COUNT(*) FROM peaks a JOIN genes b ON a.interval INTERSECTS b.interval GROUP BY a.name",
@@ -356,6 +356,9 @@ def test_user_aggregates_beside_merge():
     # HAVING COUNT(*) filters the regions; the plain MERGE is unchanged by the extra machinery
     assert s.execute("SELECT MERGE(interval, 10), COUNT(*) AS n FROM scored HAVING COUNT(*) >= 3").rows == [r[:4] for r in want if r[3] >= 3]
     assert s.execute("SELECT MERGE(interval, 10) FROM scored").rows == [r[:3] for r in want]
+    names = s.execute("SELECT MERGE(interval, 10), STRING_AGG(name, ',') AS members FROM scored").rows
+    assert [sorted(r[3].split(",")) for r in names] == [sorted(P["name"][i] for i in range(90) if P["chrom"][i] == c and a <= P["start"][i] and P["end"][i] <= b)
+                                                        for c, a, b, *_ in want]
 
 
 def test_set_operations():
